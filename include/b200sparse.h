@@ -1,0 +1,158 @@
+/*
+ * b200sparse.h -- C ABI of libb200sparse: B200 (sm_100a) SpMV / SpMM / SpGEMM
+ * for CrsMatrix data, the drop-in behind Kokkos Kernels' TPL slot for
+ * Kokkos::Cuda.
+ *
+ * Conventions
+ *  - plain C, opaque plans, caller-owned DEVICE pointers, explicit stream
+ *    (a cudaStream_t passed as void*), 0-based int32 row offsets ("Offset")
+ *    and column indices ("Ordinal") -- Kokkos Kernels' default_types
+ *    (reference common/src/KokkosKernels_default_types.hpp:41-58) and the
+ *    only combination its cuSPARSE SpMM/SpGEMM specialisations accept
+ *    (sparse/tpls/KokkosSparse_spgemm_symbolic_tpl_spec_avail.hpp:36-40).
+ *  - every entry point returns a b200sp_status; on failure
+ *    b200sp_last_error_string() describes it (thread-local).  The Kokkos shim
+ *    turns non-zero into std::runtime_error / std::invalid_argument like
+ *    KOKKOSSPARSE_IMPL_CUSPARSE_SAFE_CALL does
+ *    (sparse/src/KokkosSparse_Utils_cusparse.hpp:28-67).
+ *  - SpMV/SpMM are asynchronous on `stream`: no host synchronisation, no
+ *    device->host reads (reference contract: spmv never fences,
+ *    sparse/unit_test/Test_Sparse_spmv.hpp:193-194).  SpGEMM symbolic is
+ *    synchronous by nature (the caller needs c_nnz to allocate C).
+ *  - A plan belongs to ONE matrix (same rule as SPMVHandle,
+ *    sparse/src/KokkosSparse_spmv_handle.hpp:276-277) and is not thread-safe;
+ *    distinct plans on distinct streams may run concurrently.
+ */
+#ifndef B200SPARSE_H_
+#define B200SPARSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200SP_OK = 0,
+  B200SP_ERR_INVALID_ARGUMENT = 1, /* bad mode / negative size / null pointer    */
+  B200SP_ERR_CUDA = 2,             /* a CUDA runtime call failed                  */
+  B200SP_ERR_STATE = 3,            /* numeric before symbolic, plan/matrix mismatch */
+  B200SP_ERR_OVERFLOW = 4,         /* nnz(C) does not fit int32 offsets           */
+  B200SP_ERR_ALLOC = 5
+} b200sp_status;
+
+/* Mirrors KokkosSparse::SPMVAlgorithm for the values that reach a TPL
+ * (sparse/src/KokkosSparse_spmv_handle.hpp:32-47,76-86); SPMV_NATIVE* never
+ * get here. */
+typedef enum {
+  B200SP_SPMV_DEFAULT = 0,    /* SPMV_DEFAULT: analyse once, TMA-tiled kernel        */
+  B200SP_SPMV_FAST_SETUP = 1, /* SPMV_FAST_SETUP: no analysis, row-vector kernel     */
+  B200SP_SPMV_MERGE_PATH = 2  /* SPMV_MERGE_PATH: imbalance-proof nnz-split kernel    */
+} b200sp_spmv_algo;
+
+typedef struct b200sp_spmv_plan b200sp_spmv_plan;     /* lives in SPMVHandle::tpl_rank1 / tpl_rank2 */
+typedef struct b200sp_spgemm_plan b200sp_spgemm_plan; /* lives in SPGEMMHandle (like cuSparseSpgemmHandleType,
+                                                         sparse/src/KokkosSparse_spgemm_handle.hpp:161-198) */
+
+const char* b200sp_last_error_string(void);
+int b200sp_version(void);
+/* 1 when a CUDA device of compute capability 10.x is current, else 0. */
+int b200sp_device_ok(void);
+
+/* ---- SpMV plan ---------------------------------------------------------- */
+/* Replaces CuSparse10_SpMV_Data creation
+ * (sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:107-133).  The analysis
+ * itself happens lazily, stream-ordered, on the first spmv call. */
+int b200sp_spmv_plan_create(b200sp_spmv_plan** plan, int algo);
+/* Frees device state with cudaFreeAsync on `stream` (safe without a user
+ * fence, like TPL_SpMV_Data's destructor, spmv_handle.hpp:116-128). */
+int b200sp_spmv_plan_destroy(b200sp_spmv_plan* plan, void* stream);
+
+/* ---- SpMV rank-1: y = beta*y + alpha*op(A)*x ---------------------------- */
+/* Replaces SPMV<Kokkos::Cuda,...,true>::spmv -> spmv_cusparse
+ * (sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:31-225) and, without the
+ * cuSPARSE guards of sparse/src/KokkosSparse_spmv.hpp:230-241, accepts all four
+ * modes: 'N','C' (== N for real scalars), 'T','H' (== T).  m x n is A's shape;
+ * x has n (N/C) or m (T/H) entries, y the other.  beta == 0 never reads y
+ * (NaN in y is overwritten, Test_Sparse_spmv.hpp:394-408).  alpha == 0 or an
+ * empty A reduces to y = beta*y (KokkosSparse_spmv.hpp:145-154).
+ * plan may be NULL (row-vector kernel, nothing cached). */
+int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz,
+                        double alpha, const int* row_ptr, const int* col_idx, const double* vals,
+                        const double* x, double beta, double* y);
+int b200sp_spmv_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz,
+                        float alpha, const int* row_ptr, const int* col_idx, const float* vals,
+                        const float* x, float beta, float* y);
+
+/* Same call with HOST x / y (pinned or pageable): x is copied to the device,
+ * y (when beta != 0) too, the kernel runs, y is copied back; all on `stream`.
+ * The matrix arrays stay device-resident.  Requires a plan (owns the device
+ * staging vectors).  This is the end-to-end path bench.py times as `e2e`. */
+int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n,
+                                int64_t nnz, double alpha, const int* row_ptr, const int* col_idx,
+                                const double* vals, const double* x_host, double beta,
+                                double* y_host);
+
+/* ---- SpMV rank-2 (multivector): Y = beta*Y + alpha*op(A)*X, k columns --- */
+/* Replaces SPMV_MV<Kokkos::Cuda,...,false,true>::spmv_mv -> cusparseSpMM
+ * (sparse/tpls/KokkosSparse_spmv_mv_tpl_spec_decl.hpp:97-225).
+ * X(i,j) = X[i*ldx + j] when x_row_major (Kokkos::LayoutRight) else
+ * X[i + j*ldx] (LayoutLeft); same for Y.  Any mix of layouts is accepted. */
+int b200sp_spmm_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz,
+                        int k, double alpha, const int* row_ptr, const int* col_idx,
+                        const double* vals, const double* X, int64_t ldx, int x_row_major,
+                        double beta, double* Y, int64_t ldy, int y_row_major);
+int b200sp_spmm_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz,
+                        int k, float alpha, const int* row_ptr, const int* col_idx,
+                        const float* vals, const float* X, int64_t ldx, int x_row_major,
+                        float beta, float* Y, int64_t ldy, int y_row_major);
+
+/* ---- SpGEMM: C = A*B, A is m x n, B is n x k ---------------------------- */
+int b200sp_spgemm_plan_create(b200sp_spgemm_plan** plan);
+int b200sp_spgemm_plan_destroy(b200sp_spgemm_plan* plan, void* stream);
+
+/* Replaces SPGEMM_SYMBOLIC<...,true,*>::spgemm_symbolic -> spgemm_symbolic_cusparse
+ * (sparse/tpls/KokkosSparse_spgemm_symbolic_tpl_spec_decl.hpp:51-167,316-363).
+ * Always writes all m+1 entries of row_ptr_C (it arrives uninitialised,
+ * sparse/src/KokkosSparse_spgemm.hpp:47), returns nnz(C) and the longest C row
+ * (SPGEMMHandle::set_c_nnz / set_max_result_nnz).  Rows of A and B need not be
+ * sorted.  Structure is purely symbolic: explicit zeros are kept.  Calling it
+ * again on the same plan is idempotent (symbolic_spec.hpp:99).  Synchronises
+ * `stream` (c_nnz is returned to the host).  B200SP_ERR_OVERFLOW when
+ * nnz(C) > INT32_MAX (symbolic_tpl_spec_decl.hpp:131-133). */
+int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
+                               const int* row_ptr_A, const int* col_idx_A, const int* row_ptr_B,
+                               const int* col_idx_B, int* row_ptr_C, int64_t* c_nnz,
+                               int* c_max_row_nnz);
+
+/* Replaces SPGEMM_NUMERIC<...,true,*>::spgemm_numeric -> spgemm_numeric_cusparse
+ * (sparse/tpls/KokkosSparse_spgemm_numeric_tpl_spec_decl.hpp:44-256).
+ * Fills col_idx_C / vals_C for the row_ptr_C symbolic produced; every C row
+ * comes out SORTED by column (TPL contract; the native path sorts afterwards,
+ * sparse/impl/KokkosSparse_spgemm_numeric_spec.hpp:138-140).  Re-runnable with
+ * new value pointers on the same structure (Test_Sparse_spgemm.hpp:112-122).
+ * B200SP_ERR_STATE when symbolic was not called on this plan
+ * (numeric_spec.hpp:116-118).  Asynchronous on `stream`. */
+int b200sp_spgemm_numeric_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
+                                  const int* row_ptr_A, const int* col_idx_A, const double* vals_A,
+                                  const int* row_ptr_B, const int* col_idx_B, const double* vals_B,
+                                  const int* row_ptr_C, int* col_idx_C, double* vals_C);
+int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
+                                  const int* row_ptr_A, const int* col_idx_A, const float* vals_A,
+                                  const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
+                                  const int* row_ptr_C, int* col_idx_C, float* vals_C);
+
+/* ---- introspection / tuning (bench + tests only) ------------------------- */
+/* Counts kernels launched by this library since process start (all plans). */
+int64_t b200sp_launch_count(void);
+/* Name of the kernel variant the plan's last spmv call used ("tile<...>",
+ * "vector<...>", ...); static storage. */
+const char* b200sp_spmv_last_kernel(const b200sp_spmv_plan* plan);
+/* Override the tiled kernel's configuration for this plan before its first
+ * use: cfg = index into the built-in table, grid_mult = CTAs
+ * per SM (0 = default).  Returns B200SP_ERR_INVALID_ARGUMENT if out of range. */
+int b200sp_spmv_plan_tune(b200sp_spmv_plan* plan, int cfg, int lanes_per_row, int ctas_per_sm);
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H_ */

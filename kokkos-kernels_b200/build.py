@@ -1,0 +1,69 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel
+with the repo snapshot to the GPU box).
+
+  lib/libb200sparse.so   CUDA kernels + C ABI (include/b200sparse.h), sm_100a
+  lib/libb200matgen.so   host-side synthetic matrix generators (C + OpenMP)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "lib")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+CU_SOURCES = ["spmv.cu", "spmm.cu", "spgemm.cu"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def build(force=False, verbose=True):
+    os.makedirs(LIB, exist_ok=True)
+    out = os.path.join(LIB, "libb200sparse.so")
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b200sparse.h")]
+    if force or not _newer(out, deps):
+        objs = []
+        procs = []
+        for s in srcs:
+            o = os.path.join(LIB, os.path.basename(s) + ".o")
+            objs.append(o)
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            if verbose:
+                print("[build]", " ".join(cmd), flush=True)
+            procs.append((subprocess.Popen(cmd), cmd))
+        for p, cmd in procs:
+            if p.wait() != 0:
+                raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        if verbose:
+            print("[build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    gen = os.path.join(LIB, "libb200matgen.so")
+    gsrc = os.path.join(CSRC, "matgen.c")
+    if force or not _newer(gen, [gsrc]):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-fvisibility=hidden", "-std=gnu11", "-o", gen, gsrc, "-lm"]
+        if verbose:
+            print("[build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return out, gen
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,128 @@
+// common.cuh -- shared helpers of libb200sparse (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/b200sparse.h"
+
+namespace b200sp {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define B200SP_CUDA_TRY(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::b200sp::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,       \
+                          cudaGetErrorString(_e));                                   \
+      return B200SP_ERR_CUDA;                                                        \
+    }                                                                                \
+  } while (0)
+
+#define B200SP_LAUNCH_CHECK()                                                        \
+  do {                                                                               \
+    ::b200sp::g_launches.fetch_add(1, std::memory_order_relaxed);                    \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      ::b200sp::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,   \
+                          cudaGetErrorString(_e));                                   \
+      return B200SP_ERR_CUDA;                                                        \
+    }                                                                                \
+  } while (0)
+
+#define B200SP_REQUIRE(cond, ...)                                                    \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      ::b200sp::set_error(__VA_ARGS__);                                              \
+      return B200SP_ERR_INVALID_ARGUMENT;                                            \
+    }                                                                                \
+  } while (0)
+
+int sm_count();  // SMs of the current device (cached per device)
+
+// ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk async copy (TMA engine, SASS UBLKCP); completes `bytes`
+// on `bar`.  src/dst 16-byte aligned, bytes a multiple of 16.  `policy` is an
+// L2 cache-hint descriptor (createpolicy).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// read-only gathers (LDG.CONSTANT, L1-allocating)
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p) {
+  return __ldg(p);
+}
+// streaming loads that should not displace x in L1
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor(T v, int mask) {
+  return __shfl_xor_sync(0xffffffffu, v, mask);
+}
+
+}  // namespace b200sp

@@ -1,0 +1,875 @@
+// spgemm.cu -- C = A*B on CrsMatrix data for B200 (sm_100a): symbolic + numeric.
+//
+// Replaces the reference's Kokkos::Cuda SpGEMM legs
+//   native  KokkosSPGEMM symbolic (compression + StructureC hash kernels)
+//           sparse/impl/KokkosSparse_spgemm_impl_symbolic.hpp:903-1100,1513-1957
+//   native  numeric PortableNumericCHASH / NumericCMEM + sort_crs_matrix
+//           sparse/impl/KokkosSparse_spgemm_impl_kkmem.hpp:410-1021,1173-1258,
+//           sparse/impl/KokkosSparse_spgemm_numeric_spec.hpp:138-140
+//   TPL     cusparseSpGEMMreuse_*
+//           sparse/tpls/KokkosSparse_spgemm_{symbolic,numeric}_tpl_spec_decl.hpp
+// Results follow the reference's SPGEMM_DEBUG host path (impl_seq.hpp:23-182)
+// after sort_crs_matrix: row_ptr / col_idx bit-identical, values by its
+// accumulation law (sum of b_val*a_val, association differs).
+//
+// Design
+//  symbolic: per-row flop bound f_i and column span [cmin_i, cmax_i] from one
+//    pass over A (+ a min/max pass over B's rows); rows binned by f_i; each bin
+//    runs a shared-memory hash-set kernel (group of G threads per row, atomicCAS
+//    on keys) that counts distinct columns; rows too big for shared memory use
+//    a per-CTA global bitmap.  Exclusive scan -> row_ptr_C, c_nnz, max row.
+//  numeric: rows binned by nnz(C_i); a group of threads builds the row in a
+//    shared-memory accumulator addressed by a MONOTONE map of the column
+//    (dense accumulator when the row's span fits the table, order-preserving
+//    hash with linear probing otherwise), so the table is already sorted up to
+//    its probe clusters; an in-cluster rank turns slots into sorted output
+//    positions -- the separate sort_crs_matrix pass of the reference is gone.
+//    Rows that overflow or exceed shared memory go to a global-memory hash +
+//    in-place bitonic sort kernel.
+#include "common.cuh"
+#include <algorithm>
+#include <limits.h>
+#include <new>
+
+namespace b200sp {
+
+static constexpr int EMPTY = -1;
+
+// ---------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------
+__global__ void fill_int_kernel(int64_t n, int v, int* __restrict__ p) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// per-row min / max column of B (EMPTY rows: min = INT_MAX, max = -1)
+__global__ void brow_minmax_kernel(int n, const int* __restrict__ rp, const int* __restrict__ ci,
+                                   int* __restrict__ bmin, int* __restrict__ bmax) {
+  // 8 lanes per row
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int r = (int)(t >> 3), sl = (int)(t & 7);
+  int mn = INT_MAX, mx = -1;
+  if (r < n)
+    for (int j = rp[r] + sl; j < rp[r + 1]; j += 8) {
+      const int c = ci[j];
+      mn = min(mn, c);
+      mx = max(mx, c);
+    }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (r < n && sl == 0) {
+    bmin[r] = mn;
+    bmax[r] = mx;
+  }
+}
+
+// per A-row: flop bound, column span of the product row
+__global__ void arow_analyse_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ ciA,
+                                    const int* __restrict__ rpB, const int* __restrict__ bmin,
+                                    const int* __restrict__ bmax, int* __restrict__ flops,
+                                    int* __restrict__ cmin, int* __restrict__ cmax) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int r = (int)(t >> 3), sl = (int)(t & 7);
+  long long f = 0;
+  int mn = INT_MAX, mx = -1;
+  if (r < m)
+    for (int j = rpA[r] + sl; j < rpA[r + 1]; j += 8) {
+      const int c = ciA[j];
+      f += rpB[c + 1] - rpB[c];
+      mn = min(mn, bmin[c]);
+      mx = max(mx, bmax[c]);
+    }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    f += __shfl_xor_sync(0xffffffffu, f, o);
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (r < m && sl == 0) {
+    flops[r] = (int)min(f, (long long)INT_MAX);
+    cmin[r] = mn;
+    cmax[r] = mx;
+  }
+}
+
+// ---- binning: rows -> bins by a key array and ascending thresholds ---------
+static constexpr int MAXBINS = 8;
+struct BinSpec {
+  int nb;               // number of bins (last bin = everything above thr[nb-2])
+  int thr[MAXBINS];     // bin b holds keys <= thr[b] (and > thr[b-1])
+};
+__device__ __forceinline__ int bin_of(const BinSpec& s, int key) {
+  int b = 0;
+  while (b < s.nb - 1 && key > s.thr[b]) ++b;
+  return b;
+}
+__global__ void bin_count_kernel(int m, const int* __restrict__ key, BinSpec spec, int* __restrict__ counts) {
+  __shared__ int sc[MAXBINS];
+  if (threadIdx.x < MAXBINS) sc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) atomicAdd(&sc[bin_of(spec, key[r])], 1);
+  __syncthreads();
+  if (threadIdx.x < MAXBINS && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+__global__ void bin_scatter_kernel(int m, const int* __restrict__ key, BinSpec spec, int* __restrict__ cursors,
+                                   int* __restrict__ rows_out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x)
+    rows_out[atomicAdd(&cursors[bin_of(spec, key[r])], 1)] = r;
+}
+
+// ---- exclusive scan of row counts -> row_ptr (int32) + total (int64) + max --
+static constexpr int SCAN_ITEMS = 2048;  // per CTA (256 threads x 8)
+__global__ void __launch_bounds__(256) scan_local_kernel(int m, const int* __restrict__ cnt, int* __restrict__ out,
+                                                         long long* __restrict__ block_sum, int* __restrict__ block_max) {
+  __shared__ long long wsum[8];
+  __shared__ int wmax[8];
+  const int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+  int v[8];
+  long long s = 0;
+  int mx = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = (base + i < m) ? cnt[base + i] : 0;
+    s += v[i];
+    mx = max(mx, v[i]);
+  }
+  // warp inclusive scan of s
+  long long inc = s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 31) wsum[w] = inc;
+  if (lane == 0) wmax[w] = mx;
+  __syncthreads();
+  long long woff = 0;
+  for (int i = 0; i < w; ++i) woff += wsum[i];
+  long long run = woff + inc - s;  // exclusive prefix of this thread within the block
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (base + i < m) out[base + i] = (int)run;  // block-local; offset added later
+    run += v[i];
+  }
+  if (threadIdx.x == 255) {
+    long long tot = 0;
+    int bm = 0;
+    for (int i = 0; i < 8; ++i) {
+      tot += wsum[i];
+      bm = max(bm, wmax[i]);
+    }
+    block_sum[blockIdx.x] = tot;
+    block_max[blockIdx.x] = bm;
+  }
+}
+__global__ void scan_blocks_kernel(int nblocks, long long* __restrict__ block_sum, const int* __restrict__ block_max,
+                                   long long* __restrict__ total, int* __restrict__ maxv) {
+  // single thread block; serial over chunks of 1024 (nblocks is m/2048: small)
+  __shared__ long long carry;
+  __shared__ long long ws[32];
+  __shared__ int gm;
+  if (threadIdx.x == 0) {
+    carry = 0;
+    gm = 0;
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const long long v = i < nblocks ? block_sum[i] : 0;
+    if (i < nblocks) atomicMax(&gm, block_max[i]);
+    long long inc = v;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int k = 0; k < w; ++k) woff += ws[k];
+    const long long excl = carry + woff + inc - v;
+    if (i < nblocks) block_sum[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total = carry;
+    *maxv = gm;
+  }
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(int m, int* __restrict__ out, const long long* __restrict__ block_off,
+                                                       const long long* __restrict__ total) {
+  const long long off = block_off[blockIdx.x];
+  const int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+  const bool ok = *total <= (long long)INT_MAX;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (base + i < m) out[base + i] = ok ? (int)(out[base + i] + off) : 0;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[m] = ok ? (int)*total : 0;
+}
+
+// ---------------------------------------------------------------------------
+// SYMBOLIC: count distinct columns of row i of A*B with a shared-memory hash set.
+// G threads cooperate on one row; LB lanes walk one row of B.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash_mul(int c, int log2slots) {
+  return ((unsigned)c * 0x9E3779B1u) >> (32 - log2slots);
+}
+
+template <int G, int LOG2SLOTS>
+__global__ void __launch_bounds__(G <= 32 ? 256 : G)
+    sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
+                    const int* __restrict__ ciA, const int* __restrict__ rpB, const int* __restrict__ ciB,
+                    int* __restrict__ row_nnz) {
+  constexpr int SLOTS = 1 << LOG2SLOTS;
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  extern __shared__ int sm_keys[];  // RPC * SLOTS
+  __shared__ int sm_cnt[RPC];
+  const int g = threadIdx.x / G, tg = threadIdx.x % G;
+  int* keys = sm_keys + g * SLOTS;
+  const int ridx = blockIdx.x * RPC + g;
+  const bool active = ridx < nrows_bin;
+  for (int s = tg; s < SLOTS; s += G) keys[s] = EMPTY;
+  if (tg == 0) sm_cnt[g] = 0;
+  if (G <= 32) __syncwarp(); else __syncthreads();
+  int mine = 0;
+  if (active) {
+    const int i = rows[ridx];
+    const int a0 = rpA[i], a1 = rpA[i + 1];
+    const int subs = G / lb;  // B rows walked concurrently by the group
+    const int sub = tg / lb, sl = tg % lb;
+    for (int ja = a0 + sub; ja < a1; ja += subs) {
+      const int ca = ciA[ja];
+      const int b1 = rpB[ca + 1];
+      for (int jb = rpB[ca] + sl; jb < b1; jb += lb) {
+        const int c = ld_stream(ciB + jb);
+        unsigned h = hash_mul(c, LOG2SLOTS);
+        while (true) {
+          const int kcur = ((volatile int*)keys)[h];
+          if (kcur == c) break;
+          if (kcur == EMPTY) {
+            const int old = atomicCAS(&keys[h], EMPTY, c);
+            if (old == EMPTY) {
+              ++mine;
+              break;
+            }
+            if (old == c) break;
+          }
+          h = (h + 1) & (SLOTS - 1);
+        }
+      }
+    }
+  }
+  // group reduce
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (G <= 32) {
+    if (active && tg == 0) row_nnz[rows[ridx]] = mine;
+  } else {
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sm_cnt[g], mine);
+    __syncthreads();
+    if (active && tg == 0) row_nnz[rows[ridx]] = sm_cnt[g];
+  }
+}
+
+// rows whose flop bound exceeds the largest shared-memory table: k-bit bitmap per CTA in global memory
+__global__ void __launch_bounds__(256)
+    sym_bitmap_kernel(int nrows_bin, const int* __restrict__ rows, int k, unsigned* __restrict__ bitmaps,
+                      const int* __restrict__ rpA, const int* __restrict__ ciA, const int* __restrict__ rpB,
+                      const int* __restrict__ ciB, int* __restrict__ row_nnz) {
+  const int words = (k + 31) / 32;
+  unsigned* bm = bitmaps + (size_t)blockIdx.x * words;
+  __shared__ int cnt;
+  for (int ridx = blockIdx.x; ridx < nrows_bin; ridx += gridDim.x) {
+    const int i = rows[ridx];
+    for (int w = threadIdx.x; w < words; w += 256) bm[w] = 0u;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ja = rpA[i] + warp; ja < rpA[i + 1]; ja += 8) {
+      const int ca = ciA[ja];
+      for (int jb = rpB[ca] + lane; jb < rpB[ca + 1]; jb += 32) {
+        const int c = ciB[jb];
+        atomicOr(&bm[c >> 5], 1u << (c & 31));
+      }
+    }
+    __syncthreads();
+    int local = 0;
+    for (int w = threadIdx.x; w < words; w += 256) local += __popc(bm[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) row_nnz[i] = cnt;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// NUMERIC: monotone-addressed shared-memory accumulator -> sorted row.
+// ---------------------------------------------------------------------------
+template <typename S>
+__device__ __forceinline__ void smem_add(S* p, S v) {
+  atomicAdd(p, v);
+}
+
+template <typename S, int G, int SLOTS, int PAD>
+__global__ void __launch_bounds__(G <= 32 ? 256 : G)
+    num_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
+                    const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
+                    const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
+                    int* __restrict__ ciC, S* __restrict__ vC, const int* __restrict__ cmin_arr,
+                    const int* __restrict__ cmax_arr, int* __restrict__ fb_rows, int* __restrict__ fb_count) {
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  constexpr int TOT = SLOTS + PAD;
+  constexpr int WORDS = (TOT + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  // layout per row-group: vals[TOT] | keys[TOT] | wpre[WORDS] | wmask[WORDS]
+  constexpr size_t PER = sizeof(S) * TOT + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
+  constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
+  __shared__ int sm_flag[RPC];
+  const int g = threadIdx.x / G, tg = threadIdx.x % G;
+  unsigned char* base = smraw + (size_t)g * PER_AL;
+  S* vals = reinterpret_cast<S*>(base);
+  int* keys = reinterpret_cast<int*>(base + sizeof(S) * TOT);
+  int* wpre = keys + TOT;
+  unsigned* wmask = reinterpret_cast<unsigned*>(wpre + WORDS + 1);
+  const int ridx = blockIdx.x * RPC + g;
+  const bool active = ridx < nrows_bin;
+  auto gsync = [&]() {
+    if (G <= 32) __syncwarp(); else __syncthreads();
+  };
+  for (int s = tg; s < TOT; s += G) {
+    keys[s] = EMPTY;
+    vals[s] = S(0);
+  }
+  if (tg == 0) sm_flag[g] = 0;
+  gsync();
+  int i = 0, cbase = 0, nz = 0;
+  bool dense = false;
+  if (active) {
+    i = rows[ridx];
+    cbase = rpC[i];
+    nz = rpC[i + 1] - cbase;
+  }
+  if (active && nz > 0) {
+    const int cmin = cmin_arr[i];
+    const long long span = (long long)cmax_arr[i] - cmin + 1;
+    dense = span <= SLOTS;
+    // monotone map column -> slot in [0, SLOTS)
+    const unsigned long long mult = dense ? 0ull : (((unsigned long long)SLOTS << 32) / (unsigned long long)span);
+    const int a0 = rpA[i], a1 = rpA[i + 1];
+    const int subs = G / lb;
+    const int sub = tg / lb, sl = tg % lb;
+    bool ovf = false;
+    for (int ja = a0 + sub; ja < a1; ja += subs) {
+      const int ca = ciA[ja];
+      const S va = vA[ja];
+      const int b1 = rpB[ca + 1];
+      for (int jb = rpB[ca] + sl; jb < b1; jb += lb) {
+        const int c = ld_stream(ciB + jb);
+        const S v = ld_stream(vB + jb) * va;  // b_val * val (impl_seq.hpp:163)
+        int h = dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
+        while (true) {
+          const int kcur = ((volatile int*)keys)[h];
+          if (kcur == c) break;
+          if (kcur == EMPTY) {
+            const int old = atomicCAS(&keys[h], EMPTY, c);
+            if (old == EMPTY || old == c) break;
+          }
+          if (++h >= TOT) {
+            ovf = true;
+            break;
+          }
+        }
+        if (ovf) break;
+        smem_add(&vals[h], v);
+      }
+      if (ovf) break;
+    }
+    if (ovf) sm_flag[g] = 1;
+  }
+  gsync();
+  const bool overflow = sm_flag[g] != 0;
+  if (active && overflow && tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
+  if (active && nz > 0 && !overflow) {
+    // occupancy prefix: wpre[w] = number of occupied slots before word w
+    for (int w = tg; w < WORDS; w += G) {
+      unsigned msk = 0u;
+      const int s0 = w * 32;
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b)
+        if (s0 + b < TOT && keys[s0 + b] != EMPTY) msk |= (1u << b);
+      wmask[w] = msk;
+      wpre[w] = __popc(msk);
+    }
+    gsync();
+    if (tg < 32) {
+      int carry = 0;
+      for (int w0 = 0; w0 < WORDS; w0 += 32) {
+        const int w = w0 + tg;
+        const int v = w < WORDS ? wpre[w] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (tg >= o) inc += t;
+        }
+        if (w < WORDS) wpre[w] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    gsync();
+    for (int s = tg; s < TOT; s += G) {
+      const int key = keys[s];
+      if (key == EMPTY) continue;
+      int pos = wpre[s >> 5] + __popc(wmask[s >> 5] & ((1u << (s & 31)) - 1u));
+      if (!dense) {
+        // rank inside the probe cluster: clusters are ordered, members are not
+        for (int t = s - 1; t >= 0; --t) {
+          const int kt = keys[t];
+          if (kt == EMPTY) break;
+          pos -= (kt > key);
+        }
+        for (int t = s + 1; t < TOT; ++t) {
+          const int kt = keys[t];
+          if (kt == EMPTY) break;
+          pos += (kt < key);
+        }
+      }
+      ciC[cbase + pos] = key;
+      vC[cbase + pos] = vals[s];
+    }
+  }
+}
+
+// fallback: global-memory hash (wrap-around, multiplicative) + in-place bitonic sort of the C row
+template <typename S>
+__global__ void __launch_bounds__(256)
+    num_fallback_kernel(const int* __restrict__ fb_rows, const int* __restrict__ fb_count, int log2slots,
+                        int* __restrict__ gkeys, S* __restrict__ gvals, const int* __restrict__ rpA,
+                        const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
+                        const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
+                        int* __restrict__ ciC, S* __restrict__ vC) {
+  const size_t slots = (size_t)1 << log2slots;
+  int* keys = gkeys + (size_t)blockIdx.x * slots;
+  S* vals = gvals + (size_t)blockIdx.x * slots;
+  __shared__ int cursor;
+  const int nfb = *fb_count;
+  for (int q = blockIdx.x; q < nfb; q += gridDim.x) {
+    const int i = fb_rows[q];
+    const int cbase = rpC[i];
+    const int nz = rpC[i + 1] - cbase;
+    // table sized for this row: smallest power of two >= 2*nz (<= slots)
+    int lg = 1;
+    while (((size_t)1 << lg) < (size_t)2 * (size_t)nz) ++lg;
+    const size_t tsz = (size_t)1 << lg;
+    for (size_t s = threadIdx.x; s < tsz; s += 256) {
+      keys[s] = EMPTY;
+      vals[s] = S(0);
+    }
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ja = rpA[i] + warp; ja < rpA[i + 1]; ja += 8) {
+      const int ca = ciA[ja];
+      const S va = vA[ja];
+      for (int jb = rpB[ca] + lane; jb < rpB[ca + 1]; jb += 32) {
+        const int c = ciB[jb];
+        const S v = vB[jb] * va;
+        size_t h = hash_mul(c, lg);
+        while (true) {
+          const int kcur = ((volatile int*)keys)[h];
+          if (kcur == c) break;
+          if (kcur == EMPTY) {
+            const int old = atomicCAS(&keys[h], EMPTY, c);
+            if (old == EMPTY || old == c) break;
+          }
+          h = (h + 1) & (tsz - 1);
+        }
+        atomicAdd(&vals[h], v);
+      }
+    }
+    __syncthreads();
+    for (size_t s = threadIdx.x; s < tsz; s += 256) {
+      const int key = keys[s];
+      if (key != EMPTY) {
+        const int p = atomicAdd(&cursor, 1);
+        ciC[cbase + p] = key;
+        vC[cbase + p] = vals[s];
+      }
+    }
+    __syncthreads();
+    // bitonic network with all comparators ascending (virtual +inf padding never moves)
+    int P = 1;
+    while (P < nz) P <<= 1;
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1, first = 1; stride > 0; stride >>= 1, first = 0) {
+        for (int idx = threadIdx.x; idx < P; idx += 256) {
+          const int l = first ? (idx ^ (size - 1)) : (idx ^ stride);
+          if (l > idx && l < nz) {
+            const int ka = ciC[cbase + idx], kb = ciC[cbase + l];
+            if (ka > kb) {
+              ciC[cbase + idx] = kb;
+              ciC[cbase + l] = ka;
+              const S ta = vC[cbase + idx];
+              vC[cbase + idx] = vC[cbase + l];
+              vC[cbase + l] = ta;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200sp
+
+using namespace b200sp;
+
+// ---------------------------------------------------------------------------
+// plan + host drivers
+// ---------------------------------------------------------------------------
+// symbolic bins by flop bound f (table slots >= 2f); last bin -> global bitmap
+static const int kSymThr[] = {128, 512, 2048, 8192, 16384};
+static constexpr int kSymBins = 6;
+// numeric bins by nnz(C_i); last bin -> global fallback
+static const int kNumThr[] = {64, 256, 1024, 4096, 8192};
+static constexpr int kNumBins = 6;
+static constexpr int kFbCtas = 16;
+
+struct b200sp_spgemm_plan {
+  bool symbolic_done = false;
+  int m = 0, n = 0, k = 0;
+  const int *rpA = nullptr, *ciA = nullptr, *rpB = nullptr, *ciB = nullptr;
+  int64_t c_nnz = 0;
+  int c_max = 0;
+  int lb = 8;  // lanes walking one B row
+  // device state kept for numeric
+  int *cmin = nullptr, *cmax = nullptr;
+  int* num_rows = nullptr;  // rows grouped by numeric bin
+  int num_off[kNumBins + 1] = {0};
+  int *fb_rows = nullptr, *fb_count = nullptr;
+  int fb_static = 0;
+  int fb_log2 = 1;
+  int* fb_keys = nullptr;
+  void* fb_vals = nullptr;
+  size_t fb_vals_bytes = 0;
+};
+
+namespace b200sp {
+
+static void spgemm_release(b200sp_spgemm_plan* p, cudaStream_t st) {
+  void* ptrs[] = {p->cmin, p->cmax, p->num_rows, p->fb_rows, p->fb_count, p->fb_keys, p->fb_vals};
+  for (void* q : ptrs)
+    if (q) cudaFreeAsync(q, st);
+  p->cmin = p->cmax = p->num_rows = p->fb_rows = p->fb_count = p->fb_keys = nullptr;
+  p->fb_vals = nullptr;
+  p->fb_vals_bytes = 0;
+  p->symbolic_done = false;
+}
+
+struct DevTmp {  // frees stream-ordered on scope exit
+  cudaStream_t st;
+  void* ptrs[16];
+  int n = 0;
+  explicit DevTmp(cudaStream_t s) : st(s) {}
+  ~DevTmp() {
+    for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st);
+  }
+  template <typename T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, sizeof(T) * std::max<size_t>(count, 1), st);
+    if (e == cudaSuccess) ptrs[n++] = q;
+    *out = (T*)q;
+    return e;
+  }
+};
+
+static int bin_rows(cudaStream_t st, int m, const int* key, const BinSpec& spec, int* d_counts /*MAXBINS*/,
+                    int* rows_out, int* h_off /*nb+1*/) {
+  B200SP_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * MAXBINS, st));
+  const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
+  bin_count_kernel<<<blocks, 256, 0, st>>>(m, key, spec, d_counts);
+  B200SP_LAUNCH_CHECK();
+  int h_counts[MAXBINS];
+  B200SP_CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, sizeof(int) * MAXBINS, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  h_off[0] = 0;
+  for (int b = 0; b < spec.nb; ++b) h_off[b + 1] = h_off[b] + h_counts[b];
+  B200SP_CUDA_TRY(cudaMemcpyAsync(d_counts, h_off, sizeof(int) * spec.nb, cudaMemcpyHostToDevice, st));
+  bin_scatter_kernel<<<blocks, 256, 0, st>>>(m, key, spec, d_counts, rows_out);
+  B200SP_LAUNCH_CHECK();
+  // h_off is pageable host memory: make sure the H2D copy consumed it before it can change
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+template <int G, int LOG2SLOTS>
+static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const int* rpA, const int* ciA,
+                      const int* rpB, const int* ciB, int* row_nnz) {
+  if (nrows <= 0) return B200SP_OK;
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  const size_t smem = sizeof(int) * (size_t)RPC * ((size_t)1 << LOG2SLOTS);
+  auto kern = sym_hash_kernel<G, LOG2SLOTS>;
+  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, std::min(lb, G), rpA, ciA, rpB, ciB, row_nnz);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S, int G, int SLOTS, int PAD>
+static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
+                      const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
+  const int nrows = p->num_off[bin + 1] - p->num_off[bin];
+  if (nrows <= 0) return B200SP_OK;
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  constexpr int TOT = SLOTS + PAD;
+  constexpr int WORDS = (TOT + 31) / 32;
+  constexpr size_t PER = sizeof(S) * TOT + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
+  constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
+  const size_t smem = PER_AL * RPC;
+  auto kern = num_hash_kernel<S, G, SLOTS, PAD>;
+  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, G), rpA, ciA,
+                                                      vA, rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->fb_rows,
+                                                      p->fb_count);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S>
+static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int k, const int* rpA, const int* ciA,
+                        const S* vA, const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
+  B200SP_REQUIRE(p != nullptr, "spgemm_numeric: null plan");
+  if (!p->symbolic_done) {
+    set_error("Call spgemm symbolic before spgemm numeric");
+    return B200SP_ERR_STATE;
+  }
+  if (p->m != m || p->n != n || p->k != k) {
+    set_error("spgemm_numeric: dimensions (%d,%d,%d) differ from symbolic (%d,%d,%d)", m, n, k, p->m, p->n, p->k);
+    return B200SP_ERR_STATE;
+  }
+  if (m == 0 || p->c_nnz == 0) return B200SP_OK;
+  B200SP_REQUIRE(rpA && ciA && vA && rpB && ciB && vB && rpC && ciC && vC, "spgemm_numeric: null pointer argument");
+  // fallback scratch for values (type-dependent; keys were sized in symbolic)
+  const size_t need = sizeof(S) * (size_t)kFbCtas * ((size_t)1 << p->fb_log2);
+  if (need > p->fb_vals_bytes) {
+    if (p->fb_vals) cudaFreeAsync(p->fb_vals, st);
+    p->fb_vals = nullptr;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->fb_vals, need, st));
+    p->fb_vals_bytes = need;
+  }
+  // fallback list starts as the rows that are too long for shared memory
+  B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_count, &p->fb_static, sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc;
+  if ((rc = launch_num<S, 32, 128, 32>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 32, 512, 64>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 128, 2048, 128>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 256, 8192, 256>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 512, 16384, 512>(st, p, 4, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                  ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+extern "C" {
+
+int b200sp_spgemm_plan_create(b200sp_spgemm_plan** plan) {
+  B200SP_REQUIRE(plan != nullptr, "spgemm_plan_create: null output pointer");
+  b200sp_spgemm_plan* p = new (std::nothrow) b200sp_spgemm_plan();
+  if (!p) {
+    set_error("spgemm_plan_create: out of host memory");
+    return B200SP_ERR_ALLOC;
+  }
+  *plan = p;
+  return B200SP_OK;
+}
+
+int b200sp_spgemm_plan_destroy(b200sp_spgemm_plan* p, void* stream) {
+  if (!p) return B200SP_OK;
+  spgemm_release(p, (cudaStream_t)stream);
+  delete p;
+  return B200SP_OK;
+}
+
+int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n, int k, const int* rpA,
+                               const int* ciA, const int* rpB, const int* ciB, int* rpC, int64_t* c_nnz,
+                               int* c_max_row_nnz) {
+  B200SP_REQUIRE(p != nullptr, "spgemm_symbolic: null plan");
+  B200SP_REQUIRE(m >= 0 && n >= 0 && k >= 0, "spgemm_symbolic: negative dimension");
+  B200SP_REQUIRE(rpC != nullptr, "spgemm_symbolic: row_ptr_C is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->symbolic_done) {
+    // one handle, one product (reference debug build throws std::invalid_argument, spgemm_handle.hpp:706-746)
+    if (p->m != m || p->n != n || p->k != k || p->rpA != rpA || p->ciA != ciA || p->rpB != rpB || p->ciB != ciB) {
+      set_error("spgemm_symbolic: handle was already used for a different product; create a new handle");
+      return B200SP_ERR_STATE;
+    }
+  }
+  spgemm_release(p, st);
+  p->m = m; p->n = n; p->k = k;
+  p->rpA = rpA; p->ciA = ciA; p->rpB = rpB; p->ciB = ciB;
+  p->c_nnz = 0; p->c_max = 0; p->fb_static = 0;
+  for (int b = 0; b <= kNumBins; ++b) p->num_off[b] = 0;
+
+  // degenerate shapes: zero row_ptr, c_nnz = 0 (symbolic_spec.hpp:101-107, numeric_tpl_spec_decl.hpp:55-68)
+  int64_t nnzA = 0, nnzB = 0;
+  if (m > 0) {
+    B200SP_REQUIRE(rpA != nullptr, "spgemm_symbolic: row_ptr_A is null");
+    int last = 0;
+    B200SP_CUDA_TRY(cudaMemcpyAsync(&last, rpA + m, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+    nnzA = last;
+  }
+  if (n > 0 && nnzA > 0) {
+    B200SP_REQUIRE(rpB != nullptr, "spgemm_symbolic: row_ptr_B is null");
+    int last = 0;
+    B200SP_CUDA_TRY(cudaMemcpyAsync(&last, rpB + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+    nnzB = last;
+  }
+  // numeric needs these even for empty products
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->fb_count, sizeof(int), st));
+  if (m == 0 || n == 0 || k == 0 || nnzA == 0 || nnzB == 0) {
+    const int blocks = std::max(1, std::min((m + 1 + 255) / 256, sm_count() * 8));
+    fill_int_kernel<<<blocks, 256, 0, st>>>((int64_t)m + 1, 0, rpC);
+    B200SP_LAUNCH_CHECK();
+    B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+    p->symbolic_done = true;
+    if (c_nnz) *c_nnz = 0;
+    if (c_max_row_nnz) *c_max_row_nnz = 0;
+    return B200SP_OK;
+  }
+  B200SP_REQUIRE(ciA && ciB, "spgemm_symbolic: null column index array");
+
+  DevTmp tmp(st);
+  int *bmin, *bmax, *flops, *row_nnz, *sym_rows, *d_counts, *block_max, *d_max;
+  long long *block_sum, *d_total;
+  const int nblocks = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  B200SP_CUDA_TRY(tmp.alloc(&bmin, n));
+  B200SP_CUDA_TRY(tmp.alloc(&bmax, n));
+  B200SP_CUDA_TRY(tmp.alloc(&flops, m));
+  B200SP_CUDA_TRY(tmp.alloc(&row_nnz, m));
+  B200SP_CUDA_TRY(tmp.alloc(&sym_rows, m));
+  B200SP_CUDA_TRY(tmp.alloc(&d_counts, MAXBINS));
+  B200SP_CUDA_TRY(tmp.alloc(&block_sum, nblocks));
+  B200SP_CUDA_TRY(tmp.alloc(&block_max, nblocks));
+  B200SP_CUDA_TRY(tmp.alloc(&d_total, 1));
+  B200SP_CUDA_TRY(tmp.alloc(&d_max, 1));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->cmin, sizeof(int) * (size_t)m, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->cmax, sizeof(int) * (size_t)m, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->num_rows, sizeof(int) * (size_t)m, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->fb_rows, sizeof(int) * (size_t)m, st));
+
+  // lanes per B row from B's mean row length
+  {
+    const double avg = (double)nnzB / (double)n;
+    int lb = 4;
+    while (lb < 32 && lb < avg) lb <<= 1;
+    p->lb = lb;
+  }
+  brow_minmax_kernel<<<(unsigned)(((int64_t)n * 8 + 255) / 256), 256, 0, st>>>(n, rpB, ciB, bmin, bmax);
+  B200SP_LAUNCH_CHECK();
+  arow_analyse_kernel<<<(unsigned)(((int64_t)m * 8 + 255) / 256), 256, 0, st>>>(m, rpA, ciA, rpB, bmin, bmax, flops,
+                                                                                p->cmin, p->cmax);
+  B200SP_LAUNCH_CHECK();
+
+  // ---- bin by flop bound, count distinct columns per row
+  BinSpec sspec;
+  sspec.nb = kSymBins;
+  for (int b = 0; b < kSymBins - 1; ++b) sspec.thr[b] = kSymThr[b];
+  int soff[kSymBins + 1];
+  int rc = bin_rows(st, m, flops, sspec, d_counts, sym_rows, soff);
+  if (rc) return rc;
+  const int lb = p->lb;
+#define SYM_BIN(B, G, LG)                                                                                          \
+  if ((rc = launch_sym<G, LG>(st, soff[B + 1] - soff[B], sym_rows + soff[B], lb, rpA, ciA, rpB, ciB, row_nnz))) \
+    return rc;
+  SYM_BIN(0, 32, 8)     // f <= 128   -> 256 slots, warp per row
+  SYM_BIN(1, 32, 10)    // f <= 512   -> 1024 slots
+  SYM_BIN(2, 128, 12)   // f <= 2048  -> 4096 slots
+  SYM_BIN(3, 256, 14)   // f <= 8192  -> 16384 slots (64 KB)
+  SYM_BIN(4, 512, 15)   // f <= 16384 -> 32768 slots (128 KB)
+#undef SYM_BIN
+  {
+    const int nbig = soff[kSymBins] - soff[kSymBins - 1];
+    if (nbig > 0) {
+      const int ctas = std::min(nbig, sm_count());
+      unsigned* bitmaps;
+      B200SP_CUDA_TRY(tmp.alloc(&bitmaps, (size_t)ctas * ((k + 31) / 32)));
+      sym_bitmap_kernel<<<ctas, 256, 0, st>>>(nbig, sym_rows + soff[kSymBins - 1], k, bitmaps, rpA, ciA, rpB, ciB, row_nnz);
+      B200SP_LAUNCH_CHECK();
+    }
+  }
+
+  // ---- row_ptr_C = exclusive scan(row_nnz); total and longest row
+  scan_local_kernel<<<nblocks, 256, 0, st>>>(m, row_nnz, rpC, block_sum, block_max);
+  B200SP_LAUNCH_CHECK();
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(nblocks, block_sum, block_max, d_total, d_max);
+  B200SP_LAUNCH_CHECK();
+  scan_add_kernel<<<nblocks, 256, 0, st>>>(m, rpC, block_sum, d_total);
+  B200SP_LAUNCH_CHECK();
+  long long total = 0;
+  int mx = 0;
+  B200SP_CUDA_TRY(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(&mx, d_max, sizeof(mx), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  if (total > (long long)INT_MAX) {
+    set_error("spgemm_symbolic: nnz(C) = %lld exceeds int32 offsets", total);
+    return B200SP_ERR_OVERFLOW;
+  }
+  p->c_nnz = total;
+  p->c_max = mx;
+
+  // ---- numeric bins by nnz(C_i) (kept on the plan so numeric stays asynchronous)
+  BinSpec nspec;
+  nspec.nb = kNumBins;
+  for (int b = 0; b < kNumBins - 1; ++b) nspec.thr[b] = kNumThr[b];
+  rc = bin_rows(st, m, row_nnz, nspec, d_counts, p->num_rows, p->num_off);
+  if (rc) return rc;
+  p->fb_static = p->num_off[kNumBins] - p->num_off[kNumBins - 1];
+  if (p->fb_static > 0)
+    B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_rows, p->num_rows + p->num_off[kNumBins - 1], sizeof(int) * (size_t)p->fb_static,
+                                    cudaMemcpyDeviceToDevice, st));
+  int lg = 1;
+  while (((long long)1 << lg) < 2LL * std::max(mx, 1)) ++lg;
+  p->fb_log2 = lg;
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->fb_keys, sizeof(int) * (size_t)kFbCtas * ((size_t)1 << lg), st));
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  p->symbolic_done = true;
+  if (c_nnz) *c_nnz = total;
+  if (c_max_row_nnz) *c_max_row_nnz = mx;
+  return B200SP_OK;
+}
+
+int b200sp_spgemm_numeric_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k, const int* rpA,
+                                  const int* ciA, const double* vA, const int* rpB, const int* ciB, const double* vB,
+                                  const int* rpC, int* ciC, double* vC) {
+  return numeric_impl<double>(plan, (cudaStream_t)stream, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+}
+int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k, const int* rpA,
+                                  const int* ciA, const float* vA, const int* rpB, const int* ciB, const float* vB,
+                                  const int* rpC, int* ciC, float* vC) {
+  return numeric_impl<float>(plan, (cudaStream_t)stream, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+}
+
+}  // extern "C"

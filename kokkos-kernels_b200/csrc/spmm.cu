@@ -1,0 +1,287 @@
+// spmm.cu -- rank-2 (multivector) CrsMatrix SpMV: Y = beta*Y + alpha*op(A)*X.
+//
+// Replaces the reference's Kokkos::Cuda legs
+//   native  SPMV_MV_LayoutLeft_Functor   sparse/impl/KokkosSparse_spmv_impl.hpp:634-1004,1057-1119
+//   native  SPMV_MV_Transpose_Functor    sparse/impl/KokkosSparse_spmv_impl.hpp:547-632,1163-1229
+//   TPL     cusparseSpMM                 sparse/tpls/KokkosSparse_spmv_mv_tpl_spec_decl.hpp:97-196
+//
+// Kernels:
+//   spmm_rowmajor_kernel  X, Y LayoutRight: a group of KT lanes owns one row of
+//                         A and one strip of <= KT columns; (col,val) pairs are
+//                         loaded coalesced KT at a time and broadcast by shuffle,
+//                         X rows are read as contiguous KT*sizeof(S) segments.
+//                         One pass over A per 32-column strip, no reduction.
+//   spmm_general_kernel   any LayoutLeft / LayoutRight mix: thread per (row, j).
+//   spmm_transpose_kernel T/H modes: Y pre-scaled, atomicAdd scatter.
+// Column-major (LayoutLeft) X with k >= 4 goes through a transposed copy so the
+// gather touches one segment per nonzero instead of k sectors.
+#include "common.cuh"
+#include <algorithm>
+
+struct b200sp_spmv_plan;  // defined in spmv.cu
+
+namespace b200sp {
+
+// scratch owned by the plan (spmv.cu)
+int plan_mv_scratch(b200sp_spmv_plan* p, cudaStream_t st, size_t xt_bytes, size_t yt_bytes, void** xt, void** yt);
+void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s);
+
+template <typename S>
+__global__ void scale2d_kernel(int64_t rows, int k, S beta, S* __restrict__ Y, int64_t yr, int64_t yc) {
+  const int64_t total = rows * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // walk memory-contiguously for either layout
+    int64_t r, j;
+    if (yc == 1 || yr != 1) { r = i / k; j = i % k; } else { j = i / rows; r = i % rows; }
+    S* p = &Y[r * yr + j * yc];
+    *p = (beta == S(0)) ? S(0) : beta * *p;
+  }
+}
+
+// out(r, j) row-major [rows x k] <- in(r, j) with strides (ir, ic)   (or the reverse)
+template <typename S, bool TO_ROWMAJOR>
+__global__ void relayout_kernel(int64_t rows, int k, S* __restrict__ rm, const S* __restrict__ strided_in,
+                                S* __restrict__ strided_out, int64_t sr, int64_t sc) {
+  __shared__ S tile[32][33];
+  // tile: 32 rows x 32 columns
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    if (TO_ROWMAJOR) {
+      // read along the column-major fast axis (rows), write along columns
+      for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x;
+        const int j = j0 + jj;
+        if (r < rows && j < k) tile[threadIdx.x][jj] = strided_in[r * sr + (int64_t)j * sc];
+      }
+      __syncthreads();
+      for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t r = r0 + rr;
+        const int j = j0 + threadIdx.x;
+        if (r < rows && j < k) rm[r * k + j] = tile[rr][threadIdx.x];
+      }
+    } else {
+      for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t r = r0 + rr;
+        const int j = j0 + threadIdx.x;
+        if (r < rows && j < k) tile[rr][threadIdx.x] = rm[r * k + j];
+      }
+      __syncthreads();
+      for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int64_t r = r0 + threadIdx.x;
+        const int j = j0 + jj;
+        if (r < rows && j < k) strided_out[r * sr + (int64_t)j * sc] = tile[threadIdx.x][jj];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename S, int KT>
+__global__ void __launch_bounds__(256)
+    spmm_rowmajor_kernel(int m, int k, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                         const S* __restrict__ vals, const S* __restrict__ X, int64_t ldx, S* __restrict__ Y,
+                         int64_t ldy, S alpha, S beta) {
+  constexpr int GPW = 32 / KT;  // row groups per warp
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / KT, t = lane % KT;
+  const int nstrips = (k + KT - 1) / KT;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t work = (int64_t)((m + GPW - 1) / GPW) * nstrips;
+  for (int64_t w = warp_global; w < work; w += nwarps) {
+    const int strip = (int)(w % nstrips);
+    const int r = (int)(w / nstrips) * GPW + grp;
+    const int j = strip * KT + t;
+    int rs = 0, re = 0;
+    if (r < m) {
+      rs = row_ptr[r];
+      re = row_ptr[r + 1];
+    }
+    // all groups of the warp iterate to the longest row (shuffles are warp-wide)
+    int len = re - rs;
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o >= KT; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    S acc = S(0);
+    const bool jok = (j < k);
+    for (int b = 0; b < maxlen; b += KT) {
+      int c = 0;
+      S v = S(0);
+      if (b + t < len) {
+        c = ld_stream(col_idx + rs + b + t);
+        v = ld_stream(vals + rs + b + t);
+      }
+      const int nb = min(KT, maxlen - b);
+#pragma unroll 4
+      for (int e = 0; e < nb; ++e) {
+        const int ce = __shfl_sync(0xffffffffu, c, e, KT);
+        const S ve = __shfl_sync(0xffffffffu, v, e, KT);
+        if (jok && b + e < len) acc += ve * ldg(X + (int64_t)ce * ldx + j);
+      }
+    }
+    if (r < m && jok) {
+      S* yp = Y + (int64_t)r * ldy + j;
+      acc *= alpha;
+      *yp = (beta == S(0)) ? acc : beta * *yp + acc;
+    }
+  }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+    spmm_general_kernel(int m, int k, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                        const S* __restrict__ vals, const S* __restrict__ X, int64_t xr, int64_t xc,
+                        S* __restrict__ Y, int64_t yr, int64_t yc, S alpha, S beta) {
+  const int64_t total = (int64_t)m * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / k), j = (int)(i % k);
+    S acc = S(0);
+    for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) acc += vals[e] * ldg(X + (int64_t)col_idx[e] * xr + (int64_t)j * xc);
+    acc *= alpha;
+    S* yp = Y + (int64_t)r * yr + (int64_t)j * yc;
+    *yp = (beta == S(0)) ? acc : beta * *yp + acc;
+  }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+    spmm_transpose_kernel(int m, int k, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                          const S* __restrict__ vals, const S* __restrict__ X, int64_t xr, int64_t xc,
+                          S* __restrict__ Y, int64_t yr, int64_t yc, S alpha) {
+  const int64_t total = (int64_t)m * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / k), j = (int)(i % k);
+    const S xv = X[(int64_t)r * xr + (int64_t)j * xc];
+    for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e)
+      atomicAdd(Y + (int64_t)col_idx[e] * yr + (int64_t)j * yc, alpha * vals[e] * xv);
+  }
+}
+
+template <typename S>
+static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, const int* col_idx, const S* vals,
+                           const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  int KT = 1;
+  while (KT < k && KT < 32) KT <<= 1;
+  const int gpw = 32 / KT;
+  const int nstrips = (k + KT - 1) / KT;
+  const int64_t work = (int64_t)((m + gpw - 1) / gpw) * nstrips;
+  int blocks = (int)std::min<int64_t>((work + 7) / 8, (int64_t)sm_count() * 16);
+  if (blocks < 1) blocks = 1;
+#define B200SP_RM(K)                                                                                              \
+  case K:                                                                                                         \
+    spmm_rowmajor_kernel<S, K><<<blocks, 256, 0, st>>>(m, k, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta); \
+    break;
+  switch (KT) {
+    B200SP_RM(1)
+    B200SP_RM(2)
+    B200SP_RM(4)
+    B200SP_RM(8)
+    B200SP_RM(16)
+    B200SP_RM(32)
+  }
+#undef B200SP_RM
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S>
+static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int n, int64_t nnz, int k, S alpha,
+                     const int* row_ptr, const int* col_idx, const S* vals, const S* X, int64_t ldx, int xrm,
+                     S beta, S* Y, int64_t ldy, int yrm) {
+  B200SP_REQUIRE(m >= 0 && n >= 0 && nnz >= 0 && k >= 0, "spmm: negative dimension");
+  bool trans;
+  switch (mode) {
+    case 'N': case 'n': case 'C': case 'c': trans = false; break;
+    case 'T': case 't': case 'H': case 'h': trans = true; break;
+    default: set_error("Invalid transpose mode %c for KokkosSparse::spmv()", mode); return B200SP_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t xrows = trans ? m : n, yrows = trans ? n : m;
+  const int64_t xr = xrm ? ldx : 1, xc = xrm ? 1 : ldx;
+  const int64_t yr = yrm ? ldy : 1, yc = yrm ? 1 : ldy;
+  if (k == 0 || yrows == 0) return B200SP_OK;
+  B200SP_REQUIRE(Y != nullptr, "spmm: Y is null");
+  B200SP_REQUIRE((xrm ? ldx >= k : ldx >= xrows) && (yrm ? ldy >= k : ldy >= yrows), "spmm: leading dimension too small");
+  const int grid_elem = (int)std::min<int64_t>((yrows * k + 255) / 256, (int64_t)sm_count() * 16);
+  if (alpha == S(0) || m == 0 || n == 0 || nnz == 0) {
+    if (beta != S(1)) {
+      scale2d_kernel<S><<<std::max(grid_elem, 1), 256, 0, st>>>(yrows, k, beta, Y, yr, yc);
+      B200SP_LAUNCH_CHECK();
+    }
+    return B200SP_OK;
+  }
+  B200SP_REQUIRE(row_ptr && col_idx && vals && X, "spmm: null pointer argument");
+  if (trans) {
+    if (beta != S(1)) {
+      scale2d_kernel<S><<<std::max(grid_elem, 1), 256, 0, st>>>(yrows, k, beta, Y, yr, yc);
+      B200SP_LAUNCH_CHECK();
+    }
+    const int g = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, (int64_t)sm_count() * 16);
+    spmm_transpose_kernel<S><<<std::max(g, 1), 256, 0, st>>>(m, k, row_ptr, col_idx, vals, X, xr, xc, Y, yr, yc, alpha);
+    B200SP_LAUNCH_CHECK();
+    plan_set_last_kernel(p, "spmm_transpose");
+    return B200SP_OK;
+  }
+  if (xrm && yrm) {
+    plan_set_last_kernel(p, "spmm_rowmajor");
+    return launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+  }
+  // LayoutLeft operands: with a plan and k >= 4, relayout to row-major scratch and use the row-major kernel
+  if (p && k >= 4) {
+    void *xt = nullptr, *yt = nullptr;
+    const size_t xtb = xrm ? 0 : sizeof(S) * (size_t)xrows * k;
+    const size_t ytb = yrm ? 0 : sizeof(S) * (size_t)yrows * k;
+    int rc = plan_mv_scratch(p, st, xtb, ytb, &xt, &yt);
+    if (rc) return rc;
+    const dim3 tb(32, 8);
+    const S* Xr = X;
+    int64_t ldxr = ldx;
+    if (!xrm) {
+      relayout_kernel<S, true><<<(unsigned)((xrows + 31) / 32), tb, 0, st>>>(xrows, k, (S*)xt, X, nullptr, xr, xc);
+      B200SP_LAUNCH_CHECK();
+      Xr = (const S*)xt;
+      ldxr = k;
+    }
+    S* Yr = Y;
+    int64_t ldyr = ldy;
+    if (!yrm) {
+      Yr = (S*)yt;
+      ldyr = k;
+      if (beta != S(0)) {
+        relayout_kernel<S, true><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, Y, nullptr, yr, yc);
+        B200SP_LAUNCH_CHECK();
+      }
+    }
+    rc = launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    if (rc) return rc;
+    if (!yrm) {
+      relayout_kernel<S, false><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
+      B200SP_LAUNCH_CHECK();
+    }
+    plan_set_last_kernel(p, "spmm_relayout+rowmajor");
+    return B200SP_OK;
+  }
+  const int g = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, (int64_t)sm_count() * 16);
+  spmm_general_kernel<S><<<std::max(g, 1), 256, 0, st>>>(m, k, row_ptr, col_idx, vals, X, xr, xc, Y, yr, yc, alpha, beta);
+  B200SP_LAUNCH_CHECK();
+  plan_set_last_kernel(p, "spmm_general");
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+using namespace b200sp;
+
+extern "C" {
+int b200sp_spmm_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, int k,
+                        double alpha, const int* row_ptr, const int* col_idx, const double* vals, const double* X,
+                        int64_t ldx, int x_row_major, double beta, double* Y, int64_t ldy, int y_row_major) {
+  return spmm_impl<double>(plan, (cudaStream_t)stream, mode, m, n, nnz, k, alpha, row_ptr, col_idx, vals, X, ldx,
+                           x_row_major, beta, Y, ldy, y_row_major);
+}
+int b200sp_spmm_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, int k,
+                        float alpha, const int* row_ptr, const int* col_idx, const float* vals, const float* X,
+                        int64_t ldx, int x_row_major, float beta, float* Y, int64_t ldy, int y_row_major) {
+  return spmm_impl<float>(plan, (cudaStream_t)stream, mode, m, n, nnz, k, alpha, row_ptr, col_idx, vals, X, ldx,
+                          x_row_major, beta, Y, ldy, y_row_major);
+}
+}

@@ -1,0 +1,768 @@
+// spmv.cu -- rank-1 CrsMatrix SpMV for B200 (sm_100a): y = beta*y + alpha*op(A)*x.
+//
+// Replaces the reference's Kokkos::Cuda SpMV legs:
+//   native  SPMV_Functor team kernel   sparse/impl/KokkosSparse_spmv_impl.hpp:134-165,337-379
+//   native  merge path                 sparse/impl/KokkosSparse_spmv_impl_merge.hpp:70-334
+//   native  transpose (atomics)        sparse/impl/KokkosSparse_spmv_impl.hpp:36-84,463-513
+//   TPL     cusparseSpMV               sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:31-197
+//
+// Kernels:
+//   spmv_tile_kernel    persistent CTAs; one producer warp streams row-aligned
+//                       tiles of (vals, col_idx, row_ptr) into a shared-memory
+//                       ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier),
+//                       NW consumer warps do sub-warp-per-row dot products out of
+//                       shared memory, x gathered through L1 (ld.global.nc),
+//                       warp-shuffle reduction, fused alpha/beta epilogue.
+//   spmv_longrow_kernel rows longer than the tile's row limit: one CTA per row.
+//   spmv_vector_kernel  no-analysis fallback (FAST_SETUP, tiny or misaligned
+//                       inputs): sub-warp per row straight from global memory.
+//   spmv_transpose_kernel  T/H modes: y pre-scaled, atomicAdd scatter.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+namespace b200sp {
+
+// ---------------------------------------------------------------------------
+// error string + launch counter + device props
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64];
+  static std::once_flag once;
+  std::call_once(once, [] { memset(cached, 0, sizeof(cached)); });
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---------------------------------------------------------------------------
+// y = beta*y (beta == 0 writes exact zeros without reading y)
+// ---------------------------------------------------------------------------
+template <typename S>
+__global__ void scale_kernel(int64_t n, S beta, S* __restrict__ y) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (beta == S(0)) {
+    for (; i < n; i += stride) y[i] = S(0);
+  } else {
+    for (; i < n; i += stride) y[i] = beta * y[i];
+  }
+}
+
+template <typename S>
+static int launch_scale(cudaStream_t st, int64_t n, S beta, S* y) {
+  if (n <= 0) return B200SP_OK;
+  if (beta == S(1)) return B200SP_OK;
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
+  scale_kernel<S><<<blocks, 256, 0, st>>>(n, beta, y);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sub-warp reduction: sum over the LPR lanes that share a row
+// ---------------------------------------------------------------------------
+template <int LPR, typename S>
+__device__ __forceinline__ S subwarp_sum(S v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += shfl_xor(v, o);
+  return v;
+}
+
+template <typename S>
+__device__ __forceinline__ void store_y(S* __restrict__ y, int r, S sum, S alpha, S beta) {
+  // reference epilogue (spmv_impl.hpp:124-131): sum *= alpha; y = beta*y + sum
+  sum *= alpha;
+  if (beta == S(0)) y[r] = sum;
+  else y[r] = beta * y[r] + sum;
+}
+
+// ---------------------------------------------------------------------------
+// fallback: sub-warp per row, straight from global memory
+// ---------------------------------------------------------------------------
+template <typename S, int LPR>
+__global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __restrict__ row_ptr,
+                                                          const int* __restrict__ col_idx,
+                                                          const S* __restrict__ vals,
+                                                          const S* __restrict__ x, S* __restrict__ y,
+                                                          S alpha, S beta) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp_global; g * RPW < m; g += nwarps) {
+    const int r = (int)(g * RPW) + sub;
+    int rs = 0, re = 0;
+    if (r < m) {
+      rs = row_ptr[r];
+      re = row_ptr[r + 1];
+    }
+    S sum = S(0);
+    int j = rs + sl;
+    for (; j + 3 * LPR < re; j += 4 * LPR) {
+      const int c0 = ld_stream(col_idx + j), c1 = ld_stream(col_idx + j + LPR);
+      const int c2 = ld_stream(col_idx + j + 2 * LPR), c3 = ld_stream(col_idx + j + 3 * LPR);
+      const S v0 = ld_stream(vals + j), v1 = ld_stream(vals + j + LPR);
+      const S v2 = ld_stream(vals + j + 2 * LPR), v3 = ld_stream(vals + j + 3 * LPR);
+      const S x0 = ldg(x + c0), x1 = ldg(x + c1), x2 = ldg(x + c2), x3 = ldg(x + c3);
+      sum += v0 * x0;
+      sum += v1 * x1;
+      sum += v2 * x2;
+      sum += v3 * x3;
+    }
+    for (; j < re; j += LPR) sum += ld_stream(vals + j) * ldg(x + ld_stream(col_idx + j));
+    sum = subwarp_sum<LPR>(sum);
+    if (r < m && sl == 0) store_y(y, r, sum, alpha, beta);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// long rows: one CTA per row taken from a device-side list
+// ---------------------------------------------------------------------------
+template <typename S>
+__global__ void __launch_bounds__(256) spmv_longrow_kernel(const int* __restrict__ long_rows,
+                                                           const int* __restrict__ n_long_ptr,
+                                                           const int* __restrict__ row_ptr,
+                                                           const int* __restrict__ col_idx,
+                                                           const S* __restrict__ vals,
+                                                           const S* __restrict__ x, S* __restrict__ y,
+                                                           S alpha, S beta) {
+  __shared__ S warp_part[8];
+  const int n_long = *n_long_ptr;
+  for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
+    const int r = long_rows[i];
+    const int rs = row_ptr[r], re = row_ptr[r + 1];
+    S sum = S(0);
+    for (int j = rs + threadIdx.x; j < re; j += 256)
+      sum += ld_stream(vals + j) * ldg(x + ld_stream(col_idx + j));
+    sum = subwarp_sum<32>(sum);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      S t = S(0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += warp_part[w];
+      store_y(y, r, t, alpha, beta);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// transpose modes: y (pre-scaled) += alpha * A^T x, atomics like the reference
+// ---------------------------------------------------------------------------
+template <typename S, int LPR>
+__global__ void __launch_bounds__(256) spmv_transpose_kernel(int m, const int* __restrict__ row_ptr,
+                                                             const int* __restrict__ col_idx,
+                                                             const S* __restrict__ vals,
+                                                             const S* __restrict__ x, S* __restrict__ y,
+                                                             S alpha) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = warp_global; g * RPW < m; g += nwarps) {
+    const int r = (int)(g * RPW) + sub;
+    if (r >= m) continue;
+    const int rs = row_ptr[r], re = row_ptr[r + 1];
+    const S xv = alpha * x[r];  // serial reference order: x_val = alpha*x[i] (spmv_impl.hpp:426)
+    for (int j = rs + sl; j < re; j += LPR) atomicAdd(&y[ld_stream(col_idx + j)], ld_stream(vals + j) * xv);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tile analysis.  Tile b owns the rows whose first entry lies in
+// [b*T, (b+1)*T); descriptor = {r0, r1, s = row_ptr[r0], e = staged end}.
+// A row longer than LMAX is always the last row of its tile; it is appended
+// to long_rows and skipped by the tile kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_rows(const int* __restrict__ row_ptr, int m, int64_t v) {
+  // first r in [0, m) with row_ptr[r] >= v, else m
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((int64_t)row_ptr[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void build_tiles_kernel(int m, const int* __restrict__ row_ptr, int n_tiles, int T, int CAP,
+                                   int LMAX, int4* __restrict__ tiles, int* __restrict__ long_rows,
+                                   int* __restrict__ n_long) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_tiles) return;
+  const int r0 = lower_bound_rows(row_ptr, m, (int64_t)b * T);
+  const int r1 = lower_bound_rows(row_ptr, m, (int64_t)(b + 1) * T);
+  int s = 0, e = 0;
+  if (r1 > r0) {
+    s = row_ptr[r0];
+    e = row_ptr[r1];
+    const int last_len = e - row_ptr[r1 - 1];
+    if (last_len > LMAX) long_rows[atomicAdd(n_long, 1)] = r1 - 1;
+    const int cap_end = (s & ~3) + CAP - 4;
+    if (e > cap_end) e = cap_end;  // only a long last row can be cut
+  }
+  tiles[b] = make_int4(r0, r1, s, e);
+}
+
+// ---------------------------------------------------------------------------
+// the TMA-tiled kernel
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t dmin64(int64_t a, int64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ int64_t dmax64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+template <typename S, int CAP, int STAGES>
+struct TileSmem {
+  static constexpr int RCAP = CAP / 2;  // staged row_ptr entries per tile
+  alignas(128) S vals[STAGES][CAP];
+  alignas(128) int cols[STAGES][CAP];
+  alignas(128) int rows[STAGES][RCAP];
+  int4 desc[STAGES];
+  alignas(8) uint64_t full[STAGES];
+  alignas(8) uint64_t empty[STAGES];
+};
+
+template <typename S, int LPR, int NW, int STAGES, int CAP>
+__global__ void __launch_bounds__((NW + 1) * 32)
+    spmv_tile_kernel(int m, int64_t nnz, int n_tiles, int LMAX, const int4* __restrict__ tiles,
+                     const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                     const S* __restrict__ vals, const S* __restrict__ x, S* __restrict__ y, S alpha,
+                     S beta) {
+  using Smem = TileSmem<S, CAP, STAGES>;
+  constexpr int RCAP = Smem::RCAP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);    // producer's arrive.expect_tx (+ TMA byte count)
+      mbar_init(&sm.empty[s], NW);  // one arrive per consumer warp
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ------------------------- producer warp ------------------------------
+    const uint64_t pol = l2_policy_evict_first();
+    const int64_t nnz_al = nnz & ~(int64_t)3;           // bulk copies stay below this entry
+    const int rp_al_end = (m + 1) & ~3;                 // ... and below this row_ptr entry
+    int4 mine = make_int4(0, 0, 0, 0);
+    for (int it = 0;; ++it) {
+      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+      if (tile >= n_tiles) break;
+      if ((it & 31) == 0) {
+        const int64_t t = blockIdx.x + (int64_t)(it + lane) * gridDim.x;
+        if (t < n_tiles) mine = tiles[t];
+      }
+      int4 d;
+      d.x = __shfl_sync(0xffffffffu, mine.x, it & 31);
+      d.y = __shfl_sync(0xffffffffu, mine.y, it & 31);
+      d.z = __shfl_sync(0xffffffffu, mine.z, it & 31);
+      d.w = __shfl_sync(0xffffffffu, mine.w, it & 31);
+      const int stage = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&sm.empty[stage], ph ^ 1u);
+
+      const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
+      S* sv = sm.vals[stage];
+      int* sc = sm.cols[stage];
+      int* sr = sm.rows[stage];
+      // entries [s_al, e) -> smem[0 ..); bulk part [s_al, bulk_end), tail by plain loads
+      const int s_al = s & ~3;
+      const int e_up = (e + 3) & ~3;
+      const int bulk_end = (int)dmin64(e_up, nnz_al);
+      const int nb = (r1 > r0 && bulk_end > s_al) ? bulk_end - s_al : 0;
+      if (r1 > r0 && (int64_t)e > nnz_al) {
+        const int t0 = (int)dmax64(s_al, nnz_al);
+        for (int i = t0 + lane; i < e; i += 32) {
+          sv[i - s_al] = vals[i];
+          sc[i - s_al] = col_idx[i];
+        }
+      }
+      // row_ptr[r0_al .. r1] -> rows[0 ..], at most RCAP entries
+      const int r0_al = r0 & ~3;
+      int nrp = 0;
+      if (r1 > r0) {
+        const int want_end = min(r1 + 1, r0_al + RCAP);  // exclusive
+        const int want_up = (want_end + 3) & ~3;
+        const int rbulk_end = min(min(want_up, r0_al + RCAP), rp_al_end);
+        nrp = rbulk_end > r0_al ? rbulk_end - r0_al : 0;
+        if (want_end > rp_al_end) {
+          const int t0 = max(r0_al, rp_al_end);
+          for (int i = t0 + lane; i < want_end; i += 32) sr[i - r0_al] = row_ptr[i];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        sm.desc[stage] = d;
+        mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(nb * (sizeof(S) + 4) + nrp * 4));
+        if (nb > 0) {
+          bulk_g2s(sv, vals + s_al, (uint32_t)(nb * sizeof(S)), &sm.full[stage], pol);
+          bulk_g2s(sc, col_idx + s_al, (uint32_t)(nb * 4), &sm.full[stage], pol);
+        }
+        if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------- consumer warps -----------------------------
+    constexpr int RPW = 32 / LPR;
+    const int sub = lane / LPR, sl = lane % LPR;
+    for (int it = 0;; ++it) {
+      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+      if (tile >= n_tiles) break;
+      const int stage = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&sm.full[stage], ph);
+      const int4 d = sm.desc[stage];
+      const int r0 = d.x, r1 = d.y;
+      const int s_al = d.z & ~3;
+      const int r0_al = r0 & ~3;
+      const S* sv = sm.vals[stage];
+      const int* sc = sm.cols[stage];
+      const int* sr = sm.rows[stage];
+      // absolute row groups of RPW rows are dealt round-robin to the warps
+      const int g_first = r0 / RPW;
+      int g = g_first + ((warp - g_first % NW) + NW) % NW;
+      for (; g * RPW < r1; g += NW) {
+        const int r = g * RPW + sub;
+        const bool valid = (r >= r0) && (r < r1);
+        int rs = 0, re = 0;
+        if (valid) {
+          const int o = r - r0_al;
+          if (o + 1 < RCAP) {
+            rs = sr[o];
+            re = sr[o + 1];
+          } else {
+            rs = row_ptr[r];
+            re = row_ptr[r + 1];
+          }
+        }
+        const bool is_long = (re - rs) > LMAX;
+        if (is_long) re = rs;
+        S sum = S(0);
+        int j = rs + sl - s_al;
+        const int jend = re - s_al;
+        for (; j + 3 * LPR < jend; j += 4 * LPR) {
+          const int c0 = sc[j], c1 = sc[j + LPR], c2 = sc[j + 2 * LPR], c3 = sc[j + 3 * LPR];
+          const S x0 = ldg(x + c0), x1 = ldg(x + c1), x2 = ldg(x + c2), x3 = ldg(x + c3);
+          sum += sv[j] * x0;
+          sum += sv[j + LPR] * x1;
+          sum += sv[j + 2 * LPR] * x2;
+          sum += sv[j + 3 * LPR] * x3;
+        }
+        for (; j < jend; j += LPR) sum += sv[j] * ldg(x + sc[j]);
+        sum = subwarp_sum<LPR>(sum);
+        if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct TileCfg {
+  int cap, stages, nw;
+};
+static const TileCfg kCfgs[] = {
+    {2048, 4, 8},   // 0: 100 KB / CTA (f64) -> 2 CTAs per SM
+    {4096, 4, 16},  // 1: 200 KB / CTA -> 1 CTA per SM
+    {4096, 3, 8},   // 2: 150 KB
+    {1024, 6, 8},   // 3:  75 KB -> 3 CTAs per SM
+    {2048, 3, 16},  // 4:  75 KB -> 3 CTAs per SM
+};
+static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
+
+}  // namespace b200sp
+
+using namespace b200sp;
+
+struct b200sp_spmv_plan {
+  int algo = B200SP_SPMV_DEFAULT;
+  // tuning overrides (-1 = auto)
+  int cfg = -1, lpr = -1, ctas_per_sm = -1;
+  // cache key of the analysed matrix
+  const int* key_row_ptr = nullptr;
+  int key_m = -1, key_n = -1;
+  int64_t key_nnz = -1;
+  int key_cfg = -1;
+  // analysis products (device)
+  int4* tiles = nullptr;
+  int n_tiles = 0;
+  int T = 0, LMAX = 0;
+  int* long_rows = nullptr;
+  int* n_long = nullptr;       // device counter
+  int* n_long_host = nullptr;  // pinned mirror, valid once n_long_event completed
+  cudaEvent_t n_long_event = nullptr;
+  bool n_long_known = false;
+  int long_cap = 0;
+  // host-vector staging (b200sp_spmv_hostvec_*)
+  void* dx = nullptr;
+  void* dy = nullptr;
+  size_t dx_bytes = 0, dy_bytes = 0;
+  // rank-2 scratch (spmm.cu)
+  void* xt = nullptr;
+  void* yt = nullptr;
+  size_t xt_bytes = 0, yt_bytes = 0;
+  char last_kernel[96] = "none";
+};
+
+namespace b200sp {
+
+static void plan_release_analysis(b200sp_spmv_plan* p, cudaStream_t st) {
+  if (p->tiles) cudaFreeAsync(p->tiles, st);
+  if (p->long_rows) cudaFreeAsync(p->long_rows, st);
+  if (p->n_long) cudaFreeAsync(p->n_long, st);
+  p->tiles = nullptr;
+  p->long_rows = nullptr;
+  p->n_long = nullptr;
+  p->n_tiles = 0;
+  p->n_long_known = false;
+  p->key_row_ptr = nullptr;
+}
+
+template <typename S>
+static int plan_analyse(b200sp_spmv_plan* p, cudaStream_t st, int cfg, int m, int n, int64_t nnz,
+                        const int* row_ptr) {
+  if (p->key_row_ptr == row_ptr && p->key_m == m && p->key_n == n && p->key_nnz == nnz &&
+      p->key_cfg == cfg && p->tiles)
+    return B200SP_OK;
+  plan_release_analysis(p, st);
+  const TileCfg c = kCfgs[cfg];
+  p->LMAX = c.cap / 4;
+  p->T = c.cap - p->LMAX - 8;
+  p->n_tiles = (int)(nnz / p->T) + 1;
+  // at most one long row per tile
+  p->long_cap = p->n_tiles;
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->tiles, sizeof(int4) * (size_t)p->n_tiles, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->long_rows, sizeof(int) * (size_t)p->long_cap, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->n_long, sizeof(int), st));
+  B200SP_CUDA_TRY(cudaMemsetAsync(p->n_long, 0, sizeof(int), st));
+  build_tiles_kernel<<<(p->n_tiles + 255) / 256, 256, 0, st>>>(m, row_ptr, p->n_tiles, p->T, c.cap, p->LMAX,
+                                                               p->tiles, p->long_rows, p->n_long);
+  B200SP_LAUNCH_CHECK();
+  if (!p->n_long_host) B200SP_CUDA_TRY(cudaMallocHost((void**)&p->n_long_host, sizeof(int)));
+  if (!p->n_long_event) B200SP_CUDA_TRY(cudaEventCreateWithFlags(&p->n_long_event, cudaEventDisableTiming));
+  *p->n_long_host = -1;
+  B200SP_CUDA_TRY(cudaMemcpyAsync(p->n_long_host, p->n_long, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaEventRecord(p->n_long_event, st));
+  p->n_long_known = false;
+  p->key_row_ptr = row_ptr;
+  p->key_m = m;
+  p->key_n = n;
+  p->key_nnz = nnz;
+  p->key_cfg = cfg;
+  return B200SP_OK;
+}
+
+// rank-2 scratch + bookkeeping used by spmm.cu
+int plan_mv_scratch(b200sp_spmv_plan* p, cudaStream_t st, size_t xt_bytes, size_t yt_bytes, void** xt, void** yt) {
+  if (xt_bytes > p->xt_bytes) {
+    if (p->xt) cudaFreeAsync(p->xt, st);
+    p->xt = nullptr;
+    p->xt_bytes = 0;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->xt, xt_bytes, st));
+    p->xt_bytes = xt_bytes;
+  }
+  if (yt_bytes > p->yt_bytes) {
+    if (p->yt) cudaFreeAsync(p->yt, st);
+    p->yt = nullptr;
+    p->yt_bytes = 0;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->yt, yt_bytes, st));
+    p->yt_bytes = yt_bytes;
+  }
+  *xt = p->xt;
+  *yt = p->yt;
+  return B200SP_OK;
+}
+void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
+  if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "%s", s);
+}
+
+static int pick_lpr(int m, int64_t nnz) {
+  const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 24.0) return 8;
+  if (avg <= 96.0) return 16;
+  return 32;
+}
+
+template <typename S, int LPR, int NW, int STAGES, int CAP>
+static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr,
+                       const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta) {
+  using Smem = TileSmem<S, CAP, STAGES>;
+  auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP>;
+  const size_t smem = sizeof(Smem) + 128;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.store(true, std::memory_order_release);
+  }
+  static std::atomic<int> occ{0};
+  if (occ.load() == 0) {
+    int o = 0;
+    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, (NW + 1) * 32, smem));
+    occ.store(o > 0 ? o : 1);
+  }
+  int per_sm = p->ctas_per_sm;
+  if (per_sm <= 0) per_sm = occ.load();
+  int grid = std::min(p->n_tiles, sm_count() * per_sm);
+  if (grid < 1) grid = 1;
+  kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, p->n_tiles, p->LMAX, p->tiles, row_ptr, col_idx, vals, x, y,
+                                          alpha, beta);
+  B200SP_LAUNCH_CHECK();
+  snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d>grid=%d",
+           sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, grid);
+  return B200SP_OK;
+}
+
+template <typename S, int LPR>
+static int launch_tile_cfg(b200sp_spmv_plan* p, int cfg, cudaStream_t st, int m, int64_t nnz,
+                           const int* row_ptr, const int* col_idx, const S* vals, const S* x, S* y,
+                           S alpha, S beta) {
+  switch (cfg) {
+    case 0: return launch_tile<S, LPR, 8, 4, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 1: return launch_tile<S, LPR, 16, 4, 4096>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 2: return launch_tile<S, LPR, 8, 3, 4096>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 3: return launch_tile<S, LPR, 8, 6, 1024>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 4: return launch_tile<S, LPR, 16, 3, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+  }
+  set_error("bad tile cfg %d", cfg);
+  return B200SP_ERR_INVALID_ARGUMENT;
+}
+
+template <typename S>
+static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, const int* row_ptr,
+                         const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta) {
+  const int rpw = 32 / lpr;
+  const int64_t warps = ((int64_t)m + rpw - 1) / rpw;
+  int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16);
+  if (blocks < 1) blocks = 1;
+#define B200SP_VEC(L)                                                                              \
+  case L:                                                                                          \
+    spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta); \
+    break;
+  switch (lpr) {
+    B200SP_VEC(2)
+    B200SP_VEC(4)
+    B200SP_VEC(8)
+    B200SP_VEC(16)
+    B200SP_VEC(32)
+    default: set_error("bad lanes-per-row %d", lpr); return B200SP_ERR_INVALID_ARGUMENT;
+  }
+#undef B200SP_VEC
+  B200SP_LAUNCH_CHECK();
+  if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "vector<%s,LPR=%d>grid=%d", sizeof(S) == 8 ? "f64" : "f32", lpr, blocks);
+  return B200SP_OK;
+}
+
+template <typename S>
+static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int n, int64_t nnz, S alpha,
+                     const int* row_ptr, const int* col_idx, const S* vals, const S* x, S beta, S* y) {
+  B200SP_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "spmv: negative dimension (m=%d n=%d nnz=%lld)", m, n,
+                 (long long)nnz);
+  B200SP_REQUIRE(nnz <= INT32_MAX, "spmv: nnz=%lld exceeds int32 offsets", (long long)nnz);
+  bool trans;
+  switch (mode) {
+    case 'N': case 'n': case 'C': case 'c': trans = false; break;
+    case 'T': case 't': case 'H': case 'h': trans = true; break;
+    default:
+      // same condition the reference throws on (spmv_impl.hpp:537-541)
+      set_error("Invalid transpose mode %c for KokkosSparse::spmv()", mode);
+      return B200SP_ERR_INVALID_ARGUMENT;
+  }
+  const int ylen = trans ? n : m;
+  // alpha*op(A) == 0: y = beta*y  (KokkosSparse_spmv.hpp:145-154)
+  if (alpha == S(0) || m == 0 || n == 0 || nnz == 0) {
+    if (ylen > 0) B200SP_REQUIRE(y != nullptr, "spmv: y is null");
+    if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "scale");
+    return launch_scale<S>(st, ylen, beta, y);
+  }
+  B200SP_REQUIRE(row_ptr && col_idx && vals && x && y, "spmv: null pointer argument");
+
+  const int lpr_auto = pick_lpr(m, nnz);
+  if (trans) {
+    int rc = launch_scale<S>(st, ylen, beta, y);
+    if (rc) return rc;
+    const int lpr = lpr_auto;
+    const int rpw = 32 / lpr;
+    const int64_t warps = ((int64_t)m + rpw - 1) / rpw;
+    int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16);
+    if (blocks < 1) blocks = 1;
+    switch (lpr) {
+      case 2: spmv_transpose_kernel<S, 2><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha); break;
+      case 4: spmv_transpose_kernel<S, 4><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha); break;
+      case 8: spmv_transpose_kernel<S, 8><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha); break;
+      case 16: spmv_transpose_kernel<S, 16><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha); break;
+      default: spmv_transpose_kernel<S, 32><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha); break;
+    }
+    B200SP_LAUNCH_CHECK();
+    if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "transpose<%s,LPR=%d>", sizeof(S) == 8 ? "f64" : "f32", lpr);
+    return B200SP_OK;
+  }
+
+  const bool aligned = (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0;
+  const bool use_tile = p && p->algo != B200SP_SPMV_FAST_SETUP && aligned &&
+                        (nnz >= 32768 || p->cfg >= 0);
+  if (!use_tile) return launch_vector<S>(p, st, (p && p->lpr > 0) ? p->lpr : lpr_auto, m, row_ptr, col_idx, vals, x, y, alpha, beta);
+
+  const int cfg = p->cfg >= 0 ? p->cfg : 0;
+  int rc = plan_analyse<S>(p, st, cfg, m, n, nnz, row_ptr);
+  if (rc) return rc;
+  const int lpr = p->lpr > 0 ? p->lpr : lpr_auto;
+  switch (lpr) {
+    case 2: rc = launch_tile_cfg<S, 2>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+    case 4: rc = launch_tile_cfg<S, 4>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+    case 8: rc = launch_tile_cfg<S, 8>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+    case 16: rc = launch_tile_cfg<S, 16>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+    case 32: rc = launch_tile_cfg<S, 32>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+    default: set_error("bad lanes-per-row %d", lpr); return B200SP_ERR_INVALID_ARGUMENT;
+  }
+  if (rc) return rc;
+  // long rows: skip the launch once the (asynchronously fetched) count is known to be 0
+  if (!p->n_long_known && cudaEventQuery(p->n_long_event) == cudaSuccess) p->n_long_known = true;
+  if (!(p->n_long_known && *p->n_long_host == 0)) {
+    int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
+    spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta);
+    B200SP_LAUNCH_CHECK();
+  }
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* b200sp_last_error_string(void) { return b200sp::g_err; }
+int b200sp_version(void) { return 100; }
+int64_t b200sp_launch_count(void) { return (int64_t)b200sp::g_launches.load(); }
+
+int b200sp_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int b200sp_spmv_plan_create(b200sp_spmv_plan** plan, int algo) {
+  B200SP_REQUIRE(plan != nullptr, "spmv_plan_create: null output pointer");
+  B200SP_REQUIRE(algo >= 0 && algo <= 2, "spmv_plan_create: unknown algorithm %d", algo);
+  b200sp_spmv_plan* p = new (std::nothrow) b200sp_spmv_plan();
+  if (!p) {
+    set_error("spmv_plan_create: out of host memory");
+    return B200SP_ERR_ALLOC;
+  }
+  p->algo = algo;
+  *plan = p;
+  return B200SP_OK;
+}
+
+int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
+  if (!p) return B200SP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  plan_release_analysis(p, st);
+  if (p->dx) cudaFreeAsync(p->dx, st);
+  if (p->dy) cudaFreeAsync(p->dy, st);
+  if (p->xt) cudaFreeAsync(p->xt, st);
+  if (p->yt) cudaFreeAsync(p->yt, st);
+  if (p->n_long_event) {
+    cudaEventSynchronize(p->n_long_event);  // the pinned mirror must not be written after it is freed
+    cudaEventDestroy(p->n_long_event);
+  }
+  if (p->n_long_host) cudaFreeHost(p->n_long_host);
+  delete p;
+  return B200SP_OK;
+}
+
+int b200sp_spmv_plan_tune(b200sp_spmv_plan* p, int cfg, int lanes_per_row, int ctas_per_sm) {
+  B200SP_REQUIRE(p != nullptr, "spmv_plan_tune: null plan");
+  B200SP_REQUIRE(cfg >= -1 && cfg < kNumCfgs, "spmv_plan_tune: cfg %d out of range", cfg);
+  B200SP_REQUIRE(lanes_per_row == -1 || lanes_per_row == 2 || lanes_per_row == 4 || lanes_per_row == 8 ||
+                     lanes_per_row == 16 || lanes_per_row == 32,
+                 "spmv_plan_tune: lanes_per_row %d not in {2,4,8,16,32}", lanes_per_row);
+  B200SP_REQUIRE(ctas_per_sm >= -1 && ctas_per_sm <= 8, "spmv_plan_tune: ctas_per_sm %d out of range", ctas_per_sm);
+  p->cfg = cfg;
+  p->lpr = lanes_per_row;
+  p->ctas_per_sm = ctas_per_sm;
+  return B200SP_OK;
+}
+
+const char* b200sp_spmv_last_kernel(const b200sp_spmv_plan* p) { return p ? p->last_kernel : "none"; }
+
+int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, double alpha,
+                        const int* row_ptr, const int* col_idx, const double* vals, const double* x, double beta,
+                        double* y) {
+  return spmv_impl<double>(plan, (cudaStream_t)stream, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, x, beta, y);
+}
+
+int b200sp_spmv_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, float alpha,
+                        const int* row_ptr, const int* col_idx, const float* vals, const float* x, float beta,
+                        float* y) {
+  return spmv_impl<float>(plan, (cudaStream_t)stream, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, x, beta, y);
+}
+
+int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, int m, int n, int64_t nnz,
+                                double alpha, const int* row_ptr, const int* col_idx, const double* vals,
+                                const double* x_host, double beta, double* y_host) {
+  B200SP_REQUIRE(p != nullptr, "spmv_hostvec: a plan is required");
+  B200SP_REQUIRE(m >= 0 && n >= 0, "spmv_hostvec: negative dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool trans = (mode == 'T' || mode == 't' || mode == 'H' || mode == 'h');
+  const size_t xb = sizeof(double) * (size_t)(trans ? m : n);
+  const size_t yb = sizeof(double) * (size_t)(trans ? n : m);
+  if (xb > p->dx_bytes) {
+    if (p->dx) cudaFreeAsync(p->dx, st);
+    p->dx = nullptr;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->dx, xb, st));
+    p->dx_bytes = xb;
+  }
+  if (yb > p->dy_bytes) {
+    if (p->dy) cudaFreeAsync(p->dy, st);
+    p->dy = nullptr;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->dy, yb, st));
+    p->dy_bytes = yb;
+  }
+  if (xb) B200SP_CUDA_TRY(cudaMemcpyAsync(p->dx, x_host, xb, cudaMemcpyHostToDevice, st));
+  if (beta != 0.0 && yb) B200SP_CUDA_TRY(cudaMemcpyAsync(p->dy, y_host, yb, cudaMemcpyHostToDevice, st));
+  int rc = spmv_impl<double>(p, st, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, (const double*)p->dx, beta,
+                             (double*)p->dy);
+  if (rc) return rc;
+  if (yb) B200SP_CUDA_TRY(cudaMemcpyAsync(y_host, p->dy, yb, cudaMemcpyDeviceToHost, st));
+  return B200SP_OK;
+}
+
+}  // extern "C"

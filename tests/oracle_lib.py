@@ -1,0 +1,168 @@
+"""ctypes front end of oracle/libkkoracle.so (+ _fma, + _ref/libkkref.so).
+TEST INFRASTRUCTURE: the oracle is the checker, never the thing shipped."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+
+i32, i64, f32, f64, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+def _p(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+class Oracle:
+    def __init__(self, fma=False):
+        name = "libkkoracle_fma.so" if fma else "libkkoracle.so"
+        path = os.path.join(ODIR, name)
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle`")
+        L = self.lib = C.CDLL(path)
+        for sfx, ft in (("f64", f64), ("f32", f32)):
+            getattr(L, f"okk_spmv_serial_{sfx}").argtypes = [i32, vp, vp, vp, vp, vp, ft, ft]
+            getattr(L, f"okk_spmv_functor_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, ft, ft, i32]
+            getattr(L, f"okk_spmv_test_{sfx}").argtypes = [C.c_char, i32, i32, vp, vp, vp, vp, vp, ft, ft]
+            getattr(L, f"okk_spmv_transpose_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, ft, ft]
+            getattr(L, f"okk_spmv_mv_{sfx}").argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft, i32]
+            getattr(L, f"okk_spmv_mv_transpose_{sfx}").argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
+            getattr(L, f"okk_spgemm_numeric_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+            getattr(L, f"okk_sort_crs_{sfx}").argtypes = [i32, vp, vp, vp]
+        L.okk_spmv_serial_f32mat_f64vec.argtypes = [i32, vp, vp, vp, vp, vp, f64, f64]
+        L.okk_spmv_mv_f32mat_f64vec.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f64, f64, i32]
+        L.okk_spgemm_symbolic.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+        L.okk_spgemm_symbolic.restype = i64
+        L.okk_transpose_f64.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.okk_count_rel_mismatch_f64.argtypes = [i64, vp, vp, f64]
+        L.okk_count_rel_mismatch_f64.restype = i64
+        L.okk_mmd_size.argtypes = [i64, i64, i64]
+        L.okk_mmd_size.restype = i64
+        L.okk_mmd_entry.argtypes = [vp, i64, vp, i64, i64, i64]
+        L.okk_mmd_entry.restype = i32
+        L.okk_diagonal_search.argtypes = [vp, i64, vp, i64, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.okk_num_threads.restype = i32
+        self.ref = None
+        rpath = os.path.join(ODIR, "_ref", "libkkref.so")
+        if os.path.exists(rpath):
+            R = self.ref = C.CDLL(rpath)
+            R.kkref_spgemm_symbolic.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]
+            R.kkref_spgemm_symbolic.restype = i64
+            R.kkref_spgemm_numeric_f64.argtypes = [i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]
+
+    @staticmethod
+    def _sfx(a):
+        return "f64" if a.dtype == np.float64 else "f32"
+
+    def num_threads(self):
+        return self.lib.okk_num_threads()
+
+    # ---- SpMV ----
+    def spmv_serial(self, rp, ci, v, x, y, alpha, beta):
+        """O1: Serial path (spmv_impl.hpp:233-305); y updated in place."""
+        m = len(rp) - 1
+        if v.dtype == np.float32 and x.dtype == np.float64:
+            self.lib.okk_spmv_serial_f32mat_f64vec(m, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        else:
+            getattr(self.lib, "okk_spmv_serial_" + self._sfx(v))(m, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        return y
+
+    def spmv_functor(self, rp, ci, v, ncol, x, y, alpha, beta, threads=1):
+        """O2: functor / OpenMP order (spmv_impl.hpp:110-132)."""
+        m = len(rp) - 1
+        getattr(self.lib, "okk_spmv_functor_" + self._sfx(v))(m, ncol, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta, threads)
+        return y
+
+    def spmv_test(self, mode, rp, ci, v, x, y, alpha, beta):
+        """O3: Test::sequential_spmv (Test_Sparse_spmv.hpp:106-166)."""
+        m = len(rp) - 1
+        getattr(self.lib, "okk_spmv_test_" + self._sfx(v))(mode.encode(), m, len(y), _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        return y
+
+    def spmv_transpose(self, rp, ci, v, ncol, x, y, alpha, beta):
+        m = len(rp) - 1
+        getattr(self.lib, "okk_spmv_transpose_" + self._sfx(v))(m, ncol, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        return y
+
+    @staticmethod
+    def _strides(a):
+        es = a.itemsize
+        return a.strides[0] // es, a.strides[1] // es
+
+    def spmv_mv(self, rp, ci, v, ncol, X, Y, alpha, beta, threads=1):
+        m = len(rp) - 1
+        xr, xc = self._strides(X)
+        yr, yc = self._strides(Y)
+        if v.dtype == np.float32 and X.dtype == np.float64:
+            fn = self.lib.okk_spmv_mv_f32mat_f64vec
+        else:
+            fn = getattr(self.lib, "okk_spmv_mv_" + self._sfx(v))
+        fn(m, ncol, X.shape[1], _p(rp), _p(ci), _p(v), _p(X), xr, xc, _p(Y), yr, yc, alpha, beta, threads)
+        return Y
+
+    def spmv_mv_transpose(self, rp, ci, v, ncol, X, Y, alpha, beta):
+        m = len(rp) - 1
+        xr, xc = self._strides(X)
+        yr, yc = self._strides(Y)
+        getattr(self.lib, "okk_spmv_mv_transpose_" + self._sfx(v))(m, ncol, X.shape[1], _p(rp), _p(ci), _p(v), _p(X), xr, xc, _p(Y), yr, yc, alpha, beta)
+        return Y
+
+    # ---- SpGEMM ----
+    def spgemm(self, rpA, ciA, vA, rpB, ciB, vB, k, sort=True):
+        """O6: spgemm_debug_symbolic + numeric (+ sort_crs_matrix)."""
+        m = len(rpA) - 1
+        rpC = np.zeros(m + 1, dtype=np.int32)
+        nnz = self.lib.okk_spgemm_symbolic(m, k, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC))
+        ciC = np.empty(nnz, dtype=np.int32)
+        vC = np.empty(nnz, dtype=vA.dtype)
+        sfx = self._sfx(vA)
+        getattr(self.lib, "okk_spgemm_numeric_" + sfx)(m, k, _p(rpA), _p(ciA), _p(vA), _p(rpB), _p(ciB), _p(vB), _p(rpC), _p(ciC), _p(vC))
+        if sort:
+            getattr(self.lib, "okk_sort_crs_" + sfx)(m, _p(rpC), _p(ciC), _p(vC))
+        return rpC, ciC, vC
+
+    def sort_crs(self, rp, ci, v):
+        getattr(self.lib, "okk_sort_crs_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v))
+
+    def transpose(self, rp, ci, v, ncol):
+        m = len(rp) - 1
+        trp = np.zeros(ncol + 1, dtype=np.int32)
+        tci = np.empty(len(ci), dtype=np.int32)
+        tv = np.empty(len(v), dtype=np.float64)
+        self.lib.okk_transpose_f64(m, ncol, _p(rp), _p(ci), _p(v), _p(trp), _p(tci), _p(tv))
+        return trp, tci, tv
+
+    def rel_mismatch(self, a, b, eps):
+        return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)
+
+    def ref_spgemm(self, rpA, ciA, vA, n, rpB, ciB, vB, k):
+        """The reference's own spgemm_debug_{symbolic,numeric} (oracle/_ref), UNSORTED output."""
+        assert self.ref is not None
+        m = len(rpA) - 1
+        rpC = np.full(m + 1, 123, dtype=np.int32)
+        nnz = self.ref.kkref_spgemm_symbolic(m, n, k, _p(rpA), len(ciA), _p(ciA), _p(rpB), len(ciB), _p(ciB), _p(rpC))
+        ciC = np.empty(nnz, dtype=np.int32)
+        vC = np.empty(nnz, dtype=np.float64)
+        self.ref.kkref_spgemm_numeric_f64(m, n, k, _p(rpA), len(ciA), _p(ciA), _p(vA), _p(rpB), len(ciB), _p(ciB), _p(vB), _p(rpC), nnz, _p(ciC), _p(vC))
+        return rpC, ciC, vC
+
+    # ---- merge matrix ----
+    def mmd_size(self, na, nb, d):
+        return self.lib.okk_mmd_size(na, nb, d)
+
+    def mmd_entries(self, a, b, d):
+        a = np.asarray(a, dtype=np.int64)
+        nb = int(b) if np.isscalar(b) else len(b)
+        bb = None if np.isscalar(b) else np.asarray(b, dtype=np.int64)
+        n = self.lib.okk_mmd_size(len(a), nb, d)
+        return [self.lib.okk_mmd_entry(_p(a), len(a), _p(bb), nb, d, i) for i in range(n)]
+
+    def diagonal_search(self, a, b, d):
+        a = np.asarray(a, dtype=np.int64)
+        nb = int(b) if np.isscalar(b) else len(b)
+        bb = None if np.isscalar(b) else np.asarray(b, dtype=np.int64)
+        ai, bi = i64(0), i64(0)
+        self.lib.okk_diagonal_search(_p(a), len(a), _p(bb), nb, d, C.byref(ai), C.byref(bi))
+        return ai.value, bi.value
