@@ -1,0 +1,68 @@
+"""GPU parity of rank-2 (multivector) SpMV (Test_Sparse_spmv.hpp:465-606,1075-1092)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import kk_matrix, spmv_tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(dev, a, rowmajor):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if not rowmajor:
+        t = t.t().contiguous().t()  # LayoutLeft: stride (1, rows)
+    return t
+
+
+@pytest.mark.parametrize("rows,per,bw,var", [(1000, 3, 200, 10), (1000, 20, 100, 5), (10000, 2, 100, 5), (5000, 30, 400, 20)])
+@pytest.mark.parametrize("nv", [1, 5, 10, 16, 30])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spmm_sweep(cuda, oracle, rows, per, bw, var, nv, dtype):
+    from kokkos_kernels_b200 import sparse as sp
+
+    ncols = rows - 37
+    rp, ci, v = kk_matrix(rows, ncols, rows * per, var, bw, dtype=dtype)
+    A = sp.CrsMatrix(torch.from_numpy(rp).to(cuda), torch.from_numpy(ci).to(cuda), torch.from_numpy(v).to(cuda), ncols)
+    rng = np.random.default_rng(13718)
+    X = rng.random((ncols, nv)).astype(dtype)
+    Y0 = rng.random((rows, nv)).astype(dtype)
+    Xt = rng.random((rows, nv)).astype(dtype)
+    Yt0 = rng.random((ncols, nv)).astype(dtype)
+    eps = np.finfo(dtype).eps
+    h = sp.SPMVHandle()
+    for xrm, yrm in ((True, True), (False, False), (True, False), (False, True)):
+        for alpha, beta in ((1.0, 0.0), (2.5, -1.0), (-1.0, 1.0), (0.0, 2.5), (1.0, 2.5)):
+            tol = 16 * spmv_tolerance(eps, alpha, beta, per + var) + 1e-300
+            Y0n = Y0.copy()
+            if beta == 0.0:
+                Y0n[::19, :] = np.nan
+            Yd = _mk(cuda, Y0n, yrm)
+            sp.spmv(h if (xrm, yrm) != (True, False) else None, "N", alpha, A, _mk(cuda, X, xrm), beta, Yd)
+            exp = oracle.spmv_mv(rp, ci, v, ncols, X, np.where(np.isnan(Y0n), 0, Y0n) if beta == 0 else Y0n.copy(), alpha, beta)
+            got = Yd.cpu().numpy()
+            assert not np.isnan(got).any()
+            assert np.max(np.abs(got - exp)) <= tol, (xrm, yrm, alpha, beta, np.max(np.abs(got - exp)), tol)
+            # transpose
+            Ytd = _mk(cuda, Yt0, yrm)
+            sp.spmv(h, "T", alpha, A, _mk(cuda, Xt, xrm), beta, Ytd)
+            expt = oracle.spmv_mv_transpose(rp, ci, v, ncols, Xt, Yt0.copy(), alpha, beta)
+            assert np.max(np.abs(Ytd.cpu().numpy() - expt)) <= 4 * tol + 1e-300
+
+
+def test_spmm_powerlaw_rows(cuda, oracle):
+    """R-MAT structure (skewed rows), fp32, 16 columns: the config-3 shape at a small scale."""
+    from kokkos_kernels_b200 import matgen, sparse as sp
+
+    rp, ci = matgen.rmat(14, 16)
+    n = len(rp) - 1
+    v = matgen.fill(len(ci), 0, 1, 23, dtype=np.float32)
+    X = matgen.fill(n * 16, -1, 1, 5, dtype=np.float32).reshape(n, 16)
+    A = sp.CrsMatrix(torch.from_numpy(rp).to(cuda), torch.from_numpy(ci).to(cuda), torch.from_numpy(v).to(cuda), n)
+    exp = oracle.spmv_mv(rp, ci, v, n, X, np.zeros((n, 16), dtype=np.float32), 1.0, 0.0)
+    maxrow = int(np.diff(rp).max())
+    for rowmajor in (True, False):
+        Y = _mk(cuda, np.full((n, 16), np.nan, dtype=np.float32), rowmajor)
+        sp.spmv(sp.SPMVHandle(), "N", 1.0, A, _mk(cuda, X, rowmajor), 0.0, Y)
+        err = np.max(np.abs(Y.cpu().numpy() - exp))
+        assert err <= 10 * np.finfo(np.float32).eps * maxrow
