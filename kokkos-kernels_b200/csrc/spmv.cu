@@ -193,8 +193,9 @@ __global__ void __launch_bounds__(256) spmv_transpose_kernel(int m, const int* _
 // ---------------------------------------------------------------------------
 // tile analysis.  Tile b owns the rows whose first entry lies in
 // [b*T, (b+1)*T); descriptor = {r0, r1, s = row_ptr[r0], e = staged end}.
-// A row longer than LMAX is always the last row of its tile; it is appended
-// to long_rows and skipped by the tile kernel.
+// Rows longer than LMAX (found by find_long_rows_kernel) are skipped by the
+// tile kernel and computed by spmv_longrow_kernel; T + LMAX + 8 <= CAP makes
+// every other row fit the stage.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int lower_bound_rows(const int* __restrict__ row_ptr, int m, int64_t v) {
   // first r in [0, m) with row_ptr[r] >= v, else m
@@ -208,8 +209,7 @@ __device__ __forceinline__ int lower_bound_rows(const int* __restrict__ row_ptr,
 }
 
 __global__ void build_tiles_kernel(int m, const int* __restrict__ row_ptr, int n_tiles, int T, int CAP,
-                                   int LMAX, int4* __restrict__ tiles, int* __restrict__ long_rows,
-                                   int* __restrict__ n_long) {
+                                   int4* __restrict__ tiles) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_tiles) return;
   const int r0 = lower_bound_rows(row_ptr, m, (int64_t)b * T);
@@ -218,12 +218,18 @@ __global__ void build_tiles_kernel(int m, const int* __restrict__ row_ptr, int n
   if (r1 > r0) {
     s = row_ptr[r0];
     e = row_ptr[r1];
-    const int last_len = e - row_ptr[r1 - 1];
-    if (last_len > LMAX) long_rows[atomicAdd(n_long, 1)] = r1 - 1;
+    // every row but the last ends before (b+1)*T; only a long (> LMAX) last row can exceed the stage
     const int cap_end = (s & ~3) + CAP - 4;
-    if (e > cap_end) e = cap_end;  // only a long last row can be cut
+    if (e > cap_end) e = cap_end;
   }
   tiles[b] = make_int4(r0, r1, s, e);
+}
+
+// rows longer than LMAX are skipped by the tile kernel and handled by spmv_longrow_kernel
+__global__ void find_long_rows_kernel(int m, const int* __restrict__ row_ptr, int LMAX, int* __restrict__ long_rows,
+                                      int* __restrict__ n_long) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x)
+    if (row_ptr[r + 1] - row_ptr[r] > LMAX) long_rows[atomicAdd(n_long, 1)] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -461,14 +467,16 @@ static int plan_analyse(b200sp_spmv_plan* p, cudaStream_t st, int cfg, int m, in
   p->LMAX = c.cap / 4;
   p->T = c.cap - p->LMAX - 8;
   p->n_tiles = (int)(nnz / p->T) + 1;
-  // at most one long row per tile
-  p->long_cap = p->n_tiles;
+  // every long row holds more than LMAX entries
+  p->long_cap = (int)(nnz / (p->LMAX + 1)) + 1;
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->tiles, sizeof(int4) * (size_t)p->n_tiles, st));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->long_rows, sizeof(int) * (size_t)p->long_cap, st));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->n_long, sizeof(int), st));
   B200SP_CUDA_TRY(cudaMemsetAsync(p->n_long, 0, sizeof(int), st));
-  build_tiles_kernel<<<(p->n_tiles + 255) / 256, 256, 0, st>>>(m, row_ptr, p->n_tiles, p->T, c.cap, p->LMAX,
-                                                               p->tiles, p->long_rows, p->n_long);
+  build_tiles_kernel<<<(p->n_tiles + 255) / 256, 256, 0, st>>>(m, row_ptr, p->n_tiles, p->T, c.cap, p->tiles);
+  B200SP_LAUNCH_CHECK();
+  find_long_rows_kernel<<<std::max(1, std::min((m + 255) / 256, sm_count() * 8)), 256, 0, st>>>(m, row_ptr, p->LMAX,
+                                                                                                p->long_rows, p->n_long);
   B200SP_LAUNCH_CHECK();
   if (!p->n_long_host) B200SP_CUDA_TRY(cudaMallocHost((void**)&p->n_long_host, sizeof(int)));
   if (!p->n_long_event) B200SP_CUDA_TRY(cudaEventCreateWithFlags(&p->n_long_event, cudaEventDisableTiming));
@@ -510,10 +518,11 @@ void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
 
 static int pick_lpr(int m, int64_t nnz) {
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
-  if (avg <= 3.0) return 2;
-  if (avg <= 6.0) return 4;
-  if (avg <= 24.0) return 8;
-  if (avg <= 96.0) return 16;
+  // measured on B200 (profiles/r01_tune_spmv.csv): fewer lanes per row win until rows get long
+  if (avg <= 4.0) return 2;
+  if (avg <= 12.0) return 4;
+  if (avg <= 128.0) return 8;
+  if (avg <= 512.0) return 16;
   return 32;
 }
 
@@ -636,7 +645,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
                         (nnz >= 32768 || p->cfg >= 0);
   if (!use_tile) return launch_vector<S>(p, st, (p && p->lpr > 0) ? p->lpr : lpr_auto, m, row_ptr, col_idx, vals, x, y, alpha, beta);
 
-  const int cfg = p->cfg >= 0 ? p->cfg : 0;
+  const int cfg = p->cfg >= 0 ? p->cfg : 4;  // CAP=2048, 3 stages, 16 consumer warps, 2 CTAs/SM
   int rc = plan_analyse<S>(p, st, cfg, m, n, nnz, row_ptr);
   if (rc) return rc;
   const int lpr = p->lpr > 0 ? p->lpr : lpr_auto;

@@ -131,9 +131,9 @@ def test_unsorted_inputs_and_wide_rows(cuda, oracle):
     from kokkos_kernels_b200 import matgen, sparse as sp
 
     rng = np.random.default_rng(3)
-    m = k = n = 6000
+    m = k = n = 20000
     lens = rng.integers(0, 12, size=m)
-    lens[:3] = [3000, 1200, 400]        # very wide product rows
+    lens[:3] = [6000, 1200, 400]        # very wide product rows (row 0 exceeds every shared-memory bin)
     rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     ci = np.concatenate([rng.choice(k, size=l, replace=False) for l in lens]).astype(np.int32)
     v = rng.uniform(1, 50, len(ci))

@@ -1,0 +1,80 @@
+"""world_size-2 gloo test of the multi-GPU host logic (row-block shards + all-gather of y).
+The local SpMV is played by the oracle here -- this test covers partitioning, rebasing and the
+collective placement, not the CUDA kernel (that is tests/test_gpu_*.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, ragged, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib
+    from kokkos_kernels_b200 import matgen, partition
+
+    orc = oracle_lib.Oracle()
+    nx, ny, nz, nd = 9, 8, 10, 2
+    n = nx * ny * nz * nd
+    if ragged:
+        rp_full, ci_full, va_full = matgen.lap27(nx, ny, nz, ndof=nd, noise=0.5)
+        bounds = partition.balanced_row_blocks(rp_full, world)
+        rp, ci, va = partition.extract_shard(rp_full, ci_full, va_full, bounds[rank], bounds[rank + 1])
+    else:
+        bounds = partition.equal_row_blocks(n, world)
+        rp, ci, va = matgen.lap27(nx, ny, nz, ndof=nd, row_begin=bounds[rank], row_end=bounds[rank + 1], noise=0.5)
+    x = matgen.fill(n, -1, 1, 1)
+    for _ in range(3):  # power-iteration style: x <- A x, all-gather forms the next x
+        y = np.zeros(bounds[rank + 1] - bounds[rank])
+        orc.spmv_serial(rp, ci, va, x, y, 1.0, 0.0)
+        xn = torch.empty(n, dtype=torch.float64)
+        partition.allgather_y(torch.from_numpy(y), xn, bounds, rank)
+        x = xn.numpy().copy()
+    if rank == 0:
+        q.put(x)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_row_partition_allgather_matches_single_process(oracle, ragged):
+    from kokkos_kernels_b200 import matgen
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29511 + int(ragged)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ragged, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rp, ci, va = matgen.lap27(9, 8, 10, ndof=2, noise=0.5)
+    n = len(rp) - 1
+    x = matgen.fill(n, -1, 1, 1)
+    for _ in range(3):
+        y = np.zeros(n)
+        oracle.spmv_serial(rp, ci, va, x, y, 1.0, 0.0)
+        x = y
+    assert np.array_equal(got, x)  # row-partitioned result is bit-identical to the single-process one
+
+
+def test_balanced_blocks_cover_rows():
+    from kokkos_kernels_b200 import matgen, partition
+
+    rp, ci = matgen.rmat(12, 8)
+    b = partition.balanced_row_blocks(rp, 8)
+    assert b[0] == 0 and b[-1] == len(rp) - 1 and all(b[i] <= b[i + 1] for i in range(8))
+    nnz = [int(rp[b[i + 1]] - rp[b[i]]) for i in range(8)]
+    assert sum(nnz) == rp[-1]
+    assert max(nnz) <= rp[-1] / 8 + int(np.diff(rp).max())

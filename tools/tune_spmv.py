@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_spmv.csv"))
     ap.add_argument("--cfgs", default="0,1,2,3,4")
-    ap.add_argument("--lprs", default="8,16,32")
+    ap.add_argument("--lprs", default="4,8,16")
     ap.add_argument("--ctas", default="-1,1,2,3,4")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
