@@ -117,19 +117,22 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
       re = row_ptr[r + 1];
     }
     S sum = S(0);
-    int j = rs + sl;
-    for (; j + 3 * LPR < re; j += 4 * LPR) {
-      const int c0 = ld_stream(col_idx + j), c1 = ld_stream(col_idx + j + LPR);
-      const int c2 = ld_stream(col_idx + j + 2 * LPR), c3 = ld_stream(col_idx + j + 3 * LPR);
-      const S v0 = ld_stream(vals + j), v1 = ld_stream(vals + j + LPR);
-      const S v2 = ld_stream(vals + j + 2 * LPR), v3 = ld_stream(vals + j + 3 * LPR);
-      const S x0 = ldg(x + c0), x1 = ldg(x + c1), x2 = ldg(x + c2), x3 = ldg(x + c3);
-      sum += v0 * x0;
-      sum += v1 * x1;
-      sum += v2 * x2;
-      sum += v3 * x3;
+    constexpr int UNR = 8;
+    for (int j0 = rs + sl; j0 < re; j0 += UNR * LPR) {
+      int c[UNR];
+      S av[UNR], xv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u * LPR;
+        const bool ok = j < re;
+        c[u] = ok ? ld_stream(col_idx + j) : 0;
+        av[u] = ok ? ld_stream(vals + j) : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) xv[u] = (j0 + u * LPR < re) ? ldg(x + c[u]) : S(0);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
     }
-    for (; j < re; j += LPR) sum += ld_stream(vals + j) * ldg(x + ld_stream(col_idx + j));
     sum = subwarp_sum<LPR>(sum);
     if (r < m && sl == 0) store_y(y, r, sum, alpha, beta);
   }
@@ -249,7 +252,7 @@ struct TileSmem {
   alignas(8) uint64_t empty[STAGES];
 };
 
-template <typename S, int LPR, int NW, int STAGES, int CAP>
+template <typename S, int LPR, int NW, int STAGES, int CAP, int UNR>
 __global__ void __launch_bounds__((NW + 1) * 32)
     spmv_tile_kernel(int m, int64_t nnz, int n_tiles, int LMAX, const int4* __restrict__ tiles,
                      const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
@@ -373,17 +376,24 @@ __global__ void __launch_bounds__((NW + 1) * 32)
         const bool is_long = (re - rs) > LMAX;
         if (is_long) re = rs;
         S sum = S(0);
-        int j = rs + sl - s_al;
         const int jend = re - s_al;
-        for (; j + 3 * LPR < jend; j += 4 * LPR) {
-          const int c0 = sc[j], c1 = sc[j + LPR], c2 = sc[j + 2 * LPR], c3 = sc[j + 3 * LPR];
-          const S x0 = ldg(x + c0), x1 = ldg(x + c1), x2 = ldg(x + c2), x3 = ldg(x + c3);
-          sum += sv[j] * x0;
-          sum += sv[j + LPR] * x1;
-          sum += sv[j + 2 * LPR] * x2;
-          sum += sv[j + 3 * LPR] * x3;
+        // UNR predicated entries per lane per pass: all gathers of a row (<= UNR*LPR entries) are
+        // in flight together -- one memory latency per row instead of one per remainder step
+        for (int j0 = rs + sl - s_al; j0 < jend; j0 += UNR * LPR) {
+          int c[UNR];
+          S av[UNR], xv[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u * LPR;
+            const bool ok = j < jend;
+            c[u] = ok ? sc[j] : 0;
+            av[u] = ok ? sv[j] : S(0);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) xv[u] = (j0 + u * LPR < jend) ? ldg(x + c[u]) : S(0);
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
         }
-        for (; j < jend; j += LPR) sum += sv[j] * ldg(x + sc[j]);
         sum = subwarp_sum<LPR>(sum);
         if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta);
       }
@@ -404,7 +414,13 @@ static const TileCfg kCfgs[] = {
     {4096, 4, 16},  // 1: 200 KB / CTA -> 1 CTA per SM
     {4096, 3, 8},   // 2: 150 KB
     {1024, 6, 8},   // 3:  75 KB -> 3 CTAs per SM
-    {2048, 3, 16},  // 4:  75 KB -> 3 CTAs per SM
+    {2048, 3, 16},  // 4:  84 KB -> 2 CTAs per SM
+    {2048, 3, 24},  // 5
+    {2048, 3, 31},  // 6: 1024 threads, 2 CTAs per SM = 64 warps
+    {1024, 5, 16},  // 7:  70 KB -> 3 CTAs per SM
+    {2048, 4, 16},  // 8: 112 KB -> 2 CTAs per SM
+    {2048, 3, 16},  // 9: as 4 with UNR=4
+    {4096, 3, 31},  // 10: 168 KB, 1 CTA per SM, 32 warps
 };
 static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
@@ -519,18 +535,18 @@ void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
 static int pick_lpr(int m, int64_t nnz) {
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   // measured on B200 (profiles/r01_tune_spmv.csv): fewer lanes per row win until rows get long
-  if (avg <= 4.0) return 2;
-  if (avg <= 12.0) return 4;
-  if (avg <= 128.0) return 8;
-  if (avg <= 512.0) return 16;
+  if (avg <= 8.0) return 2;
+  if (avg <= 96.0) return 4;
+  if (avg <= 384.0) return 8;
+  if (avg <= 1536.0) return 16;
   return 32;
 }
 
-template <typename S, int LPR, int NW, int STAGES, int CAP>
+template <typename S, int LPR, int NW, int STAGES, int CAP, int UNR = 8>
 static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr,
                        const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta) {
   using Smem = TileSmem<S, CAP, STAGES>;
-  auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP>;
+  auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP, UNR>;
   const size_t smem = sizeof(Smem) + 128;
   static std::atomic<bool> attr_set{false};
   if (!attr_set.load(std::memory_order_acquire)) {
@@ -550,8 +566,8 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, p->n_tiles, p->LMAX, p->tiles, row_ptr, col_idx, vals, x, y,
                                           alpha, beta);
   B200SP_LAUNCH_CHECK();
-  snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d>grid=%d",
-           sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, grid);
+  snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d,UNR=%d>grid=%d",
+           sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, UNR, grid);
   return B200SP_OK;
 }
 
@@ -565,6 +581,12 @@ static int launch_tile_cfg(b200sp_spmv_plan* p, int cfg, cudaStream_t st, int m,
     case 2: return launch_tile<S, LPR, 8, 3, 4096>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
     case 3: return launch_tile<S, LPR, 8, 6, 1024>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
     case 4: return launch_tile<S, LPR, 16, 3, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 5: return launch_tile<S, LPR, 24, 3, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 6: return launch_tile<S, LPR, 31, 3, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 7: return launch_tile<S, LPR, 16, 5, 1024>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 8: return launch_tile<S, LPR, 16, 4, 2048>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 9: return launch_tile<S, LPR, 16, 3, 2048, 4>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
+    case 10: return launch_tile<S, LPR, 31, 3, 4096>(p, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta);
   }
   set_error("bad tile cfg %d", cfg);
   return B200SP_ERR_INVALID_ARGUMENT;
@@ -645,7 +667,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
                         (nnz >= 32768 || p->cfg >= 0);
   if (!use_tile) return launch_vector<S>(p, st, (p && p->lpr > 0) ? p->lpr : lpr_auto, m, row_ptr, col_idx, vals, x, y, alpha, beta);
 
-  const int cfg = p->cfg >= 0 ? p->cfg : 4;  // CAP=2048, 3 stages, 16 consumer warps, 2 CTAs/SM
+  const int cfg = p->cfg >= 0 ? p->cfg : 8;  // CAP=2048, 4 stages, 16 consumer warps, 2 CTAs/SM
   int rc = plan_analyse<S>(p, st, cfg, m, n, nnz, row_ptr);
   if (rc) return rc;
   const int lpr = p->lpr > 0 ? p->lpr : lpr_auto;

@@ -125,7 +125,7 @@ def test_tile_kernel_stencil_bitwise_vs_vector(cuda, oracle):
     outs = []
     for algo in (sp.SPMV_DEFAULT, sp.SPMV_FAST_SETUP):
         h = sp.SPMVHandle(algo)
-        h.tune(-1, 16, -1)
+        h.tune(-1, 8, -1)
         yd = torch.empty(n, dtype=torch.float64, device=cuda)
         sp.spmv(h, "N", 1.0, A, xd, 0.0, yd)
         outs.append((h.last_kernel(), yd.cpu().numpy()))
