@@ -16,6 +16,9 @@ One JSON line on stdout (rank 0).  A "step" is one full SpMV over the whole matr
 import argparse
 import json
 import os
+
+os.environ.setdefault("OMP_PROC_BIND", "close")  # reference protocol for the CPU leg
+os.environ.setdefault("OMP_PLACES", "cores")
 import subprocess
 import sys
 import threading
@@ -95,6 +98,22 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_spmv_tile_c2_ncu_key_metrics.csv, same workload); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_spmv_tile_c2_ncu_key_metrics.csv")
+    try:
+        vals = {}
+        for ln in open(path):
+            k, u, v = ln.strip().split(",")
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u)
+            if scale:
+                vals[k] = float(v) * scale
+        return int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"])
+    except Exception:
+        return None
 
 
 def alg_bytes(nnz, nrows, ncols, beta_nonzero=False):
@@ -355,7 +374,10 @@ def main():
                 "kernel": kernel_name, "parity_max_scaled_err": check,
             },
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4),
+                         "traffic": ncu_traffic() if (world == 1 and args.grid == GRID) else None,
+                         "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r01_spmv_tile_c2_ncu_key_metrics.csv)",
+                         "peak_source": peak_src,
                          "kernel_ms": round(kern_ms, 5), "algorithmic_bytes_per_launch": balg},
             "e2e": {"value": round(e2e_gflops, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(n_total * 8),
                     "d2h_bytes_per_step": int(nrows * 8), "ms_per_step": round(te.item(), 4),

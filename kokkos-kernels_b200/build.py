@@ -62,6 +62,18 @@ def build(force=False, verbose=True):
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    # C++ drop-in check: the Kokkos TPL specialisations (kokkos_shim/) compiled against the View mock
+    drv = os.path.join(LIB, "shim_driver")
+    root = os.path.join(HERE, "..")
+    dsrc = os.path.join(root, "tests", "shim_mock", "shim_driver.cpp")
+    shim = [os.path.join(HERE, "kokkos_shim", f) for f in sorted(os.listdir(os.path.join(HERE, "kokkos_shim")))]
+    if os.path.exists(dsrc) and (force or not _newer(drv, [dsrc, out, os.path.join(root, "tests", "shim_mock", "Kokkos_Mock.hpp")] + shim)):
+        cmd = [_nvcc(), "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "tests", "shim_mock"),
+               "-I", os.path.join(HERE, "kokkos_shim"), "-I", os.path.join(root, "include"), dsrc, "-o", drv,
+               "-L", LIB, "-lb200sparse", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+        if verbose:
+            print("[build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
     return out, gen
 
 

@@ -1,0 +1,225 @@
+// Kokkos_Mock.hpp -- the smallest stand-in for the Kokkos / Kokkos Kernels declarations that the
+// B200 shim headers (kokkos-kernels_b200/kokkos_shim/*.hpp) specialise, so the shim can be
+// compiled and RUN without Kokkos (>= 4.6.02 is not available in this image).
+// Names, template parameter lists and member names follow the reference:
+//   SPMVHandleImpl / TPL_SpMV_Data   sparse/src/KokkosSparse_spmv_handle.hpp:90-107,217-253
+//   SPMV / SPMV_MV generic decls     sparse/impl/KokkosSparse_spmv_spec.hpp:92-135
+//   spmv_tpl_spec_avail              sparse/tpls/KokkosSparse_spmv_tpl_spec_avail.hpp:27-30
+//   SPGEMM_SYMBOLIC / _NUMERIC       sparse/impl/KokkosSparse_spgemm_{symbolic,numeric}_spec.hpp:72-98
+//   SPGEMMHandle state               sparse/src/KokkosSparse_spgemm_handle.hpp:356-362,628-653
+// TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <type_traits>
+
+namespace Kokkos {
+struct LayoutLeft {};
+struct LayoutRight {};
+struct CudaSpace {};
+struct CudaUVMSpace {};
+enum MemoryTraitsFlags { Unmanaged = 0x01, RandomAccess = 0x02 };
+template <unsigned F>
+struct MemoryTraits {};
+class Cuda {
+ public:
+  Cuda() = default;
+  explicit Cuda(cudaStream_t s) : s_(s) {}
+  cudaStream_t cuda_stream() const { return s_; }
+  void fence() const { cudaStreamSynchronize(s_); }
+  bool operator!=(const Cuda& o) const { return s_ != o.s_; }
+
+ private:
+  cudaStream_t s_ = nullptr;
+};
+template <class E, class M>
+struct Device {
+  using execution_space = E;
+  using memory_space    = M;
+};
+template <class T>
+struct ArithTraits {
+  static std::string name() { return std::is_same<typename std::remove_cv<T>::type, double>::value ? "double" : "float"; }
+};
+namespace Profiling {
+inline void pushRegion(const std::string&) {}
+inline void popRegion() {}
+}  // namespace Profiling
+
+// rank-1 / rank-2 unmanaged views: data(), extent(), stride()
+template <class DataType, class Layout, class Dev, class MT>
+class View;
+template <class T, class Layout, class Dev, class MT>
+class View<T*, Layout, Dev, MT> {
+ public:
+  using non_const_value_type = typename std::remove_const<T>::type;
+  View() = default;
+  View(T* p, size_t n) : p_(p), n_(n) {}
+  T* data() const { return p_; }
+  size_t extent(int) const { return n_; }
+
+ private:
+  T* p_     = nullptr;
+  size_t n_ = 0;
+};
+template <class T, class Layout, class Dev, class MT>
+class View<T**, Layout, Dev, MT> {
+ public:
+  using non_const_value_type = typename std::remove_const<T>::type;
+  View() = default;
+  View(T* p, size_t n0, size_t n1) : p_(p), n0_(n0), n1_(n1) {}
+  T* data() const { return p_; }
+  size_t extent(int d) const { return d == 0 ? n0_ : n1_; }
+  size_t stride(int d) const {
+    return std::is_same<Layout, LayoutRight>::value ? (d == 0 ? n1_ : 1) : (d == 0 ? 1 : n0_);
+  }
+
+ private:
+  T* p_      = nullptr;
+  size_t n0_ = 0, n1_ = 0;
+};
+}  // namespace Kokkos
+
+namespace KokkosKernels {
+using default_layout = Kokkos::LayoutLeft;
+}
+
+namespace KokkosSparse {
+enum SPMVAlgorithm { SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH };
+
+template <class Scalar, class Ordinal, class Dev, class MT, class Offset>
+class CrsMatrix {
+ public:
+  using UM = Kokkos::MemoryTraits<Kokkos::Unmanaged>;
+  struct Graph {
+    Kokkos::View<Offset*, Kokkos::LayoutLeft, Dev, UM> row_map;
+    Kokkos::View<Ordinal*, Kokkos::LayoutLeft, Dev, UM> entries;
+  } graph;
+  Kokkos::View<Scalar*, Kokkos::LayoutLeft, Dev, UM> values;
+  CrsMatrix(int nrows, int ncols, size_t nnz, Scalar* v, Offset* rp, Ordinal* ci) : nrows_(nrows), ncols_(ncols), nnz_(nnz) {
+    graph.row_map = {rp, (size_t)nrows + 1};
+    graph.entries = {ci, nnz};
+    values        = {v, nnz};
+  }
+  int numRows() const { return nrows_; }
+  int numCols() const { return ncols_; }
+  size_t nnz() const { return nnz_; }
+
+ private:
+  int nrows_, ncols_;
+  size_t nnz_;
+};
+
+namespace Impl {
+template <typename ExecutionSpace>
+struct TPL_SpMV_Data {
+  TPL_SpMV_Data() = delete;
+  TPL_SpMV_Data(const ExecutionSpace& exec_) : exec(exec_) {}
+  void set_exec_space(const ExecutionSpace& new_exec) {
+    if (exec != new_exec) {
+      exec.fence();
+      exec = new_exec;
+    }
+  }
+  virtual ~TPL_SpMV_Data() {}
+  ExecutionSpace exec;
+};
+
+template <class ExecutionSpace, class MemorySpace, class Scalar, class Offset, class Ordinal>
+struct SPMVHandleImpl {
+  SPMVHandleImpl(SPMVAlgorithm algo_) : algo(algo_) {}
+  ~SPMVHandleImpl() {
+    if (tpl_rank1) delete tpl_rank1;
+    if (tpl_rank2) delete tpl_rank2;
+  }
+  SPMVAlgorithm get_algorithm() const { return algo; }
+  const SPMVAlgorithm algo                 = SPMV_DEFAULT;
+  TPL_SpMV_Data<ExecutionSpace>* tpl_rank1 = nullptr;
+  TPL_SpMV_Data<ExecutionSpace>* tpl_rank2 = nullptr;
+};
+
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
+struct spmv_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
+struct spmv_mv_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector,
+          bool tpl_spec_avail = spmv_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value>
+struct SPMV;  // only the TPL specialisations exist in the mock
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector, bool integerScalar = false,
+          bool tpl_spec_avail = spmv_mv_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value>
+struct SPMV_MV;
+}  // namespace Impl
+}  // namespace KokkosSparse
+
+struct b200sp_spgemm_plan;
+extern "C" int b200sp_spgemm_plan_destroy(b200sp_spgemm_plan*, void*);
+
+namespace KokkosSparse {
+// the SPGEMMHandle members the shim touches (+ the one member INTEGRATION.md adds)
+template <class size_type_, class lno_t_, class scalar_t_>
+struct SPGEMMHandleMock {
+  using size_type = size_type_;
+  using nnz_lno_t = lno_t_;
+  ~SPGEMMHandleMock() {
+    if (b200_spgemm_plan) b200sp_spgemm_plan_destroy(b200_spgemm_plan, nullptr);
+  }
+  void set_c_nnz(size_t v) { c_nnz = v; }
+  size_t get_c_nnz() const { return c_nnz; }
+  void set_max_result_nnz(int v) { max_nnz = v; }
+  void set_call_symbolic(bool c = true) { called_symbolic = c; }
+  void set_call_numeric(bool c = true) { called_numeric = c; }
+  void set_computed_rowptrs() { computed_rowptrs = true; }
+  void set_computed_entries() { computed_entries = true; }
+  bool is_symbolic_called() const { return called_symbolic; }
+  bool is_numeric_called() const { return called_numeric; }
+  bool are_rowptrs_computed() const { return computed_rowptrs; }
+  bool are_entries_computed() const { return computed_entries; }
+  b200sp_spgemm_plan* b200_spgemm_plan = nullptr;
+  size_t c_nnz                         = 0;
+  int max_nnz                          = 0;
+  bool called_symbolic = false, called_numeric = false, computed_rowptrs = false, computed_entries = false;
+};
+}  // namespace KokkosSparse
+
+namespace KokkosKernels {
+namespace Experimental {
+template <class size_type_, class lno_t_, class scalar_t_, class Exec, class TmpMem, class PersMem>
+struct KokkosKernelsHandle {
+  using size_type    = typename std::remove_const<size_type_>::type;
+  using nnz_lno_t    = typename std::remove_const<lno_t_>::type;
+  using nnz_scalar_t = typename std::remove_const<scalar_t_>::type;
+  using SPGEMMHandleType = KokkosSparse::SPGEMMHandleMock<size_type, nnz_lno_t, nnz_scalar_t>;
+  SPGEMMHandleType* get_spgemm_handle() { return sh; }
+  void create_spgemm_handle() { sh = new SPGEMMHandleType(); }
+  void destroy_spgemm_handle() {
+    delete sh;
+    sh = nullptr;
+  }
+  SPGEMMHandleType* sh = nullptr;
+};
+}  // namespace Experimental
+}  // namespace KokkosKernels
+
+namespace KokkosSparse {
+namespace Impl {
+template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r>
+struct spgemm_symbolic_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v>
+struct spgemm_numeric_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r, bool tpl, bool eti>
+struct SPGEMM_SYMBOLIC;
+template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v,
+          bool tpl, bool eti>
+struct SPGEMM_NUMERIC;
+}  // namespace Impl
+}  // namespace KokkosSparse

@@ -1,0 +1,160 @@
+// shim_driver.cpp -- instantiates the B200 TPL specialisations exactly as KokkosSparse::spmv /
+// spgemm_symbolic / spgemm_numeric would (Kokkos_Mock.hpp standing in for Kokkos), runs them on the
+// GPU through libb200sparse and checks the results on the host.  Exit code 0 = all checks passed.
+#define KOKKOSKERNELS_ENABLE_TPL_B200SPARSE
+#include "Kokkos_Mock.hpp"
+#include "KokkosSparse_spmv_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_spmv_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_spgemm_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_spgemm_b200_tpl_spec_decl.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+using namespace KokkosSparse;
+using Dev   = Kokkos::Device<Kokkos::Cuda, Kokkos::CudaSpace>;
+using UM    = Kokkos::MemoryTraits<Kokkos::Unmanaged>;
+using UMRA  = Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>;
+using Hnd   = Impl::SPMVHandleImpl<Kokkos::Cuda, Kokkos::CudaSpace, double, int, int>;
+using AMat  = CrsMatrix<const double, const int, Dev, UM, const int>;
+using XVec  = Kokkos::View<const double*, Kokkos::LayoutLeft, Dev, UMRA>;
+using YVec  = Kokkos::View<double*, Kokkos::LayoutLeft, Dev, UM>;
+using XMV   = Kokkos::View<const double**, Kokkos::LayoutLeft, Dev, UMRA>;
+using YMV   = Kokkos::View<double**, Kokkos::LayoutLeft, Dev, UM>;
+using KH    = KokkosKernels::Experimental::KokkosKernelsHandle<const int, const int, const double, Kokkos::Cuda, Kokkos::CudaSpace, Kokkos::CudaSpace>;
+using CIV   = Kokkos::View<const int*, KokkosKernels::default_layout, Dev, UM>;
+using IV    = Kokkos::View<int*, KokkosKernels::default_layout, Dev, UM>;
+using CSV   = Kokkos::View<const double*, KokkosKernels::default_layout, Dev, UM>;
+using SV    = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UM>;
+
+static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::value, "rank-1 specialisation must be available");
+static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
+static_assert(Impl::spgemm_symbolic_tpl_spec_avail<KH, CIV, CIV, CIV, CIV, IV>::value, "spgemm symbolic must be available");
+static_assert(Impl::spgemm_numeric_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV>::value, "spgemm numeric");
+
+template <class T>
+T* to_dev(const std::vector<T>& h) {
+  T* d = nullptr;
+  cudaMalloc(&d, sizeof(T) * (h.size() ? h.size() : 1));
+  cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+  return d;
+}
+
+int main() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    std::printf("no CUDA device\n");
+    return 77;
+  }
+  // tridiagonal-ish n x n matrix with rows of 3 (ragged at the ends), values depend on (i,j)
+  const int n = 50000;
+  std::vector<int> rp(n + 1, 0), ci;
+  std::vector<double> va, x(n), y0(n);
+  for (int i = 0; i < n; ++i) {
+    for (int j = i - 1; j <= i + 1; ++j)
+      if (j >= 0 && j < n) {
+        ci.push_back(j);
+        va.push_back(1.0 + 0.001 * ((i * 7 + j * 3) % 11));
+      }
+    rp[i + 1] = (int)ci.size();
+    x[i]  = 0.5 + 0.25 * std::sin(0.01 * i);
+    y0[i] = 1.0 + 0.001 * i;
+  }
+  int *d_rp = to_dev(rp), *d_ci = to_dev(ci);
+  double *d_va = to_dev(va), *d_x = to_dev(x), *d_y = to_dev(y0);
+  cudaStream_t stream;
+  cudaStreamCreate(&stream);
+  Kokkos::Cuda exec(stream);
+  int failures = 0;
+  {
+    Hnd handle(SPMV_DEFAULT);
+    AMat A(n, n, ci.size(), d_va, d_rp, d_ci);
+    Impl::SPMV<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::spmv(exec, &handle, "N", 2.0, A, XVec(d_x, n), 0.5, YVec(d_y, n));
+    exec.fence();
+    std::vector<double> y(n);
+    cudaMemcpy(y.data(), d_y, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int k = rp[i]; k < rp[i + 1]; ++k) s += va[k] * x[ci[k]];
+      const double e = 0.5 * y0[i] + 2.0 * s;
+      if (std::fabs(y[i] - e) > 1e-12 * (1 + std::fabs(e))) ++failures;
+    }
+    std::printf("spmv rank-1 through SPMV<...,true>::spmv : %d mismatches\n", failures);
+    // rank-2, 3 columns, LayoutLeft, transpose mode
+    const int k = 3;
+    std::vector<double> X(n * k), Y(n * k, 0.0);
+    for (int j = 0; j < k; ++j)
+      for (int i = 0; i < n; ++i) X[j * n + i] = x[i] * (j + 1);
+    double *d_X = to_dev(X), *d_Y = to_dev(Y);
+    Impl::SPMV_MV<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::spmv_mv(exec, &handle, "T", 1.0, A, XMV(d_X, n, k), 0.0, YMV(d_Y, n, k));
+    exec.fence();
+    cudaMemcpy(Y.data(), d_Y, sizeof(double) * n * k, cudaMemcpyDeviceToHost);
+    std::vector<double> E(n * k, 0.0);
+    for (int i = 0; i < n; ++i)
+      for (int q = rp[i]; q < rp[i + 1]; ++q)
+        for (int j = 0; j < k; ++j) E[j * n + ci[q]] += va[q] * X[j * n + i];
+    int f2 = 0;
+    for (int i = 0; i < n * k; ++i)
+      if (std::fabs(Y[i] - E[i]) > 1e-12 * (1 + std::fabs(E[i]))) ++f2;
+    std::printf("spmv rank-2 'T' through SPMV_MV<...,false,true>::spmv_mv : %d mismatches\n", f2);
+    failures += f2;
+    cudaFree(d_X);
+    cudaFree(d_Y);
+  }  // handle destructor frees the plan stream-ordered
+  {
+    // C = A*A through the SpGEMM specialisations; check against a host Gustavson product
+    KH kh;
+    kh.create_spgemm_handle();
+    int* d_rpC = nullptr;
+    cudaMalloc(&d_rpC, sizeof(int) * (n + 1));
+    using SYM = Impl::SPGEMM_SYMBOLIC<KH, CIV, CIV, CIV, CIV, IV, true, true>;
+    using NUM = Impl::SPGEMM_NUMERIC<KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV, true, true>;
+    CIV vrp(d_rp, n + 1), vci(d_ci, ci.size());
+    CSV vva(d_va, va.size());
+    SYM::spgemm_symbolic(&kh, n, n, n, vrp, vci, false, vrp, vci, false, IV(d_rpC, n + 1), false);
+    const size_t cnnz = kh.get_spgemm_handle()->get_c_nnz();
+    int* d_ciC = nullptr;
+    double* d_vC = nullptr;
+    cudaMalloc(&d_ciC, sizeof(int) * cnnz);
+    cudaMalloc(&d_vC, sizeof(double) * cnnz);
+    NUM::spgemm_numeric(&kh, n, n, n, vrp, vci, vva, false, vrp, vci, vva, false, CIV(d_rpC, n + 1), IV(d_ciC, cnnz), SV(d_vC, cnnz));
+    cudaDeviceSynchronize();
+    std::vector<int> rpC(n + 1), ciC(cnnz);
+    std::vector<double> vC(cnnz);
+    cudaMemcpy(rpC.data(), d_rpC, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost);
+    cudaMemcpy(ciC.data(), d_ciC, sizeof(int) * cnnz, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vC.data(), d_vC, sizeof(double) * cnnz, cudaMemcpyDeviceToHost);
+    int f3 = 0;
+    std::vector<double> acc(n, 0.0);
+    std::vector<char> flag(n, 0);
+    for (int i = 0; i < n; ++i) {
+      std::vector<int> cols;
+      for (int a = rp[i]; a < rp[i + 1]; ++a)
+        for (int b = rp[ci[a]]; b < rp[ci[a] + 1]; ++b) {
+          if (!flag[ci[b]]) {
+            flag[ci[b]] = 1;
+            cols.push_back(ci[b]);
+          }
+          acc[ci[b]] += va[b] * va[a];
+        }
+      if (rpC[i + 1] - rpC[i] != (int)cols.size()) ++f3;
+      for (int q = rpC[i]; q < rpC[i + 1] && q < (int)cnnz; ++q) {
+        if (q > rpC[i] && ciC[q] <= ciC[q - 1]) ++f3;  // sorted, no duplicates
+        if (!flag[ciC[q]] || std::fabs(vC[q] - acc[ciC[q]]) > 1e-12 * std::fabs(acc[ciC[q]])) ++f3;
+      }
+      for (int c : cols) {
+        flag[c] = 0;
+        acc[c]  = 0;
+      }
+    }
+    auto sh = kh.get_spgemm_handle();
+    if (!sh->is_symbolic_called() || !sh->is_numeric_called() || !sh->are_rowptrs_computed() || !sh->are_entries_computed()) ++f3;
+    std::printf("spgemm through SPGEMM_SYMBOLIC/NUMERIC<...,true,true> : c_nnz=%zu, %d mismatches\n", cnnz, f3);
+    failures += f3;
+    kh.destroy_spgemm_handle();
+  }
+  std::printf(failures ? "SHIM DRIVER FAILED\n" : "SHIM DRIVER OK\n");
+  return failures ? 1 : 0;
+}
