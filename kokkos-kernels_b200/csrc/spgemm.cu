@@ -217,6 +217,88 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int m, int* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// Product walker shared by symbolic and numeric.  A group of G threads expands row i of A*B:
+// per batch of <= G entries of A it stages (B row start, B row length prefix, A value) in shared
+// memory with two rounds of independent loads, then the flattened products are dealt to the
+// threads U at a time so U*G independent loads of B are in flight (the per-entry dependent chain
+// row_ptr_B -> col_idx_B of a naive walk is what bounds SpGEMM on HBM latency).
+// f(c, v) is called once per product; stop() lets the caller abandon the row.
+// ---------------------------------------------------------------------------
+template <int G, typename S>
+struct WalkSmem {
+  int bs[G];    // start of the B row of staged entry t
+  int pre[G];   // inclusive prefix of B row lengths
+  S va[G];      // A value of staged entry t
+  int wtot[G / 32 > 0 ? G / 32 : 1];
+};
+
+template <int G, bool WITH_VALS, typename S, typename F, typename Stop>
+__device__ __forceinline__ void walk_products(int tg, int a0, int a1, const int* __restrict__ ciA,
+                                              const S* __restrict__ vA, const int* __restrict__ rpB,
+                                              const int* __restrict__ ciB, const S* __restrict__ vB,
+                                              WalkSmem<G, S>& w, F&& f, Stop&& stop) {
+  constexpr int U = 4;
+  auto gsync = [&]() {
+    if (G <= 32) __syncwarp(); else __syncthreads();
+  };
+  const int lane = tg & 31, wid = tg >> 5;
+  for (int ab = a0; ab < a1; ab += G) {
+    const int nA = min(G, a1 - ab);
+    int len = 0;
+    if (tg < nA) {
+      const int ca = ciA[ab + tg];
+      const int b0 = rpB[ca];
+      len = rpB[ca + 1] - b0;
+      w.bs[tg] = b0;
+      if (WITH_VALS) w.va[tg] = vA[ab + tg];
+    }
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (G > 32) {
+      if (lane == 31) w.wtot[wid] = inc;
+      __syncthreads();
+      int off = 0;
+      for (int k = 0; k < wid; ++k) off += w.wtot[k];
+      inc += off;
+    }
+    w.pre[tg] = inc;  // entries t >= nA repeat the total (len 0)
+    gsync();
+    const int total = w.pre[G - 1];
+    for (int p0 = 0; p0 < total; p0 += G * U) {
+      int c[U];
+      S v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * G + tg;
+        c[u] = -1;
+        if (p < total) {
+          // smallest idx with pre[idx] > p
+          int lo = 0, hi = nA - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (w.pre[mid] > p) hi = mid; else lo = mid + 1;
+          }
+          const int first = (lo == 0) ? 0 : w.pre[lo - 1];
+          const int jb = w.bs[lo] + (p - first);
+          c[u] = ld_stream(ciB + jb);
+          if (WITH_VALS) v[u] = ld_stream(vB + jb) * w.va[lo];  // b_val * val (impl_seq.hpp:163)
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c[u] >= 0) f(c[u], WITH_VALS ? v[u] : S(0));
+      if (stop()) break;
+    }
+    gsync();  // staging is rewritten by the next batch
+    if (stop()) break;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // SYMBOLIC: count distinct columns of row i of A*B with a shared-memory hash set.
 // G threads cooperate on one row; LB lanes walk one row of B.
 // ---------------------------------------------------------------------------
@@ -226,7 +308,7 @@ __device__ __forceinline__ unsigned hash_mul(int c, int log2slots) {
 
 template <int G, int LOG2SLOTS>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
-    sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
+    sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA,
                     const int* __restrict__ ciA, const int* __restrict__ rpB, const int* __restrict__ ciB,
                     int* __restrict__ row_nnz) {
   constexpr int SLOTS = 1 << LOG2SLOTS;
@@ -234,6 +316,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   constexpr int RPC = THREADS / G;
   extern __shared__ int sm_keys[];  // RPC * SLOTS
   __shared__ int sm_cnt[RPC];
+  __shared__ WalkSmem<G, float> sm_walk[RPC];
   const int g = threadIdx.x / G, tg = threadIdx.x % G;
   int* keys = sm_keys + g * SLOTS;
   const int ridx = blockIdx.x * RPC + g;
@@ -242,16 +325,12 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   if (tg == 0) sm_cnt[g] = 0;
   if (G <= 32) __syncwarp(); else __syncthreads();
   int mine = 0;
-  if (active) {
-    const int i = rows[ridx];
-    const int a0 = rpA[i], a1 = rpA[i + 1];
-    const int subs = G / lb;  // B rows walked concurrently by the group
-    const int sub = tg / lb, sl = tg % lb;
-    for (int ja = a0 + sub; ja < a1; ja += subs) {
-      const int ca = ciA[ja];
-      const int b1 = rpB[ca + 1];
-      for (int jb = rpB[ca] + sl; jb < b1; jb += lb) {
-        const int c = ld_stream(ciB + jb);
+  // inactive groups (tail CTA) walk an empty row so that block-wide barriers stay matched
+  const int i = active ? rows[ridx] : 0;
+  const int a0 = active ? rpA[i] : 0, a1 = active ? rpA[i + 1] : 0;
+  walk_products<G, false, float>(
+      tg, a0, a1, ciA, (const float*)nullptr, rpB, ciB, (const float*)nullptr, sm_walk[g],
+      [&](int c, float) {
         unsigned h = hash_mul(c, LOG2SLOTS);
         while (true) {
           const int kcur = ((volatile int*)keys)[h];
@@ -266,18 +345,17 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
           }
           h = (h + 1) & (SLOTS - 1);
         }
-      }
-    }
-  }
+      },
+      []() { return false; });
   // group reduce
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
   if (G <= 32) {
-    if (active && tg == 0) row_nnz[rows[ridx]] = mine;
+    if (active && tg == 0) row_nnz[i] = mine;
   } else {
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sm_cnt[g], mine);
     __syncthreads();
-    if (active && tg == 0) row_nnz[rows[ridx]] = sm_cnt[g];
+    if (active && tg == 0) row_nnz[i] = sm_cnt[g];
   }
 }
 
@@ -324,7 +402,7 @@ __device__ __forceinline__ void smem_add(S* p, S v) {
 
 template <typename S, int G, int SLOTS, int PAD>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
-    num_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
+    num_hash_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA,
                     const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
                     const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
                     int* __restrict__ ciC, S* __restrict__ vC, const int* __restrict__ cmin_arr,
@@ -338,6 +416,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   constexpr size_t PER = sizeof(S) * TOT + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
   constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
   __shared__ int sm_flag[RPC];
+  __shared__ WalkSmem<G, S> sm_walk[RPC];
   const int g = threadIdx.x / G, tg = threadIdx.x % G;
   unsigned char* base = smraw + (size_t)g * PER_AL;
   S* vals = reinterpret_cast<S*>(base);
@@ -362,42 +441,33 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     cbase = rpC[i];
     nz = rpC[i + 1] - cbase;
   }
-  if (active && nz > 0) {
-    const int cmin = cmin_arr[i];
-    const long long span = (long long)cmax_arr[i] - cmin + 1;
+  {
+    const bool work = active && nz > 0;
+    const int cmin = work ? cmin_arr[i] : 0;
+    const long long span = work ? ((long long)cmax_arr[i] - cmin + 1) : 1;
     dense = span <= SLOTS;
     // monotone map column -> slot in [0, SLOTS)
     const unsigned long long mult = dense ? 0ull : (((unsigned long long)SLOTS << 32) / (unsigned long long)span);
-    const int a0 = rpA[i], a1 = rpA[i + 1];
-    const int subs = G / lb;
-    const int sub = tg / lb, sl = tg % lb;
-    bool ovf = false;
-    for (int ja = a0 + sub; ja < a1; ja += subs) {
-      const int ca = ciA[ja];
-      const S va = vA[ja];
-      const int b1 = rpB[ca + 1];
-      for (int jb = rpB[ca] + sl; jb < b1; jb += lb) {
-        const int c = ld_stream(ciB + jb);
-        const S v = ld_stream(vB + jb) * va;  // b_val * val (impl_seq.hpp:163)
-        int h = dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
-        while (true) {
-          const int kcur = ((volatile int*)keys)[h];
-          if (kcur == c) break;
-          if (kcur == EMPTY) {
-            const int old = atomicCAS(&keys[h], EMPTY, c);
-            if (old == EMPTY || old == c) break;
+    const int a0 = work ? rpA[i] : 0, a1 = work ? rpA[i + 1] : 0;
+    walk_products<G, true, S>(
+        tg, a0, a1, ciA, vA, rpB, ciB, vB, sm_walk[g],
+        [&](int c, S v) {
+          int h = dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
+          while (true) {
+            const int kcur = ((volatile int*)keys)[h];
+            if (kcur == c) break;
+            if (kcur == EMPTY) {
+              const int old = atomicCAS(&keys[h], EMPTY, c);
+              if (old == EMPTY || old == c) break;
+            }
+            if (++h >= TOT) {
+              sm_flag[g] = 1;  // probe ran off the pad: row goes to the fallback kernel
+              return;
+            }
           }
-          if (++h >= TOT) {
-            ovf = true;
-            break;
-          }
-        }
-        if (ovf) break;
-        smem_add(&vals[h], v);
-      }
-      if (ovf) break;
-    }
-    if (ovf) sm_flag[g] = 1;
+          smem_add(&vals[h], v);
+        },
+        [&]() { return ((volatile int*)sm_flag)[g] != 0; });
   }
   gsync();
   const bool overflow = sm_flag[g] != 0;
@@ -627,7 +697,7 @@ static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const
   const size_t smem = sizeof(int) * (size_t)RPC * ((size_t)1 << LOG2SLOTS);
   auto kern = sym_hash_kernel<G, LOG2SLOTS>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, std::min(lb, G), rpA, ciA, rpB, ciB, row_nnz);
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, rpA, ciA, rpB, ciB, row_nnz);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -646,9 +716,8 @@ static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int
   const size_t smem = PER_AL * RPC;
   auto kern = num_hash_kernel<S, G, SLOTS, PAD>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, G), rpA, ciA,
-                                                      vA, rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->fb_rows,
-                                                      p->fb_count);
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], rpA, ciA, vA, rpB, ciB, vB, rpC,
+                                                      ciC, vC, p->cmin, p->cmax, p->fb_rows, p->fb_count);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }

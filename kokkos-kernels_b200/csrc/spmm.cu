@@ -17,6 +17,7 @@
 // gather touches one segment per nonzero instead of k sectors.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 struct b200sp_spmv_plan;  // defined in spmv.cu
 
@@ -157,6 +158,114 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------
+// nnz-split kernel (power-law rows): a group of KT lanes (one per column of the strip) walks a chunk
+// of Q consecutive nonzeros; rows that lie inside the chunk are stored directly, the (at most two)
+// rows cut by the chunk borders are pre-scaled by spmm_prescale_split_rows and accumulated with
+// atomicAdd.  chunk_row[c] = row holding nonzero c*Q (built once per matrix, cached in the plan).
+// ---------------------------------------------------------------------------
+__global__ void build_chunk_rows_kernel(int m, const int* __restrict__ row_ptr, int n_chunks, int Q,
+                                        int* __restrict__ chunk_row) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  // first row r with row_ptr[r+1] > c*Q
+  const int64_t pos = (int64_t)c * Q;
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((int64_t)row_ptr[mid + 1] <= pos) lo = mid + 1;
+    else hi = mid;
+  }
+  chunk_row[c] = lo;
+}
+
+template <typename S>
+__global__ void spmm_prescale_split_rows(int m, int k, int Q, const int* __restrict__ row_ptr, S beta,
+                                         S* __restrict__ Y, int64_t ldy) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const int s = row_ptr[r], e = row_ptr[r + 1];
+    if (e > s && (s / Q) != ((e - 1) / Q)) {
+      S* yp = Y + (int64_t)r * ldy;
+      for (int j = 0; j < k; ++j) yp[j] = (beta == S(0)) ? S(0) : beta * yp[j];
+    }
+  }
+}
+
+template <typename S, int KT>
+__global__ void __launch_bounds__(256)
+    spmm_split_kernel(int m, int k, int64_t nnz, int Q, int n_chunks, const int* __restrict__ chunk_row,
+                      const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const S* __restrict__ vals,
+                      const S* __restrict__ X, int64_t ldx, S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  constexpr int GPW = 32 / KT;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / KT, t = lane % KT;
+  const unsigned gmask = (KT == 32) ? 0xffffffffu : (((1u << KT) - 1u) << (grp * KT));
+  const int gbase = grp * KT;  // shuffle source lanes are absolute
+  const int nstrips = (k + KT - 1) / KT;
+  const int64_t gid = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * GPW + grp;
+  const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
+  const int64_t work_total = (int64_t)n_chunks * nstrips;
+  for (int64_t w = gid; w < work_total; w += ngroups) {
+    const int chunk = (int)(w / nstrips);
+    const int j = (int)(w % nstrips) * KT + t;
+    const bool jok = j < k;
+    const int64_t c0 = (int64_t)chunk * Q;
+    const int64_t c1 = (c0 + Q < nnz) ? c0 + Q : nnz;
+    int row = (chunk == 0) ? 0 : chunk_row[chunk];
+    // cache of KT row ends: lane t holds row_ptr[ebase + 1 + t]
+    int ebase = row;
+    int ends = row_ptr[min(ebase + 1 + t, m)];
+    int64_t row_start = row_ptr[row];
+    int64_t next_end = __shfl_sync(gmask, ends, gbase);
+    S acc = S(0);
+    auto flush = [&]() {
+      // row `row` ends at next_end; acc holds this chunk's share of it
+      if (jok) {
+        S* yp = Y + (int64_t)row * ldy + j;
+        const S a = alpha * acc;
+        if (row_start >= c0 && next_end <= c1) *yp = (beta == S(0)) ? a : beta * *yp + a;
+        else atomicAdd(yp, a);
+      }
+      acc = S(0);
+      row_start = next_end;
+      ++row;
+      if (row - ebase == KT) {
+        ebase = row;
+        ends = row_ptr[min(ebase + 1 + t, m)];
+      }
+      next_end = __shfl_sync(gmask, ends, gbase + (row - ebase));
+    };
+    for (int64_t b = c0; b < c1; b += KT) {
+      const int64_t e = b + t;
+      int c = 0;
+      S v = S(0);
+      if (e < c1) {
+        c = ld_stream(col_idx + e);
+        v = ld_stream(vals + e);
+      }
+      const int nb = (int)((c1 - b < KT) ? (c1 - b) : KT);
+      S xv[KT];
+#pragma unroll
+      for (int u = 0; u < KT; ++u) {
+        const int cu = __shfl_sync(gmask, c, gbase + u);
+        xv[u] = (u < nb && jok) ? ldg(X + (int64_t)cu * ldx + j) : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < KT; ++u) {
+        const S vu = __shfl_sync(gmask, v, gbase + u);
+        if (u < nb) {
+          while (b + u >= next_end) flush();  // uniform within the group
+          acc += vu * xv[u];
+        }
+      }
+    }
+    // rows ending inside (or exactly at the end of) this chunk, incl. empty rows
+    while (row < m && next_end <= c1) flush();
+    // a row that continues into the next chunk: its share goes in atomically
+    if (row < m && row_start < c1 && jok) atomicAdd(Y + (int64_t)row * ldy + j, alpha * acc);
+  }
+}
+
 template <typename S>
 static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, const int* col_idx, const S* vals,
                            const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
@@ -182,6 +291,55 @@ static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, co
 #undef B200SP_RM
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
+}
+
+int plan_chunk_rows(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr, int Q, int** chunk_row,
+                    int* n_chunks);
+
+template <typename S>
+static int launch_split(b200sp_spmv_plan* p, cudaStream_t st, int m, int k, int64_t nnz, const int* row_ptr,
+                        const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  const int Q = 256;
+  int* chunk_row = nullptr;
+  int n_chunks = 0;
+  int rc = plan_chunk_rows(p, st, m, nnz, row_ptr, Q, &chunk_row, &n_chunks);
+  if (rc) return rc;
+  {
+    const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
+    spmm_prescale_split_rows<S><<<blocks, 256, 0, st>>>(m, k, Q, row_ptr, beta, Y, ldy);
+    B200SP_LAUNCH_CHECK();
+  }
+  int KT = 1;
+  while (KT < k && KT < 32) KT <<= 1;
+  const int gpw = 32 / KT;
+  const int nstrips = (k + KT - 1) / KT;
+  const int64_t work = (int64_t)n_chunks * nstrips;
+  int blocks = (int)std::min<int64_t>((work + 8 * gpw - 1) / (8 * gpw), (int64_t)sm_count() * 16);
+  if (blocks < 1) blocks = 1;
+#define B200SP_SPLIT(K)                                                                                       \
+  case K:                                                                                                     \
+    spmm_split_kernel<S, K><<<blocks, 256, 0, st>>>(m, k, nnz, Q, n_chunks, chunk_row, row_ptr, col_idx, vals, X, ldx, \
+                                                    Y, ldy, alpha, beta);                                     \
+    break;
+  switch (KT) {
+    B200SP_SPLIT(1)
+    B200SP_SPLIT(2)
+    B200SP_SPLIT(4)
+    B200SP_SPLIT(8)
+    B200SP_SPLIT(16)
+    B200SP_SPLIT(32)
+  }
+#undef B200SP_SPLIT
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+static bool use_split_kernel(b200sp_spmv_plan* p) {
+  // needs a plan (chunk table); B200SP_SPMM_KERNEL=row|split overrides for experiments
+  if (!p) return false;
+  const char* e = getenv("B200SP_SPMM_KERNEL");
+  if (e && e[0] == 'r') return false;
+  return true;
 }
 
 template <typename S>
@@ -221,8 +379,10 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
     plan_set_last_kernel(p, "spmm_transpose");
     return B200SP_OK;
   }
+  const bool split = use_split_kernel(p);
   if (xrm && yrm) {
-    plan_set_last_kernel(p, "spmm_rowmajor");
+    plan_set_last_kernel(p, split ? "spmm_split" : "spmm_rowmajor");
+    if (split) return launch_split<S>(p, st, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
     return launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
   }
   // LayoutLeft operands: with a plan and k >= 4, relayout to row-major scratch and use the row-major kernel
@@ -251,13 +411,14 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
         B200SP_LAUNCH_CHECK();
       }
     }
-    rc = launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    rc = split ? launch_split<S>(p, st, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta)
+               : launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
     if (rc) return rc;
     if (!yrm) {
       relayout_kernel<S, false><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
       B200SP_LAUNCH_CHECK();
     }
-    plan_set_last_kernel(p, "spmm_relayout+rowmajor");
+    plan_set_last_kernel(p, split ? "spmm_relayout+split" : "spmm_relayout+rowmajor");
     return B200SP_OK;
   }
   const int g = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, (int64_t)sm_count() * 16);

@@ -455,6 +455,12 @@ struct b200sp_spmv_plan {
   void* xt = nullptr;
   void* yt = nullptr;
   size_t xt_bytes = 0, yt_bytes = 0;
+  // nnz-chunk -> row table of the split SpMM kernel
+  int* chunk_row = nullptr;
+  int n_chunks = 0, chunk_q = 0;
+  const int* chunk_key = nullptr;
+  int chunk_m = -1;
+  int64_t chunk_nnz = -1;
   char last_kernel[96] = "none";
 };
 
@@ -526,6 +532,27 @@ int plan_mv_scratch(b200sp_spmv_plan* p, cudaStream_t st, size_t xt_bytes, size_
   }
   *xt = p->xt;
   *yt = p->yt;
+  return B200SP_OK;
+}
+__global__ void build_chunk_rows_kernel(int m, const int* __restrict__ row_ptr, int n_chunks, int Q,
+                                        int* __restrict__ chunk_row);
+int plan_chunk_rows(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr, int Q, int** chunk_row,
+                    int* n_chunks) {
+  if (!(p->chunk_row && p->chunk_key == row_ptr && p->chunk_m == m && p->chunk_nnz == nnz && p->chunk_q == Q)) {
+    if (p->chunk_row) cudaFreeAsync(p->chunk_row, st);
+    p->chunk_row = nullptr;
+    p->n_chunks = (int)((nnz + Q - 1) / Q);
+    if (p->n_chunks < 1) p->n_chunks = 1;
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->chunk_row, sizeof(int) * (size_t)p->n_chunks, st));
+    build_chunk_rows_kernel<<<(p->n_chunks + 255) / 256, 256, 0, st>>>(m, row_ptr, p->n_chunks, Q, p->chunk_row);
+    B200SP_LAUNCH_CHECK();
+    p->chunk_key = row_ptr;
+    p->chunk_m = m;
+    p->chunk_nnz = nnz;
+    p->chunk_q = Q;
+  }
+  *chunk_row = p->chunk_row;
+  *n_chunks = p->n_chunks;
   return B200SP_OK;
 }
 void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
@@ -730,6 +757,7 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   if (p->dy) cudaFreeAsync(p->dy, st);
   if (p->xt) cudaFreeAsync(p->xt, st);
   if (p->yt) cudaFreeAsync(p->yt, st);
+  if (p->chunk_row) cudaFreeAsync(p->chunk_row, st);
   if (p->n_long_event) {
     cudaEventSynchronize(p->n_long_event);  // the pinned mirror must not be written after it is freed
     cudaEventDestroy(p->n_long_event);
