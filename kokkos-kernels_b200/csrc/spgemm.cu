@@ -218,79 +218,66 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int m, int* __restrict__ 
 
 // ---------------------------------------------------------------------------
 // Product walker shared by symbolic and numeric.  A group of G threads expands row i of A*B:
-// per batch of <= G entries of A it stages (B row start, B row length prefix, A value) in shared
-// memory with two rounds of independent loads, then the flattened products are dealt to the
-// threads U at a time so U*G independent loads of B are in flight (the per-entry dependent chain
-// row_ptr_B -> col_idx_B of a naive walk is what bounds SpGEMM on HBM latency).
-// f(c, v) is called once per product; stop() lets the caller abandon the row.
+// per batch of <= G entries of A it stages (B row start, B row length, A value) in shared memory
+// with two rounds of independent loads; then sub-warps of LB lanes (LB ~ mean row length of B)
+// each take staged entries round-robin, UT entries at a time, so that UT independent B-row reads
+// per lane are in flight (a naive walk chains row_ptr_B -> col_idx_B loads per entry of A and is
+// bound by HBM latency).  f(c, v) is called once per product; stop() lets the caller abandon the row.
 // ---------------------------------------------------------------------------
 template <int G, typename S>
 struct WalkSmem {
-  int bs[G];    // start of the B row of staged entry t
-  int pre[G];   // inclusive prefix of B row lengths
-  S va[G];      // A value of staged entry t
-  int wtot[G / 32 > 0 ? G / 32 : 1];
+  int bs[G];   // start of the B row of staged entry t
+  int len[G];  // its length
+  S va[G];     // A value of staged entry t
 };
 
 template <int G, bool WITH_VALS, typename S, typename F, typename Stop>
-__device__ __forceinline__ void walk_products(int tg, int a0, int a1, const int* __restrict__ ciA,
+__device__ __forceinline__ void walk_products(int tg, int lb, int a0, int a1, const int* __restrict__ ciA,
                                               const S* __restrict__ vA, const int* __restrict__ rpB,
                                               const int* __restrict__ ciB, const S* __restrict__ vB,
                                               WalkSmem<G, S>& w, F&& f, Stop&& stop) {
-  constexpr int U = 4;
+  constexpr int UT = 4;
   auto gsync = [&]() {
     if (G <= 32) __syncwarp(); else __syncthreads();
   };
-  const int lane = tg & 31, wid = tg >> 5;
+  const int nsub = G / lb;
+  const int q = tg / lb, sl = tg % lb;
   for (int ab = a0; ab < a1; ab += G) {
     const int nA = min(G, a1 - ab);
-    int len = 0;
     if (tg < nA) {
       const int ca = ciA[ab + tg];
       const int b0 = rpB[ca];
-      len = rpB[ca + 1] - b0;
       w.bs[tg] = b0;
+      w.len[tg] = rpB[ca + 1] - b0;
       if (WITH_VALS) w.va[tg] = vA[ab + tg];
     }
-    int inc = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (G > 32) {
-      if (lane == 31) w.wtot[wid] = inc;
-      __syncthreads();
-      int off = 0;
-      for (int k = 0; k < wid; ++k) off += w.wtot[k];
-      inc += off;
-    }
-    w.pre[tg] = inc;  // entries t >= nA repeat the total (len 0)
     gsync();
-    const int total = w.pre[G - 1];
-    for (int p0 = 0; p0 < total; p0 += G * U) {
-      int c[U];
-      S v[U];
+    for (int t0 = q; t0 < nA; t0 += nsub * UT) {
+      int c[UT];
+      S v[UT];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int p = p0 + u * G + tg;
+      for (int u = 0; u < UT; ++u) {
+        const int t = t0 + u * nsub;
         c[u] = -1;
-        if (p < total) {
-          // smallest idx with pre[idx] > p
-          int lo = 0, hi = nA - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (w.pre[mid] > p) hi = mid; else lo = mid + 1;
-          }
-          const int first = (lo == 0) ? 0 : w.pre[lo - 1];
-          const int jb = w.bs[lo] + (p - first);
+        if (t < nA && sl < w.len[t]) {
+          const int jb = w.bs[t] + sl;
           c[u] = ld_stream(ciB + jb);
-          if (WITH_VALS) v[u] = ld_stream(vB + jb) * w.va[lo];  // b_val * val (impl_seq.hpp:163)
+          if (WITH_VALS) v[u] = ld_stream(vB + jb) * w.va[t];  // b_val * val (impl_seq.hpp:163)
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < UT; ++u)
         if (c[u] >= 0) f(c[u], WITH_VALS ? v[u] : S(0));
+      // B rows longer than the sub-warp
+#pragma unroll 1
+      for (int u = 0; u < UT; ++u) {
+        const int t = t0 + u * nsub;
+        if (t < nA)
+          for (int off = sl + lb; off < w.len[t]; off += lb) {
+            const int jb = w.bs[t] + off;
+            f(ld_stream(ciB + jb), WITH_VALS ? ld_stream(vB + jb) * w.va[t] : S(0));
+          }
+      }
       if (stop()) break;
     }
     gsync();  // staging is rewritten by the next batch
@@ -308,7 +295,7 @@ __device__ __forceinline__ unsigned hash_mul(int c, int log2slots) {
 
 template <int G, int LOG2SLOTS>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
-    sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA,
+    sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                     const int* __restrict__ ciA, const int* __restrict__ rpB, const int* __restrict__ ciB,
                     int* __restrict__ row_nnz) {
   constexpr int SLOTS = 1 << LOG2SLOTS;
@@ -329,7 +316,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   const int i = active ? rows[ridx] : 0;
   const int a0 = active ? rpA[i] : 0, a1 = active ? rpA[i + 1] : 0;
   walk_products<G, false, float>(
-      tg, a0, a1, ciA, (const float*)nullptr, rpB, ciB, (const float*)nullptr, sm_walk[g],
+      tg, lb, a0, a1, ciA, (const float*)nullptr, rpB, ciB, (const float*)nullptr, sm_walk[g],
       [&](int c, float) {
         unsigned h = hash_mul(c, LOG2SLOTS);
         while (true) {
@@ -400,27 +387,43 @@ __device__ __forceinline__ void smem_add(S* p, S v) {
   atomicAdd(p, v);
 }
 
-template <typename S, int G, int SLOTS, int PAD>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP>
+struct NumLayout {
+  static constexpr int TOT = KSLOTS + PAD;
+  static constexpr int WORDS = (TOT + 31) / 32;
+  // per row-group: vals[VCAP] | keys[TOT] | wpre[WORDS+1] | wmask[WORDS]
+  static constexpr size_t PER = sizeof(S) * VCAP + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
+  static constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
+};
+
+template <typename S, int G, int KSLOTS, int PAD, int VCAP>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
-    num_hash_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA,
+    num_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                     const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
                     const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
                     int* __restrict__ ciC, S* __restrict__ vC, const int* __restrict__ cmin_arr,
                     const int* __restrict__ cmax_arr, int* __restrict__ fb_rows, int* __restrict__ fb_count) {
+  // Sorted-by-construction accumulator.  The key table has >= 4x the row's nnz slots (load <= 0.25);
+  // the slot of column c starts at the MONOTONE map h(c); keys are placed with atomicMin and the
+  // displaced (larger) key is carried to the next slot -- ordered linear probing.  Every slot only
+  // ever decreases and a carried key is never smaller than what it leaves behind, so at quiescence
+  // each probe cluster is ascending and clusters are ordered by the monotone map: the occupied slots
+  // read left to right ARE the sorted row.  An occupancy prefix turns slot -> output position; values
+  // are accumulated by output position in a second walk over the products (keys no longer move) and
+  // leave fully coalesced.  Dense rows (span <= KSLOTS) use h(c) = c - cmin: no probing at all.
+  using L = NumLayout<S, G, KSLOTS, PAD, VCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
-  constexpr int TOT = SLOTS + PAD;
-  constexpr int WORDS = (TOT + 31) / 32;
+  constexpr int TOT = L::TOT;
+  constexpr int WORDS = L::WORDS;
+  constexpr int INF = INT_MAX;
   extern __shared__ __align__(16) unsigned char smraw[];
-  // layout per row-group: vals[TOT] | keys[TOT] | wpre[WORDS] | wmask[WORDS]
-  constexpr size_t PER = sizeof(S) * TOT + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
-  constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
   __shared__ int sm_flag[RPC];
   __shared__ WalkSmem<G, S> sm_walk[RPC];
   const int g = threadIdx.x / G, tg = threadIdx.x % G;
-  unsigned char* base = smraw + (size_t)g * PER_AL;
+  unsigned char* base = smraw + (size_t)g * L::PER_AL;
   S* vals = reinterpret_cast<S*>(base);
-  int* keys = reinterpret_cast<int*>(base + sizeof(S) * TOT);
+  int* keys = reinterpret_cast<int*>(base + sizeof(S) * VCAP);
   int* wpre = keys + TOT;
   unsigned* wmask = reinterpret_cast<unsigned*>(wpre + WORDS + 1);
   const int ridx = blockIdx.x * RPC + g;
@@ -428,99 +431,93 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   auto gsync = [&]() {
     if (G <= 32) __syncwarp(); else __syncthreads();
   };
-  for (int s = tg; s < TOT; s += G) {
-    keys[s] = EMPTY;
-    vals[s] = S(0);
-  }
+  for (int s = tg; s < TOT; s += G) keys[s] = INF;
+  for (int s = tg; s < VCAP; s += G) vals[s] = S(0);
   if (tg == 0) sm_flag[g] = 0;
   gsync();
   int i = 0, cbase = 0, nz = 0;
-  bool dense = false;
   if (active) {
     i = rows[ridx];
     cbase = rpC[i];
     nz = rpC[i + 1] - cbase;
   }
-  {
-    const bool work = active && nz > 0;
-    const int cmin = work ? cmin_arr[i] : 0;
-    const long long span = work ? ((long long)cmax_arr[i] - cmin + 1) : 1;
-    dense = span <= SLOTS;
-    // monotone map column -> slot in [0, SLOTS)
-    const unsigned long long mult = dense ? 0ull : (((unsigned long long)SLOTS << 32) / (unsigned long long)span);
-    const int a0 = work ? rpA[i] : 0, a1 = work ? rpA[i + 1] : 0;
-    walk_products<G, true, S>(
-        tg, a0, a1, ciA, vA, rpB, ciB, vB, sm_walk[g],
-        [&](int c, S v) {
-          int h = dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
-          while (true) {
-            const int kcur = ((volatile int*)keys)[h];
-            if (kcur == c) break;
-            if (kcur == EMPTY) {
-              const int old = atomicCAS(&keys[h], EMPTY, c);
-              if (old == EMPTY || old == c) break;
-            }
-            if (++h >= TOT) {
-              sm_flag[g] = 1;  // probe ran off the pad: row goes to the fallback kernel
-              return;
-            }
+  const bool work = active && nz > 0;
+  const int cmin = work ? cmin_arr[i] : 0;
+  const long long span = work ? ((long long)cmax_arr[i] - cmin + 1) : 1;
+  const bool dense = span <= KSLOTS;
+  const unsigned long long mult = dense ? 0ull : (((unsigned long long)KSLOTS << 32) / (unsigned long long)span);
+  const int a0 = work ? rpA[i] : 0, a1 = work ? rpA[i + 1] : 0;
+  auto slot_of = [&](int c) -> int {
+    return dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
+  };
+  auto stopped = [&]() { return ((volatile int*)sm_flag)[g] != 0; };
+  // ---- walk 1: keys
+  walk_products<G, false, S>(
+      tg, lb, a0, a1, ciA, vA, rpB, ciB, vB, sm_walk[g],
+      [&](int c, S) {
+        int h = slot_of(c);
+        while (true) {
+          const int old = atomicMin(&keys[h], c);
+          if (old == c || old == INF) return;  // already there / took an empty slot
+          if (old > c) c = old;                // displaced a larger key: carry it on
+          if (++h >= TOT) {
+            sm_flag[g] = 1;  // ran off the pad: row goes to the fallback kernel
+            return;
           }
-          smem_add(&vals[h], v);
-        },
-        [&]() { return ((volatile int*)sm_flag)[g] != 0; });
-  }
+        }
+      },
+      stopped);
   gsync();
   const bool overflow = sm_flag[g] != 0;
   if (active && overflow && tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
-  if (active && nz > 0 && !overflow) {
-    // occupancy prefix: wpre[w] = number of occupied slots before word w
+  // ---- occupancy prefix: wpre[w] = occupied slots before word w; column indices leave now
+  if (work && !overflow) {
     for (int w = tg; w < WORDS; w += G) {
       unsigned msk = 0u;
       const int s0 = w * 32;
 #pragma unroll 8
       for (int b = 0; b < 32; ++b)
-        if (s0 + b < TOT && keys[s0 + b] != EMPTY) msk |= (1u << b);
+        if (s0 + b < TOT && keys[s0 + b] != INF) msk |= (1u << b);
       wmask[w] = msk;
       wpre[w] = __popc(msk);
     }
-    gsync();
-    if (tg < 32) {
-      int carry = 0;
-      for (int w0 = 0; w0 < WORDS; w0 += 32) {
-        const int w = w0 + tg;
-        const int v = w < WORDS ? wpre[w] : 0;
-        int inc = v;
+  }
+  gsync();
+  if (work && !overflow && tg < 32) {
+    int carry = 0;
+    for (int w0 = 0; w0 < WORDS; w0 += 32) {
+      const int w = w0 + tg;
+      const int v = w < WORDS ? wpre[w] : 0;
+      int inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (tg >= o) inc += t;
-        }
-        if (w < WORDS) wpre[w] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tg >= o) inc += t;
       }
-    }
-    gsync();
-    for (int s = tg; s < TOT; s += G) {
-      const int key = keys[s];
-      if (key == EMPTY) continue;
-      int pos = wpre[s >> 5] + __popc(wmask[s >> 5] & ((1u << (s & 31)) - 1u));
-      if (!dense) {
-        // rank inside the probe cluster: clusters are ordered, members are not
-        for (int t = s - 1; t >= 0; --t) {
-          const int kt = keys[t];
-          if (kt == EMPTY) break;
-          pos -= (kt > key);
-        }
-        for (int t = s + 1; t < TOT; ++t) {
-          const int kt = keys[t];
-          if (kt == EMPTY) break;
-          pos += (kt < key);
-        }
-      }
-      ciC[cbase + pos] = key;
-      vC[cbase + pos] = vals[s];
+      if (w < WORDS) wpre[w] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
+  gsync();
+  if (work && !overflow) {
+    for (int s = tg; s < TOT; s += G) {
+      const int key = keys[s];
+      if (key != INF) ciC[cbase + wpre[s >> 5] + __popc(wmask[s >> 5] & ((1u << (s & 31)) - 1u))] = key;
+    }
+  }
+  // ---- walk 2: values, accumulated by output position (a0 == a1 for idle / overflowed groups)
+  const int b0 = overflow ? 0 : a0, b1 = overflow ? 0 : a1;
+  walk_products<G, true, S>(
+      tg, lb, b0, b1, ciA, vA, rpB, ciB, vB, sm_walk[g],
+      [&](int c, S v) {
+        int h = slot_of(c);
+        while (keys[h] != c) ++h;  // present by construction
+        smem_add(&vals[wpre[h >> 5] + __popc(wmask[h >> 5] & ((1u << (h & 31)) - 1u))], v);
+      },
+      []() { return false; });
+  gsync();
+  if (work && !overflow)
+    for (int q = tg; q < nz; q += G) vC[cbase + q] = vals[q];
 }
 
 // fallback: global-memory hash (wrap-around, multiplicative) + in-place bitonic sort of the C row
@@ -697,27 +694,24 @@ static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const
   const size_t smem = sizeof(int) * (size_t)RPC * ((size_t)1 << LOG2SLOTS);
   auto kern = sym_hash_kernel<G, LOG2SLOTS>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, rpA, ciA, rpB, ciB, row_nnz);
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, std::min(lb, 32), rpA, ciA, rpB, ciB, row_nnz);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
 
-template <typename S, int G, int SLOTS, int PAD>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP>
 static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
                       const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
   const int nrows = p->num_off[bin + 1] - p->num_off[bin];
   if (nrows <= 0) return B200SP_OK;
+  using L = NumLayout<S, G, KSLOTS, PAD, VCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
-  constexpr int TOT = SLOTS + PAD;
-  constexpr int WORDS = (TOT + 31) / 32;
-  constexpr size_t PER = sizeof(S) * TOT + sizeof(int) * TOT + sizeof(int) * (2 * WORDS + 2);
-  constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
-  const size_t smem = PER_AL * RPC;
-  auto kern = num_hash_kernel<S, G, SLOTS, PAD>;
+  const size_t smem = L::PER_AL * RPC;
+  auto kern = num_hash_kernel<S, G, KSLOTS, PAD, VCAP>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], rpA, ciA, vA, rpB, ciB, vB, rpC,
-                                                      ciC, vC, p->cmin, p->cmax, p->fb_rows, p->fb_count);
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
+                                                      rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->fb_rows, p->fb_count);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -747,11 +741,12 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   // fallback list starts as the rows that are too long for shared memory
   B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_count, &p->fb_static, sizeof(int), cudaMemcpyHostToDevice, st));
   int rc;
-  if ((rc = launch_num<S, 32, 128, 32>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-  if ((rc = launch_num<S, 32, 512, 64>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-  if ((rc = launch_num<S, 128, 2048, 128>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-  if ((rc = launch_num<S, 256, 8192, 256>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-  if ((rc = launch_num<S, 512, 16384, 512>(st, p, 4, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  // <S, G, key slots (>= 4 x bin's max nnz), pad, max nnz>
+  if ((rc = launch_num<S, 32, 256, 32, 64>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 32, 1024, 64, 256>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 128, 4096, 128, 1024>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 256, 16384, 256, 4096>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+  if ((rc = launch_num<S, 512, 32768, 512, 8192>(st, p, 4, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
   num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
                                                   ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
   B200SP_LAUNCH_CHECK();
