@@ -17,8 +17,11 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("OMP_PROC_BIND", "close")  # reference protocol for the CPU leg
-os.environ.setdefault("OMP_PLACES", "cores")
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    # reference protocol for the CPU leg.  Never under torchrun: with
+    # OMP_NUM_THREADS=1 per rank every rank's only thread would be pinned to the same first core.
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
 import subprocess
 import sys
 import threading
@@ -165,7 +168,7 @@ def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
                           f"min {min(ts) * 1e3:.2f} ms; {alg_bytes(nnz, rows, ncols) / mean / 1e9:.1f} GB/s algorithmic"}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's own CPU implementation of the path (its OpenMP functor loop,
     restated in oracle/kk_oracle.c -- the reference cannot be built here without Kokkos >= 4.6.02),
     all host threads, on a bounded sample of the workload per step."""
@@ -202,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": round(gf, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -217,11 +220,23 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: all-gather of y fused into the SpMV kernel (P2P stores) or NCCL after it")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # libraries (NCCL prints its version line) must not pollute stdout: the JSON line is the only thing on it
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -245,22 +260,41 @@ def main():
     x_host = matgen.fill(n_total, -1.0, 1.0, 1)
     A = sp.CrsMatrix(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev), torch.from_numpy(va).to(dev), n_total)
     x = torch.from_numpy(x_host).to(dev)
-    y = torch.empty(nrows, dtype=torch.float64, device=dev)
-    x_next = torch.empty(n_total, dtype=torch.float64, device=dev) if world > 1 else None
     equal_shards = (n_total % world == 0)
     h = sp.SPMVHandle(sp.SPMV_DEFAULT)
     h.tune(args.cfg, args.lpr, args.ctas)
     lib = kk._lib.sparse()
+    # multi-GPU: the all-gather of y is fused into the SpMV kernel -- every rank stores its y rows straight
+    # into all peers' next-x buffers over NVLink (symmetric memory, P2P stores), then a device-side barrier.
+    # Fallback (symmetric memory unavailable or --collective nccl): SpMV + NCCL all_gather_into_tensor.
+    x_next, symm, extra, collective = None, None, [], "none"
+    if world > 1:
+        assert equal_shards
+        collective = "nccl_all_gather"
+        if args.collective == "fused":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                x_next = symm_mem.empty(n_total, dtype=torch.float64, device=dev)
+                symm = symm_mem.rendezvous(x_next, dist.group.WORLD)
+                ptrs = list(symm.buffer_ptrs)
+                extra = [ptrs[q] + r0 * 8 for q in range(world) if q != rank]
+                collective = "fused_p2p_store_allgather"
+            except Exception as e:  # pragma: no cover
+                log(f"[rank {rank}] symmetric memory unavailable ({e}); falling back to NCCL all-gather")
+                x_next, symm = None, None
+        if x_next is None:
+            x_next = torch.empty(n_total, dtype=torch.float64, device=dev)
+    y = x_next[r0:r1] if symm is not None else torch.empty(nrows, dtype=torch.float64, device=dev)
 
     def step():
-        sp.spmv(h, "N", 1.0, A, x, 0.0, y)
-        if world > 1:
-            # config 5: all-gather of y (forms the next x); data stays on NVLink, result unused by the next
-            # step's input so that every step multiplies the same x (fixed work per step)
-            if equal_shards:
+        if symm is not None:
+            sp.spmv_scatter(h, 1.0, A, x, y, extra)   # y -> local slot and all peers' slots
+            symm.barrier(channel=0)                    # all ranks' rows have landed everywhere
+        else:
+            sp.spmv(h, "N", 1.0, A, x, 0.0, y)
+            if world > 1:
                 dist.all_gather_into_tensor(x_next, y)
-            else:
-                raise RuntimeError("unequal shards")
 
     # ---- parity on this rank's shard: sampled rows vs the oracle's Serial path (O1)
     step()
@@ -284,8 +318,17 @@ def main():
         check = float(np.max(np.abs(got - yref) / np.maximum(scale, 1e-300)))
         assert check <= 1e-10, f"parity failure on rank {rank}: {check}"
         if world > 1:
-            xn = x_next[r0 + b0: r0 + b1].cpu().numpy()
-            assert np.array_equal(xn, got), "all-gather placed y in the wrong slot"
+            # every rank's rows must have landed in this rank's copy of the next x: compare a slice of
+            # each block with what its owner computed
+            torch.cuda.synchronize()
+            dist.barrier()
+            blk = n_total // world
+            probe = torch.stack([x_next[q * blk: q * blk + 4096] for q in range(world)])
+            gathered = [torch.empty_like(probe) for _ in range(world)]
+            dist.all_gather(gathered, probe)
+            for q in range(world):
+                assert torch.equal(gathered[q], probe), f"rank {rank}: next-x differs from rank {q}'s copy"
+            assert np.array_equal(x_next[r0 + b0: r0 + b1].cpu().numpy(), got), "y landed in the wrong slot"
 
     # ---- timed region (device time, CUDA events on the launching stream, max over ranks)
     for _ in range(args.warmup):
@@ -368,10 +411,10 @@ def main():
             "config": {
                 "workload": f"spmv fp64 CrsMatrix (int32 offsets/ordinals), lap27({args.grid}x{args.grid}x{args.grid * world}) x {NDOF} dof: "
                             f"{n_total} rows, {total_nnz} nnz ({total_nnz / n_total:.1f}/row), alpha=1 beta=0, single vector"
-                            + (f", row-partitioned over {world} GPUs + NCCL all-gather of y each step" if world > 1 else ""),
+                            + (f", row-partitioned over {world} GPUs, all-gather of y each step ({collective})" if world > 1 else ""),
                 "baseline_config": "configs[1]" if world == 1 else "configs[4]",
                 "cache": "inputs (matrix %.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (nnz * 12 / 1e9),
-                "kernel": kernel_name, "parity_max_scaled_err": check,
+                "kernel": kernel_name, "parity_max_scaled_err": check, "collective": collective,
             },
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4),
@@ -388,7 +431,7 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -93,6 +93,17 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode,
                                 const double* vals, const double* x_host, double beta,
                                 double* y_host);
 
+/* Row-block-partitioned SpMV with the all-gather of y fused into the kernel (multi-GPU, config 5):
+ * y = alpha*A*x for this rank's row block is stored to `y` AND to `n_extra` (<= 7) further device
+ * pointers -- the slots of this row block inside the peers' next-x buffers, mapped into this process
+ * (CUDA IPC / symmetric memory) -- with plain P2P stores from the SpMV kernel itself, so the NVLink
+ * transfer overlaps the compute row by row.  No reference counterpart (the reference is single-process,
+ * README.md:12-16); result identical to b200sp_spmv_f64_i32 + all-gather.  beta is 0.  The caller
+ * synchronises the ranks between steps (bench.py uses the symmetric-memory barrier). */
+int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* plan, void* stream, int m, int n, int64_t nnz, double alpha,
+                                const int* row_ptr, const int* col_idx, const double* vals, const double* x,
+                                double* y, int n_extra, void* const* y_extra);
+
 /* ---- SpMV rank-2 (multivector): Y = beta*Y + alpha*op(A)*X, k columns --- */
 /* Replaces SPMV_MV<Kokkos::Cuda,...,false,true>::spmv_mv -> cusparseSpMM
  * (sparse/tpls/KokkosSparse_spmv_mv_tpl_spec_decl.hpp:97-225).

@@ -87,12 +87,19 @@ __device__ __forceinline__ S subwarp_sum(S v) {
   return v;
 }
 
+// extra destinations of y: peer GPUs' x buffers (fused all-gather over NVLink)
+struct YExtra {
+  void* p[7];
+  int n;
+};
+
 template <typename S>
-__device__ __forceinline__ void store_y(S* __restrict__ y, int r, S sum, S alpha, S beta) {
+__device__ __forceinline__ void store_y(S* __restrict__ y, int r, S sum, S alpha, S beta, const YExtra& ex) {
   // reference epilogue (spmv_impl.hpp:124-131): sum *= alpha; y = beta*y + sum
   sum *= alpha;
-  if (beta == S(0)) y[r] = sum;
-  else y[r] = beta * y[r] + sum;
+  const S v = (beta == S(0)) ? sum : beta * y[r] + sum;
+  y[r] = v;
+  for (int d = 0; d < ex.n; ++d) static_cast<S*>(ex.p[d])[r] = v;  // P2P stores
 }
 
 // ---------------------------------------------------------------------------
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
                                                           const int* __restrict__ col_idx,
                                                           const S* __restrict__ vals,
                                                           const S* __restrict__ x, S* __restrict__ y,
-                                                          S alpha, S beta) {
+                                                          S alpha, S beta, YExtra ex) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
       for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
     }
     sum = subwarp_sum<LPR>(sum);
-    if (r < m && sl == 0) store_y(y, r, sum, alpha, beta);
+    if (r < m && sl == 0) store_y(y, r, sum, alpha, beta, ex);
   }
 }
 
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(256) spmv_longrow_kernel(const int* __restrict
                                                            const int* __restrict__ col_idx,
                                                            const S* __restrict__ vals,
                                                            const S* __restrict__ x, S* __restrict__ y,
-                                                           S alpha, S beta) {
+                                                           S alpha, S beta, YExtra ex) {
   __shared__ S warp_part[8];
   const int n_long = *n_long_ptr;
   for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(256) spmv_longrow_kernel(const int* __restrict
       S t = S(0);
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += warp_part[w];
-      store_y(y, r, t, alpha, beta);
+      store_y(y, r, t, alpha, beta, ex);
     }
     __syncthreads();
   }
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
     spmv_tile_kernel(int m, int64_t nnz, int n_tiles, int LMAX, const int4* __restrict__ tiles,
                      const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                      const S* __restrict__ vals, const S* __restrict__ x, S* __restrict__ y, S alpha,
-                     S beta) {
+                     S beta, YExtra ex) {
   using Smem = TileSmem<S, CAP, STAGES>;
   constexpr int RCAP = Smem::RCAP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
           for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
         }
         sum = subwarp_sum<LPR>(sum);
-        if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta);
+        if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta, ex);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -462,6 +469,7 @@ struct b200sp_spmv_plan {
   int chunk_m = -1;
   int64_t chunk_nnz = -1;
   char last_kernel[96] = "none";
+  b200sp::YExtra extra = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
 };
 
 namespace b200sp {
@@ -591,7 +599,7 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   int grid = std::min(p->n_tiles, sm_count() * per_sm);
   if (grid < 1) grid = 1;
   kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, p->n_tiles, p->LMAX, p->tiles, row_ptr, col_idx, vals, x, y,
-                                          alpha, beta);
+                                          alpha, beta, p->extra);
   B200SP_LAUNCH_CHECK();
   snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d,UNR=%d>grid=%d",
            sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, UNR, grid);
@@ -626,9 +634,11 @@ static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, c
   const int64_t warps = ((int64_t)m + rpw - 1) / rpw;
   int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16);
   if (blocks < 1) blocks = 1;
+  YExtra ex = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
+  if (p) ex = p->extra;
 #define B200SP_VEC(L)                                                                              \
   case L:                                                                                          \
-    spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta); \
+    spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta, ex); \
     break;
   switch (lpr) {
     B200SP_VEC(2)
@@ -711,7 +721,8 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   if (!p->n_long_known && cudaEventQuery(p->n_long_event) == cudaSuccess) p->n_long_known = true;
   if (!(p->n_long_known && *p->n_long_host == 0)) {
     int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
-    spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta);
+    spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta,
+                                                   p->extra);
     B200SP_LAUNCH_CHECK();
   }
   return B200SP_OK;
@@ -792,6 +803,23 @@ int b200sp_spmv_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, 
                         const int* row_ptr, const int* col_idx, const float* vals, const float* x, float beta,
                         float* y) {
   return spmv_impl<float>(plan, (cudaStream_t)stream, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, x, beta, y);
+}
+
+int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* p, void* stream, int m, int n, int64_t nnz, double alpha,
+                                const int* row_ptr, const int* col_idx, const double* vals, const double* x,
+                                double* y, int n_extra, void* const* y_extra) {
+  B200SP_REQUIRE(p != nullptr, "spmv_scatter: a plan is required");
+  B200SP_REQUIRE(n_extra >= 0 && n_extra <= 7, "spmv_scatter: at most 7 extra destinations (8 GPUs), got %d", n_extra);
+  B200SP_REQUIRE(n_extra == 0 || y_extra != nullptr, "spmv_scatter: y_extra is null");
+  if (alpha == 0.0 || m == 0 || n == 0 || nnz == 0) {
+    set_error("spmv_scatter: alpha == 0 / empty matrix is not supported by the fused all-gather form");
+    return B200SP_ERR_INVALID_ARGUMENT;
+  }
+  p->extra.n = n_extra;
+  for (int d = 0; d < n_extra; ++d) p->extra.p[d] = y_extra[d];
+  const int rc = spmv_impl<double>(p, (cudaStream_t)stream, 'N', m, n, nnz, alpha, row_ptr, col_idx, vals, x, 0.0, y);
+  p->extra.n = 0;
+  return rc;
 }
 
 int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, int m, int n, int64_t nnz,

@@ -145,6 +145,16 @@ def spmv(handle, mode, alpha, A, x, beta, y):
     return y
 
 
+def spmv_scatter(handle, alpha, A, x, y, extra_ptrs):
+    """Fused SpMV + all-gather: y (this rank's row block) is also stored to the raw device pointers in
+    `extra_ptrs` (peer GPUs' next-x slots mapped into this process)."""
+    arr = (C.c_void_p * max(len(extra_ptrs), 1))(*[C.c_void_p(int(q)) for q in extra_ptrs])
+    check(_lib.sparse().b200sp_spmv_scatter_f64_i32(
+        handle._plan, _stream(), A.numRows(), A.numCols(), A.nnz(), alpha, _ptr(A.row_map), _ptr(A.entries),
+        _ptr(A.values), _ptr(x), _ptr(y), len(extra_ptrs), arr))
+    return y
+
+
 def spmv_hostvec(handle, mode, alpha, A, x_host, beta, y_host):
     """End-to-end entry: host x / y (pinned), device-resident matrix."""
     m, n = A.numRows(), A.numCols()
