@@ -220,8 +220,10 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
-                    help="N>1: all-gather of y fused into the SpMV kernel (P2P stores) or NCCL after it")
+    ap.add_argument("--collective", default="pipelined", choices=["pipelined", "fused", "nccl"],
+                    help="N>1: all-gather of y pipelined behind the compute (copy-engine pushes over NVLink), "
+                         "fused into the SpMV kernel (P2P stores), or NCCL after it")
+    ap.add_argument("--chunks", type=int, default=4)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -258,48 +260,45 @@ def main():
     nrows = r1 - r0
     nnz = len(ci)
     x_host = matgen.fill(n_total, -1.0, 1.0, 1)
-    A = sp.CrsMatrix(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev), torch.from_numpy(va).to(dev), n_total)
     x = torch.from_numpy(x_host).to(dev)
-    equal_shards = (n_total % world == 0)
-    h = sp.SPMVHandle(sp.SPMV_DEFAULT)
-    h.tune(args.cfg, args.lpr, args.ctas)
     lib = kk._lib.sparse()
-    # multi-GPU: the all-gather of y is fused into the SpMV kernel -- every rank stores its y rows straight
-    # into all peers' next-x buffers over NVLink (symmetric memory, P2P stores), then a device-side barrier.
-    # Fallback (symmetric memory unavailable or --collective nccl): SpMV + NCCL all_gather_into_tensor.
-    x_next, symm, extra, collective = None, None, [], "none"
+    # multi-GPU: row blocks + all-gather of y pipelined behind the compute over NVLink (multigpu.py)
+    op = None
+    collective = "none"
     if world > 1:
-        assert equal_shards
-        collective = "nccl_all_gather"
-        if args.collective == "fused":
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
+        from kokkos_kernels_b200 import multigpu
 
-                x_next = symm_mem.empty(n_total, dtype=torch.float64, device=dev)
-                symm = symm_mem.rendezvous(x_next, dist.group.WORLD)
-                ptrs = list(symm.buffer_ptrs)
-                extra = [ptrs[q] + r0 * 8 for q in range(world) if q != rank]
-                collective = "fused_p2p_store_allgather"
-            except Exception as e:  # pragma: no cover
-                log(f"[rank {rank}] symmetric memory unavailable ({e}); falling back to NCCL all-gather")
-                x_next, symm = None, None
-        if x_next is None:
-            x_next = torch.empty(n_total, dtype=torch.float64, device=dev)
-    y = x_next[r0:r1] if symm is not None else torch.empty(nrows, dtype=torch.float64, device=dev)
+        try:
+            op = multigpu.RowBlockSpMV(rp, ci, va, n_total, r0, r1, dev, mode=args.collective, chunks=args.chunks,
+                                       tune=(args.cfg, args.lpr, args.ctas))
+        except Exception as e:  # symmetric memory unavailable
+            log(f"[rank {rank}] {args.collective} path unavailable ({e}); falling back to NCCL all-gather")
+            op = multigpu.RowBlockSpMV(rp, ci, va, n_total, r0, r1, dev, mode="nccl", tune=(args.cfg, args.lpr, args.ctas))
+        collective = op.mode
+        x_next, y = op.x_next, op.y
+        A, h = op.A_full, op.h_full
+    else:
+        A = sp.CrsMatrix(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev), torch.from_numpy(va).to(dev), n_total)
+        h = sp.SPMVHandle(sp.SPMV_DEFAULT)
+        h.tune(args.cfg, args.lpr, args.ctas)
+        y = torch.empty(nrows, dtype=torch.float64, device=dev)
 
-    def step():
-        if symm is not None:
-            sp.spmv_scatter(h, 1.0, A, x, y, extra)   # y -> local slot and all peers' slots
-            symm.barrier(channel=0)                    # all ranks' rows have landed everywhere
+    def local_spmv():
+        if op is not None:
+            op.local_spmv_only(x)
         else:
             sp.spmv(h, "N", 1.0, A, x, 0.0, y)
-            if world > 1:
-                dist.all_gather_into_tensor(x_next, y)
+
+    def step():
+        if op is not None:
+            op.step(x)
+        else:
+            sp.spmv(h, "N", 1.0, A, x, 0.0, y)
 
     # ---- parity on this rank's shard: sampled rows vs the oracle's Serial path (O1)
     step()
     torch.cuda.synchronize()
-    kernel_name = h.last_kernel()
+    kernel_name = op.kernel_name() if op is not None else h.last_kernel()
     check = None
     if not args.no_check:
         import oracle_lib
@@ -366,7 +365,7 @@ def main():
     torch.cuda.synchronize()
     k0.record()
     for _ in range(args.steps):
-        sp.spmv(h, "N", 1.0, A, x, 0.0, y)
+        local_spmv()
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / args.steps

@@ -104,6 +104,16 @@ int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* plan, void* stream, int m, int
                                 const int* row_ptr, const int* col_idx, const double* vals, const double* x,
                                 double* y, int n_extra, void* const* y_extra);
 
+/* Copy `bytes` from device pointer src to n_dst device pointers (peer GPUs' buffers mapped into this
+ * process) with copy-engine transfers on `stream` -- the push half of the pipelined row-block SpMV
+ * (kokkos-kernels_b200/multigpu.py): chunk c of y is pushed over NVLink while chunk c+1 is computed. */
+int b200sp_peer_push(void* stream, const void* src, int64_t bytes, int n_dst, void* const* dsts);
+/* Same, one copy per communication stream (n_dst streams), each ordered after everything enqueued on
+ * compute_stream so far; b200sp_peer_join makes compute_stream wait for all of them. */
+int b200sp_peer_push_async(void* compute_stream, void* const* comm_streams, int n_dst, void* const* dsts,
+                           const void* src, int64_t bytes);
+int b200sp_peer_join(void* compute_stream, void* const* comm_streams, int n);
+
 /* ---- SpMV rank-2 (multivector): Y = beta*Y + alpha*op(A)*X, k columns --- */
 /* Replaces SPMV_MV<Kokkos::Cuda,...,false,true>::spmv_mv -> cusparseSpMM
  * (sparse/tpls/KokkosSparse_spmv_mv_tpl_spec_decl.hpp:97-225).

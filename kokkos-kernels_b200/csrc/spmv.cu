@@ -822,6 +822,50 @@ int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* p, void* stream, int m, int n,
   return rc;
 }
 
+// event pool for the push / join helpers (events may be re-recorded once the waits on them are enqueued)
+static cudaEvent_t pool_event() {
+  static cudaEvent_t ev[64];
+  static bool init[64];
+  static std::atomic<unsigned> next{0};
+  const unsigned i = next.fetch_add(1) % 64;
+  if (!init[i]) {
+    if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    init[i] = true;
+  }
+  return ev[i];
+}
+
+int b200sp_peer_push_async(void* compute_stream, void* const* comm_streams, int n_dst, void* const* dsts,
+                           const void* src, int64_t bytes) {
+  B200SP_REQUIRE(bytes >= 0 && n_dst >= 0 && (n_dst == 0 || (dsts && comm_streams)), "peer_push_async: bad arguments");
+  if (n_dst == 0) return B200SP_OK;
+  cudaEvent_t ev = pool_event();
+  B200SP_REQUIRE(ev != nullptr, "peer_push_async: cannot create event");
+  B200SP_CUDA_TRY(cudaEventRecord(ev, (cudaStream_t)compute_stream));
+  for (int d = 0; d < n_dst; ++d) {
+    B200SP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)comm_streams[d], ev, 0));
+    B200SP_CUDA_TRY(cudaMemcpyAsync(dsts[d], src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)comm_streams[d]));
+  }
+  return B200SP_OK;
+}
+
+int b200sp_peer_join(void* compute_stream, void* const* comm_streams, int n) {
+  for (int d = 0; d < n; ++d) {
+    cudaEvent_t ev = pool_event();
+    B200SP_REQUIRE(ev != nullptr, "peer_join: cannot create event");
+    B200SP_CUDA_TRY(cudaEventRecord(ev, (cudaStream_t)comm_streams[d]));
+    B200SP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)compute_stream, ev, 0));
+  }
+  return B200SP_OK;
+}
+
+int b200sp_peer_push(void* stream, const void* src, int64_t bytes, int n_dst, void* const* dsts) {
+  B200SP_REQUIRE(bytes >= 0 && n_dst >= 0 && (n_dst == 0 || dsts != nullptr), "peer_push: bad arguments");
+  for (int d = 0; d < n_dst; ++d)
+    B200SP_CUDA_TRY(cudaMemcpyAsync(dsts[d], src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200SP_OK;
+}
+
 int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, int m, int n, int64_t nnz,
                                 double alpha, const int* row_ptr, const int* col_idx, const double* vals,
                                 const double* x_host, double beta, double* y_host) {

@@ -1,0 +1,102 @@
+"""Row-block-partitioned SpMV across the GPUs of one box with the all-gather of y pipelined behind
+the compute (BASELINE.json configs[4]; no reference counterpart -- the reference is single-process).
+
+Each rank owns rows [r0, r1) of A (row_ptr rebased, global columns) and a full copy of x.  The local
+rows are cut into `chunks` pieces; piece c is computed by the TMA-tiled SpMV kernel straight into this
+rank's slot of the next-x buffer and, as soon as it is done, pushed to the same slot of every peer's
+next-x buffer by copy-engine transfers over NVLink (peer buffers are mapped through symmetric memory),
+while piece c+1 is being computed.  A device-side barrier closes the step.  Results are bit-identical
+to the single-GPU SpMV (same kernel, same per-row order).
+
+modes: "pipelined" (default), "fused" (P2P stores issued by the SpMV kernel itself,
+b200sp_spmv_scatter_f64_i32), "nccl" (SpMV then all_gather_into_tensor)."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, sparse as sp
+
+
+class RowBlockSpMV:
+    def __init__(self, rp, ci, va, n_total, r0, r1, device, mode="pipelined", chunks=4, tune=(-1, -1, -1)):
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.n_total, self.r0, self.r1, self.dev, self.mode = n_total, r0, r1, device, mode
+        nrows = r1 - r0
+        assert n_total % self.world == 0 and nrows == n_total // self.world, "equal row blocks expected"
+        self.ci_d = torch.from_numpy(ci).to(device)
+        self.va_d = torch.from_numpy(va).to(device)
+        self.symm = None
+        if mode in ("pipelined", "fused"):
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.x_next = symm_mem.empty(n_total, dtype=torch.float64, device=device)
+            self.symm = symm_mem.rendezvous(self.x_next, dist.group.WORLD)
+            self.peer_ptrs = [int(p) for p in self.symm.buffer_ptrs]
+        else:
+            self.x_next = torch.empty(n_total, dtype=torch.float64, device=device)
+        self.y = self.x_next[r0:r1]
+        # chunk boundaries on rows whose first entry is 16-byte aligned in col_idx / vals (TMA path)
+        if mode != "pipelined":
+            chunks = 1
+        bounds = [0]
+        for c in range(1, chunks):
+            r = (nrows * c) // chunks
+            while r < nrows and rp[r] % 4 != 0:
+                r += 1
+            if r > bounds[-1] and r < nrows:
+                bounds.append(r)
+        bounds.append(nrows)
+        self.pieces = []
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            s0, s1 = int(rp[c0]), int(rp[c1])
+            rpc = torch.from_numpy((rp[c0:c1 + 1].astype(np.int64) - s0).astype(np.int32)).to(device)
+            A = sp.CrsMatrix(rpc, self.ci_d[s0:s1], self.va_d[s0:s1], n_total)
+            h = sp.SPMVHandle(sp.SPMV_DEFAULT)
+            h.tune(*tune)
+            yv = self.y[c0:c1]
+            dsts = []
+            if self.symm is not None:
+                dsts = [self.peer_ptrs[q] + (r0 + c0) * 8 for q in range(self.world) if q != self.rank]
+            arr = (C.c_void_p * max(len(dsts), 1))(*[C.c_void_p(d) for d in dsts])
+            self.pieces.append((A, h, yv, dsts, arr, torch.cuda.Event()))
+        # whole-shard view (host-vector end-to-end path, parity checks)
+        self.A_full = sp.CrsMatrix(torch.from_numpy(np.ascontiguousarray(rp)).to(device), self.ci_d, self.va_d, n_total)
+        self.h_full = sp.SPMVHandle(sp.SPMV_DEFAULT)
+        # one communication stream per peer: the pushes of a piece run concurrently on the copy engines
+        self.comm = [torch.cuda.Stream(device=device) for _ in range(max(self.world - 1, 1))]
+        self.comm_arr = (C.c_void_p * len(self.comm))(*[C.c_void_p(s.cuda_stream) for s in self.comm])
+
+    def kernel_name(self):
+        return self.pieces[0][1].last_kernel()
+
+    def nnz(self):
+        return self.ci_d.numel()
+
+    def step(self, x):
+        """x_next <- all-gather(A_local @ x); returns the next-x buffer (valid on every rank after the call's
+        stream work completes)."""
+        lib = _lib.sparse()
+        cur = torch.cuda.current_stream()
+        if self.mode == "fused":
+            A, h, yv, dsts, arr, ev = self.pieces[0]
+            sp.spmv_scatter(h, 1.0, A, x, yv, dsts)
+            self.symm.barrier(channel=0)
+        elif self.mode == "pipelined":
+            cs = C.c_void_p(cur.cuda_stream)
+            for A, h, yv, dsts, arr, ev in self.pieces:
+                sp.spmv(h, "N", 1.0, A, x, 0.0, yv)
+                _lib.check(lib.b200sp_peer_push_async(cs, self.comm_arr, len(dsts), arr, C.c_void_p(yv.data_ptr()),
+                                                      yv.numel() * 8))
+            _lib.check(lib.b200sp_peer_join(cs, self.comm_arr, len(self.comm) if self.world > 1 else 0))
+            self.symm.barrier(channel=0)
+        else:
+            A, h, yv, dsts, arr, ev = self.pieces[0]
+            sp.spmv(h, "N", 1.0, A, x, 0.0, yv)
+            dist.all_gather_into_tensor(self.x_next, yv)
+        return self.x_next
+
+    def local_spmv_only(self, x):
+        for A, h, yv, dsts, arr, ev in self.pieces:
+            sp.spmv(h, "N", 1.0, A, x, 0.0, yv)

@@ -47,10 +47,19 @@ def main():
     h = sp.SPMVHandle()
     xn2 = torch.empty(n_total, dtype=torch.float64, device=dev)
     y2 = torch.empty(r1 - r0, dtype=torch.float64, device=dev)
+    import ctypes as C
+    from kokkos_kernels_b200 import _lib
+    arr = (C.c_void_p * max(len(extra), 1))(*[C.c_void_p(int(q)) for q in extra])
+
+    def push_all():
+        _lib.check(_lib.sparse().b200sp_peer_push(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(y2.data_ptr()),
+                                                  y2.numel() * 8, len(extra), arr))
+
     res = {
         "spmv_plain_ms": timeit(lambda: sp.spmv(h, "N", 1.0, A, x, 0.0, y2)),
         "spmv_scatter_ms": timeit(lambda: sp.spmv_scatter(h, 1.0, A, x, y, extra)),
         "spmv_scatter_barrier_ms": timeit(lambda: (sp.spmv_scatter(h, 1.0, A, x, y, extra), hdl.barrier(channel=0))),
+        "peer_push_80MB_x7_ms": timeit(lambda: push_all()),
         "barrier_ms": timeit(lambda: hdl.barrier(channel=0)),
         "nccl_allgather_ms": timeit(lambda: dist.all_gather_into_tensor(xn2, y2)),
         "spmv_plus_nccl_ms": timeit(lambda: (sp.spmv(h, "N", 1.0, A, x, 0.0, y2), dist.all_gather_into_tensor(xn2, y2))),
