@@ -19,6 +19,7 @@
 //   spmv_transpose_kernel  T/H modes: y pre-scaled, atomicAdd scatter.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <mutex>
@@ -470,6 +471,23 @@ struct b200sp_spmv_plan {
   int64_t chunk_nnz = -1;
   char last_kernel[96] = "none";
   b200sp::YExtra extra = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
+  // tile sub-range of the next tiled launch (host-vector pipeline computes y piece by piece); hi < 0 = all
+  int range_lo = 0, range_hi = -1;
+  // host-vector pipeline (b200sp_spmv_hostvec_*): double-buffered device x / y, copy streams, events
+  struct HostPipe {
+    bool init = false;
+    cudaStream_t sH = nullptr, sD = nullptr;
+    void* dx[2] = {nullptr, nullptr};
+    void* dy[2] = {nullptr, nullptr};
+    size_t xb = 0, yb = 0;
+    cudaEvent_t ev_x[2], ev_c[2], ev_done[2], ev_chunk[8];
+    unsigned long long call = 0;
+    int nc = 0;
+    int tile_b[9];
+    int row_b[9];
+    const int* key = nullptr;
+    int key_cfg = -1;
+  } pipe;
 };
 
 namespace b200sp {
@@ -596,9 +614,11 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   }
   int per_sm = p->ctas_per_sm;
   if (per_sm <= 0) per_sm = occ.load();
-  int grid = std::min(p->n_tiles, sm_count() * per_sm);
+  const int lo = p->range_hi < 0 ? 0 : p->range_lo;
+  const int hi = p->range_hi < 0 ? p->n_tiles : p->range_hi;
+  int grid = std::min(hi - lo, sm_count() * per_sm);
   if (grid < 1) grid = 1;
-  kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, p->n_tiles, p->LMAX, p->tiles, row_ptr, col_idx, vals, x, y,
+  kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, hi - lo, p->LMAX, p->tiles + lo, row_ptr, col_idx, vals, x, y,
                                           alpha, beta, p->extra);
   B200SP_LAUNCH_CHECK();
   snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d,UNR=%d>grid=%d",
@@ -719,7 +739,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   if (rc) return rc;
   // long rows: skip the launch once the (asynchronously fetched) count is known to be 0
   if (!p->n_long_known && cudaEventQuery(p->n_long_event) == cudaSuccess) p->n_long_known = true;
-  if (!(p->n_long_known && *p->n_long_host == 0)) {
+  if (!(p->n_long_known && *p->n_long_host == 0) && (p->range_hi < 0 || p->range_lo == 0)) {
     int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
     spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta,
                                                    p->extra);
@@ -769,6 +789,20 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   if (p->xt) cudaFreeAsync(p->xt, st);
   if (p->yt) cudaFreeAsync(p->yt, st);
   if (p->chunk_row) cudaFreeAsync(p->chunk_row, st);
+  if (p->pipe.init) {
+    cudaStreamSynchronize(p->pipe.sH);
+    cudaStreamSynchronize(p->pipe.sD);
+    for (int b = 0; b < 2; ++b) {
+      if (p->pipe.dx[b]) cudaFree(p->pipe.dx[b]);
+      if (p->pipe.dy[b]) cudaFree(p->pipe.dy[b]);
+      cudaEventDestroy(p->pipe.ev_x[b]);
+      cudaEventDestroy(p->pipe.ev_c[b]);
+      cudaEventDestroy(p->pipe.ev_done[b]);
+    }
+    for (int c = 0; c < 8; ++c) cudaEventDestroy(p->pipe.ev_chunk[c]);
+    cudaStreamDestroy(p->pipe.sH);
+    cudaStreamDestroy(p->pipe.sD);
+  }
   if (p->n_long_event) {
     cudaEventSynchronize(p->n_long_event);  // the pinned mirror must not be written after it is freed
     cudaEventDestroy(p->n_long_event);
@@ -866,15 +900,14 @@ int b200sp_peer_push(void* stream, const void* src, int64_t bytes, int n_dst, vo
   return B200SP_OK;
 }
 
-int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, int m, int n, int64_t nnz,
-                                double alpha, const int* row_ptr, const int* col_idx, const double* vals,
-                                const double* x_host, double beta, double* y_host) {
-  B200SP_REQUIRE(p != nullptr, "spmv_hostvec: a plan is required");
-  B200SP_REQUIRE(m >= 0 && n >= 0, "spmv_hostvec: negative dimension");
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool trans = (mode == 'T' || mode == 't' || mode == 'H' || mode == 'h');
-  const size_t xb = sizeof(double) * (size_t)(trans ? m : n);
-  const size_t yb = sizeof(double) * (size_t)(trans ? n : m);
+// Host-vector SpMV.  Large non-transposed products run as a pipeline: x goes up on a copy stream into
+// one of two device buffers (so the upload of call k+1 overlaps call k), the rows are computed in
+// pieces (tile sub-ranges of the TMA-tiled kernel) and every finished piece of y goes down on a second
+// copy stream while the next piece is computed.  x_host must be ready when the call is made (it is
+// read asynchronously); y_host is valid once `stream` has been synchronised.
+static int hostvec_simple(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int n, int64_t nnz, double alpha,
+                          const int* row_ptr, const int* col_idx, const double* vals, const double* x_host,
+                          double beta, double* y_host, size_t xb, size_t yb) {
   if (xb > p->dx_bytes) {
     if (p->dx) cudaFreeAsync(p->dx, st);
     p->dx = nullptr;
@@ -893,6 +926,94 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
                              (double*)p->dy);
   if (rc) return rc;
   if (yb) B200SP_CUDA_TRY(cudaMemcpyAsync(y_host, p->dy, yb, cudaMemcpyDeviceToHost, st));
+  return B200SP_OK;
+}
+
+int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, int m, int n, int64_t nnz,
+                                double alpha, const int* row_ptr, const int* col_idx, const double* vals,
+                                const double* x_host, double beta, double* y_host) {
+  B200SP_REQUIRE(p != nullptr, "spmv_hostvec: a plan is required");
+  B200SP_REQUIRE(m >= 0 && n >= 0, "spmv_hostvec: negative dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool trans = (mode == 'T' || mode == 't' || mode == 'H' || mode == 'h');
+  const size_t xb = sizeof(double) * (size_t)(trans ? m : n);
+  const size_t yb = sizeof(double) * (size_t)(trans ? n : m);
+  const bool aligned = (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0;
+  const bool piped = !trans && (mode == 'N' || mode == 'n' || mode == 'C' || mode == 'c') && alpha != 0.0 &&
+                     nnz >= (1 << 22) && aligned && p->algo != B200SP_SPMV_FAST_SETUP && getenv("B200SP_HOSTVEC_SIMPLE") == nullptr;
+  if (!piped) return hostvec_simple(p, st, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, x_host, beta, y_host, xb, yb);
+
+  auto& q = p->pipe;
+  if (!q.init) {
+    B200SP_CUDA_TRY(cudaStreamCreateWithFlags(&q.sH, cudaStreamNonBlocking));
+    B200SP_CUDA_TRY(cudaStreamCreateWithFlags(&q.sD, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      B200SP_CUDA_TRY(cudaEventCreateWithFlags(&q.ev_x[b], cudaEventDisableTiming));
+      B200SP_CUDA_TRY(cudaEventCreateWithFlags(&q.ev_c[b], cudaEventDisableTiming));
+      B200SP_CUDA_TRY(cudaEventCreateWithFlags(&q.ev_done[b], cudaEventDisableTiming));
+    }
+    for (int c = 0; c < 8; ++c) B200SP_CUDA_TRY(cudaEventCreateWithFlags(&q.ev_chunk[c], cudaEventDisableTiming));
+    q.init = true;
+  }
+  if (xb > q.xb || yb > q.yb) {
+    B200SP_CUDA_TRY(cudaDeviceSynchronize());
+    for (int b = 0; b < 2; ++b) {
+      if (q.dx[b]) cudaFree(q.dx[b]);
+      if (q.dy[b]) cudaFree(q.dy[b]);
+      q.dx[b] = q.dy[b] = nullptr;
+      B200SP_CUDA_TRY(cudaMalloc(&q.dx[b], std::max(xb, q.xb)));
+      B200SP_CUDA_TRY(cudaMalloc(&q.dy[b], std::max(yb, q.yb)));
+    }
+    q.xb = std::max(xb, q.xb);
+    q.yb = std::max(yb, q.yb);
+    q.call = 0;
+  }
+  // tile analysis + piece boundaries (once per matrix; the only synchronous part)
+  const int cfg = p->cfg >= 0 ? p->cfg : 8;
+  int rc = plan_analyse<double>(p, st, cfg, m, n, nnz, row_ptr);
+  if (rc) return rc;
+  if (q.key != row_ptr || q.key_cfg != cfg) {
+    q.nc = 4;
+    int4 d[9];
+    for (int c = 0; c <= q.nc; ++c) {
+      q.tile_b[c] = (int)(((int64_t)p->n_tiles * c) / q.nc);
+      if (c < q.nc) B200SP_CUDA_TRY(cudaMemcpyAsync(&d[c], p->tiles + q.tile_b[c], sizeof(int4), cudaMemcpyDeviceToHost, st));
+    }
+    B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c = 0; c < q.nc; ++c) q.row_b[c] = d[c].x;  // first row of the first tile of piece c
+    q.row_b[q.nc] = m;
+    q.row_b[0] = 0;
+    q.key = row_ptr;
+    q.key_cfg = cfg;
+  }
+  const int b = (int)(q.call & 1ull);
+  // upload: wait until the compute that last read this x buffer (call k-2) is done
+  if (q.call >= 2) B200SP_CUDA_TRY(cudaStreamWaitEvent(q.sH, q.ev_c[b], 0));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(q.dx[b], x_host, xb, cudaMemcpyHostToDevice, q.sH));
+  if (beta != 0.0) {
+    // dy[b] was last read by the download of call k-2, which `stream` already waited for
+    B200SP_CUDA_TRY(cudaMemcpyAsync(q.dy[b], y_host, yb, cudaMemcpyHostToDevice, q.sH));
+  }
+  B200SP_CUDA_TRY(cudaEventRecord(q.ev_x[b], q.sH));
+  B200SP_CUDA_TRY(cudaStreamWaitEvent(st, q.ev_x[b], 0));
+  for (int c = 0; c < q.nc; ++c) {
+    p->range_lo = q.tile_b[c];
+    p->range_hi = q.tile_b[c + 1];
+    rc = spmv_impl<double>(p, st, mode, m, n, nnz, alpha, row_ptr, col_idx, vals, (const double*)q.dx[b], beta,
+                           (double*)q.dy[b]);
+    p->range_lo = 0;
+    p->range_hi = -1;
+    if (rc) return rc;
+    B200SP_CUDA_TRY(cudaEventRecord(q.ev_chunk[c], st));
+    B200SP_CUDA_TRY(cudaStreamWaitEvent(q.sD, q.ev_chunk[c], 0));
+    const size_t r0 = (size_t)q.row_b[c], r1 = (size_t)q.row_b[c + 1];
+    if (r1 > r0)
+      B200SP_CUDA_TRY(cudaMemcpyAsync(y_host + r0, (double*)q.dy[b] + r0, sizeof(double) * (r1 - r0), cudaMemcpyDeviceToHost, q.sD));
+  }
+  B200SP_CUDA_TRY(cudaEventRecord(q.ev_c[b], st));
+  B200SP_CUDA_TRY(cudaEventRecord(q.ev_done[b], q.sD));
+  B200SP_CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done[b], 0));  // y_host is valid once `stream` is synchronised
+  q.call++;
   return B200SP_OK;
 }
 
