@@ -293,6 +293,123 @@ static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, co
   return B200SP_OK;
 }
 
+// Vectorised variant: every lane owns VW adjacent columns (one 16-byte load of the X row per nonzero),
+// a group of KT lanes covers KT*VW columns, so a warp advances 32/KT chunks at once.  Needs k, ldx,
+// ldy multiples of VW and 16-byte aligned X / Y.
+template <typename S> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int W = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int W = 2; };
+__device__ __forceinline__ void vec_unpack(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void vec_unpack(const double2& v, double* a) { a[0] = v.x; a[1] = v.y; }
+__device__ __forceinline__ float4 vec_pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 vec_pack(const double* a) { return make_double2(a[0], a[1]); }
+
+template <typename S, int KT>
+__global__ void __launch_bounds__(256)
+    spmm_split_vec_kernel(int m, int k, int64_t nnz, int Q, int n_chunks, const int* __restrict__ chunk_row,
+                          const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const S* __restrict__ vals,
+                          const S* __restrict__ X, int64_t ldx, S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  using V = typename VecOf<S>::type;
+  constexpr int VW = VecOf<S>::W;
+  constexpr int GPW = 32 / KT;
+  constexpr int EB = (KT >= 8) ? 1 : (8 / KT);  // entries per lane per batch
+  constexpr int BATCH = KT * EB;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / KT, t = lane % KT;
+  const unsigned gmask = (KT == 32) ? 0xffffffffu : (((1u << KT) - 1u) << (grp * KT));
+  const int gbase = grp * KT;
+  const int strip_cols = KT * VW;
+  const int nstrips = (k + strip_cols - 1) / strip_cols;
+  const int64_t gid = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * GPW + grp;
+  const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
+  const int64_t work_total = (int64_t)n_chunks * nstrips;
+  for (int64_t w = gid; w < work_total; w += ngroups) {
+    const int chunk = (int)(w / nstrips);
+    const int j = (int)(w % nstrips) * strip_cols + t * VW;
+    const bool jok = j < k;  // k % VW == 0: a lane's VW columns are all in or all out
+    const int64_t c0 = (int64_t)chunk * Q;
+    const int64_t c1 = (c0 + Q < nnz) ? c0 + Q : nnz;
+    int row = (chunk == 0) ? 0 : chunk_row[chunk];
+    int ebase = row;
+    int ends = row_ptr[min(ebase + 1 + t, m)];
+    int64_t row_start = row_ptr[row];
+    int64_t next_end = __shfl_sync(gmask, ends, gbase);
+    S acc[VW];
+#pragma unroll
+    for (int q = 0; q < VW; ++q) acc[q] = S(0);
+    auto flush = [&]() {
+      if (jok) {
+        S* yp = Y + (int64_t)row * ldy + j;
+        if (row_start >= c0 && next_end <= c1) {
+          S o[VW];
+          if (beta == S(0)) {
+#pragma unroll
+            for (int q = 0; q < VW; ++q) o[q] = alpha * acc[q];
+          } else {
+            S old[VW];
+            vec_unpack(*reinterpret_cast<const V*>(yp), old);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) o[q] = beta * old[q] + alpha * acc[q];
+          }
+          *reinterpret_cast<V*>(yp) = vec_pack(o);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VW; ++q) atomicAdd(yp + q, alpha * acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < VW; ++q) acc[q] = S(0);
+      row_start = next_end;
+      ++row;
+      if (row - ebase == KT) {
+        ebase = row;
+        ends = row_ptr[min(ebase + 1 + t, m)];
+      }
+      next_end = __shfl_sync(gmask, ends, gbase + (row - ebase));
+    };
+    for (int64_t b = c0; b < c1; b += BATCH) {
+      int c[EB];
+      S v[EB];
+#pragma unroll
+      for (int i = 0; i < EB; ++i) {
+        const int64_t e = b + i * KT + t;
+        c[i] = 0;
+        v[i] = S(0);
+        if (e < c1) {
+          c[i] = ld_stream(col_idx + e);
+          v[i] = ld_stream(vals + e);
+        }
+      }
+      const int nb = (int)((c1 - b < BATCH) ? (c1 - b) : BATCH);
+      V xv[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int cu = __shfl_sync(gmask, c[u / KT], gbase + (u % KT));
+        if (u < nb && jok) xv[u] = __ldg(reinterpret_cast<const V*>(X + (int64_t)cu * ldx + j));
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const S vu = __shfl_sync(gmask, v[u / KT], gbase + (u % KT));
+        if (u < nb) {
+          while (b + u >= next_end) flush();  // uniform within the group
+          if (jok) {
+            S xs[VW];
+            vec_unpack(xv[u], xs);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) acc[q] += vu * xs[q];
+          }
+        }
+      }
+    }
+    while (row < m && next_end <= c1) flush();
+    if (row < m && row_start < c1 && jok) {
+      S* yp = Y + (int64_t)row * ldy + j;
+#pragma unroll
+      for (int q = 0; q < VW; ++q) atomicAdd(yp + q, alpha * acc[q]);
+    }
+  }
+}
+
 int plan_chunk_rows(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr, int Q, int** chunk_row,
                     int* n_chunks);
 
@@ -308,6 +425,38 @@ static int launch_split(b200sp_spmv_plan* p, cudaStream_t st, int m, int k, int6
     const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
     spmm_prescale_split_rows<S><<<blocks, 256, 0, st>>>(m, k, Q, row_ptr, beta, Y, ldy);
     B200SP_LAUNCH_CHECK();
+  }
+  {
+    constexpr int VW = 16 / (int)sizeof(S);
+    const bool vec_ok = (k % VW == 0) && (ldx % VW == 0) && (ldy % VW == 0) &&
+                        ((((uintptr_t)X) | ((uintptr_t)Y)) & 15u) == 0 && getenv("B200SP_SPMM_VEC") != nullptr;
+    // opt-in: measured 6.6 ms vs 5.2 ms for the scalar-lane kernel on config 3 (profiles/r01_spmm.md) -- fewer
+    // lanes per chunk means fewer chunks in flight per SM at its register count; kept for the tuning round
+    if (vec_ok) {
+      int KTv = 1;
+      while (KTv * VW < k && KTv < 32) KTv <<= 1;
+      const int gpwv = 32 / KTv;
+      const int nstripsv = (k + KTv * VW - 1) / (KTv * VW);
+      const int64_t workv = (int64_t)n_chunks * nstripsv;
+      int blocksv = (int)std::min<int64_t>((workv + 8 * gpwv - 1) / (8 * gpwv), (int64_t)sm_count() * 16);
+      if (blocksv < 1) blocksv = 1;
+#define B200SP_SPLITV(K)                                                                                          \
+  case K:                                                                                                         \
+    spmm_split_vec_kernel<S, K><<<blocksv, 256, 0, st>>>(m, k, nnz, Q, n_chunks, chunk_row, row_ptr, col_idx, vals, X, \
+                                                         ldx, Y, ldy, alpha, beta);                               \
+    break;
+      switch (KTv) {
+        B200SP_SPLITV(1)
+        B200SP_SPLITV(2)
+        B200SP_SPLITV(4)
+        B200SP_SPLITV(8)
+        B200SP_SPLITV(16)
+        B200SP_SPLITV(32)
+      }
+#undef B200SP_SPLITV
+      B200SP_LAUNCH_CHECK();
+      return B200SP_OK;
+    }
   }
   int KT = 1;
   while (KT < k && KT < 32) KT <<= 1;

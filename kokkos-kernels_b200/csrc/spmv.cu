@@ -471,6 +471,11 @@ struct b200sp_spmv_plan {
   int64_t chunk_nnz = -1;
   char last_kernel[96] = "none";
   b200sp::YExtra extra = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
+  // self-tuning between the tiled and the row-vector kernel (same bits, different speed by matrix):
+  // call 0 tile, call 1 tile timed, call 2 vector timed, then the faster one
+  int at_calls = 0, at_choice = -1;
+  cudaEvent_t at_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float at_tile_ms = 0.f, at_vec_ms = 0.f;
   // tile sub-range of the next tiled launch (host-vector pipeline computes y piece by piece); hi < 0 = all
   int range_lo = 0, range_hi = -1;
   // host-vector pipeline (b200sp_spmv_hostvec_*): double-buffered device x / y, copy streams, events
@@ -537,6 +542,8 @@ static int plan_analyse(b200sp_spmv_plan* p, cudaStream_t st, int cfg, int m, in
   p->key_n = n;
   p->key_nnz = nnz;
   p->key_cfg = cfg;
+  p->at_calls = 0;
+  p->at_choice = -1;
   return B200SP_OK;
 }
 
@@ -728,6 +735,30 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   int rc = plan_analyse<S>(p, st, cfg, m, n, nnz, row_ptr);
   if (rc) return rc;
   const int lpr = p->lpr > 0 ? p->lpr : lpr_auto;
+  // ---- self-tuning (only for untuned plans on whole-matrix launches)
+  const bool autotune = p->cfg < 0 && p->range_hi < 0 && p->extra.n == 0 && getenv("B200SP_NO_AUTOTUNE") == nullptr;
+  int phase = -1;  // 1: time the tiled kernel, 2: time the vector kernel
+  if (autotune) {
+    if (p->at_choice < 0 && p->at_calls >= 3 && cudaEventQuery(p->at_ev[1]) == cudaSuccess &&
+        cudaEventQuery(p->at_ev[3]) == cudaSuccess) {
+      if (cudaEventElapsedTime(&p->at_tile_ms, p->at_ev[0], p->at_ev[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&p->at_vec_ms, p->at_ev[2], p->at_ev[3]) == cudaSuccess)
+        p->at_choice = (p->at_vec_ms < 0.9f * p->at_tile_ms) ? 1 : 0;
+    }
+    if (p->at_calls == 1 || p->at_calls == 2) {
+      phase = p->at_calls;
+      for (int i = 0; i < 4; ++i)
+        if (!p->at_ev[i]) B200SP_CUDA_TRY(cudaEventCreate(&p->at_ev[i]));
+    }
+    p->at_calls++;
+    if (phase == 2 || (phase < 0 && p->at_choice == 1)) {
+      if (phase == 2) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[2], st));
+      rc = launch_vector<S>(p, st, lpr, m, row_ptr, col_idx, vals, x, y, alpha, beta);
+      if (phase == 2) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[3], st));
+      return rc;
+    }
+    if (phase == 1) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[0], st));
+  }
   switch (lpr) {
     case 2: rc = launch_tile_cfg<S, 2>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
     case 4: rc = launch_tile_cfg<S, 4>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
@@ -745,6 +776,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
                                                    p->extra);
     B200SP_LAUNCH_CHECK();
   }
+  if (phase == 1) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[1], st));
   return B200SP_OK;
 }
 
@@ -789,6 +821,8 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   if (p->xt) cudaFreeAsync(p->xt, st);
   if (p->yt) cudaFreeAsync(p->yt, st);
   if (p->chunk_row) cudaFreeAsync(p->chunk_row, st);
+  for (int i = 0; i < 4; ++i)
+    if (p->at_ev[i]) cudaEventDestroy(p->at_ev[i]);
   if (p->pipe.init) {
     cudaStreamSynchronize(p->pipe.sH);
     cudaStreamSynchronize(p->pipe.sD);
