@@ -223,7 +223,7 @@ def main():
     ap.add_argument("--collective", default="pipelined", choices=["pipelined", "fused", "nccl"],
                     help="N>1: all-gather of y pipelined behind the compute (copy-engine pushes over NVLink), "
                          "fused into the SpMV kernel (P2P stores), or NCCL after it")
-    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--chunks", type=int, default=8)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

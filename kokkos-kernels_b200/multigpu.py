@@ -20,7 +20,7 @@ from . import _lib, sparse as sp
 
 
 class RowBlockSpMV:
-    def __init__(self, rp, ci, va, n_total, r0, r1, device, mode="pipelined", chunks=4, tune=(-1, -1, -1)):
+    def __init__(self, rp, ci, va, n_total, r0, r1, device, mode="pipelined", chunks=8, tune=(-1, -1, -1)):
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.n_total, self.r0, self.r1, self.dev, self.mode = n_total, r0, r1, device, mode
         nrows = r1 - r0
