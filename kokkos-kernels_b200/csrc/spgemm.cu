@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <limits.h>
+#include <stdlib.h>
 #include <new>
 
 namespace b200sp {
@@ -520,6 +521,277 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     for (int q = tg; q < nz; q += G) vC[cbase + q] = vals[q];
 }
 
+// ---------------------------------------------------------------------------
+// NUMERIC, variant 2 ("staged"): same sorted-by-construction accumulator as num_hash_kernel, but
+//  * ONE walk over the products: while the keys are inserted, every product (column, b*a) is parked
+//    in shared memory at its ordinal within the row (ordinals come from a group-wide exclusive scan
+//    of the B row lengths), so the value pass reads shared memory instead of gathering the B rows
+//    from HBM a second time (rows with more than PCAP products fall back to a second walk);
+//  * occupancy words by warp ballot (one instruction per 32 slots instead of a 32-step loop),
+//    16-byte table initialisation;
+//  * rows whose product count equals nnz(C_i) have no duplicate column: their values are placed
+//    with plain stores (no shared-memory atomics, no zero fill).
+// Selected with B200SP_SPGEMM_NUMERIC=2|3 (3 = half-size key tables, load factor <= 0.5).
+// ---------------------------------------------------------------------------
+template <int G, typename S>
+struct Walk2Smem {
+  int bs[G];    // start of the B row of staged entry t
+  int len[G];   // its length
+  int off[G];   // ordinal (within the C row's product list) of its first product
+  S va[G];      // A value of staged entry t
+  int wsum[G > 32 ? G / 32 : 1];
+};
+
+// exclusive scan of one int per thread over a group of G threads (G = 32: one warp, else the CTA)
+template <int G>
+__device__ __forceinline__ int group_excl_scan(int v, int tg, int* wsum, int& total) {
+  const int lane = tg & 31;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (G == 32) {
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+  }
+  const int w = tg >> 5;
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < (G > 32 ? G / 32 : 1); ++i) {
+    const int s = wsum[i];
+    if (i < w) woff += s;
+    tot += s;
+  }
+  total = tot;
+  return woff + inc - v;
+}
+
+// f(column, b_val*a_val, ordinal) once per product of row i; with_vals == false skips the value loads
+template <int G, typename S, typename F>
+__device__ __forceinline__ void walk_products2(int tg, int lb, int a0, int a1, bool with_vals,
+                                               const int* __restrict__ ciA, const S* __restrict__ vA,
+                                               const int* __restrict__ rpB, const int* __restrict__ ciB,
+                                               const S* __restrict__ vB, Walk2Smem<G, S>& w, F&& f) {
+  constexpr int UT = 4;
+  auto gsync = [&]() {
+    if (G <= 32) __syncwarp(); else __syncthreads();
+  };
+  const int nsub = G / lb;
+  const int q = tg / lb, sl = tg % lb;
+  int pbase = 0;
+  for (int ab = a0; ab < a1; ab += G) {
+    const int nA = min(G, a1 - ab);
+    int b0 = 0, ln = 0;
+    S va = S(0);
+    if (tg < nA) {
+      const int ca = ciA[ab + tg];
+      b0 = rpB[ca];
+      ln = rpB[ca + 1] - b0;
+      if (with_vals) va = vA[ab + tg];
+    }
+    int total;
+    const int excl = group_excl_scan<G>(ln, tg, w.wsum, total);
+    w.bs[tg] = b0;
+    w.len[tg] = ln;
+    w.off[tg] = pbase + excl;
+    w.va[tg] = va;
+    pbase += total;
+    gsync();
+    for (int t0 = q; t0 < nA; t0 += nsub * UT) {
+      int c[UT], id[UT];
+      S v[UT];
+#pragma unroll
+      for (int u = 0; u < UT; ++u) {
+        const int t = t0 + u * nsub;
+        c[u] = -1;
+        id[u] = 0;
+        v[u] = S(0);
+        if (t < nA && sl < w.len[t]) {
+          const int jb = w.bs[t] + sl;
+          c[u] = ld_stream(ciB + jb);
+          id[u] = w.off[t] + sl;
+          if (with_vals) v[u] = ld_stream(vB + jb) * w.va[t];  // b_val * val (impl_seq.hpp:163)
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UT; ++u)
+        if (c[u] >= 0) f(c[u], v[u], id[u]);
+      // B rows longer than the sub-warp
+#pragma unroll 1
+      for (int u = 0; u < UT; ++u) {
+        const int t = t0 + u * nsub;
+        if (t < nA)
+          for (int off = sl + lb; off < w.len[t]; off += lb) {
+            const int jb = w.bs[t] + off;
+            f(ld_stream(ciB + jb), with_vals ? ld_stream(vB + jb) * w.va[t] : S(0), w.off[t] + off);
+          }
+      }
+    }
+    gsync();  // staging is rewritten by the next batch
+  }
+}
+
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP>
+struct Num2Layout {
+  static constexpr int TOT = KSLOTS + PAD;  // multiple of 32
+  static constexpr int WORDS = TOT / 32;
+  // per row-group: vals[VCAP] | pval[PCAP] | keys[TOT] | pcol[PCAP] | wpre[WORDS] | wmask[WORDS]
+  static constexpr size_t OFF_PVAL = sizeof(S) * VCAP;
+  static constexpr size_t OFF_KEYS = OFF_PVAL + sizeof(S) * PCAP;
+  static constexpr size_t OFF_PCOL = OFF_KEYS + sizeof(int) * TOT;
+  static constexpr size_t OFF_WPRE = OFF_PCOL + sizeof(int) * PCAP;
+  static constexpr size_t OFF_WMASK = OFF_WPRE + sizeof(int) * WORDS;
+  static constexpr size_t PER = OFF_WMASK + sizeof(int) * WORDS;
+  static constexpr size_t PER_AL = (PER + 15) & ~(size_t)15;
+  static_assert(TOT % 32 == 0 && VCAP % 4 == 0 && PCAP % 4 == 0, "table sizes keep 16-byte alignment");
+};
+
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP>
+__global__ void __launch_bounds__(G <= 32 ? 256 : G)
+    num2_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
+                const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
+                const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
+                int* __restrict__ ciC, S* __restrict__ vC, const int* __restrict__ cmin_arr,
+                const int* __restrict__ cmax_arr, const int* __restrict__ flops_arr, int* __restrict__ fb_rows,
+                int* __restrict__ fb_count) {
+  using L = Num2Layout<S, G, KSLOTS, PAD, VCAP, PCAP>;
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  constexpr int NWG = G / 32;  // warps per row group
+  constexpr int TOT = L::TOT;
+  constexpr int WORDS = L::WORDS;
+  constexpr int INF = INT_MAX;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ int sm_flag[RPC];
+  __shared__ Walk2Smem<G, S> sm_walk[RPC];
+  const int g = threadIdx.x / G, tg = threadIdx.x % G;
+  const int lane = tg & 31, wg = tg >> 5;
+  unsigned char* base = smraw + (size_t)g * L::PER_AL;
+  S* vals = reinterpret_cast<S*>(base);
+  S* pval = reinterpret_cast<S*>(base + L::OFF_PVAL);
+  int* keys = reinterpret_cast<int*>(base + L::OFF_KEYS);
+  int* pcol = reinterpret_cast<int*>(base + L::OFF_PCOL);
+  int* wpre = reinterpret_cast<int*>(base + L::OFF_WPRE);
+  unsigned* wmask = reinterpret_cast<unsigned*>(base + L::OFF_WMASK);
+  const int ridx = blockIdx.x * RPC + g;
+  const bool active = ridx < nrows_bin;
+  auto gsync = [&]() {
+    if (G <= 32) __syncwarp(); else __syncthreads();
+  };
+  int i = 0, cbase = 0, nz = 0, np = 0;
+  if (active) {
+    i = rows[ridx];
+    cbase = rpC[i];
+    nz = rpC[i + 1] - cbase;
+    np = flops_arr[i];  // exact number of products of the row (clamped at INT_MAX)
+  }
+  const bool work = active && nz > 0;
+  const bool dupfree = work && np == nz;        // every product has its own column
+  const bool staged = PCAP > 0 && work && np <= PCAP;
+  {
+    int4* k4 = reinterpret_cast<int4*>(keys);
+    for (int s = tg; s < TOT / 4; s += G) k4[s] = make_int4(INF, INF, INF, INF);
+    if (work && !dupfree)
+      for (int s = tg; s < nz; s += G) vals[s] = S(0);
+    if (tg == 0) sm_flag[g] = 0;
+  }
+  gsync();
+  const int cmin = work ? cmin_arr[i] : 0;
+  const long long span = work ? ((long long)cmax_arr[i] - cmin + 1) : 1;
+  const bool dense = span <= KSLOTS;
+  const unsigned long long mult = dense ? 0ull : (((unsigned long long)KSLOTS << 32) / (unsigned long long)span);
+  const int a0 = work ? rpA[i] : 0, a1 = work ? rpA[i + 1] : 0;
+  auto slot_of = [&](int c) -> int {
+    return dense ? (c - cmin) : (int)(((unsigned long long)(unsigned)(c - cmin) * mult) >> 32);
+  };
+  // position of the (present) column c in the sorted row
+  auto rank_of = [&](int c) -> int {
+    int h = slot_of(c);
+    while (keys[h] != c) ++h;
+    return wpre[h >> 5] + __popc(wmask[h >> 5] & ((1u << (h & 31)) - 1u));
+  };
+  // ---- the walk: ordered insertion of the keys (+ products parked in shared memory)
+  walk_products2<G, S>(tg, lb, a0, a1, staged, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int id) {
+    if (PCAP > 0 && staged) {
+      pcol[id] = c;
+      pval[id] = v;
+    }
+    int h = slot_of(c);
+    while (true) {
+      const int old = atomicMin(&keys[h], c);
+      if (old == c || old == INF) return;  // already there / took an empty slot
+      if (old > c) c = old;                // displaced a larger key: carry it on
+      if (++h >= TOT) {
+        sm_flag[g] = 1;  // ran off the pad: row goes to the fallback kernel
+        return;
+      }
+    }
+  });
+  gsync();
+  const bool overflow = sm_flag[g] != 0;
+  if (active && overflow && tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
+  const bool emit = work && !overflow;  // uniform within the group
+  // ---- occupancy words (warp ballot) and their exclusive prefix
+  if (emit) {
+    for (int w = wg; w < WORDS; w += NWG) {
+      const unsigned msk = __ballot_sync(0xffffffffu, keys[w * 32 + lane] != INF);
+      if (lane == 0) {
+        wmask[w] = msk;
+        wpre[w] = __popc(msk);
+      }
+    }
+  }
+  gsync();
+  if (emit && tg < 32) {
+    int carry = 0;
+    for (int w0 = 0; w0 < WORDS; w0 += 32) {
+      const int w = w0 + tg;
+      const int v = w < WORDS ? wpre[w] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tg >= o) inc += t;
+      }
+      if (w < WORDS) wpre[w] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  gsync();
+  // ---- column indices leave in sorted order
+  if (emit) {
+    const unsigned lt = (1u << lane) - 1u;
+    for (int w = wg; w < WORDS; w += NWG) {
+      const int key = keys[w * 32 + lane];
+      if (key != INF) ciC[cbase + wpre[w] + __popc(wmask[w] & lt)] = key;
+    }
+  }
+  // ---- values by output position
+  if (PCAP > 0 && staged) {
+    if (emit) {
+      if (dupfree) {
+        for (int id = tg; id < np; id += G) vals[rank_of(pcol[id])] = pval[id];
+      } else {
+        for (int id = tg; id < np; id += G) smem_add(&vals[rank_of(pcol[id])], pval[id]);
+      }
+    }
+  } else {
+    // too many products to park: second walk (idle / overflowed groups walk an empty row)
+    const int b0 = emit ? a0 : 0, b1 = emit ? a1 : 0;
+    walk_products2<G, S>(tg, lb, b0, b1, true, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int) {
+      const int pos = rank_of(c);
+      if (dupfree) vals[pos] = v; else smem_add(&vals[pos], v);
+    });
+  }
+  gsync();
+  if (emit)
+    for (int q = tg; q < nz; q += G) vC[cbase + q] = vals[q];
+}
+
 // fallback: global-memory hash (wrap-around, multiplicative) + in-place bitonic sort of the C row
 template <typename S>
 __global__ void __launch_bounds__(256)
@@ -626,6 +898,8 @@ struct b200sp_spgemm_plan {
   int lb = 8;  // lanes walking one B row
   // device state kept for numeric
   int *cmin = nullptr, *cmax = nullptr;
+  int* flops = nullptr;     // products per row of A*B (numeric variant 2 parks them in shared memory)
+  int numeric_variant = 1;  // 1: two-walk num_hash_kernel, 2/3: staged num2_kernel (B200SP_SPGEMM_NUMERIC)
   int* num_rows = nullptr;  // rows grouped by numeric bin
   int num_off[kNumBins + 1] = {0};
   int *fb_rows = nullptr, *fb_count = nullptr;
@@ -639,10 +913,10 @@ struct b200sp_spgemm_plan {
 namespace b200sp {
 
 static void spgemm_release(b200sp_spgemm_plan* p, cudaStream_t st) {
-  void* ptrs[] = {p->cmin, p->cmax, p->num_rows, p->fb_rows, p->fb_count, p->fb_keys, p->fb_vals};
+  void* ptrs[] = {p->cmin, p->cmax, p->flops, p->num_rows, p->fb_rows, p->fb_count, p->fb_keys, p->fb_vals};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, st);
-  p->cmin = p->cmax = p->num_rows = p->fb_rows = p->fb_count = p->fb_keys = nullptr;
+  p->cmin = p->cmax = p->flops = p->num_rows = p->fb_rows = p->fb_count = p->fb_keys = nullptr;
   p->fb_vals = nullptr;
   p->fb_vals_bytes = 0;
   p->symbolic_done = false;
@@ -716,6 +990,24 @@ static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int
   return B200SP_OK;
 }
 
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP>
+static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
+                       const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
+  const int nrows = p->num_off[bin + 1] - p->num_off[bin];
+  if (nrows <= 0) return B200SP_OK;
+  using L = Num2Layout<S, G, KSLOTS, PAD, VCAP, PCAP>;
+  constexpr int THREADS = (G <= 32 ? 256 : G);
+  constexpr int RPC = THREADS / G;
+  const size_t smem = L::PER_AL * RPC;
+  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP>;
+  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
+                                                      rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->flops, p->fb_rows,
+                                                      p->fb_count);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
 template <typename S>
 static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int k, const int* rpA, const int* ciA,
                         const S* vA, const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
@@ -741,6 +1033,31 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   // fallback list starts as the rows that are too long for shared memory
   B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_count, &p->fb_static, sizeof(int), cudaMemcpyHostToDevice, st));
   int rc;
+  int variant = p->numeric_variant;
+  if (const char* e = getenv("B200SP_SPGEMM_NUMERIC")) variant = atoi(e);
+  if (variant == 2 || variant == 3) {
+    // <S, G, key slots, pad, max nnz(C_i) of the bin, parked products>
+#define NUM2(B, G, KS, PAD, VCAP, PCAP)                                                                          \
+  if ((rc = launch_num2<S, G, KS, PAD, VCAP, PCAP>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if (variant == 2) {  // key tables >= 4 x nnz (load <= 0.25)
+      NUM2(0, 32, 256, 32, 64, 128)
+      NUM2(1, 64, 1024, 64, 256, 512)
+      NUM2(2, 128, 4096, 128, 1024, 1024)
+      NUM2(3, 256, 16384, 256, 4096, 2048)
+      NUM2(4, 512, 32768, 512, 8192, 0)
+    } else {  // >= 2 x nnz (load <= 0.5): half the table to initialise and scan, longer probe chains
+      NUM2(0, 32, 128, 32, 64, 128)
+      NUM2(1, 64, 512, 64, 256, 512)
+      NUM2(2, 128, 2048, 128, 1024, 1024)
+      NUM2(3, 256, 8192, 256, 4096, 2048)
+      NUM2(4, 512, 16384, 512, 8192, 0)
+    }
+#undef NUM2
+    num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                    ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+  }
   // <S, G, key slots (>= 4 x bin's max nnz), pad, max nnz>
   if ((rc = launch_num<S, 32, 256, 32, 64>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
   if ((rc = launch_num<S, 32, 1024, 64, 256>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
@@ -826,12 +1143,11 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   B200SP_REQUIRE(ciA && ciB, "spgemm_symbolic: null column index array");
 
   DevTmp tmp(st);
-  int *bmin, *bmax, *flops, *row_nnz, *sym_rows, *d_counts, *block_max, *d_max;
+  int *bmin, *bmax, *row_nnz, *sym_rows, *d_counts, *block_max, *d_max;
   long long *block_sum, *d_total;
   const int nblocks = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
   B200SP_CUDA_TRY(tmp.alloc(&bmin, n));
   B200SP_CUDA_TRY(tmp.alloc(&bmax, n));
-  B200SP_CUDA_TRY(tmp.alloc(&flops, m));
   B200SP_CUDA_TRY(tmp.alloc(&row_nnz, m));
   B200SP_CUDA_TRY(tmp.alloc(&sym_rows, m));
   B200SP_CUDA_TRY(tmp.alloc(&d_counts, MAXBINS));
@@ -841,6 +1157,8 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   B200SP_CUDA_TRY(tmp.alloc(&d_max, 1));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->cmin, sizeof(int) * (size_t)m, st));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->cmax, sizeof(int) * (size_t)m, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->flops, sizeof(int) * (size_t)m, st));
+  int* const flops = p->flops;
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->num_rows, sizeof(int) * (size_t)m, st));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->fb_rows, sizeof(int) * (size_t)m, st));
 
