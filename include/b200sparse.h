@@ -163,6 +163,67 @@ int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m,
                                   const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
                                   const int* row_ptr_C, int* col_idx_C, float* vals_C);
 
+/* ---- CrsMatrix utilities either side of the hot path ----------------- */
+/* sort_crs_matrix / sort_crs_graph (sparse/src/KokkosSparse_SortCrs.hpp:43-120,209-270): every row
+ * sorted ascending by column, values permuted along, IN PLACE.  The sort is stable (entries with the
+ * same column keep their order), which is what the reference's Serial/OpenMP path -- a per-row LSD
+ * radix sort, common/src/KokkosKernels_Sorting.hpp:301-380 -- produces.  vals may be NULL (graph).
+ * Rows that are already sorted are only read.  Synchronises `stream` once. */
+int b200sp_sort_crs_f64_i32(void* stream, int m, const int* row_ptr, int* col_idx, double* vals);
+int b200sp_sort_crs_f32_i32(void* stream, int m, const int* row_ptr, int* col_idx, float* vals);
+int b200sp_sort_crs_graph_i32(void* stream, int m, const int* row_ptr, int* col_idx);
+
+/* sort_and_merge_matrix / _graph (SortCrs.hpp:303-380,426-491) in two calls because the caller owns
+ * the output: _count sorts the input in place (as the reference does, :336), writes the merged row
+ * map (m+1 entries; for m == 0 a single 0 when row_ptr_out is non-NULL) and returns the merged
+ * nnz; if that equals nnz(in) nothing is merged and the caller may alias the input (:346-360).
+ * _fill writes merged entries / values; duplicates are summed in storage order of the sorted row
+ * (MatrixMergedEntriesFunctor, sparse/impl/KokkosSparse_sort_crs_impl.hpp:163-205).  vals NULL = graph. */
+int b200sp_sort_and_merge_count_f64_i32(void* stream, int m, const int* row_ptr, int* col_idx, double* vals,
+                                        int* row_ptr_out, int64_t* merged_nnz);
+int b200sp_sort_and_merge_count_f32_i32(void* stream, int m, const int* row_ptr, int* col_idx, float* vals,
+                                        int* row_ptr_out, int64_t* merged_nnz);
+int b200sp_sort_and_merge_fill_f64_i32(void* stream, int m, const int* row_ptr, const int* col_idx,
+                                       const double* vals, const int* row_ptr_out, int* col_idx_out,
+                                       double* vals_out);
+int b200sp_sort_and_merge_fill_f32_i32(void* stream, int m, const int* row_ptr, const int* col_idx,
+                                       const float* vals, const int* row_ptr_out, int* col_idx_out,
+                                       float* vals_out);
+
+/* transpose_matrix / transpose_graph (sparse/src/KokkosSparse_Utils.hpp:245-450): A is m x n, the
+ * transpose n x m; t_row_ptr has n+1 entries and is fully written.  Every transposed row lists its
+ * entries in (row of A, position in that row) order -- the order of the reference's Serial loop; its
+ * parallel back ends fill with atomics and leave the order unspecified.  vals / t_vals NULL = graph.
+ * Synchronises `stream`. */
+int b200sp_transpose_f64_i32(void* stream, int m, int n, const int* row_ptr, const int* col_idx,
+                             const double* vals, int* t_row_ptr, int* t_col_idx, double* t_vals);
+int b200sp_transpose_f32_i32(void* stream, int m, int n, const int* row_ptr, const int* col_idx,
+                             const float* vals, int* t_row_ptr, int* t_col_idx, float* t_vals);
+
+/* spadd: C = alpha*A + beta*B, A, B, C all m x n (sparse/src/KokkosSparse_spadd.hpp:29-319).
+ * The plan is the SPADDHandle (sparse/src/KokkosSparse_spadd_handle.hpp:24-137): input_sorted /
+ * input_merged as given to create_spadd_handle; for unsorted input it keeps a_pos / b_pos between the
+ * two phases (:73-84).  Symbolic fills row_ptr_C (m+1 entries, arrives uninitialised) and returns
+ * nnz(C) (synchronous); numeric fills col_idx_C / vals_C: sorted input -> merged, sorted rows
+ * (SortedNumericSumFunctor, spadd_numeric_impl.hpp:27-107); unsorted input -> rows in the order of
+ * the sorted union, values accumulated A first then B (UnsortedNumericSumFunctor, :109-171).  Same
+ * operation order as the reference's one-thread-per-row functors: results are bit-identical to its
+ * Serial path.  B200SP_ERR_STATE when numeric precedes symbolic. */
+typedef struct b200sp_spadd_plan b200sp_spadd_plan;
+int b200sp_spadd_plan_create(b200sp_spadd_plan** plan, int input_sorted, int input_merged);
+int b200sp_spadd_plan_destroy(b200sp_spadd_plan* plan, void* stream);
+int b200sp_spadd_symbolic_i32(b200sp_spadd_plan* plan, void* stream, int m, int n, const int* row_ptr_A,
+                              const int* col_idx_A, const int* row_ptr_B, const int* col_idx_B,
+                              int* row_ptr_C, int64_t* c_nnz);
+int b200sp_spadd_numeric_f64_i32(b200sp_spadd_plan* plan, void* stream, int m, int n, const int* row_ptr_A,
+                                 const int* col_idx_A, const double* vals_A, double alpha,
+                                 const int* row_ptr_B, const int* col_idx_B, const double* vals_B,
+                                 double beta, const int* row_ptr_C, int* col_idx_C, double* vals_C);
+int b200sp_spadd_numeric_f32_i32(b200sp_spadd_plan* plan, void* stream, int m, int n, const int* row_ptr_A,
+                                 const int* col_idx_A, const float* vals_A, float alpha,
+                                 const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
+                                 float beta, const int* row_ptr_C, int* col_idx_C, float* vals_C);
+
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */
 int64_t b200sp_launch_count(void);

@@ -33,6 +33,20 @@ SPARSE_API = {
     "b200sp_spgemm_symbolic_i32": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i32)]),
     "b200sp_spgemm_numeric_f64_i32": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200sp_spgemm_numeric_f32_i32": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200sp_sort_crs_f64_i32": (i32, [vp, i32, vp, vp, vp]),
+    "b200sp_sort_crs_f32_i32": (i32, [vp, i32, vp, vp, vp]),
+    "b200sp_sort_crs_graph_i32": (i32, [vp, i32, vp, vp]),
+    "b200sp_sort_and_merge_count_f64_i32": (i32, [vp, i32, vp, vp, vp, vp, C.POINTER(i64)]),
+    "b200sp_sort_and_merge_count_f32_i32": (i32, [vp, i32, vp, vp, vp, vp, C.POINTER(i64)]),
+    "b200sp_sort_and_merge_fill_f64_i32": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+    "b200sp_sort_and_merge_fill_f32_i32": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+    "b200sp_transpose_f64_i32": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "b200sp_transpose_f32_i32": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "b200sp_spadd_plan_create": (i32, [C.POINTER(vp), i32, i32]),
+    "b200sp_spadd_plan_destroy": (i32, [vp, vp]),
+    "b200sp_spadd_symbolic_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64)]),
+    "b200sp_spadd_numeric_f64_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp]),
+    "b200sp_spadd_numeric_f32_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, f32, vp, vp, vp, f32, vp, vp, vp]),
     "b200sp_launch_count": (i64, []),
     "b200sp_spmv_last_kernel": (C.c_char_p, [vp]),
     "b200sp_spmv_plan_tune": (i32, [vp, i32, i32, i32]),

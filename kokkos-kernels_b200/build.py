@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
-CU_SOURCES = ["spmv.cu", "spmm.cu", "spgemm.cu"]
+CU_SOURCES = ["spmv.cu", "spmm.cu", "spgemm.cu", "crs_utils.cu"]
 
 
 def _newer(target, sources):
@@ -37,7 +37,7 @@ def build(force=False, verbose=True):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libb200sparse.so")
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b200sparse.h")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(HERE, "..", "include", "b200sparse.h")]
     if force or not _newer(out, deps):
         objs = []
         procs = []
@@ -71,6 +71,17 @@ def build(force=False, verbose=True):
         cmd = [_nvcc(), "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "tests", "shim_mock"),
                "-I", os.path.join(HERE, "kokkos_shim"), "-I", os.path.join(root, "include"), dsrc, "-o", drv,
                "-L", LIB, "-lb200sparse", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+        if verbose:
+            print("[build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    # torch-free GPU validation harness (tools/gpu_check.cpp; links the oracle as the CHECKER -- test infrastructure)
+    chk = os.path.join(LIB, "gpu_check")
+    csrc = os.path.join(root, "tools", "gpu_check.cpp")
+    orc = os.path.join(root, "oracle", "libkkoracle.so")
+    if os.path.exists(csrc) and os.path.exists(orc) and (force or not _newer(chk, [csrc, out, gen, orc])):
+        cmd = [_nvcc(), "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "include"), csrc, "-o", chk,
+               "-L", LIB, "-lb200sparse", "-lb200matgen", "-L", os.path.join(root, "oracle"), "-lkkoracle",
+               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../oracle"]
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -43,6 +43,25 @@ extern std::atomic<long long> g_launches;
 
 int sm_count();  // SMs of the current device (cached per device)
 
+// stream-ordered temporaries of one host call
+struct DevTmp {  // frees stream-ordered on scope exit
+  cudaStream_t st;
+  void* ptrs[32];
+  int n = 0;
+  explicit DevTmp(cudaStream_t s) : st(s) {}
+  ~DevTmp() {
+    for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st);
+  }
+  template <typename T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, sizeof(T) * (count > 0 ? count : 1), st);
+    if (e == cudaSuccess) ptrs[n++] = q;
+    *out = (T*)q;
+    return e;
+  }
+};
+
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

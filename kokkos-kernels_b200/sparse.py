@@ -10,6 +10,11 @@ torch CUDA tensors, compute is libb200sparse through the C ABI):
                                  sparse/src/KokkosSparse_spgemm_handle.hpp:44-87,94-747
   spgemm_symbolic / spgemm_numeric / spgemm
                                  sparse/src/KokkosSparse_spgemm.hpp:40-61,119-129,170-218
+  sort_crs_matrix / sort_crs_graph / sort_and_merge_matrix / sort_and_merge_graph
+                                 sparse/src/KokkosSparse_SortCrs.hpp:43-146,209-300,303-537
+  SPADDHandle / spadd_symbolic / spadd_numeric
+                                 sparse/src/KokkosSparse_spadd_handle.hpp:24-137, KokkosSparse_spadd.hpp:29-319
+  transpose_matrix               sparse/src/KokkosSparse_Utils.hpp:338-398
 
 PyTorch is plumbing here (device memory + streams); there is no torch compute
 on this path and no CPU fallback.
@@ -193,9 +198,47 @@ class SPGEMMHandle:
             pass
 
 
+class SPADDHandle:
+    """sparse/src/KokkosSparse_spadd_handle.hpp:24-137: input_sorted / input_merged flags, c_nnz, the
+    called flags; a_pos / b_pos of the unsorted algorithm live in the C plan."""
+
+    def __init__(self, input_is_sorted, input_is_merged=False):
+        self.input_sorted, self.input_merged = bool(input_is_sorted), bool(input_is_merged)
+        self._plan = C.c_void_p(0)
+        check(_lib.sparse().b200sp_spadd_plan_create(C.byref(self._plan), int(self.input_sorted), int(self.input_merged)))
+        self._symbolic = self._numeric = False
+        self._c_nnz = 0
+
+    def is_input_sorted(self): return self.input_sorted
+    def is_input_merged(self): return self.input_merged
+    def is_input_strict_crs(self): return self.input_sorted and self.input_merged
+    def is_symbolic_called(self): return self._symbolic
+    def is_numeric_called(self): return self._numeric
+    def get_c_nnz(self): return self._c_nnz
+
+    def __del__(self):
+        try:
+            if self._plan:
+                st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
+                _lib.sparse().b200sp_spadd_plan_destroy(self._plan, st)
+                self._plan = C.c_void_p(0)
+        except Exception:
+            pass
+
+
 class KokkosKernelsHandle:
     def __init__(self):
         self._sh = None
+        self._ah = None
+
+    def create_spadd_handle(self, input_is_sorted=False, input_is_merged=False):
+        self._ah = SPADDHandle(input_is_sorted, input_is_merged)
+
+    def get_spadd_handle(self):
+        return self._ah
+
+    def destroy_spadd_handle(self):
+        self._ah = None
 
     def create_spgemm_handle(self, algo=SPGEMM_KK):
         self._sh = SPGEMMHandle(algo)
@@ -268,4 +311,133 @@ def spgemm(A, Amode, B, Bmode):
     Cm = spgemm_symbolic(kh, A, Amode, B, Bmode)
     spgemm_numeric(kh, A, Amode, B, Bmode, Cm)
     kh.destroy_spgemm_handle()
+    return Cm
+
+
+# --------------------------------------------------------------------------- CrsMatrix utilities
+def _sfx(t):
+    if t.dtype == torch.float64:
+        return "f64"
+    if t.dtype == torch.float32:
+        return "f32"
+    raise B200SparseError("b200sparse: only double and float are instantiated")
+
+
+def sort_crs_matrix(A_or_rowmap, entries=None, values=None):
+    """sort_crs_matrix(A) / sort_crs_matrix(rowmap, entries, values): every row sorted by column,
+    values permuted along, in place (SortCrs.hpp:43-146).  Stable, like the reference's host path."""
+    if entries is None:
+        rowmap, entries, values = A_or_rowmap.row_map, A_or_rowmap.entries, A_or_rowmap.values
+    else:
+        rowmap = A_or_rowmap
+    if entries.numel() <= 1:  # :62-67
+        return
+    m = max(rowmap.numel() - 1, 0)
+    fn = getattr(_lib.sparse(), f"b200sp_sort_crs_{_sfx(values)}_i32")
+    check(fn(_stream(), m, _ptr(rowmap), _ptr(entries), _ptr(values)))
+
+
+def sort_crs_graph(rowmap, entries):
+    """SortCrs.hpp:209-300."""
+    if entries.numel() <= 1:
+        return
+    check(_lib.sparse().b200sp_sort_crs_graph_i32(_stream(), max(rowmap.numel() - 1, 0), _ptr(rowmap), _ptr(entries)))
+
+
+def sort_and_merge_matrix(A):
+    """Returns the sorted, merged matrix; A itself is sorted in place on the way, and returned as is
+    when it has no duplicate entries (SortCrs.hpp:303-400)."""
+    m = A.numRows()
+    dev = A.row_map.device
+    if m == 0:
+        return CrsMatrix(torch.zeros(A.row_map.numel(), dtype=torch.int32, device=dev), A.entries[:0], A.values[:0], A.numCols())
+    sfx = _sfx(A.values)
+    rowmap_out = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    merged = C.c_int64(0)
+    check(getattr(_lib.sparse(), f"b200sp_sort_and_merge_count_{sfx}_i32")(
+        _stream(), m, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), C.c_void_p(rowmap_out.data_ptr()), C.byref(merged)))
+    if merged.value == A.nnz():
+        return A
+    entries_out = torch.empty(merged.value, dtype=torch.int32, device=dev)
+    values_out = torch.empty(merged.value, dtype=A.values.dtype, device=dev)
+    check(getattr(_lib.sparse(), f"b200sp_sort_and_merge_fill_{sfx}_i32")(
+        _stream(), m, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(rowmap_out), _ptr(entries_out), _ptr(values_out)))
+    return CrsMatrix(rowmap_out, entries_out, values_out, A.numCols())
+
+
+def sort_and_merge_graph(rowmap, entries):
+    """Returns (rowmap_out, entries_out); the input is sorted in place (SortCrs.hpp:426-537)."""
+    m = max(rowmap.numel() - 1, 0)
+    dev = rowmap.device
+    if m == 0:
+        return torch.zeros(rowmap.numel(), dtype=torch.int32, device=dev), entries[:0]
+    rowmap_out = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    merged = C.c_int64(0)
+    lib = _lib.sparse()
+    check(lib.b200sp_sort_and_merge_count_f32_i32(_stream(), m, _ptr(rowmap), _ptr(entries), C.c_void_p(0),
+                                                  C.c_void_p(rowmap_out.data_ptr()), C.byref(merged)))
+    if merged.value == entries.numel():
+        return rowmap, entries
+    entries_out = torch.empty(merged.value, dtype=torch.int32, device=dev)
+    check(lib.b200sp_sort_and_merge_fill_f32_i32(_stream(), m, _ptr(rowmap), _ptr(entries), C.c_void_p(0), _ptr(rowmap_out),
+                                                 _ptr(entries_out), C.c_void_p(0)))
+    return rowmap_out, entries_out
+
+
+def transpose_matrix(A):
+    """KokkosSparse::Impl::transpose_matrix(A) (sparse/src/KokkosSparse_Utils.hpp:380-398); rows of the
+    result list their entries in (row of A, position) order."""
+    m, n = A.numRows(), A.numCols()
+    dev = A.row_map.device
+    t_rowmap = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    t_entries = torch.empty(A.nnz(), dtype=torch.int32, device=dev)
+    t_values = torch.empty(A.nnz(), dtype=A.values.dtype, device=dev)
+    check(getattr(_lib.sparse(), f"b200sp_transpose_{_sfx(A.values)}_i32")(
+        _stream(), m, n, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), C.c_void_p(t_rowmap.data_ptr()), _ptr(t_entries),
+        _ptr(t_values)))
+    return CrsMatrix(t_rowmap, t_entries, t_values, m)
+
+
+def spadd_symbolic_views(kh, m, n, a_rowmap, a_entries, b_rowmap, b_entries, c_rowmap):
+    """View-level spadd_symbolic (KokkosSparse_spadd.hpp:29-93): c_rowmap is allocated by the caller
+    (not initialised) and fully written; nnz(C) is left in the handle."""
+    ah = kh.get_spadd_handle()
+    if ah is None:
+        raise B200SparseInvalidArgument("spadd_symbolic: create_spadd_handle() was not called")
+    c_nnz = C.c_int64(0)
+    check(_lib.sparse().b200sp_spadd_symbolic_i32(ah._plan, _stream(), m, n, _ptr(a_rowmap), _ptr(a_entries), _ptr(b_rowmap),
+                                                  _ptr(b_entries), _ptr(c_rowmap), C.byref(c_nnz)))
+    ah._c_nnz = c_nnz.value
+    ah._symbolic, ah._numeric = True, False
+
+
+def spadd_numeric_views(kh, m, n, a_rowmap, a_entries, a_values, alpha, b_rowmap, b_entries, b_values, beta, c_rowmap, c_entries,
+                        c_values):
+    ah = kh.get_spadd_handle()
+    if ah is None or not ah.is_symbolic_called():
+        raise B200SparseError("spadd_numeric: call spadd_symbolic first")
+    fn = getattr(_lib.sparse(), f"b200sp_spadd_numeric_{_sfx(c_values)}_i32")
+    check(fn(ah._plan, _stream(), m, n, _ptr(a_rowmap), _ptr(a_entries), _ptr(a_values), alpha, _ptr(b_rowmap), _ptr(b_entries),
+             _ptr(b_values), beta, _ptr(c_rowmap), _ptr(c_entries), _ptr(c_values)))
+    ah._numeric = True
+
+
+def spadd_symbolic(kh, A, B):
+    """Matrix-level spadd_symbolic (KokkosSparse_spadd.hpp:233-271): returns C with its row map filled,
+    entries / values allocated from get_c_nnz(); C has A's dimensions even when trailing rows or
+    columns are empty (test_spadd_known_columns)."""
+    if A.numRows() != B.numRows() or A.numCols() != B.numCols():
+        raise B200SparseError("KokkosSparse::spadd_symbolic: A and B must have the same dimensions")
+    m, n = A.numRows(), A.numCols()
+    dev = A.row_map.device
+    c_rowmap = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    spadd_symbolic_views(kh, m, n, A.row_map, A.entries, B.row_map, B.entries, c_rowmap)
+    c_nnz = kh.get_spadd_handle().get_c_nnz()
+    return CrsMatrix(c_rowmap, torch.empty(c_nnz, dtype=torch.int32, device=dev),
+                     torch.empty(c_nnz, dtype=A.values.dtype, device=dev), n)
+
+
+def spadd_numeric(kh, alpha, A, beta, B, Cm):
+    spadd_numeric_views(kh, A.numRows(), A.numCols(), A.row_map, A.entries, A.values, alpha, B.row_map, B.entries, B.values, beta,
+                        Cm.row_map, Cm.entries, Cm.values)
     return Cm

@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_next: GPU tests of code that has not had its first run on a B200 yet "
+                                       "(validated with tools/gpu_check first, then promoted to `gpu`)")
 
 
 @pytest.fixture(scope="session", autouse=True)

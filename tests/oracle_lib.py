@@ -44,6 +44,18 @@ class Oracle:
         L.okk_mmd_entry.restype = i32
         L.okk_diagonal_search.argtypes = [vp, i64, vp, i64, i64, C.POINTER(i64), C.POINTER(i64)]
         L.okk_num_threads.restype = i32
+        for sfx, ft in (("f64", f64), ("f32", f32)):
+            getattr(L, f"okk_sort_crs_stable_{sfx}").argtypes = [i32, vp, vp, vp]
+            getattr(L, f"okk_merged_entries_{sfx}").argtypes = [i32, vp, vp, vp, vp, vp, vp]
+            getattr(L, f"okk_spadd_sorted_numeric_{sfx}").argtypes = [i32, vp, vp, vp, ft, vp, vp, vp, ft, vp, vp, vp]
+            getattr(L, f"okk_spadd_unsorted_numeric_{sfx}").argtypes = [i32, vp, vp, vp, ft, vp, vp, vp, ft, vp, vp, vp, vp, vp]
+        L.okk_sort_crs_stable_i32.argtypes = [i32, vp, vp, vp]
+        L.okk_merged_rowmap.argtypes = [i32, vp, vp, vp]
+        L.okk_merged_rowmap.restype = i64
+        L.okk_spadd_sorted_symbolic.argtypes = [i32, vp, vp, vp, vp, vp]
+        L.okk_spadd_sorted_symbolic.restype = i64
+        L.okk_spadd_unsorted_symbolic.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp]
+        L.okk_spadd_unsorted_symbolic.restype = i64
         self.ref = None
         rpath = os.path.join(ODIR, "_ref", "libkkref.so")
         if os.path.exists(rpath):
@@ -133,6 +145,51 @@ class Oracle:
         tv = np.empty(len(v), dtype=np.float64)
         self.lib.okk_transpose_f64(m, ncol, _p(rp), _p(ci), _p(v), _p(trp), _p(tci), _p(tv))
         return trp, tci, tv
+
+    # ---- CrsMatrix utilities (oracle/kk_oracle_crs.c) ----
+    def sort_crs_stable(self, rp, ci, v=None):
+        """sort_crs_matrix / sort_crs_graph, host path (stable LSD radix per row); in place."""
+        if v is None:
+            self.lib.okk_sort_crs_stable_f64(len(rp) - 1, _p(rp), _p(ci), None)
+        elif v.dtype == np.int32:
+            self.lib.okk_sort_crs_stable_i32(len(rp) - 1, _p(rp), _p(ci), _p(v))
+        else:
+            getattr(self.lib, "okk_sort_crs_stable_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v))
+
+    def sort_and_merge(self, rp, ci, v=None):
+        """sort_and_merge_matrix / _graph: sorts the input in place, returns the merged matrix."""
+        m = max(len(rp) - 1, 0)
+        if m == 0:
+            return np.zeros(len(rp), dtype=np.int32), np.zeros(0, np.int32), (None if v is None else np.zeros(0, v.dtype))
+        self.sort_crs_stable(rp, ci, v)
+        rpo = np.zeros(m + 1, dtype=np.int32)
+        nnz = self.lib.okk_merged_rowmap(m, _p(rp), _p(ci), _p(rpo))
+        cio = np.empty(nnz, dtype=np.int32)
+        vo = None if v is None else np.empty(nnz, dtype=v.dtype)
+        sfx = "f64" if v is None else self._sfx(v)
+        getattr(self.lib, "okk_merged_entries_" + sfx)(m, _p(rp), _p(ci), _p(v), _p(rpo), _p(cio), _p(vo))
+        return rpo, cio, vo
+
+    def spadd(self, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, sorted_input):
+        """spadd_symbolic + spadd_numeric, host path."""
+        m = len(rpA) - 1
+        rpC = np.zeros(m + 1, dtype=np.int32)
+        sfx = self._sfx(vA)
+        if sorted_input:
+            nnz = self.lib.okk_spadd_sorted_symbolic(m, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC))
+            ciC = np.empty(nnz, dtype=np.int32)
+            vC = np.empty(nnz, dtype=vA.dtype)
+            getattr(self.lib, "okk_spadd_sorted_numeric_" + sfx)(m, _p(rpA), _p(ciA), _p(vA), alpha, _p(rpB), _p(ciB), _p(vB), beta,
+                                                                 _p(rpC), _p(ciC), _p(vC))
+            return rpC, ciC, vC
+        apos = np.zeros(max(len(ciA), 1), dtype=np.int32)
+        bpos = np.zeros(max(len(ciB), 1), dtype=np.int32)
+        nnz = self.lib.okk_spadd_unsorted_symbolic(m, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC), _p(apos), _p(bpos))
+        ciC = np.empty(nnz, dtype=np.int32)
+        vC = np.empty(nnz, dtype=vA.dtype)
+        getattr(self.lib, "okk_spadd_unsorted_numeric_" + sfx)(m, _p(rpA), _p(ciA), _p(vA), alpha, _p(rpB), _p(ciB), _p(vB), beta,
+                                                               _p(rpC), _p(ciC), _p(vC), _p(apos), _p(bpos))
+        return rpC, ciC, vC
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)

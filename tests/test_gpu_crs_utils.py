@@ -1,0 +1,178 @@
+"""GPU parity of the CrsMatrix utilities (sort_crs_matrix, sort_and_merge_matrix, transpose_matrix,
+spadd) through the C ABI against the oracle's restatement of the reference's host path: every
+output array bit-identical (int32 structure AND floating-point values -- the kernels keep the
+reference's per-row operation order), plus the reference's own acceptance laws
+(Test_Sparse_SortCrs.hpp, Test_Sparse_spadd.hpp)."""
+import numpy as np
+import pytest
+import torch
+
+from crs_cases import MERGE_CASES, random_matrix, spadd_dense_check
+from helpers import kk_matrix
+
+# promoted to `gpu` once tools/gpu_check's `crs` suite has passed on a B200 (profiles/)
+pytestmark = pytest.mark.gpu_next
+
+
+def dev_mat(sp, dev, rp, ci, v, ncols):
+    return sp.CrsMatrix(torch.from_numpy(rp.copy()).to(dev), torch.from_numpy(ci.copy()).to(dev),
+                        torch.from_numpy(v.copy()).to(dev), ncols)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def long_row_matrix(rng, m, n, long_lens, dtype=np.float64):
+    """Short random rows plus a few rows in the CTA (257..4096) and global (>4096) sort classes, with
+    duplicate columns so that stability matters."""
+    lens = rng.integers(0, 40, m)
+    lens[: len(long_lens)] = long_lens
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = rng.integers(0, n, rp[-1]).astype(np.int32)
+    v = rng.uniform(-1, 1, rp[-1]).astype(dtype)
+    return rp, ci, v
+
+
+@pytest.mark.parametrize("m,n,nnz", [(10, 10, 20), (100, 100, 2000), (1000, 1000, 30000), (50, 200, 3000), (20000, 20000, 600000)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sort_crs_matrix_sweep(cuda, oracle, m, n, nnz, dtype):
+    """testSortCRS (Test_Sparse_SortCrs.hpp:44-139): kk_generate_sparse_matrix rows are unsorted."""
+    from kokkos_kernels_b200 import sparse as sp
+
+    rp, ci, v = kk_matrix(m, n, nnz, 2, n // 2, dtype=dtype)
+    A = dev_mat(sp, cuda, rp, ci, v, n)
+    sp.sort_crs_matrix(A)
+    G = torch.from_numpy(ci.copy()).to(cuda)
+    sp.sort_crs_graph(A.row_map, G)
+    oracle.sort_crs_stable(rp, ci, v)
+    assert np.array_equal(host(A.entries), ci) and np.array_equal(host(A.values), v)
+    assert np.array_equal(host(G), ci)
+    # idempotent, and already-sorted input is left untouched
+    sp.sort_crs_matrix(A)
+    assert np.array_equal(host(A.entries), ci) and np.array_equal(host(A.values), v)
+
+
+def test_sort_long_rows_and_stability(cuda, oracle):
+    from kokkos_kernels_b200 import sparse as sp
+
+    rng = np.random.default_rng(11)
+    rp, ci, v = long_row_matrix(rng, 3000, 500, [9000, 5000, 4097, 4096, 300, 257, 256, 255, 33, 32, 31, 2, 1, 0])
+    A = dev_mat(sp, cuda, rp, ci, v, 500)
+    sp.sort_crs_matrix(A)
+    oracle.sort_crs_stable(rp, ci, v)
+    assert np.array_equal(host(A.entries), ci)
+    assert np.array_equal(host(A.values), v), "ties must keep their original order (stable sort)"
+
+
+@pytest.mark.parametrize("case", sorted(MERGE_CASES))
+def test_sort_and_merge_golden(cuda, case):
+    from kokkos_kernels_b200 import sparse as sp
+
+    c = MERGE_CASES[case]
+    A = dev_mat(sp, cuda, c["rowmap"], c["entries"], c["values"], c["ncols"])
+    M = sp.sort_and_merge_matrix(A)
+    assert np.array_equal(host(M.row_map), c["gold_rowmap"])
+    assert np.array_equal(host(M.entries), c["gold_entries"])
+    assert np.array_equal(host(M.values), c["gold_values"])
+    rm, en = sp.sort_and_merge_graph(torch.from_numpy(c["rowmap"].copy()).to(cuda), torch.from_numpy(c["entries"].copy()).to(cuda))
+    assert np.array_equal(host(rm), c["gold_rowmap"]) and np.array_equal(host(en), c["gold_entries"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sort_and_merge_random(cuda, oracle, dtype):
+    from kokkos_kernels_b200 import sparse as sp
+
+    rng = np.random.default_rng(3)
+    rp, ci, v = long_row_matrix(rng, 5000, 60, [5000, 700, 100], dtype=dtype)   # 60 columns: many duplicates
+    A = dev_mat(sp, cuda, rp, ci, v, 60)
+    M = sp.sort_and_merge_matrix(A)
+    rpo, cio, vo = oracle.sort_and_merge(rp, ci, v)
+    assert np.array_equal(host(M.row_map), rpo) and np.array_equal(host(M.entries), cio)
+    assert np.array_equal(host(M.values), vo), "duplicates are summed in the sorted row's order: bit-identical"
+    assert np.array_equal(host(A.entries), ci), "the input is sorted in place on the way"
+
+
+@pytest.mark.parametrize("m,n,nnz", [(100, 300, 2000), (3000, 1000, 90000), (1, 5, 3), (7, 1, 4)])
+def test_transpose_matrix(cuda, oracle, m, n, nnz):
+    from kokkos_kernels_b200 import sparse as sp
+
+    rng = np.random.default_rng(m)
+    lens = rng.multinomial(nnz, np.ones(m) / m)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = rng.integers(0, n, nnz).astype(np.int32)          # duplicates within a row are allowed
+    v = rng.uniform(-1, 1, nnz)
+    T = sp.transpose_matrix(dev_mat(sp, cuda, rp, ci, v, n))
+    trp, tci, tv = oracle.transpose(rp, ci, v, n)
+    assert T.numRows() == n and T.numCols() == m
+    assert np.array_equal(host(T.row_map), trp) and np.array_equal(host(T.entries), tci) and np.array_equal(host(T.values), tv)
+
+
+def test_transpose_empty(cuda):
+    from kokkos_kernels_b200 import sparse as sp
+
+    A = sp.CrsMatrix(torch.zeros(6, dtype=torch.int32, device=cuda), torch.zeros(0, dtype=torch.int32, device=cuda),
+                     torch.zeros(0, dtype=torch.float64, device=cuda), 9)
+    T = sp.transpose_matrix(A)
+    assert T.row_map.numel() == 10 and not host(T.row_map).any() and T.nnz() == 0
+
+
+@pytest.mark.parametrize("sort_rows", [True, False])
+@pytest.mark.parametrize("m,n,lo,hi", [(10, 10, 0, 0), (10, 10, 0, 2), (100, 100, 50, 100), (50, 50, 75, 100), (20000, 3000, 0, 60)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spadd(cuda, oracle, sort_rows, m, n, lo, hi, dtype):
+    """test_spadd (Test_Sparse_spadd.hpp:96-187), incl. duplicated entries when maxNNZ > ncols; C's row
+    map is pre-filled with 5 and C's entries / values with 5 like the reference test does."""
+    from kokkos_kernels_b200 import sparse as sp
+
+    A = random_matrix(m, n, lo, hi, sort_rows, seed=(m << 1) ^ n, dtype=dtype)
+    B = random_matrix(m, n, lo, hi, sort_rows, seed=((m << 1) ^ n) + 1, dtype=dtype)
+    Ad, Bd = dev_mat(sp, cuda, *A, n), dev_mat(sp, cuda, *B, n)
+    kh = sp.KokkosKernelsHandle()
+    kh.create_spadd_handle(sort_rows, hi <= n)
+    ah = kh.get_spadd_handle()
+    c_rowmap = torch.full((m + 1,), 5, dtype=torch.int32, device=cuda)
+    sp.spadd_symbolic_views(kh, m, n, Ad.row_map, Ad.entries, Bd.row_map, Bd.entries, c_rowmap)
+    assert ah.is_symbolic_called() and not ah.is_numeric_called()
+    c_entries = torch.full((ah.get_c_nnz(),), 5, dtype=torch.int32, device=cuda)
+    c_values = torch.full((ah.get_c_nnz(),), 5, dtype=Ad.values.dtype, device=cuda)
+    one = dtype(1)
+    sp.spadd_numeric_views(kh, m, n, Ad.row_map, Ad.entries, Ad.values, one, Bd.row_map, Bd.entries, Bd.values, one, c_rowmap,
+                           c_entries, c_values)
+    assert ah.is_numeric_called()
+    got = (host(c_rowmap), host(c_entries), host(c_values))
+    spadd_dense_check(A, B, got, n, 1.0, 1.0)
+    exp = oracle.spadd(*A, one, *B, one, sort_rows)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+    # numeric again with other coefficients on the same symbolic
+    a2, b2 = dtype(0.3), dtype(-1.7)  # not powers of two: the products round (no FMA contraction in the kernels)
+    sp.spadd_numeric_views(kh, m, n, Ad.row_map, Ad.entries, Ad.values, a2, Bd.row_map, Bd.entries, Bd.values, b2, c_rowmap,
+                           c_entries, c_values)
+    exp2 = oracle.spadd(*A, a2, *B, b2, sort_rows)
+    assert np.array_equal(host(c_values), exp2[2])
+    kh.destroy_spadd_handle()
+
+
+def test_spadd_known_columns_and_misuse(cuda):
+    from kokkos_kernels_b200 import sparse as sp
+    from kokkos_kernels_b200 import B200SparseError
+
+    rp = torch.tensor([0, 1, 2, 3, 4, 4, 4], dtype=torch.int32, device=cuda)
+    A = sp.CrsMatrix(rp, torch.arange(4, dtype=torch.int32, device=cuda), torch.ones(4, dtype=torch.float64, device=cuda), 7)
+    kh = sp.KokkosKernelsHandle()
+    kh.create_spadd_handle(True)
+    with pytest.raises(B200SparseError):
+        sp.spadd_numeric(kh, 1.0, A, 1.0, A, A)
+    Cm = sp.spadd_symbolic(kh, A, A)
+    sp.spadd_numeric(kh, 1.0, A, 1.0, A, Cm)
+    assert Cm.numRows() == 6 and Cm.numCols() == 7 and Cm.nnz() == A.nnz()
+    assert torch.all(Cm.values == 2.0)
+    # zero rows
+    E = sp.CrsMatrix(torch.zeros(1, dtype=torch.int32, device=cuda), torch.zeros(0, dtype=torch.int32, device=cuda),
+                     torch.zeros(0, dtype=torch.float64, device=cuda), 3)
+    kh2 = sp.KokkosKernelsHandle()
+    kh2.create_spadd_handle(False)
+    C0 = sp.spadd_symbolic(kh2, E, E)
+    sp.spadd_numeric(kh2, 1.0, E, 1.0, E, C0)
+    assert C0.nnz() == 0 and host(C0.row_map).tolist() == [0]

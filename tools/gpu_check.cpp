@@ -1,0 +1,896 @@
+// gpu_check.cpp -- torch-free GPU validation + timing harness for libb200sparse (TEST INFRASTRUCTURE).
+//
+// Why: a fresh GPU box spends about a minute importing torch before the first test runs; this binary
+// starts in milliseconds, so a short gpurun slot is enough to check new kernels against the oracle and
+// to A/B-time kernel variants.  It links the product library (C ABI), the host matrix generators and
+// the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
+// faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
+//
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm
+//
+// Exit code: number of failed suites.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "b200sparse.h"
+
+extern "C" {
+// oracle (oracle/kk_oracle.c, oracle/kk_oracle_crs.c)
+int64_t okk_spgemm_symbolic(int m, int k, const int* rmA, const int* entA, const int* rmB, const int* entB, int* rmC);
+void okk_spgemm_numeric_f64(int m, int k, const int* rmA, const int* entA, const double* valA, const int* rmB,
+                            const int* entB, const double* valB, const int* rmC, int* entC, double* valC);
+void okk_spgemm_numeric_f32(int m, int k, const int* rmA, const int* entA, const float* valA, const int* rmB,
+                            const int* entB, const float* valB, const int* rmC, int* entC, float* valC);
+void okk_sort_crs_f64(int m, const int* rm, int* ent, double* val);
+void okk_sort_crs_f32(int m, const int* rm, int* ent, float* val);
+void okk_sort_crs_stable_f64(int m, const int* rm, int* ent, double* val);
+void okk_sort_crs_stable_f32(int m, const int* rm, int* ent, float* val);
+int64_t okk_merged_rowmap(int m, const int* rm, const int* ent, int* rm_out);
+void okk_merged_entries_f64(int m, const int* rm, const int* ent, const double* val, const int* rm_out, int* ent_out,
+                            double* val_out);
+void okk_merged_entries_f32(int m, const int* rm, const int* ent, const float* val, const int* rm_out, int* ent_out,
+                            float* val_out);
+int64_t okk_spadd_sorted_symbolic(int m, const int* rmA, const int* entA, const int* rmB, const int* entB, int* rmC);
+void okk_spadd_sorted_numeric_f64(int m, const int* rmA, const int* entA, const double* valA, double alpha, const int* rmB,
+                                  const int* entB, const double* valB, double beta, const int* rmC, int* entC, double* valC);
+void okk_spadd_sorted_numeric_f32(int m, const int* rmA, const int* entA, const float* valA, float alpha, const int* rmB,
+                                  const int* entB, const float* valB, float beta, const int* rmC, int* entC, float* valC);
+int64_t okk_spadd_unsorted_symbolic(int m, const int* rmA, const int* entA, const int* rmB, const int* entB, int* rmC,
+                                    int* apos, int* bpos);
+void okk_spadd_unsorted_numeric_f64(int m, const int* rmA, const int* entA, const double* valA, double alpha,
+                                    const int* rmB, const int* entB, const double* valB, double beta, const int* rmC,
+                                    int* entC, double* valC, const int* apos, const int* bpos);
+void okk_spadd_unsorted_numeric_f32(int m, const int* rmA, const int* entA, const float* valA, float alpha,
+                                    const int* rmB, const int* entB, const float* valB, float beta, const int* rmC,
+                                    int* entC, float* valC, const int* apos, const int* bpos);
+void okk_transpose_f64(int nrow, int ncol, const int* rm, const int* ent, const double* val, int* trm, int* tent,
+                       double* tval);
+void okk_spmv_mv_f64(int nrow, int ncol, int nvec, const int* rm, const int* ci, const double* v, const double* X,
+                     int64_t xr, int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta, int threads);
+void okk_spmv_mv_f32(int nrow, int ncol, int nvec, const int* rm, const int* ci, const float* v, const float* X,
+                     int64_t xr, int64_t xc, float* Y, int64_t yr, int64_t yc, float alpha, float beta, int threads);
+void okk_spmv_serial_f64(int nrow, const int* rm, const int* ci, const double* v, const double* x, double* y, double alpha,
+                         double beta);
+void okk_spmv_transpose_f64(int nrow, int ncol, const int* rm, const int* ci, const double* v, const double* x, double* y,
+                            double alpha, double beta);
+int okk_num_threads(void);
+// host generators (kokkos-kernels_b200/csrc/matgen.c)
+void b200gen_fill_f64(int64_t n, double* v, double lo, double hi, uint64_t seed);
+void b200gen_fill_f32(int64_t n, float* v, float lo, float hi, uint64_t seed);
+int64_t b200gen_kk_rowptr(int nrows, int ncols, int64_t nnz_target, int row_size_variance, int* rowptr);
+void b200gen_kk_colidx(int nrows, int ncols, int64_t nnz_target, int row_size_variance, int bandwidth, const int* rowptr,
+                       int* colind);
+int64_t b200gen_lap27_rows(int nx, int ny, int nz, int ndof, int64_t row_begin, int64_t row_end, int* rowptr, int* colidx,
+                           double* vals, double noise, uint64_t seed);
+void b200gen_uniform(int nrows, int ncols, int deg, uint64_t seed, int* rowptr, int* colidx);
+void* b200gen_rmat_build(int scale, int edge_factor, double a, double b, double c, uint64_t seed, int64_t* nnz_out);
+void b200gen_rmat_emit(void* h, int* rowptr, int* colidx);
+}
+
+// ------------------------------------------------------------------------------------------------
+static std::string g_out = "gpurun_out/gpu_check.jsonl";
+static const char* g_suite = "";
+static int g_fail = 0;
+static bool g_big = false;
+static bool g_dry = false;  // --dry: no CUDA at all (device buffers live in host memory, C-ABI calls are skipped): exercises the
+                            // generators, the oracle calls and the comparison code on a machine without a GPU
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static void record(const char* name, bool ok, const char* fmt, ...) {
+  char detail[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(detail, sizeof(detail), fmt, ap);
+  va_end(ap);
+  for (char* c = detail; *c; ++c)
+    if (*c == '"' || *c == '\\' || *c == '\n') *c = ' ';
+  FILE* f = fopen(g_out.c_str(), "a");
+  if (f) {
+    fprintf(f, "{\"suite\": \"%s\", \"check\": \"%s\", \"ok\": %s, \"detail\": \"%s\"}\n", g_suite, name, ok ? "true" : "false", detail);
+    fclose(f);
+  }
+  fprintf(stderr, "[%s] %-44s %s  %s\n", g_suite, name, ok ? "ok  " : "FAIL", detail);
+  if (!ok) ++g_fail;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    if (g_dry) break;                                                                              \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      record("cuda", false, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      exit(3);                                                                                     \
+    }                                                                                              \
+  } while (0)
+#define SP(expr)                                                                                    \
+  do {                                                                                              \
+    if (g_dry) break;                                                                               \
+    int _rc = (expr);                                                                               \
+    if (_rc != 0) {                                                                                 \
+      record("cabi", false, "%s -> status %d: %s (%s:%d)", #expr, _rc, b200sp_last_error_string(), __FILE__, __LINE__); \
+      exit(4);                                                                                      \
+    }                                                                                               \
+  } while (0)
+
+template <typename T>
+struct Dev {
+  T* p = nullptr;
+  size_t n = 0;
+  Dev() {}
+  explicit Dev(size_t count) { alloc(count); }
+  explicit Dev(const std::vector<T>& h) {
+    alloc(h.size());
+    if (n && g_dry) memcpy(p, h.data(), n * sizeof(T));
+    if (n) CK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  Dev(const Dev&) = delete;
+  Dev& operator=(const Dev&) = delete;
+  ~Dev() { release(); }
+  void release() {
+    if (p && g_dry) free(p);
+    else if (p) cudaFree(p);
+    p = nullptr;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (g_dry) p = (T*)calloc(std::max<size_t>(count, 1), sizeof(T));
+    CK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void fill_bytes(int byte) {
+    if (g_dry) memset(p, byte, std::max<size_t>(n, 1) * sizeof(T));
+    CK(cudaMemset(p, byte, std::max<size_t>(n, 1) * sizeof(T)));
+  }
+  std::vector<T> host() const { return host(0, n); }
+  std::vector<T> host(size_t off, size_t count) const {
+    std::vector<T> h(count);
+    if (count && g_dry) memcpy(h.data(), p + off, count * sizeof(T));
+    if (count) CK(cudaMemcpy(h.data(), p + off, count * sizeof(T), cudaMemcpyDeviceToHost));
+    return h;
+  }
+};
+
+struct Rng {
+  uint64_t s;
+  explicit Rng(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull) {}
+  uint64_t next() {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t x = s;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  }
+  int below(int n) { return (int)(next() % (uint64_t)std::max(n, 1)); }
+  double u01() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+template <typename S>
+struct Csr {
+  int m = 0, n = 0;
+  std::vector<int> rp, ci;
+  std::vector<S> v;
+  int64_t nnz() const { return (int64_t)ci.size(); }
+};
+
+template <typename S>
+static void fill_vals(std::vector<S>& v, double lo, double hi, uint64_t seed) {
+  Rng r(seed);
+  for (auto& x : v) x = (S)(lo + (hi - lo) * r.u01());
+}
+
+// kk_generate_sparse_matrix structure (unsorted rows, no duplicates)
+template <typename S>
+static Csr<S> gen_kk(int m, int n, int64_t nnz, int var, int bw, uint64_t seed) {
+  Csr<S> A;
+  A.m = m;
+  A.n = n;
+  A.rp.assign(m + 1, 0);
+  const int64_t got = b200gen_kk_rowptr(m, n, nnz, var, A.rp.data());
+  A.ci.resize(got);
+  b200gen_kk_colidx(m, n, nnz, var, bw, A.rp.data(), A.ci.data());
+  A.v.resize(got);
+  fill_vals(A.v, 1.0, 50.0, seed);
+  return A;
+}
+
+// arbitrary row lengths, columns uniform in [0, n) -- duplicates allowed unless `distinct`
+template <typename S>
+static Csr<S> gen_rows(const std::vector<int>& lens, int n, bool distinct, bool sorted, uint64_t seed) {
+  Csr<S> A;
+  A.m = (int)lens.size();
+  A.n = n;
+  A.rp.assign(A.m + 1, 0);
+  for (int i = 0; i < A.m; ++i) A.rp[i + 1] = A.rp[i] + lens[i];
+  A.ci.resize(A.rp[A.m]);
+  Rng r(seed);
+  std::vector<char> used;
+  if (distinct) used.assign(n, 0);
+  for (int i = 0; i < A.m; ++i) {
+    int* c = A.ci.data() + A.rp[i];
+    for (int j = 0; j < lens[i]; ++j) {
+      int col;
+      do col = r.below(n);
+      while (distinct && used[col]);
+      if (distinct) used[col] = 1;
+      c[j] = col;
+    }
+    if (distinct)
+      for (int j = 0; j < lens[i]; ++j) used[c[j]] = 0;
+    if (sorted) std::sort(c, c + lens[i]);
+  }
+  A.v.resize(A.ci.size());
+  fill_vals(A.v, 1.0, 50.0, seed + 17);
+  return A;
+}
+
+template <typename S>
+static Csr<S> gen_lap27(int g, int ndof) {
+  Csr<S> A;
+  A.m = A.n = g * g * g * ndof;
+  A.rp.assign(A.m + 1, 0);
+  const int64_t nnz = b200gen_lap27_rows(g, g, g, ndof, 0, A.m, A.rp.data(), nullptr, nullptr, 0.0, 0);
+  A.ci.resize(nnz);
+  std::vector<double> v(nnz);
+  b200gen_lap27_rows(g, g, g, ndof, 0, A.m, A.rp.data(), A.ci.data(), v.data(), 0.5, 7);
+  A.v.resize(nnz);
+  for (int64_t i = 0; i < nnz; ++i) A.v[i] = (S)(std::fabs(v[i]) + 1.0);
+  return A;
+}
+
+template <typename S>
+static Csr<S> gen_uniform(int m, int n, int deg, uint64_t seed) {
+  Csr<S> A;
+  A.m = m;
+  A.n = n;
+  A.rp.resize(m + 1);
+  A.ci.resize((size_t)m * deg);
+  b200gen_uniform(m, n, deg, seed, A.rp.data(), A.ci.data());
+  A.v.resize(A.ci.size());
+  if (sizeof(S) == 8) b200gen_fill_f64((int64_t)A.v.size(), (double*)A.v.data(), 1.0, 50.0, seed);
+  else b200gen_fill_f32((int64_t)A.v.size(), (float*)A.v.data(), 1.0f, 50.0f, seed);
+  return A;
+}
+
+template <typename S>
+static int64_t rel_mismatch(const std::vector<S>& a, const std::vector<S>& b, double eps) {
+  // is_same_matrix value law (Test_Sparse_Utils.hpp:86-118)
+  int64_t bad = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    const double x = a[i], y = b[i], ax = std::fabs(x), ay = std::fabs(y);
+    if (ax <= eps && ay <= eps) continue;
+    if (!(std::fabs(x - y) / (ax + ay) <= eps)) ++bad;
+  }
+  return bad;
+}
+
+template <typename T>
+static int64_t count_diff(const std::vector<T>& a, const std::vector<T>& b) {
+  if (a.size() != b.size()) return -1;
+  int64_t d = 0;
+  for (size_t i = 0; i < a.size(); ++i) d += (memcmp(&a[i], &b[i], sizeof(T)) != 0);
+  return d;
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() {
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+  }
+  ~Timer() {
+    if (g_dry) return;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() { CK(cudaEventRecord(a, 0)); }
+  float stop_ms() {
+    if (g_dry) return 1.0f;
+    CK(cudaEventRecord(b, 0));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    return ms;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// suite: spgemm -- numeric variants 1/2/3 against the oracle (row_ptr / col_idx exact, values by the law)
+// ------------------------------------------------------------------------------------------------
+template <typename S>
+struct OracleSpgemm {
+  std::vector<int> rp, ci;
+  std::vector<S> v;
+};
+static void oracle_numeric(int m, int k, const Csr<double>& A, const Csr<double>& B, const std::vector<int>& rp,
+                           std::vector<int>& ci, std::vector<double>& v) {
+  okk_spgemm_numeric_f64(m, k, A.rp.data(), A.ci.data(), A.v.data(), B.rp.data(), B.ci.data(), B.v.data(), rp.data(), ci.data(), v.data());
+  okk_sort_crs_f64(m, rp.data(), ci.data(), v.data());
+}
+static void oracle_numeric(int m, int k, const Csr<float>& A, const Csr<float>& B, const std::vector<int>& rp,
+                           std::vector<int>& ci, std::vector<float>& v) {
+  okk_spgemm_numeric_f32(m, k, A.rp.data(), A.ci.data(), A.v.data(), B.rp.data(), B.ci.data(), B.v.data(), rp.data(), ci.data(), v.data());
+  okk_sort_crs_f32(m, rp.data(), ci.data(), v.data());
+}
+static int numeric_call(b200sp_spgemm_plan* p, int m, int n, int k, const int* rpA, const int* ciA, const double* vA,
+                        const int* rpB, const int* ciB, const double* vB, const int* rpC, int* ciC, double* vC) {
+  return b200sp_spgemm_numeric_f64_i32(p, nullptr, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+}
+static int numeric_call(b200sp_spgemm_plan* p, int m, int n, int k, const int* rpA, const int* ciA, const float* vA,
+                        const int* rpB, const int* ciB, const float* vB, const int* rpC, int* ciC, float* vC) {
+  return b200sp_spgemm_numeric_f32_i32(p, nullptr, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+}
+
+template <typename S>
+static void spgemm_case(const char* name, const Csr<S>& A, const Csr<S>& B) {
+  const int m = A.m, n = A.n, k = B.n;
+  OracleSpgemm<S> o;
+  o.rp.assign(m + 1, 0);
+  const int64_t onnz = okk_spgemm_symbolic(m, k, A.rp.data(), A.ci.data(), B.rp.data(), B.ci.data(), o.rp.data());
+  o.ci.resize(onnz);
+  o.v.resize(onnz);
+  oracle_numeric(m, k, A, B, o.rp, o.ci, o.v);
+  Dev<int> rpA(A.rp), ciA(A.ci), rpB(B.rp), ciB(B.ci), rpC((size_t)m + 1);
+  Dev<S> vA(A.v), vB(B.v);
+  rpC.fill_bytes(0x7b);
+  b200sp_spgemm_plan* plan = nullptr;
+  SP(b200sp_spgemm_plan_create(&plan));
+  int64_t c_nnz = -1;
+  int c_max = -1;
+  SP(b200sp_spgemm_symbolic_i32(plan, nullptr, m, n, k, rpA.p, ciA.p, rpB.p, ciB.p, rpC.p, &c_nnz, &c_max));
+  char nm[128];
+  snprintf(nm, sizeof(nm), "%s/symbolic", name);
+  const bool sym_ok = c_nnz == onnz && count_diff(rpC.host(), o.rp) == 0;
+  record(nm, sym_ok, "m=%d nnzA=%lld c_nnz=%lld (oracle %lld) c_max=%d", m, (long long)A.nnz(), (long long)c_nnz, (long long)onnz, c_max);
+  if (!sym_ok) {
+    b200sp_spgemm_plan_destroy(plan, nullptr);
+    return;
+  }
+  const double eps = sizeof(S) == 8 ? 1e-7 : 3.7e-3;
+  for (int variant = 1; variant <= 3; ++variant) {
+    char ev[8];
+    snprintf(ev, sizeof(ev), "%d", variant);
+    setenv("B200SP_SPGEMM_NUMERIC", ev, 1);
+    Dev<int> ciC((size_t)c_nnz);
+    Dev<S> vC((size_t)c_nnz);
+    ciC.fill_bytes(0xff);
+    vC.fill_bytes(0xff);
+    Timer t;
+    t.start();
+    SP(numeric_call(plan, m, n, k, rpA.p, ciA.p, vA.p, rpB.p, ciB.p, vB.p, rpC.p, ciC.p, vC.p));
+    const float ms = t.stop_ms();
+    CK(cudaDeviceSynchronize());
+    const int64_t dci = count_diff(ciC.host(), o.ci);
+    const int64_t dv = rel_mismatch(vC.host(), o.v, eps);
+    snprintf(nm, sizeof(nm), "%s/numeric_v%d", name, variant);
+    record(nm, dci == 0 && dv == 0, "col_idx diffs=%lld value law violations=%lld of %lld, %.3f ms", (long long)dci, (long long)dv,
+           (long long)c_nnz, ms);
+  }
+  unsetenv("B200SP_SPGEMM_NUMERIC");
+  b200sp_spgemm_plan_destroy(plan, nullptr);
+}
+
+static void suite_spgemm() {
+  {
+    auto A = gen_kk<double>(10000, 8000, 160000, 10, 500, 1), B = gen_kk<double>(8000, 6000, 160000, 10, 500, 2);
+    okk_sort_crs_f64(A.m, A.rp.data(), A.ci.data(), A.v.data());
+    okk_sort_crs_f64(B.m, B.rp.data(), B.ci.data(), B.v.data());
+    spgemm_case("kk_10000x8000x6000_f64", A, B);
+  }
+  {
+    auto A = gen_kk<float>(1000, 500, 20000, 10, 500, 1), B = gen_kk<float>(500, 1600, 20000, 10, 500, 2);
+    spgemm_case("kk_unsorted_1000x500x1600_f32", A, B);
+  }
+  {
+    Rng r(3);
+    std::vector<int> lens(20000);
+    for (auto& l : lens) l = r.below(12);
+    lens[0] = 6000;
+    lens[1] = 1200;
+    lens[2] = 400;
+    auto A = gen_rows<double>(lens, 20000, true, false, 3);
+    spgemm_case("wide_rows_unsorted_20000_f64", A, A);
+  }
+  {
+    auto A = gen_lap27<double>(12, 2);
+    spgemm_case("lap27_12x2dof_dense_accumulator_f64", A, A);
+  }
+  {
+    auto A = gen_uniform<double>(60000, 60000, 32, 4);
+    spgemm_case("uniform32_60000_f64", A, A);
+  }
+  {
+    auto A = gen_uniform<float>(40000, 40000, 32, 5);
+    spgemm_case("uniform32_40000_f32", A, A);
+  }
+  {
+    // duplicate columns inside rows of A and B (legal input: products just accumulate)
+    Rng r(9);
+    std::vector<int> lens(5000);
+    for (auto& l : lens) l = r.below(20);
+    auto A = gen_rows<double>(lens, 300, false, false, 11);
+    auto B = gen_rows<double>(std::vector<int>(300, 9), 700, false, false, 12);
+    spgemm_case("duplicate_entries_5000x300x700_f64", A, B);
+  }
+  {
+    // medium rows: nnz(C_i) in the 64..4096 bins with products beyond the parking capacity
+    Rng r(21);
+    std::vector<int> lens(3000);
+    for (auto& l : lens) l = 20 + r.below(100);
+    auto A = gen_rows<double>(lens, 3000, true, true, 21);
+    spgemm_case("medium_rows_3000_f64", A, A);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// suite: spgemm_c4 -- BASELINE.json config 4 timing of the numeric variants (+ sampled-row parity)
+// ------------------------------------------------------------------------------------------------
+static void suite_spgemm_c4() {
+  const int n = g_big ? 2000000 : 500000, deg = 32;
+  double t0 = now_s();
+  auto A = gen_uniform<double>(n, n, deg, 4);
+  record("generate", true, "n=%d deg=%d in %.1f s", n, deg, now_s() - t0);
+  Dev<int> rp(A.rp), ci(A.ci), rpC((size_t)n + 1);
+  Dev<double> v(A.v);
+  b200sp_spgemm_plan* plan = nullptr;
+  SP(b200sp_spgemm_plan_create(&plan));
+  int64_t c_nnz = 0;
+  int c_max = 0;
+  t0 = now_s();
+  SP(b200sp_spgemm_symbolic_i32(plan, nullptr, n, n, n, rp.p, ci.p, rp.p, ci.p, rpC.p, &c_nnz, &c_max));
+  const double sym_s = now_s() - t0;
+  record("symbolic", c_nnz > 0, "c_nnz=%lld c_max=%d wall %.2f ms (first call, includes allocation)", (long long)c_nnz, c_max, sym_s * 1e3);
+  Dev<int> ciC((size_t)c_nnz);
+  Dev<double> vC((size_t)c_nnz);
+  const double flops = (double)n * deg * deg;
+  const double balg = 12.0 * 2 * A.nnz() + 4.0 * 3 * (n + 1) + 12.0 * (double)c_nnz;
+  std::vector<int> hrpC = rpC.host();
+  Rng r(0);
+  for (int variant = 1; variant <= 3; ++variant) {
+    char ev[8];
+    snprintf(ev, sizeof(ev), "%d", variant);
+    setenv("B200SP_SPGEMM_NUMERIC", ev, 1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      Timer t;
+      t.start();
+      SP(b200sp_spgemm_numeric_f64_i32(plan, nullptr, n, n, n, rp.p, ci.p, v.p, rp.p, ci.p, v.p, rpC.p, ciC.p, vC.p));
+      best = std::min(best, t.stop_ms());
+    }
+    // sampled rows against a host Gustavson product
+    int bad = 0;
+    for (int s = 0; s < 200; ++s) {
+      const int row = r.below(n);
+      std::vector<std::pair<int, double>> acc;
+      for (int a = A.rp[row]; a < A.rp[row + 1]; ++a) {
+        const int j = A.ci[a];
+        for (int b = A.rp[j]; b < A.rp[j + 1]; ++b) acc.emplace_back(A.ci[b], A.v[b] * A.v[a]);
+      }
+      std::stable_sort(acc.begin(), acc.end(), [](auto& x, auto& y) { return x.first < y.first; });
+      std::vector<int> ec;
+      std::vector<double> evv;
+      for (auto& pr : acc) {
+        if (!ec.empty() && ec.back() == pr.first) evv.back() += pr.second;
+        else {
+          ec.push_back(pr.first);
+          evv.push_back(pr.second);
+        }
+      }
+      const int s0 = hrpC[row], s1 = hrpC[row + 1];
+      if ((int)ec.size() != s1 - s0) {
+        ++bad;
+        continue;
+      }
+      auto gc = ciC.host(s0, s1 - s0);
+      auto gv = vC.host(s0, s1 - s0);
+      if (count_diff(gc, ec) != 0 || rel_mismatch(gv, evv, 1e-7) != 0) ++bad;
+    }
+    char nm[64];
+    snprintf(nm, sizeof(nm), "numeric_v%d", variant);
+    record(nm, bad == 0, "%.3f ms best of 3, %.1f GFLOP/s, %.0f GB/s algorithmic, sampled rows bad=%d", best,
+           2.0 * flops / (best * 1e-3) / 1e9, balg / (best * 1e-3) / 1e9, bad);
+  }
+  unsetenv("B200SP_SPGEMM_NUMERIC");
+  b200sp_spgemm_plan_destroy(plan, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// suite: crs -- sort / sort_and_merge / transpose / spadd, every output array bit-identical to the oracle
+// ------------------------------------------------------------------------------------------------
+static int sort_call(int m, const int* rp, int* ci, double* v) { return b200sp_sort_crs_f64_i32(nullptr, m, rp, ci, v); }
+static int sort_call(int m, const int* rp, int* ci, float* v) { return b200sp_sort_crs_f32_i32(nullptr, m, rp, ci, v); }
+static void osort(int m, const int* rp, int* ci, double* v) { okk_sort_crs_stable_f64(m, rp, ci, v); }
+static void osort(int m, const int* rp, int* ci, float* v) { okk_sort_crs_stable_f32(m, rp, ci, v); }
+
+template <typename S>
+static void sort_case(const char* name, Csr<S> A) {
+  Dev<int> rp(A.rp), ci(A.ci), g(A.ci);
+  Dev<S> v(A.v);
+  Timer t;
+  t.start();
+  SP(sort_call(A.m, rp.p, ci.p, v.p));
+  const float ms = t.stop_ms();
+  SP(b200sp_sort_crs_graph_i32(nullptr, A.m, rp.p, g.p));
+  CK(cudaDeviceSynchronize());
+  osort(A.m, A.rp.data(), A.ci.data(), A.v.data());
+  const int64_t d1 = count_diff(ci.host(), A.ci), d2 = count_diff(v.host(), A.v), d3 = count_diff(g.host(), A.ci);
+  // second call: already sorted -> no change
+  SP(sort_call(A.m, rp.p, ci.p, v.p));
+  CK(cudaDeviceSynchronize());
+  const int64_t d4 = count_diff(ci.host(), A.ci) + count_diff(v.host(), A.v);
+  record(name, d1 == 0 && d2 == 0 && d3 == 0 && d4 == 0, "m=%d nnz=%lld: entries diffs=%lld values diffs=%lld graph diffs=%lld resort diffs=%lld, %.3f ms",
+         A.m, (long long)A.nnz(), (long long)d1, (long long)d2, (long long)d3, (long long)d4, ms);
+}
+
+template <typename S>
+static void merge_case(const char* name, Csr<S> A);
+template <>
+void merge_case<double>(const char* name, Csr<double> A) {
+  Dev<int> rp(A.rp), ci(A.ci), rpo((size_t)A.m + 1);
+  Dev<double> v(A.v);
+  int64_t merged = -1;
+  SP(b200sp_sort_and_merge_count_f64_i32(nullptr, A.m, rp.p, ci.p, v.p, rpo.p, &merged));
+  okk_sort_crs_stable_f64(A.m, A.rp.data(), A.ci.data(), A.v.data());
+  std::vector<int> orp((size_t)A.m + 1, 0);
+  const int64_t om = A.m > 0 ? okk_merged_rowmap(A.m, A.rp.data(), A.ci.data(), orp.data()) : 0;
+  std::vector<int> oci(om);
+  std::vector<double> ov(om);
+  if (A.m > 0) okk_merged_entries_f64(A.m, A.rp.data(), A.ci.data(), A.v.data(), orp.data(), oci.data(), ov.data());
+  Dev<int> cio((size_t)std::max<int64_t>(merged, 0));
+  Dev<double> vo((size_t)std::max<int64_t>(merged, 0));
+  SP(b200sp_sort_and_merge_fill_f64_i32(nullptr, A.m, rp.p, ci.p, v.p, rpo.p, cio.p, vo.p));
+  CK(cudaDeviceSynchronize());
+  const bool ok = merged == om && count_diff(rpo.host(), orp) == 0 && count_diff(cio.host(), oci) == 0 && count_diff(vo.host(), ov) == 0 &&
+                  count_diff(ci.host(), A.ci) == 0;
+  record(name, ok, "m=%d nnz=%lld merged=%lld (oracle %lld)", A.m, (long long)A.nnz(), (long long)merged, (long long)om);
+}
+
+static void transpose_case(const char* name, const Csr<double>& A) {
+  Dev<int> rp(A.rp), ci(A.ci), trp((size_t)A.n + 1), tci((size_t)A.nnz());
+  Dev<double> v(A.v), tv((size_t)A.nnz());
+  trp.fill_bytes(0x55);
+  Timer t;
+  t.start();
+  SP(b200sp_transpose_f64_i32(nullptr, A.m, A.n, rp.p, ci.p, v.p, trp.p, tci.p, tv.p));
+  const float ms = t.stop_ms();
+  CK(cudaDeviceSynchronize());
+  std::vector<int> otrp((size_t)A.n + 1), otci(A.nnz());
+  std::vector<double> otv(A.nnz());
+  okk_transpose_f64(A.m, A.n, A.rp.data(), A.ci.data(), A.v.data(), otrp.data(), otci.data(), otv.data());
+  const int64_t d1 = count_diff(trp.host(), otrp), d2 = count_diff(tci.host(), otci), d3 = count_diff(tv.host(), otv);
+  record(name, d1 == 0 && d2 == 0 && d3 == 0, "%dx%d nnz=%lld: row map diffs=%lld entries diffs=%lld values diffs=%lld, %.3f ms", A.m, A.n,
+         (long long)A.nnz(), (long long)d1, (long long)d2, (long long)d3, ms);
+}
+
+// randomMatrix of Test_Sparse_spadd.hpp:41-94
+template <typename S>
+static Csr<S> spadd_matrix(int m, int n, int lo, int hi, bool sorted, uint64_t seed) {
+  Rng r(seed);
+  std::vector<int> lens(m);
+  int maxlen = 0;
+  for (auto& l : lens) {
+    l = lo + (hi > lo ? r.below(hi - lo + 1) : 0);
+    maxlen = std::max(maxlen, l);
+  }
+  Csr<S> A;
+  A.m = m;
+  A.n = n;
+  A.rp.assign(m + 1, 0);
+  for (int i = 0; i < m; ++i) A.rp[i + 1] = A.rp[i] + lens[i];
+  A.ci.resize(A.rp[m]);
+  std::vector<int> idx(std::max(n, maxlen));
+  for (int i = 0; i < m; ++i) {
+    for (size_t j = 0; j < idx.size(); ++j) idx[j] = (int)(j % (size_t)std::max(n, 1));
+    for (size_t j = idx.size(); j > 1; --j) std::swap(idx[j - 1], idx[r.below((int)j)]);
+    if (sorted) std::sort(idx.begin(), idx.begin() + lens[i]);
+    std::copy(idx.begin(), idx.begin() + lens[i], A.ci.begin() + A.rp[i]);
+  }
+  A.v.resize(A.ci.size());
+  fill_vals(A.v, 0.0, 1.0, seed + 5);
+  return A;
+}
+
+static int spadd_num(b200sp_spadd_plan* p, int m, int n, const int* ra, const int* ca, const double* va, double al, const int* rb,
+                     const int* cb, const double* vb, double be, const int* rc, int* cc, double* vc) {
+  return b200sp_spadd_numeric_f64_i32(p, nullptr, m, n, ra, ca, va, al, rb, cb, vb, be, rc, cc, vc);
+}
+static int spadd_num(b200sp_spadd_plan* p, int m, int n, const int* ra, const int* ca, const float* va, float al, const int* rb,
+                     const int* cb, const float* vb, float be, const int* rc, int* cc, float* vc) {
+  return b200sp_spadd_numeric_f32_i32(p, nullptr, m, n, ra, ca, va, al, rb, cb, vb, be, rc, cc, vc);
+}
+static void ospadd_sorted(int m, const Csr<double>& A, double al, const Csr<double>& B, double be, const std::vector<int>& rc,
+                          std::vector<int>& cc, std::vector<double>& vc) {
+  okk_spadd_sorted_numeric_f64(m, A.rp.data(), A.ci.data(), A.v.data(), al, B.rp.data(), B.ci.data(), B.v.data(), be, rc.data(), cc.data(), vc.data());
+}
+static void ospadd_sorted(int m, const Csr<float>& A, float al, const Csr<float>& B, float be, const std::vector<int>& rc,
+                          std::vector<int>& cc, std::vector<float>& vc) {
+  okk_spadd_sorted_numeric_f32(m, A.rp.data(), A.ci.data(), A.v.data(), al, B.rp.data(), B.ci.data(), B.v.data(), be, rc.data(), cc.data(), vc.data());
+}
+static void ospadd_unsorted(int m, const Csr<double>& A, double al, const Csr<double>& B, double be, const std::vector<int>& rc,
+                            std::vector<int>& cc, std::vector<double>& vc, const std::vector<int>& ap, const std::vector<int>& bp) {
+  okk_spadd_unsorted_numeric_f64(m, A.rp.data(), A.ci.data(), A.v.data(), al, B.rp.data(), B.ci.data(), B.v.data(), be, rc.data(), cc.data(),
+                                 vc.data(), ap.data(), bp.data());
+}
+static void ospadd_unsorted(int m, const Csr<float>& A, float al, const Csr<float>& B, float be, const std::vector<int>& rc,
+                            std::vector<int>& cc, std::vector<float>& vc, const std::vector<int>& ap, const std::vector<int>& bp) {
+  okk_spadd_unsorted_numeric_f32(m, A.rp.data(), A.ci.data(), A.v.data(), al, B.rp.data(), B.ci.data(), B.v.data(), be, rc.data(), cc.data(),
+                                 vc.data(), ap.data(), bp.data());
+}
+
+template <typename S>
+static void spadd_case(const char* name, int m, int n, int lo, int hi, bool sorted) {
+  auto A = spadd_matrix<S>(m, n, lo, hi, sorted, ((uint64_t)m << 1) ^ (uint64_t)n);
+  auto B = spadd_matrix<S>(m, n, lo, hi, sorted, (((uint64_t)m << 1) ^ (uint64_t)n) + 1);
+  std::vector<int> orc((size_t)m + 1, 0), ap(std::max<size_t>(A.ci.size(), 1)), bp(std::max<size_t>(B.ci.size(), 1));
+  const int64_t onnz = sorted ? okk_spadd_sorted_symbolic(m, A.rp.data(), A.ci.data(), B.rp.data(), B.ci.data(), orc.data())
+                              : okk_spadd_unsorted_symbolic(m, A.rp.data(), A.ci.data(), B.rp.data(), B.ci.data(), orc.data(), ap.data(), bp.data());
+  std::vector<int> occ(onnz);
+  std::vector<S> ovc(onnz);
+  const S al = (S)0.3, be = (S)-1.7;  // not powers of two: the products round
+  if (sorted) ospadd_sorted(m, A, al, B, be, orc, occ, ovc);
+  else ospadd_unsorted(m, A, al, B, be, orc, occ, ovc, ap, bp);
+  Dev<int> ra(A.rp), ca(A.ci), rb(B.rp), cb(B.ci), rc((size_t)m + 1);
+  Dev<S> va(A.v), vb(B.v);
+  rc.fill_bytes(0x05);
+  b200sp_spadd_plan* plan = nullptr;
+  SP(b200sp_spadd_plan_create(&plan, sorted ? 1 : 0, hi <= n ? 1 : 0));
+  int64_t c_nnz = -1;
+  Timer t;
+  t.start();
+  SP(b200sp_spadd_symbolic_i32(plan, nullptr, m, n, ra.p, ca.p, rb.p, cb.p, rc.p, &c_nnz));
+  const float ms_sym = t.stop_ms();
+  bool ok = c_nnz == onnz && count_diff(rc.host(), orc) == 0;
+  int64_t d1 = -1, d2 = -1;
+  float ms_num = 0;
+  if (ok) {
+    Dev<int> cc((size_t)c_nnz);
+    Dev<S> vc((size_t)c_nnz);
+    cc.fill_bytes(0x05);
+    vc.fill_bytes(0x05);
+    t.start();
+    SP(spadd_num(plan, m, n, ra.p, ca.p, va.p, al, rb.p, cb.p, vb.p, be, rc.p, cc.p, vc.p));
+    ms_num = t.stop_ms();
+    CK(cudaDeviceSynchronize());
+    d1 = count_diff(cc.host(), occ);
+    d2 = count_diff(vc.host(), ovc);
+    ok = d1 == 0 && d2 == 0;
+  }
+  b200sp_spadd_plan_destroy(plan, nullptr);
+  record(name, ok, "%dx%d rows %d..%d %s: c_nnz=%lld (oracle %lld) entries diffs=%lld values diffs=%lld; symbolic %.3f ms numeric %.3f ms", m, n, lo,
+         hi, sorted ? "sorted" : "unsorted", (long long)c_nnz, (long long)onnz, (long long)d1, (long long)d2, ms_sym, ms_num);
+}
+
+static void suite_crs() {
+  sort_case("sort/kk_10x10_f64", gen_kk<double>(10, 10, 20, 2, 5, 1));
+  sort_case("sort/kk_1000x1000_f64", gen_kk<double>(1000, 1000, 30000, 2, 500, 1));
+  sort_case("sort/kk_20000x20000_f32", gen_kk<float>(20000, 20000, 600000, 2, 10000, 1));
+  {
+    Rng r(11);
+    std::vector<int> lens(3000);
+    for (auto& l : lens) l = r.below(40);
+    const int special[] = {9000, 5000, 4097, 4096, 300, 257, 256, 255, 33, 32, 31, 2, 1, 0};
+    for (size_t i = 0; i < sizeof(special) / sizeof(int); ++i) lens[i] = special[i];
+    sort_case("sort/long_rows_with_ties_f64", gen_rows<double>(lens, 500, false, false, 11));
+    merge_case<double>("merge/long_rows_60_columns", gen_rows<double>(lens, 60, false, false, 12));
+  }
+  {
+    // golden case 0 of Test_Sparse_SortCrs.hpp:203-243
+    Csr<double> A;
+    A.m = 5;
+    A.n = 7;
+    A.rp = {0, 4, 4, 5, 7, 10};
+    A.ci = {4, 3, 5, 3, 6, 2, 2, 0, 1, 2};
+    A.v = {1.5, 4, 1, -3, 2, -1, -2, 0, 3.5, -2.25};
+    merge_case<double>("merge/golden_case0", A);
+    Csr<double> E;
+    E.m = 5;
+    E.n = 7;
+    E.rp = {0, 0, 0, 0, 0, 0};
+    merge_case<double>("merge/golden_case2_empty", E);
+  }
+  {
+    Rng r(5);
+    std::vector<int> lens(3000);
+    for (auto& l : lens) l = r.below(60);
+    transpose_case("transpose/3000x1000_with_duplicates", gen_rows<double>(lens, 1000, false, false, 5));
+    transpose_case("transpose/1x5", gen_rows<double>(std::vector<int>{3}, 5, true, false, 6));
+    transpose_case("transpose/lap27", gen_lap27<double>(10, 2));
+  }
+  for (int sorted = 1; sorted >= 0; --sorted) {
+    const char* tag = sorted ? "sorted" : "unsorted";
+    char nm[96];
+    snprintf(nm, sizeof(nm), "spadd/%s_10x10_empty_f64", tag);
+    spadd_case<double>(nm, 10, 10, 0, 0, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_10x10_0..2_f64", tag);
+    spadd_case<double>(nm, 10, 10, 0, 2, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_100x100_50..100_f64", tag);
+    spadd_case<double>(nm, 100, 100, 50, 100, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_50x50_75..100_duplicates_f64", tag);
+    spadd_case<double>(nm, 50, 50, 75, 100, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_50x50_75..100_duplicates_f32", tag);
+    spadd_case<float>(nm, 50, 50, 75, 100, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_20000x3000_0..60_f64", tag);
+    spadd_case<double>(nm, 20000, 3000, 0, 60, sorted);
+    snprintf(nm, sizeof(nm), "spadd/%s_20000x3000_0..60_f32", tag);
+    spadd_case<float>(nm, 20000, 3000, 0, 60, sorted);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// suite: crs_big -- timings on a bench-sized matrix (27-point stencil x 2 dof, rows shuffled for the sort)
+// ------------------------------------------------------------------------------------------------
+static void suite_crs_big() {
+  const int g = g_big ? 100 : 50;
+  auto A = gen_lap27<double>(g, 2);
+  Csr<double> U = A;  // rows reversed: every row needs sorting
+  for (int i = 0; i < U.m; ++i) {
+    std::reverse(U.ci.begin() + U.rp[i], U.ci.begin() + U.rp[i + 1]);
+    std::reverse(U.v.begin() + U.rp[i], U.v.begin() + U.rp[i + 1]);
+  }
+  const double gb = 12.0 * A.nnz() / 1e9;
+  {
+    Dev<int> rp(U.rp), ci(U.ci);
+    Dev<double> v(U.v);
+    Timer t;
+    t.start();
+    SP(b200sp_sort_crs_f64_i32(nullptr, U.m, rp.p, ci.p, v.p));
+    const float ms = t.stop_ms();
+    const bool ok = count_diff(ci.host(), A.ci) == 0 && count_diff(v.host(), A.v) == 0;
+    record("sort_reversed_rows", ok, "m=%d nnz=%lld %.3f ms (%.0f GB/s read+write of 12 B/entry)", U.m, (long long)U.nnz(), ms, 2 * gb / (ms * 1e-3));
+    t.start();
+    SP(b200sp_sort_crs_f64_i32(nullptr, U.m, rp.p, ci.p, v.p));
+    record("sort_already_sorted", true, "%.3f ms (classification pass only)", t.stop_ms());
+  }
+  {
+    Dev<int> rp(A.rp), ci(A.ci), trp((size_t)A.n + 1), tci((size_t)A.nnz());
+    Dev<double> v(A.v), tv((size_t)A.nnz());
+    Timer t;
+    t.start();
+    SP(b200sp_transpose_f64_i32(nullptr, A.m, A.n, rp.p, ci.p, v.p, trp.p, tci.p, tv.p));
+    const float ms = t.stop_ms();
+    // the stencil matrix is structurally symmetric: the transpose has the same graph
+    const bool ok = count_diff(trp.host(), A.rp) == 0 && count_diff(tci.host(), A.ci) == 0;
+    record("transpose", ok, "%.3f ms (%.0f GB/s of 24 B/entry)", ms, 2 * gb / (ms * 1e-3));
+  }
+  for (int sorted = 1; sorted >= 0; --sorted) {
+    Dev<int> rp(A.rp), ci(A.ci), rc((size_t)A.m + 1);
+    Dev<double> v(A.v);
+    b200sp_spadd_plan* plan = nullptr;
+    SP(b200sp_spadd_plan_create(&plan, sorted, 1));
+    int64_t c_nnz = 0;
+    Timer t;
+    t.start();
+    SP(b200sp_spadd_symbolic_i32(plan, nullptr, A.m, A.n, rp.p, ci.p, rp.p, ci.p, rc.p, &c_nnz));
+    const float ms_sym = t.stop_ms();
+    Dev<int> cc((size_t)c_nnz);
+    Dev<double> vc((size_t)c_nnz);
+    t.start();
+    SP(b200sp_spadd_numeric_f64_i32(plan, nullptr, A.m, A.n, rp.p, ci.p, v.p, 1.0, rp.p, ci.p, v.p, 1.0, rc.p, cc.p, vc.p));
+    const float ms_num = t.stop_ms();
+    auto hv = vc.host();
+    bool ok = c_nnz == A.nnz() && count_diff(cc.host(), A.ci) == 0;
+    for (size_t i = 0; ok && i < hv.size(); ++i) ok = hv[i] == 2.0 * A.v[i];
+    b200sp_spadd_plan_destroy(plan, nullptr);
+    record(sorted ? "spadd_sorted_A_plus_A" : "spadd_unsorted_A_plus_A", ok, "symbolic %.3f ms, numeric %.3f ms (%.0f GB/s of 36 B/entry)", ms_sym,
+           ms_num, 3 * gb / (ms_num * 1e-3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// suite: spmm -- kernel variants of the rank-2 product (B200SP_SPMM_KERNEL) against the oracle + timing
+// ------------------------------------------------------------------------------------------------
+static void suite_spmm() {
+  const int scale = g_big ? 21 : 18, k = 16;
+  int64_t nnz = 0;
+  void* h = b200gen_rmat_build(scale, 16, 0.57, 0.19, 0.19, 23, &nnz);
+  const int n = 1 << scale;
+  std::vector<int> rp((size_t)n + 1), ci((size_t)nnz);
+  b200gen_rmat_emit(h, rp.data(), ci.data());
+  std::vector<float> v((size_t)nnz), X((size_t)n * k), Y0((size_t)n * k);
+  b200gen_fill_f32(nnz, v.data(), 0.f, 1.f, 3);
+  b200gen_fill_f32((int64_t)X.size(), X.data(), -1.f, 1.f, 4);
+  b200gen_fill_f32((int64_t)Y0.size(), Y0.data(), -1.f, 1.f, 5);
+  std::vector<float> Yref = Y0;
+  okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), v.data(), X.data(), k, 1, Yref.data(), k, 1, 1.5f, 0.5f, okk_num_threads());
+  // row-scaled tolerance: |alpha| sum |a||x| + |beta||y0|
+  std::vector<float> va(v), Xa(X), Ys(Y0);
+  for (auto& x : va) x = std::fabs(x);
+  for (auto& x : Xa) x = std::fabs(x);
+  for (auto& x : Ys) x = std::fabs(x);
+  okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), va.data(), Xa.data(), k, 1, Ys.data(), k, 1, 1.5f, 0.5f, okk_num_threads());
+  Dev<int> drp(rp), dci(ci);
+  Dev<float> dv(v), dX(X), dY((size_t)n * k);
+  const double balg = 8.0 * nnz + 4.0 * (n + 1) + 4.0 * (double)n * k * 3;
+  const char* kernels[] = {"row", "split", "tile"};
+  for (const char* kn : kernels) {
+    setenv("B200SP_SPMM_KERNEL", kn, 1);
+    b200sp_spmv_plan* plan = nullptr;
+    SP(b200sp_spmv_plan_create(&plan, 0));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaMemcpy(dY.p, Y0.data(), Y0.size() * sizeof(float), cudaMemcpyHostToDevice));
+      Timer t;
+      t.start();
+      SP(b200sp_spmm_f32_i32(plan, nullptr, 'N', n, n, nnz, k, 1.5f, drp.p, dci.p, dv.p, dX.p, k, 1, 0.5f, dY.p, k, 1));
+      const float ms = t.stop_ms();
+      if (rep > 0) best = std::min(best, ms);
+    }
+    auto got = dY.host();
+    double worst = 0;
+    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, (double)std::fabs(got[i] - Yref[i]) / std::max((double)Ys[i], 1e-30));
+    char nm[64];
+    snprintf(nm, sizeof(nm), "rmat%d_k16_f32/%s", scale, kn);
+    record(nm, worst <= 1e-4, "kernel=%s %.3f ms, %.0f GFLOP/s, %.0f GB/s algorithmic, max scaled err %.2e", b200sp_spmv_last_kernel(plan), best,
+           2.0 * nnz * k / (best * 1e-3) / 1e9, balg / (best * 1e-3) / 1e9, worst);
+    b200sp_spmv_plan_destroy(plan, nullptr);
+  }
+  unsetenv("B200SP_SPMM_KERNEL");
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Suite {
+  const char* name;
+  std::function<void()> fn;
+  int timeout_s;
+};
+
+int main(int argc, char** argv) {
+  std::vector<Suite> all = {{"spgemm", suite_spgemm, 120}, {"crs", suite_crs, 120}, {"spgemm_c4", suite_spgemm_c4, 150},
+                            {"crs_big", suite_crs_big, 120}, {"spmm", suite_spmm, 150}};
+  std::vector<std::string> pick;
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
+    else if (!strcmp(argv[i], "--suite") && i + 1 < argc) pick.push_back(argv[++i]);
+    else if (!strcmp(argv[i], "--big")) g_big = true;
+    else if (!strcmp(argv[i], "--dry")) g_dry = true;
+    else {
+      fprintf(stderr, "usage: gpu_check [--out FILE] [--suite NAME]... [--big] [--dry]\n");
+      return 64;
+    }
+  }
+  int failed = 0;
+  for (auto& s : all) {
+    if (!pick.empty() && std::find(pick.begin(), pick.end(), s.name) == pick.end()) continue;
+    g_suite = s.name;
+    const double t0 = now_s();
+    fflush(nullptr);
+    const pid_t pid = fork();  // the parent never touches CUDA
+    if (pid == 0) {
+      alarm((unsigned)s.timeout_s);
+      int dev_count = 0;
+      if (!g_dry && (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0 || b200sp_device_ok() != 1)) {
+        record("device", false, "no compute-capability 10.x CUDA device");
+        _exit(2);
+      }
+      s.fn();
+      fflush(nullptr);
+      _exit(g_fail ? 1 : 0);
+    }
+    int status = 0;
+    waitpid(pid, &status, 0);
+    const bool ok = WIFEXITED(status) && WEXITSTATUS(status) == 0;
+    g_suite = "summary";
+    record(s.name, ok, "exit=%d signal=%d %.1f s", WIFEXITED(status) ? WEXITSTATUS(status) : -1, WIFSIGNALED(status) ? WTERMSIG(status) : 0,
+           now_s() - t0);
+    g_fail = 0;
+    if (!ok) ++failed;
+  }
+  return failed;
+}
