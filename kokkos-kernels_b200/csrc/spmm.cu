@@ -16,6 +16,7 @@
 // Column-major (LayoutLeft) X with k >= 4 goes through a transposed copy so the
 // gather touches one segment per nonzero instead of k sectors.
 #include "common.cuh"
+#include "tile_ring.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
@@ -266,6 +267,219 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// Vectorised variant: every lane owns VW adjacent columns (one 16-byte load of the X row per nonzero),
+// a group of KT lanes covers KT*VW columns, so a warp advances 32/KT chunks at once.  Needs k, ldx,
+// ldy multiples of VW and 16-byte aligned X / Y.
+template <typename S> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int W = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int W = 2; };
+__device__ __forceinline__ void vec_unpack(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void vec_unpack(const double2& v, double* a) { a[0] = v.x; a[1] = v.y; }
+__device__ __forceinline__ float4 vec_pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 vec_pack(const double* a) { return make_double2(a[0], a[1]); }
+
+// ---------------------------------------------------------------------------
+// Tile kernel (B200SP_SPMM_KERNEL=tile|tilev; row-major X and Y): the matrix is streamed ONCE, whatever k,
+// through the same TMA-fed shared-memory ring as the rank-1 kernel (tile_ring.cuh); a group of KTL lanes
+// owns one row at a time (rows dealt round-robin to the groups like spmv_tile_kernel does), every lane
+// accumulates VW adjacent columns in registers: per nonzero a broadcast read of (col, val) from shared
+// memory, one gather of the X row segment (VW = 1: 4/8-byte, VW = 4/2: 16-byte loads) and VW FMAs -- no
+// shuffles, no atomics, no row bookkeeping in the inner loop, deterministic.  Rows longer than the tile
+// row limit are cut into segments (plan_analyse_mm, spmv.cu) and done by spmm_seg_kernel.
+// ---------------------------------------------------------------------------
+template <typename S, int VW>
+struct Acc {
+  S a[VW];
+};
+
+template <typename S, int VW>
+__device__ __forceinline__ Acc<S, VW> load_x(const S* __restrict__ p) {
+  static_assert(VW == 1 || VW == VecOf<S>::W, "VW is 1 or the 16-byte vector width");
+  Acc<S, VW> r;
+  if constexpr (VW == 1) {
+    r.a[0] = ldg(p);
+  } else {
+    using V = typename VecOf<S>::type;
+    const V v = __ldg(reinterpret_cast<const V*>(p));
+    vec_unpack(v, r.a);
+  }
+  return r;
+}
+
+template <typename S, int VW, int KTL, int NW, int STAGES, int CAP, int UNR>
+__global__ void __launch_bounds__((NW + 1) * 32)
+    spmm_tile_kernel(int m, int k, int64_t nnz, int n_tiles, int LMAX, const int4* __restrict__ tiles,
+                     const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const S* __restrict__ vals,
+                     const S* __restrict__ X, int64_t ldx, S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  using Ring = TileRing<S, CAP, STAGES>;
+  constexpr int RCAP = Ring::RCAP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring& sm = *reinterpret_cast<Ring*>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  tile_ring_init(sm, NW);
+  if (warp == NW) {
+    tile_ring_produce<S, CAP, STAGES>(sm, lane, m, nnz, n_tiles, tiles, row_ptr, col_idx, vals);
+    return;
+  }
+  constexpr int RPW = 32 / KTL;  // rows per warp
+  const int sub = lane / KTL, t = lane % KTL;
+  const int nstrips = (k + KTL * VW - 1) / (KTL * VW);
+  for (int it = 0;; ++it) {
+    const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+    if (tile >= n_tiles) break;
+    const int stage = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&sm.full[stage], ph);
+    const int4 d = sm.desc[stage];
+    const int r0 = d.x, r1 = d.y;
+    const int s_al = d.z & ~3;
+    const int r0_al = r0 & ~3;
+    const S* sv = sm.vals[stage];
+    const int* sc = sm.cols[stage];
+    const int* sr = sm.rows[stage];
+    const int g_first = r0 / RPW;
+    int g = g_first + ((warp - g_first % NW) + NW) % NW;
+    for (; g * RPW < r1; g += NW) {
+      const int r = g * RPW + sub;
+      const bool valid = (r >= r0) && (r < r1);
+      int rs = 0, re = 0;
+      if (valid) {
+        const int o = r - r0_al;
+        if (o + 1 < RCAP) {
+          rs = sr[o];
+          re = sr[o + 1];
+        } else {
+          rs = row_ptr[r];
+          re = row_ptr[r + 1];
+        }
+      }
+      const bool is_long = (re - rs) > LMAX;
+      if (is_long) re = rs;
+      const int jbeg = rs - s_al, jend = re - s_al;
+      for (int strip = 0; strip < nstrips; ++strip) {
+        const int j = (strip * KTL + t) * VW;
+        const bool jok = j < k;  // k % VW == 0: a lane's VW columns are all in or all out
+        Acc<S, VW> acc;
+#pragma unroll
+        for (int q = 0; q < VW; ++q) acc.a[q] = S(0);
+        for (int e0 = jbeg; e0 < jend; e0 += UNR) {
+          int c[UNR];
+          S av[UNR];
+          Acc<S, VW> xv[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const bool ok = e0 + u < jend;
+            c[u] = ok ? sc[e0 + u] : 0;
+            av[u] = ok ? sv[e0 + u] : S(0);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (jok && e0 + u < jend) {
+              xv[u] = load_x<S, VW>(X + (int64_t)c[u] * ldx + j);
+            } else {
+#pragma unroll
+              for (int q = 0; q < VW; ++q) xv[u].a[q] = S(0);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int q = 0; q < VW; ++q) acc.a[q] += av[u] * xv[u].a[q];
+        }
+        if (valid && !is_long && jok) {
+          S* yp = Y + (int64_t)r * ldy + j;
+          S o[VW];
+          if (beta == S(0)) {
+#pragma unroll
+            for (int q = 0; q < VW; ++q) o[q] = alpha * acc.a[q];
+          } else {
+            const Acc<S, VW> old = load_x<S, VW>(yp);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) o[q] = beta * old.a[q] + alpha * acc.a[q];
+          }
+          if constexpr (VW == 1) {
+            yp[0] = o[0];
+          } else {
+            using V = typename VecOf<S>::type;
+            *reinterpret_cast<V*>(yp) = vec_pack(o);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+  }
+}
+
+// rows of several segments: y_row = beta*y_row before the pieces are added atomically
+template <typename S>
+__global__ void __launch_bounds__(256)
+    spmm_seg_prescale_kernel(const int4* __restrict__ segs, const int* __restrict__ n_seg_ptr, int k, S beta,
+                             S* __restrict__ Y, int64_t ldy) {
+  const int n_seg = *n_seg_ptr;
+  const int64_t total = (int64_t)n_seg * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 d = segs[i / k];
+    if ((d.w & 3) == 3) {
+      S* yp = Y + (int64_t)d.x * ldy + (i % k);
+      *yp = (beta == S(0)) ? S(0) : beta * *yp;
+    }
+  }
+}
+
+// one CTA (256 threads = 256/KT groups of KT lanes) per segment of a long row
+template <typename S, int KT>
+__global__ void __launch_bounds__(256)
+    spmm_seg_kernel(const int4* __restrict__ segs, const int* __restrict__ n_seg_ptr, int k,
+                    const int* __restrict__ col_idx, const S* __restrict__ vals, const S* __restrict__ X, int64_t ldx,
+                    S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  constexpr int G = 256 / KT;
+  constexpr int UNR = 4;
+  __shared__ S red[G][KT];
+  const int grp = threadIdx.x / KT, t = threadIdx.x % KT;
+  const int n_seg = *n_seg_ptr;
+  const int nstrips = (k + KT - 1) / KT;
+  for (int q = blockIdx.x; q < n_seg; q += gridDim.x) {
+    const int4 d = segs[q];
+    const int row = d.x, e0 = d.y, e1 = d.z;
+    const bool multi = (d.w & 1) != 0;
+    for (int strip = 0; strip < nstrips; ++strip) {
+      const int j = strip * KT + t;
+      const bool jok = j < k;
+      S acc = S(0);
+      for (int e = e0 + grp; e < e1; e += G * UNR) {
+        int c[UNR];
+        S av[UNR], xv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int ee = e + u * G;
+          const bool ok = ee < e1;
+          c[u] = ok ? ld_stream(col_idx + ee) : 0;
+          av[u] = ok ? ld_stream(vals + ee) : S(0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) xv[u] = (jok && e + u * G < e1) ? ldg(X + (int64_t)c[u] * ldx + j) : S(0);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) acc += av[u] * xv[u];
+      }
+      red[grp][t] = acc;
+      __syncthreads();
+      if (grp == 0 && jok) {
+        S sum = S(0);
+#pragma unroll 4
+        for (int gg = 0; gg < G; ++gg) sum += red[gg][t];
+        S* yp = Y + (int64_t)row * ldy + j;
+        const S a = alpha * sum;
+        if (multi) atomicAdd(yp, a);
+        else *yp = (beta == S(0)) ? a : beta * *yp + a;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 template <typename S>
 static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, const int* col_idx, const S* vals,
                            const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
@@ -292,17 +506,6 @@ static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, co
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
-
-// Vectorised variant: every lane owns VW adjacent columns (one 16-byte load of the X row per nonzero),
-// a group of KT lanes covers KT*VW columns, so a warp advances 32/KT chunks at once.  Needs k, ldx,
-// ldy multiples of VW and 16-byte aligned X / Y.
-template <typename S> struct VecOf;
-template <> struct VecOf<float> { using type = float4; static constexpr int W = 4; };
-template <> struct VecOf<double> { using type = double2; static constexpr int W = 2; };
-__device__ __forceinline__ void vec_unpack(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-__device__ __forceinline__ void vec_unpack(const double2& v, double* a) { a[0] = v.x; a[1] = v.y; }
-__device__ __forceinline__ float4 vec_pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
-__device__ __forceinline__ double2 vec_pack(const double* a) { return make_double2(a[0], a[1]); }
 
 template <typename S, int KT>
 __global__ void __launch_bounds__(256)
@@ -483,6 +686,81 @@ static int launch_split(b200sp_spmv_plan* p, cudaStream_t st, int m, int k, int6
   return B200SP_OK;
 }
 
+int plan_analyse_mm(b200sp_spmv_plan* p, cudaStream_t st, int cap, int lmax, int seg, int m, int64_t nnz, const int* row_ptr,
+                    MMTileView* out);
+
+template <typename S, int VW, int KTL>
+static int launch_mm_tile_k(cudaStream_t st, const MMTileView& tv, int m, int k, int64_t nnz, const int* row_ptr,
+                            const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  constexpr int NW = 16, STAGES = 4, CAP = 2048;
+  constexpr int UNR = (VW == 1) ? 8 : 4;
+  using Ring = TileRing<S, CAP, STAGES>;
+  auto kern = spmm_tile_kernel<S, VW, KTL, NW, STAGES, CAP, UNR>;
+  const size_t smem = sizeof(Ring) + 128;
+  B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NW + 1) * 32, smem));
+  if (occ < 1) occ = 1;
+  int grid = std::min(tv.n_tiles, sm_count() * occ);
+  if (grid < 1) grid = 1;
+  kern<<<grid, (NW + 1) * 32, smem, st>>>(m, k, nnz, tv.n_tiles, tv.LMAX, tv.tiles, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S>
+static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
+                          const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  constexpr int CAP = 2048, LMAX = 256, SEG = 2048;
+  MMTileView tv;
+  int rc = plan_analyse_mm(p, st, CAP, LMAX, SEG, m, nnz, row_ptr, &tv);
+  if (rc) return rc;
+  constexpr int W = VecOf<S>::W;
+  const int lanes_needed = vec ? (k + W - 1) / W : k;
+  int KTL = 1;
+  while (KTL < lanes_needed && KTL < 32) KTL <<= 1;
+#define B200SP_MMT(V, L)                                                                                                    \
+  case L:                                                                                                                   \
+    rc = launch_mm_tile_k<S, V, L>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);                 \
+    break;
+  if (vec) {
+    switch (KTL) {
+      B200SP_MMT(W, 1) B200SP_MMT(W, 2) B200SP_MMT(W, 4) B200SP_MMT(W, 8) B200SP_MMT(W, 16) B200SP_MMT(W, 32)
+    }
+  } else {
+    switch (KTL) {
+      B200SP_MMT(1, 1) B200SP_MMT(1, 2) B200SP_MMT(1, 4) B200SP_MMT(1, 8) B200SP_MMT(1, 16) B200SP_MMT(1, 32)
+    }
+  }
+#undef B200SP_MMT
+  if (rc) return rc;
+  // long rows: segments of <= SEG entries, one CTA each
+  const int grid = sm_count() * 4;
+  spmm_seg_prescale_kernel<S><<<grid, 256, 0, st>>>(tv.segs, tv.n_seg, k, beta, Y, ldy);
+  B200SP_LAUNCH_CHECK();
+  int KT = 1;
+  while (KT < k && KT < 32) KT <<= 1;
+#define B200SP_SEG(K)                                                                                              \
+  case K:                                                                                                          \
+    spmm_seg_kernel<S, K><<<grid, 256, 0, st>>>(tv.segs, tv.n_seg, k, col_idx, vals, X, ldx, Y, ldy, alpha, beta); \
+    break;
+  switch (KT) {
+    B200SP_SEG(1) B200SP_SEG(2) B200SP_SEG(4) B200SP_SEG(8) B200SP_SEG(16) B200SP_SEG(32)
+  }
+#undef B200SP_SEG
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+// which rank-2 kernel: 0 = row per group, 1 = nnz-split (default), 2 = tile, 3 = tile with 16-byte X loads
+static int mm_kernel_choice(b200sp_spmv_plan* p) {
+  if (!p) return 0;  // the others need a plan (chunk table / tile analysis)
+  const char* e = getenv("B200SP_SPMM_KERNEL");
+  if (e && e[0] == 'r') return 0;
+  if (e && e[0] == 't') return (e[1] == 'i' && e[2] == 'l' && e[3] == 'e' && e[4] == 'v') ? 3 : 2;
+  return 1;
+}
+
 static bool use_split_kernel(b200sp_spmv_plan* p) {
   // needs a plan (chunk table); B200SP_SPMM_KERNEL=row|split overrides for experiments
   if (!p) return false;
@@ -529,7 +807,14 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
     return B200SP_OK;
   }
   const bool split = use_split_kernel(p);
+  const int choice = mm_kernel_choice(p);
   if (xrm && yrm) {
+    if (choice >= 2 && (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0) {
+      constexpr int W = VecOf<S>::W;
+      const bool vec = choice == 3 && (k % W == 0) && (ldx % W == 0) && (ldy % W == 0) && ((((uintptr_t)X) | ((uintptr_t)Y)) & 15u) == 0;
+      plan_set_last_kernel(p, vec ? "spmm_tile_vec" : "spmm_tile");
+      return launch_mm_tile<S>(p, st, vec, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+    }
     plan_set_last_kernel(p, split ? "spmm_split" : "spmm_rowmajor");
     if (split) return launch_split<S>(p, st, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
     return launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);

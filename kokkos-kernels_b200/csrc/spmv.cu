@@ -18,6 +18,7 @@
 //                       inputs): sub-warp per row straight from global memory.
 //   spmv_transpose_kernel  T/H modes: y pre-scaled, atomicAdd scatter.
 #include "common.cuh"
+#include "tile_ring.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -469,6 +470,17 @@ struct b200sp_spmv_plan {
   const int* chunk_key = nullptr;
   int chunk_m = -1;
   int64_t chunk_nnz = -1;
+  // rank-2 tile kernel (spmm.cu): its own tile analysis (smaller row limit) + segment list of the long rows
+  int4* mm_tiles = nullptr;
+  int mm_n_tiles = 0, mm_T = 0, mm_LMAX = 0, mm_cap = 0;
+  int* mm_long_rows = nullptr;
+  int* mm_n_long = nullptr;
+  int4* mm_segs = nullptr;
+  int* mm_n_seg = nullptr;
+  int mm_seg_cap = 0;
+  const int* mm_key_row_ptr = nullptr;
+  int mm_key_m = -1, mm_key_cap = -1, mm_key_lmax = -1;
+  int64_t mm_key_nnz = -1;
   char last_kernel[96] = "none";
   b200sp::YExtra extra = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
   // self-tuning between the tiled and the row-vector kernel (same bits, different speed by matrix):
@@ -507,6 +519,18 @@ static void plan_release_analysis(b200sp_spmv_plan* p, cudaStream_t st) {
   p->n_tiles = 0;
   p->n_long_known = false;
   p->key_row_ptr = nullptr;
+}
+
+static void plan_release_mm(b200sp_spmv_plan* p, cudaStream_t st) {
+  void* ptrs[] = {p->mm_tiles, p->mm_long_rows, p->mm_n_long, p->mm_segs, p->mm_n_seg};
+  for (void* q : ptrs)
+    if (q) cudaFreeAsync(q, st);
+  p->mm_tiles = nullptr;
+  p->mm_long_rows = nullptr;
+  p->mm_n_long = nullptr;
+  p->mm_segs = nullptr;
+  p->mm_n_seg = nullptr;
+  p->mm_key_row_ptr = nullptr;
 }
 
 template <typename S>
@@ -588,6 +612,66 @@ int plan_chunk_rows(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, co
   *n_chunks = p->n_chunks;
   return B200SP_OK;
 }
+// Segments of the rows the rank-2 tile kernel leaves out (longer than LMAX): {row, first entry, end entry,
+// flags}; flags bit 0 = the row has several segments (its pieces are combined with atomics), bit 1 = first
+// segment of its row.  One thread per long row.
+__global__ void build_segments_kernel(const int* __restrict__ long_rows, const int* __restrict__ n_long,
+                                      const int* __restrict__ row_ptr, int SEG, int4* __restrict__ segs,
+                                      int* __restrict__ n_seg) {
+  const int nl = *n_long;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
+    const int r = long_rows[i];
+    const int s = row_ptr[r], e = row_ptr[r + 1];
+    const int nseg = (e - s + SEG - 1) / SEG;
+    const int base = atomicAdd(n_seg, nseg);
+    for (int q = 0; q < nseg; ++q)
+      segs[base + q] = make_int4(r, s + q * SEG, min(e, s + (q + 1) * SEG), (nseg > 1 ? 1 : 0) | (q == 0 ? 2 : 0));
+  }
+}
+
+// Tile analysis of the rank-2 tile kernel (spmm.cu): same descriptors as the rank-1 kernel's, with its own
+// stage capacity and row limit; cached per matrix in the plan; stream-ordered, no host synchronisation.
+int plan_analyse_mm(b200sp_spmv_plan* p, cudaStream_t st, int cap, int lmax, int seg, int m, int64_t nnz, const int* row_ptr,
+                    MMTileView* out) {
+  if (!(p->mm_tiles && p->mm_key_row_ptr == row_ptr && p->mm_key_m == m && p->mm_key_nnz == nnz && p->mm_key_cap == cap &&
+        p->mm_key_lmax == lmax)) {
+    plan_release_mm(p, st);
+    p->mm_cap = cap;
+    p->mm_LMAX = lmax;
+    p->mm_T = cap - lmax - 8;
+    p->mm_n_tiles = (int)(nnz / p->mm_T) + 1;
+    const int long_cap = (int)(nnz / (lmax + 1)) + 1;  // every long row holds more than lmax entries
+    p->mm_seg_cap = (int)(nnz / seg) + long_cap + 1;
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->mm_tiles, sizeof(int4) * (size_t)p->mm_n_tiles, st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->mm_long_rows, sizeof(int) * (size_t)long_cap, st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->mm_n_long, sizeof(int), st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->mm_segs, sizeof(int4) * (size_t)p->mm_seg_cap, st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->mm_n_seg, sizeof(int), st));
+    B200SP_CUDA_TRY(cudaMemsetAsync(p->mm_n_long, 0, sizeof(int), st));
+    B200SP_CUDA_TRY(cudaMemsetAsync(p->mm_n_seg, 0, sizeof(int), st));
+    build_tiles_kernel<<<(p->mm_n_tiles + 255) / 256, 256, 0, st>>>(m, row_ptr, p->mm_n_tiles, p->mm_T, cap, p->mm_tiles);
+    B200SP_LAUNCH_CHECK();
+    find_long_rows_kernel<<<std::max(1, std::min((m + 255) / 256, sm_count() * 8)), 256, 0, st>>>(m, row_ptr, lmax, p->mm_long_rows,
+                                                                                                  p->mm_n_long);
+    B200SP_LAUNCH_CHECK();
+    build_segments_kernel<<<std::max(1, std::min((long_cap + 255) / 256, sm_count() * 4)), 256, 0, st>>>(
+        p->mm_long_rows, p->mm_n_long, row_ptr, seg, p->mm_segs, p->mm_n_seg);
+    B200SP_LAUNCH_CHECK();
+    p->mm_key_row_ptr = row_ptr;
+    p->mm_key_m = m;
+    p->mm_key_nnz = nnz;
+    p->mm_key_cap = cap;
+    p->mm_key_lmax = lmax;
+  }
+  out->tiles = p->mm_tiles;
+  out->n_tiles = p->mm_n_tiles;
+  out->LMAX = p->mm_LMAX;
+  out->segs = p->mm_segs;
+  out->n_seg = p->mm_n_seg;
+  out->seg_cap = p->mm_seg_cap;
+  return B200SP_OK;
+}
+
 void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
   if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "%s", s);
 }
@@ -816,6 +900,7 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   if (!p) return B200SP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   plan_release_analysis(p, st);
+  plan_release_mm(p, st);
   if (p->dx) cudaFreeAsync(p->dx, st);
   if (p->dy) cudaFreeAsync(p->dy, st);
   if (p->xt) cudaFreeAsync(p->xt, st);

@@ -818,7 +818,7 @@ static void suite_spmm() {
   Dev<int> drp(rp), dci(ci);
   Dev<float> dv(v), dX(X), dY((size_t)n * k);
   const double balg = 8.0 * nnz + 4.0 * (n + 1) + 4.0 * (double)n * k * 3;
-  const char* kernels[] = {"row", "split", "tile"};
+  const char* kernels[] = {"row", "split", "tile", "tilev"};
   for (const char* kn : kernels) {
     setenv("B200SP_SPMM_KERNEL", kn, 1);
     b200sp_spmv_plan* plan = nullptr;
