@@ -224,6 +224,28 @@ int b200sp_spadd_numeric_f32_i32(b200sp_spadd_plan* plan, void* stream, int m, i
                                  const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
                                  float beta, const int* row_ptr_C, int* col_idx_C, float* vals_C);
 
+/* ---- matrix files (host side) ---------------------------------- */
+/* read_kokkos_crst_matrix (sparse/src/KokkosSparse_IOUtils.hpp:1237-1290): MatrixMarket (.mtx, .mm;
+ * read_mtx with symmetrize = remove_diagonal = transpose = false, :784-996 -- coordinate or array,
+ * real / integer / pattern, general / symmetric / skew-symmetric / hermitian; rows come out sorted,
+ * symmetric files are expanded) or the raw binary CRS dump (.bin, read_graph_bin :680-695; no column
+ * count in the file: ncols = largest column + 1).  The three arrays are HOST memory allocated by the
+ * library: release each with b200sp_host_free.  Harwell-Boeing files are not supported. */
+int b200sp_read_crs_f64(const char* path, int* m, int* n, int64_t* nnz, int** row_ptr, int** col_idx, double** vals);
+int b200sp_read_crs_f32(const char* path, int* m, int* n, int64_t* nnz, int** row_ptr, int** col_idx, float** vals);
+/* read_mtx with its three options (IOUtils.hpp:785-786). */
+int b200sp_read_mtx_f64(const char* path, int symmetrize, int remove_diagonal, int transpose, int* m, int* n,
+                        int64_t* nnz, int** row_ptr, int** col_idx, double** vals);
+int b200sp_read_mtx_f32(const char* path, int symmetrize, int remove_diagonal, int transpose, int* m, int* n,
+                        int64_t* nnz, int** row_ptr, int** col_idx, float** vals);
+/* write_kokkos_crst_matrix (IOUtils.hpp:740-782): .mtx / .mm (write_matrix_mtx, 17 significant digits) or
+ * .bin (write_graph_bin; square matrices only, like the reference).  HOST arrays. */
+int b200sp_write_crs_f64(const char* path, int m, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                         const double* vals);
+int b200sp_write_crs_f32(const char* path, int m, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                         const float* vals);
+void b200sp_host_free(void* p);
+
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */
 int64_t b200sp_launch_count(void);

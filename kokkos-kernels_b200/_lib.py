@@ -47,6 +47,13 @@ SPARSE_API = {
     "b200sp_spadd_symbolic_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "b200sp_spadd_numeric_f64_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp]),
     "b200sp_spadd_numeric_f32_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, f32, vp, vp, vp, f32, vp, vp, vp]),
+    "b200sp_read_crs_f64": (i32, [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b200sp_read_crs_f32": (i32, [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b200sp_read_mtx_f64": (i32, [C.c_char_p, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b200sp_read_mtx_f32": (i32, [C.c_char_p, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b200sp_write_crs_f64": (i32, [C.c_char_p, i32, i32, i64, vp, vp, vp]),
+    "b200sp_write_crs_f32": (i32, [C.c_char_p, i32, i32, i64, vp, vp, vp]),
+    "b200sp_host_free": (None, [vp]),
     "b200sp_launch_count": (i64, []),
     "b200sp_spmv_last_kernel": (C.c_char_p, [vp]),
     "b200sp_spmv_plan_tune": (i32, [vp, i32, i32, i32]),

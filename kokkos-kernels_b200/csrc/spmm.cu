@@ -845,14 +845,21 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
         B200SP_LAUNCH_CHECK();
       }
     }
-    rc = split ? launch_split<S>(p, st, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta)
-               : launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    const bool tile_ok = choice >= 2 && (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0;
+    if (tile_ok) {
+      constexpr int W = VecOf<S>::W;
+      const bool vec = choice == 3 && (k % W == 0) && (ldxr % W == 0) && (ldyr % W == 0) && ((((uintptr_t)Xr) | ((uintptr_t)Yr)) & 15u) == 0;
+      rc = launch_mm_tile<S>(p, st, vec, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    } else {
+      rc = split ? launch_split<S>(p, st, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta)
+                 : launch_rowmajor<S>(st, m, k, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    }
     if (rc) return rc;
     if (!yrm) {
       relayout_kernel<S, false><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
       B200SP_LAUNCH_CHECK();
     }
-    plan_set_last_kernel(p, split ? "spmm_relayout+split" : "spmm_relayout+rowmajor");
+    plan_set_last_kernel(p, tile_ok ? "spmm_relayout+tile" : (split ? "spmm_relayout+split" : "spmm_relayout+rowmajor"));
     return B200SP_OK;
   }
   const int g = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, (int64_t)sm_count() * 16);

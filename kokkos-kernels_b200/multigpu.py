@@ -9,7 +9,11 @@ while piece c+1 is being computed.  A device-side barrier closes the step.  Resu
 to the single-GPU SpMV (same kernel, same per-row order).
 
 modes: "pipelined" (default), "fused" (P2P stores issued by the SpMV kernel itself,
-b200sp_spmv_scatter_f64_i32), "nccl" (SpMV then all_gather_into_tensor)."""
+b200sp_spmv_scatter_f64_i32), "multicast" (as fused, but ONE store per y value to the NVSwitch multicast
+address of the symmetric buffer -- on sm_100 multimem.st is a plain st.global to a multicast mapping, the
+switch replicates it into all 8 copies, so every GPU sends its 80 MB once instead of 7 times; falls back
+to "fused" when the symmetric-memory handle has no multicast pointer; first measurements: round 2),
+"nccl" (SpMV then all_gather_into_tensor)."""
 import ctypes as C
 
 import numpy as np
@@ -28,12 +32,15 @@ class RowBlockSpMV:
         self.ci_d = torch.from_numpy(ci).to(device)
         self.va_d = torch.from_numpy(va).to(device)
         self.symm = None
-        if mode in ("pipelined", "fused"):
+        if mode in ("pipelined", "fused", "multicast"):
             import torch.distributed._symmetric_memory as symm_mem
 
             self.x_next = symm_mem.empty(n_total, dtype=torch.float64, device=device)
             self.symm = symm_mem.rendezvous(self.x_next, dist.group.WORLD)
             self.peer_ptrs = [int(p) for p in self.symm.buffer_ptrs]
+            self.mc_ptr = int(getattr(self.symm, "multicast_ptr", 0) or 0)
+            if mode == "multicast" and self.mc_ptr == 0:
+                self.mode = mode = "fused"  # no NVLS multicast mapping on this box
         else:
             self.x_next = torch.empty(n_total, dtype=torch.float64, device=device)
         self.y = self.x_next[r0:r1]
@@ -57,7 +64,9 @@ class RowBlockSpMV:
             h.tune(*tune)
             yv = self.y[c0:c1]
             dsts = []
-            if self.symm is not None:
+            if self.symm is not None and mode == "multicast":
+                dsts = [self.mc_ptr + (r0 + c0) * 8]  # one store, replicated by the switch (incl. this rank's copy)
+            elif self.symm is not None:
                 dsts = [self.peer_ptrs[q] + (r0 + c0) * 8 for q in range(self.world) if q != self.rank]
             arr = (C.c_void_p * max(len(dsts), 1))(*[C.c_void_p(d) for d in dsts])
             self.pieces.append((A, h, yv, dsts, arr, torch.cuda.Event()))
@@ -79,7 +88,7 @@ class RowBlockSpMV:
         stream work completes)."""
         lib = _lib.sparse()
         cur = torch.cuda.current_stream()
-        if self.mode == "fused":
+        if self.mode in ("fused", "multicast"):
             A, h, yv, dsts, arr, ev = self.pieces[0]
             sp.spmv_scatter(h, 1.0, A, x, yv, dsts)
             self.symm.barrier(channel=0)

@@ -441,3 +441,43 @@ def spadd_numeric(kh, alpha, A, beta, B, Cm):
     spadd_numeric_views(kh, A.numRows(), A.numCols(), A.row_map, A.entries, A.values, alpha, B.row_map, B.entries, B.values, beta,
                         Cm.row_map, Cm.entries, Cm.values)
     return Cm
+
+
+# --------------------------------------------------------------------------- matrix files
+def read_kokkos_crst_matrix(filename, dtype=torch.float64, device=None):
+    """KokkosSparse::Impl::read_kokkos_crst_matrix (sparse/src/KokkosSparse_IOUtils.hpp:1237-1290): .mtx / .mm
+    or .bin -> CrsMatrix (on `device`; host tensors when device is None)."""
+    import numpy as np
+
+    lib = _lib.sparse()
+    m, n, nnz = C.c_int(0), C.c_int(0), C.c_int64(0)
+    rp, ci, v = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+    f64 = dtype == torch.float64
+    if not f64 and dtype != torch.float32:
+        raise B200SparseError("b200sparse: only double and float are instantiated")
+    fn = lib.b200sp_read_crs_f64 if f64 else lib.b200sp_read_crs_f32
+    check(fn(str(filename).encode(), C.byref(m), C.byref(n), C.byref(nnz), C.byref(rp), C.byref(ci), C.byref(v)))
+    try:
+        def take(ptr, count, ctype, npt):
+            if count == 0:
+                return torch.zeros(0, dtype=torch.from_numpy(np.zeros(0, npt)).dtype)
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).copy()
+            return torch.from_numpy(arr)
+
+        row_map = take(rp, m.value + 1, C.c_int, np.int32)
+        entries = take(ci, nnz.value, C.c_int, np.int32)
+        values = take(v, nnz.value, C.c_double if f64 else C.c_float, np.float64 if f64 else np.float32)
+    finally:
+        for q in (rp, ci, v):
+            lib.b200sp_host_free(q)
+    if device is not None:
+        row_map, entries, values = row_map.to(device), entries.to(device), values.to(device)
+    return CrsMatrix(row_map, entries, values, n.value)
+
+
+def write_kokkos_crst_matrix(A, filename):
+    """write_kokkos_crst_matrix (IOUtils.hpp:740-782): .mtx / .mm or .bin (square only)."""
+    rp, ci, v = A.row_map.cpu().contiguous(), A.entries.cpu().contiguous(), A.values.cpu().contiguous()
+    fn = getattr(_lib.sparse(), f"b200sp_write_crs_{_sfx(v)}_i32".replace("_i32", ""))
+    check(fn(str(filename).encode(), A.numRows(), A.numCols(), A.nnz(), C.c_void_p(rp.data_ptr()), C.c_void_p(ci.data_ptr()),
+             C.c_void_p(v.data_ptr())))
