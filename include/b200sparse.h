@@ -68,6 +68,14 @@ int b200sp_spmv_plan_create(b200sp_spmv_plan** plan, int algo);
  * fence, like TPL_SpMV_Data's destructor, spmv_handle.hpp:116-128). */
 int b200sp_spmv_plan_destroy(b200sp_spmv_plan* plan, void* stream);
 
+/* Plan options.  B200SP_SPMV_OPT_CACHE_TRANSPOSE (default 0): modes T / H run through an explicit
+ * transpose kept in the plan (structure built once per matrix with b200sp_transpose's kernels, values
+ * re-gathered on every call, then the non-transposed kernel): deterministic, no atomics, at the price
+ * of 8 bytes/entry of structure + sizeof(S) bytes/entry of values.  Without it T / H use atomicAdd
+ * scatters like the reference's GPU path (sparse/impl/KokkosSparse_spmv_impl.hpp:36-84). */
+#define B200SP_SPMV_OPT_CACHE_TRANSPOSE 1
+int b200sp_spmv_plan_set_option(b200sp_spmv_plan* plan, int option, int value);
+
 /* ---- SpMV rank-1: y = beta*y + alpha*op(A)*x ---------------------------- */
 /* Replaces SPMV<Kokkos::Cuda,...,true>::spmv -> spmv_cusparse
  * (sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:31-225) and, without the

@@ -19,6 +19,7 @@ SPARSE_API = {
     "b200sp_device_ok": (i32, []),
     "b200sp_spmv_plan_create": (i32, [C.POINTER(vp), i32]),
     "b200sp_spmv_plan_destroy": (i32, [vp, vp]),
+    "b200sp_spmv_plan_set_option": (i32, [vp, i32, i32]),
     "b200sp_spmv_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, f64, vp, vp, vp, vp, f64, vp]),
     "b200sp_spmv_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, f32, vp, vp, vp, vp, f32, vp]),
     "b200sp_spmv_scatter_f64_i32": (i32, [vp, vp, i32, i32, i64, f64, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]),

@@ -484,6 +484,35 @@ static inline int grid_for(int64_t work, int per_block = 256, int mult = 8) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, (int64_t)sm_count() * mult));
 }
 
+// structure of the transpose + source entry of every transposed entry (t_src); nnz = row_ptr[m] (host value)
+int transpose_structure(cudaStream_t st, int m, int n, int64_t nnz, const int* rp, const int* ci, int* trp, int* tci,
+                        int* t_src) {
+  DevTmp tmp(st);
+  int *counts, *cursor;
+  B200SP_CUDA_TRY(tmp.alloc(&counts, (size_t)n));
+  B200SP_CUDA_TRY(tmp.alloc(&cursor, (size_t)n + 1));
+  B200SP_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n, st));
+  transpose_count_kernel<<<grid_for(nnz), 256, 0, st>>>(nnz, ci, counts);
+  B200SP_LAUNCH_CHECK();
+  int rc = counts_to_offsets(st, n, counts, trp, nullptr, nullptr);
+  if (rc) return rc;
+  B200SP_CUDA_TRY(cudaMemcpyAsync(cursor, trp, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
+  transpose_fill_kernel<<<(unsigned)(((int64_t)m * 8 + 255) / 256), 256, 0, st>>>(m, rp, ci, cursor, tci, t_src);
+  B200SP_LAUNCH_CHECK();
+  // (row, entry id) order inside every transposed row: the Serial loop's order, whatever the atomics did
+  return sort_crs_impl<int, 2>(st, n, trp, tci, t_src, nnz);
+}
+
+template <typename S>
+int gather_values(cudaStream_t st, int64_t nnz, const int* t_src, const S* v, S* tv) {
+  if (nnz <= 0) return B200SP_OK;
+  transpose_gather_kernel<S><<<grid_for(nnz), 256, 0, st>>>(nnz, t_src, v, tv);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+template int gather_values<double>(cudaStream_t, int64_t, const int*, const double*, double*);
+template int gather_values<float>(cudaStream_t, int64_t, const int*, const float*, float*);
+
 template <typename S, bool HAS_VALS>
 static int transpose_impl(cudaStream_t st, int m, int n, const int* rp, const int* ci, const S* v, int* trp, int* tci,
                           S* tv) {
@@ -500,25 +529,11 @@ static int transpose_impl(cudaStream_t st, int m, int n, const int* rp, const in
   if (n == 0 || nnz == 0) return zero_ints(st, (int64_t)n + 1, trp);
   B200SP_REQUIRE(ci && tci && (!HAS_VALS || (v && tv)), "transpose_matrix: null pointer argument");
   DevTmp tmp(st);
-  int *counts, *cursor, *t_src;
-  B200SP_CUDA_TRY(tmp.alloc(&counts, (size_t)n));
-  B200SP_CUDA_TRY(tmp.alloc(&cursor, (size_t)n + 1));
+  int* t_src;
   B200SP_CUDA_TRY(tmp.alloc(&t_src, (size_t)nnz));
-  B200SP_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n, st));
-  transpose_count_kernel<<<grid_for(nnz), 256, 0, st>>>(nnz, ci, counts);
-  B200SP_LAUNCH_CHECK();
-  int rc = counts_to_offsets(st, n, counts, trp, nullptr, nullptr);
+  int rc = transpose_structure(st, m, n, nnz, rp, ci, trp, tci, t_src);
   if (rc) return rc;
-  B200SP_CUDA_TRY(cudaMemcpyAsync(cursor, trp, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
-  transpose_fill_kernel<<<(unsigned)(((int64_t)m * 8 + 255) / 256), 256, 0, st>>>(m, rp, ci, cursor, tci, t_src);
-  B200SP_LAUNCH_CHECK();
-  // (row, entry id) order inside every transposed row: the Serial loop's order, whatever the atomics did
-  rc = sort_crs_impl<int, 2>(st, n, trp, tci, t_src, nnz);
-  if (rc) return rc;
-  if (HAS_VALS) {
-    transpose_gather_kernel<S><<<grid_for(nnz), 256, 0, st>>>(nnz, t_src, v, tv);
-    B200SP_LAUNCH_CHECK();
-  }
+  if (HAS_VALS) return gather_values<S>(st, nnz, t_src, v, tv);
   return B200SP_OK;
 }
 

@@ -481,6 +481,16 @@ struct b200sp_spmv_plan {
   const int* mm_key_row_ptr = nullptr;
   int mm_key_m = -1, mm_key_cap = -1, mm_key_lmax = -1;
   int64_t mm_key_nnz = -1;
+  // cached transpose (B200SP_SPMV_OPT_CACHE_TRANSPOSE): structure of A^T + source entry of each of its entries,
+  // values re-gathered on every call (they may have changed in place), and a plan of its own for A^T
+  bool cache_transpose = false;
+  int *t_rp = nullptr, *t_ci = nullptr, *t_src = nullptr;
+  void* t_vals = nullptr;
+  size_t t_vals_bytes = 0;
+  const int *t_key_rp = nullptr, *t_key_ci = nullptr;
+  int t_key_m = -1, t_key_n = -1;
+  int64_t t_key_nnz = -1;
+  b200sp_spmv_plan* tplan = nullptr;
   char last_kernel[96] = "none";
   b200sp::YExtra extra = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
   // self-tuning between the tiled and the row-vector kernel (same bits, different speed by matrix):
@@ -765,6 +775,68 @@ static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, c
   return B200SP_OK;
 }
 
+// crs_utils.cu
+int transpose_structure(cudaStream_t st, int m, int n, int64_t nnz, const int* rp, const int* ci, int* trp, int* tci,
+                        int* t_src);
+template <typename S>
+int gather_values(cudaStream_t st, int64_t nnz, const int* t_src, const S* v, S* tv);
+
+static void plan_release_transpose(b200sp_spmv_plan* p, cudaStream_t st) {
+  void* ptrs[] = {p->t_rp, p->t_ci, p->t_src, p->t_vals};
+  for (void* q : ptrs)
+    if (q) cudaFreeAsync(q, st);
+  p->t_rp = p->t_ci = p->t_src = nullptr;
+  p->t_vals = nullptr;
+  p->t_vals_bytes = 0;
+  p->t_key_rp = nullptr;
+}
+
+template <typename S>
+static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int n, int64_t nnz, S alpha,
+                     const int* row_ptr, const int* col_idx, const S* vals, const S* x, S beta, S* y);
+
+// y = beta*y + alpha*A^T*x through an explicit A^T kept in the plan: the transposed product becomes the
+// gather kernel's (deterministic, no atomics).  The structure is built once per matrix (synchronises the
+// stream), the values are re-gathered on every call.
+template <typename S>
+static int spmv_cached_transpose(b200sp_spmv_plan* p, cudaStream_t st, int m, int n, int64_t nnz, S alpha,
+                                 const int* row_ptr, const int* col_idx, const S* vals, const S* x, S beta, S* y) {
+  if (!(p->t_rp && p->t_key_rp == row_ptr && p->t_key_ci == col_idx && p->t_key_m == m && p->t_key_n == n &&
+        p->t_key_nnz == nnz)) {
+    plan_release_transpose(p, st);
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->t_rp, sizeof(int) * ((size_t)n + 1), st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->t_ci, sizeof(int) * (size_t)nnz, st));
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->t_src, sizeof(int) * (size_t)nnz, st));
+    int rc = transpose_structure(st, m, n, nnz, row_ptr, col_idx, p->t_rp, p->t_ci, p->t_src);
+    if (rc) return rc;
+    p->t_key_rp = row_ptr;
+    p->t_key_ci = col_idx;
+    p->t_key_m = m;
+    p->t_key_n = n;
+    p->t_key_nnz = nnz;
+    if (!p->tplan) {
+      rc = b200sp_spmv_plan_create(&p->tplan, p->algo);
+      if (rc) return rc;
+      p->tplan->cfg = p->cfg;
+      p->tplan->ctas_per_sm = p->ctas_per_sm;
+    }
+  }
+  const size_t need = sizeof(S) * (size_t)nnz;
+  if (need > p->t_vals_bytes) {
+    if (p->t_vals) cudaFreeAsync(p->t_vals, st);
+    p->t_vals = nullptr;
+    p->t_vals_bytes = 0;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->t_vals, need, st));
+    p->t_vals_bytes = need;
+  }
+  int rc = gather_values<S>(st, nnz, p->t_src, vals, (S*)p->t_vals);
+  if (rc) return rc;
+  rc = spmv_impl<S>(p->tplan, st, 'N', n, m, nnz, alpha, p->t_rp, p->t_ci, (const S*)p->t_vals, x, beta, y);
+  if (rc) return rc;
+  snprintf(p->last_kernel, sizeof(p->last_kernel), "cached_transpose+%.70s", p->tplan->last_kernel);
+  return B200SP_OK;
+}
+
 template <typename S>
 static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int n, int64_t nnz, S alpha,
                      const int* row_ptr, const int* col_idx, const S* vals, const S* x, S beta, S* y) {
@@ -790,6 +862,8 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   B200SP_REQUIRE(row_ptr && col_idx && vals && x && y, "spmv: null pointer argument");
 
   const int lpr_auto = pick_lpr(m, nnz);
+  if (trans && p && p->cache_transpose)
+    return spmv_cached_transpose<S>(p, st, m, n, nnz, alpha, row_ptr, col_idx, vals, x, beta, y);
   if (trans) {
     int rc = launch_scale<S>(st, ylen, beta, y);
     if (rc) return rc;
@@ -901,6 +975,9 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   plan_release_analysis(p, st);
   plan_release_mm(p, st);
+  plan_release_transpose(p, st);
+  if (p->tplan) b200sp_spmv_plan_destroy(p->tplan, stream);
+  p->tplan = nullptr;
   if (p->dx) cudaFreeAsync(p->dx, st);
   if (p->dy) cudaFreeAsync(p->dy, st);
   if (p->xt) cudaFreeAsync(p->xt, st);
@@ -929,6 +1006,15 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* p, void* stream) {
   if (p->n_long_host) cudaFreeHost(p->n_long_host);
   delete p;
   return B200SP_OK;
+}
+
+int b200sp_spmv_plan_set_option(b200sp_spmv_plan* p, int option, int value) {
+  B200SP_REQUIRE(p != nullptr, "spmv_plan_set_option: null plan");
+  switch (option) {
+    case B200SP_SPMV_OPT_CACHE_TRANSPOSE: p->cache_transpose = value != 0; return B200SP_OK;
+  }
+  set_error("spmv_plan_set_option: unknown option %d", option);
+  return B200SP_ERR_INVALID_ARGUMENT;
 }
 
 int b200sp_spmv_plan_tune(b200sp_spmv_plan* p, int cfg, int lanes_per_row, int ctas_per_sm) {

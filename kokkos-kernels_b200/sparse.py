@@ -75,6 +75,10 @@ class SPMVHandle:
     def get_algorithm(self):
         return self.algo
 
+    def cache_transpose(self, enable=True):
+        """Modes T / H through an explicit transpose kept in the plan (deterministic, no atomics)."""
+        check(_lib.sparse().b200sp_spmv_plan_set_option(self._plan, 1, int(bool(enable))))
+
     def tune(self, cfg=-1, lanes_per_row=-1, ctas_per_sm=-1):
         check(_lib.sparse().b200sp_spmv_plan_tune(self._plan, cfg, lanes_per_row, ctas_per_sm))
 

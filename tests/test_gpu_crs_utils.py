@@ -176,3 +176,39 @@ def test_spadd_known_columns_and_misuse(cuda):
     C0 = sp.spadd_symbolic(kh2, E, E)
     sp.spadd_numeric(kh2, 1.0, E, 1.0, E, C0)
     assert C0.nnz() == 0 and host(C0.row_map).tolist() == [0]
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 1e-4)])
+def test_spmv_cached_transpose(cuda, oracle, dtype, tol):
+    """Modes T / H through the plan's explicit transpose (SPMVHandle.cache_transpose): same result law as
+    the atomics path, and bit-reproducible from call to call."""
+    from helpers import rowwise_scale
+    from kokkos_kernels_b200 import sparse as sp
+
+    m, n = 30000, 12000
+    rp, ci, v = kk_matrix(m, n, 600000, 20, 4000, dtype=dtype, lo=-1.0, hi=1.0)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, m).astype(dtype)
+    y0 = rng.uniform(-1, 1, n).astype(dtype)
+    alpha, beta = 1.25, -0.5
+    yref = y0.astype(dtype).copy()
+    oracle.spmv_transpose(rp, ci, v, n, x, yref, dtype(alpha), dtype(beta))
+    scale = rowwise_scale(rp, ci, v, x, y0, alpha, beta, ncols_out=n, trans=True)
+    A = dev_mat(sp, cuda, rp, ci, v, n)
+    h = sp.SPMVHandle(sp.SPMV_DEFAULT)
+    h.cache_transpose(True)
+    xd = torch.from_numpy(x).to(cuda)
+    outs = []
+    for mode in ("T", "H", "T"):
+        yd = torch.from_numpy(y0.copy()).to(cuda)
+        sp.spmv(h, mode, alpha, A, xd, beta, yd)
+        outs.append(host(yd))
+    assert h.last_kernel().startswith("cached_transpose")
+    err = np.max(np.abs(outs[0].astype(np.float64) - yref.astype(np.float64)) / np.maximum(scale, 1e-300))
+    assert err <= tol, err
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), "deterministic: no atomics"
+    # the values may change in place between calls: they are re-gathered
+    A.values.mul_(2.0)
+    yd = torch.from_numpy(y0.copy()).to(cuda)
+    sp.spmv(h, "T", alpha / 2.0, A, xd, beta, yd)
+    assert np.max(np.abs(host(yd).astype(np.float64) - yref.astype(np.float64)) / np.maximum(scale, 1e-300)) <= tol

@@ -6,7 +6,7 @@
 // the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
 // faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
 //
-//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t
 //
 // Exit code: number of failed suites.
 #include <cuda_runtime.h>
@@ -844,6 +844,63 @@ static void suite_spmm() {
   unsetenv("B200SP_SPMM_KERNEL");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// suite: spmv_t -- transposed SpMV: atomics path vs the cached-transpose option, against the oracle
+// ------------------------------------------------------------------------------------------------
+static void spmv_t_case(const char* name, const Csr<double>& A) {
+  std::vector<double> x((size_t)A.m), y0((size_t)A.n), yref, scale;
+  b200gen_fill_f64(A.m, x.data(), -1.0, 1.0, 1);
+  b200gen_fill_f64(A.n, y0.data(), -1.0, 1.0, 2);
+  const double alpha = 1.25, beta = -0.5;
+  yref = y0;
+  okk_spmv_transpose_f64(A.m, A.n, A.rp.data(), A.ci.data(), A.v.data(), x.data(), yref.data(), alpha, beta);
+  std::vector<double> va(A.v), xa(x);
+  scale = y0;
+  for (auto& t : va) t = std::fabs(t);
+  for (auto& t : xa) t = std::fabs(t);
+  for (auto& t : scale) t = std::fabs(t);
+  okk_spmv_transpose_f64(A.m, A.n, A.rp.data(), A.ci.data(), va.data(), xa.data(), scale.data(), std::fabs(alpha), std::fabs(beta));
+  Dev<int> rp(A.rp), ci(A.ci);
+  Dev<double> v(A.v), dx(x), dy((size_t)A.n);
+  for (int cached = 0; cached <= 1; ++cached) {
+    b200sp_spmv_plan* plan = nullptr;
+    SP(b200sp_spmv_plan_create(&plan, 0));
+    SP(b200sp_spmv_plan_set_option(plan, B200SP_SPMV_OPT_CACHE_TRANSPOSE, cached));
+    float best = 1e30f;
+    std::vector<double> got, first;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaMemcpy(dy.p, y0.data(), y0.size() * sizeof(double), cudaMemcpyHostToDevice));
+      Timer t;
+      t.start();
+      SP(b200sp_spmv_f64_i32(plan, nullptr, 'T', A.m, A.n, A.nnz(), alpha, rp.p, ci.p, v.p, dx.p, beta, dy.p));
+      const float ms = t.stop_ms();
+      if (rep > 0) best = std::min(best, ms);
+      got = dy.host();
+      if (rep == 0) first = got;
+    }
+    double worst = 0;
+    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, std::fabs(got[i] - yref[i]) / std::max(scale[i], 1e-300));
+    const int64_t drift = count_diff(got, first);  // run-to-run bit differences (atomics reorder, the cached path must not)
+    char nm[128];
+    snprintf(nm, sizeof(nm), "%s/%s", name, cached ? "cached_transpose" : "atomics");
+    record(nm, worst <= 1e-10 && (!cached || drift == 0), "kernel=%s %.3f ms, max scaled err %.2e, run-to-run differing entries %lld",
+           b200sp_spmv_last_kernel(plan), best, worst, (long long)drift);
+    b200sp_spmv_plan_destroy(plan, nullptr);
+  }
+}
+
+static void suite_spmv_t() {
+  spmv_t_case("lap27_40x2dof", gen_lap27<double>(g_big ? 100 : 40, 2));
+  {
+    Rng r(8);
+    std::vector<int> lens(50000);
+    for (auto& l : lens) l = r.below(30);
+    lens[7] = 20000;
+    spmv_t_case("random_50000x20000_rect", gen_rows<double>(lens, 20000, false, false, 8));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct Suite {
   const char* name;
@@ -853,7 +910,7 @@ struct Suite {
 
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 120}, {"crs", suite_crs, 120}, {"spgemm_c4", suite_spgemm_c4, 150},
-                            {"crs_big", suite_crs_big, 120}, {"spmm", suite_spmm, 150}};
+                            {"crs_big", suite_crs_big, 120}, {"spmm", suite_spmm, 150}, {"spmv_t", suite_spmv_t, 120}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
