@@ -737,7 +737,7 @@ static void suite_crs() {
 // suite: crs_big -- timings on a bench-sized matrix (27-point stencil x 2 dof, rows shuffled for the sort)
 // ------------------------------------------------------------------------------------------------
 static void suite_crs_big() {
-  const int g = g_big ? 100 : 50;
+  const int g = g_big ? 64 : 40;
   auto A = gen_lap27<double>(g, 2);
   Csr<double> U = A;  // rows reversed: every row needs sorting
   for (int i = 0; i < U.m; ++i) {
@@ -909,8 +909,8 @@ struct Suite {
 };
 
 int main(int argc, char** argv) {
-  std::vector<Suite> all = {{"spgemm", suite_spgemm, 120}, {"crs", suite_crs, 120}, {"spgemm_c4", suite_spgemm_c4, 150},
-                            {"crs_big", suite_crs_big, 120}, {"spmm", suite_spmm, 150}, {"spmv_t", suite_spmv_t, 120}};
+  std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
+                            {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
