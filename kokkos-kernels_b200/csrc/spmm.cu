@@ -711,7 +711,12 @@ static int launch_mm_tile_k(cudaStream_t st, const MMTileView& tv, int m, int k,
 template <typename S>
 static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
                           const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
-  constexpr int CAP = 2048, LMAX = 256, SEG = 2048;
+  constexpr int CAP = 2048, SEG = 2048;
+  int LMAX = 256;  // rows longer than this leave the tiles for the segment kernel (B200SP_SPMM_LMAX: 16..1024)
+  if (const char* e = getenv("B200SP_SPMM_LMAX")) {
+    const int v = atoi(e);
+    if (v >= 16 && v <= 1024) LMAX = v;
+  }
   MMTileView tv;
   int rc = plan_analyse_mm(p, st, CAP, LMAX, SEG, m, nnz, row_ptr, &tv);
   if (rc) return rc;
@@ -752,13 +757,16 @@ static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m,
   return B200SP_OK;
 }
 
-// which rank-2 kernel: 0 = row per group, 1 = nnz-split (default), 2 = tile, 3 = tile with 16-byte X loads
+// which rank-2 kernel: 0 = row per group, 1 = nnz-split, 2 = tile, 3 = tile with 16-byte X loads (default:
+// measured 1.74 ms vs 4.01 ms for the split kernel on R-MAT scale 21 x 16 columns, profiles/README.md).
+// B200SP_SPMM_KERNEL=row|split|tile|tilev overrides.
 static int mm_kernel_choice(b200sp_spmv_plan* p) {
   if (!p) return 0;  // the others need a plan (chunk table / tile analysis)
   const char* e = getenv("B200SP_SPMM_KERNEL");
   if (e && e[0] == 'r') return 0;
+  if (e && e[0] == 's') return 1;
   if (e && e[0] == 't') return (e[1] == 'i' && e[2] == 'l' && e[3] == 'e' && e[4] == 'v') ? 3 : 2;
-  return 1;
+  return 3;
 }
 
 static bool use_split_kernel(b200sp_spmv_plan* p) {

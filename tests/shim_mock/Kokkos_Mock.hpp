@@ -7,6 +7,8 @@
 //   spmv_tpl_spec_avail              sparse/tpls/KokkosSparse_spmv_tpl_spec_avail.hpp:27-30
 //   SPGEMM_SYMBOLIC / _NUMERIC       sparse/impl/KokkosSparse_spgemm_{symbolic,numeric}_spec.hpp:72-98
 //   SPGEMMHandle state               sparse/src/KokkosSparse_spgemm_handle.hpp:356-362,628-653
+//   SPADDHandle                      sparse/src/KokkosSparse_spadd_handle.hpp:24-137
+//   SPADD_SYMBOLIC / _NUMERIC        sparse/impl/KokkosSparse_spadd_{symbolic,numeric}_spec.hpp:70-80
 // TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <cuda_runtime.h>
@@ -187,6 +189,35 @@ struct SPGEMMHandleMock {
 };
 }  // namespace KokkosSparse
 
+struct b200sp_spadd_plan;
+extern "C" int b200sp_spadd_plan_destroy(b200sp_spadd_plan*, void*);
+
+namespace KokkosSparse {
+// the SPADDHandle members the shim touches (+ the b200Data member INTEGRATION.md adds)
+struct SPADDHandleMock {
+  struct SpaddB200Data {
+    b200sp_spadd_plan* plan = nullptr;
+    ~SpaddB200Data() {
+      if (plan) b200sp_spadd_plan_destroy(plan, nullptr);
+    }
+  };
+  SPADDHandleMock(bool input_is_sorted, bool input_is_merged = false) : input_sorted(input_is_sorted), input_merged(input_is_merged) {}
+  void set_c_nnz(size_t v) { result_nnz_size = v; }
+  size_t get_c_nnz() const { return result_nnz_size; }
+  bool is_symbolic_called() const { return called_symbolic; }
+  bool is_numeric_called() const { return called_numeric; }
+  void set_call_symbolic(bool c = true) { called_symbolic = c; }
+  void set_call_numeric(bool c = true) { called_numeric = c; }
+  bool is_input_sorted() const { return input_sorted; }
+  bool is_input_merged() const { return input_merged; }
+  bool is_input_strict_crs() const { return input_sorted && input_merged; }
+  SpaddB200Data b200Data;
+  bool input_sorted, input_merged;
+  size_t result_nnz_size = 0;
+  bool called_symbolic = false, called_numeric = false;
+};
+}  // namespace KokkosSparse
+
 namespace KokkosKernels {
 namespace Experimental {
 template <class size_type_, class lno_t_, class scalar_t_, class Exec, class TmpMem, class PersMem>
@@ -202,6 +233,14 @@ struct KokkosKernelsHandle {
     sh = nullptr;
   }
   SPGEMMHandleType* sh = nullptr;
+  using SPADDHandleType = KokkosSparse::SPADDHandleMock;
+  SPADDHandleType* get_spadd_handle() { return ah; }
+  void create_spadd_handle(bool input_sorted = false, bool input_merged = false) { ah = new SPADDHandleType(input_sorted, input_merged); }
+  void destroy_spadd_handle() {
+    delete ah;
+    ah = nullptr;
+  }
+  SPADDHandleType* ah = nullptr;
 };
 }  // namespace Experimental
 }  // namespace KokkosKernels
@@ -221,5 +260,24 @@ struct SPGEMM_SYMBOLIC;
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v,
           bool tpl, bool eti>
 struct SPGEMM_NUMERIC;
+}  // namespace Impl
+}  // namespace KokkosSparse
+
+namespace KokkosSparse {
+namespace Impl {
+template <class ExecSpace, class KH, class a_r, class a_e, class b_r, class b_e, class c_r>
+struct spadd_symbolic_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecSpace, class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e,
+          class c_v>
+struct spadd_numeric_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecSpace, class KH, class a_r, class a_e, class b_r, class b_e, class c_r, bool tpl, bool eti>
+struct SPADD_SYMBOLIC;
+template <class ExecSpace, class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e,
+          class c_v, bool tpl, bool eti>
+struct SPADD_NUMERIC;
 }  // namespace Impl
 }  // namespace KokkosSparse

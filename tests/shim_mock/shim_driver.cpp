@@ -7,6 +7,8 @@
 #include "KokkosSparse_spmv_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spgemm_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spgemm_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_spadd_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_spadd_b200_tpl_spec_decl.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -33,6 +35,8 @@ static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::va
 static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
 static_assert(Impl::spgemm_symbolic_tpl_spec_avail<KH, CIV, CIV, CIV, CIV, IV>::value, "spgemm symbolic must be available");
 static_assert(Impl::spgemm_numeric_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV>::value, "spgemm numeric");
+static_assert(Impl::spadd_symbolic_tpl_spec_avail<Kokkos::Cuda, KH, CIV, CIV, CIV, CIV, IV>::value, "spadd symbolic must be available");
+static_assert(Impl::spadd_numeric_tpl_spec_avail<Kokkos::Cuda, KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV>::value, "spadd numeric");
 
 template <class T>
 T* to_dev(const std::vector<T>& h) {
@@ -154,6 +158,43 @@ int main() {
     std::printf("spgemm through SPGEMM_SYMBOLIC/NUMERIC<...,true,true> : c_nnz=%zu, %d mismatches\n", cnnz, f3);
     failures += f3;
     kh.destroy_spgemm_handle();
+  }
+  {
+    // C = 2*A - 0.5*A through the spadd specialisations (strict CRS input, the only case that reaches a TPL)
+    KH kh;
+    kh.create_spadd_handle(true, true);
+    int* d_rpC = nullptr;
+    cudaMalloc(&d_rpC, sizeof(int) * (n + 1));
+    using ASYM = Impl::SPADD_SYMBOLIC<Kokkos::Cuda, KH, CIV, CIV, CIV, CIV, IV, true, true>;
+    using ANUM = Impl::SPADD_NUMERIC<Kokkos::Cuda, KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV, true, true>;
+    CIV vrp(d_rp, n + 1), vci(d_ci, ci.size());
+    CSV vva(d_va, va.size());
+    ASYM::spadd_symbolic(exec, &kh, n, n, vrp, vci, vrp, vci, IV(d_rpC, n + 1));
+    const size_t cnnz = kh.get_spadd_handle()->get_c_nnz();
+    int* d_ciC = nullptr;
+    double* d_vC = nullptr;
+    cudaMalloc(&d_ciC, sizeof(int) * (cnnz ? cnnz : 1));
+    cudaMalloc(&d_vC, sizeof(double) * (cnnz ? cnnz : 1));
+    ANUM::spadd_numeric(exec, &kh, n, n, 2.0, vrp, vci, vva, -0.5, vrp, vci, vva, CIV(d_rpC, n + 1), IV(d_ciC, cnnz), SV(d_vC, cnnz));
+    exec.fence();
+    std::vector<int> rpC(n + 1), ciC(cnnz);
+    std::vector<double> vC(cnnz);
+    cudaMemcpy(rpC.data(), d_rpC, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost);
+    cudaMemcpy(ciC.data(), d_ciC, sizeof(int) * cnnz, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vC.data(), d_vC, sizeof(double) * cnnz, cudaMemcpyDeviceToHost);
+    int f4 = (cnnz == ci.size()) ? 0 : 1;
+    for (int i = 0; i <= n && !f4; ++i)
+      if (rpC[i] != rp[i]) ++f4;
+    for (size_t q = 0; q < cnnz && !f4; ++q)
+      if (ciC[q] != ci[q] || vC[q] != 2.0 * va[q] + -0.5 * va[q]) ++f4;
+    auto ah = kh.get_spadd_handle();
+    if (!ah->is_symbolic_called() || !ah->is_numeric_called()) ++f4;
+    std::printf("spadd through SPADD_SYMBOLIC/NUMERIC<...,true,true> : c_nnz=%zu, %d mismatches\n", cnnz, f4);
+    failures += f4;
+    kh.destroy_spadd_handle();
+    cudaFree(d_rpC);
+    cudaFree(d_ciC);
+    cudaFree(d_vC);
   }
   std::printf(failures ? "SHIM DRIVER FAILED\n" : "SHIM DRIVER OK\n");
   return failures ? 1 : 0;

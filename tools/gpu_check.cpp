@@ -745,6 +745,22 @@ static void suite_crs_big() {
     std::reverse(U.v.begin() + U.rp[i], U.v.begin() + U.rp[i + 1]);
   }
   const double gb = 12.0 * A.nnz() / 1e9;
+  {  // warm-up: first-use costs (module load, stream-ordered pool growth) stay out of the timings below
+    auto W = gen_lap27<double>(8, 2);
+    Dev<int> rp(W.rp), ci(W.ci), rc((size_t)W.m + 1), trp((size_t)W.n + 1), tci((size_t)W.nnz());
+    Dev<double> v(W.v), tv((size_t)W.nnz());
+    SP(b200sp_sort_crs_f64_i32(nullptr, W.m, rp.p, ci.p, v.p));
+    SP(b200sp_transpose_f64_i32(nullptr, W.m, W.n, rp.p, ci.p, v.p, trp.p, tci.p, tv.p));
+    for (int sorted = 0; sorted <= 1; ++sorted) {
+      b200sp_spadd_plan* plan = nullptr;
+      int64_t c = 0;
+      SP(b200sp_spadd_plan_create(&plan, sorted, 1));
+      SP(b200sp_spadd_symbolic_i32(plan, nullptr, W.m, W.n, rp.p, ci.p, rp.p, ci.p, rc.p, &c));
+      b200sp_spadd_plan_destroy(plan, nullptr);
+    }
+    Dev<char> big((size_t)1 << 30);  // grow the default memory pool once
+    CK(cudaDeviceSynchronize());
+  }
   {
     Dev<int> rp(U.rp), ci(U.ci);
     Dev<double> v(U.v);
@@ -796,9 +812,13 @@ static void suite_crs_big() {
 // ------------------------------------------------------------------------------------------------
 // suite: spmm -- kernel variants of the rank-2 product (B200SP_SPMM_KERNEL) against the oracle + timing
 // ------------------------------------------------------------------------------------------------
+static int g_spmm_scale = 0;  // --spmm-scale N (default 18, 21 with --big; 23 = BASELINE.json config 3)
+
 static void suite_spmm() {
-  const int scale = g_big ? 21 : 18, k = 16;
+  const int scale = g_spmm_scale > 0 ? g_spmm_scale : (g_big ? 21 : 18), k = 16;
+  const bool full_check = scale <= 21;  // above: parity on sampled rows (the full-size case is covered at scale 21)
   int64_t nnz = 0;
+  double t0 = now_s();
   void* h = b200gen_rmat_build(scale, 16, 0.57, 0.19, 0.19, 23, &nnz);
   const int n = 1 << scale;
   std::vector<int> rp((size_t)n + 1), ci((size_t)nnz);
@@ -807,43 +827,86 @@ static void suite_spmm() {
   b200gen_fill_f32(nnz, v.data(), 0.f, 1.f, 3);
   b200gen_fill_f32((int64_t)X.size(), X.data(), -1.f, 1.f, 4);
   b200gen_fill_f32((int64_t)Y0.size(), Y0.data(), -1.f, 1.f, 5);
-  std::vector<float> Yref = Y0;
-  okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), v.data(), X.data(), k, 1, Yref.data(), k, 1, 1.5f, 0.5f, okk_num_threads());
-  // row-scaled tolerance: |alpha| sum |a||x| + |beta||y0|
-  std::vector<float> va(v), Xa(X), Ys(Y0);
-  for (auto& x : va) x = std::fabs(x);
-  for (auto& x : Xa) x = std::fabs(x);
-  for (auto& x : Ys) x = std::fabs(x);
-  okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), va.data(), Xa.data(), k, 1, Ys.data(), k, 1, 1.5f, 0.5f, okk_num_threads());
+  int maxrow = 0;
+  for (int i = 0; i < n; ++i) maxrow = std::max(maxrow, rp[i + 1] - rp[i]);
+  record("generate", true, "R-MAT scale %d: n=%d nnz=%lld longest row %d, %.1f s", scale, n, (long long)nnz, maxrow, now_s() - t0);
+  const float alpha = 1.5f, beta = 0.5f;
+  std::vector<float> Yref, Ys;
+  std::vector<int> sample;
+  if (full_check) {
+    Yref = Y0;
+    okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), v.data(), X.data(), k, 1, Yref.data(), k, 1, alpha, beta, okk_num_threads());
+    // row-scaled tolerance: |alpha| sum |a||x| + |beta||y0|
+    std::vector<float> va(v), Xa(X);
+    Ys = Y0;
+    for (auto& x : va) x = std::fabs(x);
+    for (auto& x : Xa) x = std::fabs(x);
+    for (auto& x : Ys) x = std::fabs(x);
+    okk_spmv_mv_f32(n, n, k, rp.data(), ci.data(), va.data(), Xa.data(), k, 1, Ys.data(), k, 1, alpha, beta, okk_num_threads());
+  } else {
+    Rng r(1);
+    for (int i = 0; i < 3000; ++i) sample.push_back(r.below(n));
+    // the longest rows (segment path) are part of the sample
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::partial_sort(order.begin(), order.begin() + 40, order.end(), [&](int a, int b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
+    sample.insert(sample.end(), order.begin(), order.begin() + 40);
+  }
+  auto check = [&](const std::vector<float>& got) -> double {
+    double worst = 0;
+    if (full_check) {
+      for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, (double)std::fabs(got[i] - Yref[i]) / std::max((double)Ys[i], 1e-30));
+      return worst;
+    }
+    for (int row : sample) {
+      for (int j = 0; j < k; ++j) {
+        double acc = 0, sc = 0;
+        for (int e = rp[row]; e < rp[row + 1]; ++e) {
+          const double t = (double)v[e] * (double)X[(size_t)ci[e] * k + j];
+          acc += t;
+          sc += std::fabs(t);
+        }
+        const double want = beta * (double)Y0[(size_t)row * k + j] + alpha * acc;
+        const double scale_r = std::fabs(alpha) * sc + std::fabs(beta * Y0[(size_t)row * k + j]);
+        worst = std::max(worst, std::fabs((double)got[(size_t)row * k + j] - want) / std::max(scale_r, 1e-30));
+      }
+    }
+    return worst;
+  };
   Dev<int> drp(rp), dci(ci);
   Dev<float> dv(v), dX(X), dY((size_t)n * k);
   const double balg = 8.0 * nnz + 4.0 * (n + 1) + 4.0 * (double)n * k * 3;
-  const char* kernels[] = {"row", "split", "tile", "tilev"};
-  for (const char* kn : kernels) {
-    setenv("B200SP_SPMM_KERNEL", kn, 1);
+  struct Var {
+    const char* kernel;
+    const char* lmax;
+  };
+  const Var vars[] = {{"split", nullptr}, {"tile", nullptr}, {"tilev", nullptr}, {"tilev", "64"}, {"tilev", "128"}, {"tilev", "512"}, {"row", nullptr}};
+  for (const Var& vr : vars) {
+    if (!strcmp(vr.kernel, "row") && scale > 21) continue;  // 23 ms at scale 21: not worth the slot
+    setenv("B200SP_SPMM_KERNEL", vr.kernel, 1);
+    if (vr.lmax) setenv("B200SP_SPMM_LMAX", vr.lmax, 1);
+    else unsetenv("B200SP_SPMM_LMAX");
     b200sp_spmv_plan* plan = nullptr;
     SP(b200sp_spmv_plan_create(&plan, 0));
     float best = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
+    for (int rep = 0; rep < 5; ++rep) {
       CK(cudaMemcpy(dY.p, Y0.data(), Y0.size() * sizeof(float), cudaMemcpyHostToDevice));
       Timer t;
       t.start();
-      SP(b200sp_spmm_f32_i32(plan, nullptr, 'N', n, n, nnz, k, 1.5f, drp.p, dci.p, dv.p, dX.p, k, 1, 0.5f, dY.p, k, 1));
+      SP(b200sp_spmm_f32_i32(plan, nullptr, 'N', n, n, nnz, k, alpha, drp.p, dci.p, dv.p, dX.p, k, 1, beta, dY.p, k, 1));
       const float ms = t.stop_ms();
       if (rep > 0) best = std::min(best, ms);
     }
-    auto got = dY.host();
-    double worst = 0;
-    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, (double)std::fabs(got[i] - Yref[i]) / std::max((double)Ys[i], 1e-30));
-    char nm[64];
-    snprintf(nm, sizeof(nm), "rmat%d_k16_f32/%s", scale, kn);
-    record(nm, worst <= 1e-4, "kernel=%s %.3f ms, %.0f GFLOP/s, %.0f GB/s algorithmic, max scaled err %.2e", b200sp_spmv_last_kernel(plan), best,
-           2.0 * nnz * k / (best * 1e-3) / 1e9, balg / (best * 1e-3) / 1e9, worst);
+    const double worst = check(dY.host());
+    char nm[96];
+    snprintf(nm, sizeof(nm), "rmat%d_k16_f32/%s%s%s", scale, vr.kernel, vr.lmax ? "_lmax" : "", vr.lmax ? vr.lmax : "");
+    record(nm, worst <= 1e-4, "kernel=%s %.3f ms, %.0f GFLOP/s, %.0f GB/s algorithmic, max scaled err %.2e (%s)", b200sp_spmv_last_kernel(plan), best,
+           2.0 * nnz * k / (best * 1e-3) / 1e9, balg / (best * 1e-3) / 1e9, worst, full_check ? "all rows" : "sampled + longest rows");
     b200sp_spmv_plan_destroy(plan, nullptr);
   }
   unsetenv("B200SP_SPMM_KERNEL");
+  unsetenv("B200SP_SPMM_LMAX");
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // suite: spmv_t -- transposed SpMV: atomics path vs the cached-transpose option, against the oracle
@@ -917,8 +980,9 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--suite") && i + 1 < argc) pick.push_back(argv[++i]);
     else if (!strcmp(argv[i], "--big")) g_big = true;
     else if (!strcmp(argv[i], "--dry")) g_dry = true;
+    else if (!strcmp(argv[i], "--spmm-scale") && i + 1 < argc) g_spmm_scale = atoi(argv[++i]);
     else {
-      fprintf(stderr, "usage: gpu_check [--out FILE] [--suite NAME]... [--big] [--dry]\n");
+      fprintf(stderr, "usage: gpu_check [--out FILE] [--suite NAME]... [--big] [--dry] [--spmm-scale N]\n");
       return 64;
     }
   }
