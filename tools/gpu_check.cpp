@@ -6,7 +6,7 @@
 // the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
 // faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
 //
-//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep
 //
 // Exit code: number of failed suites.
 #include <cuda_runtime.h>
@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cmath>
 #include <functional>
+#include <limits>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -965,6 +966,128 @@ static void suite_spmv_t() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: spmm_sweep -- the rank-2 kernels over column counts / scalar types / leading dimensions / beta
+// ------------------------------------------------------------------------------------------------
+static void ospmm(int m, int n, int k, const Csr<double>& A, const double* X, int64_t ldx, double* Y, int64_t ldy, double al, double be) {
+  okk_spmv_mv_f64(m, n, k, A.rp.data(), A.ci.data(), A.v.data(), X, ldx, 1, Y, ldy, 1, al, be, 1);
+}
+static void ospmm(int m, int n, int k, const Csr<float>& A, const float* X, int64_t ldx, float* Y, int64_t ldy, float al, float be) {
+  okk_spmv_mv_f32(m, n, k, A.rp.data(), A.ci.data(), A.v.data(), X, ldx, 1, Y, ldy, 1, al, be, 1);
+}
+static int gspmm(b200sp_spmv_plan* p, int m, int n, int64_t nnz, int k, double al, const int* rp, const int* ci, const double* v,
+                 const double* X, int64_t ldx, double be, double* Y, int64_t ldy) {
+  return b200sp_spmm_f64_i32(p, nullptr, 'N', m, n, nnz, k, al, rp, ci, v, X, ldx, 1, be, Y, ldy, 1);
+}
+static int gspmm(b200sp_spmv_plan* p, int m, int n, int64_t nnz, int k, float al, const int* rp, const int* ci, const float* v,
+                 const float* X, int64_t ldx, float be, float* Y, int64_t ldy) {
+  return b200sp_spmm_f32_i32(p, nullptr, 'N', m, n, nnz, k, al, rp, ci, v, X, ldx, 1, be, Y, ldy, 1);
+}
+
+template <typename S>
+static void spmm_sweep_matrix(const char* name, const Csr<S>& A) {
+  const int ks[] = {1, 2, 3, 4, 5, 8, 10, 16, 17, 30, 32, 33, 64};
+  Dev<int> rp(A.rp), ci(A.ci);
+  Dev<S> v(A.v);
+  Csr<S> Aabs = A;
+  for (auto& t : Aabs.v) t = std::fabs(t);
+  const double tol = sizeof(S) == 8 ? 1e-13 : 2e-5;
+  for (const char* kern : {"tilev", "tile", "split"}) {
+    setenv("B200SP_SPMM_KERNEL", kern, 1);
+    int bad = 0, runs = 0;
+    double worst = 0;
+    std::string last;
+    for (int k : ks) {
+      for (int pad = 0; pad <= 3; pad += 3) {
+        for (int bz = 0; bz <= 1; ++bz) {
+          const int64_t ldx = k + pad, ldy = k + (pad ? 1 : 0);
+          const S al = (S)1.25, be = bz ? (S)0 : (S)-0.5;
+          std::vector<S> X((size_t)A.n * ldx), Y0((size_t)A.m * ldy);
+          fill_vals(X, -1.0, 1.0, 100 + k);
+          fill_vals(Y0, -1.0, 1.0, 200 + k);
+          std::vector<S> Yref = Y0, Xa = X, Ys = Y0;
+          ospmm(A.m, A.n, k, A, X.data(), ldx, Yref.data(), ldy, al, be);
+          for (auto& t : Xa) t = std::fabs(t);
+          for (auto& t : Ys) t = std::fabs(t);
+          ospmm(A.m, A.n, k, Aabs, Xa.data(), ldx, Ys.data(), ldy, (S)std::fabs(al), (S)std::fabs(be));
+          std::vector<S> Yin = Y0;
+          if (bz)  // beta == 0 must overwrite NaN (Test_Sparse_spmv.hpp:394-408)
+            for (int r = 0; r < A.m; r += 19)
+              for (int j = 0; j < k; ++j) Yin[(size_t)r * ldy + j] = std::numeric_limits<S>::quiet_NaN();
+          Dev<S> dX(X), dY(Yin);
+          b200sp_spmv_plan* plan = nullptr;
+          SP(b200sp_spmv_plan_create(&plan, 0));
+          SP(gspmm(plan, A.m, A.n, A.nnz(), k, al, rp.p, ci.p, v.p, dX.p, ldx, be, dY.p, ldy));
+          CK(cudaDeviceSynchronize());
+          last = b200sp_spmv_last_kernel(plan);
+          b200sp_spmv_plan_destroy(plan, nullptr);
+          auto got = dY.host();
+          ++runs;
+          bool ok = true;
+          for (int r = 0; r < A.m && ok; ++r) {
+            for (int j = 0; j < (int)ldy; ++j) {
+              const size_t i = (size_t)r * ldy + j;
+              if (j >= k) {  // padding columns must stay untouched
+                if (memcmp(&got[i], &Yin[i], sizeof(S)) != 0) ok = false;
+                continue;
+              }
+              const double err = std::fabs((double)got[i] - (double)Yref[i]) / std::max((double)Ys[i], 1e-300);
+              if (!(err <= tol)) ok = false;
+              if (err == err) worst = std::max(worst, err);
+            }
+          }
+          if (!ok) {
+            ++bad;
+            fprintf(stderr, "    mismatch: %s kernel=%s k=%d ldx=%lld beta=%g\n", name, last.c_str(), k, (long long)ldx, (double)be);
+          }
+        }
+      }
+    }
+    char nm[128];
+    snprintf(nm, sizeof(nm), "%s/%s", name, kern);
+    record(nm, bad == 0, "%d runs (13 column counts x 2 leading dimensions x beta in {0, -0.5}), %d bad, max scaled err %.2e, last kernel %s",
+           runs, bad, worst, last.c_str());
+  }
+  unsetenv("B200SP_SPMM_KERNEL");
+}
+
+static void suite_spmm_sweep() {
+  {
+    auto A = gen_kk<double>(1000, 963, 20000, 5, 100, 3);
+    for (auto& t : A.v) t = (t - 25.0) / 25.0;
+    spmm_sweep_matrix("kk_1000x963_f64", A);
+  }
+  {
+    auto A = gen_kk<float>(5000, 4963, 150000, 20, 400, 4);
+    for (auto& t : A.v) t = (t - 25.0f) / 25.0f;
+    spmm_sweep_matrix("kk_5000x4963_f32", A);
+  }
+  {
+    // power-law rows incl. rows beyond the tile row limit (segment kernel, multi-segment atomics)
+    int64_t nnz = 0;
+    void* h = b200gen_rmat_build(13, 16, 0.57, 0.19, 0.19, 23, &nnz);
+    Csr<float> A;
+    A.m = A.n = 1 << 13;
+    A.rp.resize((size_t)A.m + 1);
+    A.ci.resize((size_t)nnz);
+    b200gen_rmat_emit(h, A.rp.data(), A.ci.data());
+    A.v.resize((size_t)nnz);
+    fill_vals(A.v, -1.0, 1.0, 9);
+    spmm_sweep_matrix("rmat13_f32", A);
+  }
+  {
+    // very long rows (several segments each, combined with atomics), rows just around the tile row limit, empty rows
+    Rng r(31);
+    std::vector<int> lens(6000);
+    for (auto& l : lens) l = r.below(25);
+    const int special[] = {10000, 0, 0, 4097, 2049, 2048, 300, 257, 256, 255, 0, 1};
+    for (size_t i = 0; i < sizeof(special) / sizeof(int); ++i) lens[100 + i] = special[i];
+    auto B = gen_rows<double>(lens, 5000, false, false, 31);
+    for (auto& t : B.v) t = (t - 25.0) / 25.0;
+    spmm_sweep_matrix("long_rows_6000x5000_f64", B);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct Suite {
   const char* name;
   std::function<void()> fn;
@@ -973,7 +1096,8 @@ struct Suite {
 
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
-                            {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60}};
+                            {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
+                            {"spmm_sweep", suite_spmm_sweep, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
