@@ -10,8 +10,8 @@ import torch
 from crs_cases import MERGE_CASES, random_matrix, spadd_dense_check
 from helpers import kk_matrix
 
-# promoted to `gpu` once tools/gpu_check's `crs` suite has passed on a B200 (profiles/)
-pytestmark = pytest.mark.gpu_next
+# first B200 run: profiles/r01_gpu_check_a.log (C ABI vs oracle) and profiles/r01_pytest_b.log (this file, 58 passed)
+pytestmark = pytest.mark.gpu
 
 
 def dev_mat(sp, dev, rp, ci, v, ncols):
