@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tile_ring.cuh"
 #include <algorithm>
+#include <atomic>
 #include <stdlib.h>
 
 struct b200sp_spmv_plan;  // defined in spmv.cu
@@ -689,18 +690,20 @@ static int launch_split(b200sp_spmv_plan* p, cudaStream_t st, int m, int k, int6
 int plan_analyse_mm(b200sp_spmv_plan* p, cudaStream_t st, int cap, int lmax, int seg, int m, int64_t nnz, const int* row_ptr,
                     MMTileView* out);
 
-template <typename S, int VW, int KTL>
+template <typename S, int VW, int KTL, int NW, int STAGES, int CAP, int UNR>
 static int launch_mm_tile_k(cudaStream_t st, const MMTileView& tv, int m, int k, int64_t nnz, const int* row_ptr,
                             const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
-  constexpr int NW = 16, STAGES = 4, CAP = 2048;
-  constexpr int UNR = (VW == 1) ? 8 : 4;
   using Ring = TileRing<S, CAP, STAGES>;
   auto kern = spmm_tile_kernel<S, VW, KTL, NW, STAGES, CAP, UNR>;
   const size_t smem = sizeof(Ring) + 128;
-  B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NW + 1) * 32, smem));
-  if (occ < 1) occ = 1;
+  static std::atomic<int> occ_cached{0};  // per instantiation: attribute set + occupancy queried once
+  int occ = occ_cached.load(std::memory_order_acquire);
+  if (occ == 0) {
+    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NW + 1) * 32, smem));
+    if (occ < 1) occ = 1;
+    occ_cached.store(occ, std::memory_order_release);
+  }
   int grid = std::min(tv.n_tiles, sm_count() * occ);
   if (grid < 1) grid = 1;
   kern<<<grid, (NW + 1) * 32, smem, st>>>(m, k, nnz, tv.n_tiles, tv.LMAX, tv.tiles, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
@@ -708,14 +711,35 @@ static int launch_mm_tile_k(cudaStream_t st, const MMTileView& tv, int m, int k,
   return B200SP_OK;
 }
 
+// ring / unroll configurations of the tile kernel.  0 is the default; 1-3 exist for the 16-byte-load path only
+// (B200SP_SPMM_CFG, tuning sweeps): 1 = small ring (8 consumer warps, 1024-entry stages: 5 CTAs per SM for fp32),
+// 2 = default ring with twice the gathers in flight per lane, 3 = small ring with 16 consumer warps.
+template <typename S, int VW, int KTL>
+static int launch_mm_tile_cfg(int cfg, cudaStream_t st, const MMTileView& tv, int m, int k, int64_t nnz, const int* row_ptr,
+                              const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  if constexpr (VW > 1) {
+    switch (cfg) {
+      case 1: return launch_mm_tile_k<S, VW, KTL, 8, 4, 1024, 4>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+      case 2: return launch_mm_tile_k<S, VW, KTL, 16, 4, 2048, 8>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+      case 3: return launch_mm_tile_k<S, VW, KTL, 16, 3, 1024, 4>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+      default: break;
+    }
+  }
+  return launch_mm_tile_k<S, VW, KTL, 16, 4, 2048, (VW == 1 ? 8 : 4)>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+}
+
 template <typename S>
 static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
                           const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
-  constexpr int CAP = 2048, SEG = 2048;
-  int LMAX = 256;  // rows longer than this leave the tiles for the segment kernel (B200SP_SPMM_LMAX: 16..1024)
+  constexpr int SEG = 2048;
+  int cfg = 0;
+  if (const char* e = getenv("B200SP_SPMM_CFG")) cfg = atoi(e);
+  if (!vec || cfg < 0 || cfg > 3) cfg = 0;
+  const int CAP = (cfg == 1 || cfg == 3) ? 1024 : 2048;
+  int LMAX = 256;  // rows longer than this leave the tiles for the segment kernel (B200SP_SPMM_LMAX: 16..512)
   if (const char* e = getenv("B200SP_SPMM_LMAX")) {
     const int v = atoi(e);
-    if (v >= 16 && v <= 1024) LMAX = v;
+    if (v >= 16 && v <= 512) LMAX = v;
   }
   MMTileView tv;
   int rc = plan_analyse_mm(p, st, CAP, LMAX, SEG, m, nnz, row_ptr, &tv);
@@ -726,7 +750,7 @@ static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m,
   while (KTL < lanes_needed && KTL < 32) KTL <<= 1;
 #define B200SP_MMT(V, L)                                                                                                    \
   case L:                                                                                                                   \
-    rc = launch_mm_tile_k<S, V, L>(st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);                 \
+    rc = launch_mm_tile_cfg<S, V, L>(cfg, st, tv, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);          \
     break;
   if (vec) {
     switch (KTL) {

@@ -880,13 +880,18 @@ static void suite_spmm() {
   struct Var {
     const char* kernel;
     const char* lmax;
+    const char* cfg;
   };
-  const Var vars[] = {{"split", nullptr}, {"tile", nullptr}, {"tilev", nullptr}, {"tilev", "64"}, {"tilev", "128"}, {"tilev", "512"}, {"row", nullptr}};
+  const Var vars[] = {{"split", nullptr, nullptr}, {"tile", nullptr, nullptr},  {"tilev", nullptr, nullptr}, {"tilev", "64", nullptr},
+                      {"tilev", "128", nullptr},   {"tilev", "512", nullptr},   {"tilev", nullptr, "1"},     {"tilev", nullptr, "2"},
+                      {"tilev", nullptr, "3"},     {"tilev", "128", "1"},       {"tilev", "128", "2"},       {"row", nullptr, nullptr}};
   for (const Var& vr : vars) {
     if (!strcmp(vr.kernel, "row") && scale > 21) continue;  // 23 ms at scale 21: not worth the slot
     setenv("B200SP_SPMM_KERNEL", vr.kernel, 1);
     if (vr.lmax) setenv("B200SP_SPMM_LMAX", vr.lmax, 1);
     else unsetenv("B200SP_SPMM_LMAX");
+    if (vr.cfg) setenv("B200SP_SPMM_CFG", vr.cfg, 1);
+    else unsetenv("B200SP_SPMM_CFG");
     b200sp_spmv_plan* plan = nullptr;
     SP(b200sp_spmv_plan_create(&plan, 0));
     float best = 1e30f;
@@ -900,13 +905,15 @@ static void suite_spmm() {
     }
     const double worst = check(dY.host());
     char nm[96];
-    snprintf(nm, sizeof(nm), "rmat%d_k16_f32/%s%s%s", scale, vr.kernel, vr.lmax ? "_lmax" : "", vr.lmax ? vr.lmax : "");
+    snprintf(nm, sizeof(nm), "rmat%d_k16_f32/%s%s%s%s%s", scale, vr.kernel, vr.lmax ? "_lmax" : "", vr.lmax ? vr.lmax : "", vr.cfg ? "_cfg" : "",
+             vr.cfg ? vr.cfg : "");
     record(nm, worst <= 1e-4, "kernel=%s %.3f ms, %.0f GFLOP/s, %.0f GB/s algorithmic, max scaled err %.2e (%s)", b200sp_spmv_last_kernel(plan), best,
            2.0 * nnz * k / (best * 1e-3) / 1e9, balg / (best * 1e-3) / 1e9, worst, full_check ? "all rows" : "sampled + longest rows");
     b200sp_spmv_plan_destroy(plan, nullptr);
   }
   unsetenv("B200SP_SPMM_KERNEL");
   unsetenv("B200SP_SPMM_LMAX");
+  unsetenv("B200SP_SPMM_CFG");
 }
 
 // ------------------------------------------------------------------------------------------------
