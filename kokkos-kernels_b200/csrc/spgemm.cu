@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
 //    16-byte table initialisation;
 //  * rows whose product count equals nnz(C_i) have no duplicate column: their values are placed
 //    with plain stores (no shared-memory atomics, no zero fill).
-// Selected with B200SP_SPGEMM_NUMERIC=2|3 (3 = half-size key tables, load factor <= 0.5).
+// Selected with B200SP_SPGEMM_NUMERIC=2|3|4 (3 = half-size key tables, load factor <= 0.5; 4 = no parking:
+// only the cheaper table passes, same footprint as variant 1).
 // ---------------------------------------------------------------------------
 template <int G, typename S>
 struct Walk2Smem {
@@ -555,7 +556,7 @@ struct Num2Layout {
   static_assert(TOT % 32 == 0 && VCAP % 4 == 0 && PCAP % 4 == 0, "table sizes keep 16-byte alignment");
 };
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     num2_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                 const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
@@ -667,8 +668,9 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     }
   }
   gsync();
-  // ---- column indices leave in sorted order
-  if (emit) {
+  // ---- column indices leave in sorted order (EMIT2: written from the value pass instead, one scattered 4-byte
+  //      store per product -- no scan over the whole key table)
+  if (emit && !EMIT2) {
     const unsigned lt = (1u << lane) - 1u;
     for (int w = wg; w < WORDS; w += NWG) {
       const int key = keys[w * 32 + lane];
@@ -678,10 +680,11 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   // ---- values by output position
   if (PCAP > 0 && staged) {
     if (emit) {
-      if (dupfree) {
-        for (int id = tg; id < np; id += G) vals[rank_of(pcol[id])] = pval[id];
-      } else {
-        for (int id = tg; id < np; id += G) smem_add(&vals[rank_of(pcol[id])], pval[id]);
+      for (int id = tg; id < np; id += G) {
+        const int c = pcol[id];
+        const int pos = rank_of(c);
+        if (EMIT2) ciC[cbase + pos] = c;
+        if (dupfree) vals[pos] = pval[id]; else smem_add(&vals[pos], pval[id]);
       }
     }
   } else {
@@ -689,6 +692,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     const int b0 = emit ? a0 : 0, b1 = emit ? a1 : 0;
     walk_products2<G, S>(tg, lb, b0, b1, true, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int) {
       const int pos = rank_of(c);
+      if (EMIT2) ciC[cbase + pos] = c;
       if (dupfree) vals[pos] = v; else smem_add(&vals[pos], v);
     });
   }
@@ -804,7 +808,7 @@ struct b200sp_spgemm_plan {
   // device state kept for numeric
   int *cmin = nullptr, *cmax = nullptr;
   int* flops = nullptr;     // products per row of A*B (numeric variant 2 parks them in shared memory)
-  int numeric_variant = 1;  // 1: two-walk num_hash_kernel, 2/3: staged num2_kernel (B200SP_SPGEMM_NUMERIC)
+  int numeric_variant = 1;  // 1: two-walk num_hash_kernel, 2/3/4: num2_kernel flavours (B200SP_SPGEMM_NUMERIC)
   int* num_rows = nullptr;  // rows grouped by numeric bin
   int num_off[kNumBins + 1] = {0};
   int *fb_rows = nullptr, *fb_count = nullptr;
@@ -877,7 +881,7 @@ static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int
   return B200SP_OK;
 }
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false>
 static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
                        const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
   const int nrows = p->num_off[bin + 1] - p->num_off[bin];
@@ -886,7 +890,7 @@ static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const in
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = L::PER_AL * RPC;
-  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP>;
+  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
                                                       rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->flops, p->fb_rows,
@@ -922,7 +926,21 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   int rc;
   int variant = p->numeric_variant;
   if (const char* e = getenv("B200SP_SPGEMM_NUMERIC")) variant = atoi(e);
-  if (variant == 2 || variant == 3) {
+  if (variant == 5) {  // variant 4 + column indices written from the value pass (no scan of the key table for them)
+#define NUM5(B, G, KS, PAD, VCAP)                                                                                 \
+  if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    NUM5(0, 32, 256, 32, 64)
+    NUM5(1, 32, 1024, 64, 256)
+    NUM5(2, 128, 4096, 128, 1024)
+    NUM5(3, 256, 16384, 256, 4096)
+    NUM5(4, 512, 32768, 512, 8192)
+#undef NUM5
+    num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                    ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+  }
+  if (variant >= 2 && variant <= 4) {
     // <S, G, key slots, pad, max nnz(C_i) of the bin, parked products>
 #define NUM2(B, G, KS, PAD, VCAP, PCAP)                                                                          \
   if ((rc = launch_num2<S, G, KS, PAD, VCAP, PCAP>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
@@ -932,12 +950,19 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
       NUM2(2, 128, 4096, 128, 1024, 1024)
       NUM2(3, 256, 16384, 256, 4096, 2048)
       NUM2(4, 512, 32768, 512, 8192, 0)
-    } else {  // >= 2 x nnz (load <= 0.5): half the table to initialise and scan, longer probe chains
+    } else if (variant == 3) {  // >= 2 x nnz (load <= 0.5): half the table to initialise and scan, longer probe chains
       NUM2(0, 32, 128, 32, 64, 128)
       NUM2(1, 64, 512, 64, 256, 512)
       NUM2(2, 128, 2048, 128, 1024, 1024)
       NUM2(3, 256, 8192, 256, 4096, 2048)
       NUM2(4, 512, 16384, 512, 8192, 0)
+    } else {  // 4: variant 2's cheaper table passes (16-byte init, ballot words) WITHOUT parking the products:
+              // two walks like variant 1 and the same shared-memory footprint (same resident CTAs per SM)
+      NUM2(0, 32, 256, 32, 64, 0)
+      NUM2(1, 32, 1024, 64, 256, 0)
+      NUM2(2, 128, 4096, 128, 1024, 0)
+      NUM2(3, 256, 16384, 256, 4096, 0)
+      NUM2(4, 512, 32768, 512, 8192, 0)
     }
 #undef NUM2
     num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
