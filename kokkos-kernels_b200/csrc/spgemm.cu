@@ -199,7 +199,7 @@ __device__ __forceinline__ unsigned hash_mul(int c, int log2slots) {
   return ((unsigned)c * 0x9E3779B1u) >> (32 - log2slots);
 }
 
-template <int G, int LOG2SLOTS>
+template <int G, int LOG2SLOTS, bool V2 = false>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     sym_hash_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                     const int* __restrict__ ciA, const int* __restrict__ rpB, const int* __restrict__ ciB,
@@ -207,14 +207,19 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   constexpr int SLOTS = 1 << LOG2SLOTS;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
-  extern __shared__ int sm_keys[];  // RPC * SLOTS
+  extern __shared__ __align__(16) int sm_keys[];  // RPC * SLOTS
   __shared__ int sm_cnt[RPC];
   __shared__ WalkSmem<G, float> sm_walk[RPC];
   const int g = threadIdx.x / G, tg = threadIdx.x % G;
   int* keys = sm_keys + g * SLOTS;
   const int ridx = blockIdx.x * RPC + g;
   const bool active = ridx < nrows_bin;
-  for (int s = tg; s < SLOTS; s += G) keys[s] = EMPTY;
+  if (V2) {  // variant 2: 16-byte stores
+    int4* k4 = reinterpret_cast<int4*>(keys);
+    for (int s = tg; s < SLOTS / 4; s += G) k4[s] = make_int4(EMPTY, EMPTY, EMPTY, EMPTY);
+  } else {
+    for (int s = tg; s < SLOTS; s += G) keys[s] = EMPTY;
+  }
   if (tg == 0) sm_cnt[g] = 0;
   if (G <= 32) __syncwarp(); else __syncthreads();
   int mine = 0;
@@ -850,14 +855,14 @@ static int bin_rows(cudaStream_t st, int m, const int* key, const BinSpec& spec,
   return B200SP_OK;
 }
 
-template <int G, int LOG2SLOTS>
+template <int G, int LOG2SLOTS, bool V2 = false>
 static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const int* rpA, const int* ciA,
                       const int* rpB, const int* ciB, int* row_nnz) {
   if (nrows <= 0) return B200SP_OK;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = sizeof(int) * (size_t)RPC * ((size_t)1 << LOG2SLOTS);
-  auto kern = sym_hash_kernel<G, LOG2SLOTS>;
+  auto kern = sym_hash_kernel<G, LOG2SLOTS, V2>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, std::min(lb, 32), rpA, ciA, rpB, ciB, row_nnz);
   B200SP_LAUNCH_CHECK();
@@ -1088,29 +1093,56 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   B200SP_LAUNCH_CHECK();
 
   // ---- bin by flop bound, count distinct columns per row
+  // B200SP_SPGEMM_SYMBOLIC=2 (opt-in): tables of 2x the flop bound instead of up to 4x (a bin per power of
+  // two: half the shared memory and half the init per row for e.g. config 4's 1024-product rows), 16-byte init
+  int sym_variant = 1;
+  if (const char* e = getenv("B200SP_SPGEMM_SYMBOLIC")) sym_variant = atoi(e);
   BinSpec sspec;
-  sspec.nb = kSymBins;
-  for (int b = 0; b < kSymBins - 1; ++b) sspec.thr[b] = kSymThr[b];
-  int soff[kSymBins + 1];
-  int rc = bin_rows(st, m, flops, sspec, d_counts, sym_rows, soff);
-  if (rc) return rc;
+  int soff[MAXBINS + 1];
+  int rc;
   const int lb = p->lb;
+  int big_bin;
+  if (sym_variant == 2) {
+    static const int thr2[] = {128, 512, 1024, 2048, 4096, 8192, 16384};
+    sspec.nb = 8;
+    for (int b = 0; b < 7; ++b) sspec.thr[b] = thr2[b];
+    rc = bin_rows(st, m, flops, sspec, d_counts, sym_rows, soff);
+    if (rc) return rc;
+#define SYM_BIN2(B, G, LG)                                                                                              \
+  if ((rc = launch_sym<G, LG, true>(st, soff[B + 1] - soff[B], sym_rows + soff[B], lb, rpA, ciA, rpB, ciB, row_nnz))) \
+    return rc;
+    SYM_BIN2(0, 32, 8)     // f <= 128   -> 256 slots, warp per row
+    SYM_BIN2(1, 32, 10)    // f <= 512   -> 1024 slots
+    SYM_BIN2(2, 128, 11)   // f <= 1024  -> 2048 slots
+    SYM_BIN2(3, 128, 12)   // f <= 2048  -> 4096 slots
+    SYM_BIN2(4, 256, 13)   // f <= 4096  -> 8192 slots
+    SYM_BIN2(5, 256, 14)   // f <= 8192  -> 16384 slots
+    SYM_BIN2(6, 512, 15)   // f <= 16384 -> 32768 slots
+#undef SYM_BIN2
+    big_bin = 7;
+  } else {
+    sspec.nb = kSymBins;
+    for (int b = 0; b < kSymBins - 1; ++b) sspec.thr[b] = kSymThr[b];
+    rc = bin_rows(st, m, flops, sspec, d_counts, sym_rows, soff);
+    if (rc) return rc;
 #define SYM_BIN(B, G, LG)                                                                                          \
   if ((rc = launch_sym<G, LG>(st, soff[B + 1] - soff[B], sym_rows + soff[B], lb, rpA, ciA, rpB, ciB, row_nnz))) \
     return rc;
-  SYM_BIN(0, 32, 8)     // f <= 128   -> 256 slots, warp per row
-  SYM_BIN(1, 32, 10)    // f <= 512   -> 1024 slots
-  SYM_BIN(2, 128, 12)   // f <= 2048  -> 4096 slots
-  SYM_BIN(3, 256, 14)   // f <= 8192  -> 16384 slots (64 KB)
-  SYM_BIN(4, 512, 15)   // f <= 16384 -> 32768 slots (128 KB)
+    SYM_BIN(0, 32, 8)     // f <= 128   -> 256 slots, warp per row
+    SYM_BIN(1, 32, 10)    // f <= 512   -> 1024 slots
+    SYM_BIN(2, 128, 12)   // f <= 2048  -> 4096 slots
+    SYM_BIN(3, 256, 14)   // f <= 8192  -> 16384 slots (64 KB)
+    SYM_BIN(4, 512, 15)   // f <= 16384 -> 32768 slots (128 KB)
 #undef SYM_BIN
+    big_bin = kSymBins - 1;
+  }
   {
-    const int nbig = soff[kSymBins] - soff[kSymBins - 1];
+    const int nbig = soff[big_bin + 1] - soff[big_bin];
     if (nbig > 0) {
       const int ctas = std::min(nbig, sm_count());
       unsigned* bitmaps;
       B200SP_CUDA_TRY(tmp.alloc(&bitmaps, (size_t)ctas * ((k + 31) / 32)));
-      sym_bitmap_kernel<<<ctas, 256, 0, st>>>(nbig, sym_rows + soff[kSymBins - 1], k, bitmaps, rpA, ciA, rpB, ciB, row_nnz);
+      sym_bitmap_kernel<<<ctas, 256, 0, st>>>(nbig, sym_rows + soff[big_bin], k, bitmaps, rpA, ciA, rpB, ciB, row_nnz);
       B200SP_LAUNCH_CHECK();
     }
   }

@@ -386,6 +386,20 @@ static void spgemm_case(const char* name, const Csr<S>& A, const Csr<S>& B) {
   }
   unsetenv("B200SP_SPGEMM_NUMERIC");
   b200sp_spgemm_plan_destroy(plan, nullptr);
+  {  // symbolic variant 2 (finer bins, tables of 2x the flop bound): same row map
+    setenv("B200SP_SPGEMM_SYMBOLIC", "2", 1);
+    b200sp_spgemm_plan* p2 = nullptr;
+    SP(b200sp_spgemm_plan_create(&p2));
+    Dev<int> rpC2((size_t)m + 1);
+    rpC2.fill_bytes(0x7b);
+    int64_t c2 = -1;
+    int cm2 = -1;
+    SP(b200sp_spgemm_symbolic_i32(p2, nullptr, m, n, k, rpA.p, ciA.p, rpB.p, ciB.p, rpC2.p, &c2, &cm2));
+    snprintf(nm, sizeof(nm), "%s/symbolic_v2", name);
+    record(nm, c2 == onnz && cm2 == c_max && count_diff(rpC2.host(), o.rp) == 0, "c_nnz=%lld c_max=%d", (long long)c2, cm2);
+    b200sp_spgemm_plan_destroy(p2, nullptr);
+    unsetenv("B200SP_SPGEMM_SYMBOLIC");
+  }
 }
 
 static void suite_spgemm() {
@@ -458,6 +472,27 @@ static void suite_spgemm_c4() {
   SP(b200sp_spgemm_symbolic_i32(plan, nullptr, n, n, n, rp.p, ci.p, rp.p, ci.p, rpC.p, &c_nnz, &c_max));
   const double sym_s = now_s() - t0;
   record("symbolic", c_nnz > 0, "c_nnz=%lld c_max=%d wall %.2f ms (first call, includes allocation)", (long long)c_nnz, c_max, sym_s * 1e3);
+  for (int sv = 1; sv <= 2; ++sv) {  // warm timings of the symbolic phase (wall clock: it synchronises by nature)
+    char ev[8];
+    snprintf(ev, sizeof(ev), "%d", sv);
+    setenv("B200SP_SPGEMM_SYMBOLIC", ev, 1);
+    double best = 1e30;
+    int64_t cn = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      b200sp_spgemm_plan* p2 = nullptr;
+      SP(b200sp_spgemm_plan_create(&p2));
+      Dev<int> rpC2((size_t)n + 1);
+      CK(cudaDeviceSynchronize());
+      const double t1 = now_s();
+      SP(b200sp_spgemm_symbolic_i32(p2, nullptr, n, n, n, rp.p, ci.p, rp.p, ci.p, rpC2.p, &cn, &c_max));
+      best = std::min(best, now_s() - t1);
+      b200sp_spgemm_plan_destroy(p2, nullptr);
+    }
+    char nm[64];
+    snprintf(nm, sizeof(nm), "symbolic_v%d_warm", sv);
+    record(nm, cn == c_nnz, "%.3f ms best of 3 (wall clock incl. its host synchronisations), c_nnz=%lld", best * 1e3, (long long)cn);
+  }
+  unsetenv("B200SP_SPGEMM_SYMBOLIC");
   Dev<int> ciC((size_t)c_nnz);
   Dev<double> vC((size_t)c_nnz);
   const double flops = (double)n * deg * deg;
