@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--collective", default="pipelined", choices=["pipelined", "fused", "multicast", "nccl"],
+    ap.add_argument("--collective", default="pipelined", choices=["pipelined", "fused", "multicast", "pipelined_mc", "nccl"],
                     help="N>1: all-gather of y pipelined behind the compute (copy-engine pushes over NVLink), "
                          "fused into the SpMV kernel (P2P stores), fused with one NVSwitch-multicast store per value, "
                          "or NCCL after it")

@@ -122,6 +122,13 @@ int b200sp_peer_push_async(void* compute_stream, void* const* comm_streams, int 
                            const void* src, int64_t bytes);
 int b200sp_peer_join(void* compute_stream, void* const* comm_streams, int n);
 
+/* Copy `bytes` (multiple of 8) from src to the NVSwitch multicast mapping `mc_dst` of a symmetric buffer with
+ * 16-byte stores from `ctas` CTAs (default 16) on `stream`: the switch replicates every store into all
+ * participating GPUs' copies, so a row block's y leaves its GPU once instead of once per peer.  src and mc_dst
+ * must share their 16-byte phase.  The SM-driven counterpart of b200sp_peer_push_async for the pipelined
+ * row-block SpMV (multigpu.py mode "pipelined_mc"); no reference counterpart. */
+int b200sp_multicast_push(void* stream, const void* src, void* mc_dst, int64_t bytes, int ctas);
+
 /* ---- SpMV rank-2 (multivector): Y = beta*Y + alpha*op(A)*X, k columns --- */
 /* Replaces SPMV_MV<Kokkos::Cuda,...,false,true>::spmv_mv -> cusparseSpMM
  * (sparse/tpls/KokkosSparse_spmv_mv_tpl_spec_decl.hpp:97-225).

@@ -433,6 +433,24 @@ static const TileCfg kCfgs[] = {
 };
 static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
+// ---------------------------------------------------------------------------
+// Push a finished piece of y to the NVSwitch multicast mapping of the next-x buffer with 16-byte stores
+// (on sm_100 a plain st.global to a multicast address IS multimem.st: the switch replicates it into every
+// GPU's copy).  A few CTAs are enough (80 MB per step); they co-reside with the persistent SpMV CTAs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) multicast_push_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  // head: up to one element so that both pointers are 16-byte aligned (they share their 8-byte phase)
+  int64_t head = (((uintptr_t)dst & 15u) != 0 && n > 0) ? 1 : 0;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (head && tid == 0) dst[0] = src[0];
+  const int64_t n2 = (n - head) >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(src + head);
+  double2* d2 = reinterpret_cast<double2*>(dst + head);
+  for (int64_t i = tid; i < n2; i += nthreads) d2[i] = s2[i];
+  if (((n - head) & 1) && tid == 0) dst[n - 1] = src[n - 1];
+}
+
 }  // namespace b200sp
 
 using namespace b200sp;
@@ -1095,6 +1113,18 @@ int b200sp_peer_join(void* compute_stream, void* const* comm_streams, int n) {
     B200SP_CUDA_TRY(cudaEventRecord(ev, (cudaStream_t)comm_streams[d]));
     B200SP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)compute_stream, ev, 0));
   }
+  return B200SP_OK;
+}
+
+int b200sp_multicast_push(void* stream, const void* src, void* mc_dst, int64_t bytes, int ctas) {
+  B200SP_REQUIRE(bytes >= 0 && (bytes % 8) == 0, "multicast_push: byte count must be a non-negative multiple of 8");
+  B200SP_REQUIRE(bytes == 0 || (src && mc_dst), "multicast_push: null pointer");
+  B200SP_REQUIRE((((uintptr_t)src ^ (uintptr_t)mc_dst) & 15u) == 0 && ((uintptr_t)src & 7u) == 0,
+                 "multicast_push: source and destination must be 8-byte aligned with the same 16-byte phase");
+  if (bytes == 0) return B200SP_OK;
+  if (ctas <= 0) ctas = 16;
+  multicast_push_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>((const double*)src, (double*)mc_dst, bytes / 8);
+  B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
 

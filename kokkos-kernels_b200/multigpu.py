@@ -13,6 +13,9 @@ b200sp_spmv_scatter_f64_i32), "multicast" (as fused, but ONE store per y value t
 address of the symmetric buffer -- on sm_100 multimem.st is a plain st.global to a multicast mapping, the
 switch replicates it into all 8 copies, so every GPU sends its 80 MB once instead of 7 times; falls back
 to "fused" when the symmetric-memory handle has no multicast pointer; first measurements: round 2),
+"pipelined_mc" (pieces like "pipelined", but each finished piece is pushed ONCE to the multicast address by a
+small SM kernel with 16-byte stores, b200sp_multicast_push, on one communication stream; falls back to
+"pipelined" without a multicast pointer),
 "nccl" (SpMV then all_gather_into_tensor)."""
 import ctypes as C
 
@@ -32,7 +35,7 @@ class RowBlockSpMV:
         self.ci_d = torch.from_numpy(ci).to(device)
         self.va_d = torch.from_numpy(va).to(device)
         self.symm = None
-        if mode in ("pipelined", "fused", "multicast"):
+        if mode in ("pipelined", "fused", "multicast", "pipelined_mc"):
             import torch.distributed._symmetric_memory as symm_mem
 
             self.x_next = symm_mem.empty(n_total, dtype=torch.float64, device=device)
@@ -41,16 +44,19 @@ class RowBlockSpMV:
             self.mc_ptr = int(getattr(self.symm, "multicast_ptr", 0) or 0)
             if mode == "multicast" and self.mc_ptr == 0:
                 self.mode = mode = "fused"  # no NVLS multicast mapping on this box
+            if mode == "pipelined_mc" and self.mc_ptr == 0:
+                self.mode = mode = "pipelined"
         else:
             self.x_next = torch.empty(n_total, dtype=torch.float64, device=device)
         self.y = self.x_next[r0:r1]
         # chunk boundaries on rows whose first entry is 16-byte aligned in col_idx / vals (TMA path)
-        if mode != "pipelined":
+        if mode not in ("pipelined", "pipelined_mc"):
             chunks = 1
         bounds = [0]
         for c in range(1, chunks):
             r = (nrows * c) // chunks
-            while r < nrows and rp[r] % 4 != 0:
+            # TMA path: first entry 16-byte aligned; pipelined_mc: the piece of y starts on a 16-byte boundary too
+            while r < nrows and (rp[r] % 4 != 0 or (mode == "pipelined_mc" and (r0 + r) % 2 != 0)):
                 r += 1
             if r > bounds[-1] and r < nrows:
                 bounds.append(r)
@@ -64,7 +70,7 @@ class RowBlockSpMV:
             h.tune(*tune)
             yv = self.y[c0:c1]
             dsts = []
-            if self.symm is not None and mode == "multicast":
+            if self.symm is not None and mode in ("multicast", "pipelined_mc"):
                 dsts = [self.mc_ptr + (r0 + c0) * 8]  # one store, replicated by the switch (incl. this rank's copy)
             elif self.symm is not None:
                 dsts = [self.peer_ptrs[q] + (r0 + c0) * 8 for q in range(self.world) if q != self.rank]
@@ -91,6 +97,17 @@ class RowBlockSpMV:
         if self.mode in ("fused", "multicast"):
             A, h, yv, dsts, arr, ev = self.pieces[0]
             sp.spmv_scatter(h, 1.0, A, x, yv, dsts)
+            self.symm.barrier(channel=0)
+        elif self.mode == "pipelined_mc":
+            cs = C.c_void_p(cur.cuda_stream)
+            comm = self.comm[0]
+            for A, h, yv, dsts, arr, ev in self.pieces:
+                sp.spmv(h, "N", 1.0, A, x, 0.0, yv)
+                ev.record(cur)
+                comm.wait_event(ev)
+                _lib.check(lib.b200sp_multicast_push(C.c_void_p(comm.cuda_stream), C.c_void_p(yv.data_ptr()),
+                                                     C.c_void_p(dsts[0]), yv.numel() * 8, 16))
+            _lib.check(lib.b200sp_peer_join(cs, self.comm_arr, 1))
             self.symm.barrier(channel=0)
         elif self.mode == "pipelined":
             cs = C.c_void_p(cur.cuda_stream)
