@@ -248,3 +248,25 @@ def test_hostvec_pipeline(cuda, oracle):
         got = ys[k].numpy()
         assert not np.isnan(got).any()
         assert np.max(np.abs(got - exp) / scale) <= TOL64, k
+
+
+@pytest.mark.parametrize("bandwidth", [100000, 1000])
+def test_baseline_config1_shape(cuda, oracle, bandwidth):
+    """BASELINE.json configs[0]: fp64 CrsMatrix 100k x 100k, ~20 nnz/row random (kk_generate with
+    nnz = 2e6, row-size variance 10, bandwidth n or 0.01 n -- SURVEY.md 8d), single vector: the GPU result
+    against the oracle's Serial path (the reference's own CPU-runnable case) within 1e-10 row-scaled,
+    for the analysed (tile / self-tuned) and the no-analysis kernels."""
+    from kokkos_kernels_b200 import sparse as sp
+
+    n = 100000
+    rp, ci, v = kk_matrix(n, n, 2_000_000, 10, bandwidth, lo=-1.0, hi=1.0)
+    rng = np.random.default_rng(13718)
+    x = rng.uniform(-1, 1, n)
+    y0 = rng.uniform(-1, 1, n)
+    A = dev_matrix(sp, cuda, rp, ci, v, n)
+    for algo in (sp.SPMV_DEFAULT, sp.SPMV_FAST_SETUP):
+        h = sp.SPMVHandle(algo)
+        for alpha, beta in ((1.0, 0.0), (2.5, -0.5)):
+            for _ in range(4):  # passes through the plan's self-tuning phases (tile, tile timed, vector timed, choice)
+                run_case(sp, oracle, cuda, h, A, (rp, ci, v, n), "N", alpha, beta, x, y0,
+                         spmv_tolerance(np.finfo(np.float64).eps, alpha, beta, 30))
