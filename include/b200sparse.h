@@ -178,6 +178,24 @@ int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m,
                                   const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
                                   const int* row_ptr_C, int* col_idx_C, float* vals_C);
 
+/* spgemm_jacobi (sparse/src/KokkosSparse_spgemm_jacobi.hpp:25-190; native kernels
+ * sparse/impl/KokkosSparse_spgemm_jacobi_{sparseacc,denseacc,seq}_impl.hpp): C = (I - omega * diag(dinv) * A) * B
+ * = B - omega*dinv_i*(A*B)_i row by row, on the structure spgemm_symbolic computed for A*B with the same plan (A is
+ * square and holds its diagonal, so that row i of B lies inside the pattern of row i of A*B -- the reference's
+ * kernels assume the same; rows that violate it are completed without writing past their extent).  dinv has m
+ * entries (the reference passes an m x 1 view).  C rows come out sorted.  B200SP_ERR_STATE without a prior
+ * symbolic.  Asynchronous on `stream`.  (First GPU run pending: tests are marked gpu_next.) */
+int b200sp_spgemm_jacobi_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
+                                 const int* row_ptr_A, const int* col_idx_A, const double* vals_A,
+                                 const int* row_ptr_B, const int* col_idx_B, const double* vals_B,
+                                 const int* row_ptr_C, int* col_idx_C, double* vals_C, double omega,
+                                 const double* dinv);
+int b200sp_spgemm_jacobi_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
+                                 const int* row_ptr_A, const int* col_idx_A, const float* vals_A,
+                                 const int* row_ptr_B, const int* col_idx_B, const float* vals_B,
+                                 const int* row_ptr_C, int* col_idx_C, float* vals_C, float omega,
+                                 const float* dinv);
+
 /* ---- CrsMatrix utilities either side of the hot path ----------------- */
 /* sort_crs_matrix / sort_crs_graph (sparse/src/KokkosSparse_SortCrs.hpp:43-120,209-270): every row
  * sorted ascending by column, values permuted along, IN PLACE.  The sort is stable (entries with the

@@ -482,8 +482,11 @@ __device__ __forceinline__ int group_excl_scan(int v, int tg, int* wsum, int& to
 }
 
 // f(column, b_val*a_val, ordinal) once per product of row i; with_vals == false skips the value loads
+// jac_row >= 0 (spgemm_jacobi): the row gets one extra leading entry (column jac_row, value 1) -- row jac_row of B
+// itself -- and every value of A is multiplied by jac_mult = -omega * dinv[row]
+// (sparse/impl/KokkosSparse_spgemm_jacobi_seq_impl.hpp:78-108).
 template <int G, typename S, typename F>
-__device__ __forceinline__ void walk_products2(int tg, int lb, int a0, int a1, bool with_vals,
+__device__ __forceinline__ void walk_products2(int tg, int lb, int a0, int a1, bool with_vals, int jac_row, S jac_mult,
                                                const int* __restrict__ ciA, const S* __restrict__ vA,
                                                const int* __restrict__ rpB, const int* __restrict__ ciB,
                                                const S* __restrict__ vB, Walk2Smem<G, S>& w, F&& f) {
@@ -494,15 +497,23 @@ __device__ __forceinline__ void walk_products2(int tg, int lb, int a0, int a1, b
   const int nsub = G / lb;
   const int q = tg / lb, sl = tg % lb;
   int pbase = 0;
-  for (int ab = a0; ab < a1; ab += G) {
+  const int lo = jac_row >= 0 ? a0 - 1 : a0;  // index a0 - 1 stands for the extra entry
+  for (int ab = lo; ab < a1; ab += G) {
     const int nA = min(G, a1 - ab);
     int b0 = 0, ln = 0;
     S va = S(0);
     if (tg < nA) {
-      const int ca = ciA[ab + tg];
+      const int j = ab + tg;
+      int ca;
+      if (jac_row >= 0 && j == a0 - 1) {
+        ca = jac_row;
+        if (with_vals) va = S(1);
+      } else {
+        ca = ciA[j];
+        if (with_vals) va = jac_row >= 0 ? vA[j] * jac_mult : vA[j];
+      }
       b0 = rpB[ca];
       ln = rpB[ca + 1] - b0;
-      if (with_vals) va = vA[ab + tg];
     }
     int total;
     const int excl = group_excl_scan<G>(ln, tg, w.wsum, total);
@@ -561,14 +572,14 @@ struct Num2Layout {
   static_assert(TOT % 32 == 0 && VCAP % 4 == 0 && PCAP % 4 == 0, "table sizes keep 16-byte alignment");
 };
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     num2_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                 const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
                 const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
                 int* __restrict__ ciC, S* __restrict__ vC, const int* __restrict__ cmin_arr,
                 const int* __restrict__ cmax_arr, const int* __restrict__ flops_arr, int* __restrict__ fb_rows,
-                int* __restrict__ fb_count) {
+                int* __restrict__ fb_count, S omega, const S* __restrict__ dinv) {
   using L = Num2Layout<S, G, KSLOTS, PAD, VCAP, PCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
@@ -601,8 +612,12 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     np = flops_arr[i];  // exact number of products of the row (clamped at INT_MAX)
   }
   const bool work = active && nz > 0;
-  const bool dupfree = work && np == nz;        // every product has its own column
-  const bool staged = PCAP > 0 && work && np <= PCAP;
+  // spgemm_jacobi: row i of B joins the products (its columns are expected inside the symbolic pattern, i.e. A
+  // has its diagonal, like the reference's kernels assume): duplicates are the rule, nothing is parked
+  const bool dupfree = !JAC && work && np == nz;  // every product has its own column
+  const bool staged = !JAC && PCAP > 0 && work && np <= PCAP;
+  const int jac_row = (JAC && work) ? i : -1;
+  const S jac_mult = (JAC && work) ? -omega * dinv[i] : S(1);
   {
     int4* k4 = reinterpret_cast<int4*>(keys);
     for (int s = tg; s < TOT / 4; s += G) k4[s] = make_int4(INF, INF, INF, INF);
@@ -626,7 +641,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     return wpre[h >> 5] + __popc(wmask[h >> 5] & ((1u << (h & 31)) - 1u));
   };
   // ---- the walk: ordered insertion of the keys (+ products parked in shared memory)
-  walk_products2<G, S>(tg, lb, a0, a1, staged, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int id) {
+  walk_products2<G, S>(tg, lb, a0, a1, staged, jac_row, jac_mult, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int id) {
     if (PCAP > 0 && staged) {
       pcol[id] = c;
       pval[id] = v;
@@ -645,7 +660,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   gsync();
   const bool overflow = sm_flag[g] != 0;
   if (active && overflow && tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
-  const bool emit = work && !overflow;  // uniform within the group
+  bool emit = work && !overflow;  // uniform within the group
   // ---- occupancy words (warp ballot) and their exclusive prefix
   if (emit) {
     for (int w = wg; w < WORDS; w += NWG) {
@@ -673,6 +688,15 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     }
   }
   gsync();
+  if (JAC && emit) {
+    // row i of B brought columns the symbolic pattern does not hold (A without its diagonal): hand the row to the
+    // fallback kernel, which drops the surplus instead of writing past the row
+    const int total = wpre[WORDS - 1] + __popc(wmask[WORDS - 1]);
+    if (total != nz) {
+      emit = false;
+      if (tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
+    }
+  }
   // ---- column indices leave in sorted order (EMIT2: written from the value pass instead, one scattered 4-byte
   //      store per product -- no scan over the whole key table)
   if (emit && !EMIT2) {
@@ -695,7 +719,7 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   } else {
     // too many products to park: second walk (idle / overflowed groups walk an empty row)
     const int b0 = emit ? a0 : 0, b1 = emit ? a1 : 0;
-    walk_products2<G, S>(tg, lb, b0, b1, true, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int) {
+    walk_products2<G, S>(tg, lb, b0, b1, true, emit ? jac_row : -1, jac_mult, ciA, vA, rpB, ciB, vB, sm_walk[g], [&](int c, S v, int) {
       const int pos = rank_of(c);
       if (EMIT2) ciC[cbase + pos] = c;
       if (dupfree) vals[pos] = v; else smem_add(&vals[pos], v);
@@ -704,6 +728,92 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   gsync();
   if (emit)
     for (int q = tg; q < nz; q += G) vC[cbase + q] = vals[q];
+}
+
+// spgemm_jacobi rows that do not fit shared memory (or overflowed): num_fallback_kernel with row i of B
+// inserted first and A's values scaled by -omega*dinv[i] (kept separate from the validated fallback kernel
+// until it has had its own GPU run)
+template <typename S>
+__global__ void __launch_bounds__(256)
+    num_fallback_jacobi_kernel(const int* __restrict__ fb_rows, const int* __restrict__ fb_count, int log2slots,
+                               int* __restrict__ gkeys, S* __restrict__ gvals, const int* __restrict__ rpA,
+                               const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
+                               const int* __restrict__ ciB, const S* __restrict__ vB, const int* __restrict__ rpC,
+                               int* __restrict__ ciC, S* __restrict__ vC, S omega, const S* __restrict__ dinv) {
+  const size_t slots = (size_t)1 << log2slots;
+  int* keys = gkeys + (size_t)blockIdx.x * slots;
+  S* vals = gvals + (size_t)blockIdx.x * slots;
+  __shared__ int cursor;
+  const int nfb = *fb_count;
+  for (int q = blockIdx.x; q < nfb; q += gridDim.x) {
+    const int i = fb_rows[q];
+    const int cbase = rpC[i];
+    const int nz = rpC[i + 1] - cbase;
+    int lg = 1;
+    while (((size_t)1 << lg) < (size_t)2 * (size_t)nz) ++lg;
+    const size_t tsz = (size_t)1 << lg;
+    for (size_t s = threadIdx.x; s < tsz; s += 256) {
+      keys[s] = EMPTY;
+      vals[s] = S(0);
+    }
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    const S mult = -omega * dinv[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = rpA[i], a1 = rpA[i + 1];
+    for (int ja = a0 - 1 + warp; ja < a1; ja += 8) {  // index a0 - 1: row i of B itself, weight 1
+      const int ca = ja < a0 ? i : ciA[ja];
+      const S va = ja < a0 ? S(1) : vA[ja] * mult;
+      for (int jb = rpB[ca] + lane; jb < rpB[ca + 1]; jb += 32) {
+        const int c = ciB[jb];
+        const S v = vB[jb] * va;
+        size_t h = hash_mul(c, lg);
+        while (true) {
+          const int kcur = ((volatile int*)keys)[h];
+          if (kcur == c) break;
+          if (kcur == EMPTY) {
+            const int old = atomicCAS(&keys[h], EMPTY, c);
+            if (old == EMPTY || old == c) break;
+          }
+          h = (h + 1) & (tsz - 1);
+        }
+        atomicAdd(&vals[h], v);
+      }
+    }
+    __syncthreads();
+    for (size_t s = threadIdx.x; s < tsz; s += 256) {
+      const int key = keys[s];
+      if (key != EMPTY) {
+        const int p = atomicAdd(&cursor, 1);
+        if (p < nz) {  // more distinct columns than the symbolic pattern holds = precondition violated: drop, do not corrupt
+          ciC[cbase + p] = key;
+          vC[cbase + p] = vals[s];
+        }
+      }
+    }
+    __syncthreads();
+    int P = 1;
+    while (P < nz) P <<= 1;
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1, first = 1; stride > 0; stride >>= 1, first = 0) {
+        for (int idx = threadIdx.x; idx < P; idx += 256) {
+          const int l = first ? (idx ^ (size - 1)) : (idx ^ stride);
+          if (l > idx && l < nz) {
+            const int ka = ciC[cbase + idx], kb = ciC[cbase + l];
+            if (ka > kb) {
+              ciC[cbase + idx] = kb;
+              ciC[cbase + l] = ka;
+              const S ta = vC[cbase + idx];
+              vC[cbase + idx] = vC[cbase + l];
+              vC[cbase + l] = ta;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // fallback: global-memory hash (wrap-around, multiplicative) + in-place bitonic sort of the C row
@@ -886,20 +996,21 @@ static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int
   return B200SP_OK;
 }
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false>
 static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
-                       const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
+                       const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC, S omega = S(0),
+                       const S* dinv = nullptr) {
   const int nrows = p->num_off[bin + 1] - p->num_off[bin];
   if (nrows <= 0) return B200SP_OK;
   using L = Num2Layout<S, G, KSLOTS, PAD, VCAP, PCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = L::PER_AL * RPC;
-  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2>;
+  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2, JAC>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
                                                       rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->flops, p->fb_rows,
-                                                      p->fb_count);
+                                                      p->fb_count, omega, dinv);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -983,6 +1094,47 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   if ((rc = launch_num<S, 512, 32768, 512, 8192>(st, p, 4, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
   num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
                                                   ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S>
+static int jacobi_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int k, const int* rpA, const int* ciA,
+                       const S* vA, const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC, S omega,
+                       const S* dinv) {
+  B200SP_REQUIRE(p != nullptr, "spgemm_jacobi: null plan");
+  if (!p->symbolic_done) {
+    set_error("KokkosSparse::spgemm_jacobi: must first call spgemm_symbolic with the same handle.");
+    return B200SP_ERR_STATE;
+  }
+  if (p->m != m || p->n != n || p->k != k) {
+    set_error("spgemm_jacobi: dimensions (%d,%d,%d) differ from symbolic (%d,%d,%d)", m, n, k, p->m, p->n, p->k);
+    return B200SP_ERR_STATE;
+  }
+  B200SP_REQUIRE(m == n, "spgemm_jacobi: C = (I - omega D^-1 A) B needs a square A (m = %d, n = %d)", m, n);
+  if (m == 0 || p->c_nnz == 0) return B200SP_OK;
+  B200SP_REQUIRE(rpA && ciA && vA && rpB && ciB && vB && rpC && ciC && vC && dinv, "spgemm_jacobi: null pointer argument");
+  const size_t need = sizeof(S) * (size_t)kFbCtas * ((size_t)1 << p->fb_log2);
+  if (need > p->fb_vals_bytes) {
+    if (p->fb_vals) cudaFreeAsync(p->fb_vals, st);
+    p->fb_vals = nullptr;
+    B200SP_CUDA_TRY(cudaMallocAsync(&p->fb_vals, need, st));
+    p->fb_vals_bytes = need;
+  }
+  B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_count, &p->fb_static, sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc;
+#define NUMJ(B, G, KS, PAD, VCAP)                                                                                       \
+  if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, false, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, omega, \
+                                                            dinv)))                                                     \
+    return rc;
+  NUMJ(0, 32, 256, 32, 64)
+  NUMJ(1, 32, 1024, 64, 256)
+  NUMJ(2, 128, 4096, 128, 1024)
+  NUMJ(3, 256, 16384, 256, 4096)
+  NUMJ(4, 512, 32768, 512, 8192)
+#undef NUMJ
+  num_fallback_jacobi_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                         ciA, vA, rpB, ciB, vB, rpC, ciC, vC, omega, dinv);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -1191,6 +1343,16 @@ int b200sp_spgemm_numeric_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m,
                                   const int* ciA, const double* vA, const int* rpB, const int* ciB, const double* vB,
                                   const int* rpC, int* ciC, double* vC) {
   return numeric_impl<double>(plan, (cudaStream_t)stream, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+}
+int b200sp_spgemm_jacobi_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k, const int* rpA,
+                                 const int* ciA, const double* vA, const int* rpB, const int* ciB, const double* vB,
+                                 const int* rpC, int* ciC, double* vC, double omega, const double* dinv) {
+  return jacobi_impl<double>(plan, (cudaStream_t)stream, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, omega, dinv);
+}
+int b200sp_spgemm_jacobi_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k, const int* rpA,
+                                 const int* ciA, const float* vA, const int* rpB, const int* ciB, const float* vB,
+                                 const int* rpC, int* ciC, float* vC, float omega, const float* dinv) {
+  return jacobi_impl<float>(plan, (cudaStream_t)stream, m, n, k, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, omega, dinv);
 }
 int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k, const int* rpA,
                                   const int* ciA, const float* vA, const int* rpB, const int* ciB, const float* vB,

@@ -308,6 +308,27 @@ def spgemm_numeric(kh, A, Amode, B, Bmode, Cm):
     return Cm
 
 
+def spgemm_jacobi(kh, A, Amode, B, Bmode, Cm, omega, dinv):
+    """KokkosSparse::Experimental::spgemm_jacobi (sparse/src/KokkosSparse_spgemm_jacobi.hpp:25-190):
+    C = (I - omega * diag(dinv) * A) * B on the structure spgemm_symbolic(kh, A, B) produced; dinv has one entry
+    per row (the reference passes an m x 1 view)."""
+    if Amode or Bmode:
+        raise B200SparseError("KokkosSparse::spgemm_jacobi: transposing A or B is not supported")
+    sh = kh.get_spgemm_handle()
+    if sh is None or not sh.is_symbolic_called():
+        raise B200SparseError("KokkosSparse::spgemm_jacobi: must first call spgemm_symbolic with the same handle.")
+    dv = dinv.reshape(-1)
+    if dv.numel() != A.numRows() or dv.dtype != A.values.dtype:
+        raise B200SparseError("KokkosSparse::spgemm_jacobi: dinv must hold one value of the matrix scalar type per row")
+    fn = getattr(_lib.sparse(), f"b200sp_spgemm_jacobi_{_sfx(A.values)}_i32")
+    check(fn(sh._plan, _stream(), A.numRows(), A.numCols(), B.numCols(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+             _ptr(B.row_map), _ptr(B.entries), _ptr(B.values), _ptr(Cm.row_map), _ptr(Cm.entries), _ptr(Cm.values), omega,
+             _ptr(dv.contiguous())))
+    sh._numeric = True
+    sh._entries = True
+    return Cm
+
+
 def spgemm(A, Amode, B, Bmode):
     """No-reuse interface (sparse/src/KokkosSparse_spgemm.hpp:170-218)."""
     kh = KokkosKernelsHandle()

@@ -287,3 +287,58 @@ OKK_API int64_t okk_spadd_unsorted_symbolic(int m, const int* rmA, const int* en
 
 DEF_SPADD_UNSORTED_NUMERIC(okk_spadd_unsorted_numeric_f64, double)
 DEF_SPADD_UNSORTED_NUMERIC(okk_spadd_unsorted_numeric_f32, float)
+
+/* ------------------------------------------------------------------------
+ * spgemm_jacobi_seq (sparse/impl/KokkosSparse_spgemm_jacobi_seq_impl.hpp:26-131):
+ * C = (I - omega*diag(dinv)*A)*B on the row map of spgemm_symbolic(A, B): per
+ * row, B's row i is inserted first (weight 1), then every product with
+ * val = a_ij * (-omega*dinv_i), b_val = b * val; columns in first-touch order
+ * (the caller sorts, like the unit test does for the SPGEMM_SERIAL result,
+ * sparse/unit_test/Test_Sparse_spgemm_jacobi.hpp:216-219).
+ * ---------------------------------------------------------------------- */
+#define DEF_SPGEMM_JACOBI(NAME, ST)                                                \
+  OKK_API void NAME(int m, int k, const int* rmA, const int* entA, const ST* valA, \
+                    const int* rmB, const int* entB, const ST* valB,               \
+                    const int* rmC, int* entC, ST* valC, ST omega,                 \
+                    const ST* dinv) {                                              \
+    ST* accumulator = (ST*)calloc((size_t)(k > 0 ? k : 1), sizeof(ST));            \
+    unsigned char* acc_flag = (unsigned char*)calloc((size_t)(k > 0 ? k : 1), 1);  \
+    for (int i = 0; i < m; ++i) {                                                  \
+      const int c_row_begin = rmC[i];                                              \
+      const int c_row_size = rmC[i + 1] - c_row_begin;                             \
+      int counter = 0;                                                             \
+      const ST mult = -omega * dinv[i];                                            \
+      for (int z = rmB[i]; z < rmB[i + 1]; ++z) {                                  \
+        const int b_col = entB[z];                                                 \
+        const ST b_val = valB[z];                                                  \
+        if (!acc_flag[b_col]) {                                                    \
+          acc_flag[b_col] = 1;                                                     \
+          entC[c_row_begin + counter++] = b_col;                                   \
+        }                                                                          \
+        accumulator[b_col] += b_val;                                               \
+      }                                                                            \
+      for (int ja = rmA[i]; ja < rmA[i + 1]; ++ja) {                               \
+        const int col = entA[ja];                                                  \
+        const ST val = valA[ja] * mult;                                            \
+        for (int jb = rmB[col]; jb < rmB[col + 1]; ++jb) {                         \
+          const int b_col = entB[jb];                                              \
+          const ST b_val = valB[jb] * val;                                         \
+          if (!acc_flag[b_col]) {                                                  \
+            acc_flag[b_col] = 1;                                                   \
+            entC[c_row_begin + counter++] = b_col;                                 \
+          }                                                                        \
+          accumulator[b_col] += b_val;                                             \
+        }                                                                          \
+      }                                                                            \
+      for (int j = 0; j < c_row_size; ++j) {                                       \
+        const int c = entC[c_row_begin + j];                                       \
+        valC[c_row_begin + j] = accumulator[c];                                    \
+        accumulator[c] = 0;                                                        \
+        acc_flag[c] = 0;                                                           \
+      }                                                                            \
+    }                                                                              \
+    free(accumulator); free(acc_flag);                                             \
+  }
+
+DEF_SPGEMM_JACOBI(okk_spgemm_jacobi_f64, double)
+DEF_SPGEMM_JACOBI(okk_spgemm_jacobi_f32, float)

@@ -50,6 +50,8 @@ class Oracle:
             getattr(L, f"okk_spadd_sorted_numeric_{sfx}").argtypes = [i32, vp, vp, vp, ft, vp, vp, vp, ft, vp, vp, vp]
             getattr(L, f"okk_spadd_unsorted_numeric_{sfx}").argtypes = [i32, vp, vp, vp, ft, vp, vp, vp, ft, vp, vp, vp, vp, vp]
         L.okk_sort_crs_stable_i32.argtypes = [i32, vp, vp, vp]
+        L.okk_spgemm_jacobi_f64.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp]
+        L.okk_spgemm_jacobi_f32.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
         L.okk_merged_rowmap.argtypes = [i32, vp, vp, vp]
         L.okk_merged_rowmap.restype = i64
         L.okk_spadd_sorted_symbolic.argtypes = [i32, vp, vp, vp, vp, vp]
@@ -131,6 +133,20 @@ class Oracle:
         vC = np.empty(nnz, dtype=vA.dtype)
         sfx = self._sfx(vA)
         getattr(self.lib, "okk_spgemm_numeric_" + sfx)(m, k, _p(rpA), _p(ciA), _p(vA), _p(rpB), _p(ciB), _p(vB), _p(rpC), _p(ciC), _p(vC))
+        if sort:
+            getattr(self.lib, "okk_sort_crs_" + sfx)(m, _p(rpC), _p(ciC), _p(vC))
+        return rpC, ciC, vC
+
+    def spgemm_jacobi(self, rpA, ciA, vA, rpB, ciB, vB, k, omega, dinv, sort=True):
+        """spgemm_symbolic + spgemm_jacobi_seq (+ sort_crs_matrix): C = (I - omega diag(dinv) A) B."""
+        m = len(rpA) - 1
+        rpC = np.zeros(m + 1, dtype=np.int32)
+        nnz = self.lib.okk_spgemm_symbolic(m, k, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC))
+        ciC = np.empty(nnz, dtype=np.int32)
+        vC = np.empty(nnz, dtype=vA.dtype)
+        sfx = self._sfx(vA)
+        getattr(self.lib, "okk_spgemm_jacobi_" + sfx)(m, k, _p(rpA), _p(ciA), _p(vA), _p(rpB), _p(ciB), _p(vB), _p(rpC), _p(ciC),
+                                                      _p(vC), omega, _p(dinv))
         if sort:
             getattr(self.lib, "okk_sort_crs_" + sfx)(m, _p(rpC), _p(ciC), _p(vC))
         return rpC, ciC, vC

@@ -6,7 +6,7 @@
 // the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
 // faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
 //
-//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep jacobi
 //
 // Exit code: number of failed suites.
 #include <cuda_runtime.h>
@@ -69,6 +69,8 @@ void okk_spmv_serial_f64(int nrow, const int* rm, const int* ci, const double* v
                          double beta);
 void okk_spmv_transpose_f64(int nrow, int ncol, const int* rm, const int* ci, const double* v, const double* x, double* y,
                             double alpha, double beta);
+void okk_spgemm_jacobi_f64(int m, int k, const int* rmA, const int* entA, const double* valA, const int* rmB, const int* entB,
+                           const double* valB, const int* rmC, int* entC, double* valC, double omega, const double* dinv);
 int okk_num_threads(void);
 // host generators (kokkos-kernels_b200/csrc/matgen.c)
 void b200gen_fill_f64(int64_t n, double* v, double lo, double hi, uint64_t seed);
@@ -1130,6 +1132,89 @@ static void suite_spmm_sweep() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: jacobi -- spgemm_jacobi (C = (I - omega D^-1 A) B) against the oracle's spgemm_jacobi_seq
+// ------------------------------------------------------------------------------------------------
+static void jacobi_case(const char* name, Csr<double> A, bool add_diagonal) {
+  // diagonally dominant like the reference test: diagonal = 10 * sum |row| (+1), rows sorted
+  if (add_diagonal) {
+    Csr<double> D;
+    D.m = A.m;
+    D.n = A.n;
+    D.rp.assign(A.m + 1, 0);
+    for (int i = 0; i < A.m; ++i) {
+      std::vector<std::pair<int, double>> row;
+      double sum = 0;
+      for (int j = A.rp[i]; j < A.rp[i + 1]; ++j)
+        if (A.ci[j] != i) {
+          const double v = (A.v[j] - 25.0) / 25.0;
+          row.emplace_back(A.ci[j], v);
+          sum += std::fabs(v);
+        }
+      row.emplace_back(i, 10.0 * sum + 1.0);
+      std::sort(row.begin(), row.end());
+      row.erase(std::unique(row.begin(), row.end(), [](auto& x, auto& y) { return x.first == y.first; }), row.end());
+      for (auto& pr : row) {
+        D.ci.push_back(pr.first);
+        D.v.push_back(pr.second);
+      }
+      D.rp[i + 1] = (int)D.ci.size();
+    }
+    A = D;
+  }
+  const int m = A.m;
+  const double omega = 3.0;
+  std::vector<double> dinv((size_t)m, 2.0);
+  std::vector<int> orp((size_t)m + 1, 0);
+  const int64_t onnz = okk_spgemm_symbolic(m, m, A.rp.data(), A.ci.data(), A.rp.data(), A.ci.data(), orp.data());
+  std::vector<int> oci(onnz);
+  std::vector<double> ov(onnz);
+  okk_spgemm_jacobi_f64(m, m, A.rp.data(), A.ci.data(), A.v.data(), A.rp.data(), A.ci.data(), A.v.data(), orp.data(), oci.data(), ov.data(),
+                        omega, dinv.data());
+  okk_sort_crs_f64(m, orp.data(), oci.data(), ov.data());
+  Dev<int> rp(A.rp), ci(A.ci), rpC((size_t)m + 1);
+  Dev<double> v(A.v), dd(dinv);
+  b200sp_spgemm_plan* plan = nullptr;
+  SP(b200sp_spgemm_plan_create(&plan));
+  int64_t c_nnz = -1;
+  int c_max = -1;
+  SP(b200sp_spgemm_symbolic_i32(plan, nullptr, m, m, m, rp.p, ci.p, rp.p, ci.p, rpC.p, &c_nnz, &c_max));
+  bool ok = c_nnz == onnz && count_diff(rpC.host(), orp) == 0;
+  int64_t dci = -1, dv = -1;
+  float ms = 0;
+  if (ok) {
+    Dev<int> ciC((size_t)c_nnz);
+    Dev<double> vC((size_t)c_nnz);
+    ciC.fill_bytes(0xff);
+    vC.fill_bytes(0xff);
+    Timer t;
+    t.start();
+    SP(b200sp_spgemm_jacobi_f64_i32(plan, nullptr, m, m, m, rp.p, ci.p, v.p, rp.p, ci.p, v.p, rpC.p, ciC.p, vC.p, omega, dd.p));
+    ms = t.stop_ms();
+    CK(cudaDeviceSynchronize());
+    dci = count_diff(ciC.host(), oci);
+    dv = rel_mismatch(vC.host(), ov, 1e-7);
+    ok = dci == 0 && dv == 0;
+  }
+  b200sp_spgemm_plan_destroy(plan, nullptr);
+  record(name, ok, "m=%d c_nnz=%lld (oracle %lld) col_idx diffs=%lld value law violations=%lld, %.3f ms", m, (long long)c_nnz, (long long)onnz,
+         (long long)dci, (long long)dv, ms);
+}
+
+static void suite_jacobi() {
+  jacobi_case("kk_1000_diag_dominant", gen_kk<double>(1000, 1000, 10000, 10, 50, 1), true);
+  jacobi_case("kk_30000_diag_dominant", gen_kk<double>(30000, 30000, 240000, 6, 3000, 2), true);
+  {
+    Rng r(3);
+    std::vector<int> lens(8000);
+    for (auto& l : lens) l = r.below(12);
+    lens[0] = 3000;  // rows in the large shared-memory bins and in the global fallback
+    lens[1] = 700;
+    jacobi_case("wide_rows_8000_diag_dominant", gen_rows<double>(lens, 8000, true, false, 3), true);
+  }
+  jacobi_case("lap27_10x2dof", gen_lap27<double>(10, 2), false);  // has its diagonal already
+}
+
+// ------------------------------------------------------------------------------------------------
 struct Suite {
   const char* name;
   std::function<void()> fn;
@@ -1139,7 +1224,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];

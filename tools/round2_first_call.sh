@@ -10,6 +10,7 @@ O=gpurun_out/r02_gpu_check_first.jsonl
 # 1. parity + clean timings of all harness suites at full size (config 4 SpGEMM, config 3 SpMM incl. the row-limit sweep)
 $G --big --out $O > gpurun_out/r02_gpu_check_first.log 2>&1
 $G --suite spmm --spmm-scale 23 --out $O >> gpurun_out/r02_gpu_check_first.log 2>&1
+# (the `jacobi` suite of the --big run above is the first GPU run of spgemm_jacobi; then: pytest tests/test_gpu_jacobi.py -m gpu_next)
 # 2. ncu: launch lists + one full capture per kernel of interest (never bench numbers)
 ncu --metrics gpu__time_duration.sum --clock-control none --target-processes all -c 400 --csv \
     --log-file gpurun_out/r02_launches_spmm.csv $G --big --suite spmm --out gpurun_out/scratch.jsonl > /dev/null 2>&1
