@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib, sparse as sp
+from . import _lib, partition, sparse as sp
 
 
 class RowBlockSpMV:
@@ -52,15 +52,7 @@ class RowBlockSpMV:
         # chunk boundaries on rows whose first entry is 16-byte aligned in col_idx / vals (TMA path)
         if mode not in ("pipelined", "pipelined_mc"):
             chunks = 1
-        bounds = [0]
-        for c in range(1, chunks):
-            r = (nrows * c) // chunks
-            # TMA path: first entry 16-byte aligned; pipelined_mc: the piece of y starts on a 16-byte boundary too
-            while r < nrows and (rp[r] % 4 != 0 or (mode == "pipelined_mc" and (r0 + r) % 2 != 0)):
-                r += 1
-            if r > bounds[-1] and r < nrows:
-                bounds.append(r)
-        bounds.append(nrows)
+        bounds = partition.piece_bounds(rp, chunks, row_offset=r0, even_rows=(mode == "pipelined_mc"))
         self.pieces = []
         for c0, c1 in zip(bounds[:-1], bounds[1:]):
             s0, s1 = int(rp[c0]), int(rp[c1])

@@ -20,6 +20,25 @@ def balanced_row_blocks(row_ptr, world):
     return [int(v) for v in np.maximum.accumulate(b)]
 
 
+def piece_bounds(row_ptr, chunks, row_offset=0, even_rows=False):
+    """Boundaries (local row indices, first = 0, last = nrows) of the pieces a row block is computed / pushed in by
+    the pipelined all-gather (multigpu.RowBlockSpMV): about nrows/chunks rows each, every piece starting on a row
+    whose first entry is 16-byte aligned in col_idx / vals (row_ptr % 4 == 0: the TMA-tiled kernel is handed a
+    sub-matrix view) and -- even_rows, for the 16-byte multicast pushes -- whose global row index
+    (row_offset + r) is even, so that the piece of y starts on a 16-byte boundary.  Pieces that cannot satisfy
+    the constraints are merged into their predecessor."""
+    nrows = len(row_ptr) - 1
+    bounds = [0]
+    for c in range(1, max(int(chunks), 1)):
+        r = (nrows * c) // chunks
+        while r < nrows and (row_ptr[r] % 4 != 0 or (even_rows and (row_offset + r) % 2 != 0)):
+            r += 1
+        if bounds[-1] < r < nrows:
+            bounds.append(r)
+    bounds.append(nrows)
+    return bounds
+
+
 def extract_shard(row_ptr, col_idx, values, r0, r1):
     """Rows [r0, r1) with offsets rebased to 0 (fits int32 per shard); columns stay global."""
     s, e = int(row_ptr[r0]), int(row_ptr[r1])

@@ -78,3 +78,27 @@ def test_balanced_blocks_cover_rows():
     nnz = [int(rp[b[i + 1]] - rp[b[i]]) for i in range(8)]
     assert sum(nnz) == rp[-1]
     assert max(nnz) <= rp[-1] / 8 + int(np.diff(rp).max())
+
+
+def test_piece_bounds_alignment():
+    """Pieces of the pipelined all-gather start on 16-byte-aligned CSR offsets (and on even global rows for the
+    multicast pushes), cover the block exactly once and degrade gracefully when no row qualifies."""
+    import numpy as np
+
+    from kokkos_kernels_b200 import partition
+
+    rng = np.random.default_rng(0)
+    for nrows, chunks, off, even in [(1000, 8, 0, False), (1000, 8, 333, True), (17, 8, 5, True), (5, 8, 0, False), (0, 4, 0, True)]:
+        lens = rng.integers(0, 9, nrows)
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        b = partition.piece_bounds(rp, chunks, row_offset=off, even_rows=even)
+        assert b[0] == 0 and b[-1] == nrows and all(x < y for x, y in zip(b[:-1], b[1:])) or nrows == 0
+        assert len(b) - 1 <= max(chunks, 1)
+        for r in b[1:-1]:
+            assert rp[r] % 4 == 0
+            if even:
+                assert (off + r) % 2 == 0
+    # rows of 3 entries: only every 4th row starts aligned
+    rp = np.arange(0, 3 * 101, 3)
+    b = partition.piece_bounds(rp, 4)
+    assert all(rp[r] % 4 == 0 for r in b[1:-1]) and b[-1] == 100
