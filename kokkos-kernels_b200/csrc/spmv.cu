@@ -1208,7 +1208,11 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
   int rc = plan_analyse<double>(p, st, cfg, m, n, nnz, row_ptr);
   if (rc) return rc;
   if (q.key != row_ptr || q.key_cfg != cfg) {
-    q.nc = 4;
+    q.nc = 4;  // pieces of y that go down while the next piece is computed (B200SP_HOSTVEC_PIECES: 1..8, tuning)
+    if (const char* e = getenv("B200SP_HOSTVEC_PIECES")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= 8) q.nc = v;
+    }
     int4 d[9];
     for (int c = 0; c <= q.nc; ++c) {
       q.tile_b[c] = (int)(((int64_t)p->n_tiles * c) / q.nc);
