@@ -47,7 +47,8 @@ typedef enum {
 typedef enum {
   B200SP_SPMV_DEFAULT = 0,    /* SPMV_DEFAULT: analyse once, TMA-tiled kernel        */
   B200SP_SPMV_FAST_SETUP = 1, /* SPMV_FAST_SETUP: no analysis, row-vector kernel     */
-  B200SP_SPMV_MERGE_PATH = 2  /* SPMV_MERGE_PATH: imbalance-proof nnz-split kernel    */
+  B200SP_SPMV_MERGE_PATH = 2  /* SPMV_MERGE_PATH: same kernels as DEFAULT (tiles are nnz-balanced; rows beyond the tile
+                                 row limit go to a long-row kernel, optionally split into segments)        */
 } b200sp_spmv_algo;
 
 typedef struct b200sp_spmv_plan b200sp_spmv_plan;     /* lives in SPMVHandle::tpl_rank1 / tpl_rank2 */

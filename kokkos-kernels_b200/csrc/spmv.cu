@@ -13,7 +13,8 @@
 //                       NW consumer warps do sub-warp-per-row dot products out of
 //                       shared memory, x gathered through L1 (ld.global.nc),
 //                       warp-shuffle reduction, fused alpha/beta epilogue.
-//   spmv_longrow_kernel rows longer than the tile's row limit: one CTA per row.
+//   spmv_longrow_kernel rows longer than the tile's row limit: one CTA per row (default), or -- opt-in,
+//                       B200SP_SPMV_LONGROWS=seg -- segments of <= 4096 entries + ordered combine.
 //   spmv_vector_kernel  no-analysis fallback (FAST_SETUP, tiny or misaligned
 //                       inputs): sub-warp per row straight from global memory.
 //   spmv_transpose_kernel  T/H modes: y pre-scaled, atomicAdd scatter.
@@ -176,6 +177,75 @@ __global__ void __launch_bounds__(256) spmv_longrow_kernel(const int* __restrict
       store_y(y, r, t, alpha, beta, ex);
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// long rows, adaptive row splitting (opt-in, B200SP_SPMV_LONGROWS=seg): every long row is cut into segments of
+// <= SEG entries (build_row_segments_kernel, once per matrix), one CTA sums a segment, and a second small kernel
+// adds a row's partial sums in segment order -- the longest row no longer serialises on one CTA (R-MAT scale 23:
+// 152,801 entries), and the result stays deterministic (fixed association, no atomics).
+// ---------------------------------------------------------------------------
+__global__ void build_row_segments_kernel(const int* __restrict__ long_rows, const int* __restrict__ n_long,
+                                          const int* __restrict__ row_ptr, int SEG, int4* __restrict__ segs,
+                                          int* __restrict__ n_seg, int2* __restrict__ row_seg) {
+  const int nl = *n_long;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
+    const int r = long_rows[i];
+    const int s = row_ptr[r], e = row_ptr[r + 1];
+    const int nseg = (e - s + SEG - 1) / SEG;
+    const int base = atomicAdd(n_seg, nseg);
+    row_seg[i] = make_int2(base, nseg);
+    for (int q = 0; q < nseg; ++q) segs[base + q] = make_int4(r, s + q * SEG, min(e, s + (q + 1) * SEG), q);
+  }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) spmv_seg_partial_kernel(const int4* __restrict__ segs, const int* __restrict__ n_seg_ptr,
+                                                               const int* __restrict__ col_idx, const S* __restrict__ vals,
+                                                               const S* __restrict__ x, S* __restrict__ partial) {
+  __shared__ S warp_part[8];
+  const int n_seg = *n_seg_ptr;
+  for (int q = blockIdx.x; q < n_seg; q += gridDim.x) {
+    const int4 d = segs[q];
+    S sum = S(0);
+    constexpr int UNR = 4;
+    for (int j0 = d.y + threadIdx.x; j0 < d.z; j0 += 256 * UNR) {
+      int c[UNR];
+      S av[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u * 256;
+        const bool ok = j < d.z;
+        c[u] = ok ? ld_stream(col_idx + j) : 0;
+        av[u] = ok ? ld_stream(vals + j) : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) sum += (j0 + u * 256 < d.z) ? av[u] * ldg(x + c[u]) : S(0);
+    }
+    sum = subwarp_sum<32>(sum);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      S t = S(0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += warp_part[w];
+      partial[q] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) spmv_seg_combine_kernel(const int* __restrict__ long_rows, const int* __restrict__ n_long_ptr,
+                                                               const int2* __restrict__ row_seg, const S* __restrict__ partial,
+                                                               S* __restrict__ y, S alpha, S beta, YExtra ex) {
+  const int n_long = *n_long_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_long; i += gridDim.x * blockDim.x) {
+    const int2 rs = row_seg[i];
+    S t = S(0);
+    for (int q = 0; q < rs.y; ++q) t += partial[rs.x + q];
+    store_y(y, long_rows[i], t, alpha, beta, ex);
   }
 }
 
@@ -488,6 +558,13 @@ struct b200sp_spmv_plan {
   const int* chunk_key = nullptr;
   int chunk_m = -1;
   int64_t chunk_nnz = -1;
+  // adaptive row splitting of the long rows (B200SP_SPMV_LONGROWS=seg): segments, per-row (first segment, count), partial sums
+  int4* r1_segs = nullptr;
+  int* r1_n_seg = nullptr;
+  int2* r1_row_seg = nullptr;
+  void* r1_partial = nullptr;
+  int r1_seg_cap = 0;
+  bool r1_built = false;
   // rank-2 tile kernel (spmm.cu): its own tile analysis (smaller row limit) + segment list of the long rows
   int4* mm_tiles = nullptr;
   int mm_n_tiles = 0, mm_T = 0, mm_LMAX = 0, mm_cap = 0;
@@ -541,6 +618,15 @@ static void plan_release_analysis(b200sp_spmv_plan* p, cudaStream_t st) {
   if (p->tiles) cudaFreeAsync(p->tiles, st);
   if (p->long_rows) cudaFreeAsync(p->long_rows, st);
   if (p->n_long) cudaFreeAsync(p->n_long, st);
+  if (p->r1_segs) cudaFreeAsync(p->r1_segs, st);
+  if (p->r1_n_seg) cudaFreeAsync(p->r1_n_seg, st);
+  if (p->r1_row_seg) cudaFreeAsync(p->r1_row_seg, st);
+  if (p->r1_partial) cudaFreeAsync(p->r1_partial, st);
+  p->r1_segs = nullptr;
+  p->r1_n_seg = nullptr;
+  p->r1_row_seg = nullptr;
+  p->r1_partial = nullptr;
+  p->r1_built = false;
   p->tiles = nullptr;
   p->long_rows = nullptr;
   p->n_long = nullptr;
@@ -947,10 +1033,33 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   // long rows: skip the launch once the (asynchronously fetched) count is known to be 0
   if (!p->n_long_known && cudaEventQuery(p->n_long_event) == cudaSuccess) p->n_long_known = true;
   if (!(p->n_long_known && *p->n_long_host == 0) && (p->range_hi < 0 || p->range_lo == 0)) {
-    int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
-    spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta,
-                                                   p->extra);
-    B200SP_LAUNCH_CHECK();
+    const char* lr = getenv("B200SP_SPMV_LONGROWS");
+    if (lr && lr[0] == 's') {
+      constexpr int SEG = 4096;
+      if (!p->r1_built) {
+        p->r1_seg_cap = (int)(nnz / SEG) + p->long_cap + 1;
+        B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->r1_segs, sizeof(int4) * (size_t)p->r1_seg_cap, st));
+        B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->r1_n_seg, sizeof(int), st));
+        B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->r1_row_seg, sizeof(int2) * (size_t)p->long_cap, st));
+        B200SP_CUDA_TRY(cudaMallocAsync(&p->r1_partial, sizeof(double) * (size_t)p->r1_seg_cap, st));
+        B200SP_CUDA_TRY(cudaMemsetAsync(p->r1_n_seg, 0, sizeof(int), st));
+        build_row_segments_kernel<<<std::max(1, std::min((p->long_cap + 255) / 256, sm_count() * 4)), 256, 0, st>>>(
+            p->long_rows, p->n_long, row_ptr, SEG, p->r1_segs, p->r1_n_seg, p->r1_row_seg);
+        B200SP_LAUNCH_CHECK();
+        p->r1_built = true;
+      }
+      spmv_seg_partial_kernel<S><<<sm_count() * 4, 256, 0, st>>>(p->r1_segs, p->r1_n_seg, col_idx, vals, x, (S*)p->r1_partial);
+      B200SP_LAUNCH_CHECK();
+      spmv_seg_combine_kernel<S><<<std::max(1, std::min((p->long_cap + 255) / 256, sm_count())), 256, 0, st>>>(
+          p->long_rows, p->n_long, p->r1_row_seg, (const S*)p->r1_partial, y, alpha, beta, p->extra);
+      B200SP_LAUNCH_CHECK();
+      snprintf(p->last_kernel + strlen(p->last_kernel), sizeof(p->last_kernel) - strlen(p->last_kernel), "+seg");
+    } else {
+      int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
+      spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta,
+                                                     p->extra);
+      B200SP_LAUNCH_CHECK();
+    }
   }
   if (phase == 1) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[1], st));
   return B200SP_OK;

@@ -6,7 +6,7 @@
 // the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
 // faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
 //
-//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep jacobi
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep jacobi spmv_longrows
 //
 // Exit code: number of failed suites.
 #include <cuda_runtime.h>
@@ -1215,6 +1215,67 @@ static void suite_jacobi() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: spmv_longrows -- rank-1 SpMV on a power-law matrix: one CTA per long row (default) vs segments
+// ------------------------------------------------------------------------------------------------
+static void suite_spmv_longrows() {
+  const int scale = g_big ? 22 : 18;
+  int64_t nnz = 0;
+  void* h = b200gen_rmat_build(scale, 16, 0.57, 0.19, 0.19, 23, &nnz);
+  Csr<double> A;
+  A.m = A.n = 1 << scale;
+  A.rp.resize((size_t)A.m + 1);
+  A.ci.resize((size_t)nnz);
+  b200gen_rmat_emit(h, A.rp.data(), A.ci.data());
+  A.v.resize((size_t)nnz);
+  b200gen_fill_f64(nnz, A.v.data(), -1.0, 1.0, 3);
+  std::vector<double> x((size_t)A.n), y0((size_t)A.m), yref, scale_v, va(A.v), xa;
+  b200gen_fill_f64(A.n, x.data(), -1.0, 1.0, 4);
+  b200gen_fill_f64(A.m, y0.data(), -1.0, 1.0, 5);
+  const double alpha = 1.25, beta = -0.5;
+  yref = y0;
+  okk_spmv_serial_f64(A.m, A.rp.data(), A.ci.data(), A.v.data(), x.data(), yref.data(), alpha, beta);
+  xa = x;
+  scale_v = y0;
+  for (auto& t : va) t = std::fabs(t);
+  for (auto& t : xa) t = std::fabs(t);
+  for (auto& t : scale_v) t = std::fabs(t);
+  okk_spmv_serial_f64(A.m, A.rp.data(), A.ci.data(), va.data(), xa.data(), scale_v.data(), std::fabs(alpha), std::fabs(beta));
+  int maxrow = 0;
+  for (int i = 0; i < A.m; ++i) maxrow = std::max(maxrow, A.rp[i + 1] - A.rp[i]);
+  Dev<int> rp(A.rp), ci(A.ci);
+  Dev<double> v(A.v), dx(x), dy((size_t)A.m);
+  setenv("B200SP_NO_AUTOTUNE", "1", 1);  // stay on the tiled kernel: the comparison is about its long-row path
+  for (int seg = 0; seg <= 1; ++seg) {
+    if (seg) setenv("B200SP_SPMV_LONGROWS", "seg", 1);
+    else unsetenv("B200SP_SPMV_LONGROWS");
+    b200sp_spmv_plan* plan = nullptr;
+    SP(b200sp_spmv_plan_create(&plan, 0));
+    float best = 1e30f;
+    std::vector<double> got, first;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaMemcpy(dy.p, y0.data(), y0.size() * sizeof(double), cudaMemcpyHostToDevice));
+      Timer t;
+      t.start();
+      SP(b200sp_spmv_f64_i32(plan, nullptr, 'N', A.m, A.n, nnz, alpha, rp.p, ci.p, v.p, dx.p, beta, dy.p));
+      const float ms = t.stop_ms();
+      if (rep > 0) best = std::min(best, ms);
+      got = dy.host();
+      if (rep == 0) first = got;
+    }
+    double worst = 0;
+    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, std::fabs(got[i] - yref[i]) / std::max(scale_v[i], 1e-300));
+    const double balg = 12.0 * nnz + 4.0 * (A.m + 1) + 8.0 * A.n + 16.0 * A.m;
+    record(seg ? "rmat_f64/segments" : "rmat_f64/cta_per_row", worst <= 1e-10 && count_diff(got, first) == 0,
+           "scale %d nnz=%lld longest row %d: kernel=%s %.3f ms (%.0f GB/s algorithmic), max scaled err %.2e, run-to-run differing entries %lld",
+           scale, (long long)nnz, maxrow, b200sp_spmv_last_kernel(plan), best, balg / (best * 1e-3) / 1e9, worst,
+           (long long)count_diff(got, first));
+    b200sp_spmv_plan_destroy(plan, nullptr);
+  }
+  unsetenv("B200SP_SPMV_LONGROWS");
+  unsetenv("B200SP_NO_AUTOTUNE");
+}
+
+// ------------------------------------------------------------------------------------------------
 struct Suite {
   const char* name;
   std::function<void()> fn;
@@ -1224,7 +1285,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
