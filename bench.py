@@ -147,8 +147,9 @@ def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
     rows = min(rows, len(rp) - 1)
     rps = np.ascontiguousarray(rp[: rows + 1])
     nnz = int(rps[-1])
-    cis, vas = ci[:nnz], va[:nnz]
-    y = np.zeros(rows)
+    # pages first touched by the threads that will stream them (parallel initialisation, reference protocol)
+    rps, cis, vas, x = (orc.first_touch_copy(a, threads) for a in (rps, ci[:nnz], va[:nnz], x))
+    y = orc.first_touch_copy(np.zeros(rows), threads)
     ncols = len(x)
     orc.spmv_functor(rps, cis, vas, ncols, x, y, 1.0, 0.0, threads)  # warm-up / first touch
     t0 = time.perf_counter()
@@ -187,6 +188,8 @@ def run_reference(args, emit):
     x = matgen.fill(ncols, -1.0, 1.0, 1)
     y = np.zeros(rows)
     nnz = int(rp[-1])
+    # pages first touched by the threads that will stream them (parallel initialisation, reference protocol)
+    rp, ci, va, x, y = (orc.first_touch_copy(a, threads) for a in (rp, ci, va, x, y))
     for _ in range(max(args.warmup, 1)):
         orc.spmv_functor(rp, ci, va, ncols, x, y, 1.0, 0.0, threads)
     t0 = time.perf_counter()

@@ -495,6 +495,23 @@ OKK_API int64_t okk_count_rel_mismatch_f64(int64_t n, const double* a, const dou
   return bad;
 }
 
+/* First-touch placement for the CPU timing legs (bench.py cpu_baseline / --impl reference): copies `bytes`
+ * from src to the untouched allocation dst with an OpenMP static partition, so that the pages of dst are
+ * spread over the NUMA nodes of the threads that will stream them -- what a Kokkos application gets from
+ * initialising its views in parallel (reference protocol
+ * perf_test/sparse/KokkosSparse_kk_spmv.cpp:121-167).  Not part of any result. */
+OKK_API void okk_parallel_copy(void* dst, const void* src, int64_t bytes, int threads) {
+  const int64_t chunk = 1 << 16;
+  const int64_t nchunks = (bytes + chunk - 1) / chunk;
+  (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads)
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t o = c * chunk;
+    const int64_t n = bytes - o < chunk ? bytes - o : chunk;
+    memcpy((char*)dst + o, (const char*)src + o, (size_t)n);
+  }
+}
+
 OKK_API int okk_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -44,6 +44,7 @@ class Oracle:
         L.okk_mmd_entry.restype = i32
         L.okk_diagonal_search.argtypes = [vp, i64, vp, i64, i64, C.POINTER(i64), C.POINTER(i64)]
         L.okk_num_threads.restype = i32
+        L.okk_parallel_copy.argtypes = [vp, vp, i64, i32]
         for sfx, ft in (("f64", f64), ("f32", f32)):
             getattr(L, f"okk_sort_crs_stable_{sfx}").argtypes = [i32, vp, vp, vp]
             getattr(L, f"okk_merged_entries_{sfx}").argtypes = [i32, vp, vp, vp, vp, vp, vp]
@@ -72,6 +73,14 @@ class Oracle:
 
     def num_threads(self):
         return self.lib.okk_num_threads()
+
+    def first_touch_copy(self, a, threads):
+        """Copy of `a` whose pages are first touched by `threads` OpenMP threads (static partition): NUMA placement
+        for the CPU timing legs, not part of any result."""
+        a = np.ascontiguousarray(a)
+        out = np.empty_like(a)
+        self.lib.okk_parallel_copy(_p(out), _p(a), a.nbytes, threads)
+        return out
 
     # ---- SpMV ----
     def spmv_serial(self, rp, ci, v, x, y, alpha, beta):
