@@ -572,7 +572,7 @@ struct Num2Layout {
   static_assert(TOT % 32 == 0 && VCAP % 4 == 0 && PCAP % 4 == 0, "table sizes keep 16-byte alignment");
 };
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false, bool FASTW = false>
 __global__ void __launch_bounds__(G <= 32 ? 256 : G)
     num2_kernel(int nrows_bin, const int* __restrict__ rows, int lb, const int* __restrict__ rpA,
                 const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
@@ -661,33 +661,79 @@ __global__ void __launch_bounds__(G <= 32 ? 256 : G)
   const bool overflow = sm_flag[g] != 0;
   if (active && overflow && tg == 0) fb_rows[atomicAdd(fb_count, 1)] = i;
   bool emit = work && !overflow;  // uniform within the group
-  // ---- occupancy words (warp ballot) and their exclusive prefix
-  if (emit) {
-    for (int w = wg; w < WORDS; w += NWG) {
-      const unsigned msk = __ballot_sync(0xffffffffu, keys[w * 32 + lane] != INF);
-      if (lane == 0) {
-        wmask[w] = msk;
-        wpre[w] = __popc(msk);
+  // ---- occupancy words and their exclusive prefix
+  if (FASTW) {
+    // variant 6: 128 slots per step -- every lane reads 4 keys with one 16-byte load, its 4 occupancy bits are
+    // OR-reduced over the 8 lanes that make up a word; then every thread scans a contiguous run of words and the
+    // runs are combined with one group-wide scan (all warps busy, instead of warp 0 walking every word)
+    if (emit) {
+      for (int chunk = wg; chunk * 128 < TOT; chunk += NWG) {
+        const int s0 = chunk * 128 + lane * 4;
+        unsigned nib = 0u;
+        if (s0 < TOT) {  // TOT % 4 == 0: the four keys are all in range or all out
+          const int4 kk = *reinterpret_cast<const int4*>(&keys[s0]);
+          nib = (kk.x != INF ? 1u : 0u) | (kk.y != INF ? 2u : 0u) | (kk.z != INF ? 4u : 0u) | (kk.w != INF ? 8u : 0u);
+        }
+        unsigned word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        const int w = chunk * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && w < WORDS) {
+          wmask[w] = word;
+          wpre[w] = __popc(word);
+        }
       }
     }
-  }
-  gsync();
-  if (emit && tg < 32) {
-    int carry = 0;
-    for (int w0 = 0; w0 < WORDS; w0 += 32) {
-      const int w = w0 + tg;
-      const int v = w < WORDS ? wpre[w] : 0;
-      int inc = v;
+    gsync();
+    constexpr int WPT = (WORDS + G - 1) / G;  // words per thread
+    int local[WPT];
+    int tsum = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (tg >= o) inc += t;
-      }
-      if (w < WORDS) wpre[w] = carry + inc - v;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
+    for (int q = 0; q < WPT; ++q) {
+      const int w = tg * WPT + q;
+      const int v = (emit && w < WORDS) ? wpre[w] : 0;
+      local[q] = tsum;
+      tsum += v;
     }
+    int total_words;
+    const int excl = group_excl_scan<G>(tsum, tg, sm_walk[g].wsum, total_words);  // barrier inside for G > 32
+    (void)total_words;
+    gsync();  // every wpre[] read above precedes the writes below
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) {
+      const int w = tg * WPT + q;
+      if (emit && w < WORDS) wpre[w] = excl + local[q];
+    }
+    gsync();
+  } else {
+    if (emit) {
+      for (int w = wg; w < WORDS; w += NWG) {
+        const unsigned msk = __ballot_sync(0xffffffffu, keys[w * 32 + lane] != INF);
+        if (lane == 0) {
+          wmask[w] = msk;
+          wpre[w] = __popc(msk);
+        }
+      }
+    }
+    gsync();
+    if (emit && tg < 32) {
+      int carry = 0;
+      for (int w0 = 0; w0 < WORDS; w0 += 32) {
+        const int w = w0 + tg;
+        const int v = w < WORDS ? wpre[w] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (tg >= o) inc += t;
+        }
+        if (w < WORDS) wpre[w] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    gsync();
   }
-  gsync();
   if (JAC && emit) {
     // row i of B brought columns the symbolic pattern does not hold (A without its diagonal): hand the row to the
     // fallback kernel, which drops the surplus instead of writing past the row
@@ -996,7 +1042,7 @@ static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int
   return B200SP_OK;
 }
 
-template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false>
+template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2 = false, bool JAC = false, bool FASTW = false>
 static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
                        const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC, S omega = S(0),
                        const S* dinv = nullptr) {
@@ -1006,7 +1052,7 @@ static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const in
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = L::PER_AL * RPC;
-  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2, JAC>;
+  auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2, JAC, FASTW>;
   if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
                                                       rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->flops, p->fb_rows,
@@ -1042,6 +1088,20 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   int rc;
   int variant = p->numeric_variant;
   if (const char* e = getenv("B200SP_SPGEMM_NUMERIC")) variant = atoi(e);
+  if (variant == 6) {  // variant 5 + occupancy words from 16-byte key loads and a scan that keeps every warp busy
+#define NUM6(B, G, KS, PAD, VCAP)                                                                                 \
+  if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, true, false, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    NUM6(0, 32, 256, 32, 64)
+    NUM6(1, 32, 1024, 64, 256)
+    NUM6(2, 128, 4096, 128, 1024)
+    NUM6(3, 256, 16384, 256, 4096)
+    NUM6(4, 512, 32768, 512, 8192)
+#undef NUM6
+    num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                    ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+  }
   if (variant == 5) {  // variant 4 + column indices written from the value pass (no scan of the key table for them)
 #define NUM5(B, G, KS, PAD, VCAP)                                                                                 \
   if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;

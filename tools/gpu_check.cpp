@@ -367,7 +367,7 @@ static void spgemm_case(const char* name, const Csr<S>& A, const Csr<S>& B) {
     return;
   }
   const double eps = sizeof(S) == 8 ? 1e-7 : 3.7e-3;
-  for (int variant = 1; variant <= 5; ++variant) {
+  for (int variant = 1; variant <= 6; ++variant) {
     char ev[8];
     snprintf(ev, sizeof(ev), "%d", variant);
     setenv("B200SP_SPGEMM_NUMERIC", ev, 1);
@@ -501,7 +501,7 @@ static void suite_spgemm_c4() {
   const double balg = 12.0 * 2 * A.nnz() + 4.0 * 3 * (n + 1) + 12.0 * (double)c_nnz;
   std::vector<int> hrpC = rpC.host();
   Rng r(0);
-  for (int variant = 1; variant <= 5; ++variant) {
+  for (int variant = 1; variant <= 6; ++variant) {
     char ev[8];
     snprintf(ev, sizeof(ev), "%d", variant);
     setenv("B200SP_SPGEMM_NUMERIC", ev, 1);
