@@ -481,6 +481,86 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// 16-byte-load flavour of spmm_seg_kernel (opt-in, B200SP_SPMM_SEG=vec): groups of KTL lanes with VW adjacent columns
+// each (the tile kernel's vec layout), so that a 256-thread CTA keeps 256/KTL nonzeros' X rows in flight per step
+// instead of 256/KT; partial sums are reduced by shuffles inside a warp and through shared memory across the 8 warps.
+template <typename S, int KTL>
+__global__ void __launch_bounds__(256)
+    spmm_seg_vec_kernel(const int4* __restrict__ segs, const int* __restrict__ n_seg_ptr, int k,
+                        const int* __restrict__ col_idx, const S* __restrict__ vals, const S* __restrict__ X, int64_t ldx,
+                        S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  constexpr int VW = VecOf<S>::W;
+  constexpr int G = 256 / KTL;       // groups per CTA
+  constexpr int GPW = 32 / KTL;      // groups per warp
+  constexpr int UNR = 4;
+  __shared__ S red[8][KTL * VW];
+  const int grp = threadIdx.x / KTL, t = threadIdx.x % KTL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_seg = *n_seg_ptr;
+  const int nstrips = (k + KTL * VW - 1) / (KTL * VW);
+  for (int q = blockIdx.x; q < n_seg; q += gridDim.x) {
+    const int4 d = segs[q];
+    const int row = d.x, e0 = d.y, e1 = d.z;
+    const bool multi = (d.w & 1) != 0;
+    for (int strip = 0; strip < nstrips; ++strip) {
+      const int j = (strip * KTL + t) * VW;
+      const bool jok = j < k;
+      Acc<S, VW> acc;
+#pragma unroll
+      for (int c = 0; c < VW; ++c) acc.a[c] = S(0);
+      for (int e = e0 + grp; e < e1; e += G * UNR) {
+        int c[UNR];
+        S av[UNR];
+        Acc<S, VW> xv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int ee = e + u * G;
+          const bool ok = ee < e1;
+          c[u] = ok ? ld_stream(col_idx + ee) : 0;
+          av[u] = ok ? ld_stream(vals + ee) : S(0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (jok && e + u * G < e1) {
+            xv[u] = load_x<S, VW>(X + (int64_t)c[u] * ldx + j);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < VW; ++cc) xv[u].a[cc] = S(0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av[u] * xv[u].a[cc];
+      }
+      // groups of one warp: lanes with the same t are KTL apart
+#pragma unroll
+      for (int o = KTL; o < 32; o <<= 1)
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) acc.a[cc] += __shfl_xor_sync(0xffffffffu, acc.a[cc], o);
+      if (lane < KTL) {
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) red[warp][lane * VW + cc] = acc.a[cc];
+      }
+      __syncthreads();
+      if (threadIdx.x < KTL && jok) {
+        S* yp = Y + (int64_t)row * ldy + j;
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) {
+          S sum = S(0);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x * VW + cc];
+          const S a = alpha * sum;
+          if (multi) atomicAdd(yp + cc, a);
+          else yp[cc] = (beta == S(0)) ? a : beta * yp[cc] + a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  (void)GPW;
+}
+
 template <typename S>
 static int launch_rowmajor(cudaStream_t st, int m, int k, const int* row_ptr, const int* col_idx, const S* vals,
                            const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
@@ -767,6 +847,21 @@ static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m,
   const int grid = sm_count() * 4;
   spmm_seg_prescale_kernel<S><<<grid, 256, 0, st>>>(tv.segs, tv.n_seg, k, beta, Y, ldy);
   B200SP_LAUNCH_CHECK();
+  if (vec) {
+    const char* e = getenv("B200SP_SPMM_SEG");
+    if (e && e[0] == 'v') {
+#define B200SP_SEGV(L)                                                                                               \
+  case L:                                                                                                            \
+    spmm_seg_vec_kernel<S, L><<<grid, 256, 0, st>>>(tv.segs, tv.n_seg, k, col_idx, vals, X, ldx, Y, ldy, alpha, beta); \
+    break;
+      switch (KTL) {
+        B200SP_SEGV(1) B200SP_SEGV(2) B200SP_SEGV(4) B200SP_SEGV(8) B200SP_SEGV(16) B200SP_SEGV(32)
+      }
+#undef B200SP_SEGV
+      B200SP_LAUNCH_CHECK();
+      return B200SP_OK;
+    }
+  }
   int KT = 1;
   while (KT < k && KT < 32) KT <<= 1;
 #define B200SP_SEG(K)                                                                                              \

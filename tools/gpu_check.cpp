@@ -921,14 +921,17 @@ static void suite_spmm() {
   };
   const Var vars[] = {{"split", nullptr, nullptr}, {"tile", nullptr, nullptr},  {"tilev", nullptr, nullptr}, {"tilev", "64", nullptr},
                       {"tilev", "128", nullptr},   {"tilev", "512", nullptr},   {"tilev", nullptr, "1"},     {"tilev", nullptr, "2"},
-                      {"tilev", nullptr, "3"},     {"tilev", "128", "1"},       {"tilev", "128", "2"},       {"row", nullptr, nullptr}};
+                      {"tilev", nullptr, "3"},     {"tilev", "128", "1"},       {"tilev", "128", "2"},       {"tilev", "128", "segvec"},
+                      {"tilev", "64", "segvec"},   {"row", nullptr, nullptr}};
   for (const Var& vr : vars) {
     if (!strcmp(vr.kernel, "row") && scale > 21) continue;  // 23 ms at scale 21: not worth the slot
     setenv("B200SP_SPMM_KERNEL", vr.kernel, 1);
     if (vr.lmax) setenv("B200SP_SPMM_LMAX", vr.lmax, 1);
     else unsetenv("B200SP_SPMM_LMAX");
-    if (vr.cfg) setenv("B200SP_SPMM_CFG", vr.cfg, 1);
-    else unsetenv("B200SP_SPMM_CFG");
+    unsetenv("B200SP_SPMM_CFG");
+    unsetenv("B200SP_SPMM_SEG");
+    if (vr.cfg && !strcmp(vr.cfg, "segvec")) setenv("B200SP_SPMM_SEG", "vec", 1);
+    else if (vr.cfg) setenv("B200SP_SPMM_CFG", vr.cfg, 1);
     b200sp_spmv_plan* plan = nullptr;
     SP(b200sp_spmv_plan_create(&plan, 0));
     float best = 1e30f;
@@ -951,6 +954,7 @@ static void suite_spmm() {
   unsetenv("B200SP_SPMM_KERNEL");
   unsetenv("B200SP_SPMM_LMAX");
   unsetenv("B200SP_SPMM_CFG");
+  unsetenv("B200SP_SPMM_SEG");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1035,8 +1039,11 @@ static void spmm_sweep_matrix(const char* name, const Csr<S>& A) {
   Csr<S> Aabs = A;
   for (auto& t : Aabs.v) t = std::fabs(t);
   const double tol = sizeof(S) == 8 ? 1e-13 : 2e-5;
-  for (const char* kern : {"tilev", "tile", "split"}) {
-    setenv("B200SP_SPMM_KERNEL", kern, 1);
+  for (const char* kern : {"tilev", "tile", "split", "tilev+segvec"}) {
+    const bool segvec = strstr(kern, "segvec") != nullptr;
+    setenv("B200SP_SPMM_KERNEL", segvec ? "tilev" : kern, 1);
+    if (segvec) setenv("B200SP_SPMM_SEG", "vec", 1);
+    else unsetenv("B200SP_SPMM_SEG");
     int bad = 0, runs = 0;
     double worst = 0;
     std::string last;
@@ -1092,6 +1099,7 @@ static void spmm_sweep_matrix(const char* name, const Csr<S>& A) {
            runs, bad, worst, last.c_str());
   }
   unsetenv("B200SP_SPMM_KERNEL");
+  unsetenv("B200SP_SPMM_SEG");
 }
 
 static void suite_spmm_sweep() {
