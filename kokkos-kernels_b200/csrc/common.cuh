@@ -1,6 +1,10 @@
 // common.cuh -- shared helpers of libb200sparse (sm_100a only).
 #pragma once
+#ifdef B200SP_EMU
+#include "cuda_emu.h"  // tools/emu: CUDA-on-CPU emulation of the kernels (test infrastructure)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -62,6 +66,37 @@ struct DevTmp {  // frees stream-ordered on scope exit
   }
 };
 
+#ifdef B200SP_EMU
+// ---- emulation of the PTX wrappers (tools/emu/cuda_emu.h): same names, same protocol -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)(uintptr_t)p; }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { b200emu::mbar_init(bar, count); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { b200emu::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { b200emu::mbar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return b200emu::mbar_test_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// the bulk copy completes at issue time; alignment rules of cp.async.bulk are checked
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t) {
+  if ((((uintptr_t)smem_dst | (uintptr_t)gsrc | bytes) & 15u) != 0) {
+    fprintf(stderr, "b200emu: cp.async.bulk with unaligned operands (dst %p src %p bytes %u)\n", smem_dst, gsrc, bytes);
+    abort();
+  }
+  memcpy(smem_dst, gsrc, bytes);
+  b200emu::mbar_complete_tx(bar, bytes);
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p) {
+  return *p;
+}
+__device__ __forceinline__ int ld_stream(const int* p) { return *p; }
+__device__ __forceinline__ double ld_stream(const double* p) { return *p; }
+__device__ __forceinline__ float ld_stream(const float* p) { return *p; }
+#else
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -138,6 +173,8 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+
+#endif  // B200SP_EMU
 
 template <typename T>
 __device__ __forceinline__ T shfl_xor(T v, int mask) {

@@ -4,6 +4,7 @@
 // scan of the block sums (+ total as int64, + maximum count), offset add.  out has m+1 entries;
 // when the total exceeds INT32_MAX every offset is written as 0 and the caller reports the overflow.
 #pragma once
+#include <limits.h>
 #include "common.cuh"
 
 namespace b200sp {

@@ -1,0 +1,250 @@
+// emu_runtime.cpp -- fiber scheduler, barriers and mbarrier emulation behind tools/emu/cuda_emu.h (TEST INFRASTRUCTURE).
+#include "cuda_emu.h"
+
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <map>
+#include <vector>
+
+namespace b200emu {
+
+namespace {
+
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr int kMaxThreads = 1024;
+
+struct Warp {
+  unsigned exist = 0;     // lanes that exist in this block
+  unsigned alive = 0;     // ... and have not returned yet
+  unsigned arrived = 0;   // lanes waiting in warp_barrier
+  unsigned released = 0;  // lanes whose barrier completed
+  unsigned long long slots[32];
+};
+
+struct FiberState {
+  ucontext_t ctx;
+  ThreadCtx tc;
+  bool done = false;
+  bool at_block_barrier = false;
+  void* stack = nullptr;
+};
+
+struct MBar {
+  unsigned count = 0;    // arrivals expected per phase
+  unsigned pending = 0;  // arrivals still missing in the current phase
+  long long tx = 0;      // bytes still expected in the current phase
+  unsigned phase = 0;    // parity of the phase in progress
+};
+
+ucontext_t g_sched;
+std::vector<FiberState> g_fibers;
+std::vector<Warp> g_warps;
+int g_nthreads = 0;
+int g_cur = -1;
+int g_alive_threads = 0;
+int g_block_arrived = 0;
+unsigned long g_progress = 0;
+const std::function<void()>* g_body = nullptr;
+std::map<void*, MBar> g_mbars;
+alignas(128) unsigned char g_dyn_smem[256 * 1024];
+
+void fiber_main() {
+  (*g_body)();
+  FiberState& f = g_fibers[g_cur];
+  f.done = true;
+  Warp& w = g_warps[f.tc.linear >> 5];
+  w.alive &= ~(1u << (f.tc.linear & 31));
+  --g_alive_threads;
+  ++g_progress;
+  swapcontext(&f.ctx, &g_sched);
+}
+
+void switch_out() {
+  FiberState& f = g_fibers[g_cur];
+  swapcontext(&f.ctx, &g_sched);
+}
+
+void try_release_block() {
+  if (g_block_arrived > 0 && g_block_arrived == g_alive_threads) {
+    for (int t = 0; t < g_nthreads; ++t) g_fibers[t].at_block_barrier = false;
+    g_block_arrived = 0;
+    ++g_progress;
+  }
+}
+
+}  // namespace
+
+void* device_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
+  return p;
+}
+void device_free(void* p) { free(p); }
+
+ThreadCtx* cur() { return &g_fibers[g_cur].tc; }
+void* dyn_smem() { return g_dyn_smem; }
+void note_progress() { ++g_progress; }
+unsigned long long* warp_slots() { return g_warps[g_fibers[g_cur].tc.linear >> 5].slots; }
+unsigned warp_alive() { return g_warps[g_fibers[g_cur].tc.linear >> 5].alive; }
+
+void yield_blocked() { switch_out(); }
+
+void block_barrier() {
+  FiberState& f = g_fibers[g_cur];
+  f.at_block_barrier = true;
+  ++g_block_arrived;
+  ++g_progress;
+  try_release_block();
+  while (f.at_block_barrier) {
+    switch_out();
+    try_release_block();  // threads may have exited meanwhile
+  }
+}
+
+void warp_barrier(unsigned mask) {
+  FiberState& f = g_fibers[g_cur];
+  Warp& w = g_warps[f.tc.linear >> 5];
+  const unsigned bit = 1u << (f.tc.linear & 31);
+  if (!(mask & bit)) {
+    fprintf(stderr, "b200emu: lane %d calls a warp collective with mask %08x that does not name it\n", f.tc.linear & 31, mask);
+    abort();
+  }
+  w.arrived |= bit;
+  ++g_progress;
+  for (;;) {
+    if (w.released & bit) {
+      w.released &= ~bit;
+      return;
+    }
+    const unsigned need = mask & w.alive;
+    if ((w.arrived & need) == need) {
+      w.arrived &= ~need;
+      w.released |= need;
+      ++g_progress;
+      continue;  // picks up its own release
+    }
+    switch_out();
+  }
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  const int nthreads = (int)(block.x * block.y * block.z);
+  if (nthreads <= 0 || nthreads > kMaxThreads || smem > sizeof(g_dyn_smem)) {
+    fprintf(stderr, "b200emu: bad launch configuration (%d threads, %zu bytes of dynamic shared memory)\n", nthreads, smem);
+    abort();
+  }
+  if (g_cur >= 0) {
+    fprintf(stderr, "b200emu: nested launch\n");
+    abort();
+  }
+  if ((int)g_fibers.size() < nthreads) {
+    const size_t old = g_fibers.size();
+    g_fibers.resize(nthreads);
+    for (size_t t = old; t < g_fibers.size(); ++t) {
+      g_fibers[t].stack = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (g_fibers[t].stack == MAP_FAILED) {
+        perror("b200emu: mmap");
+        abort();
+      }
+    }
+  }
+  g_body = &body;
+  g_nthreads = nthreads;
+  const int nwarps = (nthreads + 31) / 32;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_warps.assign(nwarps, Warp());
+        g_mbars.clear();
+        g_alive_threads = nthreads;
+        g_block_arrived = 0;
+        for (int t = 0; t < nthreads; ++t) {
+          FiberState& f = g_fibers[t];
+          f.done = false;
+          f.at_block_barrier = false;
+          f.tc.linear = t;
+          f.tc.tid = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+          f.tc.bid = uint3{bx, by, bz};
+          f.tc.bdim = block;
+          f.tc.gdim = grid;
+          g_warps[t >> 5].exist |= 1u << (t & 31);
+          g_warps[t >> 5].alive |= 1u << (t & 31);
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack;
+          f.ctx.uc_stack.ss_size = kStackBytes;
+          f.ctx.uc_link = &g_sched;
+          makecontext(&f.ctx, fiber_main, 0);
+        }
+        // round-robin until every fiber has returned; a full pass without progress is a deadlock
+        while (g_alive_threads > 0) {
+          const unsigned long before = g_progress;
+          for (int t = 0; t < nthreads; ++t) {
+            if (g_fibers[t].done) continue;
+            g_cur = t;
+            swapcontext(&g_sched, &g_fibers[t].ctx);
+          }
+          g_cur = -1;
+          if (g_progress == before && g_alive_threads > 0) {
+            fprintf(stderr, "b200emu: deadlock in block (%u,%u,%u): %d threads alive, %d at the block barrier\n", bx, by, bz,
+                    g_alive_threads, g_block_arrived);
+            for (int w = 0; w < nwarps; ++w)
+              fprintf(stderr, "  warp %d: alive %08x arrived %08x released %08x\n", w, g_warps[w].alive, g_warps[w].arrived, g_warps[w].released);
+            abort();
+          }
+        }
+        g_cur = -1;
+      }
+  g_body = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------- mbarrier
+void mbar_init(void* bar, unsigned count) {
+  MBar& b = g_mbars[bar];
+  b.count = b.pending = count;
+  b.tx = 0;
+  b.phase = 0;
+  ++g_progress;
+}
+static void mbar_check(MBar& b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1u;
+    b.pending = b.count;
+    ++g_progress;
+  }
+}
+void mbar_arrive(void* bar) {
+  MBar& b = g_mbars[bar];
+  if (b.pending == 0) {
+    fprintf(stderr, "b200emu: mbarrier over-arrival\n");
+    abort();
+  }
+  --b.pending;
+  ++g_progress;
+  mbar_check(b);
+}
+void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
+  MBar& b = g_mbars[bar];
+  b.tx += bytes;
+  if (b.pending == 0) {
+    fprintf(stderr, "b200emu: mbarrier over-arrival\n");
+    abort();
+  }
+  --b.pending;
+  ++g_progress;
+  mbar_check(b);
+}
+void mbar_complete_tx(void* bar, unsigned bytes) {
+  MBar& b = g_mbars[bar];
+  b.tx -= bytes;
+  ++g_progress;
+  mbar_check(b);
+}
+bool mbar_test_wait(void* bar, unsigned parity) {
+  // true once the phase with the given parity has completed, i.e. the phase in progress has the other parity
+  MBar& b = g_mbars[bar];
+  if (b.phase != parity) return true;
+  switch_out();
+  return g_mbars[bar].phase != parity;
+}
+
+}  // namespace b200emu

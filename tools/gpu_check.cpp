@@ -850,6 +850,7 @@ static void suite_crs_big() {
 // ------------------------------------------------------------------------------------------------
 // suite: spmm -- kernel variants of the rank-2 product (B200SP_SPMM_KERNEL) against the oracle + timing
 // ------------------------------------------------------------------------------------------------
+static int g_timeout_scale = 1;  // --timeout-scale N: the emulated build is orders of magnitude slower
 static int g_spmm_scale = 0;  // --spmm-scale N (default 18, 21 with --big; 23 = BASELINE.json config 3)
 
 static void suite_spmm() {
@@ -1301,6 +1302,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--big")) g_big = true;
     else if (!strcmp(argv[i], "--dry")) g_dry = true;
     else if (!strcmp(argv[i], "--spmm-scale") && i + 1 < argc) g_spmm_scale = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--timeout-scale") && i + 1 < argc) g_timeout_scale = std::max(1, atoi(argv[++i]));
     else {
       fprintf(stderr, "usage: gpu_check [--out FILE] [--suite NAME]... [--big] [--dry] [--spmm-scale N]\n");
       return 64;
@@ -1314,7 +1316,7 @@ int main(int argc, char** argv) {
     fflush(nullptr);
     const pid_t pid = fork();  // the parent never touches CUDA
     if (pid == 0) {
-      alarm((unsigned)s.timeout_s);
+      alarm((unsigned)(s.timeout_s * g_timeout_scale));
       int dev_count = 0;
       if (!g_dry && (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0 || b200sp_device_ok() != 1)) {
         record("device", false, "no compute-capability 10.x CUDA device");
