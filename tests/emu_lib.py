@@ -1,0 +1,122 @@
+"""ctypes view of the EMULATED library (tools/emu: the product's .cu sources compiled by g++ against a
+CUDA-on-CPU emulation layer -- fibers for threads, warp/block collectives, mbarrier/TMA, a fake runtime).
+"Device" pointers of that build are host pointers, so numpy arrays go straight through the C ABI.
+
+TEST INFRASTRUCTURE: this is how kernel LOGIC (indexing, collectives, barrier protocols, launch
+configuration, host-side planning) is exercised without a GPU.  It says nothing about memory-model races or
+speed; the `-m gpu` parity tests remain the real gate."""
+import ctypes as C
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "kokkos-kernels_b200"))
+
+
+def _builder():
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_LIB = None
+
+
+def lib():
+    """The emulated libb200sparse, built on demand (about 20 s) and bound with the product's signature table."""
+    global _LIB
+    if _LIB is None:
+        b = _builder()
+        if not b.up_to_date():
+            b.build(verbose=False)
+        import _lib as product_binding  # kokkos-kernels_b200/_lib.py: only its SPARSE_API table is used
+
+        so = C.CDLL(os.path.join(b.OUT, "libb200sparse_emu.so"))
+        for name, (res, args) in product_binding.SPARSE_API.items():
+            fn = getattr(so, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = so
+    return _LIB
+
+
+def harness():
+    b = _builder()
+    if not b.up_to_date():
+        b.build(verbose=False)
+    return os.path.join(b.OUT, "gpu_check_emu")
+
+
+def ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def ok(rc):
+    if rc != 0:
+        raise RuntimeError("b200sp status %d: %s" % (rc, lib().b200sp_last_error_string().decode()))
+
+
+def sfx(dtype):
+    return "f64" if np.dtype(dtype) == np.float64 else "f32"
+
+
+def scalar(dtype, x):
+    return C.c_double(x) if np.dtype(dtype) == np.float64 else C.c_float(x)
+
+
+class SpmvPlan:
+    def __init__(self, algo=0):
+        self.h = C.c_void_p()
+        ok(lib().b200sp_spmv_plan_create(C.byref(self.h), algo))
+
+    def close(self):
+        if self.h:
+            ok(lib().b200sp_spmv_plan_destroy(self.h, None))
+            self.h = C.c_void_p()
+
+    def kernel(self):
+        return lib().b200sp_spmv_last_kernel(self.h).decode()
+
+
+def spmv(plan, mode, nrows, ncols, rp, ci, v, x, y, alpha, beta):
+    fn = getattr(lib(), "b200sp_spmv_%s_i32" % sfx(v.dtype))
+    ok(fn(plan.h, None, mode.encode(), nrows, ncols, len(ci), scalar(v.dtype, alpha), ptr(rp), ptr(ci), ptr(v), ptr(x),
+          scalar(v.dtype, beta), ptr(y)))
+
+
+def spmm(plan, mode, nrows, ncols, rp, ci, v, X, Y, alpha, beta):
+    """X, Y: 2-D numpy arrays, either C- or F-ordered (LayoutRight / LayoutLeft); strides are passed in elements."""
+    fn = getattr(lib(), "b200sp_spmm_%s_i32" % sfx(v.dtype))
+    it = v.dtype.itemsize
+
+    def lay(a):
+        if a.strides[1] == it:  # row-major: leading dimension = row stride
+            return a.strides[0] // it, 1
+        assert a.strides[0] == it
+        return a.strides[1] // it, 0
+
+    ldx, rmx = lay(X)
+    ldy, rmy = lay(Y)
+    ok(fn(plan.h, None, mode.encode(), nrows, ncols, len(ci), X.shape[1], scalar(v.dtype, alpha), ptr(rp), ptr(ci), ptr(v), ptr(X),
+          ldx, rmx, scalar(v.dtype, beta), ptr(Y), ldy, rmy))
+
+
+def spgemm(A, B, m, n, k, dtype):
+    """symbolic + numeric; returns (rowmapC, entriesC, valuesC)."""
+    L = lib()
+    h = C.c_void_p()
+    ok(L.b200sp_spgemm_plan_create(C.byref(h)))
+    try:
+        rpC = np.full(m + 1, 123, dtype=np.int32)
+        nnz, mx = C.c_int64(), C.c_int()
+        ok(L.b200sp_spgemm_symbolic_i32(h, None, m, n, k, ptr(A[0]), ptr(A[1]), ptr(B[0]), ptr(B[1]), ptr(rpC), C.byref(nnz), C.byref(mx)))
+        ciC = np.full(nnz.value, -1, dtype=np.int32)
+        vC = np.full(nnz.value, np.nan, dtype=dtype)
+        fn = getattr(L, "b200sp_spgemm_numeric_%s_i32" % sfx(dtype))
+        ok(fn(h, None, m, n, k, ptr(A[0]), ptr(A[1]), ptr(A[2]), ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(rpC), ptr(ciC), ptr(vC)))
+        return rpC, ciC, vC, mx.value
+    finally:
+        ok(L.b200sp_spgemm_plan_destroy(h, None))

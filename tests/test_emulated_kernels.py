@@ -1,0 +1,299 @@
+"""The library's CUDA kernels EXECUTED on the CPU (tools/emu: the .cu sources compiled by g++ against a
+CUDA-on-CPU emulation layer) and checked against the oracle through the same C ABI the GPU tests use.
+
+What this covers: kernel logic -- indexing, warp/group collectives, block barriers, the mbarrier/TMA ring
+protocol, hash tables, the host-side planning and launch configuration -- including the opt-in variants
+ that have not had a GPU run yet.  What it does not cover: real concurrency (fibers run one
+at a time), the memory model, PTX, performance.  `-m gpu` stays the parity gate; this is the guard that keeps
+a logic bug from costing a GPU call.
+
+Shapes follow the reference's unit tests (Test_Sparse_spmv.hpp:1060-1068, Test_Sparse_spgemm.hpp:483-511,
+Test_Sparse_SortCrs.hpp, Test_Sparse_spadd.hpp) at the small end so the file runs in about a minute."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import emu_lib as E
+from crs_cases import MERGE_CASES, random_matrix, spadd_dense_check
+from helpers import kk_matrix, rowwise_scale
+
+TOL = {np.dtype(np.float64): 1e-10, np.dtype(np.float32): 1e-4}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return E.lib()
+
+
+class env:
+    """Set library knobs (read by getenv at call time) for one block."""
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def check_spmv(oracle, plan, mode, rp, ci, v, ncols, x, y0, alpha, beta):
+    nrows = len(rp) - 1
+    trans = mode in "TH"
+    y = y0.copy()
+    E.spmv(plan, mode, nrows, ncols, rp, ci, v, x, y, alpha, beta)
+    if not trans:
+        exp = oracle.spmv_serial(rp, ci, v, x, y0.copy(), alpha, beta)
+    else:
+        exp = oracle.spmv_transpose(rp, ci, v, ncols, x, y0.copy(), alpha, beta)
+    assert not np.isnan(y).any(), "NaN survived beta == 0"
+    scale = rowwise_scale(rp, ci, v, x, y0, alpha, beta, ncols_out=ncols, trans=trans)
+    err = np.abs(y.astype(np.float64) - exp.astype(np.float64))
+    bad = err > TOL[v.dtype] * scale + 1e-300
+    assert not bad.any(), f"{plan.kernel()} mode {mode} a={alpha} b={beta}: {bad.sum()} entries off"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spmv_modes_and_kernels(emu, oracle, dtype):
+    rows, cols = 3000, 2500
+    rp, ci, v = kk_matrix(rows, cols, rows * 12, 10, 200, dtype=dtype)
+    rng = np.random.default_rng(13718)
+    seen = set()
+    for algo in (0, 1, 2):  # DEFAULT, NATIVE, MERGE_PATH (include/b200sparse.h)
+        plan = E.SpmvPlan(algo)
+        for mode in "NCTH":
+            nx, ny = (cols, rows) if mode in "NC" else (rows, cols)
+            x = rng.random(nx).astype(dtype)
+            y0 = rng.random(ny).astype(dtype)
+            y0[::17] = np.nan
+            check_spmv(oracle, plan, mode, rp, ci, v, cols, x, y0, 2.5, 0.0)
+            seen.add(plan.kernel().split("<")[0])
+            y0 = rng.random(ny).astype(dtype)
+            check_spmv(oracle, plan, mode, rp, ci, v, cols, x, y0, -1.0, 0.5)
+        plan.close()
+    assert any(k.startswith("tile") for k in seen) and any(k.startswith("transpose") for k in seen), seen
+
+
+def test_spmv_unaligned_and_degenerate(emu, oracle):
+    # CSR arrays at odd offsets: the TMA ring needs 16-byte alignment, the library must pick another kernel
+    rp, ci, v = kk_matrix(2000, 2000, 30000, 5, 100)
+    cib = np.empty(len(ci) + 1, np.int32)
+    cib[1:] = ci
+    vb = np.empty(len(v) + 1, np.float64)
+    vb[1:] = v
+    x = np.random.default_rng(1).random(2000)
+    plan = E.SpmvPlan()
+    check_spmv(oracle, plan, "N", rp, cib[1:], vb[1:], 2000, x, np.zeros(2000), 1.0, 0.0)
+    assert not plan.kernel().startswith("tile"), plan.kernel()
+    plan.close()
+    # no rows / no entries
+    plan = E.SpmvPlan()
+    y = np.full(5, 3.0)
+    E.spmv(plan, "N", 5, 4, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0), np.ones(4), y, 1.0, 2.0)
+    assert np.array_equal(y, np.full(5, 6.0))
+    E.spmv(plan, "N", 0, 4, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0), np.ones(4), np.zeros(0), 1.0, 0.0)
+    plan.close()
+
+
+def test_spmv_long_rows_both_strategies(emu, oracle):
+    # a few rows far beyond the tile capacity: CTA-per-row kernel (default) and the opt-in segment path
+    rng = np.random.default_rng(5)
+    rows = cols = 6000
+    lens = rng.integers(0, 8, rows)
+    lens[[7, 3000, 5999]] = [5000, 2049, 6000]
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.int32)
+    v = rng.uniform(-1, 1, len(ci))
+    x, y0 = rng.random(cols), rng.random(rows)
+    for knob in (None, "seg"):
+        with env(B200SP_SPMV_LONGROWS=knob):
+            plan = E.SpmvPlan()
+            check_spmv(oracle, plan, "N", rp, ci, v, cols, x, y0, 1.5, -0.5)
+            assert ("+seg" in plan.kernel()) == (knob == "seg"), plan.kernel()
+            plan.close()
+
+
+def test_spmv_cached_transpose(emu, oracle):
+    rp, ci, v = kk_matrix(2500, 1500, 30000, 10, 300)
+    rng = np.random.default_rng(2)
+    x, y0 = rng.random(2500), rng.random(1500)
+    plan = E.SpmvPlan()
+    E.ok(emu.b200sp_spmv_plan_set_option(plan.h, 1, 1))  # B200SP_SPMV_OPT_CACHE_TRANSPOSE
+    for _ in range(2):  # second call reuses the cached transpose
+        check_spmv(oracle, plan, "T", rp, ci, v, 1500, x, y0, 2.0, 0.25)
+        assert plan.kernel().startswith("cached_transpose"), plan.kernel()
+    plan.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel,extra", [("tilev", {}), ("tile", {}), ("split", {}), ("row", {}),
+                                          ("tilev", {"B200SP_SPMM_SEG": "vec"}), ("tilev", {"B200SP_SPMM_LMAX": "64"})])
+def test_spmm_kernels_layouts(emu, oracle, dtype, kernel, extra):
+    rng = np.random.default_rng(11)
+    rows, cols = 1500, 1300
+    lens = rng.integers(0, 30, rows)
+    lens[[3, 700]] = [1200, 1100]  # long rows -> the segment kernels
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.int32)
+    v = rng.uniform(-1, 1, len(ci)).astype(dtype)
+    with env(B200SP_SPMM_KERNEL=kernel, **extra):
+        for k in (1, 3, 8, 17):
+            for order in "CF":
+                X = np.asarray(rng.random((cols, k)).astype(dtype), order=order)
+                Y0 = np.asarray(rng.random((rows, k)).astype(dtype), order=order)
+                for alpha, beta in ((1.0, 0.0), (-2.0, 0.5)):
+                    Y = Y0.copy(order=order)
+                    if beta == 0.0:
+                        Y[::13] = np.nan
+                    plan = E.SpmvPlan()
+                    E.spmm(plan, "N", rows, cols, rp, ci, v, X, Y, alpha, beta)
+                    plan.close()
+                    exp = oracle.spmv_mv(rp, ci, v, cols, X, np.zeros_like(Y0) if beta == 0.0 else Y0.copy(order=order), alpha, beta)
+                    assert not np.isnan(Y).any()
+                    for j in range(k):
+                        scale = rowwise_scale(rp, ci, v, X[:, j], Y0[:, j], alpha, beta)
+                        err = np.abs(Y[:, j].astype(np.float64) - exp[:, j].astype(np.float64))
+                        assert not (err > TOL[v.dtype] * scale + 1e-300).any(), (kernel, extra, k, order, alpha, beta, j)
+
+
+def gen_ab(oracle, m, k, n, nnz, dtype):
+    A = kk_matrix(m, k, nnz, 10, 200, dtype=dtype, lo=1.0, hi=50.0, seed=1, sort=True, oracle=oracle)
+    B = kk_matrix(k, n, nnz, 10, 200, dtype=dtype, lo=1.0, hi=50.0, seed=2, sort=True, oracle=oracle)
+    return A, B
+
+
+@pytest.mark.parametrize("dtype,eps", [(np.float64, 1e-7), (np.float32, 3.7e-3)])
+def test_spgemm_all_variants(emu, oracle, dtype, eps):
+    m, k, n = 1000, 500, 1600  # Test_Sparse_spgemm.hpp:483-511's small shape
+    A, B = gen_ab(oracle, m, k, n, 20000, dtype)
+    exp = oracle.spgemm(*A, *B, n)
+    for sym in (1, 2):
+        for num in (1, 2, 3, 4, 5, 6):
+            if sym == 2 and num not in (1, 6):
+                continue
+            with env(B200SP_SPGEMM_SYMBOLIC=sym, B200SP_SPGEMM_NUMERIC=num):
+                rpC, ciC, vC, mx = E.spgemm(A, B, m, k, n, dtype)
+            assert np.array_equal(rpC, exp[0]), (sym, num)
+            assert mx == int(np.diff(exp[0]).max())
+            assert np.array_equal(ciC, exp[1]), (sym, num)
+            assert oracle.rel_mismatch(vC.astype(np.float64), exp[2].astype(np.float64), eps) == 0, (sym, num)
+
+
+def test_spgemm_wide_rows_global_fallback(emu, oracle):
+    # C rows beyond every shared-memory table: the global-memory accumulator
+    rng = np.random.default_rng(9)
+    m, k, n = 200, 3000, 40000
+    lens = rng.integers(1, 4, m)
+    lens[5] = 900
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([rng.choice(k, l, replace=False) for l in lens]).astype(np.int32)  # unsorted input rows
+    v = rng.uniform(1, 50, len(ci))
+    lensB = np.full(k, 40)
+    rpB = np.concatenate([[0], np.cumsum(lensB)]).astype(np.int32)
+    ciB = np.concatenate([rng.choice(n, 40, replace=False) for _ in range(k)]).astype(np.int32)
+    vB = rng.uniform(1, 50, len(ciB))
+    exp = oracle.spgemm(rp, ci, v, rpB, ciB, vB, n)
+    assert np.diff(exp[0]).max() > 16384
+    for num in (1, 6):
+        with env(B200SP_SPGEMM_NUMERIC=num):
+            rpC, ciC, vC, _ = E.spgemm((rp, ci, v), (rpB, ciB, vB), m, k, n, np.float64)
+        assert np.array_equal(rpC, exp[0]) and np.array_equal(ciC, exp[1])
+        assert oracle.rel_mismatch(vC, exp[2], 1e-7) == 0
+
+
+def test_spgemm_jacobi(emu, oracle):
+    rng = np.random.default_rng(3)
+    m = 800
+    rp, ci, v = kk_matrix(m, m, 16000, 5, 100, lo=-1.0, hi=1.0, sort=True, oracle=oracle)
+    # A must hold its diagonal (KokkosSparse_spgemm_jacobi.hpp): add it through the oracle's own spadd
+    rpI = np.arange(m + 1, dtype=np.int32)
+    ciI = np.arange(m, dtype=np.int32)
+    rpA, ciA, vA = oracle.spadd(rp, ci, v, 1.0, rpI, ciI, np.full(m, 10.0), 1.0, True)
+    rpB, ciB, vB = rpA, ciA, rng.uniform(-1, 1, len(ciA))
+    dinv = rng.uniform(0.5, 1.5, m)
+    exp = oracle.spgemm_jacobi(rpA, ciA, vA, rpB, ciB, vB, m, 0.7, dinv)
+    L = emu
+    h = C.c_void_p()
+    E.ok(L.b200sp_spgemm_plan_create(C.byref(h)))
+    rpC = np.zeros(m + 1, np.int32)
+    nnz, mx = C.c_int64(), C.c_int()
+    E.ok(L.b200sp_spgemm_symbolic_i32(h, None, m, m, m, E.ptr(rpA), E.ptr(ciA), E.ptr(rpB), E.ptr(ciB), E.ptr(rpC), C.byref(nnz), C.byref(mx)))
+    ciC = np.full(nnz.value, -1, np.int32)
+    vC = np.full(nnz.value, np.nan)
+    E.ok(L.b200sp_spgemm_jacobi_f64_i32(h, None, m, m, m, E.ptr(rpA), E.ptr(ciA), E.ptr(vA), E.ptr(rpB), E.ptr(ciB), E.ptr(vB), E.ptr(rpC),
+                                        E.ptr(ciC), E.ptr(vC), 0.7, E.ptr(dinv)))
+    E.ok(L.b200sp_spgemm_plan_destroy(h, None))
+    assert np.array_equal(rpC, exp[0]) and np.array_equal(ciC, exp[1])
+    assert oracle.rel_mismatch(vC, exp[2], 1e-7) == 0
+
+
+@pytest.mark.parametrize("case", sorted(MERGE_CASES))
+def test_sort_and_merge_golden(emu, case):
+    c = MERGE_CASES[case]
+    if c["nrows"] == 0 and len(c["rowmap"]) == 0:
+        pytest.skip("no row map at all: handled above the C ABI")
+    rp, ci, v = c["rowmap"].copy(), c["entries"].copy(), c["values"].copy()
+    out_rp = np.zeros_like(rp)
+    nnz = C.c_int64()
+    E.ok(emu.b200sp_sort_and_merge_count_f64_i32(None, c["nrows"], E.ptr(rp), E.ptr(ci), E.ptr(v), E.ptr(out_rp), C.byref(nnz)))
+    assert nnz.value == len(c["gold_entries"]) and np.array_equal(out_rp, c["gold_rowmap"])
+    oci, ov = np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+    E.ok(emu.b200sp_sort_and_merge_fill_f64_i32(None, c["nrows"], E.ptr(rp), E.ptr(ci), E.ptr(v), E.ptr(out_rp), E.ptr(oci), E.ptr(ov)))
+    assert np.array_equal(oci, c["gold_entries"]) and np.array_equal(ov, c["gold_values"])
+
+
+def test_sort_transpose(emu, oracle):
+    rp, ci, v = random_matrix(700, 90, 0, 200, False, seed=4)  # rows longer than ncols: repeated columns (ties)
+    eci, ev = ci.copy(), v.copy()
+    oracle.sort_crs_stable(rp, eci, ev)
+    ci2, v2 = ci.copy(), v.copy()
+    E.ok(emu.b200sp_sort_crs_f64_i32(None, 700, E.ptr(rp), E.ptr(ci2), E.ptr(v2)))
+    assert np.array_equal(ci2, eci) and np.array_equal(v2, ev)
+    t_rp, t_ci, t_v = np.zeros(91, np.int32), np.zeros(len(ci), np.int32), np.zeros(len(ci))
+    E.ok(emu.b200sp_transpose_f64_i32(None, 700, 90, E.ptr(rp), E.ptr(ci), E.ptr(v), E.ptr(t_rp), E.ptr(t_ci), E.ptr(t_v)))
+    e_rp, e_ci, e_v = oracle.transpose(rp, ci, v, 90)
+    assert np.array_equal(t_rp, e_rp) and np.array_equal(t_ci, e_ci) and np.array_equal(t_v, e_v)
+
+
+@pytest.mark.parametrize("sorted_input", [True, False])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spadd(emu, oracle, sorted_input, dtype):
+    m, n = 600, 400
+    A = random_matrix(m, n, 0, 60, sorted_input, seed=1, dtype=dtype)
+    B = random_matrix(m, n, 0, 60, sorted_input, seed=2, dtype=dtype)
+    h = C.c_void_p()
+    E.ok(emu.b200sp_spadd_plan_create(C.byref(h), int(sorted_input), 0))
+    rpC = np.zeros(m + 1, np.int32)
+    nnz = C.c_int64()
+    E.ok(emu.b200sp_spadd_symbolic_i32(h, None, m, n, E.ptr(A[0]), E.ptr(A[1]), E.ptr(B[0]), E.ptr(B[1]), E.ptr(rpC), C.byref(nnz)))
+    ciC, vC = np.zeros(nnz.value, np.int32), np.zeros(nnz.value, dtype)
+    fn = getattr(emu, "b200sp_spadd_numeric_%s_i32" % E.sfx(dtype))
+    E.ok(fn(h, None, m, n, E.ptr(A[0]), E.ptr(A[1]), E.ptr(A[2]), E.scalar(dtype, 0.3), E.ptr(B[0]), E.ptr(B[1]), E.ptr(B[2]),
+            E.scalar(dtype, -1.7), E.ptr(rpC), E.ptr(ciC), E.ptr(vC)))
+    E.ok(emu.b200sp_spadd_plan_destroy(h, None))
+    exp = oracle.spadd(*A, 0.3, *B, -1.7, sorted_input)
+    assert np.array_equal(rpC, exp[0]) and np.array_equal(ciC, exp[1]) and np.array_equal(vC, exp[2])
+    spadd_dense_check(A, B, (rpC, ciC, vC), n, 0.3, -1.7)
+
+
+def test_harness_runs_emulated():
+    """tools/gpu_check.cpp -- the torch-free harness of the GPU calls -- linked against the emulated library:
+    the `spmv_t` suite executes (not --dry) and every check is ok."""
+    out = subprocess.run([E.harness(), "--timeout-scale", "40", "--suite", "spmv_t", "--out", os.devnull], capture_output=True, text=True,
+                         timeout=900)
+    log = out.stdout + out.stderr
+    assert out.returncode == 0, log[-3000:]
+    assert "[summary] spmv_t" in log and " FAIL" not in log, log[-3000:]

@@ -105,6 +105,19 @@ def transform(text):
     return out
 
 
+def up_to_date():
+    """True when the emulated library is newer than every file it is built from."""
+    lib = os.path.join(OUT, "libb200sparse_emu.so")
+    chk = os.path.join(OUT, "gpu_check_emu")
+    if not (os.path.exists(lib) and os.path.exists(chk)):
+        return False
+    deps = [os.path.join(CSRC, n) for n in SOURCES + HEADERS]
+    deps += [os.path.join(HERE, n) for n in ("cuda_emu.h", "emu_runtime.cpp", "build_emu.py", "cuda_runtime.h")]
+    deps += [os.path.join(ROOT, "include", "b200sparse.h"), os.path.join(ROOT, "tools", "gpu_check.cpp")]
+    newest = max(os.path.getmtime(d) for d in deps)
+    return min(os.path.getmtime(lib), os.path.getmtime(chk)) >= newest
+
+
 def build(verbose=True):
     os.makedirs(OUT, exist_ok=True)
     srcdir = os.path.join(OUT, "src", "csrc")
@@ -139,7 +152,7 @@ def build(verbose=True):
         if p.wait() != 0:
             raise RuntimeError("emulation build failed: " + " ".join(cmd))
     lib = os.path.join(OUT, "libb200sparse_emu.so")
-    subprocess.check_call(["g++", "-shared", "-o", lib] + objs + [rt])
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", lib] + objs + [rt])
     # the harness against the emulated library (its <cuda_runtime.h> is tools/emu/cuda_runtime.h)
     libdir = os.path.join(ROOT, "kokkos-kernels_b200", "lib")
     chk = os.path.join(OUT, "gpu_check_emu")
