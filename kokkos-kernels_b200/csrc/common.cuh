@@ -78,14 +78,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// the bulk copy completes at issue time; alignment rules of cp.async.bulk are checked
+// asynchronous like the real thing: the destination is poisoned at issue time and the bytes land only when a thread
+// waits on the barrier (tools/emu/emu_runtime.cpp); alignment rules of cp.async.bulk are checked
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t) {
-  if ((((uintptr_t)smem_dst | (uintptr_t)gsrc | bytes) & 15u) != 0) {
-    fprintf(stderr, "b200emu: cp.async.bulk with unaligned operands (dst %p src %p bytes %u)\n", smem_dst, gsrc, bytes);
-    abort();
-  }
-  memcpy(smem_dst, gsrc, bytes);
-  b200emu::mbar_complete_tx(bar, bytes);
+  b200emu::bulk_copy_async(smem_dst, gsrc, bytes, bar);
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }

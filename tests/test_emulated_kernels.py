@@ -68,7 +68,7 @@ def check_spmv(oracle, plan, mode, rp, ci, v, ncols, x, y0, alpha, beta):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_spmv_modes_and_kernels(emu, oracle, dtype):
-    rows, cols = 3000, 2500
+    rows, cols = 30000, 25000  # enough tiles per CTA (emulated device: 8 SMs) to wrap the TMA ring several times
     rp, ci, v = kk_matrix(rows, cols, rows * 12, 10, 200, dtype=dtype)
     rng = np.random.default_rng(13718)
     seen = set()
@@ -289,11 +289,30 @@ def test_spadd(emu, oracle, sorted_input, dtype):
     spadd_dense_check(A, B, (rpC, ciC, vC), n, 0.3, -1.7)
 
 
-def test_harness_runs_emulated():
-    """tools/gpu_check.cpp -- the torch-free harness of the GPU calls -- linked against the emulated library:
-    the `spmv_t` suite executes (not --dry) and every check is ok."""
-    out = subprocess.run([E.harness(), "--timeout-scale", "40", "--suite", "spmv_t", "--out", os.devnull], capture_output=True, text=True,
-                         timeout=900)
+@pytest.mark.parametrize("suite,order", [("spmv_t", "random:5"), ("crs", "reverse"), ("jacobi", "random:11"), ("spmv_longrows", "reverse")])
+def test_harness_runs_emulated(suite, order):
+    """tools/gpu_check.cpp -- the torch-free harness of the GPU calls -- linked against the emulated library: the
+    suite EXECUTES (not --dry) and every check is ok.  B200EMU_GUARD puts every device allocation of the harness
+    between inaccessible pages (an out-of-bounds access of a kernel is a fault, not a silent read); B200EMU_ORDER runs
+    the threads of a block in another order (a missing barrier that forward order hides shows up)."""
+    envv = dict(os.environ, B200EMU_GUARD="1", B200EMU_ORDER=order)
+    out = subprocess.run([E.harness(), "--timeout-scale", "40", "--suite", suite, "--out", os.devnull], capture_output=True, text=True,
+                         timeout=900, env=envv)
     log = out.stdout + out.stderr
     assert out.returncode == 0, log[-3000:]
-    assert "[summary] spmv_t" in log and " FAIL" not in log, log[-3000:]
+    assert "[summary] " + suite in log and " FAIL" not in log, log[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("B200EMU_NESTED") == "1", reason="this is the nested run")
+@pytest.mark.parametrize("order", ["reverse", "random:9"])
+def test_kernels_under_other_schedules(order):
+    """The ctypes tests of this file once more with the threads of every block scheduled differently: `reverse`
+    runs high thread ids first; `random` shuffles every pass and gives each warp its own speed, so producer warps run
+    ahead of (or behind) the consumers.  Correct kernels do not care.  (Checked by mutation when this was written:
+    removing the consumers' wait on the `full` barrier of the SpMV tile ring fails under every order, removing the
+    producer's wait on the `empty` barrier fails under `random` only.)"""
+    envv = dict(os.environ, B200EMU_ORDER=order, B200EMU_NESTED="1")
+    out = subprocess.run([os.sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
+                          "(spmv or spmm or spgemm or sort or spadd) and not harness"], capture_output=True, text=True, timeout=1500, env=envv,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]

@@ -120,6 +120,7 @@ void mbar_arrive(void* bar);
 void mbar_arrive_expect_tx(void* bar, unsigned bytes);
 void mbar_complete_tx(void* bar, unsigned bytes);
 bool mbar_test_wait(void* bar, unsigned parity);
+void bulk_copy_async(void* smem_dst, const void* gsrc, unsigned bytes, void* bar);
 
 }  // namespace b200emu
 

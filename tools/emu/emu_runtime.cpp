@@ -85,6 +85,13 @@ int g_block_arrived = 0;
 unsigned long g_progress = 0;
 const std::function<void()>* g_body = nullptr;
 std::map<void*, MBar> g_mbars;
+struct PendingCopy {  // an issued cp.async.bulk whose bytes have not been delivered yet
+  void* dst;
+  const void* src;
+  unsigned bytes;
+  void* bar;
+};
+std::vector<PendingCopy> g_pending;
 alignas(128) unsigned char g_dyn_smem[256 * 1024];
 
 void switch_out() {
@@ -145,12 +152,83 @@ void try_release_block() {
 
 }  // namespace
 
-void* device_alloc(size_t bytes) {
-  void* p = nullptr;
-  if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
-  return p;
+// B200EMU_GUARD=1: every "device" allocation ends (rounded up to 16 bytes, the widest vector access) right before an
+// inaccessible page, and is preceded by one, so that a kernel reading or writing past either end of an exact-size array
+// faults here instead of passing silently -- what a cudaMalloc granule or torch's caching allocator would hide on a GPU.
+static int guard_mode() {
+  static int g = -1;
+  if (g < 0) {
+    const char* e = getenv("B200EMU_GUARD");
+    g = (e && atoi(e) > 0) ? 1 : 0;
+  }
+  return g;
 }
-void device_free(void* p) { free(p); }
+static std::map<void*, std::pair<void*, size_t>> g_guarded;  // user pointer -> (mapping, mapped bytes)
+
+// ---------------------------------------------------------------------------------------------- schedule order
+static int g_order = -1;  // 0 forward, 1 reverse, 2 random
+static unsigned long long g_rng = 0x9E3779B97F4A7C15ull;
+static std::vector<int> g_perm;
+static void order_init() {
+  if (g_order >= 0) return;
+  g_order = 0;
+  if (const char* e = getenv("B200EMU_ORDER")) {
+    if (!strncmp(e, "reverse", 7)) g_order = 1;
+    if (!strncmp(e, "random", 6)) {
+      g_order = 2;
+      if (e[6] == ':') g_rng ^= strtoull(e + 7, nullptr, 10) * 0xD1B54A32D192ED03ull;
+    }
+  }
+}
+static int pass_order(int i, int n) {
+  if (g_order == 0) return i;
+  if (g_order == 1) return n - 1 - i;
+  if (i == 0) {  // new pass: new permutation (Fisher-Yates with a xorshift generator)
+    g_perm.resize(n);
+    for (int k = 0; k < n; ++k) g_perm[k] = k;
+    for (int k = n - 1; k > 0; --k) {
+      g_rng ^= g_rng << 13;
+      g_rng ^= g_rng >> 7;
+      g_rng ^= g_rng << 17;
+      std::swap(g_perm[k], g_perm[(int)(g_rng % (unsigned)(k + 1))]);
+    }
+  }
+  return g_perm[i];
+}
+
+void* device_alloc(size_t bytes) {
+  if (!guard_mode()) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
+    return p;
+  }
+  const size_t page = 4096;
+  const size_t payload = ((bytes ? bytes : 1) + 15) & ~(size_t)15;
+  const size_t body = (payload + page - 1) / page * page;
+  const size_t total = body + 2 * page;
+  char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == (char*)MAP_FAILED) return nullptr;
+  mprotect(base, page, PROT_NONE);
+  mprotect(base + page + body, page, PROT_NONE);
+  char* user = base + page + body - payload;
+  memset(base + page, 0xA5, body);  // uninitialised device memory is not zero
+  g_guarded[user] = {base, total};
+  return user;
+}
+void device_free(void* p) {
+  if (!p) return;
+  if (!guard_mode()) {
+    free(p);
+    return;
+  }
+  auto it = g_guarded.find(p);
+  if (it == g_guarded.end()) {
+    fprintf(stderr, "b200emu: cudaFree of a pointer cudaMalloc did not return\n");
+    abort();
+  }
+  munmap(it->second.first, it->second.second);
+  g_guarded.erase(it);
+}
 
 ThreadCtx* cur() { return &g_fibers[g_cur].tc; }
 void* dyn_smem() { return g_dyn_smem; }
@@ -219,6 +297,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
       }
     }
   }
+  order_init();
   g_body = &body;
   g_nthreads = nthreads;
   const int nwarps = (nthreads + 31) / 32;
@@ -227,6 +306,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_warps.assign(nwarps, Warp());
         g_mbars.clear();
+        g_pending.clear();
         g_alive_threads = nthreads;
         g_block_arrived = 0;
         for (int t = 0; t < nthreads; ++t) {
@@ -242,21 +322,43 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
           g_warps[t >> 5].alive |= 1u << (t & 31);
           fiber_prepare(f);
         }
-        // round-robin until every fiber has returned; a full pass without progress is a deadlock
+        // round-robin until every fiber has returned; a full window of passes without progress is a deadlock.  The
+        // order of a pass is a knob (B200EMU_ORDER=forward|reverse|random[:seed]): code that is correct only because
+        // lower threads happen to run first (a missing __syncwarp / __syncthreads) fails under the other orders.  Under
+        // `random` every warp of a block also gets its own speed (it runs in one pass out of 1..4), so that a producer
+        // warp can run ahead of slow consumers, or the other way round: a missing "slot is free" wait, which equal speeds
+        // never expose, corrupts the result here.
+        unsigned char period[kMaxThreads / 32];
+        for (int w = 0; w < nwarps; ++w) {
+          period[w] = 1;
+          if (g_order == 2) {
+            g_rng ^= g_rng << 13;
+            g_rng ^= g_rng >> 7;
+            g_rng ^= g_rng << 17;
+            period[w] = (unsigned char)(1 + (g_rng >> 20) % 4);
+          }
+        }
+        constexpr unsigned kWindow = 12;  // lcm of the periods: every warp has run at least once
+        unsigned pass = 0;
+        unsigned long window_start = g_progress;
         while (g_alive_threads > 0) {
-          const unsigned long before = g_progress;
-          for (int t = 0; t < nthreads; ++t) {
-            if (g_fibers[t].done) continue;
+          for (int i = 0; i < nthreads; ++i) {
+            const int t = pass_order(i, nthreads);
+            if (g_fibers[t].done || pass % period[t >> 5] != 0) continue;
             g_cur = t;
             switch_in(g_fibers[t]);
           }
           g_cur = -1;
-          if (g_progress == before && g_alive_threads > 0) {
-            fprintf(stderr, "b200emu: deadlock in block (%u,%u,%u): %d threads alive, %d at the block barrier\n", bx, by, bz,
-                    g_alive_threads, g_block_arrived);
-            for (int w = 0; w < nwarps; ++w)
-              fprintf(stderr, "  warp %d: alive %08x arrived %08x released %08x\n", w, g_warps[w].alive, g_warps[w].arrived, g_warps[w].released);
-            abort();
+          if (++pass % kWindow == 0) {
+            if (g_progress == window_start && g_alive_threads > 0) {
+              fprintf(stderr, "b200emu: deadlock in block (%u,%u,%u): %d threads alive, %d at the block barrier\n", bx, by, bz,
+                      g_alive_threads, g_block_arrived);
+              for (int w = 0; w < nwarps; ++w)
+                fprintf(stderr, "  warp %d: alive %08x arrived %08x released %08x\n", w, g_warps[w].alive, g_warps[w].arrived,
+                        g_warps[w].released);
+              abort();
+            }
+            window_start = g_progress;
           }
         }
         g_cur = -1;
@@ -306,8 +408,41 @@ void mbar_complete_tx(void* bar, unsigned bytes) {
   ++g_progress;
   mbar_check(b);
 }
+// cp.async.bulk global -> shared.  The copy is ASYNCHRONOUS on the hardware: nothing may read the destination before
+// its mbarrier completes the phase.  To make code that breaks this rule fail here too, the destination is filled with
+// 0xFF at issue time and the bytes are delivered only when some thread polls that barrier.
+
+void bulk_copy_async(void* smem_dst, const void* gsrc, unsigned bytes, void* bar) {
+  if ((((uintptr_t)smem_dst | (uintptr_t)gsrc | bytes) & 15u) != 0) {
+    fprintf(stderr, "b200emu: cp.async.bulk with unaligned operands (dst %p src %p bytes %u)\n", smem_dst, gsrc, bytes);
+    abort();
+  }
+  if ((unsigned char*)smem_dst < g_dyn_smem || (unsigned char*)smem_dst + bytes > g_dyn_smem + sizeof(g_dyn_smem)) {
+    fprintf(stderr, "b200emu: cp.async.bulk destination outside dynamic shared memory\n");
+    abort();
+  }
+  memset(smem_dst, 0xFF, bytes);
+  g_pending.push_back({smem_dst, gsrc, bytes, bar});
+  ++g_progress;
+}
+
+static void deliver_pending(void* bar) {
+  size_t keep = 0;
+  for (size_t i = 0; i < g_pending.size(); ++i) {
+    PendingCopy c = g_pending[i];
+    if (c.bar == bar) {
+      memcpy(c.dst, c.src, c.bytes);
+      mbar_complete_tx(bar, c.bytes);
+    } else {
+      g_pending[keep++] = c;
+    }
+  }
+  g_pending.resize(keep);
+}
+
 bool mbar_test_wait(void* bar, unsigned parity) {
   // true once the phase with the given parity has completed, i.e. the phase in progress has the other parity
+  deliver_pending(bar);
   MBar& b = g_mbars[bar];
   if (b.phase != parity) return true;
   switch_out();
