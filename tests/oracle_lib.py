@@ -59,6 +59,10 @@ class Oracle:
         L.okk_spadd_sorted_symbolic.restype = i64
         L.okk_spadd_unsorted_symbolic.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp]
         L.okk_spadd_unsorted_symbolic.restype = i64
+        for sfx, ft in (("f64", f64), ("f32", f32)):
+            getattr(L, f"okk_bsr_spmv_v42_{sfx}").argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
+            getattr(L, f"okk_bsr_spmv_v41_{sfx}").argtypes = [C.c_char, i32, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
+            getattr(L, f"okk_bsr_to_crs_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         self.ref = None
         rpath = os.path.join(ODIR, "_ref", "libkkref.so")
         if os.path.exists(rpath):
@@ -66,6 +70,9 @@ class Oracle:
             R.kkref_spgemm_symbolic.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]
             R.kkref_spgemm_symbolic.restype = i64
             R.kkref_spgemm_numeric_f64.argtypes = [i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]
+            if hasattr(R, "kkref_bsr_spmv_v42_f64"):
+                R.kkref_bsr_spmv_v42_f64.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f64, f64]
+                R.kkref_bsr_spmv_v42_f32.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f32, f32]
 
     @staticmethod
     def _sfx(a):
@@ -215,6 +222,41 @@ class Oracle:
         getattr(self.lib, "okk_spadd_unsorted_numeric_" + sfx)(m, _p(rpA), _p(ciA), _p(vA), alpha, _p(rpB), _p(ciB), _p(vB), beta,
                                                                _p(rpC), _p(ciC), _p(vC), _p(apos), _p(bpos))
         return rpC, ciC, vC
+
+    # ---- BsrMatrix SpMV (oracle/kk_oracle_bsr.c) ----
+    @staticmethod
+    def _as2d(a):
+        return a.reshape(-1, 1) if a.ndim == 1 else a
+
+    def bsr_spmv_v42(self, bs, rp, ci, v, x, y, alpha, beta, ref=False):
+        """B1 (mode N, the order of the reference's GPU-space functor); x, y rank 1 or 2, y updated in place.
+        ref=True runs the reference's own functor (oracle/_ref) instead of the restatement."""
+        X, Y = self._as2d(x), self._as2d(y)
+        xr, xc = self._strides(X)
+        yr, yc = self._strides(Y)
+        lib = self.ref if ref else self.lib
+        name = ("kkref_bsr_spmv_v42_" if ref else "okk_bsr_spmv_v42_") + self._sfx(v)
+        getattr(lib, name)(len(rp) - 1, bs, X.shape[1], _p(rp), _p(ci), _p(v), _p(X), xr, xc, _p(Y), yr, yc, alpha, beta)
+        return y
+
+    def bsr_spmv_v41(self, mode, bs, nb_cols, rp, ci, v, x, y, alpha, beta):
+        """B2 / B3: the host (Serial) functors for N, C, T, H; nb_cols = block columns of A."""
+        X, Y = self._as2d(x), self._as2d(y)
+        xr, xc = self._strides(X)
+        yr, yc = self._strides(Y)
+        mb = len(rp) - 1
+        ylen_b = nb_cols if mode in "THth" else mb
+        getattr(self.lib, "okk_bsr_spmv_v41_" + self._sfx(v))(mode.encode(), mb, ylen_b, bs, X.shape[1], _p(rp), _p(ci), _p(v), _p(X),
+                                                             xr, xc, _p(Y), yr, yc, alpha, beta)
+        return y
+
+    def bsr_to_crs(self, bs, rp, ci, v):
+        mb = len(rp) - 1
+        crp = np.zeros(mb * bs + 1, dtype=np.int32)
+        cci = np.empty(len(ci) * bs * bs, dtype=np.int32)
+        cv = np.empty(len(ci) * bs * bs, dtype=v.dtype)
+        getattr(self.lib, "okk_bsr_to_crs_" + self._sfx(v))(mb, bs, _p(rp), _p(ci), _p(v), _p(crp), _p(cci), _p(cv))
+        return crp, cci, cv
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)
