@@ -280,6 +280,43 @@ int b200sp_write_crs_f32(const char* path, int m, int n, int64_t nnz, const int*
                          const float* vals);
 void b200sp_host_free(void* p);
 
+/* ---- BsrMatrix SpMV / SpMM --------------------------------------------------
+ * Replaces SPMV_BSRMATRIX<Kokkos::Cuda, ..., tpl = true>::spmv_bsrmatrix -> spmv_bsr_cusparse
+ * (sparse/tpls/KokkosSparse_spmv_bsrmatrix_tpl_spec_decl.hpp:279-352,469-493) and
+ * SPMV_MV_BSRMATRIX<...>::spmv_mv_bsrmatrix -> spmv_mv_bsr_cusparse (:372-455,522-546), plus the native
+ * functors the front end falls back to for the modes cuSPARSE lacks (KokkosSparse_spmv.hpp:322-375;
+ * sparse/impl/KokkosSparse_spmv_bsrmatrix_impl_v42.hpp, ..._impl.hpp:707-834).
+ *
+ * A is mb x nb blocks of bs x bs (BsrMatrix, sparse/src/KokkosSparse_BsrMatrix.hpp:355-370): row_ptr has
+ * mb+1 entries, col_idx nnzb block columns, vals nnzb*bs*bs values with every block row-major.
+ * y = beta*y + alpha*op(A)*x, op by mode 'N','C' (= N for real scalars),'T','H' (= T); beta == 0 overwrites y
+ * (NaN-safe), alpha == 0 only scales.  Unlike the cuSPARSE leg every mode and bs == 1 are accepted (bs == 1 is
+ * forwarded to the CrsMatrix path as the reference's front end does, KokkosSparse_spmv.hpp:169-185).
+ * The plan caches the tile analysis of the last block structure (keyed on row_ptr, mb, nnzb, bs), i.e. what
+ * SPMVHandle::tpl_rank1 / tpl_rank2 hold for cuSPARSE; one plan per matrix, like the handle.
+ * Errors: B200SP_ERR_INVALID_ARGUMENT for bs < 1 (BsrMatrix.hpp:429-433), an unknown mode, null arrays,
+ * dimensions beyond int32.  Asynchronous on `stream`. */
+typedef struct b200sp_bsr_plan b200sp_bsr_plan;
+int b200sp_bsr_plan_create(b200sp_bsr_plan** plan);
+int b200sp_bsr_plan_destroy(b200sp_bsr_plan* plan, void* stream);
+int b200sp_bsr_spmv_f64_i32(b200sp_bsr_plan* plan, void* stream, char mode, int mb, int nb, int64_t nnzb, int bs,
+                            double alpha, const int* row_ptr, const int* col_idx, const double* vals,
+                            const double* x, double beta, double* y);
+int b200sp_bsr_spmv_f32_i32(b200sp_bsr_plan* plan, void* stream, char mode, int mb, int nb, int64_t nnzb, int bs,
+                            float alpha, const int* row_ptr, const int* col_idx, const float* vals,
+                            const float* x, float beta, float* y);
+/* k columns; X is (cols of op(A)) x k, Y is (rows of op(A)) x k; ld* = leading dimension in elements, *_row_major
+ * as for b200sp_spmm_* (LayoutRight = 1, LayoutLeft = 0; the cuSPARSE leg takes LayoutLeft only, decl:365-371). */
+int b200sp_bsr_spmm_f64_i32(b200sp_bsr_plan* plan, void* stream, char mode, int mb, int nb, int64_t nnzb, int bs, int k,
+                            double alpha, const int* row_ptr, const int* col_idx, const double* vals,
+                            const double* X, int64_t ldx, int x_row_major, double beta, double* Y, int64_t ldy,
+                            int y_row_major);
+int b200sp_bsr_spmm_f32_i32(b200sp_bsr_plan* plan, void* stream, char mode, int mb, int nb, int64_t nnzb, int bs, int k,
+                            float alpha, const int* row_ptr, const int* col_idx, const float* vals, const float* X,
+                            int64_t ldx, int x_row_major, float beta, float* Y, int64_t ldy, int y_row_major);
+/* Name of the kernel the plan's last call used; static storage (tests / bench). */
+const char* b200sp_bsr_last_kernel(const b200sp_bsr_plan* plan);
+
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */
 int64_t b200sp_launch_count(void);

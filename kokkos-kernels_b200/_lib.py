@@ -58,6 +58,13 @@ SPARSE_API = {
     "b200sp_write_crs_f64": (i32, [C.c_char_p, i32, i32, i64, vp, vp, vp]),
     "b200sp_write_crs_f32": (i32, [C.c_char_p, i32, i32, i64, vp, vp, vp]),
     "b200sp_host_free": (None, [vp]),
+    "b200sp_bsr_plan_create": (i32, [C.POINTER(vp)]),
+    "b200sp_bsr_plan_destroy": (i32, [vp, vp]),
+    "b200sp_bsr_spmv_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, f64, vp, vp, vp, vp, f64, vp]),
+    "b200sp_bsr_spmv_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, f32, vp, vp, vp, vp, f32, vp]),
+    "b200sp_bsr_spmm_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, i32, f64, vp, vp, vp, vp, i64, i32, f64, vp, i64, i32]),
+    "b200sp_bsr_spmm_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, i32, f32, vp, vp, vp, vp, i64, i32, f32, vp, i64, i32]),
+    "b200sp_bsr_last_kernel": (C.c_char_p, [vp]),
     "b200sp_launch_count": (i64, []),
     "b200sp_spmv_last_kernel": (C.c_char_p, [vp]),
     "b200sp_spmv_plan_tune": (i32, [vp, i32, i32, i32]),

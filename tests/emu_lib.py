@@ -120,3 +120,38 @@ def spgemm(A, B, m, n, k, dtype):
         return rpC, ciC, vC, mx.value
     finally:
         ok(L.b200sp_spgemm_plan_destroy(h, None))
+
+
+class BsrPlan:
+    def __init__(self):
+        self.h = C.c_void_p()
+        ok(lib().b200sp_bsr_plan_create(C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            ok(lib().b200sp_bsr_plan_destroy(self.h, None))
+            self.h = C.c_void_p()
+
+    def kernel(self):
+        return lib().b200sp_bsr_last_kernel(self.h).decode()
+
+
+def bsr_spmv(plan, mode, mb, nb, bs, rp, ci, v, x, y, alpha, beta):
+    fn = getattr(lib(), "b200sp_bsr_spmv_%s_i32" % sfx(v.dtype))
+    ok(fn(plan.h, None, mode.encode(), mb, nb, len(ci), bs, scalar(v.dtype, alpha), ptr(rp), ptr(ci), ptr(v), ptr(x), scalar(v.dtype, beta),
+          ptr(y)))
+
+
+def bsr_spmm(plan, mode, mb, nb, bs, rp, ci, v, X, Y, alpha, beta):
+    fn = getattr(lib(), "b200sp_bsr_spmm_%s_i32" % sfx(v.dtype))
+    it = v.dtype.itemsize
+
+    def lay(a):
+        if a.shape[1] == 1 or a.strides[0] == it:  # column-major (LayoutLeft)
+            return max(a.strides[1] // it, a.shape[0]), 0
+        return a.strides[0] // it, 1
+
+    ldx, rmx = lay(X)
+    ldy, rmy = lay(Y)
+    ok(fn(plan.h, None, mode.encode(), mb, nb, len(ci), bs, X.shape[1], scalar(v.dtype, alpha), ptr(rp), ptr(ci), ptr(v), ptr(X), ldx, rmx,
+          scalar(v.dtype, beta), ptr(Y), ldy, rmy))
