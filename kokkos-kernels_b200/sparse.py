@@ -15,6 +15,7 @@ torch CUDA tensors, compute is libb200sparse through the C ABI):
   SPADDHandle / spadd_symbolic / spadd_numeric
                                  sparse/src/KokkosSparse_spadd_handle.hpp:24-137, KokkosSparse_spadd.hpp:29-319
   transpose_matrix               sparse/src/KokkosSparse_Utils.hpp:338-398
+  BsrMatrix (spmv accepts it)    sparse/src/KokkosSparse_BsrMatrix.hpp:317-520, KokkosSparse_spmv.hpp:113,169-185,322-375
 
 PyTorch is plumbing here (device memory + streams); there is no torch compute
 on this path and no CPU fallback.
@@ -27,11 +28,14 @@ from . import _lib
 from ._lib import B200SparseError, B200SparseInvalidArgument, check
 
 # SPMVAlgorithm (spmv_handle.hpp:32-47)
-SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH = range(5)
+SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH, SPMV_BSR_V41, SPMV_BSR_V42, SPMV_BSR_TC = range(8)
 # SPGEMMAlgorithm subset that matters here (spgemm_handle.hpp:44-87)
 SPGEMM_KK, SPGEMM_KK_MEMORY, SPGEMM_KK_SPEED, SPGEMM_KK_LP, SPGEMM_DEBUG, SPGEMM_SERIAL = range(6)
 
-_ALGO_TO_C = {SPMV_DEFAULT: 0, SPMV_FAST_SETUP: 1, SPMV_NATIVE: 1, SPMV_MERGE_PATH: 2, SPMV_NATIVE_MERGE_PATH: 2}
+# the BsrMatrix-only algorithm requests (V41 / V42 / tensor cores) name reference-native kernels; here they select the one
+# BsrMatrix path and, on a CrsMatrix, the default
+_ALGO_TO_C = {SPMV_DEFAULT: 0, SPMV_FAST_SETUP: 1, SPMV_NATIVE: 1, SPMV_MERGE_PATH: 2, SPMV_NATIVE_MERGE_PATH: 2, SPMV_BSR_V41: 0,
+              SPMV_BSR_V42: 0, SPMV_BSR_TC: 0}
 
 
 def _ptr(t):
@@ -61,6 +65,40 @@ class CrsMatrix:
         return self.entries.numel()
 
 
+class BsrMatrix:
+    """KokkosSparse::Experimental::BsrMatrix: graph.row_map / graph.entries over BLOCKS, values =
+    nnzb*blockDim*blockDim with every block row-major (BsrMatrix.hpp:355-370); numRows()/numCols() count
+    block rows / block columns, numPointRows()/numPointCols() the point dimensions (:880-900)."""
+
+    def __init__(self, row_map, entries, values, ncols_blocks, block_dim):
+        assert row_map.dtype == torch.int32 and entries.dtype == torch.int32
+        if int(block_dim) < 1:  # BsrMatrix.hpp:429-433
+            raise B200SparseError(f"KokkosSparse::Experimental::BsrMatrix: Inappropriate block size: {block_dim}")
+        if values.numel() != entries.numel() * int(block_dim) ** 2:
+            raise B200SparseError("BsrMatrix: values must hold nnz*blockDim*blockDim entries")
+        self.row_map, self.entries, self.values = row_map, entries, values
+        self._ncols = int(ncols_blocks)
+        self._bs = int(block_dim)
+
+    def blockDim(self):
+        return self._bs
+
+    def numRows(self):
+        return max(self.row_map.numel() - 1, 0)
+
+    def numCols(self):
+        return self._ncols
+
+    def numPointRows(self):
+        return self.numRows() * self._bs
+
+    def numPointCols(self):
+        return self._ncols * self._bs
+
+    def nnz(self):
+        return self.entries.numel()
+
+
 class SPMVHandle:
     """Owns the per-matrix plan like SPMVHandle owns tpl_rank1/tpl_rank2; all
     calls through one handle must use the same matrix (spmv_handle.hpp:276-277)."""
@@ -70,7 +108,13 @@ class SPMVHandle:
             raise B200SparseInvalidArgument(f"unknown SPMVAlgorithm {algo}")
         self.algo = algo
         self._plan = C.c_void_p(0)
+        self._bsr_plan = C.c_void_p(0)  # created by the first BsrMatrix call (the handle then only ever sees that matrix)
         check(_lib.sparse().b200sp_spmv_plan_create(C.byref(self._plan), _ALGO_TO_C[algo]))
+
+    def _bsr(self):
+        if not self._bsr_plan:
+            check(_lib.sparse().b200sp_bsr_plan_create(C.byref(self._bsr_plan)))
+        return self._bsr_plan
 
     def get_algorithm(self):
         return self.algo
@@ -83,12 +127,17 @@ class SPMVHandle:
         check(_lib.sparse().b200sp_spmv_plan_tune(self._plan, cfg, lanes_per_row, ctas_per_sm))
 
     def last_kernel(self):
+        if self._bsr_plan:
+            return _lib.sparse().b200sp_bsr_last_kernel(self._bsr_plan).decode()
         return _lib.sparse().b200sp_spmv_last_kernel(self._plan).decode()
 
     def __del__(self):
         try:
+            st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
+            if self._bsr_plan:
+                _lib.sparse().b200sp_bsr_plan_destroy(self._bsr_plan, st)
+                self._bsr_plan = C.c_void_p(0)
             if self._plan:
-                st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
                 _lib.sparse().b200sp_spmv_plan_destroy(self._plan, st)
                 self._plan = C.c_void_p(0)
         except Exception:
@@ -106,7 +155,8 @@ def spmv(handle, mode, alpha, A, x, beta, y):
     (the convenience overload builds a throw-away SPMV_FAST_SETUP handle,
     KokkosSparse_spmv.hpp:465-474)."""
     m0 = _mode_char(mode)
-    m, n = A.numRows(), A.numCols()
+    is_bsr = isinstance(A, BsrMatrix)
+    m, n = (A.numPointRows(), A.numPointCols()) if is_bsr else (A.numRows(), A.numCols())
     if x.dim() != y.dim() or x.dim() not in (1, 2):
         raise B200SparseError("KokkosSparse::spmv: x and y must both be rank 1 or both rank 2")
     xcols = x.shape[1] if x.dim() == 2 else 1
@@ -130,6 +180,9 @@ def spmv(handle, mode, alpha, A, x, beta, y):
     if not f64 and x.dtype != torch.float32:
         raise B200SparseError("b200sparse: only double and float are instantiated")
     mc = m0.encode()
+    if is_bsr:
+        tmp = handle if handle is not None else SPMVHandle(SPMV_FAST_SETUP)
+        return _spmv_bsr(lib, tmp._bsr(), mc, alpha, A, x, beta, y, f64, xcols)
     if x.dim() == 1:
         if x.stride(0) != 1 or y.stride(0) != 1:
             raise B200SparseError("b200sparse: rank-1 x and y must be contiguous")
@@ -151,6 +204,34 @@ def spmv(handle, mode, alpha, A, x, beta, y):
     fn = lib.b200sp_spmm_f64_i32 if f64 else lib.b200sp_spmm_f32_i32
     check(fn(plan, _stream(), mc, m, n, A.nnz(), xcols, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
              _ptr(x), ldx, xrm, beta, _ptr(y), ldy, yrm))
+    return y
+
+
+def _mv_layout(t):
+    # LayoutRight: (ld, 1); LayoutLeft: (ld, 0)
+    if t.shape[1] == 1 or t.stride(1) == 1:
+        return (max(t.stride(0), 1) if t.shape[0] > 1 else max(t.shape[1], 1)), 1
+    if t.stride(0) == 1:
+        return t.stride(1), 0
+    raise B200SparseError("b200sparse: X/Y must be LayoutLeft or LayoutRight")
+
+
+def _spmv_bsr(lib, plan, mc, alpha, A, x, beta, y, f64, xcols):
+    """SPMV_BSRMATRIX / SPMV_MV_BSRMATRIX (sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:165-283) on the
+    b200sp_bsr_* entries; every mode and blockDim() == 1 are accepted."""
+    mb, nb, bs = A.numRows(), A.numCols(), A.blockDim()
+    if x.dim() == 1:
+        if x.stride(0) != 1 or y.stride(0) != 1:
+            raise B200SparseError("b200sparse: rank-1 x and y must be contiguous")
+        fn = lib.b200sp_bsr_spmv_f64_i32 if f64 else lib.b200sp_bsr_spmv_f32_i32
+        check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(x), beta,
+                 _ptr(y)))
+        return y
+    ldx, xrm = _mv_layout(x)
+    ldy, yrm = _mv_layout(y)
+    fn = lib.b200sp_bsr_spmm_f64_i32 if f64 else lib.b200sp_bsr_spmm_f32_i32
+    check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, xcols, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(x), ldx,
+             xrm, beta, _ptr(y), ldy, yrm))
     return y
 
 

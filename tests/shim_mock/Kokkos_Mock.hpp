@@ -114,6 +114,36 @@ class CrsMatrix {
   size_t nnz_;
 };
 
+namespace Experimental {
+// BsrMatrix: the members the shim touches (sparse/src/KokkosSparse_BsrMatrix.hpp:317-520); numRows / numCols / nnz
+// count BLOCKS (:868-889)
+template <class Scalar, class Ordinal, class Dev, class MT, class Offset>
+class BsrMatrix {
+ public:
+  using UM = Kokkos::MemoryTraits<Kokkos::Unmanaged>;
+  struct Graph {
+    Kokkos::View<Offset*, Kokkos::LayoutLeft, Dev, UM> row_map;
+    Kokkos::View<Ordinal*, Kokkos::LayoutLeft, Dev, UM> entries;
+  } graph;
+  Kokkos::View<Scalar*, Kokkos::LayoutRight, Dev, UM> values;
+  BsrMatrix(int nbrows, int nbcols, size_t nnzb, Scalar* v, Offset* rp, Ordinal* ci, int blockDim)
+      : nrows_(nbrows), ncols_(nbcols), nnz_(nnzb), blockDim_(blockDim) {
+    graph.row_map = {rp, (size_t)nbrows + 1};
+    graph.entries = {ci, nnzb};
+    values        = {v, nnzb * blockDim * blockDim};
+  }
+  int numRows() const { return nrows_; }
+  int numCols() const { return ncols_; }
+  size_t nnz() const { return nnz_; }
+  int blockDim() const { return blockDim_; }
+
+ private:
+  int nrows_, ncols_;
+  size_t nnz_;
+  int blockDim_;
+};
+}  // namespace Experimental
+
 namespace Impl {
 template <typename ExecutionSpace>
 struct TPL_SpMV_Data {
@@ -156,6 +186,25 @@ struct SPMV;  // only the TPL specialisations exist in the mock
 template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector, bool integerScalar = false,
           bool tpl_spec_avail = spmv_mv_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value>
 struct SPMV_MV;
+
+// sparse/tpls/KokkosSparse_spmv_bsrmatrix_tpl_spec_avail.hpp:27-30,121-124 and
+// sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:89-112 (eti always true in the mock, as in a library build)
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
+struct spmv_bsrmatrix_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
+struct spmv_mv_bsrmatrix_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector,
+          bool tpl_spec_avail = spmv_bsrmatrix_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value,
+          bool eti_spec_avail = true>
+struct SPMV_BSRMATRIX;
+template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector, const bool integerScalarType = false,
+          bool tpl_spec_avail = spmv_mv_bsrmatrix_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value,
+          bool eti_spec_avail = true>
+struct SPMV_MV_BSRMATRIX;
 }  // namespace Impl
 }  // namespace KokkosSparse
 

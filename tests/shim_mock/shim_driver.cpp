@@ -9,10 +9,13 @@
 #include "KokkosSparse_spgemm_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spadd_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spadd_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_decl.hpp"
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 using namespace KokkosSparse;
@@ -33,6 +36,9 @@ using SV    = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UM>;
 
 static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::value, "rank-1 specialisation must be available");
 static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
+using BMat  = Experimental::BsrMatrix<const double, const int, Dev, UM, const int>;
+static_assert(Impl::spmv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XVec, YVec>::value, "BsrMatrix rank-1 must be available");
+static_assert(Impl::spmv_mv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XMV, YMV>::value, "BsrMatrix rank-2 must be available");
 static_assert(Impl::spgemm_symbolic_tpl_spec_avail<KH, CIV, CIV, CIV, CIV, IV>::value, "spgemm symbolic must be available");
 static_assert(Impl::spgemm_numeric_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, CIV, IV, SV>::value, "spgemm numeric");
 static_assert(Impl::spadd_symbolic_tpl_spec_avail<Kokkos::Cuda, KH, CIV, CIV, CIV, CIV, IV>::value, "spadd symbolic must be available");
@@ -46,7 +52,9 @@ T* to_dev(const std::vector<T>& h) {
   return d;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
+  const bool with_bsr = argc > 1 && std::string(argv[1]) == "--bsr";
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     std::printf("no CUDA device\n");
@@ -195,6 +203,72 @@ int main() {
     cudaFree(d_rpC);
     cudaFree(d_ciC);
     cudaFree(d_vC);
+  }
+  if (with_bsr) {
+    // BsrMatrix: block-tridiagonal, 3 x 3 blocks, through SPMV_BSRMATRIX<...,true,true> (N) and
+    // SPMV_MV_BSRMATRIX<...,false,true,true> ('T', 2 columns)
+    const int mb = 20000, bs = 3;
+    std::vector<int> brp(mb + 1, 0), bci;
+    std::vector<double> bva;
+    for (int i = 0; i < mb; ++i) {
+      for (int j = i - 1; j <= i + 1; ++j)
+        if (j >= 0 && j < mb) {
+          bci.push_back(j);
+          for (int q = 0; q < bs * bs; ++q) bva.push_back(0.5 + 0.01 * ((i * 5 + j * 3 + q) % 13));
+        }
+      brp[i + 1] = (int)bci.size();
+    }
+    const int np = mb * bs;
+    std::vector<double> bx(np), by0(np);
+    for (int i = 0; i < np; ++i) {
+      bx[i]  = 0.5 + 0.25 * std::cos(0.01 * i);
+      by0[i] = 1.0 + 0.001 * (i % 977);
+    }
+    int *d_brp = to_dev(brp), *d_bci = to_dev(bci);
+    double *d_bva = to_dev(bva), *d_bx = to_dev(bx), *d_by = to_dev(by0);
+    Hnd handle(SPMV_DEFAULT);
+    BMat A(mb, mb, bci.size(), d_bva, d_brp, d_bci, bs);
+    Impl::SPMV_BSRMATRIX<Kokkos::Cuda, Hnd, BMat, XVec, YVec>::spmv_bsrmatrix(exec, &handle, "N", 2.0, A, XVec(d_bx, np), 0.5,
+                                                                              YVec(d_by, np));
+    exec.fence();
+    std::vector<double> y(np);
+    cudaMemcpy(y.data(), d_by, sizeof(double) * np, cudaMemcpyDeviceToHost);
+    int f5 = 0;
+    for (int i = 0; i < mb; ++i)
+      for (int lr = 0; lr < bs; ++lr) {
+        double s = 0;
+        for (int q = brp[i]; q < brp[i + 1]; ++q)
+          for (int c = 0; c < bs; ++c) s += bva[(size_t)q * bs * bs + lr * bs + c] * bx[bci[q] * bs + c];
+        const double e = 0.5 * by0[i * bs + lr] + 2.0 * s;
+        if (std::fabs(y[i * bs + lr] - e) > 1e-12 * (1 + std::fabs(e))) ++f5;
+      }
+    std::printf("BsrMatrix spmv through SPMV_BSRMATRIX<...,true,true>::spmv_bsrmatrix : %d mismatches\n", f5);
+    const int k = 2;
+    std::vector<double> X(np * k), Y(np * k, 0.0), E(np * k, 0.0);
+    for (int j = 0; j < k; ++j)
+      for (int i = 0; i < np; ++i) X[j * np + i] = bx[i] * (j + 1);
+    double *d_X = to_dev(X), *d_Y = to_dev(Y);
+    Impl::SPMV_MV_BSRMATRIX<Kokkos::Cuda, Hnd, BMat, XMV, YMV>::spmv_mv_bsrmatrix(exec, &handle, "T", 1.0, A, XMV(d_X, np, k), 0.0,
+                                                                                  YMV(d_Y, np, k));
+    exec.fence();
+    cudaMemcpy(Y.data(), d_Y, sizeof(double) * np * k, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < mb; ++i)
+      for (int q = brp[i]; q < brp[i + 1]; ++q)
+        for (int lr = 0; lr < bs; ++lr)
+          for (int c = 0; c < bs; ++c)
+            for (int j = 0; j < k; ++j) E[j * np + bci[q] * bs + c] += bva[(size_t)q * bs * bs + lr * bs + c] * X[j * np + i * bs + lr];
+    int f6 = 0;
+    for (int i = 0; i < np * k; ++i)
+      if (std::fabs(Y[i] - E[i]) > 1e-12 * (1 + std::fabs(E[i]))) ++f6;
+    std::printf("BsrMatrix spmv 'T' rank-2 through SPMV_MV_BSRMATRIX<...,false,true,true>::spmv_mv_bsrmatrix : %d mismatches\n", f6);
+    failures += f5 + f6;
+    cudaFree(d_X);
+    cudaFree(d_Y);
+    cudaFree(d_brp);
+    cudaFree(d_bci);
+    cudaFree(d_bva);
+    cudaFree(d_bx);
+    cudaFree(d_by);
   }
   std::printf(failures ? "SHIM DRIVER FAILED\n" : "SHIM DRIVER OK\n");
   return failures ? 1 : 0;

@@ -109,11 +109,14 @@ def up_to_date():
     """True when the emulated library is newer than every file it is built from."""
     lib = os.path.join(OUT, "libb200sparse_emu.so")
     chk = os.path.join(OUT, "gpu_check_emu")
-    if not (os.path.exists(lib) and os.path.exists(chk)):
+    if not (os.path.exists(lib) and os.path.exists(chk) and os.path.exists(os.path.join(OUT, "shim_driver_emu"))):
         return False
     deps = [os.path.join(CSRC, n) for n in SOURCES + HEADERS]
     deps += [os.path.join(HERE, n) for n in ("cuda_emu.h", "emu_runtime.cpp", "build_emu.py", "cuda_runtime.h")]
     deps += [os.path.join(ROOT, "include", "b200sparse.h"), os.path.join(ROOT, "tools", "gpu_check.cpp")]
+    shim = os.path.join(ROOT, "kokkos-kernels_b200", "kokkos_shim")
+    deps += [os.path.join(shim, f) for f in os.listdir(shim)]
+    deps += [os.path.join(ROOT, "tests", "shim_mock", f) for f in ("shim_driver.cpp", "Kokkos_Mock.hpp")]
     newest = max(os.path.getmtime(d) for d in deps)
     return min(os.path.getmtime(lib), os.path.getmtime(chk)) >= newest
 
@@ -160,6 +163,14 @@ def build(verbose=True):
            os.path.join(ROOT, "tools", "gpu_check.cpp"), "-o", chk, "-L", OUT, "-lb200sparse_emu", "-L", libdir, "-lb200matgen",
            "-L", os.path.join(ROOT, "oracle"), "-lkkoracle", "-Wl,-rpath," + OUT, "-Wl,-rpath," + libdir,
            "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
+    if verbose:
+        print("[emu]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    # the Kokkos TPL shim driver (tests/shim_mock) against the emulated library: the specialisations run on the host
+    drv = os.path.join(OUT, "shim_driver_emu")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-DB200SP_EMU", "-I", HERE, "-I", os.path.join(ROOT, "tests", "shim_mock"),
+           "-I", os.path.join(ROOT, "kokkos-kernels_b200", "kokkos_shim"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "shim_mock", "shim_driver.cpp"), "-o", drv, "-L", OUT, "-lb200sparse_emu", "-Wl,-rpath," + OUT]
     if verbose:
         print("[emu]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -124,10 +124,12 @@ void bulk_copy_async(void* smem_dst, const void* gsrc, unsigned bytes, void* bar
 
 }  // namespace b200emu
 
+#ifndef B200EMU_HOST_PROGRAM  // host programs (tools/emu/cuda_runtime.h) only need the runtime API, not the built-ins
 #define threadIdx (b200emu::cur()->tid)
 #define blockIdx (b200emu::cur()->bid)
 #define blockDim (b200emu::cur()->bdim)
 #define gridDim (b200emu::cur()->gdim)
+#endif
 
 #define B200_EMU_LAUNCH(KERN, GRID, BLOCK, SMEM, ...) \
   b200emu::launch(dim3(GRID), dim3(BLOCK), (size_t)(SMEM), [&]() { KERN(__VA_ARGS__); })

@@ -71,6 +71,10 @@ void okk_spmv_transpose_f64(int nrow, int ncol, const int* rm, const int* ci, co
                             double alpha, double beta);
 void okk_spgemm_jacobi_f64(int m, int k, const int* rmA, const int* entA, const double* valA, const int* rmB, const int* entB,
                            const double* valB, const int* rmC, int* entC, double* valC, double omega, const double* dinv);
+void okk_bsr_spmv_v42_f64(int mb, int bs, int nvec, const int* rm, const int* ent, const double* val, const double* X, int64_t xr,
+                          int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta);
+void okk_bsr_spmv_v41_f64(char mode, int mb, int ylen_b, int bs, int nvec, const int* rm, const int* ent, const double* val,
+                          const double* X, int64_t xr, int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta);
 int okk_num_threads(void);
 // host generators (kokkos-kernels_b200/csrc/matgen.c)
 void b200gen_fill_f64(int64_t n, double* v, double lo, double hi, uint64_t seed);
@@ -1015,6 +1019,132 @@ static void suite_spmv_t() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: bsr -- BsrMatrix SpMV (N: TMA tile kernel and the per-row kernel; T: atomics) and SpMM against the oracle's
+// restatement of the reference functors (oracle/kk_oracle_bsr.c), with the algorithmic bandwidth of the N kernel
+// ------------------------------------------------------------------------------------------------
+static void bsr_case(const char* name, const Csr<double>& G, int bs) {
+  const int mb = G.m, nb = G.n;
+  const int64_t nnzb = G.nnz();
+  const int64_t np_r = (int64_t)mb * bs, np_c = (int64_t)nb * bs;
+  std::vector<double> vals((size_t)nnzb * bs * bs), x((size_t)np_c), xt((size_t)np_r), y0((size_t)np_r), yt0((size_t)np_c);
+  b200gen_fill_f64((int64_t)vals.size(), vals.data(), -1.0, 1.0, 11 + bs);
+  b200gen_fill_f64(np_c, x.data(), -1.0, 1.0, 1);
+  b200gen_fill_f64(np_r, xt.data(), -1.0, 1.0, 2);
+  b200gen_fill_f64(np_r, y0.data(), -1.0, 1.0, 3);
+  b200gen_fill_f64(np_c, yt0.data(), -1.0, 1.0, 4);
+  const double alpha = 1.25, beta = -0.5;
+  std::vector<double> va(vals), xa(x), xta(xt);
+  for (auto& t : va) t = std::fabs(t);
+  for (auto& t : xa) t = std::fabs(t);
+  for (auto& t : xta) t = std::fabs(t);
+  Dev<int> rp(G.rp), ci(G.ci);
+  Dev<double> v(vals), dx(x), dxt(xt), dy((size_t)np_r), dyt((size_t)np_c);
+  const double bytes = (double)nnzb * (bs * bs * 8.0 + 4.0) + (mb + 1) * 4.0 + (double)np_c * 8.0 + (double)np_r * 16.0;
+  // ---- N: tile kernel (default) and the per-row kernel
+  {
+    std::vector<double> yref(y0), scale(y0);
+    okk_bsr_spmv_v42_f64(mb, bs, 1, G.rp.data(), G.ci.data(), vals.data(), x.data(), 1, 0, yref.data(), 1, 0, alpha, beta);
+    for (auto& t : scale) t = std::fabs(t);
+    okk_bsr_spmv_v42_f64(mb, bs, 1, G.rp.data(), G.ci.data(), va.data(), xa.data(), 1, 0, scale.data(), 1, 0, std::fabs(alpha),
+                         std::fabs(beta));
+    for (int variant = 0; variant < 2; ++variant) {
+      if (variant) setenv("B200SP_BSR_KERNEL", "vector", 1);
+      else unsetenv("B200SP_BSR_KERNEL");
+      b200sp_bsr_plan* plan = nullptr;
+      SP(b200sp_bsr_plan_create(&plan));
+      float best = 1e30f;
+      std::vector<double> got;
+      for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaMemcpy(dy.p, y0.data(), y0.size() * sizeof(double), cudaMemcpyHostToDevice));
+        Timer t;
+        t.start();
+        SP(b200sp_bsr_spmv_f64_i32(plan, nullptr, 'N', mb, nb, nnzb, bs, alpha, rp.p, ci.p, v.p, dx.p, beta, dy.p));
+        const float ms = t.stop_ms();
+        if (rep > 0) best = std::min(best, ms);
+        got = dy.host();
+      }
+      double worst = 0;
+      for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, std::fabs(got[i] - yref[i]) / std::max(scale[i], 1e-300));
+      char nm[160];
+      snprintf(nm, sizeof(nm), "%s_bs%d/N_%s", name, bs, variant ? "vector" : "default");
+      record(nm, worst <= 1e-10, "mb=%d nnzb=%lld kernel=%s %.3f ms (%.0f GB/s algorithmic), max scaled err %.2e", mb, (long long)nnzb,
+             b200sp_bsr_last_kernel(plan), best, bytes / (best * 1e-3) / 1e9, worst);
+      b200sp_bsr_plan_destroy(plan, nullptr);
+    }
+    unsetenv("B200SP_BSR_KERNEL");
+  }
+  // ---- T (atomics) and a 5-column multivector in both modes
+  {
+    std::vector<double> yref(yt0), scale(yt0);
+    okk_bsr_spmv_v41_f64('T', mb, nb, bs, 1, G.rp.data(), G.ci.data(), vals.data(), xt.data(), 1, 0, yref.data(), 1, 0, alpha, beta);
+    for (auto& t : scale) t = std::fabs(t);
+    okk_bsr_spmv_v41_f64('T', mb, nb, bs, 1, G.rp.data(), G.ci.data(), va.data(), xta.data(), 1, 0, scale.data(), 1, 0, std::fabs(alpha),
+                         std::fabs(beta));
+    b200sp_bsr_plan* plan = nullptr;
+    SP(b200sp_bsr_plan_create(&plan));
+    CK(cudaMemcpy(dyt.p, yt0.data(), yt0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    Timer t;
+    t.start();
+    SP(b200sp_bsr_spmv_f64_i32(plan, nullptr, 'T', mb, nb, nnzb, bs, alpha, rp.p, ci.p, v.p, dxt.p, beta, dyt.p));
+    const float ms = t.stop_ms();
+    auto got = dyt.host();
+    double worst = 0;
+    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, std::fabs(got[i] - yref[i]) / std::max(scale[i], 1e-300));
+    char nm[160];
+    snprintf(nm, sizeof(nm), "%s_bs%d/T", name, bs);
+    record(nm, worst <= 1e-10, "kernel=%s %.3f ms (first call), max scaled err %.2e", b200sp_bsr_last_kernel(plan), ms, worst);
+    const int k = 5;
+    for (int rm = 0; rm <= 1; ++rm) {
+      const int64_t ldx = rm ? k + 1 : np_c + 3, ldy = rm ? k : np_r + 1;
+      const int64_t xr = rm ? ldx : 1, xc = rm ? 1 : ldx, yr = rm ? ldy : 1, yc = rm ? 1 : ldy;
+      std::vector<double> X((size_t)(rm ? np_c * ldx : ldx * k)), Y0((size_t)(rm ? np_r * ldy : ldy * k));
+      fill_vals(X, -1.0, 1.0, 31);
+      fill_vals(Y0, -1.0, 1.0, 32);
+      std::vector<double> Yref(Y0), Xa(X), Ys(Y0);
+      okk_bsr_spmv_v42_f64(mb, bs, k, G.rp.data(), G.ci.data(), vals.data(), X.data(), xr, xc, Yref.data(), yr, yc, alpha, beta);
+      for (auto& q : Xa) q = std::fabs(q);
+      for (auto& q : Ys) q = std::fabs(q);
+      okk_bsr_spmv_v42_f64(mb, bs, k, G.rp.data(), G.ci.data(), va.data(), Xa.data(), xr, xc, Ys.data(), yr, yc, std::fabs(alpha),
+                           std::fabs(beta));
+      Dev<double> dX(X), dY(Y0);
+      SP(b200sp_bsr_spmm_f64_i32(plan, nullptr, 'N', mb, nb, nnzb, bs, k, alpha, rp.p, ci.p, v.p, dX.p, ldx, rm, beta, dY.p, ldy, rm));
+      CK(cudaDeviceSynchronize());
+      auto gotm = dY.host();
+      double w2 = 0;
+      int64_t touched_pad = 0;
+      for (size_t i = 0; i < gotm.size(); ++i) {
+        const int64_t r = rm ? (int64_t)i / ldy : (int64_t)i % ldy, c = rm ? (int64_t)i % ldy : (int64_t)i / ldy;
+        if (r >= np_r || c >= k) {
+          if (gotm[i] != Y0[i]) ++touched_pad;
+          continue;
+        }
+        w2 = std::max(w2, std::fabs(gotm[i] - Yref[i]) / std::max(Ys[i], 1e-300));
+      }
+      snprintf(nm, sizeof(nm), "%s_bs%d/N_x%d_%s", name, bs, k, rm ? "layoutright" : "layoutleft");
+      record(nm, w2 <= 1e-10 && touched_pad == 0, "kernel=%s max scaled err %.2e, padding entries touched %lld", b200sp_bsr_last_kernel(plan),
+             w2, (long long)touched_pad);
+    }
+    b200sp_bsr_plan_destroy(plan, nullptr);
+  }
+}
+
+static void suite_bsr() {
+  const Csr<double> G = gen_lap27<double>(g_big ? 64 : 24, 1);  // 27 blocks per block row
+  for (int bs : {2, 3, 4, 5, 8, 16}) {
+    if (g_big && bs > 8) continue;  // 7 M blocks x 256 values would not fit next to the oracle copies
+    bsr_case("lap27", G, bs);
+  }
+  {  // skewed block rows: a few beyond the stage, many empty
+    Rng r(5);
+    std::vector<int> lens(20000);
+    for (auto& l : lens) l = r.below(7);
+    lens[3] = 900;
+    lens[9000] = 2500;
+    bsr_case("skewed", gen_rows<double>(lens, 20000, false, false, 6), 3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // suite: spmm_sweep -- the rank-2 kernels over column counts / scalar types / leading dimensions / beta
 // ------------------------------------------------------------------------------------------------
 static void ospmm(int m, int n, int k, const Csr<double>& A, const double* X, int64_t ldx, double* Y, int64_t ldy, double al, double be) {
@@ -1294,7 +1424,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];

@@ -10,12 +10,14 @@ O=gpurun_out/r02_gpu_check_first.jsonl
 # 1. parity + clean timings of all harness suites at full size (config 4 SpGEMM, config 3 SpMM incl. the row-limit sweep)
 $G --big --out $O > gpurun_out/r02_gpu_check_first.log 2>&1
 $G --suite spmm --spmm-scale 23 --out $O >> gpurun_out/r02_gpu_check_first.log 2>&1
-# (the `jacobi` suite of the --big run above is the first GPU run of spgemm_jacobi; then: pytest tests/test_gpu_jacobi.py -m gpu_next)
+# (the `jacobi` and `bsr` suites of the --big run above are the first GPU runs of spgemm_jacobi and of the BsrMatrix kernels)
+python -m pytest tests -x -q -m gpu_next > gpurun_out/r02_pytest_gpu_next.log 2>&1; tail -n 3 gpurun_out/r02_pytest_gpu_next.log
+# -> on success: change `gpu_next` to `gpu` in tests/test_gpu_jacobi.py, tests/test_gpu_bsr.py, tests/test_shim.py
 # 2. ncu: launch lists + one full capture per kernel of interest (never bench numbers)
 ncu --metrics gpu__time_duration.sum --clock-control none --target-processes all -c 400 --csv \
     --log-file gpurun_out/r02_launches_spmm.csv $G --big --suite spmm --out gpurun_out/scratch.jsonl > /dev/null 2>&1
-for k in spmm_seg_kernel spmm_tile_kernel num_hash_kernel sym_hash_kernel; do
-  suite=spmm; [ "${k#num}" != "$k" ] && suite=spgemm_c4; [ "${k#sym}" != "$k" ] && suite=spgemm_c4
+for k in spmm_seg_kernel spmm_tile_kernel num_hash_kernel sym_hash_kernel bsr_tile_kernel; do
+  suite=spmm; [ "${k#num}" != "$k" ] && suite=spgemm_c4; [ "${k#sym}" != "$k" ] && suite=spgemm_c4; [ "${k#bsr}" != "$k" ] && suite=bsr
   timeout 120 ncu --set full --import-source on --clock-control none --target-processes all -k regex:$k -c 1 -f \
       -o gpurun_out/r02_$k $G --suite $suite --out gpurun_out/scratch.jsonl > gpurun_out/r02_ncu_$k.log 2>&1
 done
