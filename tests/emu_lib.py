@@ -155,3 +155,32 @@ def bsr_spmm(plan, mode, mb, nb, bs, rp, ci, v, X, Y, alpha, beta):
     ldy, rmy = lay(Y)
     ok(fn(plan.h, None, mode.encode(), mb, nb, len(ci), bs, X.shape[1], scalar(v.dtype, alpha), ptr(rp), ptr(ci), ptr(v), ptr(X), ldx, rmx,
           scalar(v.dtype, beta), ptr(Y), ldy, rmy))
+
+
+# ---- guarded inputs: numpy views over blocks that end right before an inaccessible page (tools/emu/emu_runtime.cpp) ----
+_GUARDED = []
+
+
+def guarded(a, align=None):
+    """Copy `a` (1-D or contiguous 2-D) into a guarded block and return an ndarray view of it.  align = element size
+    (default): the byte after the array faults, the start is aligned to the element only (the library's unaligned
+    paths); align = 16: the start is 16-byte aligned (TMA paths) and up to 15 bytes of slack precede the guard page."""
+    L = lib()
+    L.b200emu_guarded_alloc.restype = C.c_void_p
+    L.b200emu_guarded_alloc.argtypes = [C.c_size_t, C.c_size_t]
+    a = np.ascontiguousarray(a) if not a.flags.f_contiguous or a.ndim == 1 else a
+    al = a.dtype.itemsize if align is None else align
+    p = L.b200emu_guarded_alloc(a.nbytes, al)
+    assert p, "guarded allocation failed"
+    _GUARDED.append(p)
+    buf = (C.c_char * max(a.nbytes, 1)).from_address(p)
+    v = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape, order="F" if (a.ndim == 2 and a.flags.f_contiguous and not a.flags.c_contiguous) else "C")
+    v[...] = a
+    return v
+
+
+def guarded_release():
+    L = lib()
+    L.b200emu_guarded_free.argtypes = [C.c_void_p]
+    while _GUARDED:
+        L.b200emu_guarded_free(_GUARDED.pop())

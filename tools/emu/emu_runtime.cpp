@@ -196,6 +196,24 @@ static int pass_order(int i, int n) {
   return g_perm[i];
 }
 
+// Guarded block for test inputs (tests/emu_lib.py): `bytes` of payload ending `slack` bytes before an inaccessible page
+// (slack = 0: the first byte past the array faults; the array then starts wherever that puts it, aligned to `align`).
+static void* guarded_block(size_t bytes, size_t align) {
+  const size_t page = 4096;
+  const size_t payload = bytes ? bytes : 1;
+  const size_t body = (payload + align + page - 1) / page * page;
+  const size_t total = body + 2 * page;
+  char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == (char*)MAP_FAILED) return nullptr;
+  mprotect(base, page, PROT_NONE);
+  mprotect(base + page + body, page, PROT_NONE);
+  char* end = base + page + body;
+  char* user = (char*)(((uintptr_t)(end - payload)) & ~(uintptr_t)(align - 1));
+  memset(base + page, 0xA5, body);
+  g_guarded[user] = {base, total};
+  return user;
+}
+
 void* device_alloc(size_t bytes) {
   if (!guard_mode()) {
     void* p = nullptr;
@@ -450,3 +468,17 @@ bool mbar_test_wait(void* bar, unsigned parity) {
 }
 
 }  // namespace b200emu
+
+// C entry points for tests that want their INPUT arrays guarded too (numpy views over these blocks, tests/emu_lib.py)
+extern "C" {
+__attribute__((visibility("default"))) void* b200emu_guarded_alloc(size_t bytes, size_t align) {
+  if (align == 0 || (align & (align - 1)) != 0) return nullptr;
+  return b200emu::guarded_block(bytes, align);
+}
+__attribute__((visibility("default"))) void b200emu_guarded_free(void* p) {
+  auto it = b200emu::g_guarded.find(p);
+  if (it == b200emu::g_guarded.end()) abort();
+  munmap(it->second.first, it->second.second);
+  b200emu::g_guarded.erase(it);
+}
+}
