@@ -15,7 +15,8 @@
 //
 //   * the block rows are cut into tiles of about T blocks; a producer warp streams each tile's values, block columns
 //     and row-map slice into a shared-memory ring with 1-D bulk (TMA) copies, evict-first in L2;
-//   * consumer warps give every point row (block row, local row) LPR lanes; lane `sl` walks the entries
+//   * bs in {2,3,4,5}: element-per-lane consumers (bsr_tile_e_kernel, block size compile-time); other bs <= 16:
+//     consumer warps give every point row (block row, local row) LPR lanes; lane `sl` walks the entries
 //     sl, sl+LPR, ... of its point row -- entry k is element (lr, k % bs) of block k / bs -- with all index arithmetic
 //     carried incrementally (no division in the loop, bs is a run-time value); UNR gathers of x are in flight per lane;
 //   * the epilogue is the reference functor's: y = beta*y (exact 0 for beta == 0), y += alpha*sum.
@@ -102,27 +103,31 @@ __global__ void bsr_find_long_rows_kernel(int mb, const int* __restrict__ row_pt
 template <typename S, int UNR, bool STREAM>
 __device__ __forceinline__ S bsr_row_dot(const S* __restrict__ vrow, const int* __restrict__ crow, const S* __restrict__ x, int nk,
                                          int bs, int vpe, int lpr, int sl, int j0, int i0, int dj, int di) {
+  // (j, i) = (block, column in block) of the lane's current entry; off = j*vpe + i, its value offset from vrow.  One step
+  // adds (dj, di) with a carry into j when i passes bs -- carried as additions, no multiplication or division per entry.
+  // Entries past the end of the row read entry (j0, i0) again (always inside the row here) and contribute exactly 0.
   S sum = S(0);
   int j = j0, i = i0;
+  int off = j0 * vpe + i0;
+  const int doff = dj * vpe + di, carry = vpe - bs;
+  const int off0 = off;
   for (int k = sl; k < nk; k += UNR * lpr) {
-    int c[UNR];
+    unsigned c[UNR];
     S av[UNR], xv[UNR];
     bool ok[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       ok[u] = (k + u * lpr) < nk;
-      if (ok[u]) {
-        c[u] = (STREAM ? ld_stream(crow + j) : crow[j]) * bs + i;
-        av[u] = STREAM ? ld_stream(vrow + (int64_t)j * vpe + i) : vrow[j * vpe + i];
-      } else {
-        c[u] = 0;
-        av[u] = S(0);
-      }
+      const int jj = ok[u] ? j : j0, ii = ok[u] ? i : i0, oo = ok[u] ? off : off0;
+      c[u] = (unsigned)((STREAM ? ld_stream(crow + jj) : crow[jj]) * bs + ii);
+      av[u] = STREAM ? ld_stream(vrow + oo) : vrow[oo];
       i += di;
       j += dj;
+      off += doff;
       if (i >= bs) {
         i -= bs;
         ++j;
+        off += carry;
       }
     }
 #pragma unroll
@@ -190,6 +195,74 @@ struct BsrSmem {
   alignas(8) uint64_t empty[STAGES];
 };
 
+// The producer warp of both tile kernels: streams tile after tile into the ring (values, block columns, row-map slice).
+template <typename S, typename Smem, int STAGES>
+__device__ __forceinline__ void bsr_produce(Smem& sm, int lane, int mb, int64_t nnzb, int vpe, int n_tiles, const int4* __restrict__ tiles,
+                                            const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                            const S* __restrict__ vals) {
+  constexpr int RCAP = Smem::RCAP;
+  const uint64_t pol = l2_policy_evict_first();
+  const int64_t nnzb_al = nnzb & ~(int64_t)3;  // bulk copies stay below this block
+  const int rp_al_end = (mb + 1) & ~3;         // ... and below this row-map entry
+  int4 mine = make_int4(0, 0, 0, 0);
+  for (int it = 0;; ++it) {
+    const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+    if (tile >= n_tiles) break;
+    if ((it & 31) == 0) {
+      const int64_t t = blockIdx.x + (int64_t)(it + lane) * gridDim.x;
+      if (t < n_tiles) mine = tiles[t];
+    }
+    int4 d;
+    d.x = __shfl_sync(0xffffffffu, mine.x, it & 31);
+    d.y = __shfl_sync(0xffffffffu, mine.y, it & 31);
+    d.z = __shfl_sync(0xffffffffu, mine.z, it & 31);
+    d.w = __shfl_sync(0xffffffffu, mine.w, it & 31);
+    const int stage = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&sm.empty[stage], ph ^ 1u);
+
+    const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
+    S* sv = sm.vals[stage];
+    int* sc = sm.cols[stage];
+    int* sr = sm.rows[stage];
+    // blocks [s_al, e) -> stage slot 0..; bulk part [s_al, bulk_end), the last (< 4) blocks of the matrix by plain loads
+    const int s_al = s & ~3;
+    const int e_up = (e + 3) & ~3;
+    const int bulk_end = (int)((int64_t)e_up < nnzb_al ? (int64_t)e_up : nnzb_al);
+    const int nbk = (r1 > r0 && bulk_end > s_al) ? bulk_end - s_al : 0;
+    if (r1 > r0 && (int64_t)e > nnzb_al) {
+      const int t0 = (int)((int64_t)s_al > nnzb_al ? (int64_t)s_al : nnzb_al);
+      for (int b = t0 + lane; b < e; b += 32) sc[b - s_al] = col_idx[b];
+      const int64_t v0 = (int64_t)t0 * vpe, v1 = (int64_t)e * vpe, voff = (int64_t)s_al * vpe;
+      for (int64_t q = v0 + lane; q < v1; q += 32) sv[q - voff] = vals[q];
+    }
+    const int r0_al = r0 & ~3;
+    int nrp = 0;
+    if (r1 > r0) {
+      const int want_end = min(r1 + 1, r0_al + RCAP);  // exclusive
+      const int want_up = (want_end + 3) & ~3;
+      const int rbulk_end = min(min(want_up, r0_al + RCAP), rp_al_end);
+      nrp = rbulk_end > r0_al ? rbulk_end - r0_al : 0;
+      if (want_end > rp_al_end) {
+        const int t0 = max(r0_al, rp_al_end);
+        for (int i = t0 + lane; i < want_end; i += 32) sr[i - r0_al] = row_ptr[i];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      sm.desc[stage] = d;
+      const uint32_t vbytes = (uint32_t)((size_t)nbk * vpe * sizeof(S));
+      mbar_arrive_expect_tx(&sm.full[stage], vbytes + (uint32_t)(nbk * 4) + (uint32_t)(nrp * 4));
+      if (nbk > 0) {
+        bulk_g2s(sv, vals + (int64_t)s_al * vpe, vbytes, &sm.full[stage], pol);
+        bulk_g2s(sc, col_idx + s_al, (uint32_t)(nbk * 4), &sm.full[stage], pol);
+      }
+      if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
+    }
+    __syncwarp();
+  }
+}
+
 template <typename S, int NW, int STAGES, int VCAP, int UNR>
 __global__ void __launch_bounds__((NW + 1) * 32)
     bsr_tile_kernel(int mb, int64_t nnzb, int bs, int lpr, int lmaxb, int n_tiles, const int4* __restrict__ tiles,
@@ -215,67 +288,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
   __syncthreads();
 
   if (warp == NW) {
-    // ------------------------------------------------ producer warp
-    const uint64_t pol = l2_policy_evict_first();
-    const int64_t nnzb_al = nnzb & ~(int64_t)3;  // bulk copies stay below this block
-    const int rp_al_end = (mb + 1) & ~3;         // ... and below this row-map entry
-    int4 mine = make_int4(0, 0, 0, 0);
-    for (int it = 0;; ++it) {
-      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-      if (tile >= n_tiles) break;
-      if ((it & 31) == 0) {
-        const int64_t t = blockIdx.x + (int64_t)(it + lane) * gridDim.x;
-        if (t < n_tiles) mine = tiles[t];
-      }
-      int4 d;
-      d.x = __shfl_sync(0xffffffffu, mine.x, it & 31);
-      d.y = __shfl_sync(0xffffffffu, mine.y, it & 31);
-      d.z = __shfl_sync(0xffffffffu, mine.z, it & 31);
-      d.w = __shfl_sync(0xffffffffu, mine.w, it & 31);
-      const int stage = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(&sm.empty[stage], ph ^ 1u);
-
-      const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
-      S* sv = sm.vals[stage];
-      int* sc = sm.cols[stage];
-      int* sr = sm.rows[stage];
-      // blocks [s_al, e) -> stage slot 0..; bulk part [s_al, bulk_end), the last (< 4) blocks of the matrix by plain loads
-      const int s_al = s & ~3;
-      const int e_up = (e + 3) & ~3;
-      const int bulk_end = (int)((int64_t)e_up < nnzb_al ? (int64_t)e_up : nnzb_al);
-      const int nbk = (r1 > r0 && bulk_end > s_al) ? bulk_end - s_al : 0;
-      if (r1 > r0 && (int64_t)e > nnzb_al) {
-        const int t0 = (int)((int64_t)s_al > nnzb_al ? (int64_t)s_al : nnzb_al);
-        for (int b = t0 + lane; b < e; b += 32) sc[b - s_al] = col_idx[b];
-        const int64_t v0 = (int64_t)t0 * vpe, v1 = (int64_t)e * vpe, voff = (int64_t)s_al * vpe;
-        for (int64_t q = v0 + lane; q < v1; q += 32) sv[q - voff] = vals[q];
-      }
-      const int r0_al = r0 & ~3;
-      int nrp = 0;
-      if (r1 > r0) {
-        const int want_end = min(r1 + 1, r0_al + RCAP);  // exclusive
-        const int want_up = (want_end + 3) & ~3;
-        const int rbulk_end = min(min(want_up, r0_al + RCAP), rp_al_end);
-        nrp = rbulk_end > r0_al ? rbulk_end - r0_al : 0;
-        if (want_end > rp_al_end) {
-          const int t0 = max(r0_al, rp_al_end);
-          for (int i = t0 + lane; i < want_end; i += 32) sr[i - r0_al] = row_ptr[i];
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        sm.desc[stage] = d;
-        const uint32_t vbytes = (uint32_t)((size_t)nbk * vpe * sizeof(S));
-        mbar_arrive_expect_tx(&sm.full[stage], vbytes + (uint32_t)(nbk * 4) + (uint32_t)(nrp * 4));
-        if (nbk > 0) {
-          bulk_g2s(sv, vals + (int64_t)s_al * vpe, vbytes, &sm.full[stage], pol);
-          bulk_g2s(sc, col_idx + s_al, (uint32_t)(nbk * 4), &sm.full[stage], pol);
-        }
-        if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
-      }
-      __syncwarp();
-    }
+    bsr_produce<S, Smem, STAGES>(sm, lane, mb, nnzb, vpe, n_tiles, tiles, row_ptr, col_idx, vals);
   } else {
     // ------------------------------------------------ consumer warps
     const int G = bs * lpr;    // lanes of one block row
@@ -320,6 +333,107 @@ __global__ void __launch_bounds__((NW + 1) * 32)
                                            dj, di);
         sum = bsr_group_sum(sum, lpr);
         if (valid && !is_long && sl == 0) bsr_store(y + (int64_t)brow * bs + lr, sum, alpha, beta);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The tile kernel for the common small block sizes (BS compile-time, BS*BS <= 32): ELEMENT per lane.  A warp takes one
+// block row at a time; lane L owns element e = L % BS^2 = (lr, i) of block slot p = L / BS^2, so a warp pass covers
+// P = 32 / BS^2 whole blocks, read from the stage as ONE contiguous run of values (no bank conflicts, no index
+// arithmetic beyond j*BS^2 + e) while the BS lanes that share a column i gather the same x entry (one request).  Per
+// entry: LDS value, LDS block column, multiply-add for the x index, LDG x, FMA -- a quarter of the instructions of the
+// run-time-bs walk above, which matters because 8 + 4/BS^2 bytes per entry leave fewer issue slots per byte than CSR's 12.
+// After the row: sum over the BS lanes of a local row and over the P slots by shuffles, lanes (p = 0, i = 0) store.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename S, int BS, int NW, int STAGES, int VCAP, int UNR>
+__global__ void __launch_bounds__((NW + 1) * 32)
+    bsr_tile_e_kernel(int mb, int64_t nnzb, int lmaxb, int n_tiles, const int4* __restrict__ tiles, const int* __restrict__ row_ptr,
+                      const int* __restrict__ col_idx, const S* __restrict__ vals, const S* __restrict__ x, S* __restrict__ y, S alpha,
+                      S beta) {
+  using Smem = BsrSmem<S, VCAP, STAGES>;
+  constexpr int RCAP = Smem::RCAP;
+  constexpr int VPE = BS * BS;
+  constexpr int P = 32 / VPE;
+  static_assert(P >= 1, "element-per-lane kernel needs BS*BS <= 32");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    bsr_produce<S, Smem, STAGES>(sm, lane, mb, nnzb, VPE, n_tiles, tiles, row_ptr, col_idx, vals);
+  } else {
+    const int p = lane / VPE, e = lane % VPE;
+    const int lr = e / BS, i = e % BS;
+    const bool lane_used = p < P;
+    for (int it = 0;; ++it) {
+      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+      if (tile >= n_tiles) break;
+      const int stage = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&sm.full[stage], ph);
+      const int4 d = sm.desc[stage];
+      const int r0 = d.x, r1 = d.y;
+      const int s_al = d.z & ~3;
+      const int r0_al = r0 & ~3;
+      const S* sv = sm.vals[stage];
+      const int* sc = sm.cols[stage];
+      const int* sr = sm.rows[stage];
+      // block rows dealt round-robin to the warps by absolute index
+      for (int brow = r0 + ((warp - r0 % NW) + NW) % NW; brow < r1; brow += NW) {
+        int rs, re;
+        const int o = brow - r0_al;
+        if (o + 1 < RCAP) {
+          rs = sr[o];
+          re = sr[o + 1];
+        } else {
+          rs = row_ptr[brow];
+          re = row_ptr[brow + 1];
+        }
+        if (re - rs > lmaxb) continue;  // left to bsr_vector_kernel (uniform across the warp)
+        const int nblk = re - rs;
+        const S* vb = sv + (rs - s_al) * VPE + e;
+        const int* cb = sc + (rs - s_al);
+        S sum = S(0);
+        const int nb_eff = lane_used ? nblk : 0;  // lanes beyond the last whole slot (32 % BS^2 of them) idle
+        int j = p;
+        for (; j + (UNR - 1) * P < nb_eff; j += UNR * P) {  // UNR blocks per lane in flight, no predicates
+          unsigned c[UNR];
+          S av[UNR], xv[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            c[u] = (unsigned)(cb[j + u * P] * BS + i);
+            av[u] = vb[(j + u * P) * VPE];
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) xv[u] = ldg(x + c[u]);
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
+        }
+        for (; j < nb_eff; j += P) sum += vb[j * VPE] * ldg(x + (unsigned)(cb[j] * BS + i));
+        // local row total: the BS lanes (lr, 0..BS-1) of a slot, then the P slots
+        S t = sum;
+#pragma unroll
+        for (int q = 1; q < BS; ++q) t += __shfl_down_sync(0xffffffffu, sum, q);
+        S r = t;
+#pragma unroll
+        for (int q = 1; q < P; ++q) r += __shfl_down_sync(0xffffffffu, t, q * VPE);
+        if (p == 0 && i == 0) bsr_store(y + (int64_t)brow * BS + lr, r, alpha, beta);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -536,6 +650,37 @@ int launch_tile(b200sp_bsr_plan* p, cudaStream_t st, int mb, int64_t nnzb, int b
   return B200SP_OK;
 }
 
+template <typename S, int BS, int NW, int STAGES, int VCAP>
+int launch_tile_e(b200sp_bsr_plan* p, cudaStream_t st, int mb, int64_t nnzb, const int* rp, const int* ci, const S* v, const S* x, S* y,
+                  S alpha, S beta) {
+  using Smem = BsrSmem<S, VCAP, STAGES>;
+  constexpr int UNR = 4;
+  auto kern = bsr_tile_e_kernel<S, BS, NW, STAGES, VCAP, UNR>;
+  const size_t smem = sizeof(Smem) + 128;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.store(true, std::memory_order_release);
+  }
+  static std::atomic<int> occ{0};
+  if (occ.load() == 0) {
+    int o = 0;
+    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, (NW + 1) * 32, smem));
+    occ.store(o > 0 ? o : 1);
+  }
+  const int capb = std::min(Smem::CCAP, VCAP / (BS * BS)) & ~3;
+  int rc = bsr_analyse(p, st, mb, nnzb, BS, capb, rp);
+  if (rc != B200SP_OK) return rc;
+  const int grid = std::max(1, std::min(p->n_tiles, sm_count() * occ.load()));
+  kern<<<grid, (NW + 1) * 32, smem, st>>>(mb, nnzb, p->lmaxb, p->n_tiles, p->tiles, rp, ci, v, x, y, alpha, beta);
+  B200SP_LAUNCH_CHECK();
+  bsr_vector_kernel<S><<<sm_count() * 2, 256, 0, st>>>(mb, BS, 32, rp, ci, v, x, y, alpha, beta, p->long_rows, p->n_long);
+  B200SP_LAUNCH_CHECK();
+  snprintf(p->last_kernel, sizeof(p->last_kernel), "bsr_tile_e<%s,BS=%d,NW=%d,STAGES=%d,VCAP=%d>grid=%d", sizeof(S) == 8 ? "f64" : "f32", BS,
+           NW, STAGES, VCAP, grid);
+  return B200SP_OK;
+}
+
 bool aligned16(const void* a, const void* b, const void* c) { return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15u) == 0; }
 
 template <typename S>
@@ -601,6 +746,15 @@ int bsr_spmv_impl(b200sp_bsr_plan* p, cudaStream_t st, char mode, int mb, int nb
   bool tile = aligned16(rp, ci, v) && bs <= 16 && nnzb >= 64;
   if (force && !strcmp(force, "vector")) tile = false;
   if (!tile) return launch_vector<S>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
+  if (!(force && !strcmp(force, "walk"))) {  // element-per-lane kernel for the block sizes it is instantiated for
+    switch (bs) {
+      case 2: return launch_tile_e<S, 2, 16, 4, 2048>(p, st, mb, nnzb, rp, ci, v, x, y, alpha, beta);
+      case 3: return launch_tile_e<S, 3, 16, 4, 2048>(p, st, mb, nnzb, rp, ci, v, x, y, alpha, beta);
+      case 4: return launch_tile_e<S, 4, 16, 4, 2048>(p, st, mb, nnzb, rp, ci, v, x, y, alpha, beta);
+      case 5: return launch_tile_e<S, 5, 16, 3, 4096>(p, st, mb, nnzb, rp, ci, v, x, y, alpha, beta);
+      default: break;
+    }
+  }
   if (bs <= 4) return launch_tile<S, 16, 4, 2048>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
   return launch_tile<S, 16, 3, 4096>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
 }

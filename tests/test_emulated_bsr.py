@@ -91,9 +91,19 @@ def test_tile_kernel_every_block_size(emu, oracle, bs):
     rp, ci, v = bsr_random(bs, mb, nb, seed=bs, min_blocks=0, max_blocks=12, sort=False)
     plan = E.BsrPlan()
     rng = np.random.default_rng(bs)
-    for alpha, beta in ((1.0, 0.0), (3.7, -1.5)):
-        run_rank1(oracle, plan, "N", bs, mb, nb, rp, ci, v, rng, alpha, beta, np.float64)
-        assert plan.kernel().startswith("bsr_tile" if bs <= 16 else "bsr_vector"), plan.kernel()
+    import os
+    for knob in (None, "walk"):  # default: element-per-lane kernel for bs 2..5; "walk": the run-time-bs kernel for every bs
+        if knob:
+            os.environ["B200SP_BSR_KERNEL"] = knob
+        try:
+            for alpha, beta in ((1.0, 0.0), (3.7, -1.5)):
+                for dtype in (np.float64, np.float32):
+                    vv = v.astype(dtype)
+                    run_rank1(oracle, plan, "N", bs, mb, nb, rp, ci, vv, rng, alpha, beta, dtype)
+                    want = "bsr_vector" if bs > 16 else ("bsr_tile_e<" if (bs <= 5 and not knob) else "bsr_tile<")
+                    assert plan.kernel().startswith(want), plan.kernel()
+        finally:
+            os.environ.pop("B200SP_BSR_KERNEL", None)
     run_rank1(oracle, plan, "T", bs, mb, nb, rp, ci, v, rng, -1.0, 1.0, np.float64)
     plan.close()
 

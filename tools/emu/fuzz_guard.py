@@ -238,6 +238,9 @@ def op_bsr(rng, orc, verbose):
     alpha, beta = [(1.0, 0.0), (3.7, -1.5), (-1.0, 1.0), (3.7, 0.0), (1.0, 1.0), (-1.0, -1.5), (1.0, 0.0), (0.0, -1.0)][rng.integers(0, 8)]
     grp, gci, gv = g(rp, rng), g(ci, rng), g(v, rng)
     plan = E.BsrPlan()
+    knob = [None, None, "walk", "vector"][rng.integers(0, 4)]
+    if knob:
+        os.environ["B200SP_BSR_KERNEL"] = knob
     k = 1 if rng.random() < 0.6 else int(rng.integers(1, 9))
     if k == 1 and rng.random() < 0.8:
         x, y0 = rng.uniform(0, 10, nx).astype(dtype), rng.uniform(0, 10, ny).astype(dtype)
@@ -253,6 +256,7 @@ def op_bsr(rng, orc, verbose):
         got = gY
     kern = plan.kernel()
     plan.close()
+    os.environ.pop("B200SP_BSR_KERNEL", None)
     Yc = Y0.copy(order="K")
     exp = orc.bsr_spmv_v41(mode, bs, nb, rp, ci, v, X, Yc, alpha, beta) if trans else orc.bsr_spmv_v42(bs, rp, ci, v, X, Yc, alpha, beta)
     tol = tolerance(dtype, alpha, beta, op_max_nnz_per_row(bs, rp, ci, nb, trans))

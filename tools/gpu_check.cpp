@@ -1047,8 +1047,9 @@ static void bsr_case(const char* name, const Csr<double>& G, int bs) {
     for (auto& t : scale) t = std::fabs(t);
     okk_bsr_spmv_v42_f64(mb, bs, 1, G.rp.data(), G.ci.data(), va.data(), xa.data(), 1, 0, scale.data(), 1, 0, std::fabs(alpha),
                          std::fabs(beta));
-    for (int variant = 0; variant < 2; ++variant) {
-      if (variant) setenv("B200SP_BSR_KERNEL", "vector", 1);
+    for (int variant = 0; variant < 3; ++variant) {
+      if (variant == 2 && bs > 5) continue;  // "walk" is already the default tile kernel beyond bs = 5
+      if (variant) setenv("B200SP_BSR_KERNEL", variant == 1 ? "vector" : "walk", 1);
       else unsetenv("B200SP_BSR_KERNEL");
       b200sp_bsr_plan* plan = nullptr;
       SP(b200sp_bsr_plan_create(&plan));
@@ -1066,7 +1067,7 @@ static void bsr_case(const char* name, const Csr<double>& G, int bs) {
       double worst = 0;
       for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, std::fabs(got[i] - yref[i]) / std::max(scale[i], 1e-300));
       char nm[160];
-      snprintf(nm, sizeof(nm), "%s_bs%d/N_%s", name, bs, variant ? "vector" : "default");
+      snprintf(nm, sizeof(nm), "%s_bs%d/N_%s", name, bs, variant == 0 ? "default" : variant == 1 ? "vector" : "walk");
       record(nm, worst <= 1e-10, "mb=%d nnzb=%lld kernel=%s %.3f ms (%.0f GB/s algorithmic), max scaled err %.2e", mb, (long long)nnzb,
              b200sp_bsr_last_kernel(plan), best, bytes / (best * 1e-3) / 1e9, worst);
       b200sp_bsr_plan_destroy(plan, nullptr);
