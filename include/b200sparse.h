@@ -317,6 +317,19 @@ int b200sp_bsr_spmm_f32_i32(b200sp_bsr_plan* plan, void* stream, char mode, int 
 /* Name of the kernel the plan's last call used; static storage (tests / bench). */
 const char* b200sp_bsr_last_kernel(const b200sp_bsr_plan* plan);
 
+/* ---- CG driver (callers of spmv in a loop) ---------------------------------------------------
+ * KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false (perf_test/sparse/KokkosSparse_pcg.hpp:248-466;
+ * the driver perf_test/sparse/KokkosSparse_pcg.cpp:69-122 calls it with tolerance 1e-7): solves A x = b for a symmetric
+ * positive definite CrsMatrix, x = initial guess on entry, solution on return.  The recurrence is the reference's,
+ * operation for operation; alpha, beta and the residual stay on the device and the host only polls a `done` word every
+ * check_every iterations (<= 0: 8), where the reference synchronises three times per iteration.  `plan` is the SpMV
+ * plan of A (its analysis is reused by every iteration).  Returns the iteration count and sqrt(r.r) of the recurrence
+ * (CGSolveResult::iteration / norm_res).  Synchronous: returns after the solve. */
+int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t nnz, const int* row_ptr,
+                            const int* col_idx, const double* vals, const double* b, double* x,
+                            int maximum_iteration, double tolerance, int check_every, int* iterations,
+                            double* norm_res);
+
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */
 int64_t b200sp_launch_count(void);

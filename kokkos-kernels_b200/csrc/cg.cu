@@ -1,0 +1,209 @@
+// cg.cu -- unpreconditioned conjugate gradients on the device: the reference's CG driver (a caller of spmv in a loop,
+// SURVEY.md section 8f rank 4) with no host round trip per iteration.
+//
+// Follows KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false
+// (perf_test/sparse/KokkosSparse_pcg.hpp:248-466; driver perf_test/sparse/KokkosSparse_pcg.cpp:69-122):
+//   p = x; Ap = A p; r = b - Ap; p = r; old_rdot = r.r
+//   while (tolerance < sqrt(old_rdot) && iteration < maximum_iteration)
+//     Ap = A p; alpha = old_rdot / p.Ap; x += alpha p; r -= alpha Ap; beta = r.r / old_rdot; p = r + beta p
+// The reference reads three scalars back per iteration (KokkosBlas::dot returns to the host, :385,398).  Here alpha, beta,
+// the residual and the iteration counter live in device memory; one iteration is the library's SpMV plus three small
+// kernels on the same stream, every kernel first looks at a `done` word, and the host polls that word (pinned, async copy)
+// every `check_every` iterations -- so the loop is launch-bound on the host side only for tiny matrices.
+// Dots are two-stage with a fixed reduction order (per-thread strided partials, shuffle tree, per-block slots summed by the
+// last block in slot order): bit-reproducible run to run for a given grid.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+struct b200sp_spmv_plan;
+
+namespace b200sp {
+namespace {
+
+struct CgState {       // device-resident scalars of the recurrence
+  double old_rdot;     // r.r of the previous iteration
+  double pAp;          // p.Ap
+  double beta;         // r.r / old_rdot
+  double norm_res;     // sqrt(r.r)
+  int iteration;       // completed iterations
+  int done;            // 1 once norm_res <= tolerance or the limit is reached
+  unsigned ticket;     // last-block election of the two-stage reductions
+  unsigned pad;
+};
+
+constexpr int kCgThreads = 256;
+
+// sum of v over the block in a fixed order; result valid in thread 0
+__device__ __forceinline__ double cg_block_sum(double v) {
+  __shared__ double warp_part[kCgThreads / 32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_part[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kCgThreads / 32; ++w) t += warp_part[w];
+  __syncthreads();
+  return t;
+}
+
+// Publishes this block's partial and elects the last block; returns true (in thread 0 of that block) with the total in
+// *total, summed over the slots in slot order.
+__device__ __forceinline__ bool cg_grid_sum(double block_total, double* __restrict__ slots, CgState* __restrict__ st, double* total) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    slots[blockIdx.x] = block_total;
+    __threadfence();
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return false;
+  __threadfence();
+  double s = 0.0;
+  for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile double*)slots)[b];
+  st->ticket = 0;
+  *total = s;
+  return true;
+}
+
+// r = b - Ap; p = r; old_rdot = r.r   (setup, after Ap = A x)
+__global__ void __launch_bounds__(kCgThreads) cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ Ap,
+                                                             double* __restrict__ r, double* __restrict__ p, double* __restrict__ slots,
+                                                             CgState* __restrict__ st, double tolerance, int maximum_iteration) {
+  double part = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = 1.0 * b[i] + -1.0 * Ap[i];
+    r[i] = ri;
+    p[i] = ri;
+    part += ri * ri;
+  }
+  double total;
+  if (cg_grid_sum(cg_block_sum(part), slots, st, &total)) {
+    st->old_rdot = total;
+    st->norm_res = sqrt(total);
+    st->iteration = 0;
+    st->beta = 0.0;
+    st->done = !(tolerance < st->norm_res && 0 < maximum_iteration);
+  }
+}
+
+// pAp = p.Ap
+__global__ void __launch_bounds__(kCgThreads) cg_dot_kernel(int n, const double* __restrict__ p, const double* __restrict__ Ap,
+                                                            double* __restrict__ slots, CgState* __restrict__ st) {
+  if (((volatile CgState*)st)->done) return;
+  double part = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) part += p[i] * Ap[i];
+  double total;
+  if (cg_grid_sum(cg_block_sum(part), slots, st, &total)) st->pAp = total;
+}
+
+// x += alpha p; r -= alpha Ap; r_dot = r.r; then the scalar part of the iteration
+__global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ Ap,
+                                                               double* __restrict__ x, double* __restrict__ r, double* __restrict__ slots,
+                                                               CgState* __restrict__ st, double tolerance, int maximum_iteration) {
+  if (((volatile CgState*)st)->done) return;
+  const double alpha = st->old_rdot / st->pAp;
+  double part = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = alpha * p[i] + 1.0 * x[i];
+    const double ri = -alpha * Ap[i] + 1.0 * r[i];
+    r[i] = ri;
+    part += ri * ri;
+  }
+  double total;
+  if (cg_grid_sum(cg_block_sum(part), slots, st, &total)) {
+    st->beta = total / st->old_rdot;
+    st->old_rdot = total;
+    st->norm_res = sqrt(total);
+    st->iteration += 1;
+    // `done` is raised by cg_p_kernel (the last kernel of the iteration) so that p still gets its update, as in the reference
+  }
+}
+
+// p = r + beta p; raises `done` when the loop condition of the reference fails
+__global__ void __launch_bounds__(kCgThreads) cg_p_kernel(int n, const double* __restrict__ r, double* __restrict__ p, CgState* __restrict__ st,
+                                                          double tolerance, int maximum_iteration) {
+  if (((volatile CgState*)st)->done) return;
+  const double beta = st->beta;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = 1.0 * r[i] + beta * p[i];
+  // every block has read `done` == 0 before any block can get here AND finish the grid?  No: blocks run independently, so the
+  // flag is raised by a separate one-thread kernel after this one (cg_flag_kernel) -- see the launch sequence.
+}
+
+__global__ void cg_flag_kernel(CgState* __restrict__ st, double tolerance, int maximum_iteration) {
+  if (st->done) return;
+  if (!(tolerance < st->norm_res && st->iteration < maximum_iteration)) st->done = 1;
+}
+
+}  // namespace
+}  // namespace b200sp
+
+using namespace b200sp;
+
+extern "C" int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, double alpha,
+                                   const int* row_ptr, const int* col_idx, const double* vals, const double* x, double beta, double* y);
+
+extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                                       const double* vals, const double* b, double* x, int maximum_iteration, double tolerance,
+                                       int check_every, int* iterations, double* norm_res) {
+  B200SP_REQUIRE(plan != nullptr, "cg_solve: null plan (create one with b200sp_spmv_plan_create)");
+  B200SP_REQUIRE(n >= 0 && nnz >= 0 && maximum_iteration >= 0, "cg_solve: negative size");
+  B200SP_REQUIRE(iterations != nullptr && norm_res != nullptr, "cg_solve: null result pointer");
+  B200SP_REQUIRE(n == 0 || (row_ptr && b && x), "cg_solve: null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (check_every <= 0) check_every = 8;
+  *iterations = 0;
+  *norm_res = 0.0;
+  if (n == 0) return B200SP_OK;
+  DevTmp tmp(st);
+  double *p = nullptr, *r = nullptr, *Ap = nullptr, *slots = nullptr;
+  CgState* state = nullptr;
+  const int grid = std::max(1, std::min((n + kCgThreads - 1) / kCgThreads, sm_count() * 4));
+  B200SP_CUDA_TRY(tmp.alloc(&p, (size_t)n));
+  B200SP_CUDA_TRY(tmp.alloc(&r, (size_t)n));
+  B200SP_CUDA_TRY(tmp.alloc(&Ap, (size_t)n));
+  B200SP_CUDA_TRY(tmp.alloc(&slots, (size_t)grid));
+  B200SP_CUDA_TRY(tmp.alloc(&state, 1));
+  B200SP_CUDA_TRY(cudaMemsetAsync(state, 0, sizeof(CgState), st));
+  CgState* host_state = nullptr;
+  B200SP_CUDA_TRY(cudaMallocHost((void**)&host_state, sizeof(CgState)));
+  struct HostFree {
+    CgState* q;
+    ~HostFree() { cudaFreeHost(q); }
+  } host_free{host_state};
+
+  // Ap = A x (p = x in the reference; x itself is read here), r = b - Ap, p = r
+  int rc = b200sp_spmv_f64_i32(plan, stream, 'N', n, n, nnz, 1.0, row_ptr, col_idx, vals, x, 0.0, Ap);
+  if (rc != B200SP_OK) return rc;
+  cg_init_kernel<<<grid, kCgThreads, 0, st>>>(n, b, Ap, r, p, slots, state, tolerance, maximum_iteration);
+  B200SP_LAUNCH_CHECK();
+
+  int issued = 0;
+  for (;;) {
+    B200SP_CUDA_TRY(cudaMemcpyAsync(host_state, state, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+    if (host_state->done || issued >= maximum_iteration) break;
+    const int batch = std::min(check_every, maximum_iteration - issued);
+    for (int k = 0; k < batch; ++k) {
+      // iterations issued past convergence are no-ops except for their SpMV (it cannot see the flag): at most check_every - 1
+      rc = b200sp_spmv_f64_i32(plan, stream, 'N', n, n, nnz, 1.0, row_ptr, col_idx, vals, p, 0.0, Ap);
+      if (rc != B200SP_OK) return rc;
+      cg_dot_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, slots, state);
+      B200SP_LAUNCH_CHECK();
+      cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state, tolerance, maximum_iteration);
+      B200SP_LAUNCH_CHECK();
+      cg_p_kernel<<<grid, kCgThreads, 0, st>>>(n, r, p, state, tolerance, maximum_iteration);
+      B200SP_LAUNCH_CHECK();
+      cg_flag_kernel<<<1, 1, 0, st>>>(state, tolerance, maximum_iteration);
+      B200SP_LAUNCH_CHECK();
+    }
+    issued += batch;
+  }
+  *iterations = host_state->iteration;
+  *norm_res = host_state->norm_res;
+  return B200SP_OK;
+}

@@ -235,6 +235,31 @@ def _spmv_bsr(lib, plan, mc, alpha, A, x, beta, y, f64, xcols):
     return y
 
 
+class CGSolveResult:
+    """perf_test/sparse/KokkosSparse_pcg.hpp:38-45 (the fields this driver fills)."""
+
+    def __init__(self, iteration, norm_res):
+        self.iteration, self.norm_res = iteration, norm_res
+
+
+def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.220446049250313e-16, check_every=0):
+    """KokkosKernels::Experimental::Example::pcgsolve(kh, crsMat, y_vector, x_vector, maximum_iteration, tolerance, &result,
+    use_sgs = false) (perf_test/sparse/KokkosSparse_pcg.hpp:248-466): unpreconditioned CG for a symmetric positive definite
+    CrsMatrix; x_vector is the initial guess and receives the solution.  `handle` is the SPMVHandle of A (None: a
+    throw-away one).  The loop runs on the device (b200sp_cg_solve_f64_i32); double only, like the reference driver."""
+    n = A.numRows()
+    if A.numCols() != n or y_vector.shape[0] != n or x_vector.shape[0] != n or y_vector.dim() != 1 or x_vector.dim() != 1:
+        raise B200SparseError("pcgsolve: A must be square and x, b rank-1 vectors of its size")
+    if A.values.dtype != torch.float64 or x_vector.dtype != torch.float64 or y_vector.dtype != torch.float64:
+        raise B200SparseError("pcgsolve: The PCG performance test only works with scalar = double.")  # pcg.hpp:258-259
+    h = handle if handle is not None else SPMVHandle(SPMV_DEFAULT)
+    it, nr = C.c_int(0), C.c_double(0.0)
+    check(_lib.sparse().b200sp_cg_solve_f64_i32(h._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+                                                _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
+                                                int(check_every), C.byref(it), C.byref(nr)))
+    return CGSolveResult(it.value, nr.value)
+
+
 def spmv_scatter(handle, alpha, A, x, y, extra_ptrs):
     """Fused SpMV + all-gather: y (this rank's row block) is also stored to the raw device pointers in
     `extra_ptrs` (peer GPUs' next-x slots mapped into this process)."""

@@ -1,0 +1,68 @@
+/*
+ * kk_oracle_cg.c -- CPU restatement of the reference's unpreconditioned CG driver (SURVEY.md section 8f rank 4:
+ * "drivers that call spmv in a loop").
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (same rules as kk_oracle.c).
+ *
+ * Follows KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false
+ * (perf_test/sparse/KokkosSparse_pcg.hpp:248-466; driver perf_test/sparse/KokkosSparse_pcg.cpp:69-122, tolerance 1e-7):
+ *   p = x; Ap = A p; r = b - Ap; p = r; old_rdot = r.r; norm_res = sqrt(old_rdot)          (:279-292)
+ *   while (tolerance < norm_res && iteration < maximum_iteration)                           (:372)
+ *     Ap = A p; pAp = p.Ap; alpha = old_rdot / pAp                                          (:376-391)
+ *     x = alpha p + x; r = -alpha Ap + r; r_dot = r.r                                       (:394-398)
+ *     beta = r_dot / old_rdot; p = r + beta p; norm_res = sqrt(old_rdot = r_dot); ++iter    (:400,434,448-452)
+ * spmv("N", 1, A, p, 0, Ap) in the functor order (sparse/impl/KokkosSparse_spmv_impl.hpp:110-132), KokkosBlas::dot and
+ * axpby as their Serial loops (one accumulator; a*x + b*y per element).  Not pinned bit for bit on reference code (the
+ * driver needs real Kokkos); pinned by definition: on return b - A x has the norm it reports (tests/test_oracle_cg.py).
+ * Compiled with -ffp-contract=off.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#define OKK_API __attribute__((visibility("default")))
+
+static void cg_spmv(int n, const int* rm, const int* ci, const double* v, const double* x, double* y) {
+  for (int i = 0; i < n; ++i) {
+    double sum = 0.0;
+    for (int j = rm[i]; j < rm[i + 1]; ++j) sum += v[j] * x[ci[j]];
+    y[i] = sum; /* alpha = 1, beta = 0 */
+  }
+}
+static double cg_dot(int n, const double* a, const double* b) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+/* returns the iteration count; *norm_res_out = sqrt(r.r) of the recurrence residual */
+OKK_API int okk_cg_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x,
+                       int maximum_iteration, double tolerance, double* norm_res_out) {
+  double* p = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+  double* r = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  double* Ap = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) p[i] = x[i];
+  cg_spmv(n, row_map, col_idx, values, p, Ap);
+  for (int i = 0; i < n; ++i) r[i] = 1.0 * b[i] + -1.0 * Ap[i];
+  for (int i = 0; i < n; ++i) p[i] = r[i];
+  double old_rdot = cg_dot(n, r, r);
+  double norm_res = sqrt(old_rdot);
+  int iteration = 0;
+  while (tolerance < norm_res && iteration < maximum_iteration) {
+    cg_spmv(n, row_map, col_idx, values, p, Ap);
+    const double pAp_dot = cg_dot(n, p, Ap);
+    const double alpha = old_rdot / pAp_dot;
+    for (int i = 0; i < n; ++i) x[i] = alpha * p[i] + 1.0 * x[i];
+    for (int i = 0; i < n; ++i) r[i] = -alpha * Ap[i] + 1.0 * r[i];
+    const double r_dot = cg_dot(n, r, r);
+    const double beta = r_dot / old_rdot;
+    for (int i = 0; i < n; ++i) p[i] = 1.0 * r[i] + beta * p[i];
+    norm_res = sqrt(old_rdot = r_dot);
+    ++iteration;
+  }
+  free(p);
+  free(r);
+  free(Ap);
+  *norm_res_out = norm_res;
+  return iteration;
+}

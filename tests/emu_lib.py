@@ -184,3 +184,10 @@ def guarded_release():
     L.b200emu_guarded_free.argtypes = [C.c_void_p]
     while _GUARDED:
         L.b200emu_guarded_free(_GUARDED.pop())
+
+
+def cg_solve(plan, rp, ci, v, b, x, maximum_iteration, tolerance, check_every=0):
+    it, nr = C.c_int(), C.c_double()
+    ok(lib().b200sp_cg_solve_f64_i32(plan.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), ptr(b), ptr(x), maximum_iteration,
+                                     C.c_double(tolerance), check_every, C.byref(it), C.byref(nr)))
+    return it.value, nr.value

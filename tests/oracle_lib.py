@@ -63,6 +63,8 @@ class Oracle:
             getattr(L, f"okk_bsr_spmv_v42_{sfx}").argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
             getattr(L, f"okk_bsr_spmv_v41_{sfx}").argtypes = [C.c_char, i32, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
             getattr(L, f"okk_bsr_to_crs_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.okk_cg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64)]
+        L.okk_cg_f64.restype = i32
         self.ref = None
         rpath = os.path.join(ODIR, "_ref", "libkkref.so")
         if os.path.exists(rpath):
@@ -257,6 +259,12 @@ class Oracle:
         cv = np.empty(len(ci) * bs * bs, dtype=v.dtype)
         getattr(self.lib, "okk_bsr_to_crs_" + self._sfx(v))(mb, bs, _p(rp), _p(ci), _p(v), _p(crp), _p(cci), _p(cv))
         return crp, cci, cv
+
+    def cg(self, rp, ci, v, b, x, maximum_iteration, tolerance):
+        """pcgsolve(use_sgs=false); x updated in place; returns (iterations, norm_res)."""
+        nr = f64()
+        it = self.lib.okk_cg_f64(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), maximum_iteration, tolerance, C.byref(nr))
+        return it, nr.value
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)

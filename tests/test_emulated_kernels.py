@@ -327,3 +327,34 @@ def test_kernels_under_other_schedules(order):
                           "(spmv or spmm or spgemm or sort or spadd) and not harness"], capture_output=True, text=True, timeout=1500, env=envv,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+
+
+def test_cg_driver(emu, oracle):
+    """b200sp_cg_solve (device-resident CG, the reference's pcgsolve without preconditioner) against the oracle's
+    restatement: same iteration count up to the rounding of the dots (+-2), same residual bound, same solution."""
+    from test_oracle_cg import spd_lap27
+
+    rp, ci, v = spd_lap27(14, shift=0.5)
+    n = len(rp) - 1
+    rng = np.random.default_rng(0)
+    xs = rng.uniform(-1, 1, n)
+    b = np.zeros(n)
+    oracle.spmv_serial(rp, ci, v, xs, b, 1.0, 0.0)
+    xo = np.zeros(n)
+    it_o, nr_o = oracle.cg(rp, ci, v, b, xo, 100000, 1e-7)
+    for check_every in (1, 8):
+        plan = E.SpmvPlan()
+        x = np.zeros(n)
+        it, nr = E.cg_solve(plan, rp, ci, v, b, x, 100000, 1e-7, check_every)
+        plan.close()
+        assert abs(it - it_o) <= 2 and nr <= 1e-7, (it, it_o, nr)
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-8
+    plan = E.SpmvPlan()
+    x = np.zeros(n)
+    it, nr = E.cg_solve(plan, rp, ci, v, b, x, 7, 1e-7, 3)  # the limit stops it (7 is not a multiple of the polling interval)
+    xo7 = np.zeros(n)
+    it7, nr7 = oracle.cg(rp, ci, v, b, xo7, 7, 1e-7)
+    assert it == 7 == it7 and abs(nr - nr7) <= 1e-9 * nr7 and np.allclose(x, xo7, rtol=1e-10, atol=1e-12)
+    it0, _ = E.cg_solve(plan, rp, ci, v, b, xo.copy(), 100, 1e-5, 4)  # converged start: no iteration
+    assert it0 == 0
+    plan.close()

@@ -137,6 +137,8 @@ void bulk_copy_async(void* smem_dst, const void* gsrc, unsigned bytes, void* bar
 // ---------------------------------------------------------------------------------------------- device intrinsics
 static inline void __syncthreads() { b200emu::block_barrier(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { b200emu::warp_barrier(mask); }
+static inline void __threadfence() {}  // one fiber runs at a time: memory is always coherent here
+static inline void __threadfence_block() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

@@ -75,6 +75,8 @@ void okk_bsr_spmv_v42_f64(int mb, int bs, int nvec, const int* rm, const int* en
                           int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta);
 void okk_bsr_spmv_v41_f64(char mode, int mb, int ylen_b, int bs, int nvec, const int* rm, const int* ent, const double* val,
                           const double* X, int64_t xr, int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta);
+int okk_cg_f64(int n, const int* rm, const int* ci, const double* v, const double* b, double* x, int maximum_iteration, double tolerance,
+               double* norm_res_out);
 int okk_num_threads(void);
 // host generators (kokkos-kernels_b200/csrc/matgen.c)
 void b200gen_fill_f64(int64_t n, double* v, double lo, double hi, uint64_t seed);
@@ -1146,6 +1148,55 @@ static void suite_bsr() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: cg -- the device-resident CG driver against the oracle's restatement of the reference's pcgsolve, with the time per
+// iteration next to the time of the SpMV alone (what the three extra kernels and the polling cost)
+// ------------------------------------------------------------------------------------------------
+static void suite_cg() {
+  Csr<double> A = gen_lap27<double>(g_big ? 128 : 20, 1);
+  for (int r = 0; r < A.m; ++r)  // shift the diagonal: the 27-point operator alone has the constants in its null space
+    for (int q = A.rp[r]; q < A.rp[r + 1]; ++q)
+      if (A.ci[q] == r) A.v[q] += 0.5;
+  const int n = A.m;
+  std::vector<double> xs((size_t)n), b((size_t)n, 0.0), xo((size_t)n, 0.0);
+  b200gen_fill_f64(n, xs.data(), -1.0, 1.0, 9);
+  okk_spmv_serial_f64(n, A.rp.data(), A.ci.data(), A.v.data(), xs.data(), b.data(), 1.0, 0.0);
+  double nr_o = 0;
+  const int it_o = okk_cg_f64(n, A.rp.data(), A.ci.data(), A.v.data(), b.data(), xo.data(), 100000, 1e-7, &nr_o);
+  Dev<int> rp(A.rp), ci(A.ci);
+  Dev<double> v(A.v), db(b), dx((size_t)n), dy((size_t)n);
+  b200sp_spmv_plan* plan = nullptr;
+  SP(b200sp_spmv_plan_create(&plan, 0));
+  float spmv_ms = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {  // also lets the plan finish its self-tuning before the solve
+    Timer t;
+    t.start();
+    SP(b200sp_spmv_f64_i32(plan, nullptr, 'N', n, n, A.nnz(), 1.0, rp.p, ci.p, v.p, db.p, 0.0, dy.p));
+    spmv_ms = std::min(spmv_ms, t.stop_ms());
+  }
+  for (int check_every : {1, 8, 32}) {
+    dx.fill_bytes(0);
+    int it = 0;
+    double nr = 0;
+    const double t0 = now_s();
+    SP(b200sp_cg_solve_f64_i32(plan, nullptr, n, A.nnz(), rp.p, ci.p, v.p, db.p, dx.p, 100000, 1e-7, check_every, &it, &nr));
+    const double ms = (now_s() - t0) * 1e3;
+    auto x = dx.host();
+    double num = 0, den = 0;
+    for (int i = 0; i < n; ++i) {
+      num += (x[i] - xo[i]) * (x[i] - xo[i]);
+      den += xo[i] * xo[i];
+    }
+    char nm[96];
+    snprintf(nm, sizeof(nm), "lap27_shifted/check_every_%d", check_every);
+    record(nm, std::abs(it - it_o) <= 2 && nr <= 1e-7 && std::sqrt(num / std::max(den, 1e-300)) < 1e-8,
+           "n=%d nnz=%lld: %d iterations (oracle %d), norm_res %.2e, |x-x_oracle|/|x_oracle| %.1e; %.3f ms = %.4f ms/iteration (SpMV alone "
+           "%.4f ms)",
+           n, (long long)A.nnz(), it, it_o, nr, std::sqrt(num / std::max(den, 1e-300)), ms, ms / std::max(it, 1), spmv_ms);
+  }
+  b200sp_spmv_plan_destroy(plan, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
 // suite: spmm_sweep -- the rank-2 kernels over column counts / scalar types / leading dimensions / beta
 // ------------------------------------------------------------------------------------------------
 static void ospmm(int m, int n, int k, const Csr<double>& A, const double* X, int64_t ldx, double* Y, int64_t ldy, double al, double be) {
@@ -1425,7 +1476,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
