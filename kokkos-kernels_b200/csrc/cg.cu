@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_dot_kernel(int n, const double*
 // x += alpha p; r -= alpha Ap; r_dot = r.r; then the scalar part of the iteration
 __global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ Ap,
                                                                double* __restrict__ x, double* __restrict__ r, double* __restrict__ slots,
-                                                               CgState* __restrict__ st, double tolerance, int maximum_iteration) {
+                                                               CgState* __restrict__ st) {
   if (((volatile CgState*)st)->done) return;
   const double alpha = st->old_rdot / st->pAp;
   double part = 0.0;
@@ -119,21 +119,20 @@ __global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const doub
     st->old_rdot = total;
     st->norm_res = sqrt(total);
     st->iteration += 1;
-    // `done` is raised by cg_p_kernel (the last kernel of the iteration) so that p still gets its update, as in the reference
+    // `done` is raised after the p update of this iteration (cg_flag_kernel), as the reference's loop does
   }
 }
 
-// p = r + beta p; raises `done` when the loop condition of the reference fails
-__global__ void __launch_bounds__(kCgThreads) cg_p_kernel(int n, const double* __restrict__ r, double* __restrict__ p, CgState* __restrict__ st,
-                                                          double tolerance, int maximum_iteration) {
+// p = r + beta p
+__global__ void __launch_bounds__(kCgThreads) cg_p_kernel(int n, const double* __restrict__ r, double* __restrict__ p, CgState* __restrict__ st) {
   if (((volatile CgState*)st)->done) return;
   const double beta = st->beta;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = 1.0 * r[i] + beta * p[i];
-  // every block has read `done` == 0 before any block can get here AND finish the grid?  No: blocks run independently, so the
-  // flag is raised by a separate one-thread kernel after this one (cg_flag_kernel) -- see the launch sequence.
 }
 
+// The loop condition of the reference (:372), evaluated once per iteration AFTER the p update.  A kernel of its own: the blocks of
+// cg_p_kernel run independently, so none of them may raise a flag the others still have to read as 0.
 __global__ void cg_flag_kernel(CgState* __restrict__ st, double tolerance, int maximum_iteration) {
   if (st->done) return;
   if (!(tolerance < st->norm_res && st->iteration < maximum_iteration)) st->done = 1;
@@ -194,9 +193,9 @@ extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int
       if (rc != B200SP_OK) return rc;
       cg_dot_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, slots, state);
       B200SP_LAUNCH_CHECK();
-      cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state, tolerance, maximum_iteration);
+      cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state);
       B200SP_LAUNCH_CHECK();
-      cg_p_kernel<<<grid, kCgThreads, 0, st>>>(n, r, p, state, tolerance, maximum_iteration);
+      cg_p_kernel<<<grid, kCgThreads, 0, st>>>(n, r, p, state);
       B200SP_LAUNCH_CHECK();
       cg_flag_kernel<<<1, 1, 0, st>>>(state, tolerance, maximum_iteration);
       B200SP_LAUNCH_CHECK();
