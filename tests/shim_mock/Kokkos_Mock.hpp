@@ -304,6 +304,14 @@ template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class
 struct spgemm_numeric_tpl_spec_avail {
   enum : bool { value = false };
 };
+// sparse/tpls/KokkosSparse_spgemm_jacobi_tpl_spec_avail.hpp:24-31, sparse/impl/KokkosSparse_spgemm_jacobi_spec.hpp:83-107
+template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v>
+struct spgemm_jacobi_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v,
+          bool tpl = spgemm_jacobi_tpl_spec_avail<KH, a_r, a_e, a_v, b_r, b_e, b_v, c_r, c_e, c_v, dinv_v>::value, bool eti = true>
+struct SPGEMM_JACOBI;
 template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r, bool tpl, bool eti>
 struct SPGEMM_SYMBOLIC;
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v,

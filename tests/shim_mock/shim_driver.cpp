@@ -9,6 +9,8 @@
 #include "KokkosSparse_spgemm_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spadd_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spadd_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_spgemm_jacobi_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_spgemm_jacobi_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_decl.hpp"
 
@@ -36,6 +38,8 @@ using SV    = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UM>;
 
 static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::value, "rank-1 specialisation must be available");
 static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
+using DINV  = Kokkos::View<const double**, KokkosKernels::default_layout, Dev, UM>;
+static_assert(Impl::spgemm_jacobi_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, IV, IV, SV, DINV>::value, "spgemm_jacobi must be available");
 using BMat  = Experimental::BsrMatrix<const double, const int, Dev, UM, const int>;
 static_assert(Impl::spmv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XVec, YVec>::value, "BsrMatrix rank-1 must be available");
 static_assert(Impl::spmv_mv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XMV, YMV>::value, "BsrMatrix rank-2 must be available");
@@ -54,7 +58,11 @@ T* to_dev(const std::vector<T>& h) {
 
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
-  const bool with_bsr = argc > 1 && std::string(argv[1]) == "--bsr";
+  bool with_bsr = false, with_jacobi = false;  // --jacobi: likewise for spgemm_jacobi
+  for (int a = 1; a < argc; ++a) {
+    with_bsr |= std::string(argv[a]) == "--bsr";
+    with_jacobi |= std::string(argv[a]) == "--jacobi";
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     std::printf("no CUDA device\n");
@@ -165,6 +173,45 @@ int main(int argc, char** argv) {
     if (!sh->is_symbolic_called() || !sh->is_numeric_called() || !sh->are_rowptrs_computed() || !sh->are_entries_computed()) ++f3;
     std::printf("spgemm through SPGEMM_SYMBOLIC/NUMERIC<...,true,true> : c_nnz=%zu, %d mismatches\n", cnnz, f3);
     failures += f3;
+    if (with_jacobi) {
+      // C = (I - omega*diag(dinv)*A)*A on the structure just computed, through SPGEMM_JACOBI<...,true,true>
+      using JAC = Impl::SPGEMM_JACOBI<KH, CIV, CIV, CSV, CIV, CIV, CSV, IV, IV, SV, DINV, true, true>;
+      const double omega = 0.75;
+      std::vector<double> dinv(n);
+      for (int i = 0; i < n; ++i) dinv[i] = 0.5 + 0.001 * (i % 97);
+      double* d_dinv = to_dev(dinv);
+      IV vciC(d_ciC, cnnz);
+      SV vvC(d_vC, cnnz);
+      JAC::spgemm_jacobi(&kh, n, n, n, vrp, vci, vva, false, vrp, vci, vva, false, IV(d_rpC, n + 1), vciC, vvC, omega, DINV(d_dinv, n, 1));
+      cudaDeviceSynchronize();
+      cudaMemcpy(ciC.data(), d_ciC, sizeof(int) * cnnz, cudaMemcpyDeviceToHost);
+      cudaMemcpy(vC.data(), d_vC, sizeof(double) * cnnz, cudaMemcpyDeviceToHost);
+      int f7 = 0;
+      for (int i = 0; i < n; ++i) {
+        std::vector<int> cols;
+        for (int a = rp[i]; a < rp[i + 1]; ++a)
+          for (int b = rp[ci[a]]; b < rp[ci[a] + 1]; ++b) {
+            if (!flag[ci[b]]) {
+              flag[ci[b]] = 1;
+              cols.push_back(ci[b]);
+            }
+            acc[ci[b]] += va[b] * va[a];
+          }
+        for (int c : cols) acc[c] *= -omega * dinv[i];
+        for (int b = rp[i]; b < rp[i + 1]; ++b) acc[ci[b]] += va[b];  // + row i of B (= A here)
+        for (int q = rpC[i]; q < rpC[i + 1]; ++q) {
+          if (q > rpC[i] && ciC[q] <= ciC[q - 1]) ++f7;
+          if (!flag[ciC[q]] || std::fabs(vC[q] - acc[ciC[q]]) > 1e-12 * (1 + std::fabs(acc[ciC[q]]))) ++f7;
+        }
+        for (int c : cols) {
+          flag[c] = 0;
+          acc[c]  = 0;
+        }
+      }
+      std::printf("spgemm_jacobi through SPGEMM_JACOBI<...,true,true> : %d mismatches\n", f7);
+      failures += f7;
+      cudaFree(d_dinv);
+    }
     kh.destroy_spgemm_handle();
   }
   {
