@@ -358,3 +358,69 @@ def test_cg_driver(emu, oracle):
     it0, _ = E.cg_solve(plan, rp, ci, v, b, xo.copy(), 100, 1e-5, 4)  # converged start: no iteration
     assert it0 == 0
     plan.close()
+
+
+def test_multi_gpu_kernels_single_process(emu, oracle):
+    """The device side of the row-block operator (kokkos-kernels_b200/multigpu.py) with the ranks played one after the other in
+    one process: every rank's SpMV stores its block of y into its own buffer AND into the slots of the other ranks' next-x
+    buffers (b200sp_spmv_scatter_*, the fused all-gather; peer pointers are plain pointers here), then the copy kernel of the
+    multicast mode (b200sp_multicast_push) for every size / alignment class it distinguishes.  Needs no NVLink: logic only."""
+    L = emu
+    n, P = 9000, 3
+    rp, ci, v = kk_matrix(n, n, n * 9, 5, 400)
+    x = np.random.default_rng(4).uniform(-1, 1, n)
+    exp = oracle.spmv_serial(rp, ci, v, x, np.zeros(n), 1.0, 0.0)
+    bounds = [0, 2999, 6001, n]  # ragged blocks, odd offsets (8-byte aligned slots only)
+    nxt = [np.full(n, np.nan) for _ in range(P)]  # every rank's buffer for the next x
+    for r in range(P):
+        lo, hi = bounds[r], bounds[r + 1]
+        rpl = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)  # row block with rebased row map; columns stay global
+        cil, vl = ci[rp[lo]:rp[hi]].copy(), v[rp[lo]:rp[hi]].copy()
+        plan = E.SpmvPlan()
+        E.ok(L.b200sp_spmv_plan_tune(plan.h, 8, 4, 0))  # the tile kernel, as at bench size
+        extra = [nxt[q][lo:hi] for q in range(P) if q != r]
+        arr = (C.c_void_p * len(extra))(*[C.c_void_p(a.ctypes.data) for a in extra])
+        E.ok(L.b200sp_spmv_scatter_f64_i32(plan.h, None, hi - lo, n, len(cil), 1.0, E.ptr(rpl), E.ptr(cil), E.ptr(vl), E.ptr(x),
+                                           E.ptr(nxt[r][lo:hi]), len(extra), arr))
+        assert plan.kernel().startswith("tile"), plan.kernel()
+        plan.close()
+    scale = rowwise_scale(rp, ci, v, x, np.zeros(n), 1.0, 0.0)
+    for q in range(P):
+        assert not np.isnan(nxt[q]).any()
+        assert np.array_equal(nxt[q], nxt[0])  # every replica bit-identical
+        assert np.all(np.abs(nxt[q] - exp) <= 1e-10 * scale + 1e-300)
+    # multicast push: 16-byte stores with a one-element head / tail when the 16-byte phase asks for it
+    src_all = np.random.default_rng(5).uniform(-1, 1, 5000)
+    for off in (0, 1):  # 8-byte phase of both pointers (they must agree)
+        for cnt in (0, 1, 2, 3, 255, 256, 257, 4097):
+            src = src_all[off:off + cnt]
+            dst_all = np.full(5000, -7.0)
+            dst = dst_all[2 + off:2 + off + cnt]
+            assert ((src.ctypes.data ^ dst.ctypes.data) & 15) == 0 or cnt == 0
+            E.ok(L.b200sp_multicast_push(None, E.ptr(src) if cnt else None, E.ptr(dst) if cnt else None, cnt * 8, 3))
+            assert np.array_equal(dst, src)
+            assert np.all(dst_all[:2 + off] == -7.0) and np.all(dst_all[2 + off + cnt:] == -7.0)  # nothing outside
+    y = np.zeros(4)
+    assert L.b200sp_multicast_push(None, E.ptr(src_all[0:4]), E.ptr(y[1:]), 24, 1) != 0  # different 16-byte phase: refused
+
+
+@pytest.mark.parametrize("pieces", [None, "1", "3", "8"])
+def test_hostvec_pipeline_logic(emu, oracle, pieces):
+    """b200sp_spmv_hostvec_* (host x / y, double-buffered upload, piecewise compute + download): the piece arithmetic for
+    every piece count, incl. the B200SP_HOSTVEC_PIECES override; streams and copies are synchronous under the emulation."""
+    n = 70000  # nnz >= 2^22 switches the pipeline on
+    rp, ci, v = kk_matrix(n, n, n * 64, 3, 2000)
+    assert len(ci) >= (1 << 22)
+    rng = np.random.default_rng(8)
+    x, y0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    with env(B200SP_HOSTVEC_PIECES=pieces):
+        for alpha, beta in ((1.0, 0.0), (2.0, -0.5)):
+            plan = E.SpmvPlan()
+            y = y0.copy()
+            for _ in range(2):  # second call: staging buffers and analysis reused
+                y[:] = y0
+                E.ok(emu.b200sp_spmv_hostvec_f64_i32(plan.h, None, b"N", n, n, len(ci), alpha, E.ptr(rp), E.ptr(ci), E.ptr(v), E.ptr(x), beta,
+                                                     E.ptr(y)))
+            plan.close()
+            exp = oracle.spmv_serial(rp, ci, v, x, y0.copy(), alpha, beta)
+            assert np.all(np.abs(y - exp) <= 1e-10 * rowwise_scale(rp, ci, v, x, y0, alpha, beta) + 1e-300)
