@@ -330,6 +330,24 @@ int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t
                             int maximum_iteration, double tolerance, int check_every, int* iterations,
                             double* norm_res);
 
+/* ---- GMRES -----------------------------------------------------------------------------------
+ * KokkosSparse::Experimental::gmres(handle, A, B, X, precond) (sparse/src/KokkosSparse_gmres.hpp:60-160 ->
+ * GmresWrap::gmres, sparse/impl/KokkosSparse_gmres_impl.hpp:58-327) for a CrsMatrix: restarted GMRES(m) with CGS2
+ * (ortho = 0) or MGS (ortho = 1), x = initial guess on entry and solution on return.  m, tol, max_restart and the three
+ * results are GMRESHandle's (sparse/src/KokkosSparse_gmres_handle.hpp:76-110,175): num_iters, end_rel_res, conv_flag
+ * (0 Conv, 1 NoConv, 2 LOA).  The optional right preconditioner is the reference's MatrixPrec -- an spmv with the matrix
+ * (row_ptr_M, col_idx_M, vals_M), which needs its own plan; pass row_ptr_M = NULL for none.  B200SP_ERR_STATE with the
+ * reference's message where it throws (lucky breakdown without convergence, NaN residual, :211-218);
+ * B200SP_ERR_INVALID_ARGUMENT for an unknown ortho (:173).  Synchronous: returns after the solve. */
+int b200sp_gmres_f64_i32(b200sp_spmv_plan* plan_A, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                         const double* vals, b200sp_spmv_plan* plan_M, int64_t nnz_M, const int* row_ptr_M,
+                         const int* col_idx_M, const double* vals_M, const double* b, double* x, int m, double tol,
+                         int max_restart, int ortho, int* num_iters, double* end_rel_res, int* conv_flag);
+int b200sp_gmres_f32_i32(b200sp_spmv_plan* plan_A, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                         const float* vals, b200sp_spmv_plan* plan_M, int64_t nnz_M, const int* row_ptr_M,
+                         const int* col_idx_M, const float* vals_M, const float* b, float* x, int m, float tol,
+                         int max_restart, int ortho, int* num_iters, float* end_rel_res, int* conv_flag);
+
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */
 int64_t b200sp_launch_count(void);

@@ -235,6 +235,80 @@ def _spmv_bsr(lib, plan, mc, alpha, A, x, beta, y, f64, xcols):
     return y
 
 
+class GMRESHandle:
+    """sparse/src/KokkosSparse_gmres_handle.hpp:66-186: options (m, tol, max_restart, ortho, verbose) and the statistics of the
+    last run (num_iters, end_rel_res, conv_flag_val)."""
+
+    CGS2, MGS = 0, 1  # Ortho (:76-79)
+    Conv, NoConv, LOA, NotRun = 0, 1, 2, 3  # Flag (:84-89)
+
+    def __init__(self, m=50, tol=1e-8, max_restart=50):
+        self.reset_handle(m, tol, max_restart)
+
+    def reset_handle(self, m=50, tol=1e-8, max_restart=50):
+        self.m, self.tol, self.max_restart = int(m), float(tol), int(max_restart)
+        self.ortho, self.verbose = GMRESHandle.CGS2, False
+        self.num_iters, self.end_rel_res, self.conv_flag_val = -1, 0.0, GMRESHandle.NotRun
+
+    def set_m(self, m): self.m = int(m)
+    def set_tol(self, tol): self.tol = float(tol)
+    def set_max_restart(self, r): self.max_restart = int(r)
+    def set_ortho(self, o): self.ortho = o
+    def set_verbose(self, v): self.verbose = bool(v)
+    def get_m(self): return self.m
+    def get_tol(self): return self.tol
+    def get_max_restart(self): return self.max_restart
+    def get_ortho(self): return self.ortho
+    def get_num_iters(self): return self.num_iters
+    def get_end_rel_res(self): return self.end_rel_res
+    def get_conv_flag_val(self): return self.conv_flag_val
+
+
+class MatrixPrec:
+    """KokkosSparse::Experimental::MatrixPrec (sparse/src/KokkosSparse_MatrixPrec.hpp:33-96): a preconditioner whose apply is
+    an spmv with the given matrix."""
+
+    def __init__(self, A):
+        self.A = A
+        self._handle = SPMVHandle(SPMV_DEFAULT)
+
+
+def gmres(handle, A, B, X, precond=None, spmv_handle=None):
+    """KokkosSparse::Experimental::gmres(handle, A, B, X, precond) (sparse/src/KokkosSparse_gmres.hpp:60-160): `handle` is a
+    GMRESHandle (or a KokkosKernelsHandle carrying one); A a CrsMatrix (a BsrMatrix is not wired to this entry yet); X is the
+    initial guess and receives the solution.  Statistics land on the handle (set_stats, gmres_handle.hpp:175)."""
+    gh = handle.get_gmres_handle() if hasattr(handle, "get_gmres_handle") else handle
+    if isinstance(A, BsrMatrix):
+        raise B200SparseError("b200sparse: gmres on a BsrMatrix is not available (CrsMatrix only)")
+    n = A.numRows()
+    if A.numCols() != n:  # gmres.hpp:84-90
+        raise B200SparseError(f"KokkosSparse::gmres: A must be a square matrix: numRows: {n}  numCols: {A.numCols()}")
+    if X.dim() != 1 or B.dim() != 1 or X.shape[0] != n or B.shape[0] != n:  # :92-101
+        raise B200SparseError(f"KokkosSparse::gmres: Dimensions do not match: X: {X.shape[0]} B: {B.shape[0]} A: {n}")
+    if not (A.values.dtype == X.dtype == B.dtype) or X.dtype not in (torch.float64, torch.float32):
+        raise B200SparseError("b200sparse: gmres needs A, B, X of one scalar type (double or float)")
+    if gh.ortho not in (GMRESHandle.CGS2, GMRESHandle.MGS):
+        raise B200SparseInvalidArgument("Invalid argument for 'ortho'.  Please use 'CGS2' or 'MGS'.")
+    f64 = X.dtype == torch.float64
+    lib = _lib.sparse()
+    fn = lib.b200sp_gmres_f64_i32 if f64 else lib.b200sp_gmres_f32_i32
+    ha = spmv_handle if spmv_handle is not None else SPMVHandle(SPMV_DEFAULT)
+    it, flag = C.c_int(0), C.c_int(0)
+    res = C.c_double(0.0) if f64 else C.c_float(0.0)
+    tol = C.c_double(gh.tol) if f64 else C.c_float(gh.tol)
+    if precond is not None:
+        M = precond.A
+        if M.numRows() != n or M.numCols() != n or M.values.dtype != X.dtype:
+            raise B200SparseError("gmres: the MatrixPrec matrix must be n x n with A's scalar type")
+        pm, nnzm, rpm, cim, vm = precond._handle._plan, M.nnz(), _ptr(M.row_map), _ptr(M.entries), _ptr(M.values)
+    else:
+        pm, nnzm, rpm, cim, vm = C.c_void_p(0), 0, C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+    check(fn(ha._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm, _ptr(B), _ptr(X),
+             gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
+    gh.num_iters, gh.end_rel_res, gh.conv_flag_val = it.value, float(res.value), flag.value
+    return gh
+
+
 class CGSolveResult:
     """perf_test/sparse/KokkosSparse_pcg.hpp:38-45 (the fields this driver fills)."""
 
@@ -349,6 +423,15 @@ class KokkosKernelsHandle:
 
     def destroy_spadd_handle(self):
         self._ah = None
+
+    def create_gmres_handle(self, m=50, tol=1e-8, max_restart=50):  # KokkosKernels_Handle.hpp (create_gmres_handle)
+        self._gmres = GMRESHandle(m, tol, max_restart)
+
+    def get_gmres_handle(self):
+        return self._gmres
+
+    def destroy_gmres_handle(self):
+        self._gmres = None
 
     def create_spgemm_handle(self, algo=SPGEMM_KK):
         self._sh = SPGEMMHandle(algo)

@@ -191,3 +191,17 @@ def cg_solve(plan, rp, ci, v, b, x, maximum_iteration, tolerance, check_every=0)
     ok(lib().b200sp_cg_solve_f64_i32(plan.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), ptr(b), ptr(x), maximum_iteration,
                                      C.c_double(tolerance), check_every, C.byref(it), C.byref(nr)))
     return it.value, nr.value
+
+
+def gmres(plan_a, A, b, x, m=50, tol=1e-8, max_restart=50, ortho=0, prec=None, plan_m=None):
+    """b200sp_gmres_*: returns (status, num_iters, end_rel_res, conv_flag); x updated in place."""
+    rp, ci, v = A
+    f64 = v.dtype == np.float64
+    fn = lib().b200sp_gmres_f64_i32 if f64 else lib().b200sp_gmres_f32_i32
+    it, flag = C.c_int(), C.c_int()
+    res = C.c_double() if f64 else C.c_float()
+    pr = prec if prec is not None else (None, None, None)
+    rc = fn(plan_a.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), plan_m.h if plan_m else None, len(pr[1]) if prec is not None else 0,
+            ptr(pr[0]), ptr(pr[1]), ptr(pr[2]), ptr(b), ptr(x), m, scalar(v.dtype, tol), max_restart, ortho, C.byref(it), C.byref(res),
+            C.byref(flag))
+    return rc, it.value, res.value, flag.value

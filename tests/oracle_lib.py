@@ -63,6 +63,8 @@ class Oracle:
             getattr(L, f"okk_bsr_spmv_v42_{sfx}").argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
             getattr(L, f"okk_bsr_spmv_v41_{sfx}").argtypes = [C.c_char, i32, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
             getattr(L, f"okk_bsr_to_crs_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.okk_gmres_f64.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
+        L.okk_gmres_f32.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
         L.okk_cg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64)]
         L.okk_cg_f64.restype = i32
         self.ref = None
@@ -265,6 +267,17 @@ class Oracle:
         nr = f64()
         it = self.lib.okk_cg_f64(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), maximum_iteration, tolerance, C.byref(nr))
         return it, nr.value
+
+    def gmres(self, A, b, x, m=50, tol=1e-8, max_restart=50, ortho=0, prec=None):
+        """KokkosSparse::Experimental::gmres (host restatement); x updated in place.  prec = (rp, ci, v) of a MatrixPrec.
+        Returns (status, num_iters, end_rel_res, conv_flag); status -1 / -2 = the reference's breakdown / NaN throws."""
+        rp, ci, v = A
+        ft = f64 if v.dtype == np.float64 else f32
+        it, res, flag = i32(), ft(), i32()
+        pr = prec if prec is not None else (None, None, None)
+        st = getattr(self.lib, "okk_gmres_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(pr[0]), _p(pr[1]), _p(pr[2]), _p(b), _p(x), m, tol,
+                                                           max_restart, ortho, C.byref(it), C.byref(res), C.byref(flag))
+        return st, it.value, res.value, flag.value
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)

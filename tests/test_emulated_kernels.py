@@ -424,3 +424,55 @@ def test_hostvec_pipeline_logic(emu, oracle, pieces):
             plan.close()
             exp = oracle.spmv_serial(rp, ci, v, x, y0.copy(), alpha, beta)
             assert np.all(np.abs(y - exp) <= 1e-10 * rowwise_scale(rp, ci, v, x, y0, alpha, beta) + 1e-300)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-5)])
+@pytest.mark.parametrize("variant", ["cgs2", "mgs", "matrixprec"])
+def test_gmres(emu, oracle, dtype, tol, variant):
+    """b200sp_gmres_* on the reference's own unit test (sparse/unit_test/Test_Sparse_gmres.hpp:86-170: n = 5000, m = 15, B = 1,
+    X = 0, CGS2 / MGS / MatrixPrec(A), double 1e-8 and float 1e-5): true relative residual below the tolerance, flag Conv, and
+    the same iteration count as the oracle's restatement of the reference algorithm."""
+    from gmres_cases import gmres_matrix, true_rel_res
+
+    n, m = 5000, 15
+    A = gmres_matrix(n, 1.0, dtype=dtype)
+    b = np.ones(n, dtype=dtype)
+    prec = A if variant == "matrixprec" else None
+    ortho = 1 if variant == "mgs" else 0
+    xo = np.zeros(n, dtype=dtype)
+    st_o, it_o, res_o, flag_o = oracle.gmres(A, b, xo, m=m, tol=tol, ortho=ortho, prec=prec)
+    pa, pm = E.SpmvPlan(), (E.SpmvPlan() if prec is not None else None)
+    x = np.zeros(n, dtype=dtype)
+    rc, it, res, flag = E.gmres(pa, A, b, x, m=m, tol=tol, ortho=ortho, prec=prec, plan_m=pm)
+    pa.close()
+    if pm:
+        pm.close()
+    assert rc == 0 and flag == 0 == flag_o, (rc, it, res, flag)
+    assert true_rel_res(oracle, A, b, x) < tol and res < tol
+    assert abs(it - it_o) <= 1, (it, it_o)
+    assert np.linalg.norm(x.astype(np.float64) - xo.astype(np.float64)) / np.linalg.norm(xo.astype(np.float64)) < 50 * tol
+
+
+def test_gmres_corner_cases(emu, oracle):
+    from gmres_cases import gmres_matrix
+
+    n = 300
+    A = gmres_matrix(n, 2.0)
+    pa = E.SpmvPlan()
+    x = np.ones(n)
+    rc, it, res, flag = E.gmres(pa, A, np.zeros(n), x, m=10)  # zero rhs: X reset to 0
+    assert rc == 0 and it == 0 and res == 0 and np.all(x == 0) and flag == 0
+    xs = np.random.default_rng(1).uniform(-1, 1, n)
+    b = np.zeros(n)
+    oracle.spmv_serial(A[0], A[1], A[2], xs, b, 1.0, 0.0)
+    x = xs.copy()
+    rc, it, res, flag = E.gmres(pa, A, b, x, m=10)  # exact guess
+    assert rc == 0 and it == 0 and flag == 0 and np.array_equal(x, xs)
+    hard = gmres_matrix(n, 0.02)
+    x, xo = np.zeros(n), np.zeros(n)
+    rc, it, res, flag = E.gmres(pa, hard, np.ones(n), x, m=2, tol=1e-13, max_restart=1)  # restart limit: never Conv
+    st_o, it_o, res_o, flag_o = oracle.gmres(hard, np.ones(n), xo, m=2, tol=1e-13, max_restart=1)
+    assert rc == 0 and flag == flag_o != 0 and it == it_o and abs(res - res_o) <= 1e-8 * abs(res_o)
+    assert emu.b200sp_gmres_f64_i32(pa.h, None, n, len(A[1]), E.ptr(A[0]), E.ptr(A[1]), E.ptr(A[2]), None, 0, None, None, None, E.ptr(b), E.ptr(x), 10,
+                                    1e-8, 50, 7, C.byref(C.c_int()), C.byref(C.c_double()), C.byref(C.c_int())) != 0  # ortho
+    pa.close()
