@@ -347,6 +347,17 @@ int b200sp_gmres_f32_i32(b200sp_spmv_plan* plan_A, void* stream, int n, int64_t 
                          const float* vals, b200sp_spmv_plan* plan_M, int64_t nnz_M, const int* row_ptr_M,
                          const int* col_idx_M, const float* vals_M, const float* b, float* x, int m, float tol,
                          int max_restart, int ortho, int* num_iters, float* end_rel_res, int* conv_flag);
+/* The BsrMatrix overload (sparse/impl/KokkosSparse_gmres_spec.hpp:79-82): A (and the MatrixPrec matrix) are mb x mb blocks of
+ * bs x bs; b and x have mb*bs entries; the plans are b200sp_bsr_plan. */
+int b200sp_gmres_bsr_f64_i32(b200sp_bsr_plan* plan_A, void* stream, int mb, int64_t nnzb, int bs, const int* row_ptr,
+                             const int* col_idx, const double* vals, b200sp_bsr_plan* plan_M, int64_t nnzb_M,
+                             const int* row_ptr_M, const int* col_idx_M, const double* vals_M, const double* b, double* x,
+                             int m, double tol, int max_restart, int ortho, int* num_iters, double* end_rel_res,
+                             int* conv_flag);
+int b200sp_gmres_bsr_f32_i32(b200sp_bsr_plan* plan_A, void* stream, int mb, int64_t nnzb, int bs, const int* row_ptr,
+                             const int* col_idx, const float* vals, b200sp_bsr_plan* plan_M, int64_t nnzb_M,
+                             const int* row_ptr_M, const int* col_idx_M, const float* vals_M, const float* b, float* x, int m,
+                             float tol, int max_restart, int ortho, int* num_iters, float* end_rel_res, int* conv_flag);
 
 /* ---- introspection / tuning (bench + tests only) ------------------------- */
 /* Counts kernels launched by this library since process start (all plans). */

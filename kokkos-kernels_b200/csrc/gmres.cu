@@ -2,7 +2,7 @@
 //
 // Follows KokkosSparse::Experimental::gmres = GmresWrap::gmres, sparse/impl/KokkosSparse_gmres_impl.hpp:58-327 (public entry
 // sparse/src/KokkosSparse_gmres.hpp:60-160, options and results sparse/src/KokkosSparse_gmres_handle.hpp:76-110,175), for
-// real scalars on a CrsMatrix, with the optional right preconditioner in the form the reference ships and tests: MatrixPrec,
+// real scalars on a CrsMatrix or a BsrMatrix, with the optional right preconditioner in the form the reference ships and tests: MatrixPrec,
 // an spmv with a given matrix (sparse/src/KokkosSparse_MatrixPrec.hpp:79-83).
 //
 // The algorithm is the reference's, step for step (Arnoldi with CGS2 or MGS, Givens rotations and the triangular solve on
@@ -18,11 +18,7 @@
 
 #include "common.cuh"
 
-struct b200sp_spmv_plan;
-extern "C" int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, double alpha,
-                                   const int* row_ptr, const int* col_idx, const double* vals, const double* x, double beta, double* y);
-extern "C" int b200sp_spmv_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, float alpha,
-                                   const int* row_ptr, const int* col_idx, const float* vals, const float* x, float beta, float* y);
+// (the b200sp_spmv_* / b200sp_bsr_spmv_* prototypes come with b200sparse.h through common.cuh)
 
 namespace b200sp {
 namespace {
@@ -30,13 +26,25 @@ namespace {
 constexpr int kGmThreads = 256;
 constexpr int kGmDots = 8;  // basis vectors per pass of the multi-dot kernel
 
-inline int call_spmv(b200sp_spmv_plan* p, cudaStream_t st, int n, int64_t nnz, const int* rp, const int* ci, const double* v,
-                     const double* x, double* y) {
-  return b200sp_spmv_f64_i32(p, st, 'N', n, n, nnz, 1.0, rp, ci, v, x, 0.0, y);
+// y = A x for the two matrix types the reference's gmres accepts (sparse/impl/KokkosSparse_gmres_spec.hpp:76-82): a CrsMatrix
+// (bs == 0, plan = b200sp_spmv_plan) or a BsrMatrix (bs >= 1, plan = b200sp_bsr_plan; rows / nnz count blocks)
+template <typename S>
+struct LinOp {
+  void* plan;
+  int rows;
+  int64_t nnz;
+  int bs;
+  const int* rp;
+  const int* ci;
+  const S* v;
+};
+inline int apply_op(const LinOp<double>& a, cudaStream_t st, const double* x, double* y) {
+  if (a.bs == 0) return b200sp_spmv_f64_i32((b200sp_spmv_plan*)a.plan, st, 'N', a.rows, a.rows, a.nnz, 1.0, a.rp, a.ci, a.v, x, 0.0, y);
+  return b200sp_bsr_spmv_f64_i32((b200sp_bsr_plan*)a.plan, st, 'N', a.rows, a.rows, a.nnz, a.bs, 1.0, a.rp, a.ci, a.v, x, 0.0, y);
 }
-inline int call_spmv(b200sp_spmv_plan* p, cudaStream_t st, int n, int64_t nnz, const int* rp, const int* ci, const float* v,
-                     const float* x, float* y) {
-  return b200sp_spmv_f32_i32(p, st, 'N', n, n, nnz, 1.0f, rp, ci, v, x, 0.0f, y);
+inline int apply_op(const LinOp<float>& a, cudaStream_t st, const float* x, float* y) {
+  if (a.bs == 0) return b200sp_spmv_f32_i32((b200sp_spmv_plan*)a.plan, st, 'N', a.rows, a.rows, a.nnz, 1.0f, a.rp, a.ci, a.v, x, 0.0f, y);
+  return b200sp_bsr_spmv_f32_i32((b200sp_bsr_plan*)a.plan, st, 'N', a.rows, a.rows, a.nnz, a.bs, 1.0f, a.rp, a.ci, a.v, x, 0.0f, y);
 }
 
 // out[i] = V(:, i) . w for i < cnt (cnt <= kGmDots); V column-major with leading dimension ldv.  Two-stage: per-block
@@ -157,16 +165,19 @@ struct Gm {
   } while (0)
 
 template <typename S>
-int gmres_impl(b200sp_spmv_plan* planA, cudaStream_t st, int n, int64_t nnz, const int* rp, const int* ci, const S* v,
-               b200sp_spmv_plan* planM, int64_t nnzM, const int* rpM, const int* ciM, const S* vM, const S* B, S* X, int m, S tol,
-               int max_restart, int ortho, int* num_iters_out, S* end_rel_res_out, int* conv_flag_out) {
-  B200SP_REQUIRE(planA != nullptr, "gmres: null SpMV plan for A");
-  B200SP_REQUIRE(n >= 0 && nnz >= 0 && m >= 1 && max_restart >= 0, "gmres: bad size (n=%d m=%d max_restart=%d)", n, m, max_restart);
+int gmres_impl(const LinOp<S>& A, const LinOp<S>* M, cudaStream_t st, const S* B, S* X, int m, S tol, int max_restart, int ortho,
+               int* num_iters_out, S* end_rel_res_out, int* conv_flag_out) {
+  B200SP_REQUIRE(A.plan != nullptr, "gmres: null plan for A");
+  B200SP_REQUIRE(A.rows >= 0 && A.nnz >= 0 && A.bs >= 0 && m >= 1 && max_restart >= 0, "gmres: bad size (rows=%d m=%d max_restart=%d)", A.rows, m,
+                 max_restart);
+  B200SP_REQUIRE((int64_t)A.rows * std::max(A.bs, 1) <= INT32_MAX, "gmres: point dimension exceeds int32");
+  const int n = A.rows * std::max(A.bs, 1);
+  const int* rp = A.rp;
   B200SP_REQUIRE(ortho == 0 || ortho == 1, "Invalid argument for 'ortho'.  Please use 'CGS2' or 'MGS'.");  // gmres_impl.hpp:173
   B200SP_REQUIRE(num_iters_out && end_rel_res_out && conv_flag_out, "gmres: null result pointer");
   B200SP_REQUIRE(n == 0 || (rp && B && X), "gmres: null array");
-  const bool prec = rpM != nullptr;
-  B200SP_REQUIRE(!prec || planM != nullptr, "gmres: the preconditioner matrix needs its own SpMV plan");
+  const bool prec = M != nullptr;
+  B200SP_REQUIRE(!prec || (M->plan != nullptr && M->rows * std::max(M->bs, 1) == n), "gmres: the preconditioner matrix needs its own plan and A's size");
   *num_iters_out = 0;
   *end_rel_res_out = S(0);
   *conv_flag_out = 0;
@@ -196,7 +207,7 @@ int gmres_impl(b200sp_spmv_plan* planA, cudaStream_t st, int n, int64_t nnz, con
   S nrmB, trueRes, relRes, shortRelRes;
   GM_TRY(g.nrm2(B, &nrmB));
   B200SP_CUDA_TRY(cudaMemcpyAsync(Res, B, sizeof(S) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-  GM_TRY(call_spmv(planA, st, n, nnz, rp, ci, v, X, Wj));  // wj = A x
+  GM_TRY(apply_op(A, st, X, Wj));  // wj = A x
   GM_TRY(g.axpby(S(-1), Wj, S(1), Res));                   // res = b - A x
   GM_TRY(g.nrm2(Res, &trueRes));
   if (nrmB != S(0)) {
@@ -217,10 +228,10 @@ int gmres_impl(b200sp_spmv_plan* planA, cudaStream_t st, int n, int64_t nnz, con
     GM_TRY(g.axpby(S(1) / trueRes, Res, S(0), Vj));  // V0 = res / |res|
     for (int j = 0; j < m; j++) {
       if (prec) {  // right preconditioner: wj = A (M vj)
-        GM_TRY(call_spmv(planM, st, n, nnzM, rpM, ciM, vM, Vj, Wj2));
-        GM_TRY(call_spmv(planA, st, n, nnz, rp, ci, v, Wj2, Wj));
+        GM_TRY(apply_op(*M, st, Vj, Wj2));
+        GM_TRY(apply_op(A, st, Wj2, Wj));
       } else {
-        GM_TRY(call_spmv(planA, st, n, nnz, rp, ci, v, Vj, Wj));
+        GM_TRY(apply_op(A, st, Vj, Wj));
       }
       S* Hj = H.data() + (size_t)j * ldh;
       if (ortho == 1) {  // MGS: the coefficient of each step feeds the next update on the device
@@ -282,14 +293,14 @@ int gmres_impl(b200sp_spmv_plan* planA, cudaStream_t st, int n, int64_t nnz, con
         if (prec) {  // Xiter = X + M (V y)
           gm_lincomb_kernel<S><<<grid, kGmThreads, 0, st>>>(n, j + 1, V, ld, hdev, (const S*)nullptr, Wj);
           B200SP_LAUNCH_CHECK();
-          GM_TRY(call_spmv(planM, st, n, nnzM, rpM, ciM, vM, Wj, Wj2));
+          GM_TRY(apply_op(*M, st, Wj, Wj2));
           B200SP_CUDA_TRY(cudaMemcpyAsync(Xiter, X, sizeof(S) * (size_t)n, cudaMemcpyDeviceToDevice, st));
           GM_TRY(g.axpby(S(1), Wj2, S(1), Xiter));
         } else {  // Xiter = X + V y
           gm_lincomb_kernel<S><<<grid, kGmThreads, 0, st>>>(n, j + 1, V, ld, hdev, X, Xiter);
           B200SP_LAUNCH_CHECK();
         }
-        GM_TRY(call_spmv(planA, st, n, nnz, rp, ci, v, Xiter, Wj));
+        GM_TRY(apply_op(A, st, Xiter, Wj));
         B200SP_CUDA_TRY(cudaMemcpyAsync(Res, B, sizeof(S) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         GM_TRY(g.axpby(S(-1), Wj, S(1), Res));
         GM_TRY(g.nrm2(Res, &trueRes));
@@ -321,19 +332,19 @@ using namespace b200sp;
 
 extern "C" {
 
-int b200sp_gmres_f64_i32(b200sp_spmv_plan* plan_A, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
-                         const double* vals, b200sp_spmv_plan* plan_M, int64_t nnz_M, const int* row_ptr_M, const int* col_idx_M,
-                         const double* vals_M, const double* b, double* x, int m, double tol, int max_restart, int ortho, int* num_iters,
-                         double* end_rel_res, int* conv_flag) {
-  return gmres_impl<double>(plan_A, (cudaStream_t)stream, n, nnz, row_ptr, col_idx, vals, plan_M, nnz_M, row_ptr_M, col_idx_M, vals_M, b, x, m,
-                            tol, max_restart, ortho, num_iters, end_rel_res, conv_flag);
-}
-int b200sp_gmres_f32_i32(b200sp_spmv_plan* plan_A, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
-                         const float* vals, b200sp_spmv_plan* plan_M, int64_t nnz_M, const int* row_ptr_M, const int* col_idx_M,
-                         const float* vals_M, const float* b, float* x, int m, float tol, int max_restart, int ortho, int* num_iters,
-                         float* end_rel_res, int* conv_flag) {
-  return gmres_impl<float>(plan_A, (cudaStream_t)stream, n, nnz, row_ptr, col_idx, vals, plan_M, nnz_M, row_ptr_M, col_idx_M, vals_M, b, x, m,
-                           tol, max_restart, ortho, num_iters, end_rel_res, conv_flag);
-}
+#define B200SP_GMRES_ENTRY(NAME, S, PLAN, BSARG, BSVAL)                                                                                \
+  int NAME(PLAN* plan_A, void* stream, int rows, int64_t nnz BSARG, const int* row_ptr, const int* col_idx, const S* vals, PLAN* plan_M,  \
+           int64_t nnz_M, const int* row_ptr_M, const int* col_idx_M, const S* vals_M, const S* b, S* x, int m, S tol, int max_restart,   \
+           int ortho, int* num_iters, S* end_rel_res, int* conv_flag) {                                                                \
+    const LinOp<S> A{(void*)plan_A, rows, nnz, BSVAL, row_ptr, col_idx, vals};                                                          \
+    const LinOp<S> M{(void*)plan_M, rows, nnz_M, BSVAL, row_ptr_M, col_idx_M, vals_M};                                                  \
+    return gmres_impl<S>(A, row_ptr_M ? &M : nullptr, (cudaStream_t)stream, b, x, m, tol, max_restart, ortho, num_iters, end_rel_res,   \
+                         conv_flag);                                                                                                    \
+  }
+#define B200SP_COMMA_BS , int bs
+B200SP_GMRES_ENTRY(b200sp_gmres_f64_i32, double, b200sp_spmv_plan, , 0)
+B200SP_GMRES_ENTRY(b200sp_gmres_f32_i32, float, b200sp_spmv_plan, , 0)
+B200SP_GMRES_ENTRY(b200sp_gmres_bsr_f64_i32, double, b200sp_bsr_plan, B200SP_COMMA_BS, bs)
+B200SP_GMRES_ENTRY(b200sp_gmres_bsr_f32_i32, float, b200sp_bsr_plan, B200SP_COMMA_BS, bs)
 
 }  // extern "C"

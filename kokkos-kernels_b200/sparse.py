@@ -275,14 +275,14 @@ class MatrixPrec:
 
 def gmres(handle, A, B, X, precond=None, spmv_handle=None):
     """KokkosSparse::Experimental::gmres(handle, A, B, X, precond) (sparse/src/KokkosSparse_gmres.hpp:60-160): `handle` is a
-    GMRESHandle (or a KokkosKernelsHandle carrying one); A a CrsMatrix (a BsrMatrix is not wired to this entry yet); X is the
+    GMRESHandle (or a KokkosKernelsHandle carrying one); A a CrsMatrix or a BsrMatrix; X is the
     initial guess and receives the solution.  Statistics land on the handle (set_stats, gmres_handle.hpp:175)."""
     gh = handle.get_gmres_handle() if hasattr(handle, "get_gmres_handle") else handle
-    if isinstance(A, BsrMatrix):
-        raise B200SparseError("b200sparse: gmres on a BsrMatrix is not available (CrsMatrix only)")
-    n = A.numRows()
-    if A.numCols() != n:  # gmres.hpp:84-90
-        raise B200SparseError(f"KokkosSparse::gmres: A must be a square matrix: numRows: {n}  numCols: {A.numCols()}")
+    is_bsr = isinstance(A, BsrMatrix)
+    n = A.numPointRows() if is_bsr else A.numRows()
+    ncols = A.numPointCols() if is_bsr else A.numCols()
+    if ncols != n:  # gmres.hpp:84-90
+        raise B200SparseError(f"KokkosSparse::gmres: A must be a square matrix: numRows: {n}  numCols: {ncols}")
     if X.dim() != 1 or B.dim() != 1 or X.shape[0] != n or B.shape[0] != n:  # :92-101
         raise B200SparseError(f"KokkosSparse::gmres: Dimensions do not match: X: {X.shape[0]} B: {B.shape[0]} A: {n}")
     if not (A.values.dtype == X.dtype == B.dtype) or X.dtype not in (torch.float64, torch.float32):
@@ -291,20 +291,28 @@ def gmres(handle, A, B, X, precond=None, spmv_handle=None):
         raise B200SparseInvalidArgument("Invalid argument for 'ortho'.  Please use 'CGS2' or 'MGS'.")
     f64 = X.dtype == torch.float64
     lib = _lib.sparse()
-    fn = lib.b200sp_gmres_f64_i32 if f64 else lib.b200sp_gmres_f32_i32
     ha = spmv_handle if spmv_handle is not None else SPMVHandle(SPMV_DEFAULT)
     it, flag = C.c_int(0), C.c_int(0)
     res = C.c_double(0.0) if f64 else C.c_float(0.0)
     tol = C.c_double(gh.tol) if f64 else C.c_float(gh.tol)
+    null = C.c_void_p(0)
     if precond is not None:
         M = precond.A
-        if M.numRows() != n or M.numCols() != n or M.values.dtype != X.dtype:
-            raise B200SparseError("gmres: the MatrixPrec matrix must be n x n with A's scalar type")
-        pm, nnzm, rpm, cim, vm = precond._handle._plan, M.nnz(), _ptr(M.row_map), _ptr(M.entries), _ptr(M.values)
+        if isinstance(M, BsrMatrix) != is_bsr or M.values.dtype != X.dtype or (is_bsr and M.blockDim() != A.blockDim()) or \
+                M.numRows() != A.numRows() or M.numCols() != A.numCols():
+            raise B200SparseError("gmres: the MatrixPrec matrix must have A's type, size and scalar")
+        pm = precond._handle._bsr() if is_bsr else precond._handle._plan
+        nnzm, rpm, cim, vm = M.nnz(), _ptr(M.row_map), _ptr(M.entries), _ptr(M.values)
     else:
-        pm, nnzm, rpm, cim, vm = C.c_void_p(0), 0, C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
-    check(fn(ha._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm, _ptr(B), _ptr(X),
-             gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
+        pm, nnzm, rpm, cim, vm = null, 0, null, null, null
+    if is_bsr:
+        fn = lib.b200sp_gmres_bsr_f64_i32 if f64 else lib.b200sp_gmres_bsr_f32_i32
+        check(fn(ha._bsr(), _stream(), A.numRows(), A.nnz(), A.blockDim(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm,
+                 _ptr(B), _ptr(X), gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
+    else:
+        fn = lib.b200sp_gmres_f64_i32 if f64 else lib.b200sp_gmres_f32_i32
+        check(fn(ha._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm, _ptr(B), _ptr(X),
+                 gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
     gh.num_iters, gh.end_rel_res, gh.conv_flag_val = it.value, float(res.value), flag.value
     return gh
 

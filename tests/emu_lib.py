@@ -205,3 +205,17 @@ def gmres(plan_a, A, b, x, m=50, tol=1e-8, max_restart=50, ortho=0, prec=None, p
             ptr(pr[0]), ptr(pr[1]), ptr(pr[2]), ptr(b), ptr(x), m, scalar(v.dtype, tol), max_restart, ortho, C.byref(it), C.byref(res),
             C.byref(flag))
     return rc, it.value, res.value, flag.value
+
+
+def gmres_bsr(plan_a, bs, A, b, x, m=50, tol=1e-8, max_restart=50, ortho=0, prec=None, plan_m=None):
+    """b200sp_gmres_bsr_*: A (and prec) = (block row map, block columns, values); plans are BsrPlan."""
+    rp, ci, v = A
+    f64 = v.dtype == np.float64
+    fn = lib().b200sp_gmres_bsr_f64_i32 if f64 else lib().b200sp_gmres_bsr_f32_i32
+    it, flag = C.c_int(), C.c_int()
+    res = C.c_double() if f64 else C.c_float()
+    pr = prec if prec is not None else (None, None, None)
+    rc = fn(plan_a.h, None, len(rp) - 1, len(ci), bs, ptr(rp), ptr(ci), ptr(v), plan_m.h if plan_m else None, len(pr[1]) if prec is not None else 0,
+            ptr(pr[0]), ptr(pr[1]), ptr(pr[2]), ptr(b), ptr(x), m, scalar(v.dtype, tol), max_restart, ortho, C.byref(it), C.byref(res),
+            C.byref(flag))
+    return rc, it.value, res.value, flag.value

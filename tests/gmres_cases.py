@@ -29,3 +29,24 @@ def true_rel_res(oracle, A, b, x):
     y = np.zeros(len(b), dtype=np.float64)
     oracle.spmv_serial(rp, ci, v.astype(np.float64), x.astype(np.float64), y, 1.0, 0.0)
     return np.linalg.norm(b.astype(np.float64) - y) / np.linalg.norm(b.astype(np.float64))
+
+
+def crs_to_bsr(rp, ci, v, bs):
+    """BsrMatrix(const CrsMatrix&, blockDim) (sparse/src/KokkosSparse_BsrMatrix.hpp:520-610): the block structure of the point
+    matrix with explicit zeros where a block is only partly filled.  n must be a multiple of bs."""
+    n = len(rp) - 1
+    assert n % bs == 0
+    mb = n // bs
+    brp, bci, bv = [0], [], []
+    for br in range(mb):
+        cols = sorted({int(c) // bs for r in range(br * bs, br * bs + bs) for c in ci[rp[r]:rp[r + 1]]})
+        pos = {c: k for k, c in enumerate(cols)}
+        blk = np.zeros((len(cols), bs, bs), dtype=v.dtype)
+        for lr in range(bs):
+            r = br * bs + lr
+            for q in range(rp[r], rp[r + 1]):
+                blk[pos[int(ci[q]) // bs], lr, int(ci[q]) % bs] = v[q]
+        bci.extend(cols)
+        bv.append(blk.reshape(-1))
+        brp.append(len(bci))
+    return np.array(brp, np.int32), np.array(bci, np.int32), (np.concatenate(bv) if bv else np.zeros(0, v.dtype))

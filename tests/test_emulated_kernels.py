@@ -476,3 +476,25 @@ def test_gmres_corner_cases(emu, oracle):
     assert emu.b200sp_gmres_f64_i32(pa.h, None, n, len(A[1]), E.ptr(A[0]), E.ptr(A[1]), E.ptr(A[2]), None, 0, None, None, None, E.ptr(b), E.ptr(x), 10,
                                     1e-8, 50, 7, C.byref(C.c_int()), C.byref(C.c_double()), C.byref(C.c_int())) != 0  # ortho
     pa.close()
+
+
+@pytest.mark.parametrize("variant", ["cgs2", "matrixprec"])
+def test_gmres_bsr(emu, oracle, variant):
+    """The BsrMatrix half of the reference's GMRES test (Test_Sparse_gmres.hpp:86-101: the same matrix as 10 x 10 blocks)."""
+    from gmres_cases import crs_to_bsr, gmres_matrix, true_rel_res
+
+    n, m, bs, tol = 5000, 15, 10, 1e-8
+    A = gmres_matrix(n, 1.0)
+    Ab = crs_to_bsr(*A, bs)
+    b = np.ones(n)
+    prec = Ab if variant == "matrixprec" else None
+    pa, pm = E.BsrPlan(), (E.BsrPlan() if prec is not None else None)
+    x = np.zeros(n)
+    rc, it, res, flag = E.gmres_bsr(pa, bs, Ab, b, x, m=m, tol=tol, prec=prec, plan_m=pm)
+    pa.close()
+    if pm:
+        pm.close()
+    xo = np.zeros(n)
+    st_o, it_o, _, flag_o = oracle.gmres(A, b, xo, m=m, tol=tol, prec=A if prec is not None else None)
+    assert rc == 0 and flag == 0 == flag_o and abs(it - it_o) <= 1, (rc, it, it_o, flag)
+    assert true_rel_res(oracle, A, b, x) < tol and res < tol

@@ -6,19 +6,24 @@ import numpy as np
 import pytest
 import torch
 
-from gmres_cases import gmres_matrix, true_rel_res
+from gmres_cases import crs_to_bsr, gmres_matrix, true_rel_res
 
 # first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
 pytestmark = pytest.mark.gpu_next
 
 
+@pytest.mark.parametrize("use_blocks", [False, True])  # run_test_gmres<false> / <true> (:202-203): CrsMatrix, BsrMatrix of 10 x 10 blocks
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-5)])
-def test_gmres_reference_test(cuda, oracle, dtype, tol):
+def test_gmres_reference_test(cuda, oracle, dtype, tol, use_blocks):
     from kokkos_kernels_b200 import sparse as sp
 
     n, m = 5000, 15
     A = gmres_matrix(n, 1.0, dtype=dtype)
-    Ad = sp.CrsMatrix(torch.from_numpy(A[0]).to(cuda), torch.from_numpy(A[1]).to(cuda), torch.from_numpy(A[2]).to(cuda), n)
+    if use_blocks:
+        brp, bci, bv = crs_to_bsr(*A, 10)
+        Ad = sp.BsrMatrix(torch.from_numpy(brp).to(cuda), torch.from_numpy(bci).to(cuda), torch.from_numpy(bv).to(cuda), n // 10, 10)
+    else:
+        Ad = sp.CrsMatrix(torch.from_numpy(A[0]).to(cuda), torch.from_numpy(A[1]).to(cuda), torch.from_numpy(A[2]).to(cuda), n)
     b = np.ones(n, dtype=dtype)
     Bd = torch.from_numpy(b).to(cuda)
     kh = sp.KokkosKernelsHandle()
