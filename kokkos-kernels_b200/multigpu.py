@@ -118,3 +118,52 @@ class RowBlockSpMV:
     def local_spmv_only(self, x):
         for A, h, yv, dsts, arr, ev in self.pieces:
             sp.spmv(h, "N", 1.0, A, x, 0.0, yv)
+
+
+class RowBlockSpGEMM:
+    """C = A * B with the rows of A (hence of C) sharded over the ranks and B replicated ("SpGEMM also
+    shards by row blocks of A with B replicated; rowptr needs one exchange of P counts").  Every rank runs the single-GPU
+    spgemm_symbolic / spgemm_numeric of the library on its row block -- the rows of C are independent, so the block is
+    bit-identical to the same rows of the single-GPU product -- and ONE all_gather of the P block sizes gives each rank the
+    offset of its block in the global C (no collective on the data path).  No reference counterpart (single-process library).
+
+        op = RowBlockSpGEMM(A_local, B, group=None)   # A_local: rows [r0, r1) of A, row map rebased, global columns
+        C_local = op.symbolic()                       # structure of this rank's rows; op.block_nnz / op.offset are known
+        op.numeric()                                  # values; re-runnable with new values on the same structure
+        op.global_row_map()                           # int64: C_local.row_map + op.offset (global nnz may exceed int32)
+    """
+
+    def __init__(self, A_local, B, group=None):
+        if A_local.numCols() != B.numRows():
+            raise sp.B200SparseError(f"RowBlockSpGEMM: inner dimensions differ: {A_local.numCols()} vs {B.numRows()}")
+        self.A, self.B, self.group = A_local, B, group
+        self.kh = sp.KokkosKernelsHandle()
+        self.kh.create_spgemm_handle(sp.SPGEMM_KK)
+        self.C = None
+        self.block_nnz = None  # nnz of every rank's block of C
+        self.offset = None     # where this rank's block starts in the global entries / values of C
+
+    def symbolic(self):
+        self.C = sp.spgemm_symbolic(self.kh, self.A, False, self.B, False)
+        mine = int(self.kh.get_spgemm_handle().get_c_nnz())
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.group)
+            counts = [None] * world
+            dist.all_gather_object(counts, mine, group=self.group)
+            rank = dist.get_rank(self.group)
+        else:
+            counts, rank = [mine], 0
+        self.block_nnz = [int(c) for c in counts]
+        self.offset = int(sum(self.block_nnz[:rank]))
+        return self.C
+
+    def numeric(self, A_values=None, B_values=None):
+        if self.C is None:
+            raise sp.B200SparseInvalidArgument("RowBlockSpGEMM.numeric: call symbolic first")
+        A = self.A if A_values is None else sp.CrsMatrix(self.A.row_map, self.A.entries, A_values, self.A.numCols())
+        B = self.B if B_values is None else sp.CrsMatrix(self.B.row_map, self.B.entries, B_values, self.B.numCols())
+        sp.spgemm_numeric(self.kh, A, False, B, False, self.C)
+        return self.C
+
+    def global_row_map(self):
+        return self.C.row_map.to(torch.int64) + self.offset

@@ -102,3 +102,58 @@ def test_piece_bounds_alignment():
     rp = np.arange(0, 3 * 101, 3)
     b = partition.piece_bounds(rp, 4)
     assert all(rp[r] % 4 == 0 for r in b[1:-1]) and b[-1] == 100
+
+
+def _spgemm_worker(rank, world, port, q):
+    """Row-block SpGEMM on 2 ranks: the device kernels run under the CPU emulation (tests/conftest.py::_emulated_device), the
+    collective over gloo."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import conftest
+    import oracle_lib
+    from helpers import kk_matrix
+
+    dev = conftest._emulated_device()
+    from kokkos_kernels_b200 import multigpu, partition, sparse as sp
+
+    orc = oracle_lib.Oracle()
+    m, k, n = 900, 700, 1100
+    A = kk_matrix(m, k, 9000, 10, 200, lo=1.0, hi=50.0, seed=1, sort=True, oracle=orc)
+    B = kk_matrix(k, n, 9000, 10, 200, lo=1.0, hi=50.0, seed=2, sort=True, oracle=orc)
+    bounds = partition.balanced_row_blocks(A[0], world)
+    rp, ci, va = partition.extract_shard(*A, bounds[rank], bounds[rank + 1])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    op = multigpu.RowBlockSpGEMM(sp.CrsMatrix(t(rp), t(ci), t(va), k), sp.CrsMatrix(t(B[0]), t(B[1]), t(B[2]), n))
+    C = op.symbolic()
+    op.numeric()
+    out = [None] * world
+    dist.all_gather_object(out, (op.offset, op.block_nnz, op.global_row_map().numpy(), C.entries.numpy().copy(), C.values.numpy().copy()))
+    if rank == 0:
+        q.put((bounds, out))
+    dist.destroy_process_group()
+
+
+def test_row_block_spgemm_matches_single_process(oracle):
+    from helpers import kk_matrix
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spgemm_worker, args=(r, 2, 29533, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    bounds, out = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m, k, n = 900, 700, 1100
+    A = kk_matrix(m, k, 9000, 10, 200, lo=1.0, hi=50.0, seed=1, sort=True, oracle=oracle)
+    B = kk_matrix(k, n, 9000, 10, 200, lo=1.0, hi=50.0, seed=2, sort=True, oracle=oracle)
+    rpC, ciC, vC = oracle.spgemm(*A, *B, n)
+    row_map = np.concatenate([o[2][:-1] for o in out] + [out[-1][2][-1:]])
+    assert np.array_equal(row_map, rpC.astype(np.int64))  # block row maps + offsets = the global row map
+    assert np.array_equal(np.concatenate([o[3] for o in out]), ciC)
+    assert oracle.rel_mismatch(np.concatenate([o[4] for o in out]), vC, 1e-7) == 0
+    assert out[0][1] == out[1][1] and out[0][0] == 0 and out[1][0] == out[0][1][0] == int(rpC[bounds[1]])
