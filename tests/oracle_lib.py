@@ -74,6 +74,14 @@ class Oracle:
             R.kkref_spgemm_symbolic.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]
             R.kkref_spgemm_symbolic.restype = i64
             R.kkref_spgemm_numeric_f64.argtypes = [i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]
+            if hasattr(R, "kkref_spadd_sorted_numeric_f64"):
+                R.kkref_spadd_sorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp]
+                R.kkref_spadd_unsorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp, vp, vp]
+            if hasattr(R, "kkref_spgemm_jacobi_f64"):
+                R.kkref_spgemm_jacobi_f64.argtypes = [i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, f64, vp]
+            if hasattr(R, "kkref_radix_sort2_u32_f64"):
+                R.kkref_radix_sort2_u32_f64.argtypes = [vp, vp, vp, vp, i32]
+                R.kkref_radix_sort2_u32_i32.argtypes = [vp, vp, vp, vp, i32]
             if hasattr(R, "kkref_bsr_spmv_v42_f64"):
                 R.kkref_bsr_spmv_v42_f64.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f64, f64]
                 R.kkref_bsr_spmv_v42_f32.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f32, f32]
@@ -278,6 +286,44 @@ class Oracle:
         st = getattr(self.lib, "okk_gmres_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(pr[0]), _p(pr[1]), _p(pr[2]), _p(b), _p(x), m, tol,
                                                            max_restart, ortho, C.byref(it), C.byref(res), C.byref(flag))
         return st, it.value, res.value, flag.value
+
+    def ref_spadd_numeric(self, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, sorted_input):
+        """The reference's own SortedNumericSumFunctor / UnsortedNumericSumFunctor (oracle/_ref) on the structure (and a_pos / b_pos)
+        of the restated symbolic phase; returns (rowmapC, entriesC, valuesC)."""
+        assert self.ref is not None and vA.dtype == np.float64
+        m = len(rpA) - 1
+        rpC = np.zeros(m + 1, dtype=np.int32)
+        if sorted_input:
+            nnz = self.lib.okk_spadd_sorted_symbolic(m, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC))
+            ciC, vC = np.empty(nnz, dtype=np.int32), np.empty(nnz)
+            self.ref.kkref_spadd_sorted_numeric_f64(m, _p(rpA), _p(ciA), _p(vA), alpha, _p(rpB), _p(ciB), _p(vB), beta, _p(rpC), _p(ciC), _p(vC))
+            return rpC, ciC, vC
+        apos = np.zeros(max(len(ciA), 1), dtype=np.int32)
+        bpos = np.zeros(max(len(ciB), 1), dtype=np.int32)
+        nnz = self.lib.okk_spadd_unsorted_symbolic(m, _p(rpA), _p(ciA), _p(rpB), _p(ciB), _p(rpC), _p(apos), _p(bpos))
+        ciC, vC = np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        self.ref.kkref_spadd_unsorted_numeric_f64(m, _p(rpA), _p(ciA), _p(vA), alpha, _p(rpB), _p(ciB), _p(vB), beta, _p(rpC), _p(ciC), _p(vC),
+                                                  _p(apos), _p(bpos))
+        return rpC, ciC, vC
+
+    def ref_spgemm_jacobi(self, rpA, ciA, vA, rpB, ciB, vB, k, omega, dinv):
+        """The reference's own spgemm_symbolic (debug) + spgemm_jacobi_seq (oracle/_ref), UNSORTED output (first-touch order)."""
+        assert self.ref is not None
+        m, n = len(rpA) - 1, len(rpB) - 1
+        rpC = np.full(m + 1, 123, dtype=np.int32)
+        nnz = self.ref.kkref_spgemm_symbolic(m, n, k, _p(rpA), len(ciA), _p(ciA), _p(rpB), len(ciB), _p(ciB), _p(rpC))
+        ciC = np.empty(nnz, dtype=np.int32)
+        vC = np.empty(nnz, dtype=np.float64)
+        self.ref.kkref_spgemm_jacobi_f64(m, n, k, _p(rpA), len(ciA), _p(ciA), _p(vA), _p(rpB), len(ciB), _p(ciB), _p(vB), _p(rpC), nnz, _p(ciC),
+                                         _p(vC), omega, _p(dinv))
+        return rpC, ciC, vC
+
+    def ref_radix_sort2(self, keys, perm):
+        """The reference's own SerialRadixSort2 (oracle/_ref): sorts uint32 keys in place, perm (f64 or i32) follows."""
+        assert self.ref is not None and keys.dtype == np.uint32
+        ka, pa = np.empty_like(keys), np.empty_like(perm)
+        fn = self.ref.kkref_radix_sort2_u32_f64 if perm.dtype == np.float64 else self.ref.kkref_radix_sort2_u32_i32
+        fn(_p(keys), _p(ka), _p(perm), _p(pa), len(keys))
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)

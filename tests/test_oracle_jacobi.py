@@ -40,3 +40,18 @@ def test_jacobi_matches_dense(oracle, n, per, dtype, tol):
     assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want))
     for i in range(n):
         assert np.all(np.diff(ciC[rpC[i]:rpC[i + 1]]) > 0)
+
+
+@pytest.mark.parametrize("n,per", [(60, 4), (500, 9), (3000, 7)])
+def test_jacobi_restatement_equals_reference_seq(oracle, n, per):
+    """The restatement equals the reference's own spgemm_jacobi_seq -- sparse/impl/KokkosSparse_spgemm_jacobi_seq_impl.hpp
+    compiled from the reference tree in place (oracle/_ref) -- bit for bit: entries in first-touch order, values."""
+    if oracle.ref is None or not hasattr(oracle.ref, "kkref_spgemm_jacobi_f64"):
+        pytest.skip("oracle/_ref not built")
+    rp, ci, v = diag_dominant(n, per, n + 1)
+    rng = np.random.default_rng(n)
+    vB = rng.uniform(-1, 1, len(ci))
+    dinv = rng.uniform(0.5, 1.5, n)
+    got = oracle.spgemm_jacobi(rp, ci, v, rp, ci, vB, n, 0.7, dinv, sort=False)
+    ref = oracle.ref_spgemm_jacobi(rp, ci, v, rp, ci, vB, n, 0.7, dinv)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
