@@ -7,13 +7,15 @@
  * loads or calls anything in oracle/.
  *
  * Every function restates, operation for operation, a loop of the reference
- * (paths relative to /root/reference).  The reference itself cannot be built
- * here (needs Kokkos >= 4.6.02, CMakeLists.txt:150-157; only Kokkos 3.3 is on
- * disk); parity is pinned by the reference's own known-answer tests (issue
- * 101, NaN/beta==0, merge-matrix diagonal tables, issue-402 fixture) in
- * tests/test_oracle_*.py, and the SpGEMM restatement is additionally checked
- * against the reference's real spgemm_impl_seq.hpp compiled over a tiny View
- * mock (oracle/_ref, see oracle/Makefile).
+ * (paths relative to /root/reference).  The reference as a whole cannot be
+ * built here (needs Kokkos >= 4.6.02, CMakeLists.txt:150-157; only Kokkos 3.3
+ * is on disk); parity is pinned (a) by the reference's own known-answer tests
+ * (issue 101, NaN/beta==0, merge-matrix diagonal tables, issue-402 fixture) in
+ * tests/test_oracle_*.py and (b) bit for bit by the reference's own code for
+ * this path -- spmv_impl.hpp (Serial loop, generic functor, transpose,
+ * multivector), spgemm_impl_seq.hpp, spgemm_jacobi_seq_impl.hpp -- compiled
+ * from the reference tree where it lies over small stand-ins for the Kokkos
+ * names it mentions (oracle/_ref, oracle/kkref_*.cpp, oracle/Makefile).
  *
  * Build flags: -O2 -ffp-contract=off (no FMA contraction, no fast-math) so
  * the rounding sequence is exactly the one the C expressions spell out.  A

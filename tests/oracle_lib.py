@@ -74,6 +74,14 @@ class Oracle:
             R.kkref_spgemm_symbolic.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]
             R.kkref_spgemm_symbolic.restype = i64
             R.kkref_spgemm_numeric_f64.argtypes = [i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]
+            if hasattr(R, "kkref_spmv_serial_f64"):
+                for nm, ft in (("f64", f64), ("f32", f32)):
+                    getattr(R, "kkref_spmv_serial_" + nm).argtypes = [i32, vp, vp, vp, vp, vp, ft, ft]
+                    getattr(R, "kkref_spmv_functor_" + nm).argtypes = [i32, vp, vp, vp, vp, vp, ft, ft]
+                    if hasattr(R, "kkref_spmv_mv_" + nm):
+                        getattr(R, "kkref_spmv_mv_" + nm).argtypes = [C.c_char, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
+                    if hasattr(R, "kkref_spmv_transpose_" + nm):
+                        getattr(R, "kkref_spmv_transpose_" + nm).argtypes = [i32, i32, vp, vp, vp, vp, vp, ft, ft]
             if hasattr(R, "kkref_spadd_sorted_numeric_f64"):
                 R.kkref_spadd_sorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp]
                 R.kkref_spadd_unsorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp, vp, vp]
@@ -286,6 +294,26 @@ class Oracle:
         st = getattr(self.lib, "okk_gmres_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(pr[0]), _p(pr[1]), _p(pr[2]), _p(b), _p(x), m, tol,
                                                            max_restart, ortho, C.byref(it), C.byref(res), C.byref(flag))
         return st, it.value, res.value, flag.value
+
+    def ref_spmv(self, which, rp, ci, v, x, y, alpha, beta):
+        """The reference's own host SpMV (oracle/_ref): which = "serial" (the hand-unrolled Kokkos::Serial loop) or "functor"
+        (SPMV_Functor through a RangePolicy, every other host execution space); y updated in place."""
+        assert self.ref is not None
+        if which == "transpose":  # y has ncols entries
+            getattr(self.ref, "kkref_spmv_transpose_" + self._sfx(v))(len(rp) - 1, len(y), _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+            return y
+        getattr(self.ref, f"kkref_spmv_{which}_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        return y
+
+    def ref_spmv_mv(self, mode, rp, ci, v, ncol, X, Y, alpha, beta):
+        """The reference's own host multivector SpMV (spmv_alpha_mv and below, oracle/_ref), RangePolicy functors run in row
+        order; Y updated in place."""
+        assert self.ref is not None
+        xr, xc = self._strides(X)
+        yr, yc = self._strides(Y)
+        getattr(self.ref, "kkref_spmv_mv_" + self._sfx(v))(mode.encode(), len(rp) - 1, ncol, X.shape[1], _p(rp), _p(ci), _p(v), _p(X), xr, xc,
+                                                          _p(Y), yr, yc, alpha, beta)
+        return Y
 
     def ref_spadd_numeric(self, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, sorted_input):
         """The reference's own SortedNumericSumFunctor / UnsortedNumericSumFunctor (oracle/_ref) on the structure (and a_pos / b_pos)
