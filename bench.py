@@ -138,12 +138,25 @@ def build_shard(world, rank, grid=GRID):
     return rp, ci, va, n_total, r0, r1
 
 
+def _cpu_spmv(orc):
+    """The CPU implementation both timing legs run, all host threads: the reference's OWN host SpMV when oracle/_ref holds it
+    (SPMV_Functor of sparse/impl/KokkosSparse_spmv_impl.hpp compiled from the reference tree in place, driven by an OpenMP
+    RangePolicy stand-in: kind "reference"), else the oracle's restatement of that loop (kind "port").  Both produce the same
+    bits (tests/test_oracle_spmv.py)."""
+    if orc.has_ref_spmv_omp():
+        return (lambda rp, ci, va, ncols, x, y, threads: orc.ref_spmv_functor_omp(rp, ci, va, x, y, 1.0, 0.0, threads)), "reference", \
+            "the reference's own SPMV_Functor (spmv_impl.hpp:86-132 compiled in place, oracle/_ref) under an OpenMP RangePolicy"
+    return (lambda rp, ci, va, ncols, x, y, threads: orc.spmv_functor(rp, ci, va, ncols, x, y, 1.0, 0.0, threads)), "port", \
+        "oracle O2 (OpenMP functor order, spmv_impl.hpp:110-132)"
+
+
 def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
-    """Oracle O2 (OpenMP functor order, the reference's host path) on the first `rows` rows of the
-    same matrix with the full x: a bounded sample of the workload.  Returns (gflops, dict)."""
+    """The reference's host SpMV (see _cpu_spmv) on the first `rows` rows of the same matrix with the full x: a bounded sample
+    of the workload.  Returns (gflops, dict)."""
     import oracle_lib
 
     orc = oracle_lib.Oracle()
+    run, kind, what = _cpu_spmv(orc)
     rows = min(rows, len(rp) - 1)
     rps = np.ascontiguousarray(rp[: rows + 1])
     nnz = int(rps[-1])
@@ -151,27 +164,27 @@ def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
     rps, cis, vas, x = (orc.first_touch_copy(a, threads) for a in (rps, ci[:nnz], va[:nnz], x))
     y = orc.first_touch_copy(np.zeros(rows), threads)
     ncols = len(x)
-    orc.spmv_functor(rps, cis, vas, ncols, x, y, 1.0, 0.0, threads)  # warm-up / first touch
+    run(rps, cis, vas, ncols, x, y, threads)  # warm-up / first touch
     t0 = time.perf_counter()
-    orc.spmv_functor(rps, cis, vas, ncols, x, y, 1.0, 0.0, threads)
+    run(rps, cis, vas, ncols, x, y, threads)
     one = time.perf_counter() - t0
     iters = int(max(3, min(200, seconds_budget / max(one, 1e-4))))
     ts = []
     for _ in range(iters):
         t0 = time.perf_counter()
-        orc.spmv_functor(rps, cis, vas, ncols, x, y, 1.0, 0.0, threads)
+        run(rps, cis, vas, ncols, x, y, threads)
         ts.append(time.perf_counter() - t0)
     mean = float(np.mean(ts))
     gf = 2.0 * nnz / mean / 1e9
-    return gf, {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port",
-                "sample": f"oracle O2 (OpenMP functor order, spmv_impl.hpp:110-132), first {rows} rows of the same "
+    return gf, {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
+                "sample": f"{what}, first {rows} rows of the same "
                           f"matrix ({nnz} nnz), full x, {iters} iterations, mean {mean * 1e3:.2f} ms, "
                           f"min {min(ts) * 1e3:.2f} ms; {alg_bytes(nnz, rows, ncols) / mean / 1e9:.1f} GB/s algorithmic"}
 
 
 def run_reference(args, emit):
-    """--impl reference: the reference's own CPU implementation of the path (its OpenMP functor loop,
-    restated in oracle/kk_oracle.c -- the reference cannot be built here without Kokkos >= 4.6.02),
+    """--impl reference: the reference's own CPU implementation of the path -- its host SPMV_Functor compiled from the reference
+    tree in place (oracle/_ref; falls back to the oracle's restatement of the same loop when that library is absent) --
     all host threads, on a bounded sample of the workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,6 +193,7 @@ def run_reference(args, emit):
     from kokkos_kernels_b200 import matgen
 
     orc = oracle_lib.Oracle()
+    run, kind, what = _cpu_spmv(orc)
     threads = orc.num_threads()
     rows = 1_250_000
     nz = max(3, (rows // (GRID * GRID * NDOF)) + 2)
@@ -191,10 +205,10 @@ def run_reference(args, emit):
     # pages first touched by the threads that will stream them (parallel initialisation, reference protocol)
     rp, ci, va, x, y = (orc.first_touch_copy(a, threads) for a in (rp, ci, va, x, y))
     for _ in range(max(args.warmup, 1)):
-        orc.spmv_functor(rp, ci, va, ncols, x, y, 1.0, 0.0, threads)
+        run(rp, ci, va, ncols, x, y, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.spmv_functor(rp, ci, va, ncols, x, y, 1.0, 0.0, threads)
+        run(rp, ci, va, ncols, x, y, threads)
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
     gf = 2.0 * nnz / (ms * 1e-3) / 1e9
     out = {
@@ -203,8 +217,8 @@ def run_reference(args, emit):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"spmv fp64 CrsMatrix lap27({GRID}^3)x{NDOF}dof family, bounded sample: first {rows} rows "
                                f"({nnz} nnz) per step, alpha=1 beta=0"},
-        "cpu_baseline": {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle O2 OpenMP, {rows} rows x {nnz} nnz per step"},
+        "cpu_baseline": {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
+                         "sample": f"{what}, {rows} rows x {nnz} nnz per step"},
         "e2e": {"value": round(gf, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

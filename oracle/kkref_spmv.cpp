@@ -55,8 +55,8 @@ struct Crs {
     return KokkosSparse::SparseRowViewConst<Crs>{values.p + b, graph.entries.p + b, graph.row_map(i + 1) - b};
   }
 };
-struct Handle {
-  bool force_dynamic_schedule = false, force_static_schedule = true;
+struct Handle {  // SPMVHandleImpl's scheduling switches (sparse/src/KokkosSparse_spmv_handle.hpp:306-307): both false by default
+  bool force_dynamic_schedule = false, force_static_schedule = false;
 };
 struct NotSerial {  // an execution space that is not Kokkos::Serial: takes the generic (functor) path
   int concurrency() const { return 2; }
@@ -138,6 +138,13 @@ __attribute__((visibility("default"))) void kkref_spmv_serial_f32(int nrows, con
 __attribute__((visibility("default"))) void kkref_spmv_functor_f64(int nrows, const int* rm, const int* ci, const double* v,
                                                                     const double* x, double* y, double alpha, double beta) {
   run<NotSerial, double>(nrows, rm, ci, v, x, y, alpha, beta);
+}
+// the same functor path on `threads` OpenMP threads (bench.py's CPU legs): rows are independent, so the result is the serial one
+__attribute__((visibility("default"))) void kkref_spmv_functor_omp_f64(int threads, int nrows, const int* rm, const int* ci, const double* v,
+                                                                        const double* x, double* y, double alpha, double beta) {
+  Kokkos::kkmock_threads() = threads > 1 ? threads : 1;
+  run<NotSerial, double>(nrows, rm, ci, v, x, y, alpha, beta);
+  Kokkos::kkmock_threads() = 1;
 }
 __attribute__((visibility("default"))) void kkref_spmv_functor_f32(int nrows, const int* rm, const int* ci, const float* v, const float* x,
                                                                     float* y, float alpha, float beta) {

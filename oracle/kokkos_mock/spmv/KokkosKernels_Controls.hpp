@@ -57,10 +57,34 @@ struct TeamPolicy {
   template <class F, class Tag>
   int team_size_max(const F&, Tag) const { return 1; }
 };
-// the one parallel_for that runs: a RangePolicy over rows, in order
+// the one parallel_for that runs: a RangePolicy over rows -- in order on one thread, or (kkmock_threads() > 1, the timing legs of
+// bench.py) with OpenMP the way Kokkos::OpenMP schedules a RangePolicy: static blocks, or dynamic chunks for Schedule<Dynamic>
+inline int& kkmock_threads() {
+  static int t = 1;
+  return t;
+}
+template <class... Props>
+struct is_dynamic : std::false_type {};
+template <class First, class... Rest>
+struct is_dynamic<First, Rest...> : std::integral_constant<bool, std::is_same<First, Schedule<Dynamic>>::value || is_dynamic<Rest...>::value> {};
 template <class... Props, class Functor>
 inline void parallel_for(const std::string&, const RangePolicy<Props...>& p, const Functor& f) {
+  const int threads = kkmock_threads();
+  if (threads <= 1) {
+    for (int64_t i = p.begin; i < p.end; ++i) f(static_cast<int>(i));
+    return;
+  }
+#ifdef _OPENMP
+  if (is_dynamic<Props...>::value) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t i = p.begin; i < p.end; ++i) f(static_cast<int>(i));
+  } else {
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int64_t i = p.begin; i < p.end; ++i) f(static_cast<int>(i));
+  }
+#else
   for (int64_t i = p.begin; i < p.end; ++i) f(static_cast<int>(i));
+#endif
 }
 template <class... Props, class Functor>
 inline void parallel_for(const std::string&, const TeamPolicy<Props...>&, const Functor&) {

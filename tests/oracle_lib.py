@@ -82,6 +82,8 @@ class Oracle:
                         getattr(R, "kkref_spmv_mv_" + nm).argtypes = [C.c_char, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, ft, ft]
                     if hasattr(R, "kkref_spmv_transpose_" + nm):
                         getattr(R, "kkref_spmv_transpose_" + nm).argtypes = [i32, i32, vp, vp, vp, vp, vp, ft, ft]
+            if hasattr(R, "kkref_spmv_functor_omp_f64"):
+                R.kkref_spmv_functor_omp_f64.argtypes = [i32, i32, vp, vp, vp, vp, vp, f64, f64]
             if hasattr(R, "kkref_spadd_sorted_numeric_f64"):
                 R.kkref_spadd_sorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp]
                 R.kkref_spadd_unsorted_numeric_f64.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp, f64, vp, vp, vp, vp, vp]
@@ -303,6 +305,14 @@ class Oracle:
             getattr(self.ref, "kkref_spmv_transpose_" + self._sfx(v))(len(rp) - 1, len(y), _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
             return y
         getattr(self.ref, f"kkref_spmv_{which}_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
+        return y
+
+    def has_ref_spmv_omp(self):
+        return self.ref is not None and hasattr(self.ref, "kkref_spmv_functor_omp_f64")
+
+    def ref_spmv_functor_omp(self, rp, ci, v, x, y, alpha, beta, threads):
+        """The reference's own SPMV_Functor (oracle/_ref) under an OpenMP RangePolicy stand-in: bench.py's CPU legs."""
+        self.ref.kkref_spmv_functor_omp_f64(threads, len(rp) - 1, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta)
         return y
 
     def ref_spmv_mv(self, mode, rp, ci, v, ncol, X, Y, alpha, beta):
