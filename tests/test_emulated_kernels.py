@@ -404,7 +404,7 @@ def test_multi_gpu_kernels_single_process(emu, oracle):
     assert L.b200sp_multicast_push(None, E.ptr(src_all[0:4]), E.ptr(y[1:]), 24, 1) != 0  # different 16-byte phase: refused
 
 
-@pytest.mark.parametrize("pieces", [None, "1", "3", "8"])
+@pytest.mark.parametrize("pieces", [None, "3"])
 def test_hostvec_pipeline_logic(emu, oracle, pieces):
     """b200sp_spmv_hostvec_* (host x / y, double-buffered upload, piecewise compute + download): the piece arithmetic for
     every piece count, incl. the B200SP_HOSTVEC_PIECES override; streams and copies are synchronous under the emulation."""

@@ -201,7 +201,7 @@ def test_o5_equals_the_reference_transpose_code(oracle, rows, cols, per):
 
 
 @pytest.mark.parametrize("order", ["F", "C"])
-@pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 17, 22, 33])
+@pytest.mark.parametrize("k", [1, 3, 16, 17, 33])
 def test_o4_equals_the_reference_multivector_code(oracle, order, k):
     """O4 (CPU multivector strips, alpha folded per term when alpha is not 0 / +-1, dobeta = -1 as -y + sum) and the multivector
     transpose against the reference's own spmv_alpha_mv compiled in place (sparse/impl/KokkosSparse_spmv_impl.hpp:547-1270),
