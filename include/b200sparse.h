@@ -317,6 +317,39 @@ int b200sp_bsr_spmm_f32_i32(b200sp_bsr_plan* plan, void* stream, char mode, int 
 /* Name of the kernel the plan's last call used; static storage (tests / bench). */
 const char* b200sp_bsr_last_kernel(const b200sp_bsr_plan* plan);
 
+/* ---- point Gauss-Seidel (the preconditioner of the reference's CG driver) ---------------------
+ * gauss_seidel_symbolic / gauss_seidel_numeric / {symmetric_,forward_sweep_,backward_sweep_}gauss_seidel_apply for the point
+ * (multicolour) algorithm (sparse/src/KokkosSparse_gauss_seidel.hpp:49-1100 -> PointGaussSeidel,
+ * sparse/impl/KokkosSparse_gauss_seidel_impl.hpp; GS_DEFAULT of every execution space).  symbolic colours the graph of the
+ * n x n matrix (is_graph_symmetric = 0: on pattern(A) + pattern(A^T)) and builds the row list of every colour set -- the
+ * matrix is NOT permuted or copied; numeric extracts 1 / a_ii (B200SP_ERR_INVALID_ARGUMENT when a row has no or a zero
+ * diagonal); apply runs `sweeps` sweeps over the colour sets: direction 0 = symmetric (forward then backward), 1 = forward,
+ * 2 = backward; per row  sum = y_i - sum_j a_ij x_j,  x_i += omega * sum / a_ii  (PSGS::operator(), impl.hpp:159-179);
+ * init_zero_x != 0 zeroes x first.  The plan is the GaussSeidelHandle's device state; B200SP_ERR_STATE when a phase is
+ * called before its predecessor.  symbolic / numeric synchronise; apply is asynchronous on `stream`. */
+typedef struct b200sp_gs_plan b200sp_gs_plan;
+int b200sp_gs_plan_create(b200sp_gs_plan** plan);
+int b200sp_gs_plan_destroy(b200sp_gs_plan* plan, void* stream);
+int b200sp_gs_symbolic_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                           int is_graph_symmetric);
+int b200sp_gs_numeric_f64_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                              const double* vals);
+int b200sp_gs_numeric_f32_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                              const float* vals);
+int b200sp_gs_apply_f64_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                            const double* vals, double* x, const double* y, int init_zero_x, double omega, int sweeps,
+                            int direction);
+int b200sp_gs_apply_f32_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                            const float* vals, float* x, const float* y, int init_zero_x, float omega, int sweeps,
+                            int direction);
+/* The colouring symbolic produced (device pointers owned by the plan): colour of every row, and the rows of colour c at
+ * color_rows[color_ptr[c] .. color_ptr[c+1]), ascending. */
+int b200sp_gs_get_coloring(const b200sp_gs_plan* plan, int* num_colors, const int** colors, const int** color_ptr,
+                           const int** color_rows);
+/* The same copied to host arrays of n, num_colors + 1 and n entries (NULL: skipped); synchronises `stream`. */
+int b200sp_gs_copy_coloring(const b200sp_gs_plan* plan, void* stream, int* colors_host, int* color_ptr_host,
+                            int* color_rows_host);
+
 /* ---- CG driver (callers of spmv in a loop) ---------------------------------------------------
  * KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false (perf_test/sparse/KokkosSparse_pcg.hpp:248-466;
  * the driver perf_test/sparse/KokkosSparse_pcg.cpp:69-122 calls it with tolerance 1e-7): solves A x = b for a symmetric
@@ -329,6 +362,14 @@ int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t
                             const int* col_idx, const double* vals, const double* b, double* x,
                             int maximum_iteration, double tolerance, int check_every, int* iterations,
                             double* norm_res);
+
+/* pcgsolve with use_sgs = true (its default; pcg.hpp:339-358,412-437): the same loop with z = M^-1 r by one symmetric point
+ * Gauss-Seidel sweep (zero initial guess, omega = 1) over the colour sets of gs_plan -- b200sp_gs_symbolic / _numeric must have
+ * run on this matrix -- alpha = r.z / p.Ap, beta = r.z' / r.z, p = z + beta p; the stopping test stays sqrt(r.r). */
+int b200sp_pcg_solve_f64_i32(b200sp_spmv_plan* plan, b200sp_gs_plan* gs_plan, void* stream, int n, int64_t nnz,
+                             const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
+                             int maximum_iteration, double tolerance, int check_every, int* iterations,
+                             double* norm_res);
 
 /* ---- GMRES -----------------------------------------------------------------------------------
  * KokkosSparse::Experimental::gmres(handle, A, B, X, precond) (sparse/src/KokkosSparse_gmres.hpp:60-160 ->

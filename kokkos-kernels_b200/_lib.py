@@ -69,6 +69,16 @@ SPARSE_API = {
     "b200sp_gmres_f32_i32": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]),
     "b200sp_gmres_bsr_f64_i32": (i32, [vp, vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]),
     "b200sp_gmres_bsr_f32_i32": (i32, [vp, vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]),
+    "b200sp_gs_plan_create": (i32, [C.POINTER(vp)]),
+    "b200sp_gs_plan_destroy": (i32, [vp, vp]),
+    "b200sp_gs_symbolic_i32": (i32, [vp, vp, i32, vp, vp, i32]),
+    "b200sp_gs_numeric_f64_i32": (i32, [vp, vp, i32, vp, vp, vp]),
+    "b200sp_gs_numeric_f32_i32": (i32, [vp, vp, i32, vp, vp, vp]),
+    "b200sp_gs_apply_f64_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, f64, i32, i32]),
+    "b200sp_gs_apply_f32_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, i32, i32]),
+    "b200sp_gs_copy_coloring": (i32, [vp, vp, vp, vp, vp]),
+    "b200sp_gs_get_coloring": (i32, [vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b200sp_pcg_solve_f64_i32": (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, i32, f64, i32, C.POINTER(i32), C.POINTER(f64)]),
     "b200sp_cg_solve_f64_i32": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, vp, i32, f64, i32, C.POINTER(i32), C.POINTER(f64)]),
     "b200sp_launch_count": (i64, []),
     "b200sp_spmv_last_kernel": (C.c_char_p, [vp]),

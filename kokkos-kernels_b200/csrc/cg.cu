@@ -23,6 +23,7 @@ namespace b200sp {
 namespace {
 
 struct CgState {       // device-resident scalars of the recurrence
+  double precond_old;  // r.z of the previous iteration (preconditioned runs)
   double old_rdot;     // r.r of the previous iteration
   double pAp;          // p.Ap
   double beta;         // r.r / old_rdot
@@ -103,9 +104,9 @@ __global__ void __launch_bounds__(kCgThreads) cg_dot_kernel(int n, const double*
 // x += alpha p; r -= alpha Ap; r_dot = r.r; then the scalar part of the iteration
 __global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ Ap,
                                                                double* __restrict__ x, double* __restrict__ r, double* __restrict__ slots,
-                                                               CgState* __restrict__ st) {
+                                                               CgState* __restrict__ st, int pcg) {
   if (((volatile CgState*)st)->done) return;
-  const double alpha = st->old_rdot / st->pAp;
+  const double alpha = (pcg ? st->precond_old : st->old_rdot) / st->pAp;  // pcg.hpp:387-391
   double part = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] = alpha * p[i] + 1.0 * x[i];
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const doub
   }
   double total;
   if (cg_grid_sum(cg_block_sum(part), slots, st, &total)) {
-    st->beta = total / st->old_rdot;
+    if (!pcg) st->beta = total / st->old_rdot;  // preconditioned: beta comes from r.z (cg_rz_kernel)
     st->old_rdot = total;
     st->norm_res = sqrt(total);
     st->iteration += 1;
@@ -123,12 +124,26 @@ __global__ void __launch_bounds__(kCgThreads) cg_update_kernel(int n, const doub
   }
 }
 
-// p = r + beta p
+// p = r + beta p   (preconditioned: p = z + beta p; the caller passes z for r)
 __global__ void __launch_bounds__(kCgThreads) cg_p_kernel(int n, const double* __restrict__ r, double* __restrict__ p, CgState* __restrict__ st) {
   if (((volatile CgState*)st)->done) return;
   const double beta = st->beta;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = 1.0 * r[i] + beta * p[i];
+}
+
+// preconditioned runs: rz = r.z; setup (init != 0): precond_old = rz; in the loop: beta = rz / precond_old, precond_old = rz
+// (pcg.hpp:361,428-429,449)
+__global__ void __launch_bounds__(kCgThreads) cg_rz_kernel(int n, const double* __restrict__ r, const double* __restrict__ z,
+                                                           double* __restrict__ slots, CgState* __restrict__ st, int init) {
+  if (((volatile CgState*)st)->done && !init) return;
+  double part = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) part += r[i] * z[i];
+  double total;
+  if (cg_grid_sum(cg_block_sum(part), slots, st, &total)) {
+    if (!init) st->beta = total / st->precond_old;
+    st->precond_old = total;
+  }
 }
 
 // The loop condition of the reference (:372), evaluated once per iteration AFTER the p update.  A kernel of its own: the blocks of
@@ -143,12 +158,17 @@ __global__ void cg_flag_kernel(CgState* __restrict__ st, double tolerance, int m
 
 using namespace b200sp;
 
+struct b200sp_gs_plan;
 extern "C" int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, int n, int64_t nnz, double alpha,
                                    const int* row_ptr, const int* col_idx, const double* vals, const double* x, double beta, double* y);
+extern "C" int b200sp_gs_apply_f64_i32(b200sp_gs_plan* p, void* stream, int n, const int* row_ptr, const int* col_idx, const double* vals,
+                                       double* x, const double* y, int init_zero_x, double omega, int sweeps, int direction);
 
-extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
-                                       const double* vals, const double* b, double* x, int maximum_iteration, double tolerance,
-                                       int check_every, int* iterations, double* norm_res) {
+// gs != nullptr: symmetric Gauss-Seidel preconditioner, z = SGS(r) with zero initial guess, omega = 1, one sweep
+// (pcgsolve's use_sgs = true, perf_test/sparse/KokkosSparse_pcg.hpp:339-358,412-427)
+static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                    const double* vals, const double* b, double* x, int maximum_iteration, double tolerance, int check_every, int* iterations,
+                    double* norm_res) {
   B200SP_REQUIRE(plan != nullptr, "cg_solve: null plan (create one with b200sp_spmv_plan_create)");
   B200SP_REQUIRE(n >= 0 && nnz >= 0 && maximum_iteration >= 0, "cg_solve: negative size");
   B200SP_REQUIRE(iterations != nullptr && norm_res != nullptr, "cg_solve: null result pointer");
@@ -158,13 +178,15 @@ extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int
   *iterations = 0;
   *norm_res = 0.0;
   if (n == 0) return B200SP_OK;
+  const int pcg = gs != nullptr;
   DevTmp tmp(st);
-  double *p = nullptr, *r = nullptr, *Ap = nullptr, *slots = nullptr;
+  double *p = nullptr, *r = nullptr, *Ap = nullptr, *z = nullptr, *slots = nullptr;
   CgState* state = nullptr;
   const int grid = std::max(1, std::min((n + kCgThreads - 1) / kCgThreads, sm_count() * 4));
   B200SP_CUDA_TRY(tmp.alloc(&p, (size_t)n));
   B200SP_CUDA_TRY(tmp.alloc(&r, (size_t)n));
   B200SP_CUDA_TRY(tmp.alloc(&Ap, (size_t)n));
+  if (pcg) B200SP_CUDA_TRY(tmp.alloc(&z, (size_t)n));
   B200SP_CUDA_TRY(tmp.alloc(&slots, (size_t)grid));
   B200SP_CUDA_TRY(tmp.alloc(&state, 1));
   B200SP_CUDA_TRY(cudaMemsetAsync(state, 0, sizeof(CgState), st));
@@ -180,6 +202,13 @@ extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int
   if (rc != B200SP_OK) return rc;
   cg_init_kernel<<<grid, kCgThreads, 0, st>>>(n, b, Ap, r, p, slots, state, tolerance, maximum_iteration);
   B200SP_LAUNCH_CHECK();
+  if (pcg) {  // z = M^-1 r; precond_old_rdot = r.z; p = z
+    rc = b200sp_gs_apply_f64_i32(gs, stream, n, row_ptr, col_idx, vals, z, r, 1, 1.0, 1, 0);
+    if (rc != B200SP_OK) return rc;
+    cg_rz_kernel<<<grid, kCgThreads, 0, st>>>(n, r, z, slots, state, 1);
+    B200SP_LAUNCH_CHECK();
+    B200SP_CUDA_TRY(cudaMemcpyAsync(p, z, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  }
 
   int issued = 0;
   for (;;) {
@@ -188,14 +217,21 @@ extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int
     if (host_state->done || issued >= maximum_iteration) break;
     const int batch = std::min(check_every, maximum_iteration - issued);
     for (int k = 0; k < batch; ++k) {
-      // iterations issued past convergence are no-ops except for their SpMV (it cannot see the flag): at most check_every - 1
+      // iterations issued past convergence are no-ops except for their SpMV / Gauss-Seidel sweeps (they cannot see the flag):
+      // at most check_every - 1 of them
       rc = b200sp_spmv_f64_i32(plan, stream, 'N', n, n, nnz, 1.0, row_ptr, col_idx, vals, p, 0.0, Ap);
       if (rc != B200SP_OK) return rc;
       cg_dot_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, slots, state);
       B200SP_LAUNCH_CHECK();
-      cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state);
+      cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state, pcg);
       B200SP_LAUNCH_CHECK();
-      cg_p_kernel<<<grid, kCgThreads, 0, st>>>(n, r, p, state);
+      if (pcg) {
+        rc = b200sp_gs_apply_f64_i32(gs, stream, n, row_ptr, col_idx, vals, z, r, 1, 1.0, 1, 0);
+        if (rc != B200SP_OK) return rc;
+        cg_rz_kernel<<<grid, kCgThreads, 0, st>>>(n, r, z, slots, state, 0);
+        B200SP_LAUNCH_CHECK();
+      }
+      cg_p_kernel<<<grid, kCgThreads, 0, st>>>(n, pcg ? z : r, p, state);
       B200SP_LAUNCH_CHECK();
       cg_flag_kernel<<<1, 1, 0, st>>>(state, tolerance, maximum_iteration);
       B200SP_LAUNCH_CHECK();
@@ -205,4 +241,17 @@ extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int
   *iterations = host_state->iteration;
   *norm_res = host_state->norm_res;
   return B200SP_OK;
+}
+
+extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+                                       const double* vals, const double* b, double* x, int maximum_iteration, double tolerance,
+                                       int check_every, int* iterations, double* norm_res) {
+  return cg_solve(plan, nullptr, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
+}
+
+extern "C" int b200sp_pcg_solve_f64_i32(b200sp_spmv_plan* plan, b200sp_gs_plan* gs_plan, void* stream, int n, int64_t nnz,
+                                        const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
+                                        int maximum_iteration, double tolerance, int check_every, int* iterations, double* norm_res) {
+  B200SP_REQUIRE(gs_plan != nullptr, "pcg_solve: null Gauss-Seidel plan (symbolic and numeric must have run on this matrix)");
+  return cg_solve(plan, gs_plan, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
 }

@@ -317,6 +317,92 @@ def gmres(handle, A, B, X, precond=None, spmv_handle=None):
     return gh
 
 
+class GaussSeidelHandle:
+    """The point Gauss-Seidel handle (sparse/src/KokkosSparse_gauss_seidel_handle.hpp:37-330; GS_DEFAULT): owns the colouring and
+    the inverse diagonal (b200sp_gs_plan)."""
+
+    def __init__(self):
+        self._plan = C.c_void_p(0)
+        check(_lib.sparse().b200sp_gs_plan_create(C.byref(self._plan)))
+        self._symbolic = self._numeric = False
+
+    def is_symbolic_called(self): return self._symbolic
+    def is_numeric_called(self): return self._numeric
+
+    def get_num_colors(self):
+        nc = C.c_int(0)
+        check(_lib.sparse().b200sp_gs_get_coloring(self._plan, C.byref(nc), None, None, None))
+        return nc.value
+
+    def get_coloring(self, n):
+        """(colors[n], color_ptr[num_colors + 1], color_rows[n]) as host numpy arrays."""
+        import numpy as np
+
+        nc = self.get_num_colors()
+        colors, cptr, crows = np.zeros(n, np.int32), np.zeros(nc + 1, np.int32), np.zeros(n, np.int32)
+        check(_lib.sparse().b200sp_gs_copy_coloring(self._plan, _stream(), C.c_void_p(colors.ctypes.data), C.c_void_p(cptr.ctypes.data),
+                                                    C.c_void_p(crows.ctypes.data)))
+        return colors, cptr, crows
+
+    def __del__(self):
+        try:
+            if self._plan:
+                st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
+                _lib.sparse().b200sp_gs_plan_destroy(self._plan, st)
+                self._plan = C.c_void_p(0)
+        except Exception:
+            pass
+
+
+def _gs_handle(handle):
+    gh = handle.get_gs_handle() if hasattr(handle, "get_gs_handle") else handle
+    if gh is None:
+        raise B200SparseInvalidArgument("Gauss-Seidel handle has not been created (create_gs_handle)")
+    return gh
+
+
+def gauss_seidel_symbolic(handle, num_rows, num_cols, row_map, entries, is_graph_symmetric=True):
+    """KokkosSparse::gauss_seidel_symbolic (sparse/src/KokkosSparse_gauss_seidel.hpp:49-110)."""
+    if num_rows != num_cols:
+        raise B200SparseError("b200sparse: point Gauss-Seidel needs a square matrix")
+    gh = _gs_handle(handle)
+    check(_lib.sparse().b200sp_gs_symbolic_i32(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), int(bool(is_graph_symmetric))))
+    gh._symbolic, gh._numeric = True, False
+
+
+def gauss_seidel_numeric(handle, num_rows, num_cols, row_map, entries, values, is_graph_symmetric=True):
+    """KokkosSparse::gauss_seidel_numeric (:223-290); is_graph_symmetric only matters to symbolic."""
+    gh = _gs_handle(handle)
+    fn = _lib.sparse().b200sp_gs_numeric_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_numeric_f32_i32
+    check(fn(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), _ptr(values)))
+    gh._numeric = True
+
+
+def _gs_apply(handle, num_rows, row_map, entries, values, x_lhs, y_rhs, init_zero_x_vector, omega, numIter, direction):
+    gh = _gs_handle(handle)
+    if values.dtype != x_lhs.dtype or x_lhs.dtype != y_rhs.dtype or x_lhs.dim() != 1 or y_rhs.dim() != 1:
+        raise B200SparseError("b200sparse: gauss_seidel_apply needs rank-1 x, y of the matrix' scalar type")
+    fn = _lib.sparse().b200sp_gs_apply_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_apply_f32_i32
+    check(fn(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), _ptr(values), _ptr(x_lhs), _ptr(y_rhs), int(bool(init_zero_x_vector)),
+             omega, int(numIter), direction))
+
+
+def symmetric_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
+                                 init_zero_x_vector, update_y_vector, omega, numIter):
+    """KokkosSparse::symmetric_gauss_seidel_apply (:363-470); update_y_vector is moot (y is never permuted or copied here)."""
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 0)
+
+
+def forward_sweep_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
+                                     init_zero_x_vector, update_y_vector, omega, numIter):
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 1)
+
+
+def backward_sweep_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
+                                      init_zero_x_vector, update_y_vector, omega, numIter):
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 2)
+
+
 class CGSolveResult:
     """perf_test/sparse/KokkosSparse_pcg.hpp:38-45 (the fields this driver fills)."""
 
@@ -324,11 +410,14 @@ class CGSolveResult:
         self.iteration, self.norm_res = iteration, norm_res
 
 
-def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.220446049250313e-16, check_every=0):
+def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.220446049250313e-16, check_every=0, use_sgs=False,
+             gs_handle=None):
     """KokkosKernels::Experimental::Example::pcgsolve(kh, crsMat, y_vector, x_vector, maximum_iteration, tolerance, &result,
-    use_sgs = false) (perf_test/sparse/KokkosSparse_pcg.hpp:248-466): unpreconditioned CG for a symmetric positive definite
-    CrsMatrix; x_vector is the initial guess and receives the solution.  `handle` is the SPMVHandle of A (None: a
-    throw-away one).  The loop runs on the device (b200sp_cg_solve_f64_i32); double only, like the reference driver."""
+    use_sgs) (perf_test/sparse/KokkosSparse_pcg.hpp:248-466): CG for a symmetric positive definite CrsMatrix, unpreconditioned or
+    (use_sgs, the reference's default) preconditioned by one symmetric point Gauss-Seidel sweep; x_vector is the initial guess and
+    receives the solution.  `handle` is the SPMVHandle of A (None: a throw-away one); gs_handle a GaussSeidelHandle whose symbolic /
+    numeric already ran on A (None with use_sgs: created here, as the reference's driver does, :296-337).  The loop runs on the
+    device (b200sp_cg_solve_f64_i32 / b200sp_pcg_solve_f64_i32); double only, like the reference driver."""
     n = A.numRows()
     if A.numCols() != n or y_vector.shape[0] != n or x_vector.shape[0] != n or y_vector.dim() != 1 or x_vector.dim() != 1:
         raise B200SparseError("pcgsolve: A must be square and x, b rank-1 vectors of its size")
@@ -336,6 +425,16 @@ def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.2
         raise B200SparseError("pcgsolve: The PCG performance test only works with scalar = double.")  # pcg.hpp:258-259
     h = handle if handle is not None else SPMVHandle(SPMV_DEFAULT)
     it, nr = C.c_int(0), C.c_double(0.0)
+    if use_sgs:
+        gh = gs_handle
+        if gh is None:
+            gh = GaussSeidelHandle()
+            gauss_seidel_symbolic(gh, n, n, A.row_map, A.entries, True)  # SPD: the pattern is symmetric
+            gauss_seidel_numeric(gh, n, n, A.row_map, A.entries, A.values, True)
+        check(_lib.sparse().b200sp_pcg_solve_f64_i32(h._plan, gh._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+                                                     _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
+                                                     int(check_every), C.byref(it), C.byref(nr)))
+        return CGSolveResult(it.value, nr.value)
     check(_lib.sparse().b200sp_cg_solve_f64_i32(h._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
                                                 _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
                                                 int(check_every), C.byref(it), C.byref(nr)))
@@ -431,6 +530,18 @@ class KokkosKernelsHandle:
 
     def destroy_spadd_handle(self):
         self._ah = None
+
+    def create_gs_handle(self, *args, **kwargs):  # GS_DEFAULT; algorithm / colouring arguments of the reference are accepted and ignored
+        self._gs = GaussSeidelHandle()
+
+    def get_gs_handle(self):
+        return getattr(self, "_gs", None)
+
+    def get_point_gs_handle(self):
+        return getattr(self, "_gs", None)
+
+    def destroy_gs_handle(self):
+        self._gs = None
 
     def create_gmres_handle(self, m=50, tol=1e-8, max_restart=50):  # KokkosKernels_Handle.hpp (create_gmres_handle)
         self._gmres = GMRESHandle(m, tol, max_restart)

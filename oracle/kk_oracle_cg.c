@@ -35,9 +35,29 @@ static double cg_dot(int n, const double* a, const double* b) {
   return s;
 }
 
+void okk_gs_apply_f64(int n, const int* rm, const int* ci, const double* v, int ncolors, const int* color_ptr, const int* color_rows,
+                      const double* dinv, const double* y, double* x, int init_zero_x, double omega, int sweeps, int direction);
+
+/* use_sgs = true (pcg.hpp:339-358,412-437): z = one symmetric point Gauss-Seidel sweep on r from z = 0, omega = 1, over the
+ * given colour sets (kk_oracle_gs.c); alpha = r.z / p.Ap; beta = r.z' / r.z; p = z + beta p.  ncolors = 0: no preconditioner. */
+static int cg_core(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x, int maximum_iteration,
+                   double tolerance, double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv);
+
 /* returns the iteration count; *norm_res_out = sqrt(r.r) of the recurrence residual */
 OKK_API int okk_cg_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x,
                        int maximum_iteration, double tolerance, double* norm_res_out) {
+  return cg_core(n, row_map, col_idx, values, b, x, maximum_iteration, tolerance, norm_res_out, 0, 0, 0, 0);
+}
+OKK_API int okk_pcg_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x,
+                        int maximum_iteration, double tolerance, double* norm_res_out, int ncolors, const int* color_ptr,
+                        const int* color_rows, const double* dinv) {
+  return cg_core(n, row_map, col_idx, values, b, x, maximum_iteration, tolerance, norm_res_out, ncolors, color_ptr, color_rows, dinv);
+}
+static int cg_core(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x, int maximum_iteration,
+                   double tolerance, double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv) {
+  const int use_sgs = ncolors > 0;
+  double* z = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+  double precond_old_rdot = 1;
   double* p = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
   double* r = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
   double* Ap = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
@@ -47,22 +67,36 @@ OKK_API int okk_cg_f64(int n, const int* row_map, const int* col_idx, const doub
   for (int i = 0; i < n; ++i) p[i] = r[i];
   double old_rdot = cg_dot(n, r, r);
   double norm_res = sqrt(old_rdot);
+  if (use_sgs) {
+    okk_gs_apply_f64(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z, 1, 1.0, 1, 0);
+    precond_old_rdot = cg_dot(n, r, z);
+    for (int i = 0; i < n; ++i) p[i] = z[i];
+  }
   int iteration = 0;
   while (tolerance < norm_res && iteration < maximum_iteration) {
     cg_spmv(n, row_map, col_idx, values, p, Ap);
     const double pAp_dot = cg_dot(n, p, Ap);
-    const double alpha = old_rdot / pAp_dot;
+    const double alpha = (use_sgs ? precond_old_rdot : old_rdot) / pAp_dot;
     for (int i = 0; i < n; ++i) x[i] = alpha * p[i] + 1.0 * x[i];
     for (int i = 0; i < n; ++i) r[i] = -alpha * Ap[i] + 1.0 * r[i];
     const double r_dot = cg_dot(n, r, r);
-    const double beta = r_dot / old_rdot;
-    for (int i = 0; i < n; ++i) p[i] = 1.0 * r[i] + beta * p[i];
+    double beta = r_dot / old_rdot;
+    if (use_sgs) {
+      okk_gs_apply_f64(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z, 1, 1.0, 1, 0);
+      const double precond_r_dot = cg_dot(n, r, z);
+      beta = precond_r_dot / precond_old_rdot;
+      for (int i = 0; i < n; ++i) p[i] = 1.0 * z[i] + beta * p[i];
+      precond_old_rdot = precond_r_dot;
+    } else {
+      for (int i = 0; i < n; ++i) p[i] = 1.0 * r[i] + beta * p[i];
+    }
     norm_res = sqrt(old_rdot = r_dot);
     ++iteration;
   }
   free(p);
   free(r);
   free(Ap);
+  free(z);
   *norm_res_out = norm_res;
   return iteration;
 }

@@ -219,3 +219,39 @@ def gmres_bsr(plan_a, bs, A, b, x, m=50, tol=1e-8, max_restart=50, ortho=0, prec
             ptr(pr[0]), ptr(pr[1]), ptr(pr[2]), ptr(b), ptr(x), m, scalar(v.dtype, tol), max_restart, ortho, C.byref(it), C.byref(res),
             C.byref(flag))
     return rc, it.value, res.value, flag.value
+
+
+class GsPlan:
+    def __init__(self):
+        self.h = C.c_void_p()
+        ok(lib().b200sp_gs_plan_create(C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            ok(lib().b200sp_gs_plan_destroy(self.h, None))
+            self.h = C.c_void_p()
+
+    def symbolic(self, n, rp, ci, symmetric):
+        ok(lib().b200sp_gs_symbolic_i32(self.h, None, n, ptr(rp), ptr(ci), int(symmetric)))
+
+    def numeric(self, n, rp, ci, v):
+        return getattr(lib(), "b200sp_gs_numeric_%s_i32" % sfx(v.dtype))(self.h, None, n, ptr(rp), ptr(ci), ptr(v))
+
+    def apply(self, n, rp, ci, v, x, y, init_zero_x, omega, sweeps, direction):
+        return getattr(lib(), "b200sp_gs_apply_%s_i32" % sfx(v.dtype))(self.h, None, n, ptr(rp), ptr(ci), ptr(v), ptr(x), ptr(y), int(init_zero_x),
+                                                                       scalar(v.dtype, omega), sweeps, direction)
+
+    def coloring(self, n):
+        """(num_colors, colors[n], color_ptr[nc+1], color_rows[n]) copied out of the plan ("device" memory is host memory here)."""
+        nc = C.c_int()
+        pc, pp, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ok(lib().b200sp_gs_get_coloring(self.h, C.byref(nc), C.byref(pc), C.byref(pp), C.byref(pr)))
+        arr = lambda p, cnt: np.ctypeslib.as_array((C.c_int * cnt).from_address(p.value)).copy() if cnt else np.zeros(0, np.int32)
+        return nc.value, arr(pc, n), arr(pp, nc.value + 1), arr(pr, n)
+
+
+def pcg_solve(plan, gs_plan, rp, ci, v, b, x, maximum_iteration, tolerance, check_every=0):
+    it, nr = C.c_int(), C.c_double()
+    ok(lib().b200sp_pcg_solve_f64_i32(plan.h, gs_plan.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), ptr(b), ptr(x), maximum_iteration,
+                                      C.c_double(tolerance), check_every, C.byref(it), C.byref(nr)))
+    return it.value, nr.value

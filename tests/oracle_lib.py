@@ -65,8 +65,12 @@ class Oracle:
             getattr(L, f"okk_bsr_to_crs_{sfx}").argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         L.okk_gmres_f64.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
         L.okk_gmres_f32.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
+        L.okk_gs_apply_f64.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f64, i32, i32]
+        L.okk_gs_apply_f32.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, i32, i32]
         L.okk_cg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64)]
         L.okk_cg_f64.restype = i32
+        L.okk_pcg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64), i32, vp, vp, vp]
+        L.okk_pcg_f64.restype = i32
         self.ref = None
         rpath = os.path.join(ODIR, "_ref", "libkkref.so")
         if os.path.exists(rpath):
@@ -280,6 +284,12 @@ class Oracle:
         getattr(self.lib, "okk_bsr_to_crs_" + self._sfx(v))(mb, bs, _p(rp), _p(ci), _p(v), _p(crp), _p(cci), _p(cv))
         return crp, cci, cv
 
+    def gs_apply(self, rp, ci, v, color_ptr, color_rows, dinv, y, x, init_zero_x, omega, sweeps, direction):
+        """Point Gauss-Seidel sweeps over the given colour sets (direction 0 symmetric, 1 forward, 2 backward); x in place."""
+        getattr(self.lib, "okk_gs_apply_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), len(color_ptr) - 1, _p(color_ptr), _p(color_rows),
+                                                         _p(dinv), _p(y), _p(x), int(init_zero_x), omega, sweeps, direction)
+        return x
+
     def cg(self, rp, ci, v, b, x, maximum_iteration, tolerance):
         """pcgsolve(use_sgs=false); x updated in place; returns (iterations, norm_res)."""
         nr = f64()
@@ -362,6 +372,13 @@ class Oracle:
         ka, pa = np.empty_like(keys), np.empty_like(perm)
         fn = self.ref.kkref_radix_sort2_u32_f64 if perm.dtype == np.float64 else self.ref.kkref_radix_sort2_u32_i32
         fn(_p(keys), _p(ka), _p(perm), _p(pa), len(keys))
+
+    def pcg(self, rp, ci, v, b, x, maximum_iteration, tolerance, color_ptr, color_rows, dinv):
+        """pcgsolve(use_sgs=true) over the given colour sets; returns (iterations, norm_res)."""
+        nr = f64()
+        it = self.lib.okk_pcg_f64(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), maximum_iteration, tolerance, C.byref(nr), len(color_ptr) - 1,
+                                  _p(color_ptr), _p(color_rows), _p(dinv))
+        return it, nr.value
 
     def rel_mismatch(self, a, b, eps):
         return self.lib.okk_count_rel_mismatch_f64(len(a), _p(a), _p(b), eps)

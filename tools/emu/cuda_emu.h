@@ -236,6 +236,8 @@ static inline int __syncthreads_or(int pred) {
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; b200emu::note_progress(); return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; b200emu::note_progress(); return o; }
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; b200emu::note_progress(); return o; }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; b200emu::note_progress(); return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; b200emu::note_progress(); return o; }
 static inline int atomicCAS(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; b200emu::note_progress(); return o; }
