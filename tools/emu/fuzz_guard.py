@@ -264,7 +264,47 @@ def op_bsr(rng, orc, verbose):
     return ok, f"bsr {mode} {np.dtype(dtype).name} bs={bs} {mb}x{nb} nnzb={len(ci)} k={k} {kern}"
 
 
-OPS = {"spmv": op_spmv, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
+def op_gs(rng, orc, verbose):
+    """Point Gauss-Seidel: colouring (symmetric or not), inverse diagonal, sweeps in every direction against the oracle over the
+    library's own colour sets."""
+    dtype = [np.float64, np.float32][rng.integers(0, 2)]
+    n = int(rng.integers(1, 1500))
+    rp, ci, v = rand_csr(rng, n, n, np.float64, sort=True, distinct=True, long_rows=bool(rng.random() < 0.3))
+    # put a dominant diagonal into every row (merge it into the sorted row)
+    rows = []
+    for i in range(n):
+        c = set(ci[rp[i]:rp[i + 1]].tolist()) | {i}
+        rows.append(np.array(sorted(c), dtype=np.int32))
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    ci = np.concatenate(rows).astype(np.int32)
+    rid = np.repeat(np.arange(n), np.diff(rp))
+    v = rng.uniform(-1, 1, len(ci))
+    v[rid == ci] = np.bincount(rid, weights=np.abs(v), minlength=n) + 1.0
+    v = v.astype(dtype)
+    grp, gci, gv = g(rp, rng), g(ci, rng), g(v, rng)
+    plan = E.GsPlan()
+    plan.symbolic(n, grp, gci, False)
+    nc, colors, cptr, crows = plan.coloring(n)
+    ok = not np.any((colors[rid] == colors[ci]) & (rid != ci)) and cptr[-1] == n and np.array_equal(np.sort(crows), np.arange(n))
+    # symmetrised check: colours of (j, i) for every (i, j) differ as well
+    ok &= E.lib().b200sp_gs_numeric_f64_i32(plan.h, None, n, E.ptr(grp), E.ptr(gci), E.ptr(gv)) == 0 if dtype == np.float64 else plan.numeric(n, grp, gci, gv) == 0
+    y = rng.uniform(-1, 1, n).astype(dtype)
+    gy = g(y, rng)
+    direction, sweeps = int(rng.integers(0, 3)), int(rng.integers(1, 4))
+    omega = [1.0, 0.9, 1.3][rng.integers(0, 3)]
+    x = E.guarded(rng.uniform(-1, 1, n).astype(dtype))
+    x0 = x.copy()
+    init_zero = bool(rng.integers(0, 2))
+    ok &= plan.apply(n, grp, gci, gv, x, gy, init_zero, omega, sweeps, direction) == 0
+    plan.close()
+    dinv = (1.0 / v[rid == ci].astype(np.float64)).astype(dtype)
+    xo = orc.gs_apply(rp, ci, v, cptr, crows, dinv, y, x0.copy(), init_zero, dtype(omega), sweeps, direction)
+    tol = 1e-11 if dtype == np.float64 else 5e-5
+    ok &= bool(np.max(np.abs(x.astype(np.float64) - xo.astype(np.float64)), initial=0.0) <= tol * max(1.0, float(np.max(np.abs(xo), initial=0.0))))
+    return ok, f"gs {np.dtype(dtype).name} n={n} nnz={len(ci)} colors={nc} dir={direction} sweeps={sweeps}"
+
+
+OPS = {"gs": op_gs, "spmv": op_spmv, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
 
 
 def main():
