@@ -240,6 +240,24 @@ struct SPGEMMHandleMock {
 
 struct b200sp_spadd_plan;
 extern "C" int b200sp_spadd_plan_destroy(b200sp_spadd_plan*, void*);
+struct b200sp_gs_plan;
+extern "C" int b200sp_gs_plan_destroy(b200sp_gs_plan*, void*);
+
+namespace KokkosSparse {
+enum class SparseMatrixFormat { BSR, CRS };  // sparse/src/KokkosSparse_Utils.hpp
+// the PointGaussSeidelHandle members the shim touches (+ the b200_gs_plan member INTEGRATION.md adds)
+struct PointGaussSeidelHandleMock {
+  ~PointGaussSeidelHandleMock() {
+    if (b200_gs_plan) b200sp_gs_plan_destroy(b200_gs_plan, nullptr);
+  }
+  bool is_symbolic_called() const { return called_symbolic; }
+  bool is_numeric_called() const { return called_numeric; }
+  void set_call_symbolic(bool c = true) { called_symbolic = c; }
+  void set_call_numeric(bool c = true) { called_numeric = c; }
+  b200sp_gs_plan* b200_gs_plan = nullptr;
+  bool called_symbolic = false, called_numeric = false;
+};
+}  // namespace KokkosSparse
 
 namespace KokkosSparse {
 // the SPADDHandle members the shim touches (+ the b200Data member INTEGRATION.md adds)
@@ -282,6 +300,14 @@ struct KokkosKernelsHandle {
     sh = nullptr;
   }
   SPGEMMHandleType* sh = nullptr;
+  using const_nnz_lno_t = const int;
+  KokkosSparse::PointGaussSeidelHandleMock* get_point_gs_handle() { return gsh; }
+  void create_gs_handle() { gsh = new KokkosSparse::PointGaussSeidelHandleMock(); }
+  void destroy_gs_handle() {
+    delete gsh;
+    gsh = nullptr;
+  }
+  KokkosSparse::PointGaussSeidelHandleMock* gsh = nullptr;
   using SPADDHandleType = KokkosSparse::SPADDHandleMock;
   SPADDHandleType* get_spadd_handle() { return ah; }
   void create_spadd_handle(bool input_sorted = false, bool input_merged = false) { ah = new SPADDHandleType(input_sorted, input_merged); }
@@ -304,6 +330,27 @@ template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class
 struct spgemm_numeric_tpl_spec_avail {
   enum : bool { value = false };
 };
+// sparse/tpls/KokkosSparse_gauss_seidel_tpl_spec_avail.hpp and sparse/impl/KokkosSparse_gauss_seidel_spec.hpp:105-151
+template <class KH, class a_r, class a_e>
+struct gauss_seidel_symbolic_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class a_r, class a_e, class a_v>
+struct gauss_seidel_numeric_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class a_r, class a_e, class a_v, class x_v, class y_v>
+struct gauss_seidel_apply_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class Exec, class KH, class a_r, class a_e, bool tpl = gauss_seidel_symbolic_tpl_spec_avail<KH, a_r, a_e>::value, bool eti = true>
+struct GAUSS_SEIDEL_SYMBOLIC;
+template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a_r, class a_e, class a_v,
+          bool tpl = gauss_seidel_numeric_tpl_spec_avail<KH, a_r, a_e, a_v>::value, bool eti = true>
+struct GAUSS_SEIDEL_NUMERIC;
+template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a_r, class a_e, class a_v, class x_v, class y_v,
+          bool tpl = gauss_seidel_apply_tpl_spec_avail<KH, a_r, a_e, a_v, x_v, y_v>::value, bool eti = true>
+struct GAUSS_SEIDEL_APPLY;
 // sparse/tpls/KokkosSparse_spgemm_jacobi_tpl_spec_avail.hpp:24-31, sparse/impl/KokkosSparse_spgemm_jacobi_spec.hpp:83-107
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v>
 struct spgemm_jacobi_tpl_spec_avail {

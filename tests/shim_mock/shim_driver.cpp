@@ -11,6 +11,8 @@
 #include "KokkosSparse_spadd_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spgemm_jacobi_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spgemm_jacobi_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_gauss_seidel_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_gauss_seidel_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_decl.hpp"
 
@@ -40,6 +42,11 @@ static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::va
 static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
 using DINV  = Kokkos::View<const double**, KokkosKernels::default_layout, Dev, UM>;
 static_assert(Impl::spgemm_jacobi_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, IV, IV, SV, DINV>::value, "spgemm_jacobi must be available");
+using XGS   = Kokkos::View<double**, KokkosKernels::default_layout, Dev, UM>;
+using YGS   = Kokkos::View<const double**, KokkosKernels::default_layout, Dev, UM>;
+static_assert(Impl::gauss_seidel_symbolic_tpl_spec_avail<KH, CIV, CIV>::value && Impl::gauss_seidel_numeric_tpl_spec_avail<KH, CIV, CIV, CSV>::value &&
+                  Impl::gauss_seidel_apply_tpl_spec_avail<KH, CIV, CIV, CSV, XGS, YGS>::value,
+              "Gauss-Seidel symbolic / numeric / apply must be available");
 using BMat  = Experimental::BsrMatrix<const double, const int, Dev, UM, const int>;
 static_assert(Impl::spmv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XVec, YVec>::value, "BsrMatrix rank-1 must be available");
 static_assert(Impl::spmv_mv_bsrmatrix_tpl_spec_avail<Kokkos::Cuda, Hnd, BMat, XMV, YMV>::value, "BsrMatrix rank-2 must be available");
@@ -58,10 +65,11 @@ T* to_dev(const std::vector<T>& h) {
 
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
-  bool with_bsr = false, with_jacobi = false;  // --jacobi: likewise for spgemm_jacobi
+  bool with_bsr = false, with_jacobi = false, with_gs = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
   for (int a = 1; a < argc; ++a) {
     with_bsr |= std::string(argv[a]) == "--bsr";
     with_jacobi |= std::string(argv[a]) == "--jacobi";
+    with_gs |= std::string(argv[a]) == "--gs";
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -250,6 +258,46 @@ int main(int argc, char** argv) {
     cudaFree(d_rpC);
     cudaFree(d_ciC);
     cudaFree(d_vC);
+  }
+  if (with_gs) {
+    // Gauss-Seidel through GAUSS_SEIDEL_SYMBOLIC / NUMERIC / APPLY<Kokkos::Cuda, ..., true, true>: the tridiagonal-ish matrix made
+    // diagonally dominant, two columns of right-hand sides, 12 symmetric sweeps from x = 0 must reach the solution
+    std::vector<double> vd(va);
+    for (int i = 0; i < n; ++i)
+      for (int q = rp[i]; q < rp[i + 1]; ++q)
+        if (ci[q] == i) vd[q] = 4.0;
+    double* d_vd = to_dev(vd);
+    const int k = 2;
+    std::vector<double> xs(n * k), yy(n * k, 0.0), x0(n * k, 7.0);
+    for (int j = 0; j < k; ++j)
+      for (int i = 0; i < n; ++i) xs[j * n + i] = std::sin(0.01 * i + j);
+    for (int j = 0; j < k; ++j)
+      for (int i = 0; i < n; ++i)
+        for (int q = rp[i]; q < rp[i + 1]; ++q) yy[j * n + i] += vd[q] * xs[j * n + ci[q]];
+    double *d_xg = to_dev(x0), *d_yg = to_dev(yy);
+    KH kh;
+    kh.create_gs_handle();
+    CIV vrp(d_rp, n + 1), vci(d_ci, ci.size());
+    CSV vvd(d_vd, vd.size());
+    using GSS = Impl::GAUSS_SEIDEL_SYMBOLIC<Kokkos::Cuda, KH, CIV, CIV, true, true>;
+    using GSN = Impl::GAUSS_SEIDEL_NUMERIC<Kokkos::Cuda, KH, SparseMatrixFormat::CRS, CIV, CIV, CSV, true, true>;
+    using GSA = Impl::GAUSS_SEIDEL_APPLY<Kokkos::Cuda, KH, SparseMatrixFormat::CRS, CIV, CIV, CSV, XGS, YGS, true, true>;
+    GSS::gauss_seidel_symbolic(exec, &kh, n, n, vrp, vci, true);
+    GSN::gauss_seidel_numeric(exec, &kh, n, n, vrp, vci, vvd, true);
+    GSA::gauss_seidel_apply(exec, &kh, n, n, vrp, vci, vvd, XGS(d_xg, n, k), YGS(d_yg, n, k), true, true, 1.0, 12, true, true);
+    exec.fence();
+    std::vector<double> xg(n * k);
+    cudaMemcpy(xg.data(), d_xg, sizeof(double) * n * k, cudaMemcpyDeviceToHost);
+    int f8 = 0;
+    for (int i = 0; i < n * k; ++i)
+      if (std::fabs(xg[i] - xs[i]) > 1e-6) ++f8;
+    if (!kh.get_point_gs_handle()->is_symbolic_called() || !kh.get_point_gs_handle()->is_numeric_called()) ++f8;
+    std::printf("Gauss-Seidel through GAUSS_SEIDEL_SYMBOLIC/NUMERIC/APPLY<...,true,true> : %d mismatches\n", f8);
+    failures += f8;
+    kh.destroy_gs_handle();
+    cudaFree(d_vd);
+    cudaFree(d_xg);
+    cudaFree(d_yg);
   }
   if (with_bsr) {
     // BsrMatrix: block-tridiagonal, 3 x 3 blocks, through SPMV_BSRMATRIX<...,true,true> (N) and
