@@ -242,6 +242,65 @@ struct b200sp_spadd_plan;
 extern "C" int b200sp_spadd_plan_destroy(b200sp_spadd_plan*, void*);
 struct b200sp_gs_plan;
 extern "C" int b200sp_gs_plan_destroy(b200sp_gs_plan*, void*);
+struct b200sp_spmv_plan;
+struct b200sp_bsr_plan;
+extern "C" int b200sp_spmv_plan_destroy(b200sp_spmv_plan*, void*);
+extern "C" int b200sp_bsr_plan_destroy(b200sp_bsr_plan*, void*);
+
+namespace KokkosSparse {
+// the GMRESHandle members the shim touches (sparse/src/KokkosSparse_gmres_handle.hpp:66-186) + the two plan members
+// INTEGRATION.md adds
+struct GMRESHandleMock {
+  enum Ortho { CGS2, MGS };
+  enum Flag { Conv, NoConv, LOA, NotRun };
+  GMRESHandleMock(int m_ = 50, double tol_ = 1e-8, int max_restart_ = 50) : m(m_), tol(tol_), max_restart(max_restart_) {}
+  ~GMRESHandleMock() {
+    if (b200_spmv_plan) b200sp_spmv_plan_destroy(b200_spmv_plan, nullptr);
+    if (b200_bsr_plan) b200sp_bsr_plan_destroy(b200_bsr_plan, nullptr);
+  }
+  int get_m() const { return m; }
+  double get_tol() const { return tol; }
+  int get_max_restart() const { return max_restart; }
+  Ortho get_ortho() const { return ortho; }
+  void set_ortho(Ortho o) { ortho = o; }
+  void set_stats(int it, double res, Flag f) {
+    num_iters = it;
+    end_rel_res = res;
+    conv_flag_val = f;
+  }
+  int m, max_restart;
+  double tol;
+  Ortho ortho = CGS2;
+  int num_iters = -1;
+  double end_rel_res = 0;
+  Flag conv_flag_val = NotRun;
+  b200sp_spmv_plan* b200_spmv_plan = nullptr;
+  b200sp_bsr_plan* b200_bsr_plan   = nullptr;
+};
+namespace Experimental {
+template <class AMatrix>
+struct Preconditioner {  // sparse/src/KokkosSparse_Preconditioner.hpp: the base class gmres takes a pointer to
+  virtual ~Preconditioner() {}
+};
+}  // namespace Experimental
+namespace Impl {
+namespace Experimental {
+// the native implementation the shim falls back to when a preconditioner is given (sparse/impl/KokkosSparse_gmres_impl.hpp:39-60);
+// the mock only records the call
+template <class GmresHandle>
+struct GmresWrap {
+  static int& calls() {
+    static int c = 0;
+    return c;
+  }
+  template <class A, class B, class X, class P>
+  static void gmres(GmresHandle&, const A&, const B&, X&, P*) {
+    ++calls();
+  }
+};
+}  // namespace Experimental
+}  // namespace Impl
+}  // namespace KokkosSparse
 
 namespace KokkosSparse {
 enum class SparseMatrixFormat { BSR, CRS };  // sparse/src/KokkosSparse_Utils.hpp
@@ -308,6 +367,13 @@ struct KokkosKernelsHandle {
     gsh = nullptr;
   }
   KokkosSparse::PointGaussSeidelHandleMock* gsh = nullptr;
+  KokkosSparse::GMRESHandleMock* get_gmres_handle() { return gmh; }
+  void create_gmres_handle(int m = 50, double tol = 1e-8, int max_restart = 50) { gmh = new KokkosSparse::GMRESHandleMock(m, tol, max_restart); }
+  void destroy_gmres_handle() {
+    delete gmh;
+    gmh = nullptr;
+  }
+  KokkosSparse::GMRESHandleMock* gmh = nullptr;
   using SPADDHandleType = KokkosSparse::SPADDHandleMock;
   SPADDHandleType* get_spadd_handle() { return ah; }
   void create_spadd_handle(bool input_sorted = false, bool input_merged = false) { ah = new SPADDHandleType(input_sorted, input_merged); }
@@ -330,6 +396,14 @@ template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class
 struct spgemm_numeric_tpl_spec_avail {
   enum : bool { value = false };
 };
+// sparse/tpls/KokkosSparse_gmres_tpl_spec_avail.hpp:26-29, sparse/impl/KokkosSparse_gmres_spec.hpp:69-82
+template <class KH, class AT, class AO, class AD, class AM, class AS, class BType, class XType>
+struct gmres_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class KH, class AT, class AO, class AD, class AM, class AS, class BType, class XType,
+          bool tpl = gmres_tpl_spec_avail<KH, AT, AO, AD, AM, AS, BType, XType>::value, bool eti = true>
+struct GMRES;
 // sparse/tpls/KokkosSparse_gauss_seidel_tpl_spec_avail.hpp and sparse/impl/KokkosSparse_gauss_seidel_spec.hpp:105-151
 template <class KH, class a_r, class a_e>
 struct gauss_seidel_symbolic_tpl_spec_avail {

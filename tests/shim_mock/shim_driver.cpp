@@ -14,6 +14,8 @@
 #include "KokkosSparse_gauss_seidel_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_gauss_seidel_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_gmres_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_gmres_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_decl.hpp"
 
 #include <cmath>
@@ -65,11 +67,12 @@ T* to_dev(const std::vector<T>& h) {
 
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
-  bool with_bsr = false, with_jacobi = false, with_gs = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
+  bool with_bsr = false, with_jacobi = false, with_gs = false, with_gmres = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
   for (int a = 1; a < argc; ++a) {
     with_bsr |= std::string(argv[a]) == "--bsr";
     with_jacobi |= std::string(argv[a]) == "--jacobi";
     with_gs |= std::string(argv[a]) == "--gs";
+    with_gmres |= std::string(argv[a]) == "--gmres";
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -298,6 +301,51 @@ int main(int argc, char** argv) {
     cudaFree(d_vd);
     cudaFree(d_xg);
     cudaFree(d_yg);
+  }
+  if (with_gmres) {
+    // gmres through GMRES<KH, ..., true, true>::gmres (CrsMatrix, no preconditioner -> the library; with one -> the native GmresWrap)
+    using UMRAV = Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>;
+    using GB    = Kokkos::View<const double*, KokkosKernels::default_layout, Dev, UMRAV>;
+    using GX    = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UMRAV>;
+    using GM    = Impl::GMRES<KH, const double, const int, Dev, UM, const int, GB, GX, true, true>;
+    static_assert(Impl::gmres_tpl_spec_avail<KH, const double, const int, Dev, UM, const int, GB, GX>::value, "gmres must be available");
+    std::vector<double> vd(va);
+    for (int i = 0; i < n; ++i)
+      for (int q = rp[i]; q < rp[i + 1]; ++q)
+        if (ci[q] == i) vd[q] = 3.0;
+    double* d_vd = to_dev(vd);
+    std::vector<double> ones(n, 1.0), zeros(n, 0.0);
+    double *d_b = to_dev(ones), *d_xx = to_dev(zeros);
+    KH kh;
+    kh.create_gmres_handle(15, 1e-8);
+    AMat A(n, n, ci.size(), d_vd, d_rp, d_ci);
+    GB Bv(d_b, n);
+    GX Xv(d_xx, n);
+    GM::gmres(&kh, A, Bv, Xv);
+    cudaDeviceSynchronize();
+    std::vector<double> xg(n);
+    cudaMemcpy(xg.data(), d_xx, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    double rr = 0, bb = 0;
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int q = rp[i]; q < rp[i + 1]; ++q) s += vd[q] * xg[ci[q]];
+      rr += (1.0 - s) * (1.0 - s);
+      bb += 1.0;
+    }
+    auto gh = kh.get_gmres_handle();
+    int f9  = (std::sqrt(rr / bb) < 1e-8 && gh->conv_flag_val == GMRESHandleMock::Conv && gh->num_iters > 0) ? 0 : 1;
+    Experimental::Preconditioner<AMat> prec;
+    using Wrap = Impl::Experimental::GmresWrap<GMRESHandleMock>;
+    const int before = Wrap::calls();
+    GM::gmres(&kh, A, Bv, Xv, &prec);
+    if (Wrap::calls() != before + 1) ++f9;  // a preconditioner routes to the native implementation
+    std::printf("gmres through GMRES<...,true,true>::gmres : rel. residual %.2e after %d iterations, %d mismatches\n", std::sqrt(rr / bb),
+                gh->num_iters, f9);
+    failures += f9;
+    kh.destroy_gmres_handle();
+    cudaFree(d_vd);
+    cudaFree(d_b);
+    cudaFree(d_xx);
   }
   if (with_bsr) {
     // BsrMatrix: block-tridiagonal, 3 x 3 blocks, through SPMV_BSRMATRIX<...,true,true> (N) and
