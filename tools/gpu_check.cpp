@@ -77,6 +77,12 @@ void okk_bsr_spmv_v41_f64(char mode, int mb, int ylen_b, int bs, int nvec, const
                           const double* X, int64_t xr, int64_t xc, double* Y, int64_t yr, int64_t yc, double alpha, double beta);
 int okk_cg_f64(int n, const int* rm, const int* ci, const double* v, const double* b, double* x, int maximum_iteration, double tolerance,
                double* norm_res_out);
+int okk_pcg_f64(int n, const int* rm, const int* ci, const double* v, const double* b, double* x, int maximum_iteration, double tolerance,
+                double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv);
+void okk_gs_apply_f64(int n, const int* rm, const int* ci, const double* v, int ncolors, const int* color_ptr, const int* color_rows,
+                      const double* dinv, const double* y, double* x, int init_zero_x, double omega, int sweeps, int direction);
+int okk_gmres_f64(int n, const int* rm, const int* ci, const double* v, const int* prm, const int* pci, const double* pv, const double* B,
+                  double* X, int m, double tol, int max_restart, int ortho, int* num_iters_out, double* end_rel_res_out, int* conv_flag_out);
 int okk_num_threads(void);
 // host generators (kokkos-kernels_b200/csrc/matgen.c)
 void b200gen_fill_f64(int64_t n, double* v, double lo, double hi, uint64_t seed);
@@ -1197,6 +1203,117 @@ static void suite_cg() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: solvers -- point Gauss-Seidel (colouring, sweeps), the SGS-preconditioned CG and GMRES against the oracle, with the times
+// that matter next to the SpMV's: symbolic, one symmetric sweep, PCG and GMRES per iteration
+// ------------------------------------------------------------------------------------------------
+static void suite_solvers() {
+  Csr<double> A = gen_lap27<double>(g_big ? 128 : 20, 1);
+  for (int r = 0; r < A.m; ++r)
+    for (int q = A.rp[r]; q < A.rp[r + 1]; ++q)
+      if (A.ci[q] == r) A.v[q] += 0.5;
+  const int n = A.m;
+  std::vector<double> xs((size_t)n), b((size_t)n, 0.0), dinv((size_t)n, 1.0);
+  b200gen_fill_f64(n, xs.data(), -1.0, 1.0, 9);
+  okk_spmv_serial_f64(n, A.rp.data(), A.ci.data(), A.v.data(), xs.data(), b.data(), 1.0, 0.0);
+  for (int r = 0; r < n; ++r)
+    for (int q = A.rp[r]; q < A.rp[r + 1]; ++q)
+      if (A.ci[q] == r) dinv[r] = 1.0 / A.v[q];
+  Dev<int> rp(A.rp), ci(A.ci);
+  Dev<double> v(A.v), db(b), dx((size_t)n);
+  b200sp_spmv_plan* plan = nullptr;
+  SP(b200sp_spmv_plan_create(&plan, 0));
+  float spmv_ms = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    Timer t;
+    t.start();
+    SP(b200sp_spmv_f64_i32(plan, nullptr, 'N', n, n, A.nnz(), 1.0, rp.p, ci.p, v.p, db.p, 0.0, dx.p));
+    spmv_ms = std::min(spmv_ms, t.stop_ms());
+  }
+  // ---- Gauss-Seidel
+  b200sp_gs_plan* gs = nullptr;
+  SP(b200sp_gs_plan_create(&gs));
+  double t0 = now_s();
+  SP(b200sp_gs_symbolic_i32(gs, nullptr, n, rp.p, ci.p, 1));
+  const double sym_ms = (now_s() - t0) * 1e3;
+  SP(b200sp_gs_numeric_f64_i32(gs, nullptr, n, rp.p, ci.p, v.p));
+  int nc = 0;
+  SP(b200sp_gs_get_coloring(gs, &nc, nullptr, nullptr, nullptr));
+  std::vector<int> colors((size_t)n), cptr((size_t)nc + 1), crows((size_t)n);
+  SP(b200sp_gs_copy_coloring(gs, nullptr, colors.data(), cptr.data(), crows.data()));
+  int64_t clashes = 0;
+  for (int r = 0; r < n; ++r)
+    for (int q = A.rp[r]; q < A.rp[r + 1]; ++q)
+      if (A.ci[q] != r && colors[A.ci[q]] == colors[r]) ++clashes;
+  for (int direction = 0; direction < 3; ++direction) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      Timer t;
+      t.start();
+      SP(b200sp_gs_apply_f64_i32(gs, nullptr, n, rp.p, ci.p, v.p, dx.p, db.p, 1, 0.9, 2, direction));
+      best = std::min(best, t.stop_ms());
+    }
+    auto x = dx.host();
+    std::vector<double> xo((size_t)n, 0.0);
+    okk_gs_apply_f64(n, A.rp.data(), A.ci.data(), A.v.data(), nc, cptr.data(), crows.data(), dinv.data(), b.data(), xo.data(), 1, 0.9, 2, direction);
+    double worst = 0, err = 0, nrm = 0;
+    for (int i = 0; i < n; ++i) {
+      worst = std::max(worst, std::fabs(x[i] - xo[i]));
+      err += (x[i] - xs[i]) * (x[i] - xs[i]);
+      nrm += xs[i] * xs[i];
+    }
+    char nm[96];
+    snprintf(nm, sizeof(nm), "gauss_seidel/%s", direction == 0 ? "symmetric" : direction == 1 ? "forward" : "backward");
+    record(nm, clashes == 0 && worst <= 1e-12 && err < nrm,
+           "n=%d: %d colours (%lld clashes), symbolic %.2f ms; 2 sweeps %.3f ms (SpMV %.4f ms), max |x - x_oracle| %.1e, error norm %.3f of the "
+           "initial one",
+           n, nc, (long long)clashes, sym_ms, best, spmv_ms, worst, std::sqrt(err / nrm));
+  }
+  // ---- PCG (symmetric Gauss-Seidel preconditioner) next to plain CG
+  {
+    std::vector<double> xo((size_t)n, 0.0), xc((size_t)n, 0.0);
+    double nr_o = 0, nr_c = 0;
+    const int it_o = okk_pcg_f64(n, A.rp.data(), A.ci.data(), A.v.data(), b.data(), xo.data(), 100000, 1e-7, &nr_o, nc, cptr.data(), crows.data(),
+                                 dinv.data());
+    const int it_c = okk_cg_f64(n, A.rp.data(), A.ci.data(), A.v.data(), b.data(), xc.data(), 100000, 1e-7, &nr_c);
+    dx.fill_bytes(0);
+    int it = 0;
+    double nr = 0;
+    t0 = now_s();
+    SP(b200sp_pcg_solve_f64_i32(plan, gs, nullptr, n, A.nnz(), rp.p, ci.p, v.p, db.p, dx.p, 100000, 1e-7, 8, &it, &nr));
+    const double ms = (now_s() - t0) * 1e3;
+    auto x = dx.host();
+    double num = 0, den = 0;
+    for (int i = 0; i < n; ++i) {
+      num += (x[i] - xo[i]) * (x[i] - xo[i]);
+      den += xo[i] * xo[i];
+    }
+    record("pcg_sgs", std::abs(it - it_o) <= 1 && nr <= 1e-7 && std::sqrt(num / std::max(den, 1e-300)) < 1e-8,
+           "%d iterations (oracle %d; plain CG %d), norm_res %.2e, |x-x_oracle|/|x_oracle| %.1e; %.3f ms = %.4f ms/iteration (SpMV %.4f ms)", it,
+           it_o, it_c, nr, std::sqrt(num / std::max(den, 1e-300)), ms, ms / std::max(it, 1), spmv_ms);
+  }
+  // ---- GMRES(15), CGS2 and MGS
+  for (int ortho = 0; ortho < 2; ++ortho) {
+    std::vector<double> xo((size_t)n, 0.0);
+    int it_o = 0, flag_o = 0;
+    double res_o = 0;
+    okk_gmres_f64(n, A.rp.data(), A.ci.data(), A.v.data(), nullptr, nullptr, nullptr, b.data(), xo.data(), 15, 1e-8, 50, ortho, &it_o, &res_o,
+                  &flag_o);
+    dx.fill_bytes(0);
+    int it = 0, flag = 0;
+    double res = 0;
+    t0 = now_s();
+    SP(b200sp_gmres_f64_i32(plan, nullptr, n, A.nnz(), rp.p, ci.p, v.p, nullptr, 0, nullptr, nullptr, nullptr, db.p, dx.p, 15, 1e-8, 50, ortho, &it,
+                            &res, &flag));
+    const double ms = (now_s() - t0) * 1e3;
+    record(ortho ? "gmres15/mgs" : "gmres15/cgs2", flag == 0 && flag_o == 0 && std::abs(it - it_o) <= 1 && res < 1e-8,
+           "%d iterations (oracle %d), relative residual %.2e, flag %d; %.3f ms = %.4f ms/iteration (SpMV %.4f ms)", it, it_o, res, flag, ms,
+           ms / std::max(it, 1), spmv_ms);
+  }
+  b200sp_gs_plan_destroy(gs, nullptr);
+  b200sp_spmv_plan_destroy(plan, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
 // suite: spmm_sweep -- the rank-2 kernels over column counts / scalar types / leading dimensions / beta
 // ------------------------------------------------------------------------------------------------
 static void ospmm(int m, int n, int k, const Csr<double>& A, const double* X, int64_t ldx, double* Y, int64_t ldy, double al, double be) {
@@ -1476,7 +1593,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}, {"solvers", suite_solvers, 90}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
