@@ -5,6 +5,7 @@ restatement of the reference's PSGS functor over the same sets; and the referenc
 symmetric / forward / backward: the error norm drops below the norm of the solution)."""
 import numpy as np
 import pytest
+import scipy.sparse as sps
 
 import emu_lib as E
 from gmres_cases import gmres_matrix
@@ -72,6 +73,34 @@ def test_reference_unit_test_and_oracle_parity(emu, oracle, symmetric, dtype):
     assert plan.apply(n, rp, ci, v, x, y, False, 0.9, 3, 0) == 0
     assert np.linalg.norm(x.astype(np.float64) - xs.astype(np.float64)) < 0.5 * before
     plan.close()
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_iterated_greedy_recolouring_never_adds_colours(emu, monkeypatch, symmetric):
+    """gs.cu re-colours class by class (Culberson) after Jones-Plassmann: valid, deterministic, never more colours."""
+    n = 2500
+    rp, ci, v = gmres_matrix(n, 1.0, seed=99)
+    if symmetric:
+        rp, ci, v = symmetrize(rp, ci, v, n)
+    counts = {}
+    for passes in ("0", "1", "2", "5"):
+        monkeypatch.setenv("B200SP_GS_RECOLOR", passes)
+        got = []
+        for _ in range(2):
+            plan = E.GsPlan()
+            plan.symbolic(n, rp, ci, symmetric)
+            nc, colors, cptr, crows = plan.coloring(n)
+            if not symmetric:  # the colouring is of the symmetrised graph
+                S = sps.csr_matrix((np.ones(len(ci)), ci, rp), shape=(n, n))
+                S = (S + S.T).tocsr()
+                check_coloring(n, S.indptr, S.indices, nc, colors, cptr, crows)
+            else:
+                check_coloring(n, rp, ci, nc, colors, cptr, crows)
+            got.append(colors.copy())
+            plan.close()
+        assert np.array_equal(got[0], got[1])  # same input, same colouring
+        counts[passes] = nc
+    assert counts["0"] >= counts["1"] >= counts["2"] >= counts["5"]
 
 
 def test_structure_corner_cases(emu, oracle):
