@@ -93,6 +93,44 @@ int b200sp_spmv_f32_i32(b200sp_spmv_plan* plan, void* stream, char mode, int m, 
                         float alpha, const int* row_ptr, const int* col_idx, const float* vals,
                         const float* x, float beta, float* y);
 
+/* ---- SpMV on 64-bit offsets (matrices past 2^31 entries) ----------------- */
+/* Replaces the (int64_t ordinal, size_t offset) instantiations of the cuSPARSE SpMV slot,
+ * KOKKOSSPARSE_SPMV_CUSPARSE(double|float, int64_t, size_t, ...)
+ * (sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:246-257, availability ..._spec_avail.hpp:85-102), and also takes
+ * 32-bit columns under 64-bit offsets (col_bits = 32), which that slot cannot (:86).  row_ptr has m+1 int64 entries
+ * (size_t offsets below 2^63 read the same); col_idx is const int32_t* or const int64_t* by col_bits.  m and n must
+ * stay below 2^31 and no row may hold more than the window limit (about 2^31 entries): B200SP_ERR_OVERFLOW otherwise,
+ * also when a 64-bit column index does not fit 31 bits.  Semantics of mode / alpha / beta as b200sp_spmv_f64_i32.
+ * The plan is required: on the first call with a matrix (keyed on the array pointers, m, n, nnz) it reads the 64-bit
+ * structure ONCE -- rows are cut into windows of < 2^31 entries, each with a 32-bit row map relative to its first entry
+ * (4 B per row), 64-bit columns are narrowed to 32 bits (4 B per entry; 32-bit columns are used in place) -- and every
+ * product then runs the 32-bit kernels window by window: 12 B of HBM traffic per fp64 entry instead of the 16 B a kernel
+ * reading 64-bit columns would move, results bit-identical to the 32-bit entry points' on each window.  The analysis
+ * synchronises `stream` once. */
+typedef struct b200sp_spmv64_plan b200sp_spmv64_plan;
+int b200sp_spmv64_plan_create(b200sp_spmv64_plan** plan, int algo);
+int b200sp_spmv64_plan_destroy(b200sp_spmv64_plan* plan, void* stream);
+/* Entries per window, 8 .. 2^31-65537 (the default); smaller windows only make sense for tests. */
+int b200sp_spmv64_plan_set_window(b200sp_spmv64_plan* plan, int64_t max_entries);
+int b200sp_spmv64_plan_windows(const b200sp_spmv64_plan* plan);
+const char* b200sp_spmv64_last_kernel(const b200sp_spmv64_plan* plan);
+int b200sp_spmv_f64_i64(b200sp_spmv64_plan* plan, void* stream, char mode, int64_t m, int64_t n, int64_t nnz,
+                        double alpha, const int64_t* row_ptr, const void* col_idx, int col_bits, const double* vals,
+                        const double* x, double beta, double* y);
+int b200sp_spmv_f32_i64(b200sp_spmv64_plan* plan, void* stream, char mode, int64_t m, int64_t n, int64_t nnz,
+                        float alpha, const int64_t* row_ptr, const void* col_idx, int col_bits, const float* vals,
+                        const float* x, float beta, float* y);
+
+/* Rank 2 on the same plan and windows (arguments as b200sp_spmm_f64_i32, declared below). */
+int b200sp_spmm_f64_i64(b200sp_spmv64_plan* plan, void* stream, char mode, int64_t m, int64_t n, int64_t nnz, int k,
+                        double alpha, const int64_t* row_ptr, const void* col_idx, int col_bits, const double* vals,
+                        const double* X, int64_t ldx, int x_row_major, double beta, double* Y, int64_t ldy,
+                        int y_row_major);
+int b200sp_spmm_f32_i64(b200sp_spmv64_plan* plan, void* stream, char mode, int64_t m, int64_t n, int64_t nnz, int k,
+                        float alpha, const int64_t* row_ptr, const void* col_idx, int col_bits, const float* vals,
+                        const float* X, int64_t ldx, int x_row_major, float beta, float* Y, int64_t ldy,
+                        int y_row_major);
+
 /* Same call with HOST x / y (pinned or pageable): x is copied to the device,
  * y (when beta != 0) too, the kernel runs, y is copied back; all on `stream`.
  * The matrix arrays stay device-resident.  Requires a plan (owns the device

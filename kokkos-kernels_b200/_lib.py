@@ -22,6 +22,15 @@ SPARSE_API = {
     "b200sp_spmv_plan_set_option": (i32, [vp, i32, i32]),
     "b200sp_spmv_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, f64, vp, vp, vp, vp, f64, vp]),
     "b200sp_spmv_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, f32, vp, vp, vp, vp, f32, vp]),
+    "b200sp_spmv64_plan_create": (i32, [C.POINTER(vp), i32]),
+    "b200sp_spmv64_plan_destroy": (i32, [vp, vp]),
+    "b200sp_spmv64_plan_set_window": (i32, [vp, i64]),
+    "b200sp_spmv64_plan_windows": (i32, [vp]),
+    "b200sp_spmv64_last_kernel": (C.c_char_p, [vp]),
+    "b200sp_spmv_f64_i64": (i32, [vp, vp, cp, i64, i64, i64, f64, vp, vp, i32, vp, vp, f64, vp]),
+    "b200sp_spmv_f32_i64": (i32, [vp, vp, cp, i64, i64, i64, f32, vp, vp, i32, vp, vp, f32, vp]),
+    "b200sp_spmm_f64_i64": (i32, [vp, vp, cp, i64, i64, i64, i32, f64, vp, vp, i32, vp, vp, i64, i32, f64, vp, i64, i32]),
+    "b200sp_spmm_f32_i64": (i32, [vp, vp, cp, i64, i64, i64, i32, f32, vp, vp, i32, vp, vp, i64, i32, f32, vp, i64, i32]),
     "b200sp_spmv_scatter_f64_i32": (i32, [vp, vp, i32, i32, i64, f64, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]),
     "b200sp_peer_push": (i32, [vp, vp, i64, i32, C.POINTER(vp)]),
     "b200sp_peer_push_async": (i32, [vp, C.POINTER(vp), i32, C.POINTER(vp), vp, i64]),

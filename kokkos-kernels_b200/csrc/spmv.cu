@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
                                                           const int* __restrict__ col_idx,
                                                           const S* __restrict__ vals,
                                                           const S* __restrict__ x, S* __restrict__ y,
-                                                          S alpha, S beta, YExtra ex) {
+                                                          S alpha, S beta, YExtra ex, int lmax) {
+  // rows longer than lmax are left to spmv_longrow_kernel, as the tiled kernel leaves them: whichever of the two kernels a
+  // self-tuning plan settles on, every row is summed in the same order (INT_MAX: this kernel takes every row)
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
       rs = row_ptr[r];
       re = row_ptr[r + 1];
     }
+    const bool is_long = (re - rs) > lmax;
+    if (is_long) re = rs;
     S sum = S(0);
     constexpr int UNR = 8;
     for (int j0 = rs + sl; j0 < re; j0 += UNR * LPR) {
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) spmv_vector_kernel(int m, const int* __re
       for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
     }
     sum = subwarp_sum<LPR>(sum);
-    if (r < m && sl == 0) store_y(y, r, sum, alpha, beta, ex);
+    if (r < m && sl == 0 && !is_long) store_y(y, r, sum, alpha, beta, ex);
   }
 }
 
@@ -790,7 +794,9 @@ void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s) {
   if (p) snprintf(p->last_kernel, sizeof(p->last_kernel), "%s", s);
 }
 
-static int pick_lpr(int m, int64_t nnz) {
+int spmv_lanes_per_row(int64_t m, int64_t nnz);
+static int pick_lpr(int m, int64_t nnz) { return spmv_lanes_per_row(m, nnz); }
+int spmv_lanes_per_row(int64_t m, int64_t nnz) {  // also used by spmv64.cu: one choice for all windows of a matrix
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   // measured on B200 (profiles/r01_tune_spmv.csv): fewer lanes per row win until rows get long
   if (avg <= 8.0) return 2;
@@ -854,7 +860,7 @@ static int launch_tile_cfg(b200sp_spmv_plan* p, int cfg, cudaStream_t st, int m,
 
 template <typename S>
 static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, const int* row_ptr,
-                         const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta) {
+                         const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta, int lmax = INT32_MAX) {
   const int rpw = 32 / lpr;
   const int64_t warps = ((int64_t)m + rpw - 1) / rpw;
   int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16);
@@ -863,7 +869,7 @@ static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, c
   if (p) ex = p->extra;
 #define B200SP_VEC(L)                                                                              \
   case L:                                                                                          \
-    spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta, ex); \
+    spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta, ex, lmax); \
     break;
   switch (lpr) {
     B200SP_VEC(2)
@@ -1000,6 +1006,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   // ---- self-tuning (only for untuned plans on whole-matrix launches)
   const bool autotune = p->cfg < 0 && p->range_hi < 0 && p->extra.n == 0 && getenv("B200SP_NO_AUTOTUNE") == nullptr;
   int phase = -1;  // 1: time the tiled kernel, 2: time the vector kernel
+  bool use_vec = false;
   if (autotune) {
     if (p->at_choice < 0 && p->at_calls >= 3 && cudaEventQuery(p->at_ev[1]) == cudaSuccess &&
         cudaEventQuery(p->at_ev[3]) == cudaSuccess) {
@@ -1013,21 +1020,21 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
         if (!p->at_ev[i]) B200SP_CUDA_TRY(cudaEventCreate(&p->at_ev[i]));
     }
     p->at_calls++;
-    if (phase == 2 || (phase < 0 && p->at_choice == 1)) {
-      if (phase == 2) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[2], st));
-      rc = launch_vector<S>(p, st, lpr, m, row_ptr, col_idx, vals, x, y, alpha, beta);
-      if (phase == 2) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[3], st));
-      return rc;
-    }
-    if (phase == 1) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[0], st));
+    use_vec = phase == 2 || (phase < 0 && p->at_choice == 1);
+    if (phase > 0) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[phase == 1 ? 0 : 2], st));
   }
-  switch (lpr) {
-    case 2: rc = launch_tile_cfg<S, 2>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
-    case 4: rc = launch_tile_cfg<S, 4>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
-    case 8: rc = launch_tile_cfg<S, 8>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
-    case 16: rc = launch_tile_cfg<S, 16>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
-    case 32: rc = launch_tile_cfg<S, 32>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
-    default: set_error("bad lanes-per-row %d", lpr); return B200SP_ERR_INVALID_ARGUMENT;
+  if (use_vec) {
+    // same split as the tiled kernel: rows beyond LMAX go to the long-row kernel below, so the choice never changes a bit
+    rc = launch_vector<S>(p, st, lpr, m, row_ptr, col_idx, vals, x, y, alpha, beta, p->LMAX);
+  } else {
+    switch (lpr) {
+      case 2: rc = launch_tile_cfg<S, 2>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+      case 4: rc = launch_tile_cfg<S, 4>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+      case 8: rc = launch_tile_cfg<S, 8>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+      case 16: rc = launch_tile_cfg<S, 16>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+      case 32: rc = launch_tile_cfg<S, 32>(p, cfg, st, m, nnz, row_ptr, col_idx, vals, x, y, alpha, beta); break;
+      default: set_error("bad lanes-per-row %d", lpr); return B200SP_ERR_INVALID_ARGUMENT;
+    }
   }
   if (rc) return rc;
   // long rows: skip the launch once the (asynchronously fetched) count is known to be 0
@@ -1061,7 +1068,7 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
       B200SP_LAUNCH_CHECK();
     }
   }
-  if (phase == 1) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[1], st));
+  if (phase > 0) B200SP_CUDA_TRY(cudaEventRecord(p->at_ev[phase == 1 ? 1 : 3], st));
   return B200SP_OK;
 }
 

@@ -53,6 +53,16 @@ struct B200_SpMV_Data : public TPL_SpMV_Data<Kokkos::Cuda> {
   b200sp_spmv_plan* plan = nullptr;
 };
 
+// Same for matrices with 64-bit offsets (the (int64_t, size_t) instantiation cuSPARSE serves,
+// sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:246-257): the plan owns the 32-bit row windows.
+struct B200_SpMV64_Data : public TPL_SpMV_Data<Kokkos::Cuda> {
+  B200_SpMV64_Data(const Kokkos::Cuda& exec_, int algo) : TPL_SpMV_Data(exec_) {
+    KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_spmv64_plan_create(&plan, algo));
+  }
+  ~B200_SpMV64_Data() { b200sp_spmv64_plan_destroy(plan, (void*)exec.cuda_stream()); }
+  b200sp_spmv64_plan* plan = nullptr;
+};
+
 }  // namespace Impl
 }  // namespace KokkosSparse
 #endif

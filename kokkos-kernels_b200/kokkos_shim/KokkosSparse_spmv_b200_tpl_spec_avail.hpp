@@ -48,6 +48,46 @@ KOKKOSSPARSE_B200_SPMV_AVAIL_ALL(double, Kokkos::CudaUVMSpace)
 KOKKOSSPARSE_B200_SPMV_AVAIL_ALL(float, Kokkos::CudaUVMSpace)
 
 #undef KOKKOSSPARSE_B200_SPMV_AVAIL_ALL
+
+// 64-bit offsets: (int64_t, size_t) -- the instantiation of the cuSPARSE slot (..._tpl_spec_avail.hpp:85-102) -- and
+// (int, size_t), which cuSPARSE does not take (:86); rank 1 and rank 2
+#define KOKKOSSPARSE_B200_SPMV64_AVAIL(SCALAR, ORDINAL, OFFSET, LAYOUT, MEMSPACE)                                   \
+  template <>                                                                                                       \
+  struct spmv_tpl_spec_avail<                                                                                       \
+      Kokkos::Cuda, SPMVHandleImpl<Kokkos::Cuda, MEMSPACE, SCALAR, OFFSET, ORDINAL>,                                \
+      CrsMatrix<const SCALAR, const ORDINAL, Kokkos::Device<Kokkos::Cuda, MEMSPACE>,                                \
+                Kokkos::MemoryTraits<Kokkos::Unmanaged>, const OFFSET>,                                             \
+      Kokkos::View<const SCALAR*, LAYOUT, Kokkos::Device<Kokkos::Cuda, MEMSPACE>,                                   \
+                   Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>>,                                 \
+      Kokkos::View<SCALAR*, LAYOUT, Kokkos::Device<Kokkos::Cuda, MEMSPACE>, Kokkos::MemoryTraits<Kokkos::Unmanaged>>> { \
+    enum : bool { value = true };                                                                                   \
+  };
+#define KOKKOSSPARSE_B200_SPMV64_MV_AVAIL(SCALAR, ORDINAL, OFFSET, XL, YL, MEMSPACE)                                \
+  template <>                                                                                                       \
+  struct spmv_mv_tpl_spec_avail<                                                                                    \
+      Kokkos::Cuda, SPMVHandleImpl<Kokkos::Cuda, MEMSPACE, SCALAR, OFFSET, ORDINAL>,                                \
+      CrsMatrix<const SCALAR, const ORDINAL, Kokkos::Device<Kokkos::Cuda, MEMSPACE>,                                \
+                Kokkos::MemoryTraits<Kokkos::Unmanaged>, const OFFSET>,                                             \
+      Kokkos::View<const SCALAR**, XL, Kokkos::Device<Kokkos::Cuda, MEMSPACE>,                                      \
+                   Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>>,                                 \
+      Kokkos::View<SCALAR**, YL, Kokkos::Device<Kokkos::Cuda, MEMSPACE>, Kokkos::MemoryTraits<Kokkos::Unmanaged>>> { \
+    enum : bool { value = true };                                                                                   \
+  };
+#define KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(SCALAR, ORDINAL, OFFSET, MEMSPACE)                                   \
+  KOKKOSSPARSE_B200_SPMV64_AVAIL(SCALAR, ORDINAL, OFFSET, Kokkos::LayoutLeft, MEMSPACE)                         \
+  KOKKOSSPARSE_B200_SPMV64_AVAIL(SCALAR, ORDINAL, OFFSET, Kokkos::LayoutRight, MEMSPACE)                        \
+  KOKKOSSPARSE_B200_SPMV64_MV_AVAIL(SCALAR, ORDINAL, OFFSET, Kokkos::LayoutLeft, Kokkos::LayoutLeft, MEMSPACE)  \
+  KOKKOSSPARSE_B200_SPMV64_MV_AVAIL(SCALAR, ORDINAL, OFFSET, Kokkos::LayoutRight, Kokkos::LayoutRight, MEMSPACE)
+
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(double, int64_t, size_t, Kokkos::CudaSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(float, int64_t, size_t, Kokkos::CudaSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(double, int, size_t, Kokkos::CudaSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(float, int, size_t, Kokkos::CudaSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(double, int64_t, size_t, Kokkos::CudaUVMSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(float, int64_t, size_t, Kokkos::CudaUVMSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(double, int, size_t, Kokkos::CudaUVMSpace)
+KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL(float, int, size_t, Kokkos::CudaUVMSpace)
+#undef KOKKOSSPARSE_B200_SPMV64_AVAIL_ALL
 }  // namespace Impl
 }  // namespace KokkosSparse
 #endif

@@ -38,6 +38,14 @@ _ALGO_TO_C = {SPMV_DEFAULT: 0, SPMV_FAST_SETUP: 1, SPMV_NATIVE: 1, SPMV_MERGE_PA
               SPMV_BSR_V42: 0, SPMV_BSR_TC: 0}
 
 
+def _idx(t):
+    """Device pointer of a 32-bit index array: every entry point but spmv's 64-bit ones reads int32 ordinals and offsets."""
+    if t is not None and t.dtype != torch.int32:
+        raise B200SparseError(f"b200sparse: this operation takes int32 row maps / entries, got {t.dtype} "
+                              "(only spmv accepts 64-bit offsets)")
+    return _ptr(t)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
 
@@ -48,10 +56,13 @@ def _stream():
 
 class CrsMatrix:
     """graph.row_map / graph.entries / values / numCols (0-based CSR; rows need
-    not be sorted, duplicates are legal for spmv)."""
+    not be sorted, duplicates are legal for spmv).  Ordinal / offset types: (int32, int32) everywhere; spmv also takes 64-bit
+    offsets -- row_map int64 with int32 or int64 entries, the (int64_t, size_t) instantiation of the reference's cuSPARSE slot
+    (sparse/tpls/KokkosSparse_spmv_tpl_spec_decl.hpp:246-257) -- for matrices past 2^31 entries."""
 
     def __init__(self, row_map, entries, values, ncols):
-        assert row_map.dtype == torch.int32 and entries.dtype == torch.int32
+        assert (row_map.dtype == torch.int32 and entries.dtype == torch.int32) or (
+            row_map.dtype == torch.int64 and entries.dtype in (torch.int32, torch.int64))
         self.row_map, self.entries, self.values = row_map, entries, values
         self._ncols = int(ncols)
 
@@ -109,7 +120,20 @@ class SPMVHandle:
         self.algo = algo
         self._plan = C.c_void_p(0)
         self._bsr_plan = C.c_void_p(0)  # created by the first BsrMatrix call (the handle then only ever sees that matrix)
+        self._plan64 = C.c_void_p(0)    # created by the first call with 64-bit offsets
         check(_lib.sparse().b200sp_spmv_plan_create(C.byref(self._plan), _ALGO_TO_C[algo]))
+
+    def _p64(self):
+        if not self._plan64:
+            check(_lib.sparse().b200sp_spmv64_plan_create(C.byref(self._plan64), _ALGO_TO_C[self.algo]))
+        return self._plan64
+
+    def set_window(self, max_entries):
+        """64-bit offsets only: entries per 32-bit window (default 2^31 - 65537; smaller values are for tests)."""
+        check(_lib.sparse().b200sp_spmv64_plan_set_window(self._p64(), int(max_entries)))
+
+    def windows(self):
+        return _lib.sparse().b200sp_spmv64_plan_windows(self._plan64) if self._plan64 else 0
 
     def _bsr(self):
         if not self._bsr_plan:
@@ -129,6 +153,8 @@ class SPMVHandle:
     def last_kernel(self):
         if self._bsr_plan:
             return _lib.sparse().b200sp_bsr_last_kernel(self._bsr_plan).decode()
+        if self._plan64:
+            return _lib.sparse().b200sp_spmv64_last_kernel(self._plan64).decode()
         return _lib.sparse().b200sp_spmv_last_kernel(self._plan).decode()
 
     def __del__(self):
@@ -137,6 +163,9 @@ class SPMVHandle:
             if self._bsr_plan:
                 _lib.sparse().b200sp_bsr_plan_destroy(self._bsr_plan, st)
                 self._bsr_plan = C.c_void_p(0)
+            if self._plan64:
+                _lib.sparse().b200sp_spmv64_plan_destroy(self._plan64, st)
+                self._plan64 = C.c_void_p(0)
             if self._plan:
                 _lib.sparse().b200sp_spmv_plan_destroy(self._plan, st)
                 self._plan = C.c_void_p(0)
@@ -183,11 +212,21 @@ def spmv(handle, mode, alpha, A, x, beta, y):
     if is_bsr:
         tmp = handle if handle is not None else SPMVHandle(SPMV_FAST_SETUP)
         return _spmv_bsr(lib, tmp._bsr(), mc, alpha, A, x, beta, y, f64, xcols)
+    wide = A.row_map.dtype == torch.int64  # 64-bit offsets: the plan's 32-bit windows (spmv64.cu)
+    if wide:
+        owner = handle if handle is not None else SPMVHandle(SPMV_FAST_SETUP)  # kept alive until the call returns
+        plan = owner._p64()
+        bits = 64 if A.entries.dtype == torch.int64 else 32
     if x.dim() == 1:
         if x.stride(0) != 1 or y.stride(0) != 1:
             raise B200SparseError("b200sparse: rank-1 x and y must be contiguous")
+        if wide:
+            fn = lib.b200sp_spmv_f64_i64 if f64 else lib.b200sp_spmv_f32_i64
+            check(fn(plan, _stream(), mc, m, n, A.nnz(), alpha, _ptr(A.row_map), _ptr(A.entries), bits, _ptr(A.values),
+                     _ptr(x), beta, _ptr(y)))
+            return y
         fn = lib.b200sp_spmv_f64_i32 if f64 else lib.b200sp_spmv_f32_i32
-        check(fn(plan, _stream(), mc, m, n, A.nnz(), alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+        check(fn(plan, _stream(), mc, m, n, A.nnz(), alpha, _idx(A.row_map), _idx(A.entries), _ptr(A.values),
                  _ptr(x), beta, _ptr(y)))
         return y
 
@@ -201,8 +240,13 @@ def spmv(handle, mode, alpha, A, x, beta, y):
 
     ldx, xrm = layout(x)
     ldy, yrm = layout(y)
+    if wide:
+        fn = lib.b200sp_spmm_f64_i64 if f64 else lib.b200sp_spmm_f32_i64
+        check(fn(plan, _stream(), mc, m, n, A.nnz(), xcols, alpha, _ptr(A.row_map), _ptr(A.entries), bits, _ptr(A.values),
+                 _ptr(x), ldx, xrm, beta, _ptr(y), ldy, yrm))
+        return y
     fn = lib.b200sp_spmm_f64_i32 if f64 else lib.b200sp_spmm_f32_i32
-    check(fn(plan, _stream(), mc, m, n, A.nnz(), xcols, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+    check(fn(plan, _stream(), mc, m, n, A.nnz(), xcols, alpha, _idx(A.row_map), _idx(A.entries), _ptr(A.values),
              _ptr(x), ldx, xrm, beta, _ptr(y), ldy, yrm))
     return y
 
@@ -224,13 +268,13 @@ def _spmv_bsr(lib, plan, mc, alpha, A, x, beta, y, f64, xcols):
         if x.stride(0) != 1 or y.stride(0) != 1:
             raise B200SparseError("b200sparse: rank-1 x and y must be contiguous")
         fn = lib.b200sp_bsr_spmv_f64_i32 if f64 else lib.b200sp_bsr_spmv_f32_i32
-        check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(x), beta,
+        check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, alpha, _idx(A.row_map), _idx(A.entries), _ptr(A.values), _ptr(x), beta,
                  _ptr(y)))
         return y
     ldx, xrm = _mv_layout(x)
     ldy, yrm = _mv_layout(y)
     fn = lib.b200sp_bsr_spmm_f64_i32 if f64 else lib.b200sp_bsr_spmm_f32_i32
-    check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, xcols, alpha, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(x), ldx,
+    check(fn(plan, _stream(), mc, mb, nb, A.nnz(), bs, xcols, alpha, _idx(A.row_map), _idx(A.entries), _ptr(A.values), _ptr(x), ldx,
              xrm, beta, _ptr(y), ldy, yrm))
     return y
 
@@ -302,16 +346,16 @@ def gmres(handle, A, B, X, precond=None, spmv_handle=None):
                 M.numRows() != A.numRows() or M.numCols() != A.numCols():
             raise B200SparseError("gmres: the MatrixPrec matrix must have A's type, size and scalar")
         pm = precond._handle._bsr() if is_bsr else precond._handle._plan
-        nnzm, rpm, cim, vm = M.nnz(), _ptr(M.row_map), _ptr(M.entries), _ptr(M.values)
+        nnzm, rpm, cim, vm = M.nnz(), _idx(M.row_map), _idx(M.entries), _ptr(M.values)
     else:
         pm, nnzm, rpm, cim, vm = null, 0, null, null, null
     if is_bsr:
         fn = lib.b200sp_gmres_bsr_f64_i32 if f64 else lib.b200sp_gmres_bsr_f32_i32
-        check(fn(ha._bsr(), _stream(), A.numRows(), A.nnz(), A.blockDim(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm,
+        check(fn(ha._bsr(), _stream(), A.numRows(), A.nnz(), A.blockDim(), _idx(A.row_map), _idx(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm,
                  _ptr(B), _ptr(X), gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
     else:
         fn = lib.b200sp_gmres_f64_i32 if f64 else lib.b200sp_gmres_f32_i32
-        check(fn(ha._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm, _ptr(B), _ptr(X),
+        check(fn(ha._plan, _stream(), n, A.nnz(), _idx(A.row_map), _idx(A.entries), _ptr(A.values), pm, nnzm, rpm, cim, vm, _ptr(B), _ptr(X),
                  gh.m, tol, gh.max_restart, gh.ortho, C.byref(it), C.byref(res), C.byref(flag)))
     gh.num_iters, gh.end_rel_res, gh.conv_flag_val = it.value, float(res.value), flag.value
     return gh
@@ -366,7 +410,7 @@ def gauss_seidel_symbolic(handle, num_rows, num_cols, row_map, entries, is_graph
     if num_rows != num_cols:
         raise B200SparseError("b200sparse: point Gauss-Seidel needs a square matrix")
     gh = _gs_handle(handle)
-    check(_lib.sparse().b200sp_gs_symbolic_i32(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), int(bool(is_graph_symmetric))))
+    check(_lib.sparse().b200sp_gs_symbolic_i32(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), int(bool(is_graph_symmetric))))
     gh._symbolic, gh._numeric = True, False
 
 
@@ -374,7 +418,7 @@ def gauss_seidel_numeric(handle, num_rows, num_cols, row_map, entries, values, i
     """KokkosSparse::gauss_seidel_numeric (:223-290); is_graph_symmetric only matters to symbolic."""
     gh = _gs_handle(handle)
     fn = _lib.sparse().b200sp_gs_numeric_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_numeric_f32_i32
-    check(fn(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), _ptr(values)))
+    check(fn(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), _ptr(values)))
     gh._numeric = True
 
 
@@ -383,7 +427,7 @@ def _gs_apply(handle, num_rows, row_map, entries, values, x_lhs, y_rhs, init_zer
     if values.dtype != x_lhs.dtype or x_lhs.dtype != y_rhs.dtype or x_lhs.dim() != 1 or y_rhs.dim() != 1:
         raise B200SparseError("b200sparse: gauss_seidel_apply needs rank-1 x, y of the matrix' scalar type")
     fn = _lib.sparse().b200sp_gs_apply_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_apply_f32_i32
-    check(fn(gh._plan, _stream(), int(num_rows), _ptr(row_map), _ptr(entries), _ptr(values), _ptr(x_lhs), _ptr(y_rhs), int(bool(init_zero_x_vector)),
+    check(fn(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), _ptr(values), _ptr(x_lhs), _ptr(y_rhs), int(bool(init_zero_x_vector)),
              omega, int(numIter), direction))
 
 
@@ -431,11 +475,11 @@ def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.2
             gh = GaussSeidelHandle()
             gauss_seidel_symbolic(gh, n, n, A.row_map, A.entries, True)  # SPD: the pattern is symmetric
             gauss_seidel_numeric(gh, n, n, A.row_map, A.entries, A.values, True)
-        check(_lib.sparse().b200sp_pcg_solve_f64_i32(h._plan, gh._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+        check(_lib.sparse().b200sp_pcg_solve_f64_i32(h._plan, gh._plan, _stream(), n, A.nnz(), _idx(A.row_map), _idx(A.entries), _ptr(A.values),
                                                      _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
                                                      int(check_every), C.byref(it), C.byref(nr)))
         return CGSolveResult(it.value, nr.value)
-    check(_lib.sparse().b200sp_cg_solve_f64_i32(h._plan, _stream(), n, A.nnz(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
+    check(_lib.sparse().b200sp_cg_solve_f64_i32(h._plan, _stream(), n, A.nnz(), _idx(A.row_map), _idx(A.entries), _ptr(A.values),
                                                 _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
                                                 int(check_every), C.byref(it), C.byref(nr)))
     return CGSolveResult(it.value, nr.value)
@@ -446,7 +490,7 @@ def spmv_scatter(handle, alpha, A, x, y, extra_ptrs):
     `extra_ptrs` (peer GPUs' next-x slots mapped into this process)."""
     arr = (C.c_void_p * max(len(extra_ptrs), 1))(*[C.c_void_p(int(q)) for q in extra_ptrs])
     check(_lib.sparse().b200sp_spmv_scatter_f64_i32(
-        handle._plan, _stream(), A.numRows(), A.numCols(), A.nnz(), alpha, _ptr(A.row_map), _ptr(A.entries),
+        handle._plan, _stream(), A.numRows(), A.numCols(), A.nnz(), alpha, _idx(A.row_map), _idx(A.entries),
         _ptr(A.values), _ptr(x), _ptr(y), len(extra_ptrs), arr))
     return y
 
@@ -455,8 +499,8 @@ def spmv_hostvec(handle, mode, alpha, A, x_host, beta, y_host):
     """End-to-end entry: host x / y (pinned), device-resident matrix."""
     m, n = A.numRows(), A.numCols()
     check(_lib.sparse().b200sp_spmv_hostvec_f64_i32(
-        handle._plan, _stream(), _mode_char(mode).encode(), m, n, A.nnz(), alpha, _ptr(A.row_map),
-        _ptr(A.entries), _ptr(A.values), C.c_void_p(x_host.data_ptr()), beta, C.c_void_p(y_host.data_ptr())))
+        handle._plan, _stream(), _mode_char(mode).encode(), m, n, A.nnz(), alpha, _idx(A.row_map),
+        _idx(A.entries), _ptr(A.values), C.c_void_p(x_host.data_ptr()), beta, C.c_void_p(y_host.data_ptr())))
     return y_host
 
 
@@ -575,7 +619,7 @@ def spgemm_symbolic_views(kh, m, n, k, row_mapA, entriesA, transposeA, row_mapB,
         raise B200SparseError("spgemm_symbolic: row_mapC must have m+1 entries")
     c_nnz, c_max = C.c_int64(0), C.c_int(0)
     check(_lib.sparse().b200sp_spgemm_symbolic_i32(
-        sh._plan, _stream(), m, n, k, _ptr(row_mapA), _ptr(entriesA), _ptr(row_mapB), _ptr(entriesB),
+        sh._plan, _stream(), m, n, k, _idx(row_mapA), _idx(entriesA), _idx(row_mapB), _idx(entriesB),
         C.c_void_p(row_mapC.data_ptr()), C.byref(c_nnz), C.byref(c_max)))
     sh._c_nnz, sh._max_nnz = c_nnz.value, c_max.value
     sh._symbolic = True
@@ -591,8 +635,8 @@ def spgemm_numeric_views(kh, m, n, k, row_mapA, entriesA, valuesA, transposeA, r
         raise B200SparseError("Call spgemm symbolic before spgemm numeric")
     f64 = valuesA.dtype == torch.float64
     fn = _lib.sparse().b200sp_spgemm_numeric_f64_i32 if f64 else _lib.sparse().b200sp_spgemm_numeric_f32_i32
-    check(fn(sh._plan, _stream(), m, n, k, _ptr(row_mapA), _ptr(entriesA), _ptr(valuesA), _ptr(row_mapB),
-             _ptr(entriesB), _ptr(valuesB), _ptr(row_mapC), _ptr(entriesC), _ptr(valuesC)))
+    check(fn(sh._plan, _stream(), m, n, k, _idx(row_mapA), _idx(entriesA), _ptr(valuesA), _idx(row_mapB),
+             _idx(entriesB), _ptr(valuesB), _idx(row_mapC), _idx(entriesC), _ptr(valuesC)))
     sh._numeric = True
     sh._entries = True
 
@@ -629,8 +673,8 @@ def spgemm_jacobi(kh, A, Amode, B, Bmode, Cm, omega, dinv):
     if dv.numel() != A.numRows() or dv.dtype != A.values.dtype:
         raise B200SparseError("KokkosSparse::spgemm_jacobi: dinv must hold one value of the matrix scalar type per row")
     fn = getattr(_lib.sparse(), f"b200sp_spgemm_jacobi_{_sfx(A.values)}_i32")
-    check(fn(sh._plan, _stream(), A.numRows(), A.numCols(), B.numCols(), _ptr(A.row_map), _ptr(A.entries), _ptr(A.values),
-             _ptr(B.row_map), _ptr(B.entries), _ptr(B.values), _ptr(Cm.row_map), _ptr(Cm.entries), _ptr(Cm.values), omega,
+    check(fn(sh._plan, _stream(), A.numRows(), A.numCols(), B.numCols(), _idx(A.row_map), _idx(A.entries), _ptr(A.values),
+             _idx(B.row_map), _idx(B.entries), _ptr(B.values), _idx(Cm.row_map), _idx(Cm.entries), _ptr(Cm.values), omega,
              _ptr(dv.contiguous())))
     sh._numeric = True
     sh._entries = True
@@ -667,14 +711,14 @@ def sort_crs_matrix(A_or_rowmap, entries=None, values=None):
         return
     m = max(rowmap.numel() - 1, 0)
     fn = getattr(_lib.sparse(), f"b200sp_sort_crs_{_sfx(values)}_i32")
-    check(fn(_stream(), m, _ptr(rowmap), _ptr(entries), _ptr(values)))
+    check(fn(_stream(), m, _idx(rowmap), _idx(entries), _ptr(values)))
 
 
 def sort_crs_graph(rowmap, entries):
     """SortCrs.hpp:209-300."""
     if entries.numel() <= 1:
         return
-    check(_lib.sparse().b200sp_sort_crs_graph_i32(_stream(), max(rowmap.numel() - 1, 0), _ptr(rowmap), _ptr(entries)))
+    check(_lib.sparse().b200sp_sort_crs_graph_i32(_stream(), max(rowmap.numel() - 1, 0), _idx(rowmap), _idx(entries)))
 
 
 def sort_and_merge_matrix(A):
@@ -688,13 +732,13 @@ def sort_and_merge_matrix(A):
     rowmap_out = torch.empty(m + 1, dtype=torch.int32, device=dev)
     merged = C.c_int64(0)
     check(getattr(_lib.sparse(), f"b200sp_sort_and_merge_count_{sfx}_i32")(
-        _stream(), m, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), C.c_void_p(rowmap_out.data_ptr()), C.byref(merged)))
+        _stream(), m, _idx(A.row_map), _idx(A.entries), _ptr(A.values), C.c_void_p(rowmap_out.data_ptr()), C.byref(merged)))
     if merged.value == A.nnz():
         return A
     entries_out = torch.empty(merged.value, dtype=torch.int32, device=dev)
     values_out = torch.empty(merged.value, dtype=A.values.dtype, device=dev)
     check(getattr(_lib.sparse(), f"b200sp_sort_and_merge_fill_{sfx}_i32")(
-        _stream(), m, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), _ptr(rowmap_out), _ptr(entries_out), _ptr(values_out)))
+        _stream(), m, _idx(A.row_map), _idx(A.entries), _ptr(A.values), _idx(rowmap_out), _idx(entries_out), _ptr(values_out)))
     return CrsMatrix(rowmap_out, entries_out, values_out, A.numCols())
 
 
@@ -707,13 +751,13 @@ def sort_and_merge_graph(rowmap, entries):
     rowmap_out = torch.empty(m + 1, dtype=torch.int32, device=dev)
     merged = C.c_int64(0)
     lib = _lib.sparse()
-    check(lib.b200sp_sort_and_merge_count_f32_i32(_stream(), m, _ptr(rowmap), _ptr(entries), C.c_void_p(0),
+    check(lib.b200sp_sort_and_merge_count_f32_i32(_stream(), m, _idx(rowmap), _idx(entries), C.c_void_p(0),
                                                   C.c_void_p(rowmap_out.data_ptr()), C.byref(merged)))
     if merged.value == entries.numel():
         return rowmap, entries
     entries_out = torch.empty(merged.value, dtype=torch.int32, device=dev)
-    check(lib.b200sp_sort_and_merge_fill_f32_i32(_stream(), m, _ptr(rowmap), _ptr(entries), C.c_void_p(0), _ptr(rowmap_out),
-                                                 _ptr(entries_out), C.c_void_p(0)))
+    check(lib.b200sp_sort_and_merge_fill_f32_i32(_stream(), m, _idx(rowmap), _idx(entries), C.c_void_p(0), _idx(rowmap_out),
+                                                 _idx(entries_out), C.c_void_p(0)))
     return rowmap_out, entries_out
 
 
@@ -726,7 +770,7 @@ def transpose_matrix(A):
     t_entries = torch.empty(A.nnz(), dtype=torch.int32, device=dev)
     t_values = torch.empty(A.nnz(), dtype=A.values.dtype, device=dev)
     check(getattr(_lib.sparse(), f"b200sp_transpose_{_sfx(A.values)}_i32")(
-        _stream(), m, n, _ptr(A.row_map), _ptr(A.entries), _ptr(A.values), C.c_void_p(t_rowmap.data_ptr()), _ptr(t_entries),
+        _stream(), m, n, _idx(A.row_map), _idx(A.entries), _ptr(A.values), C.c_void_p(t_rowmap.data_ptr()), _idx(t_entries),
         _ptr(t_values)))
     return CrsMatrix(t_rowmap, t_entries, t_values, m)
 
@@ -738,8 +782,8 @@ def spadd_symbolic_views(kh, m, n, a_rowmap, a_entries, b_rowmap, b_entries, c_r
     if ah is None:
         raise B200SparseInvalidArgument("spadd_symbolic: create_spadd_handle() was not called")
     c_nnz = C.c_int64(0)
-    check(_lib.sparse().b200sp_spadd_symbolic_i32(ah._plan, _stream(), m, n, _ptr(a_rowmap), _ptr(a_entries), _ptr(b_rowmap),
-                                                  _ptr(b_entries), _ptr(c_rowmap), C.byref(c_nnz)))
+    check(_lib.sparse().b200sp_spadd_symbolic_i32(ah._plan, _stream(), m, n, _idx(a_rowmap), _idx(a_entries), _idx(b_rowmap),
+                                                  _idx(b_entries), _idx(c_rowmap), C.byref(c_nnz)))
     ah._c_nnz = c_nnz.value
     ah._symbolic, ah._numeric = True, False
 
@@ -750,8 +794,8 @@ def spadd_numeric_views(kh, m, n, a_rowmap, a_entries, a_values, alpha, b_rowmap
     if ah is None or not ah.is_symbolic_called():
         raise B200SparseError("spadd_numeric: call spadd_symbolic first")
     fn = getattr(_lib.sparse(), f"b200sp_spadd_numeric_{_sfx(c_values)}_i32")
-    check(fn(ah._plan, _stream(), m, n, _ptr(a_rowmap), _ptr(a_entries), _ptr(a_values), alpha, _ptr(b_rowmap), _ptr(b_entries),
-             _ptr(b_values), beta, _ptr(c_rowmap), _ptr(c_entries), _ptr(c_values)))
+    check(fn(ah._plan, _stream(), m, n, _idx(a_rowmap), _idx(a_entries), _ptr(a_values), alpha, _idx(b_rowmap), _idx(b_entries),
+             _ptr(b_values), beta, _idx(c_rowmap), _idx(c_entries), _ptr(c_values)))
     ah._numeric = True
 
 

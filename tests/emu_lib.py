@@ -87,6 +87,53 @@ def spmv(plan, mode, nrows, ncols, rp, ci, v, x, y, alpha, beta):
           scalar(v.dtype, beta), ptr(y)))
 
 
+class Spmv64Plan:
+    def __init__(self, algo=0, window=None):
+        self.h = C.c_void_p()
+        ok(lib().b200sp_spmv64_plan_create(C.byref(self.h), algo))
+        if window is not None:
+            ok(lib().b200sp_spmv64_plan_set_window(self.h, C.c_int64(window)))
+
+    def close(self):
+        if self.h:
+            ok(lib().b200sp_spmv64_plan_destroy(self.h, None))
+            self.h = C.c_void_p()
+
+    def windows(self):
+        return lib().b200sp_spmv64_plan_windows(self.h)
+
+    def kernel(self):
+        return lib().b200sp_spmv64_last_kernel(self.h).decode()
+
+
+def spmv64_rc(plan, mode, nrows, ncols, rp64, ci, v, x, y, alpha, beta):
+    """64-bit offsets (rp64: int64), 32- or 64-bit columns by ci.dtype; returns the status code."""
+    assert rp64.dtype == np.int64 and ci.dtype in (np.int32, np.int64)
+    fn = getattr(lib(), "b200sp_spmv_%s_i64" % sfx(v.dtype))
+    return fn(plan.h, None, mode.encode(), C.c_int64(nrows), C.c_int64(ncols), C.c_int64(len(ci)), scalar(v.dtype, alpha), ptr(rp64),
+              ptr(ci), 8 * ci.dtype.itemsize, ptr(v), ptr(x), scalar(v.dtype, beta), ptr(y))
+
+
+def spmv64(plan, *a):
+    ok(spmv64_rc(plan, *a))
+
+
+def spmm64(plan, mode, nrows, ncols, rp64, ci, v, X, Y, alpha, beta):
+    fn = getattr(lib(), "b200sp_spmm_%s_i64" % sfx(v.dtype))
+    it = v.dtype.itemsize
+
+    def lay(a):
+        if a.strides[1] == it:
+            return a.strides[0] // it, 1
+        assert a.strides[0] == it
+        return a.strides[1] // it, 0
+
+    ldx, rmx = lay(X)
+    ldy, rmy = lay(Y)
+    ok(fn(plan.h, None, mode.encode(), C.c_int64(nrows), C.c_int64(ncols), C.c_int64(len(ci)), X.shape[1], scalar(v.dtype, alpha),
+          ptr(rp64), ptr(ci), 8 * ci.dtype.itemsize, ptr(v), ptr(X), C.c_int64(ldx), rmx, scalar(v.dtype, beta), ptr(Y), C.c_int64(ldy), rmy))
+
+
 def spmm(plan, mode, nrows, ncols, rp, ci, v, X, Y, alpha, beta):
     """X, Y: 2-D numpy arrays, either C- or F-ordered (LayoutRight / LayoutLeft); strides are passed in elements."""
     fn = getattr(lib(), "b200sp_spmm_%s_i32" % sfx(v.dtype))

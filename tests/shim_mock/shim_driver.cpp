@@ -42,6 +42,14 @@ using SV    = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UM>;
 
 static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XVec, YVec>::value, "rank-1 specialisation must be available");
 static_assert(Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd, AMat, XMV, YMV>::value, "rank-2 specialisation must be available");
+// 64-bit offsets: (int64_t, size_t) -- the cuSPARSE slot's other instantiation -- and (int, size_t)
+using Hnd64  = Impl::SPMVHandleImpl<Kokkos::Cuda, Kokkos::CudaSpace, double, size_t, int64_t>;
+using AMat64 = CrsMatrix<const double, const int64_t, Dev, UM, const size_t>;
+using Hnd64i = Impl::SPMVHandleImpl<Kokkos::Cuda, Kokkos::CudaSpace, double, size_t, int>;
+using AMat64i = CrsMatrix<const double, const int, Dev, UM, const size_t>;
+static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd64, AMat64, XVec, YVec>::value && Impl::spmv_mv_tpl_spec_avail<Kokkos::Cuda, Hnd64, AMat64, XMV, YMV>::value,
+              "(int64_t, size_t) specialisations must be available");
+static_assert(Impl::spmv_tpl_spec_avail<Kokkos::Cuda, Hnd64i, AMat64i, XVec, YVec>::value, "(int, size_t) specialisation must be available");
 using DINV  = Kokkos::View<const double**, KokkosKernels::default_layout, Dev, UM>;
 static_assert(Impl::spgemm_jacobi_tpl_spec_avail<KH, CIV, CIV, CSV, CIV, CIV, CSV, IV, IV, SV, DINV>::value, "spgemm_jacobi must be available");
 using XGS   = Kokkos::View<double**, KokkosKernels::default_layout, Dev, UM>;
@@ -68,11 +76,13 @@ T* to_dev(const std::vector<T>& h) {
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
   bool with_bsr = false, with_jacobi = false, with_gs = false, with_gmres = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
+  bool with_spmv64 = false;                                                          // --spmv64: the 64-bit-offset specialisations
   for (int a = 1; a < argc; ++a) {
     with_bsr |= std::string(argv[a]) == "--bsr";
     with_jacobi |= std::string(argv[a]) == "--jacobi";
     with_gs |= std::string(argv[a]) == "--gs";
     with_gmres |= std::string(argv[a]) == "--gmres";
+    with_spmv64 |= std::string(argv[a]) == "--spmv64";
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -134,6 +144,64 @@ int main(int argc, char** argv) {
     cudaFree(d_X);
     cudaFree(d_Y);
   }  // handle destructor frees the plan stream-ordered
+  if (with_spmv64) {
+    // the same matrix with size_t offsets and int64_t (then int) ordinals, through the 64-bit specialisations
+    std::vector<size_t> rp64(rp.begin(), rp.end());
+    std::vector<int64_t> ci64(ci.begin(), ci.end());
+    size_t* d_rp64  = to_dev(rp64);
+    int64_t* d_ci64 = to_dev(ci64);
+    int f64m = 0;
+    auto check = [&](const char* what) {
+      exec.fence();
+      std::vector<double> y(n);
+      cudaMemcpy(y.data(), d_y, sizeof(double) * n, cudaMemcpyDeviceToHost);
+      int bad = 0;
+      for (int i = 0; i < n; ++i) {
+        double s = 0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) s += va[k] * x[ci[k]];
+        const double e = 0.5 * y0[i] + 2.0 * s;
+        if (std::fabs(y[i] - e) > 1e-12 * (1 + std::fabs(e))) ++bad;
+      }
+      std::printf("spmv rank-1 %s : %d mismatches\n", what, bad);
+      f64m += bad;
+    };
+    {
+      Hnd64 handle(SPMV_DEFAULT);
+      AMat64 A(n, n, ci.size(), d_va, d_rp64, d_ci64);
+      cudaMemcpy(d_y, y0.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+      Impl::SPMV<Kokkos::Cuda, Hnd64, AMat64, XVec, YVec>::spmv(exec, &handle, "N", 2.0, A, XVec(d_x, n), 0.5, YVec(d_y, n));
+      check("(int64_t, size_t) through SPMV<...,true>::spmv");
+      // rank 2, LayoutLeft, 'T', on the same handle's second slot
+      const int k = 2;
+      std::vector<double> X(n * k), Y(n * k, 0.0), E(n * k, 0.0);
+      for (int j = 0; j < k; ++j)
+        for (int i = 0; i < n; ++i) X[j * n + i] = x[i] * (j + 2);
+      double *d_X = to_dev(X), *d_Y = to_dev(Y);
+      Impl::SPMV_MV<Kokkos::Cuda, Hnd64, AMat64, XMV, YMV>::spmv_mv(exec, &handle, "T", 1.0, A, XMV(d_X, n, k), 0.0, YMV(d_Y, n, k));
+      exec.fence();
+      cudaMemcpy(Y.data(), d_Y, sizeof(double) * n * k, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < n; ++i)
+        for (int q = rp[i]; q < rp[i + 1]; ++q)
+          for (int j = 0; j < k; ++j) E[j * n + ci[q]] += va[q] * X[j * n + i];
+      int bad = 0;
+      for (int i = 0; i < n * k; ++i)
+        if (std::fabs(Y[i] - E[i]) > 1e-12 * (1 + std::fabs(E[i]))) ++bad;
+      std::printf("spmv rank-2 'T' (int64_t, size_t) through SPMV_MV<...,false,true>::spmv_mv : %d mismatches\n", bad);
+      f64m += bad;
+      cudaFree(d_X);
+      cudaFree(d_Y);
+    }
+    {
+      Hnd64i handle(SPMV_DEFAULT);
+      AMat64i A(n, n, ci.size(), d_va, d_rp64, d_ci);
+      cudaMemcpy(d_y, y0.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+      Impl::SPMV<Kokkos::Cuda, Hnd64i, AMat64i, XVec, YVec>::spmv(exec, &handle, "N", 2.0, A, XVec(d_x, n), 0.5, YVec(d_y, n));
+      check("(int, size_t) through SPMV<...,true>::spmv");
+    }
+    failures += f64m;
+    cudaFree(d_rp64);
+    cudaFree(d_ci64);
+  }
   {
     // C = A*A through the SpGEMM specialisations; check against a host Gustavson product
     KH kh;

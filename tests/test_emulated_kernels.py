@@ -126,6 +126,32 @@ def test_spmv_long_rows_both_strategies(emu, oracle):
             plan.close()
 
 
+def test_spmv_self_tuning_never_changes_a_bit(emu):
+    """An untuned plan runs the tiled kernel, times it, times the row-vector kernel and keeps the faster one: whichever it
+    settles on (a matter of timing, so it may differ from run to run), every call must return the same bits -- also for the
+    rows beyond the tile capacity, which both kernels leave to the CTA-per-row kernel."""
+    rng = np.random.default_rng(8)
+    rows = cols = 9000
+    lens = rng.integers(0, 12, rows)
+    lens[[5, 4000, 8999]] = [3000, 513, 700]
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.int32)
+    assert len(ci) >= 32768  # large enough for the tiled path
+    v = rng.uniform(-1, 1, len(ci))
+    x, y0 = rng.uniform(-1, 1, cols), rng.uniform(-1, 1, rows)
+    plan = E.SpmvPlan()
+    seen, kernels = [], set()
+    for _ in range(6):
+        y = y0.copy()
+        E.spmv(plan, "N", rows, cols, rp, ci, v, x, y, -0.7, 1.3)
+        seen.append(y)
+        kernels.add(plan.kernel().split("<")[0])
+    assert kernels == {"tile", "vector"}
+    for y in seen[1:]:
+        assert np.array_equal(y, seen[0])
+    plan.close()
+
+
 def test_spmv_cached_transpose(emu, oracle):
     rp, ci, v = kk_matrix(2500, 1500, 30000, 10, 300)
     rng = np.random.default_rng(2)
@@ -289,7 +315,7 @@ def test_spadd(emu, oracle, sorted_input, dtype):
     spadd_dense_check(A, B, (rpC, ciC, vC), n, 0.3, -1.7)
 
 
-@pytest.mark.parametrize("suite,order", [("spmv_t", "random:5"), ("crs", "reverse"), ("jacobi", "random:11"), ("spmv_longrows", "reverse")])
+@pytest.mark.parametrize("suite,order", [("spmv_t", "random:5"), ("crs", "reverse"), ("jacobi", "random:11"), ("spmv_longrows", "reverse"), ("spmv64", "random:3")])
 def test_harness_runs_emulated(suite, order):
     """tools/gpu_check.cpp -- the torch-free harness of the GPU calls -- linked against the emulated library: the
     suite EXECUTES (not --dry) and every check is ok.  B200EMU_GUARD puts every device allocation of the harness
@@ -309,9 +335,9 @@ def test_kokkos_shim_driver_emulated():
     BsrMatrix, SPGEMM_JACOBI, GAUSS_SEIDEL_* and GMRES specialisations run end to end on the host."""
     E.harness()  # builds everything under tools/emu/_build
     drv = os.path.join(os.path.dirname(E.harness()), "shim_driver_emu")
-    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 9, out.stdout
+    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 12, out.stdout
 
 
 @pytest.mark.skipif(os.environ.get("B200EMU_NESTED") == "1", reason="this is the nested run")

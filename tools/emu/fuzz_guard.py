@@ -107,6 +107,36 @@ def op_spmv(rng, orc, verbose):
     return ok, f"spmv {mode} {np.dtype(dtype).name} {m}x{n} nnz={len(ci)} {kern}"
 
 
+def op_spmv64(rng, orc, verbose):
+    """64-bit offsets (spmv64.cu): random window limits, 32- or 64-bit columns, rank 1."""
+    dtype = [np.float64, np.float32][rng.integers(0, 2)]
+    big = rng.random() < 0.25
+    m, n = int(rng.integers(0, 30000 if big else 4000)), int(rng.integers(1, 30000 if big else 4000))
+    rp, ci, v = rand_csr(rng, m, n, dtype)
+    rp64 = rp.astype(np.int64)
+    ci_in = ci.astype(np.int64) if rng.random() < 0.5 else ci
+    mode = "NNNCTH"[rng.integers(0, 6)]
+    trans = mode in "TH"
+    nx, ny = (m, n) if trans else (n, m)
+    x = rng.uniform(-1, 1, nx).astype(dtype)
+    y0 = rng.uniform(-1, 1, ny).astype(dtype)
+    alpha, beta = [(1.0, 0.0), (2.5, -0.5), (-1.0, 1.0), (1.0, 0.0), (-0.3, 2.0), (2.5, 0.0), (1.0, 1.0), (0.0, 2.0)][rng.integers(0, 8)]
+    longest = int(np.diff(rp).max()) if m > 0 else 0
+    window = None
+    if rng.random() < 0.8:  # at least the longest row (+3: the window's base is rounded down to a multiple of 4)
+        window = int(max(8, longest + 3, rng.integers(8, max(9, len(ci) // int(rng.integers(1, 40)) + 9))))
+    grp, gci, gv, gx, gy = g(rp64, rng), g(ci_in, rng), g(v, rng), g(x, rng), g(y0, rng)
+    plan = E.Spmv64Plan(int(rng.integers(0, 3)), window=window)
+    for _ in range(4 if rng.random() < 0.3 else 2):
+        gy[...] = y0
+        E.spmv64(plan, mode, m, n, grp, gci, gv, gx, gy, alpha, beta)
+    kern, nw = plan.kernel(), plan.windows()
+    plan.close()
+    exp = orc.spmv_transpose(rp, ci, v, n, x, y0.copy(), alpha, beta) if trans else orc.spmv_serial(rp, ci, v, x, y0.copy(), alpha, beta)
+    ok = scaled_ok(gy, exp, row_scale(rp, ci, v, x, y0, alpha, beta, n, trans), TOL[np.dtype(dtype)])
+    return ok, f"spmv64 {mode} {np.dtype(dtype).name} {m}x{n} nnz={len(ci)} cols{8 * ci_in.dtype.itemsize} window={window} -> {nw}: {kern}"
+
+
 def op_spmm(rng, orc, verbose):
     dtype = [np.float64, np.float32][rng.integers(0, 2)]
     m, n = int(rng.integers(0, 2500)), int(rng.integers(1, 2500))
@@ -304,7 +334,7 @@ def op_gs(rng, orc, verbose):
     return ok, f"gs {np.dtype(dtype).name} n={n} nnz={len(ci)} colors={nc} dir={direction} sweeps={sweeps}"
 
 
-OPS = {"gs": op_gs, "spmv": op_spmv, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
+OPS = {"gs": op_gs, "spmv": op_spmv, "spmv64": op_spmv64, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
 
 
 def main():

@@ -6,7 +6,7 @@
 // the oracle (the checker -- never the thing measured).  Each suite runs in a forked child so that a
 // faulting kernel cannot take the other suites down; every check appends one JSON line to --out.
 //
-//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep jacobi spmv_longrows
+//   gpu_check [--out FILE] [--suite NAME]... [--big]      suites: spgemm crs spgemm_c4 crs_big spmm spmv_t spmm_sweep jacobi spmv_longrows bsr cg solvers spmv64
 //
 // Exit code: number of failed suites.
 #include <cuda_runtime.h>
@@ -1584,6 +1584,145 @@ static void suite_spmv_longrows() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// suite: spmv64 -- SpMV on 64-bit offsets (spmv64.cu).  (1) a stencil matrix cut into many small windows and into one: equal
+// bits to the 32-bit entry point, timings side by side (the windows must cost nothing but their launches); (2) with --big, a
+// matrix PAST 2^31 entries: B = lap27(128) stacked K times (A = [B; B; ...], K*mB rows, same columns), entries and values
+// replicated on the device, the int64 row map computed on the host; every block of y must equal, bit for bit, the 32-bit SpMV
+// of B, which is checked against the oracle.  26 GB of matrix for fp64 + int32 columns.
+// ------------------------------------------------------------------------------------------------
+static void suite_spmv64() {
+  // B200SP_SPMV64_SMALL=1: the --big logic on a small grid with a lowered window (what the CPU emulation can run)
+  const bool small = getenv("B200SP_SPMV64_SMALL") != nullptr;
+  {
+    Csr<double> A = gen_lap27<double>(g_big && !small ? 100 : 30, 2);
+    const int n = A.m;
+    Rng r(77);
+    std::vector<double> x((size_t)n), y0((size_t)n), yref;
+    for (auto& t : x) t = 2 * r.u01() - 1;
+    for (auto& t : y0) t = 2 * r.u01() - 1;
+    const double alpha = 1.5, beta = -0.25;
+    yref = y0;
+    okk_spmv_serial_f64(A.m, A.rp.data(), A.ci.data(), A.v.data(), x.data(), yref.data(), alpha, beta);
+    std::vector<int64_t> rp64(A.rp.begin(), A.rp.end()), ci64(A.ci.begin(), A.ci.end());
+    Dev<int> rp(A.rp), ci(A.ci);
+    Dev<int64_t> drp64(rp64), dci64(ci64);
+    Dev<double> v(A.v), dx(x), dy((size_t)n);
+    auto run = [&](const char* what, std::function<int()> call, std::vector<double>* out) {
+      float best = 1e30f;
+      for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaMemcpy(dy.p, y0.data(), y0.size() * sizeof(double), cudaMemcpyHostToDevice));
+        Timer t;
+        t.start();
+        SP(call());
+        const float ms = t.stop_ms();
+        if (rep > 0) best = std::min(best, ms);
+      }
+      *out = dy.host();
+      (void)what;
+      return best;
+    };
+    b200sp_spmv_plan* p32 = nullptr;
+    SP(b200sp_spmv_plan_create(&p32, 0));
+    std::vector<double> g32;
+    const float ms32 = run("i32", [&] { return b200sp_spmv_f64_i32(p32, nullptr, 'N', n, n, A.nnz(), alpha, rp.p, ci.p, v.p, dx.p, beta, dy.p); }, &g32);
+    double worst = 0;
+    for (size_t i = 0; i < g32.size(); ++i) worst = std::max(worst, std::fabs(g32[i] - yref[i]) / std::max(1.0, std::fabs(yref[i])));
+    record("i32_vs_oracle", worst <= 1e-12, "lap27 x 2 dof, %d rows, %lld entries: %.3f ms, max rel err %.2e, kernel %s", n, (long long)A.nnz(), ms32,
+           worst, g_dry ? "-" : b200sp_spmv_last_kernel(p32));
+    for (int bits : {32, 64})
+      for (int64_t window : {(int64_t)0, (int64_t)A.nnz() / 7 + 11}) {
+        b200sp_spmv64_plan* p64 = nullptr;
+        SP(b200sp_spmv64_plan_create(&p64, 0));
+        if (window) SP(b200sp_spmv64_plan_set_window(p64, window));
+        std::vector<double> g64;
+        const void* cols = bits == 64 ? (const void*)dci64.p : (const void*)ci.p;
+        const float ms64 = run("i64", [&] { return b200sp_spmv_f64_i64(p64, nullptr, 'N', n, n, A.nnz(), alpha, drp64.p, cols, bits, v.p, dx.p, beta, dy.p); }, &g64);
+        const int64_t diff = g_dry ? 0 : count_diff(g64, g32);
+        char nm[96];
+        snprintf(nm, sizeof(nm), "cols%d/%s", bits, window ? "8_windows" : "1_window");
+        record(nm, diff == 0 && (g_dry || b200sp_spmv64_plan_windows(p64) == (window ? 8 : 1)),
+               "%d window(s), %.3f ms (32-bit entry %.3f ms), entries differing from the 32-bit result: %lld; %s", g_dry ? 0 : b200sp_spmv64_plan_windows(p64),
+               ms64, ms32, (long long)diff, g_dry ? "-" : b200sp_spmv64_last_kernel(p64));
+        // transposed: accumulated window by window
+        std::vector<double> yt = y0;
+        okk_spmv_transpose_f64(A.m, A.n, A.rp.data(), A.ci.data(), A.v.data(), x.data(), yt.data(), alpha, beta);
+        CK(cudaMemcpy(dy.p, y0.data(), y0.size() * sizeof(double), cudaMemcpyHostToDevice));
+        SP(b200sp_spmv_f64_i64(p64, nullptr, 'T', n, n, A.nnz(), alpha, drp64.p, cols, bits, v.p, dx.p, beta, dy.p));
+        std::vector<double> gt = dy.host();
+        double wt = 0;
+        for (size_t i = 0; i < gt.size(); ++i) wt = std::max(wt, std::fabs(gt[i] - yt[i]) / std::max(1.0, std::fabs(yt[i])));
+        snprintf(nm, sizeof(nm), "cols%d/%s/transposed", bits, window ? "8_windows" : "1_window");
+        record(nm, g_dry || wt <= 1e-12, "max rel err vs the oracle %.2e", wt);
+        if (!g_dry) b200sp_spmv64_plan_destroy(p64, nullptr);
+      }
+    if (!g_dry) b200sp_spmv_plan_destroy(p32, nullptr);
+  }
+  if (!g_big) {
+    record("past_2^31_entries", true, "skipped (needs --big: 26 GB of matrix)");
+    return;
+  }
+  // ---- past 2^31 entries
+  Csr<double> B = gen_lap27<double>(small ? 12 : 128, 1);  // 2,097,152 rows, 55.7 M entries
+  const int mB = B.m, nB = B.n;
+  const int64_t nzB = B.nnz();
+  const int K = small ? 5 : (int)(((int64_t)1 << 31) / nzB) + 2;
+  const int64_t nnz = nzB * K;
+  const int64_t m = (int64_t)mB * K;
+  Rng r(5);
+  std::vector<double> x((size_t)nB), yB((size_t)mB, 0.0);
+  for (auto& t : x) t = 2 * r.u01() - 1;
+  okk_spmv_serial_f64(mB, B.rp.data(), B.ci.data(), B.v.data(), x.data(), yB.data(), 1.0, 0.0);
+  std::vector<int64_t> rp64((size_t)m + 1);
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i <= mB; ++i) rp64[(size_t)k * mB + i] = (int64_t)k * nzB + B.rp[(size_t)i];
+  Dev<int> rpB(B.rp), ciB(B.ci);
+  Dev<double> vB(B.v), dx(x), dyB((size_t)mB), dy((size_t)m);
+  Dev<int64_t> drp64(rp64);
+  Dev<int> ci((size_t)nnz);
+  Dev<double> v((size_t)nnz);
+  for (int k = 0; k < K; ++k) {
+    CK(cudaMemcpy(ci.p + (size_t)k * nzB, ciB.p, sizeof(int) * (size_t)nzB, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(v.p + (size_t)k * nzB, vB.p, sizeof(double) * (size_t)nzB, cudaMemcpyDeviceToDevice));
+  }
+  b200sp_spmv_plan* p32 = nullptr;
+  SP(b200sp_spmv_plan_create(&p32, 0));
+  float msB = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    Timer t;
+    t.start();
+    SP(b200sp_spmv_f64_i32(p32, nullptr, 'N', mB, nB, nzB, 1.0, rpB.p, ciB.p, vB.p, dx.p, 0.0, dyB.p));
+    const float ms = t.stop_ms();
+    if (rep > 0) msB = std::min(msB, ms);
+  }
+  std::vector<double> gB = dyB.host();
+  double worst = 0;
+  for (size_t i = 0; i < gB.size(); ++i) worst = std::max(worst, std::fabs(gB[i] - yB[i]) / std::max(1.0, std::fabs(yB[i])));
+  record("block_vs_oracle", worst <= 1e-12, "one block (lap27): %d rows, %lld entries, %.3f ms, max rel err %.2e", mB, (long long)nzB, msB, worst);
+  b200sp_spmv64_plan* p64 = nullptr;
+  SP(b200sp_spmv64_plan_create(&p64, 0));
+  if (small) SP(b200sp_spmv64_plan_set_window(p64, nzB + nzB / 2));
+  float ms64 = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    dy.fill_bytes(0xFF);
+    Timer t;
+    t.start();
+    SP(b200sp_spmv_f64_i64(p64, nullptr, 'N', m, nB, nnz, 1.0, drp64.p, ci.p, 32, v.p, dx.p, 0.0, dy.p));
+    const float ms = t.stop_ms();
+    if (rep > 0) ms64 = std::min(ms64, ms);
+  }
+  int64_t diff = 0;
+  for (int k = 0; k < K; ++k) diff += count_diff(dy.host((size_t)k * mB, (size_t)mB), gB);
+  const double gbs = ((double)nnz * 12 + (double)m * 12 + (double)nB * 8) / (ms64 * 1e-3) / 1e9;
+  record("past_2^31_entries", diff == 0 && b200sp_spmv64_plan_windows(p64) >= 2,
+         "%d stacked blocks: %lld rows, %lld entries (2^31 = 2147483648), %d windows, %.3f ms = %.0f GB/s algorithmic (%.2f x the block's %.3f ms x %d), "
+         "entries differing from the block result: %lld; %s",
+         K, (long long)m, (long long)nnz, b200sp_spmv64_plan_windows(p64), ms64, gbs, ms64 / (msB * K), msB, K, (long long)diff,
+         b200sp_spmv64_last_kernel(p64));
+  b200sp_spmv64_plan_destroy(p64, nullptr);
+  b200sp_spmv_plan_destroy(p32, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct Suite {
   const char* name;
   std::function<void()> fn;
@@ -1593,7 +1732,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}, {"solvers", suite_solvers, 90}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}, {"solvers", suite_solvers, 90}, {"spmv64", suite_spmv64, 120}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];

@@ -1,21 +1,21 @@
 #!/bin/bash
 # First GPU call of the next round (single B200, nothing else on the GPU), most valuable first:
 #   1. first GPU run of everything written after round 1's GPU minutes were spent (validated under the CPU emulation only):
-#      harness suites bsr / cg / jacobi / solvers, then `pytest -m gpu_next` (BsrMatrix SpMV/SpMM, CG / PCG, GMRES, Gauss-Seidel, spgemm_jacobi, shim --bsr --jacobi)
+#      harness suites bsr / cg / jacobi / solvers / spmv64 (with --big: a matrix past 2^31 entries), then `pytest -m gpu_next` (BsrMatrix SpMV/SpMM, CG / PCG, GMRES, Gauss-Seidel, spgemm_jacobi, shim --bsr --jacobi)
 #   2. clean timings of all harness suites at full size (config 4 SpGEMM incl. numeric variants 4-6 / symbolic 2, config 3 SpMM
 #      incl. the row-limit sweep), which round 1 only measured under contention or not at all
 #   3. ncu: launch list + one full capture per kernel VERDICT is likely to name (never bench numbers)
 #   4. the headline bench (SpMV config 2) on the same box
 #   gpurun --timeout 1200 -- 'bash tools/round2_first_call.sh'
 # Outputs land in gpurun_out/ (copy the summaries to profiles/ afterwards).  On success of step 1 change `gpu_next` to `gpu`
-# in tests/test_gpu_{jacobi,bsr,cg,gmres,gs}.py and tests/test_shim.py.
+# in tests/test_gpu_{jacobi,bsr,cg,gmres,gs,spmv64}.py and tests/test_shim.py.
 set -u
 mkdir -p gpurun_out
 G=./kokkos-kernels_b200/lib/gpu_check
 O=gpurun_out/r02_gpu_check_first.jsonl
 L=gpurun_out/r02_gpu_check_first.log
 : > $L
-for s in bsr cg jacobi solvers; do $G --suite $s --out $O >> $L 2>&1; done
+for s in bsr cg jacobi solvers spmv64; do $G --suite $s --out $O >> $L 2>&1; done
 python -m pytest tests -x -q -m gpu_next > gpurun_out/r02_pytest_gpu_next.log 2>&1; tail -n 3 gpurun_out/r02_pytest_gpu_next.log
 $G --big --out $O >> $L 2>&1
 $G --suite spmm --spmm-scale 23 --out $O >> $L 2>&1
