@@ -1732,7 +1732,7 @@ struct Suite {
 int main(int argc, char** argv) {
   std::vector<Suite> all = {{"spgemm", suite_spgemm, 60},       {"crs", suite_crs, 45},       {"spgemm_c4", suite_spgemm_c4, 60},
                             {"crs_big", suite_crs_big, 60},     {"spmv_t", suite_spmv_t, 45}, {"spmm", suite_spmm, 60},
-                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}, {"solvers", suite_solvers, 90}, {"spmv64", suite_spmv64, 120}};
+                            {"spmm_sweep", suite_spmm_sweep, 60}, {"jacobi", suite_jacobi, 60}, {"spmv_longrows", suite_spmv_longrows, 60}, {"bsr", suite_bsr, 60}, {"cg", suite_cg, 60}, {"solvers", suite_solvers, 90}, {"spmv64", suite_spmv64, 300}};
   std::vector<std::string> pick;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--out") && i + 1 < argc) g_out = argv[++i];
