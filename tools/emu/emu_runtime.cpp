@@ -214,7 +214,16 @@ static void* guarded_block(size_t bytes, size_t align) {
   return user;
 }
 
+// live "device" allocations (both modes): b200emu_live_allocations() lets a test assert that destroying a plan gives back
+// everything the library allocated for it -- a leak a long-running solver would pay for in HBM
+static std::map<void*, size_t> g_live;
+static void* device_alloc_impl(size_t bytes);
 void* device_alloc(size_t bytes) {
+  void* p = device_alloc_impl(bytes);
+  if (p) g_live[p] = bytes;
+  return p;
+}
+static void* device_alloc_impl(size_t bytes) {
   if (!guard_mode()) {
     void* p = nullptr;
     if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
@@ -235,6 +244,10 @@ void* device_alloc(size_t bytes) {
 }
 void device_free(void* p) {
   if (!p) return;
+  if (g_live.erase(p) == 0) {
+    fprintf(stderr, "b200emu: cudaFree of a pointer cudaMalloc did not return (or freed twice)\n");
+    abort();
+  }
   if (!guard_mode()) {
     free(p);
     return;
@@ -474,6 +487,12 @@ extern "C" {
 __attribute__((visibility("default"))) void* b200emu_guarded_alloc(size_t bytes, size_t align) {
   if (align == 0 || (align & (align - 1)) != 0) return nullptr;
   return b200emu::guarded_block(bytes, align);
+}
+__attribute__((visibility("default"))) long long b200emu_live_allocations(long long* bytes) {
+  long long b = 0;
+  for (auto& kv : b200emu::g_live) b += (long long)kv.second;
+  if (bytes) *bytes = b;
+  return (long long)b200emu::g_live.size();
 }
 __attribute__((visibility("default"))) void b200emu_guarded_free(void* p) {
   auto it = b200emu::g_guarded.find(p);

@@ -347,12 +347,19 @@ def main():
     ops = a.ops.split(",")
     orc = oracle_lib.Oracle()
     bad = 0
+    L = E.lib()
+    L.b200emu_live_allocations.restype = C.c_longlong
+    L.b200emu_live_allocations.argtypes = [C.c_void_p]
     for seed in range(lo, hi):
         for name in ops:
             rng = np.random.default_rng([seed, sorted(OPS).index(name)])
             print(f"[fuzz] seed {seed} {name} ...", end=" ", flush=True)  # printed BEFORE the call: a fault names its seed
+            live0 = L.b200emu_live_allocations(None)
             ok, what = OPS[name](rng, orc, a.v)
             E.guarded_release()
+            leaked = L.b200emu_live_allocations(None) - live0  # plans are closed inside the op: nothing may stay allocated
+            if leaked:
+                ok, what = False, what + f"  LEAK: {leaked} device blocks still allocated"
             print(("ok   " if ok else "MISMATCH ") + what, flush=True)
             bad += 0 if ok else 1
     print(f"[fuzz] seeds {lo}:{hi} ops {','.join(ops)}: {bad} mismatches")
