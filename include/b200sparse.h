@@ -388,6 +388,45 @@ int b200sp_gs_get_coloring(const b200sp_gs_plan* plan, int* num_colors, const in
 int b200sp_gs_copy_coloring(const b200sp_gs_plan* plan, void* stream, int* colors_host, int* color_ptr_host,
                             int* color_rows_host);
 
+/* ---- Two-stage Gauss-Seidel (the Gauss-Seidel that is a loop of SpMVs) -------------------------
+ * gauss_seidel_symbolic / numeric / apply with a handle created as GS_TWOSTAGE and inner Jacobi-Richardson sweeps
+ * (TwostageGaussSeidel, sparse/impl/KokkosSparse_twostage_gauss_seidel_impl.hpp: symbolic :544-697, numeric :700-772, apply
+ * :778-1035; handle sparse/src/KokkosSparse_gauss_seidel_handle.hpp:513-673).  A (n x ncols, ncols >= n; columns >= n address
+ * ghost entries of x, read and never written) = L + D + U on its square part.  symbolic builds L and U (and, in the compact
+ * form, the complements La / Ua) in A's storage order; numeric takes D = 1 / a_ii -- or given_inverse_diagonal (n entries,
+ * the reference's handle->set_diagonal... path, NULL for none) -- and scales L, U by it; apply runs
+ *   max(outer sweeps, num_iter) sweeps (symmetric: each a forward then a backward one), per sweep
+ *     R = B - A x                          (compact form: R = B - Ua x or La x, + (1/omega - 1) Da.*x)
+ *     T = D.*R; R = gamma T;  inner sweeps:  Z = T - omega (L or U) R;  Z = gamma Z + (1 - gamma) R;  R = Z
+ *     x += omega Z                         (compact form: x = omega Z)
+ * with the library's SpMV for every product (plans of A, L, U, La, Ua kept in this plan) and the KokkosBlas steps in between
+ * evaluated expression by expression as the reference does.  x: ncols x nrhs, b: n x nrhs, column-major with leading
+ * dimensions ldx / ldb (LayoutLeft, the reference's default_layout on the GPU); direction 0 = symmetric, 1 = forward,
+ * 2 = backward; init_zero_x != 0 zeroes x first (and skips the first residual product).  Options (before symbolic for
+ * COMPACT_FORM): KokkosKernelsHandle::set_gs_twostage_compact_form / set_gs_set_num_inner_sweeps / _num_outer_sweeps /
+ * _inner_damp_factor (sparse/src/KokkosKernels_Handle.hpp:639-683); defaults 0, 1, 1, 1.0.  The sptrsv variant
+ * (set_gs_twostage(false, ...)) is not provided.  B200SP_ERR_INVALID_ARGUMENT when a row has no diagonal entry,
+ * B200SP_ERR_STATE when a phase is called before its predecessor or with another matrix.  symbolic synchronises `stream`. */
+#define B200SP_GS2_COMPACT_FORM 1
+#define B200SP_GS2_NUM_INNER_SWEEPS 2
+#define B200SP_GS2_NUM_OUTER_SWEEPS 3
+#define B200SP_GS2_INNER_DAMP_FACTOR 4
+typedef struct b200sp_gs2_plan b200sp_gs2_plan;
+int b200sp_gs2_plan_create(b200sp_gs2_plan** plan);
+int b200sp_gs2_plan_destroy(b200sp_gs2_plan* plan, void* stream);
+int b200sp_gs2_plan_set(b200sp_gs2_plan* plan, int option, double value);
+int b200sp_gs2_symbolic_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx);
+int b200sp_gs2_numeric_f64_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                               const double* vals, const double* given_inverse_diagonal);
+int b200sp_gs2_numeric_f32_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                               const float* vals, const float* given_inverse_diagonal);
+int b200sp_gs2_apply_f64_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                             const double* vals, double* x, int64_t ldx, const double* b, int64_t ldb, int nrhs,
+                             int init_zero_x, double omega, int num_iter, int direction);
+int b200sp_gs2_apply_f32_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                             const float* vals, float* x, int64_t ldx, const float* b, int64_t ldb, int nrhs,
+                             int init_zero_x, float omega, int num_iter, int direction);
+
 /* ---- CG driver (callers of spmv in a loop) ---------------------------------------------------
  * KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false (perf_test/sparse/KokkosSparse_pcg.hpp:248-466;
  * the driver perf_test/sparse/KokkosSparse_pcg.cpp:69-122 calls it with tolerance 1e-7): solves A x = b for a symmetric

@@ -29,6 +29,9 @@ from ._lib import B200SparseError, B200SparseInvalidArgument, check
 
 # SPMVAlgorithm (spmv_handle.hpp:32-47)
 SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH, SPMV_BSR_V41, SPMV_BSR_V42, SPMV_BSR_TC = range(8)
+# GSAlgorithm (sparse/src/KokkosSparse_gauss_seidel_handle.hpp:29): the point (multicolour) algorithm serves GS_DEFAULT / PERMUTED / TEAM,
+# GS_TWOSTAGE is the SpMV-based two-stage method; GS_CLUSTER is not provided
+GS_DEFAULT, GS_PERMUTED, GS_TEAM, GS_CLUSTER, GS_TWOSTAGE = range(5)
 # SPGEMMAlgorithm subset that matters here (spgemm_handle.hpp:44-87)
 SPGEMM_KK, SPGEMM_KK_MEMORY, SPGEMM_KK_SPEED, SPGEMM_KK_LP, SPGEMM_DEBUG, SPGEMM_SERIAL = range(6)
 
@@ -398,6 +401,64 @@ class GaussSeidelHandle:
             pass
 
 
+class TwoStageGaussSeidelHandle:
+    """TwoStageGaussSeidelHandle (sparse/src/KokkosSparse_gauss_seidel_handle.hpp:513-673) with inner Jacobi-Richardson sweeps: owns
+    L, U (and La, Ua in the compact form), the scaled diagonal, the work vectors and the SpMV plans (b200sp_gs2_plan)."""
+
+    def __init__(self):
+        self._plan = C.c_void_p(0)
+        check(_lib.sparse().b200sp_gs2_plan_create(C.byref(self._plan)))
+        self._symbolic = self._numeric = False
+        self.two_stage, self.compact_form, self.num_inner_sweeps, self.num_outer_sweeps, self.inner_omega = True, False, 1, 1, 1.0
+
+    def is_symbolic_called(self): return self._symbolic
+    def is_numeric_called(self): return self._numeric
+
+    def _set(self, option, value):
+        check(_lib.sparse().b200sp_gs2_plan_set(self._plan, option, C.c_double(float(value))))
+
+    def setTwoStage(self, two_stage):
+        if not two_stage:  # the sptrsv variant ("classic" in the reference's unit test) is outside the path
+            raise B200SparseError("b200sparse: two-stage Gauss-Seidel is provided with inner Jacobi-Richardson sweeps only (no sptrsv)")
+        self.two_stage = True
+
+    def isTwoStage(self): return self.two_stage
+
+    def setCompactForm(self, compact_form):
+        self.compact_form = bool(compact_form)
+        self._set(1, self.compact_form)
+        self._symbolic = self._numeric = False
+
+    def isCompactForm(self): return self.compact_form
+
+    def setNumInnerSweeps(self, n):
+        self.num_inner_sweeps = int(n)
+        self._set(2, n)
+
+    def getNumInnerSweeps(self): return self.num_inner_sweeps
+
+    def setNumOuterSweeps(self, n):
+        self.num_outer_sweeps = int(n)
+        self._set(3, n)
+
+    def getNumOuterSweeps(self): return self.num_outer_sweeps
+
+    def setInnerDampFactor(self, g):
+        self.inner_omega = float(g)
+        self._set(4, g)
+
+    def getInnerDampFactor(self): return self.inner_omega
+
+    def __del__(self):
+        try:
+            if self._plan:
+                st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
+                _lib.sparse().b200sp_gs2_plan_destroy(self._plan, st)
+                self._plan = C.c_void_p(0)
+        except Exception:
+            pass
+
+
 def _gs_handle(handle):
     gh = handle.get_gs_handle() if hasattr(handle, "get_gs_handle") else handle
     if gh is None:
@@ -407,23 +468,55 @@ def _gs_handle(handle):
 
 def gauss_seidel_symbolic(handle, num_rows, num_cols, row_map, entries, is_graph_symmetric=True):
     """KokkosSparse::gauss_seidel_symbolic (sparse/src/KokkosSparse_gauss_seidel.hpp:49-110)."""
+    gh = _gs_handle(handle)
+    if isinstance(gh, TwoStageGaussSeidelHandle):
+        check(_lib.sparse().b200sp_gs2_symbolic_i32(gh._plan, _stream(), int(num_rows), int(num_cols), _idx(row_map), _idx(entries)))
+        gh._symbolic, gh._numeric = True, False
+        return
     if num_rows != num_cols:
         raise B200SparseError("b200sparse: point Gauss-Seidel needs a square matrix")
-    gh = _gs_handle(handle)
     check(_lib.sparse().b200sp_gs_symbolic_i32(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), int(bool(is_graph_symmetric))))
     gh._symbolic, gh._numeric = True, False
 
 
-def gauss_seidel_numeric(handle, num_rows, num_cols, row_map, entries, values, is_graph_symmetric=True):
-    """KokkosSparse::gauss_seidel_numeric (:223-290); is_graph_symmetric only matters to symbolic."""
+def gauss_seidel_numeric(handle, num_rows, num_cols, row_map, entries, values, is_graph_symmetric=True, given_inverse_diagonal=None):
+    """KokkosSparse::gauss_seidel_numeric (:223-290, and the overload taking the inverse diagonal :118-221 -- used by the two-stage
+    method only here); is_graph_symmetric only matters to symbolic."""
     gh = _gs_handle(handle)
+    if isinstance(gh, TwoStageGaussSeidelHandle):
+        fn = _lib.sparse().b200sp_gs2_numeric_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs2_numeric_f32_i32
+        check(fn(gh._plan, _stream(), int(num_rows), int(num_cols), _idx(row_map), _idx(entries), _ptr(values), _ptr(given_inverse_diagonal)))
+        gh._numeric = True
+        return
     fn = _lib.sparse().b200sp_gs_numeric_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_numeric_f32_i32
     check(fn(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), _ptr(values)))
     gh._numeric = True
 
 
-def _gs_apply(handle, num_rows, row_map, entries, values, x_lhs, y_rhs, init_zero_x_vector, omega, numIter, direction):
+def _gs2_apply(gh, num_rows, num_cols, row_map, entries, values, x_lhs, y_rhs, init_zero_x_vector, omega, numIter, direction):
+    """rank-1 or rank-2 (columns contiguous: LayoutLeft, the reference's default_layout on the GPU) x (num_cols rows) and y (num_rows)."""
+    if values.dtype != x_lhs.dtype or x_lhs.dtype != y_rhs.dtype or x_lhs.dim() != y_rhs.dim() or x_lhs.dim() not in (1, 2):
+        raise B200SparseError("b200sparse: gauss_seidel_apply needs x, y of the matrix' scalar type, both rank 1 or both rank 2")
+    if x_lhs.shape[0] != num_cols or y_rhs.shape[0] != num_rows:
+        raise B200SparseError("b200sparse: gauss_seidel_apply: x needs num_cols rows, y num_rows")
+    nrhs, ldx, ldy = 1, int(num_cols), int(num_rows)
+    if x_lhs.dim() == 2:
+        nrhs = x_lhs.shape[1]
+        if y_rhs.shape[1] != nrhs or (x_lhs.shape[0] > 1 and x_lhs.stride(0) != 1) or (y_rhs.shape[0] > 1 and y_rhs.stride(0) != 1):
+            raise B200SparseError("b200sparse: two-stage gauss_seidel_apply needs LayoutLeft multivectors with equal column counts")
+        ldx, ldy = (x_lhs.stride(1), y_rhs.stride(1)) if nrhs > 1 else (ldx, ldy)
+    elif x_lhs.stride(0) != 1 or y_rhs.stride(0) != 1:
+        raise B200SparseError("b200sparse: rank-1 x and y must be contiguous")
+    fn = _lib.sparse().b200sp_gs2_apply_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs2_apply_f32_i32
+    check(fn(gh._plan, _stream(), int(num_rows), int(num_cols), _idx(row_map), _idx(entries), _ptr(values), _ptr(x_lhs), ldx, _ptr(y_rhs), ldy,
+             int(nrhs), int(bool(init_zero_x_vector)), omega, int(numIter), direction))
+
+
+def _gs_apply(handle, num_rows, row_map, entries, values, x_lhs, y_rhs, init_zero_x_vector, omega, numIter, direction, num_cols=None):
     gh = _gs_handle(handle)
+    if isinstance(gh, TwoStageGaussSeidelHandle):
+        return _gs2_apply(gh, num_rows, num_rows if num_cols is None else num_cols, row_map, entries, values, x_lhs, y_rhs, init_zero_x_vector,
+                          omega, numIter, direction)
     if values.dtype != x_lhs.dtype or x_lhs.dtype != y_rhs.dtype or x_lhs.dim() != 1 or y_rhs.dim() != 1:
         raise B200SparseError("b200sparse: gauss_seidel_apply needs rank-1 x, y of the matrix' scalar type")
     fn = _lib.sparse().b200sp_gs_apply_f64_i32 if values.dtype == torch.float64 else _lib.sparse().b200sp_gs_apply_f32_i32
@@ -434,17 +527,17 @@ def _gs_apply(handle, num_rows, row_map, entries, values, x_lhs, y_rhs, init_zer
 def symmetric_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
                                  init_zero_x_vector, update_y_vector, omega, numIter):
     """KokkosSparse::symmetric_gauss_seidel_apply (:363-470); update_y_vector is moot (y is never permuted or copied here)."""
-    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 0)
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 0, num_cols)
 
 
 def forward_sweep_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
                                      init_zero_x_vector, update_y_vector, omega, numIter):
-    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 1)
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 1, num_cols)
 
 
 def backward_sweep_gauss_seidel_apply(handle, num_rows, num_cols, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec,
                                       init_zero_x_vector, update_y_vector, omega, numIter):
-    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 2)
+    _gs_apply(handle, num_rows, row_map, entries, values, x_lhs_output_vec, y_rhs_input_vec, init_zero_x_vector, omega, numIter, 2, num_cols)
 
 
 class CGSolveResult:
@@ -575,8 +668,28 @@ class KokkosKernelsHandle:
     def destroy_spadd_handle(self):
         self._ah = None
 
-    def create_gs_handle(self, *args, **kwargs):  # GS_DEFAULT; algorithm / colouring arguments of the reference are accepted and ignored
-        self._gs = GaussSeidelHandle()
+    def create_gs_handle(self, gs_algorithm=GS_DEFAULT, *args, **kwargs):
+        """KokkosKernelsHandle::create_gs_handle(GSAlgorithm, coloring algorithm) (sparse/src/KokkosKernels_Handle.hpp:624-630):
+        GS_DEFAULT / GS_PERMUTED / GS_TEAM -> the point multicolour handle (colouring arguments are accepted and ignored),
+        GS_TWOSTAGE -> the two-stage handle; GS_CLUSTER is not provided."""
+        if gs_algorithm == GS_TWOSTAGE:
+            self._gs = TwoStageGaussSeidelHandle()
+        elif gs_algorithm in (GS_DEFAULT, GS_PERMUTED, GS_TEAM) or not isinstance(gs_algorithm, int):
+            self._gs = GaussSeidelHandle()
+        else:
+            raise B200SparseError("b200sparse: cluster Gauss-Seidel is not provided (point and two-stage are)")
+
+    def get_twostage_gs_handle(self):
+        gh = getattr(self, "_gs", None)
+        if not isinstance(gh, TwoStageGaussSeidelHandle):  # KokkosKernels_Handle.hpp:631-637
+            raise B200SparseError("TwoStageGaussSeidelHandle has not been created, or is set to Default.")
+        return gh
+
+    def set_gs_set_num_outer_sweeps(self, n): self.get_twostage_gs_handle().setNumOuterSweeps(n)
+    def set_gs_set_num_inner_sweeps(self, n): self.get_twostage_gs_handle().setNumInnerSweeps(n)
+    def set_gs_set_inner_damp_factor(self, g): self.get_twostage_gs_handle().setInnerDampFactor(g)
+    def set_gs_twostage(self, two_stage, nrows=0): self.get_twostage_gs_handle().setTwoStage(two_stage)
+    def set_gs_twostage_compact_form(self, compact_form): self.get_twostage_gs_handle().setCompactForm(compact_form)
 
     def get_gs_handle(self):
         return getattr(self, "_gs", None)

@@ -302,3 +302,35 @@ def pcg_solve(plan, gs_plan, rp, ci, v, b, x, maximum_iteration, tolerance, chec
     ok(lib().b200sp_pcg_solve_f64_i32(plan.h, gs_plan.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), ptr(b), ptr(x), maximum_iteration,
                                       C.c_double(tolerance), check_every, C.byref(it), C.byref(nr)))
     return it.value, nr.value
+
+
+class Gs2Plan:
+    """b200sp_gs2_*: two-stage Gauss-Seidel (inner Jacobi-Richardson sweeps)."""
+
+    def __init__(self, compact=False, inner=1, outer=1, gamma=1.0):
+        self.h = C.c_void_p()
+        ok(lib().b200sp_gs2_plan_create(C.byref(self.h)))
+        for opt, val in ((1, float(compact)), (2, float(inner)), (3, float(outer)), (4, float(gamma))):
+            ok(lib().b200sp_gs2_plan_set(self.h, opt, C.c_double(val)))
+
+    def close(self):
+        if self.h:
+            ok(lib().b200sp_gs2_plan_destroy(self.h, None))
+            self.h = C.c_void_p()
+
+    def set(self, option, value):
+        return lib().b200sp_gs2_plan_set(self.h, option, C.c_double(value))
+
+    def symbolic(self, n, ncols, rp, ci):
+        return lib().b200sp_gs2_symbolic_i32(self.h, None, n, ncols, ptr(rp), ptr(ci))
+
+    def numeric(self, n, ncols, rp, ci, v, dinv=None):
+        return getattr(lib(), "b200sp_gs2_numeric_%s_i32" % sfx(v.dtype))(self.h, None, n, ncols, ptr(rp), ptr(ci), ptr(v), ptr(dinv))
+
+    def apply(self, n, ncols, rp, ci, v, x, b, init_zero_x, omega, num_iter, direction):
+        """x: (ncols,) or (ncols, nrhs) F-ordered; b likewise with n rows."""
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        ldx = ncols if x.ndim == 1 else x.strides[1] // x.itemsize
+        ldb = n if b.ndim == 1 else b.strides[1] // b.itemsize
+        return getattr(lib(), "b200sp_gs2_apply_%s_i32" % sfx(v.dtype))(self.h, None, n, ncols, ptr(rp), ptr(ci), ptr(v), ptr(x), C.c_int64(ldx), ptr(b),
+                                                                       C.c_int64(ldb), nrhs, int(init_zero_x), scalar(v.dtype, omega), num_iter, direction)

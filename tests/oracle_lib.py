@@ -67,6 +67,9 @@ class Oracle:
         L.okk_gmres_f32.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]
         L.okk_gs_apply_f64.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f64, i32, i32]
         L.okk_gs_apply_f32.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, f32, i32, i32]
+        L.okk_gs2_apply_f64.argtypes = [i32, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, i32, f64, i32, i32]
+        L.okk_gs2_apply_f32.argtypes = [i32, i32, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, i32, f32, i32, i32]
+        L.okk_gs2_apply_f64.restype = L.okk_gs2_apply_f32.restype = i32
         L.okk_cg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64)]
         L.okk_cg_f64.restype = i32
         L.okk_pcg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64), i32, vp, vp, vp]
@@ -288,6 +291,17 @@ class Oracle:
         """Point Gauss-Seidel sweeps over the given colour sets (direction 0 symmetric, 1 forward, 2 backward); x in place."""
         getattr(self.lib, "okk_gs_apply_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), len(color_ptr) - 1, _p(color_ptr), _p(color_rows),
                                                          _p(dinv), _p(y), _p(x), int(init_zero_x), omega, sweeps, direction)
+        return x
+
+    def gs2_apply(self, rp, ci, v, ncols, x, b, init_zero_x, omega, num_iter, direction, compact=False, inner_sweeps=1, outer_sweeps=1,
+                  gamma=1.0, inverse_diagonal=None):
+        """Two-stage Gauss-Seidel (inner Jacobi-Richardson sweeps; direction 0 symmetric, 1 forward, 2 backward); x (ncols entries)
+        in place.  Raises when a row has no diagonal entry."""
+        rc = getattr(self.lib, "okk_gs2_apply_" + self._sfx(v))(len(rp) - 1, ncols, _p(rp), _p(ci), _p(v), _p(inverse_diagonal), int(compact),
+                                                               inner_sweeps, outer_sweeps, gamma, _p(x), _p(b), int(init_zero_x), omega, num_iter,
+                                                               direction)
+        if rc:
+            raise ValueError(f"row {rc - 1} has no diagonal entry")
         return x
 
     def cg(self, rp, ci, v, b, x, maximum_iteration, tolerance):

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <stdexcept>
 #include <string>
 #include <type_traits>
 
@@ -242,6 +243,8 @@ struct b200sp_spadd_plan;
 extern "C" int b200sp_spadd_plan_destroy(b200sp_spadd_plan*, void*);
 struct b200sp_gs_plan;
 extern "C" int b200sp_gs_plan_destroy(b200sp_gs_plan*, void*);
+struct b200sp_gs2_plan;
+extern "C" int b200sp_gs2_plan_destroy(b200sp_gs2_plan*, void*);
 struct b200sp_spmv_plan;
 struct b200sp_bsr_plan;
 extern "C" int b200sp_spmv_plan_destroy(b200sp_spmv_plan*, void*);
@@ -304,17 +307,49 @@ struct GmresWrap {
 
 namespace KokkosSparse {
 enum class SparseMatrixFormat { BSR, CRS };  // sparse/src/KokkosSparse_Utils.hpp
-// the PointGaussSeidelHandle members the shim touches (+ the b200_gs_plan member INTEGRATION.md adds)
-struct PointGaussSeidelHandleMock {
-  ~PointGaussSeidelHandleMock() {
-    if (b200_gs_plan) b200sp_gs_plan_destroy(b200_gs_plan, nullptr);
-  }
+// the GaussSeidelHandle hierarchy as far as the shim touches it (sparse/src/KokkosSparse_gauss_seidel_handle.hpp: base :37-330,
+// PointGaussSeidelHandle, TwoStageGaussSeidelHandle :513-673) + the plan members INTEGRATION.md adds
+enum GSAlgorithm { GS_DEFAULT, GS_PERMUTED, GS_TEAM, GS_CLUSTER, GS_TWOSTAGE };
+struct GaussSeidelHandleMock {
+  explicit GaussSeidelHandleMock(GSAlgorithm a) : algorithm_type(a) {}
+  virtual ~GaussSeidelHandleMock() {}
+  GSAlgorithm get_algorithm_type() const { return algorithm_type; }
   bool is_symbolic_called() const { return called_symbolic; }
   bool is_numeric_called() const { return called_numeric; }
   void set_call_symbolic(bool c = true) { called_symbolic = c; }
   void set_call_numeric(bool c = true) { called_numeric = c; }
-  b200sp_gs_plan* b200_gs_plan = nullptr;
+  GSAlgorithm algorithm_type;
   bool called_symbolic = false, called_numeric = false;
+};
+struct PointGaussSeidelHandleMock : GaussSeidelHandleMock {
+  explicit PointGaussSeidelHandleMock(GSAlgorithm a = GS_DEFAULT) : GaussSeidelHandleMock(a) {}
+  ~PointGaussSeidelHandleMock() {
+    if (b200_gs_plan) b200sp_gs_plan_destroy(b200_gs_plan, nullptr);
+  }
+  b200sp_gs_plan* b200_gs_plan = nullptr;
+};
+struct ClusterGaussSeidelHandleMock : GaussSeidelHandleMock {
+  ClusterGaussSeidelHandleMock() : GaussSeidelHandleMock(GS_CLUSTER) {}
+};
+struct TwoStageGaussSeidelHandleMock : GaussSeidelHandleMock {
+  TwoStageGaussSeidelHandleMock() : GaussSeidelHandleMock(GS_TWOSTAGE) {}
+  ~TwoStageGaussSeidelHandleMock() {
+    if (b200_gs2_plan) b200sp_gs2_plan_destroy(b200_gs2_plan, nullptr);
+  }
+  void setTwoStage(bool t) { two_stage = t; }
+  bool isTwoStage() { return two_stage; }
+  void setCompactForm(bool c) { compact_form = c; }
+  bool isCompactForm() { return compact_form; }
+  void setNumOuterSweeps(int n) { num_outer_sweeps = n; }
+  int getNumOuterSweeps() { return num_outer_sweeps; }
+  void setNumInnerSweeps(int n) { num_inner_sweeps = n; }
+  int getNumInnerSweeps() { return num_inner_sweeps; }
+  void setInnerDampFactor(double g) { inner_omega = g; }
+  double getInnerDampFactor() { return inner_omega; }
+  bool two_stage = true, compact_form = false;
+  int num_inner_sweeps = 1, num_outer_sweeps = 1;
+  double inner_omega = 1.0;
+  b200sp_gs2_plan* b200_gs2_plan = nullptr;
 };
 }  // namespace KokkosSparse
 
@@ -360,13 +395,34 @@ struct KokkosKernelsHandle {
   }
   SPGEMMHandleType* sh = nullptr;
   using const_nnz_lno_t = const int;
-  KokkosSparse::PointGaussSeidelHandleMock* get_point_gs_handle() { return gsh; }
-  void create_gs_handle() { gsh = new KokkosSparse::PointGaussSeidelHandleMock(); }
+  // sparse/src/KokkosKernels_Handle.hpp:520-554,624-683: the accessors cast and throw when the handle is of another kind
+  KokkosSparse::GaussSeidelHandleMock* get_gs_handle() { return gsh; }
+  KokkosSparse::PointGaussSeidelHandleMock* get_point_gs_handle() {
+    auto p = dynamic_cast<KokkosSparse::PointGaussSeidelHandleMock*>(gsh);
+    if (gsh && !p) throw std::runtime_error("GaussSeidelHandle exists but is not set up for point-coloring GS.");
+    return p;
+  }
+  KokkosSparse::TwoStageGaussSeidelHandleMock* get_twostage_gs_handle() {
+    auto p = dynamic_cast<KokkosSparse::TwoStageGaussSeidelHandleMock*>(gsh);
+    if (gsh && !p) throw std::runtime_error("GaussSeidelHandle exists but is not set up for two-stage GS.");
+    return p;
+  }
+  void create_gs_handle(KokkosSparse::GSAlgorithm a = KokkosSparse::GS_DEFAULT) {
+    destroy_gs_handle();
+    if (a == KokkosSparse::GS_TWOSTAGE) gsh = new KokkosSparse::TwoStageGaussSeidelHandleMock();
+    else if (a == KokkosSparse::GS_CLUSTER) gsh = new KokkosSparse::ClusterGaussSeidelHandleMock();
+    else gsh = new KokkosSparse::PointGaussSeidelHandleMock(a);
+  }
+  void set_gs_set_num_outer_sweeps(int n) { get_twostage_gs_handle()->setNumOuterSweeps(n); }
+  void set_gs_set_num_inner_sweeps(int n) { get_twostage_gs_handle()->setNumInnerSweeps(n); }
+  void set_gs_set_inner_damp_factor(double g) { get_twostage_gs_handle()->setInnerDampFactor(g); }
+  void set_gs_twostage(bool t, size_t) { get_twostage_gs_handle()->setTwoStage(t); }
+  void set_gs_twostage_compact_form(bool c) { get_twostage_gs_handle()->setCompactForm(c); }
   void destroy_gs_handle() {
     delete gsh;
     gsh = nullptr;
   }
-  KokkosSparse::PointGaussSeidelHandleMock* gsh = nullptr;
+  KokkosSparse::GaussSeidelHandleMock* gsh = nullptr;
   KokkosSparse::GMRESHandleMock* get_gmres_handle() { return gmh; }
   void create_gmres_handle(int m = 50, double tol = 1e-8, int max_restart = 50) { gmh = new KokkosSparse::GMRESHandleMock(m, tol, max_restart); }
   void destroy_gmres_handle() {
@@ -425,6 +481,34 @@ struct GAUSS_SEIDEL_NUMERIC;
 template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a_r, class a_e, class a_v, class x_v, class y_v,
           bool tpl = gauss_seidel_apply_tpl_spec_avail<KH, a_r, a_e, a_v, x_v, y_v>::value, bool eti = true>
 struct GAUSS_SEIDEL_APPLY;
+// the native bodies (tpl = false; sparse/impl/KokkosSparse_gauss_seidel_spec.hpp:153-262): stand-ins that count their calls -- the
+// B200 specialisations forward what they do not serve (cluster Gauss-Seidel, the sptrsv variant of the two-stage method)
+inline int& mock_native_gs_calls() {
+  static int n = 0;
+  return n;
+}
+template <class Exec, class KH, class a_r, class a_e, bool eti>
+struct GAUSS_SEIDEL_SYMBOLIC<Exec, KH, a_r, a_e, false, eti> {
+  static void gauss_seidel_symbolic(const Exec&, KH*, typename KH::const_nnz_lno_t, typename KH::const_nnz_lno_t, a_r, a_e, bool) {
+    ++mock_native_gs_calls();
+  }
+};
+template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a_r, class a_e, class a_v, bool eti>
+struct GAUSS_SEIDEL_NUMERIC<Exec, KH, format, a_r, a_e, a_v, false, eti> {
+  static void gauss_seidel_numeric(const Exec&, KH*, typename KH::const_nnz_lno_t, typename KH::const_nnz_lno_t, a_r, a_e, a_v, bool) {
+    ++mock_native_gs_calls();
+  }
+  static void gauss_seidel_numeric(const Exec&, KH*, typename KH::const_nnz_lno_t, typename KH::const_nnz_lno_t, a_r, a_e, a_v, a_v, bool) {
+    ++mock_native_gs_calls();
+  }
+};
+template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a_r, class a_e, class a_v, class x_v, class y_v, bool eti>
+struct GAUSS_SEIDEL_APPLY<Exec, KH, format, a_r, a_e, a_v, x_v, y_v, false, eti> {
+  static void gauss_seidel_apply(const Exec&, KH*, typename KH::const_nnz_lno_t, typename KH::const_nnz_lno_t, a_r, a_e, a_v, x_v, y_v, bool, bool,
+                                 typename KH::nnz_scalar_t, int, bool, bool) {
+    ++mock_native_gs_calls();
+  }
+};
 // sparse/tpls/KokkosSparse_spgemm_jacobi_tpl_spec_avail.hpp:24-31, sparse/impl/KokkosSparse_spgemm_jacobi_spec.hpp:83-107
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v>
 struct spgemm_jacobi_tpl_spec_avail {

@@ -337,7 +337,7 @@ def test_kokkos_shim_driver_emulated():
     drv = os.path.join(os.path.dirname(E.harness()), "shim_driver_emu")
     out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 12, out.stdout
+    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 13, out.stdout
 
 
 @pytest.mark.skipif(os.environ.get("B200EMU_NESTED") == "1", reason="this is the nested run")

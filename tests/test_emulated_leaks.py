@@ -126,6 +126,14 @@ def test_solvers(emu):
         E.pcg_solve(p, g, srp, sci, sv, b, np.zeros(n), 50, 1e-10)
         g.close()
         p.close()
+    with balanced(emu, "two-stage Gauss-Seidel plan (L, U, La, Ua, diagonals, work vectors, five SpMV plans); re-symbolic; error path"):
+        g2 = E.Gs2Plan(compact=True, inner=2)
+        assert g2.symbolic(n, n, srp, sci) == 0 and g2.numeric(n, n, srp, sci, sv) == 0
+        assert g2.apply(n, n, srp, sci, sv, np.zeros(n), b, True, 0.9, 2, 0) == 0
+        assert g2.set(1, 0.0) == 0  # classic form: symbolic again
+        assert g2.symbolic(n, n, srp, sci) == 0 and g2.numeric(n, n, srp, sci, sv.astype(np.float32)) == 0
+        assert g2.symbolic(3, 3, np.array([0, 1, 2, 3], np.int32), np.array([0, 0, 2], np.int32)) == 1  # no diagonal in row 1
+        g2.close()
     with balanced(emu, "GMRES (Krylov basis, Hessenberg scratch)"):
         p = E.SpmvPlan()
         E.gmres(p, (rp, ci, v), b, np.zeros(n), m=15, tol=1e-8, max_restart=5, ortho=0)

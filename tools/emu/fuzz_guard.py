@@ -107,6 +107,42 @@ def op_spmv(rng, orc, verbose):
     return ok, f"spmv {mode} {np.dtype(dtype).name} {m}x{n} nnz={len(ci)} {kern}"
 
 
+def op_gs2(rng, orc, verbose):
+    """two-stage Gauss-Seidel (gs2.cu): random options, ghost columns, directions."""
+    import scipy.sparse as sps
+
+    dtype = [np.float64, np.float32][rng.integers(0, 2)]
+    n = int(rng.integers(1, 3000))
+    ghosts = int(rng.integers(0, 50)) if rng.random() < 0.5 else 0
+    rp, ci, v = rand_csr(rng, n, n + ghosts, np.float64)
+    A = sps.csr_matrix((v, ci, rp), shape=(n, n + ghosts)).tolil()
+    rowsum = np.asarray(abs(sps.csr_matrix((v, ci, rp), shape=(n, n + ghosts))).sum(axis=1)).ravel()
+    A.setdiag(rowsum + 1.0 + rng.random(n))  # diagonally dominant, every row has its diagonal
+    A = A.tocsr()
+    if rng.random() < 0.5:
+        A.sort_indices()
+    rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(dtype)
+    ncols = n + ghosts
+    compact, inner, outer = bool(rng.integers(0, 2)), int(rng.integers(0, 4)), int(rng.integers(1, 3))
+    gamma = [1.0, 0.9][rng.integers(0, 2)]
+    omega = [1.0, 0.9, 1.1][rng.integers(0, 3)]
+    direction, init_zero, num_iter = int(rng.integers(0, 3)), bool(rng.integers(0, 2)), int(rng.integers(1, 3))
+    b = rng.uniform(-1, 1, n).astype(dtype)
+    x0 = rng.uniform(-1, 1, ncols).astype(dtype)
+    grp, gci, gv, gb, gx = g(rp, rng), g(ci, rng), g(v, rng), g(b, rng), g(x0, rng)
+    plan = E.Gs2Plan(compact=compact, inner=inner, outer=outer, gamma=gamma)
+    E.ok(plan.symbolic(n, ncols, grp, gci))
+    E.ok(plan.numeric(n, ncols, grp, gci, gv))
+    E.ok(plan.apply(n, ncols, grp, gci, gv, gx, gb, init_zero, omega, num_iter, direction))
+    plan.close()
+    xo = x0.copy()
+    orc.gs2_apply(rp, ci, v, ncols, xo, b, init_zero, dtype(omega), num_iter, direction, compact=compact, inner_sweeps=inner, outer_sweeps=outer,
+                  gamma=dtype(gamma))
+    tol = 1e-12 if dtype == np.float64 else 5e-5
+    ok = bool(np.max(np.abs(gx.astype(np.float64) - xo.astype(np.float64)), initial=0.0) <= tol * max(1.0, np.max(np.abs(xo), initial=0.0)))
+    return ok, f"gs2 {np.dtype(dtype).name} n={n}+{ghosts} nnz={len(ci)} compact={compact} inner={inner} outer={outer} gamma={gamma} omega={omega} dir={direction}"
+
+
 def op_spmv64(rng, orc, verbose):
     """64-bit offsets (spmv64.cu): random window limits, 32- or 64-bit columns, rank 1."""
     dtype = [np.float64, np.float32][rng.integers(0, 2)]
@@ -334,7 +370,7 @@ def op_gs(rng, orc, verbose):
     return ok, f"gs {np.dtype(dtype).name} n={n} nnz={len(ci)} colors={nc} dir={direction} sweeps={sweeps}"
 
 
-OPS = {"gs": op_gs, "spmv": op_spmv, "spmv64": op_spmv64, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
+OPS = {"gs": op_gs, "gs2": op_gs2, "spmv": op_spmv, "spmv64": op_spmv64, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
 
 
 def main():

@@ -79,6 +79,9 @@ int okk_cg_f64(int n, const int* rm, const int* ci, const double* v, const doubl
                double* norm_res_out);
 int okk_pcg_f64(int n, const int* rm, const int* ci, const double* v, const double* b, double* x, int maximum_iteration, double tolerance,
                 double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv);
+int okk_gs2_apply_f64(int n, int ncols, const int* rm, const int* ci, const double* v, const double* given_inverse_diagonal, int compact,
+                      int inner_sweeps, int outer_sweeps, double gamma, double* x, const double* b, int init_zero_x, double omega, int num_iter,
+                      int direction);
 void okk_gs_apply_f64(int n, const int* rm, const int* ci, const double* v, int ncolors, const int* color_ptr, const int* color_rows,
                       const double* dinv, const double* y, double* x, int init_zero_x, double omega, int sweeps, int direction);
 int okk_gmres_f64(int n, const int* rm, const int* ci, const double* v, const int* prm, const int* pci, const double* pv, const double* B,
@@ -1268,6 +1271,44 @@ static void suite_solvers() {
            "initial one",
            n, nc, (long long)clashes, sym_ms, best, spmv_ms, worst, std::sqrt(err / nrm));
   }
+  // ---- two-stage Gauss-Seidel (every product the library's SpMV): classic and compact recurrence, 1 and 3 inner sweeps
+  for (int compact = 0; compact <= 1; ++compact)
+    for (int inner : {1, 3}) {
+      b200sp_gs2_plan* g2 = nullptr;
+      SP(b200sp_gs2_plan_create(&g2));
+      SP(b200sp_gs2_plan_set(g2, B200SP_GS2_COMPACT_FORM, compact));
+      SP(b200sp_gs2_plan_set(g2, B200SP_GS2_NUM_INNER_SWEEPS, inner));
+      t0 = now_s();
+      SP(b200sp_gs2_symbolic_i32(g2, nullptr, n, n, rp.p, ci.p));
+      SP(b200sp_gs2_numeric_f64_i32(g2, nullptr, n, n, rp.p, ci.p, v.p, nullptr));
+      CK(cudaDeviceSynchronize());
+      const double setup_ms = (now_s() - t0) * 1e3;
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        Timer t;
+        t.start();
+        SP(b200sp_gs2_apply_f64_i32(g2, nullptr, n, n, rp.p, ci.p, v.p, dx.p, n, db.p, n, 1, 1, 0.9, 2, 0));
+        const float ms = t.stop_ms();
+        if (rep > 0) best = std::min(best, ms);
+      }
+      auto x = dx.host();
+      std::vector<double> xo((size_t)n, 0.0);
+      okk_gs2_apply_f64(n, n, A.rp.data(), A.ci.data(), A.v.data(), nullptr, compact, inner, 1, 1.0, xo.data(), b.data(), 1, 0.9, 2, 0);
+      double worst = 0, err = 0, nrm = 0;
+      for (int i = 0; i < n; ++i) {
+        worst = std::max(worst, std::fabs(x[i] - xo[i]));
+        err += (x[i] - xs[i]) * (x[i] - xs[i]);
+        nrm += xs[i] * xs[i];
+      }
+      char nm[96];
+      snprintf(nm, sizeof(nm), "two_stage_gs/%s/inner%d", compact ? "compact" : "classic", inner);
+      // 2 symmetric sweeps = 4 sweeps of (residual SpMV with A unless skipped) + `inner` SpMVs with L or U (half of A each)
+      record(nm, g_dry || (worst <= 1e-12 && err < nrm),
+             "symbolic + numeric %.2f ms; 2 symmetric sweeps %.3f ms = %.1f x the SpMV of A (%.4f ms), max |x - x_oracle| %.1e, error norm %.3f of the "
+             "initial one",
+             setup_ms, best, best / spmv_ms, spmv_ms, worst, std::sqrt(err / nrm));
+      if (!g_dry) b200sp_gs2_plan_destroy(g2, nullptr);
+    }
   // ---- PCG (symmetric Gauss-Seidel preconditioner) next to plain CG
   {
     std::vector<double> xo((size_t)n, 0.0), xc((size_t)n, 0.0);

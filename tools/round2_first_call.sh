@@ -8,7 +8,7 @@
 #   4. the headline bench (SpMV config 2) on the same box
 #   gpurun --timeout 1200 -- 'bash tools/round2_first_call.sh'
 # Outputs land in gpurun_out/ (copy the summaries to profiles/ afterwards).  On success of step 1 change `gpu_next` to `gpu`
-# in tests/test_gpu_{jacobi,bsr,cg,gmres,gs,spmv64}.py and tests/test_shim.py.
+# in tests/test_gpu_{jacobi,bsr,cg,gmres,gs,gs2,spmv64}.py and tests/test_shim.py.
 set -u
 mkdir -p gpurun_out
 G=./kokkos-kernels_b200/lib/gpu_check
