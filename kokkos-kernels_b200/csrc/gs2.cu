@@ -294,9 +294,11 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
         rc = spmv32(p->plan[q], stream, n, n, p->cnt[q], -omega, p->rp[q], p->ci[q], (const S*)p->v[q], R, one, Z);
         if (rc) return rc;
         const int copy_back = ii + 1 < p->inner;
-        if (gamma != one || copy_back) {
+        if (gamma != one) {
           gs2_inner_kernel<S><<<nb, 256, 0, st>>>(n, Z, R, gamma, copy_back);
           B200SP_LAUNCH_CHECK();
+        } else if (copy_back) {
+          std::swap(R, Z);  // R = 1 * Z is exact: the next inner sweep reads the buffer just written, no copy
         }
       }
       gs2_update_kernel<S><<<nb, 256, 0, st>>>(n, Z, omega, xj, p->compact ? 1 : 0);

@@ -160,7 +160,7 @@ def op_spmv64(rng, orc, verbose):
     longest = int(np.diff(rp).max()) if m > 0 else 0
     window = None
     if rng.random() < 0.8:  # at least the longest row (+3: the window's base is rounded down to a multiple of 4)
-        window = int(max(8, longest + 3, rng.integers(8, max(9, len(ci) // int(rng.integers(1, 40)) + 9))))
+        window = int(max(8, longest + 3, len(ci) // 2000 + 8, rng.integers(8, max(9, len(ci) // int(rng.integers(1, 40)) + 9))))  # <= 4096 windows
     grp, gci, gv, gx, gy = g(rp64, rng), g(ci_in, rng), g(v, rng), g(x, rng), g(y0, rng)
     plan = E.Spmv64Plan(int(rng.integers(0, 3)), window=window)
     for _ in range(4 if rng.random() < 0.3 else 2):
