@@ -447,6 +447,13 @@ int b200sp_pcg_solve_f64_i32(b200sp_spmv_plan* plan, b200sp_gs_plan* gs_plan, vo
                              const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
                              int maximum_iteration, double tolerance, int check_every, int* iterations,
                              double* norm_res);
+/* The same with the TWO-STAGE Gauss-Seidel as preconditioner (one symmetric sweep of b200sp_gs2_apply from z = 0, omega = 1): what
+ * pcgsolve runs when its kernel handle was given a GS_TWOSTAGE handle -- symmetric_gauss_seidel_apply dispatches on the handle
+ * (pcg.hpp:321-335).  b200sp_gs2_symbolic / _numeric must have run on this matrix. */
+int b200sp_pcg_solve_gs2_f64_i32(b200sp_spmv_plan* plan, b200sp_gs2_plan* gs2_plan, void* stream, int n, int64_t nnz,
+                                 const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
+                                 int maximum_iteration, double tolerance, int check_every, int* iterations,
+                                 double* norm_res);
 
 /* ---- GMRES -----------------------------------------------------------------------------------
  * KokkosSparse::Experimental::gmres(handle, A, B, X, precond) (sparse/src/KokkosSparse_gmres.hpp:60-160 ->

@@ -164,9 +164,22 @@ extern "C" int b200sp_spmv_f64_i32(b200sp_spmv_plan* plan, void* stream, char mo
 extern "C" int b200sp_gs_apply_f64_i32(b200sp_gs_plan* p, void* stream, int n, const int* row_ptr, const int* col_idx, const double* vals,
                                        double* x, const double* y, int init_zero_x, double omega, int sweeps, int direction);
 
+struct b200sp_gs2_plan;
+extern "C" int b200sp_gs2_apply_f64_i32(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                                        const double* vals, double* x, int64_t ldx, const double* b, int64_t ldb, int nrhs, int init_zero_x,
+                                        double omega, int num_iter, int direction);
+
+// z = M^-1 r by one symmetric sweep from z = 0 with omega = 1: the point (multicolour) method or the two-stage one, whichever
+// plan was given -- what symmetric_gauss_seidel_apply does for the GS handle held by pcgsolve's kernel handle
+static int cg_precond(b200sp_gs_plan* gs, b200sp_gs2_plan* gs2, void* stream, int n, const int* row_ptr, const int* col_idx, const double* vals,
+                      double* z, const double* r) {
+  if (gs) return b200sp_gs_apply_f64_i32(gs, stream, n, row_ptr, col_idx, vals, z, r, 1, 1.0, 1, 0);
+  return b200sp_gs2_apply_f64_i32(gs2, stream, n, n, row_ptr, col_idx, vals, z, n, r, n, 1, 1, 1.0, 1, 0);
+}
+
 // gs != nullptr: symmetric Gauss-Seidel preconditioner, z = SGS(r) with zero initial guess, omega = 1, one sweep
 // (pcgsolve's use_sgs = true, perf_test/sparse/KokkosSparse_pcg.hpp:339-358,412-427)
-static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
+static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, b200sp_gs2_plan* gs2, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
                     const double* vals, const double* b, double* x, int maximum_iteration, double tolerance, int check_every, int* iterations,
                     double* norm_res) {
   B200SP_REQUIRE(plan != nullptr, "cg_solve: null plan (create one with b200sp_spmv_plan_create)");
@@ -178,7 +191,7 @@ static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, in
   *iterations = 0;
   *norm_res = 0.0;
   if (n == 0) return B200SP_OK;
-  const int pcg = gs != nullptr;
+  const int pcg = gs != nullptr || gs2 != nullptr;
   DevTmp tmp(st);
   double *p = nullptr, *r = nullptr, *Ap = nullptr, *z = nullptr, *slots = nullptr;
   CgState* state = nullptr;
@@ -203,7 +216,7 @@ static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, in
   cg_init_kernel<<<grid, kCgThreads, 0, st>>>(n, b, Ap, r, p, slots, state, tolerance, maximum_iteration);
   B200SP_LAUNCH_CHECK();
   if (pcg) {  // z = M^-1 r; precond_old_rdot = r.z; p = z
-    rc = b200sp_gs_apply_f64_i32(gs, stream, n, row_ptr, col_idx, vals, z, r, 1, 1.0, 1, 0);
+    rc = cg_precond(gs, gs2, stream, n, row_ptr, col_idx, vals, z, r);
     if (rc != B200SP_OK) return rc;
     cg_rz_kernel<<<grid, kCgThreads, 0, st>>>(n, r, z, slots, state, 1);
     B200SP_LAUNCH_CHECK();
@@ -226,7 +239,7 @@ static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, in
       cg_update_kernel<<<grid, kCgThreads, 0, st>>>(n, p, Ap, x, r, slots, state, pcg);
       B200SP_LAUNCH_CHECK();
       if (pcg) {
-        rc = b200sp_gs_apply_f64_i32(gs, stream, n, row_ptr, col_idx, vals, z, r, 1, 1.0, 1, 0);
+        rc = cg_precond(gs, gs2, stream, n, row_ptr, col_idx, vals, z, r);
         if (rc != B200SP_OK) return rc;
         cg_rz_kernel<<<grid, kCgThreads, 0, st>>>(n, r, z, slots, state, 0);
         B200SP_LAUNCH_CHECK();
@@ -246,12 +259,20 @@ static int cg_solve(b200sp_spmv_plan* plan, b200sp_gs_plan* gs, void* stream, in
 extern "C" int b200sp_cg_solve_f64_i32(b200sp_spmv_plan* plan, void* stream, int n, int64_t nnz, const int* row_ptr, const int* col_idx,
                                        const double* vals, const double* b, double* x, int maximum_iteration, double tolerance,
                                        int check_every, int* iterations, double* norm_res) {
-  return cg_solve(plan, nullptr, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
+  return cg_solve(plan, nullptr, nullptr, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
 }
 
 extern "C" int b200sp_pcg_solve_f64_i32(b200sp_spmv_plan* plan, b200sp_gs_plan* gs_plan, void* stream, int n, int64_t nnz,
                                         const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
                                         int maximum_iteration, double tolerance, int check_every, int* iterations, double* norm_res) {
   B200SP_REQUIRE(gs_plan != nullptr, "pcg_solve: null Gauss-Seidel plan (symbolic and numeric must have run on this matrix)");
-  return cg_solve(plan, gs_plan, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
+  return cg_solve(plan, gs_plan, nullptr, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations, norm_res);
+}
+
+extern "C" int b200sp_pcg_solve_gs2_f64_i32(b200sp_spmv_plan* plan, b200sp_gs2_plan* gs2_plan, void* stream, int n, int64_t nnz,
+                                            const int* row_ptr, const int* col_idx, const double* vals, const double* b, double* x,
+                                            int maximum_iteration, double tolerance, int check_every, int* iterations, double* norm_res) {
+  B200SP_REQUIRE(gs2_plan != nullptr, "pcg_solve: null two-stage Gauss-Seidel plan (symbolic and numeric must have run on this matrix)");
+  return cg_solve(plan, nullptr, gs2_plan, stream, n, nnz, row_ptr, col_idx, vals, b, x, maximum_iteration, tolerance, check_every, iterations,
+                  norm_res);
 }

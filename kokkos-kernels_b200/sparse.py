@@ -553,7 +553,9 @@ def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.2
     use_sgs) (perf_test/sparse/KokkosSparse_pcg.hpp:248-466): CG for a symmetric positive definite CrsMatrix, unpreconditioned or
     (use_sgs, the reference's default) preconditioned by one symmetric point Gauss-Seidel sweep; x_vector is the initial guess and
     receives the solution.  `handle` is the SPMVHandle of A (None: a throw-away one); gs_handle a GaussSeidelHandle whose symbolic /
-    numeric already ran on A (None with use_sgs: created here, as the reference's driver does, :296-337).  The loop runs on the
+    numeric already ran on A (None with use_sgs: created here, as the reference's driver does, :296-337), or a
+    TwoStageGaussSeidelHandle / a KokkosKernelsHandle holding one: the preconditioner is then one symmetric two-stage sweep, as in the
+    reference, whose symmetric_gauss_seidel_apply dispatches on the handle.  The loop runs on the
     device (b200sp_cg_solve_f64_i32 / b200sp_pcg_solve_f64_i32); double only, like the reference driver."""
     n = A.numRows()
     if A.numCols() != n or y_vector.shape[0] != n or x_vector.shape[0] != n or y_vector.dim() != 1 or x_vector.dim() != 1:
@@ -568,7 +570,15 @@ def pcgsolve(handle, A, y_vector, x_vector, maximum_iteration=200, tolerance=2.2
             gh = GaussSeidelHandle()
             gauss_seidel_symbolic(gh, n, n, A.row_map, A.entries, True)  # SPD: the pattern is symmetric
             gauss_seidel_numeric(gh, n, n, A.row_map, A.entries, A.values, True)
-        check(_lib.sparse().b200sp_pcg_solve_f64_i32(h._plan, gh._plan, _stream(), n, A.nnz(), _idx(A.row_map), _idx(A.entries), _ptr(A.values),
+        gh = gh.get_gs_handle() if hasattr(gh, "get_gs_handle") else gh  # a KokkosKernelsHandle holding the GS handle, as the reference passes
+        if isinstance(gh, TwoStageGaussSeidelHandle):
+            if not gh.is_numeric_called():
+                gauss_seidel_symbolic(gh, n, n, A.row_map, A.entries, True)
+                gauss_seidel_numeric(gh, n, n, A.row_map, A.entries, A.values, True)
+            solve = _lib.sparse().b200sp_pcg_solve_gs2_f64_i32
+        else:
+            solve = _lib.sparse().b200sp_pcg_solve_f64_i32
+        check(solve(h._plan, gh._plan, _stream(), n, A.nnz(), _idx(A.row_map), _idx(A.entries), _ptr(A.values),
                                                      _ptr(y_vector), _ptr(x_vector), int(maximum_iteration), C.c_double(tolerance),
                                                      int(check_every), C.byref(it), C.byref(nr)))
         return CGSolveResult(it.value, nr.value)

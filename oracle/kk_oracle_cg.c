@@ -35,6 +35,9 @@ static double cg_dot(int n, const double* a, const double* b) {
   return s;
 }
 
+int okk_gs2_apply_f64(int n, int ncols, const int* rm, const int* ci, const double* v, const double* given_inverse_diagonal, int compact,
+                      int inner_sweeps, int outer_sweeps, double gamma, double* x, const double* b, int init_zero_x, double omega, int num_iter,
+                      int direction);
 void okk_gs_apply_f64(int n, const int* rm, const int* ci, const double* v, int ncolors, const int* color_ptr, const int* color_rows,
                       const double* dinv, const double* y, double* x, int init_zero_x, double omega, int sweeps, int direction);
 
@@ -48,14 +51,27 @@ OKK_API int okk_cg_f64(int n, const int* row_map, const int* col_idx, const doub
                        int maximum_iteration, double tolerance, double* norm_res_out) {
   return cg_core(n, row_map, col_idx, values, b, x, maximum_iteration, tolerance, norm_res_out, 0, 0, 0, 0);
 }
+OKK_API int okk_pcg_gs2_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x,
+                            int maximum_iteration, double tolerance, double* norm_res_out, int inner_sweeps, int compact) {
+  const int opt[2] = {inner_sweeps, compact};
+  return cg_core(n, row_map, col_idx, values, b, x, maximum_iteration, tolerance, norm_res_out, -1, opt, 0, 0);
+}
 OKK_API int okk_pcg_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x,
                         int maximum_iteration, double tolerance, double* norm_res_out, int ncolors, const int* color_ptr,
                         const int* color_rows, const double* dinv) {
   return cg_core(n, row_map, col_idx, values, b, x, maximum_iteration, tolerance, norm_res_out, ncolors, color_ptr, color_rows, dinv);
 }
+/* ncolors > 0: point (multicolour) symmetric Gauss-Seidel over the given colour sets; ncolors == -1: the two-stage symmetric
+ * Gauss-Seidel (kk_oracle_gs2.c), color_ptr[0] = inner sweeps, color_ptr[1] = compact form -- what the reference's pcgsolve runs when
+ * the caller's kernel handle holds a GS_TWOSTAGE handle (symmetric_gauss_seidel_apply dispatches on it) */
+static void cg_precond(int n, const int* row_map, const int* col_idx, const double* values, int ncolors, const int* color_ptr,
+                       const int* color_rows, const double* dinv, const double* r, double* z) {
+  if (ncolors > 0) okk_gs_apply_f64(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z, 1, 1.0, 1, 0);
+  else okk_gs2_apply_f64(n, n, row_map, col_idx, values, 0, color_ptr[1], color_ptr[0], 1, 1.0, z, r, 1, 1.0, 1, 0);
+}
 static int cg_core(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x, int maximum_iteration,
                    double tolerance, double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv) {
-  const int use_sgs = ncolors > 0;
+  const int use_sgs = ncolors != 0;
   double* z = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
   double precond_old_rdot = 1;
   double* p = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
@@ -68,7 +84,7 @@ static int cg_core(int n, const int* row_map, const int* col_idx, const double* 
   double old_rdot = cg_dot(n, r, r);
   double norm_res = sqrt(old_rdot);
   if (use_sgs) {
-    okk_gs_apply_f64(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z, 1, 1.0, 1, 0);
+    cg_precond(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z);
     precond_old_rdot = cg_dot(n, r, z);
     for (int i = 0; i < n; ++i) p[i] = z[i];
   }
@@ -82,7 +98,7 @@ static int cg_core(int n, const int* row_map, const int* col_idx, const double* 
     const double r_dot = cg_dot(n, r, r);
     double beta = r_dot / old_rdot;
     if (use_sgs) {
-      okk_gs_apply_f64(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z, 1, 1.0, 1, 0);
+      cg_precond(n, row_map, col_idx, values, ncolors, color_ptr, color_rows, dinv, r, z);
       const double precond_r_dot = cg_dot(n, r, z);
       beta = precond_r_dot / precond_old_rdot;
       for (int i = 0; i < n; ++i) p[i] = 1.0 * z[i] + beta * p[i];

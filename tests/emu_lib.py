@@ -304,6 +304,13 @@ def pcg_solve(plan, gs_plan, rp, ci, v, b, x, maximum_iteration, tolerance, chec
     return it.value, nr.value
 
 
+def pcg_solve_gs2(plan, gs2_plan, rp, ci, v, b, x, maximum_iteration, tolerance, check_every=0):
+    it, nr = C.c_int(), C.c_double()
+    ok(lib().b200sp_pcg_solve_gs2_f64_i32(plan.h, gs2_plan.h, None, len(rp) - 1, len(ci), ptr(rp), ptr(ci), ptr(v), ptr(b), ptr(x), maximum_iteration,
+                                          C.c_double(tolerance), check_every, C.byref(it), C.byref(nr)))
+    return it.value, nr.value
+
+
 class Gs2Plan:
     """b200sp_gs2_*: two-stage Gauss-Seidel (inner Jacobi-Richardson sweeps)."""
 

@@ -74,6 +74,8 @@ class Oracle:
         L.okk_cg_f64.restype = i32
         L.okk_pcg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64), i32, vp, vp, vp]
         L.okk_pcg_f64.restype = i32
+        L.okk_pcg_gs2_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64), i32, i32]
+        L.okk_pcg_gs2_f64.restype = i32
         self.ref = None
         rpath = os.path.join(ODIR, "_ref", "libkkref.so")
         if os.path.exists(rpath):
@@ -392,6 +394,13 @@ class Oracle:
         nr = f64()
         it = self.lib.okk_pcg_f64(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), maximum_iteration, tolerance, C.byref(nr), len(color_ptr) - 1,
                                   _p(color_ptr), _p(color_rows), _p(dinv))
+        return it, nr.value
+
+    def pcg_gs2(self, rp, ci, v, b, x, maximum_iteration, tolerance, inner_sweeps=1, compact=False):
+        """pcgsolve(use_sgs=true) with a GS_TWOSTAGE handle: one symmetric two-stage sweep as preconditioner; (iterations, norm_res)."""
+        nr = f64()
+        it = self.lib.okk_pcg_gs2_f64(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), maximum_iteration, tolerance, C.byref(nr), inner_sweeps,
+                                      int(compact))
         return it, nr.value
 
     def rel_mismatch(self, a, b, eps):

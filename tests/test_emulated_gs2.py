@@ -112,3 +112,30 @@ def test_corner_cases_and_errors(emu):
     assert plan.set(1, 1.0) == 0
     assert plan.numeric(n, n, rp, ci, v) == 3
     plan.close()
+
+
+@pytest.mark.parametrize("inner,compact", [(1, False), (3, False), (4, True)])
+def test_pcg_with_two_stage_preconditioner(emu, oracle, inner, compact):
+    """pcgsolve with a GS_TWOSTAGE handle (perf_test/sparse/KokkosSparse_pcg.hpp:321-335: symmetric_gauss_seidel_apply dispatches on
+    the handle): the device-resident loop with one symmetric two-stage sweep as preconditioner follows the oracle iteration for
+    iteration and beats plain CG."""
+    from test_oracle_cg import spd_lap27
+
+    rp, ci, v = spd_lap27(12, shift=0.5)
+    n = len(rp) - 1
+    xs = np.random.default_rng(0).uniform(-1, 1, n)
+    b = np.zeros(n)
+    oracle.spmv_serial(rp, ci, v, xs, b, 1.0, 0.0)
+    xo = np.zeros(n)
+    it_o, nr_o = oracle.pcg_gs2(rp, ci, v, b, xo, 500, 1e-9, inner_sweeps=inner, compact=compact)
+    it_c, _ = oracle.cg(rp, ci, v, b, np.zeros(n), 500, 1e-9)
+    g2, p = E.Gs2Plan(compact=compact, inner=inner), E.SpmvPlan()
+    assert g2.symbolic(n, n, rp, ci) == 0 and g2.numeric(n, n, rp, ci, v) == 0
+    x = np.zeros(n)
+    it, nr = E.pcg_solve_gs2(p, g2, rp, ci, v, b, x, 500, 1e-9, check_every=3)
+    assert abs(it - it_o) <= 1 and it < it_c, (it, it_o, it_c)
+    assert nr <= 1e-9 and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-8
+    if it == it_o:
+        assert np.max(np.abs(x - xo)) <= 1e-10 * max(1.0, np.max(np.abs(xo)))
+    g2.close()
+    p.close()

@@ -89,3 +89,28 @@ def test_reference_unit_test_and_multivectors(cuda, oracle):
     kh2.create_gs_handle()
     with pytest.raises(sp.B200SparseError):
         kh2.set_gs_set_num_inner_sweeps(2)  # not a two-stage handle (KokkosKernels_Handle.hpp:631-637)
+
+
+def test_pcgsolve_with_two_stage_handle(cuda, oracle):
+    from kokkos_kernels_b200 import sparse as sp
+    from test_oracle_cg import spd_lap27
+
+    rp, ci, v = spd_lap27(24, shift=0.5)
+    n = len(rp) - 1
+    xs = np.random.default_rng(0).uniform(-1, 1, n)
+    b = np.zeros(n)
+    oracle.spmv_serial(rp, ci, v, xs, b, 1.0, 0.0)
+    xo = np.zeros(n)
+    it_o, _ = oracle.pcg_gs2(rp, ci, v, b, xo, 500, 1e-9, inner_sweeps=2)
+    it_c, _ = oracle.cg(rp, ci, v, b, np.zeros(n), 500, 1e-9)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    A = sp.CrsMatrix(t(rp), t(ci), t(v), n)
+    kh = sp.KokkosKernelsHandle()
+    kh.create_gs_handle(sp.GS_TWOSTAGE)
+    kh.set_gs_set_num_inner_sweeps(2)
+    xd = torch.zeros(n, dtype=torch.float64, device=cuda)
+    res = sp.pcgsolve(None, A, t(b), xd, 500, 1e-9, use_sgs=True, gs_handle=kh)
+    torch.cuda.synchronize()
+    x = xd.cpu().numpy()
+    assert abs(res.iteration - it_o) <= 1 and res.iteration < it_c
+    assert res.norm_res <= 1e-9 and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-8
