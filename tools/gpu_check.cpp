@@ -79,6 +79,8 @@ int okk_cg_f64(int n, const int* rm, const int* ci, const double* v, const doubl
                double* norm_res_out);
 int okk_pcg_f64(int n, const int* rm, const int* ci, const double* v, const double* b, double* x, int maximum_iteration, double tolerance,
                 double* norm_res_out, int ncolors, const int* color_ptr, const int* color_rows, const double* dinv);
+int okk_pcg_gs2_f64(int n, const int* row_map, const int* col_idx, const double* values, const double* b, double* x, int maximum_iteration,
+                    double tolerance, double* norm_res_out, int inner_sweeps, int compact);
 int okk_gs2_apply_f64(int n, int ncols, const int* rm, const int* ci, const double* v, const double* given_inverse_diagonal, int compact,
                       int inner_sweeps, int outer_sweeps, double gamma, double* x, const double* b, int init_zero_x, double omega, int num_iter,
                       int direction);
@@ -1331,6 +1333,55 @@ static void suite_solvers() {
     record("pcg_sgs", std::abs(it - it_o) <= 1 && nr <= 1e-7 && std::sqrt(num / std::max(den, 1e-300)) < 1e-8,
            "%d iterations (oracle %d; plain CG %d), norm_res %.2e, |x-x_oracle|/|x_oracle| %.1e; %.3f ms = %.4f ms/iteration (SpMV %.4f ms)", it,
            it_o, it_c, nr, std::sqrt(num / std::max(den, 1e-300)), ms, ms / std::max(it, 1), spmv_ms);
+  }
+  // ---- PCG with the two-stage Gauss-Seidel as preconditioner (1 and 2 inner sweeps), next to plain CG.  The inner Jacobi-Richardson
+  // sweeps need |D^-1 L| well below 1, which the stencil matrix above (positive off-diagonals summing to the diagonal) does not offer:
+  // the same pattern with the diagonal raised to 1.5 x the off-diagonal row sum
+  {
+    Csr<double> A2 = A;
+    for (int r = 0; r < n; ++r) {
+      double off = 0;
+      for (int q = A2.rp[r]; q < A2.rp[r + 1]; ++q)
+        if (A2.ci[q] != r) off += std::fabs(A2.v[q]);
+      for (int q = A2.rp[r]; q < A2.rp[r + 1]; ++q)
+        if (A2.ci[q] == r) A2.v[q] = 1.5 * off + 1.0;
+    }
+    std::vector<double> b2((size_t)n, 0.0), xc((size_t)n, 0.0);
+    okk_spmv_serial_f64(n, A2.rp.data(), A2.ci.data(), A2.v.data(), xs.data(), b2.data(), 1.0, 0.0);
+    double nr_c = 0;
+    const int it_c = okk_cg_f64(n, A2.rp.data(), A2.ci.data(), A2.v.data(), b2.data(), xc.data(), 500, 1e-7, &nr_c);
+    Dev<double> v2(A2.v), db2(b2);
+    b200sp_spmv_plan* plan2 = nullptr;
+    SP(b200sp_spmv_plan_create(&plan2, 0));
+    for (int inner : {1, 2}) {
+      std::vector<double> xo((size_t)n, 0.0);
+      double nr_o = 0;
+      const int it_o = okk_pcg_gs2_f64(n, A2.rp.data(), A2.ci.data(), A2.v.data(), b2.data(), xo.data(), 500, 1e-7, &nr_o, inner, 0);
+      b200sp_gs2_plan* g2 = nullptr;
+      SP(b200sp_gs2_plan_create(&g2));
+      SP(b200sp_gs2_plan_set(g2, B200SP_GS2_NUM_INNER_SWEEPS, inner));
+      SP(b200sp_gs2_symbolic_i32(g2, nullptr, n, n, rp.p, ci.p));
+      SP(b200sp_gs2_numeric_f64_i32(g2, nullptr, n, n, rp.p, ci.p, v2.p, nullptr));
+      dx.fill_bytes(0);
+      int it = 0;
+      double nr = 0;
+      t0 = now_s();
+      SP(b200sp_pcg_solve_gs2_f64_i32(plan2, g2, nullptr, n, A2.nnz(), rp.p, ci.p, v2.p, db2.p, dx.p, 500, 1e-7, 8, &it, &nr));
+      const double ms = (now_s() - t0) * 1e3;
+      auto x = dx.host();
+      double num = 0, den = 0;
+      for (int i = 0; i < n; ++i) {
+        num += (x[i] - xo[i]) * (x[i] - xo[i]);
+        den += xo[i] * xo[i];
+      }
+      char nm[64];
+      snprintf(nm, sizeof(nm), "pcg_two_stage_gs/inner%d", inner);
+      record(nm, g_dry || (std::abs(it - it_o) <= 1 && it < it_c && nr <= 1e-7 && std::sqrt(num / std::max(den, 1e-300)) < 1e-7),
+             "%d iterations (oracle %d; plain CG %d), norm_res %.2e, |x-x_oracle|/|x_oracle| %.1e; %.3f ms = %.4f ms/iteration (SpMV %.4f ms)", it,
+             it_o, it_c, nr, std::sqrt(num / std::max(den, 1e-300)), ms, ms / std::max(it, 1), spmv_ms);
+      if (!g_dry) b200sp_gs2_plan_destroy(g2, nullptr);
+    }
+    if (!g_dry) b200sp_spmv_plan_destroy(plan2, nullptr);
   }
   // ---- GMRES(15), CGS2 and MGS
   for (int ortho = 0; ortho < 2; ++ortho) {
