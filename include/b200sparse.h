@@ -400,7 +400,8 @@ int b200sp_gs_copy_coloring(const b200sp_gs_plan* plan, void* stream, int* color
  *     T = D.*R; R = gamma T;  inner sweeps:  Z = T - omega (L or U) R;  Z = gamma Z + (1 - gamma) R;  R = Z
  *     x += omega Z                         (compact form: x = omega Z)
  * with the library's SpMV for every product (plans of A, L, U, La, Ua kept in this plan) and the KokkosBlas steps in between
- * evaluated expression by expression as the reference does.  x: ncols x nrhs, b: n x nrhs, column-major with leading
+ * evaluated expression by expression as the reference does (nrhs > 1: the multivector products, one pass over the matrix for
+ * all right-hand sides).  x: ncols x nrhs, b: n x nrhs, column-major with leading
  * dimensions ldx / ldb (LayoutLeft, the reference's default_layout on the GPU); direction 0 = symmetric, 1 = forward,
  * 2 = backward; init_zero_x != 0 zeroes x first (and skips the first residual product).  Options (before symbolic for
  * COMPACT_FORM): KokkosKernelsHandle::set_gs_twostage_compact_form / set_gs_set_num_inner_sweeps / _num_outer_sweeps /

@@ -16,7 +16,8 @@
 // Every product is the library's own SpMV (spmv.cu: the TMA-tiled kernel with its plan, one plan per matrix A, L, U, La, Ua);
 // the vector updates in between are fused into one kernel per step, each computing exactly the expression the reference's
 // KokkosBlas call sequence computes (mult with beta = 0, scal, axpy), so the only difference to the reference is the summation
-// order inside the SpMVs.  No colouring, no atomics: deterministic and independent of the row order.
+// order inside the SpMVs.  No colouring, no atomics: deterministic and independent of the row order.  Several right-hand sides go
+// through the multivector products (spmm.cu), so a sweep reads the matrix once for all of them.
 // The sptrsv variant (two_stage = false, "classic" in the reference's unit test) is not provided: sptrsv is outside the path.
 #include <algorithm>
 #include <new>
@@ -39,6 +40,7 @@ struct b200sp_gs2_plan {
   int64_t cnt[4] = {0, 0, 0, 0};
   void *D = nullptr, *Da = nullptr;
   void *R = nullptr, *T = nullptr, *Z = nullptr;
+  int work_cols = 0;  // right-hand sides R, T, Z are sized for
   b200sp_spmv_plan* plan[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // L, U, La, Ua, A
 };
 
@@ -131,57 +133,66 @@ __global__ void __launch_bounds__(256) gs2_values_kernel(int n, const int* __res
   }
 }
 
-// the vector steps between the SpMVs; every expression is the one the reference's KokkosBlas sequence evaluates
+// the vector steps between the SpMVs; every expression is the one the reference's KokkosBlas sequence evaluates.  All of them
+// run over an n x k block (k right-hand sides, column-major): element e -> row e % n, column e / n; the work vectors R, T, Z
+// have leading dimension n, x and b the caller's.
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_copy_kernel(int n, const S* __restrict__ a, S* __restrict__ out) {  // scal(out, one, a)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = S(1) * a[i];
+__global__ void __launch_bounds__(256) gs2_copy_kernel(int64_t total, int n, const S* __restrict__ a, int64_t lda, S* __restrict__ out,
+                                                       int64_t ldo) {  // scal(out, one, a)
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e % n, j = e / n;
+    out[i + j * ldo] = S(1) * a[i + j * lda];
+  }
 }
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_diag_term_kernel(int n, const S* __restrict__ Da, const S* __restrict__ x, S omega2, S* __restrict__ Z,
-                                                            S* __restrict__ R) {  // Z = Da.*x;  R += omega2 Z
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const S z = S(1) * Da[i] * x[i];
-    Z[i] = z;
-    R[i] += omega2 * z;
+__global__ void __launch_bounds__(256) gs2_diag_term_kernel(int64_t total, int n, const S* __restrict__ Da, const S* __restrict__ x, int64_t ldx,
+                                                            S omega2, S* __restrict__ Z, S* __restrict__ R) {  // Z = Da.*x;  R += omega2 Z
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e % n, j = e / n;
+    const S z = S(1) * Da[i] * x[i + j * ldx];
+    Z[e] = z;
+    R[e] += omega2 * z;
   }
 }
 // inner == 0:  Z = D.*R (times gamma);  else  T = D.*R, R = T (times gamma)
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_start_kernel(int n, const S* __restrict__ D, S* __restrict__ R, S* __restrict__ T, S* __restrict__ Z,
-                                                        S gamma, int inner) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const S t = S(1) * D[i] * R[i];
+__global__ void __launch_bounds__(256) gs2_start_kernel(int64_t total, int n, const S* __restrict__ D, S* __restrict__ R, S* __restrict__ T,
+                                                        S* __restrict__ Z, S gamma, int inner) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const S t = S(1) * D[e % n] * R[e];
     if (inner == 0) {
-      Z[i] = (gamma != S(1)) ? gamma * t : t;
+      Z[e] = (gamma != S(1)) ? gamma * t : t;
     } else {
-      T[i] = t;
+      T[e] = t;
       const S r = S(1) * t;
-      R[i] = (gamma != S(1)) ? gamma * r : r;
+      R[e] = (gamma != S(1)) ? gamma * r : r;
     }
   }
 }
 // after Z = T - omega M R:  gamma != 1: Z = gamma Z + (1 - gamma) R;  not the last inner sweep: R = Z
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_inner_kernel(int n, S* __restrict__ Z, S* __restrict__ R, S gamma, int copy_back) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    S z = Z[i];
+__global__ void __launch_bounds__(256) gs2_inner_kernel(int64_t total, S* __restrict__ Z, S* __restrict__ R, S gamma, int copy_back) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    S z = Z[e];
     if (gamma != S(1)) {
       z = gamma * z;
-      z += (S(1) - gamma) * R[i];
-      Z[i] = z;
+      z += (S(1) - gamma) * R[e];
+      Z[e] = z;
     }
-    if (copy_back) R[i] = S(1) * z;
+    if (copy_back) R[e] = S(1) * z;
   }
 }
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_update_kernel(int n, const S* __restrict__ Z, S omega, S* __restrict__ x, int compact) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (compact) x[i] = omega * Z[i];
-    else x[i] += omega * Z[i];
+__global__ void __launch_bounds__(256) gs2_update_kernel(int64_t total, int n, const S* __restrict__ Z, S omega, S* __restrict__ x, int64_t ldx,
+                                                         int compact) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = e % n + (e / n) * ldx;
+    if (compact) x[q] = omega * Z[e];
+    else x[q] += omega * Z[e];
   }
 }
 
-inline int vec_blocks(int n) { return std::max(1, std::min((n + 255) / 256, sm_count() * 8)); }
+inline int vec_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8)); }
 
 void release_parts(b200sp_gs2_plan* p, cudaStream_t st) {
   for (int q = 0; q < 4; ++q) {
@@ -199,6 +210,7 @@ void release_parts(b200sp_gs2_plan* p, cudaStream_t st) {
   }
   p->symbolic = p->numeric = false;
   p->scalar_bytes = 0;
+  p->work_cols = 0;
 }
 
 inline int spmv32(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, double a, const int* rp, const int* ci, const double* v,
@@ -208,6 +220,23 @@ inline int spmv32(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, dou
 inline int spmv32(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, float a, const int* rp, const int* ci, const float* v,
                   const float* x, float b, float* y) {
   return b200sp_spmv_f32_i32(pl, st, 'N', m, n, nnz, a, rp, ci, v, x, b, y);
+}
+
+inline int spmm32(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, int k, double a, const int* rp, const int* ci, const double* v,
+                  const double* X, int64_t ldx, double b, double* Y, int64_t ldy) {
+  return b200sp_spmm_f64_i32(pl, st, 'N', m, n, nnz, k, a, rp, ci, v, X, ldx, 0, b, Y, ldy, 0);
+}
+inline int spmm32(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, int k, float a, const int* rp, const int* ci, const float* v,
+                  const float* X, int64_t ldx, float b, float* Y, int64_t ldy) {
+  return b200sp_spmm_f32_i32(pl, st, 'N', m, n, nnz, k, a, rp, ci, v, X, ldx, 0, b, Y, ldy, 0);
+}
+// Y = beta Y + alpha M X for k columns (column-major): the rank-1 kernels for one column, the multivector kernels otherwise --
+// the matrix is read once for all right-hand sides
+template <typename S>
+inline int product(b200sp_spmv_plan* pl, void* st, int m, int n, int64_t nnz, int k, S a, const int* rp, const int* ci, const S* v, const S* X,
+                   int64_t ldx, S b, S* Y, int64_t ldy) {
+  if (k == 1) return spmv32(pl, st, m, n, nnz, a, rp, ci, v, X, b, Y);
+  return spmm32(pl, st, m, n, nnz, k, a, rp, ci, v, X, ldx, b, Y, ldy);
 }
 
 template <typename S>
@@ -229,6 +258,7 @@ int numeric_impl(b200sp_gs2_plan* p, cudaStream_t st, int n, int ncols, const in
     void** vecs[] = {&p->D, &p->Da, &p->R, &p->T, &p->Z};
     for (void** q : vecs) B200SP_CUDA_TRY(cudaMallocAsync(q, sizeof(S) * (size_t)std::max(n, 1), st));
     p->scalar_bytes = (int)sizeof(S);
+    p->work_cols = 1;
   }
   if (n > 0) {
     B200SP_REQUIRE(vals != nullptr, "gs2_numeric: null values");
@@ -257,53 +287,66 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
   B200SP_REQUIRE(nrhs == 1 || (ldx >= ncols && ldb >= n), "gs2_apply: leading dimensions too small (ldx=%lld ldb=%lld)", (long long)ldx,
                  (long long)ldb);
   const S one = S(1), gamma = (S)p->gamma;
+  const int k = nrhs;
+  const int64_t total = (int64_t)n * k;
+  if (k > p->work_cols) {  // work vectors for k right-hand sides (numeric sizes them for one)
+    void** vecs[] = {&p->R, &p->T, &p->Z};
+    for (void** q : vecs) {
+      if (*q) cudaFreeAsync(*q, st);
+      *q = nullptr;
+    }
+    p->work_cols = 0;
+    for (void** q : vecs) B200SP_CUDA_TRY(cudaMallocAsync(q, sizeof(S) * (size_t)total, st));
+    p->work_cols = k;
+  }
   S *R = (S*)p->R, *T = (S*)p->T, *Z = (S*)p->Z;
   const S *D = (const S*)p->D, *Da = (const S*)p->Da;
-  const int nb = vec_blocks(n);
+  const int nb = vec_blocks(total);
+  if (k == 1) {
+    ldx = ncols;
+    ldb = n;
+  }
   int sweeps = std::max(p->outer, num_iter);
   if (direction == 0) sweeps *= 2;
-  for (int j = 0; j < nrhs; ++j) {  // columns are contiguous (LayoutLeft, the reference's default_layout on the GPU)
-    S* xj = x + (int64_t)j * ldx;
-    const S* bj = b + (int64_t)j * ldb;
-    if (init_zero_x) B200SP_CUDA_TRY(cudaMemsetAsync(xj, 0, sizeof(S) * (size_t)ncols, st));
-    for (int sweep = 0; sweep < sweeps; ++sweep) {
-      const bool forward = direction == 1 || (direction == 0 && sweep % 2 == 0);
-      gs2_copy_kernel<S><<<nb, 256, 0, st>>>(n, bj, R);
-      B200SP_LAUNCH_CHECK();
-      int rc = B200SP_OK;
-      if (sweep > 0 || !init_zero_x) {
-        if (p->compact) {
-          const int q = forward ? kUa : kLa;
-          rc = spmv32(p->plan[q], stream, n, ncols, p->cnt[q], -one, p->rp[q], p->ci[q], (const S*)p->v[q], xj, one, R);
-          if (rc) return rc;
-          if (omega != one) {
-            gs2_diag_term_kernel<S><<<nb, 256, 0, st>>>(n, Da, xj, one / omega - one, Z, R);
-            B200SP_LAUNCH_CHECK();
-          }
-        } else {
-          rc = spmv32(p->plan[kA], stream, n, ncols, p->nnz, -one, row_ptr, col_idx, vals, xj, one, R);
-          if (rc) return rc;
-        }
-      }
-      gs2_start_kernel<S><<<nb, 256, 0, st>>>(n, D, R, T, Z, gamma, p->inner);
-      B200SP_LAUNCH_CHECK();
-      for (int ii = 0; ii < p->inner; ++ii) {
-        gs2_copy_kernel<S><<<nb, 256, 0, st>>>(n, T, Z);
-        B200SP_LAUNCH_CHECK();
-        const int q = forward ? kL : kU;
-        rc = spmv32(p->plan[q], stream, n, n, p->cnt[q], -omega, p->rp[q], p->ci[q], (const S*)p->v[q], R, one, Z);
+  if (init_zero_x)
+    for (int j = 0; j < k; ++j) B200SP_CUDA_TRY(cudaMemsetAsync(x + (int64_t)j * ldx, 0, sizeof(S) * (size_t)ncols, st));
+  for (int sweep = 0; sweep < sweeps; ++sweep) {
+    const bool forward = direction == 1 || (direction == 0 && sweep % 2 == 0);
+    gs2_copy_kernel<S><<<nb, 256, 0, st>>>(total, n, b, ldb, R, (int64_t)n);
+    B200SP_LAUNCH_CHECK();
+    int rc = B200SP_OK;
+    if (sweep > 0 || !init_zero_x) {
+      if (p->compact) {
+        const int q = forward ? kUa : kLa;
+        rc = product<S>(p->plan[q], stream, n, ncols, p->cnt[q], k, -one, p->rp[q], p->ci[q], (const S*)p->v[q], x, ldx, one, R, n);
         if (rc) return rc;
-        const int copy_back = ii + 1 < p->inner;
-        if (gamma != one) {
-          gs2_inner_kernel<S><<<nb, 256, 0, st>>>(n, Z, R, gamma, copy_back);
+        if (omega != one) {
+          gs2_diag_term_kernel<S><<<nb, 256, 0, st>>>(total, n, Da, x, ldx, one / omega - one, Z, R);
           B200SP_LAUNCH_CHECK();
-        } else if (copy_back) {
-          std::swap(R, Z);  // R = 1 * Z is exact: the next inner sweep reads the buffer just written, no copy
         }
+      } else {
+        rc = product<S>(p->plan[kA], stream, n, ncols, p->nnz, k, -one, row_ptr, col_idx, vals, x, ldx, one, R, n);
+        if (rc) return rc;
       }
-      gs2_update_kernel<S><<<nb, 256, 0, st>>>(n, Z, omega, xj, p->compact ? 1 : 0);
-      B200SP_LAUNCH_CHECK();
     }
+    gs2_start_kernel<S><<<nb, 256, 0, st>>>(total, n, D, R, T, Z, gamma, p->inner);
+    B200SP_LAUNCH_CHECK();
+    for (int ii = 0; ii < p->inner; ++ii) {
+      gs2_copy_kernel<S><<<nb, 256, 0, st>>>(total, n, T, (int64_t)n, Z, (int64_t)n);
+      B200SP_LAUNCH_CHECK();
+      const int q = forward ? kL : kU;
+      rc = product<S>(p->plan[q], stream, n, n, p->cnt[q], k, -omega, p->rp[q], p->ci[q], (const S*)p->v[q], R, n, one, Z, n);
+      if (rc) return rc;
+      const int copy_back = ii + 1 < p->inner;
+      if (gamma != one) {
+        gs2_inner_kernel<S><<<nb, 256, 0, st>>>(total, Z, R, gamma, copy_back);
+        B200SP_LAUNCH_CHECK();
+      } else if (copy_back) {
+        std::swap(R, Z);  // R = 1 * Z is exact: the next inner sweep reads the buffer just written, no copy
+      }
+    }
+    gs2_update_kernel<S><<<nb, 256, 0, st>>>(total, n, Z, omega, x, ldx, p->compact ? 1 : 0);
+    B200SP_LAUNCH_CHECK();
   }
   return B200SP_OK;
 }

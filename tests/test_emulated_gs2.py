@@ -139,3 +139,40 @@ def test_pcg_with_two_stage_preconditioner(emu, oracle, inner, compact):
         assert np.max(np.abs(x - xo)) <= 1e-10 * max(1.0, np.max(np.abs(xo)))
     g2.close()
     p.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("compact", [False, True])
+def test_several_right_hand_sides_use_the_multivector_products(emu, oracle, dtype, compact):
+    """k > 1: every product is one SpMM over all columns (the matrix is read once), x and b with padded leading dimensions and ghost
+    rows; each column must equal the oracle's single-vector run."""
+    n, ghosts, k = 2500, 30, 4
+    rp, ci, v = dd_matrix(n, 21, extra_cols=ghosts)
+    v = v.astype(dtype)
+    ncols = n + ghosts
+    rng = np.random.default_rng(6)
+    Xfull = np.asfortranarray(rng.uniform(-1, 1, (ncols + 5, k)).astype(dtype))
+    Bfull = np.asfortranarray(rng.uniform(-1, 1, (n + 3, k)).astype(dtype))
+    X0, B = Xfull[:ncols], Bfull[:n]  # views: leading dimensions ncols + 5 and n + 3
+    tol = 1e-13 if dtype == np.float64 else 1e-5
+    plan = E.Gs2Plan(compact=compact, inner=2, gamma=0.9)
+    assert plan.symbolic(n, ncols, rp, ci) == 0 and plan.numeric(n, ncols, rp, ci, v) == 0
+    for direction, omega, init_zero in ((0, 0.9, False), (1, 1.0, True), (2, 1.1, False)):
+        Xw = Xfull.copy(order="F")
+        X = Xw[:ncols]
+        assert plan.apply(n, ncols, rp, ci, v, X, B, init_zero, omega, 2, direction) == 0
+        assert np.array_equal(Xw[ncols:], Xfull[ncols:])  # the padding rows are not touched
+        for j in range(k):
+            xo = np.ascontiguousarray(X0[:, j]).copy()
+            oracle.gs2_apply(rp, ci, v, ncols, xo, np.ascontiguousarray(B[:, j]), init_zero, dtype(omega), 2, direction, compact=compact,
+                             inner_sweeps=2, gamma=dtype(0.9))
+            err = np.max(np.abs(X[:, j].astype(np.float64) - xo.astype(np.float64)))
+            assert err <= tol * 20 * max(1.0, np.max(np.abs(xo))), (direction, j, err)
+    # one column afterwards on the same plan (rank-1 products again), then more columns than before (work vectors regrown)
+    x1 = np.ascontiguousarray(X0[:, 0]).copy()
+    assert plan.apply(n, ncols, rp, ci, v, x1, np.ascontiguousarray(B[:, 0]), False, 1.0, 1, 0) == 0
+    X6 = np.asfortranarray(rng.uniform(-1, 1, (ncols, 6)).astype(dtype))
+    B6 = np.asfortranarray(rng.uniform(-1, 1, (n, 6)).astype(dtype))
+    assert plan.apply(n, ncols, rp, ci, v, X6, B6, True, 1.0, 1, 0) == 0
+    assert np.all(np.isfinite(X6))
+    plan.close()
