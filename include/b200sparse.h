@@ -75,6 +75,13 @@ int b200sp_spmv_plan_destroy(b200sp_spmv_plan* plan, void* stream);
  * of 8 bytes/entry of structure + sizeof(S) bytes/entry of values.  Without it T / H use atomicAdd
  * scatters like the reference's GPU path (sparse/impl/KokkosSparse_spmv_impl.hpp:36-84). */
 #define B200SP_SPMV_OPT_CACHE_TRANSPOSE 1
+/* B200SP_SPMV_OPT_HOSTVEC_DEFER (default 0), for b200sp_spmv_hostvec_*: a call no longer makes `stream` wait for its own
+ * download of y, so the next call's kernel runs while this call's y is still on its way to the host (upload of call k+1,
+ * compute of call k+1 and download of call k all overlap: the step time tends to the slowest of the three instead of
+ * compute + download).  The price is the completion rule: y_host of ALL calls issued so far is valid only after
+ * b200sp_spmv_hostvec_flush(plan, stream) followed by a synchronisation of `stream`; calls in flight must not depend on
+ * each other's y_host (beta != 0 reads y_host at call time). */
+#define B200SP_SPMV_OPT_HOSTVEC_DEFER 2
 int b200sp_spmv_plan_set_option(b200sp_spmv_plan* plan, int option, int value);
 
 /* ---- SpMV rank-1: y = beta*y + alpha*op(A)*x ---------------------------- */
@@ -139,6 +146,9 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* plan, void* stream, char mode,
                                 int64_t nnz, double alpha, const int* row_ptr, const int* col_idx,
                                 const double* vals, const double* x_host, double beta,
                                 double* y_host);
+
+/* Deferred mode (B200SP_SPMV_OPT_HOSTVEC_DEFER) only: makes `stream` wait for every download issued so far. */
+int b200sp_spmv_hostvec_flush(b200sp_spmv_plan* plan, void* stream);
 
 /* Row-block-partitioned SpMV with the all-gather of y fused into the kernel (multi-GPU, config 5):
  * y = alpha*A*x for this rank's row block is stored to `y` AND to `n_extra` (<= 7) further device

@@ -613,6 +613,8 @@ struct b200sp_spmv_plan {
     int row_b[9];
     const int* key = nullptr;
     int key_cfg = -1;
+    bool defer = false;  // B200SP_SPMV_OPT_HOSTVEC_DEFER: `stream` does not wait for a call's download before the next call computes
+    int last_b = -1;     // buffer of the latest call whose download `stream` has not been made to wait for
   } pipe;
 };
 
@@ -1146,6 +1148,13 @@ int b200sp_spmv_plan_set_option(b200sp_spmv_plan* p, int option, int value) {
   B200SP_REQUIRE(p != nullptr, "spmv_plan_set_option: null plan");
   switch (option) {
     case B200SP_SPMV_OPT_CACHE_TRANSPOSE: p->cache_transpose = value != 0; return B200SP_OK;
+    case B200SP_SPMV_OPT_HOSTVEC_DEFER:
+      if (p->pipe.defer && value == 0 && p->pipe.last_b >= 0) {
+        set_error("spmv_plan_set_option: downloads are outstanding, call b200sp_spmv_hostvec_flush first");
+        return B200SP_ERR_STATE;
+      }
+      p->pipe.defer = value != 0;
+      return B200SP_OK;
   }
   set_error("spmv_plan_set_option: unknown option %d", option);
   return B200SP_ERR_INVALID_ARGUMENT;
@@ -1342,6 +1351,11 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
     q.key_cfg = cfg;
   }
   const int b = (int)(q.call & 1ull);
+  if (q.defer && q.call >= 2) {
+    // deferred mode: nothing made `stream` wait for the download of call k-2, which reads the y buffer this call writes
+    B200SP_CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done[b], 0));
+    if (beta != 0.0) B200SP_CUDA_TRY(cudaStreamWaitEvent(q.sH, q.ev_done[b], 0));
+  }
   // upload: wait until the compute that last read this x buffer (call k-2) is done
   if (q.call >= 2) B200SP_CUDA_TRY(cudaStreamWaitEvent(q.sH, q.ev_c[b], 0));
   B200SP_CUDA_TRY(cudaMemcpyAsync(q.dx[b], x_host, xb, cudaMemcpyHostToDevice, q.sH));
@@ -1367,8 +1381,23 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
   }
   B200SP_CUDA_TRY(cudaEventRecord(q.ev_c[b], st));
   B200SP_CUDA_TRY(cudaEventRecord(q.ev_done[b], q.sD));
-  B200SP_CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done[b], 0));  // y_host is valid once `stream` is synchronised
+  if (q.defer) {
+    q.last_b = b;  // y_host is valid once b200sp_spmv_hostvec_flush has been called and `stream` synchronised
+  } else {
+    B200SP_CUDA_TRY(cudaStreamWaitEvent(st, q.ev_done[b], 0));  // y_host is valid once `stream` is synchronised
+  }
   q.call++;
+  return B200SP_OK;
+}
+
+int b200sp_spmv_hostvec_flush(b200sp_spmv_plan* p, void* stream) {
+  B200SP_REQUIRE(p != nullptr, "spmv_hostvec_flush: null plan");
+  auto& q = p->pipe;
+  if (q.init && q.last_b >= 0) {
+    // the download stream is in order: waiting for the latest download covers all earlier ones
+    B200SP_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, q.ev_done[q.last_b], 0));
+    q.last_b = -1;
+  }
   return B200SP_OK;
 }
 

@@ -150,6 +150,14 @@ class SPMVHandle:
         """Modes T / H through an explicit transpose kept in the plan (deterministic, no atomics)."""
         check(_lib.sparse().b200sp_spmv_plan_set_option(self._plan, 1, int(bool(enable))))
 
+    def hostvec_defer(self, enable=True):
+        """spmv_hostvec calls stop making the stream wait for their own download of y: consecutive calls overlap upload, kernel and
+        download; y_host is valid after hostvec_flush() + a stream synchronisation (B200SP_SPMV_OPT_HOSTVEC_DEFER)."""
+        check(_lib.sparse().b200sp_spmv_plan_set_option(self._plan, 2, int(bool(enable))))
+
+    def hostvec_flush(self):
+        check(_lib.sparse().b200sp_spmv_hostvec_flush(self._plan, _stream()))
+
     def tune(self, cfg=-1, lanes_per_row=-1, ctas_per_sm=-1):
         check(_lib.sparse().b200sp_spmv_plan_tune(self._plan, cfg, lanes_per_row, ctas_per_sm))
 

@@ -452,6 +452,30 @@ def test_hostvec_pipeline_logic(emu, oracle, pieces):
             assert np.all(np.abs(y - exp) <= 1e-10 * rowwise_scale(rp, ci, v, x, y0, alpha, beta) + 1e-300)
 
 
+def test_hostvec_deferred_completion_logic(emu, oracle):
+    """B200SP_SPMV_OPT_HOSTVEC_DEFER: calls stop waiting for their own download; b200sp_spmv_hostvec_flush closes the sequence.
+    Under the emulation the copies are synchronous, so this checks the bookkeeping (buffers alternate, flush resets, the option
+    cannot be switched off with downloads outstanding), not the overlap."""
+    n = 70000
+    rp, ci, v = kk_matrix(n, n, n * 64, 3, 2000)
+    rng = np.random.default_rng(8)
+    xs = [rng.uniform(-1, 1, n) for _ in range(5)]
+    ys = [np.full(n, np.nan) for _ in range(5)]
+    plan = E.SpmvPlan()
+    E.ok(emu.b200sp_spmv_plan_set_option(plan.h, 2, 1))
+    for x, y in zip(xs, ys):
+        E.ok(emu.b200sp_spmv_hostvec_f64_i32(plan.h, None, b"N", n, n, len(ci), 1.0, E.ptr(rp), E.ptr(ci), E.ptr(v), E.ptr(x), 0.0, E.ptr(y)))
+    assert emu.b200sp_spmv_plan_set_option(plan.h, 2, 0) == 3  # B200SP_ERR_STATE: downloads outstanding
+    E.ok(emu.b200sp_spmv_hostvec_flush(plan.h, None))
+    E.ok(emu.b200sp_spmv_hostvec_flush(plan.h, None))  # idempotent
+    E.ok(emu.b200sp_spmv_plan_set_option(plan.h, 2, 0))
+    for x, y in zip(xs, ys):
+        exp = oracle.spmv_serial(rp, ci, v, x, np.zeros(n), 1.0, 0.0)
+        assert np.all(np.abs(y - exp) <= 1e-10 * rowwise_scale(rp, ci, v, x, np.zeros(n), 1.0, 0.0) + 1e-300)
+    plan.close()
+    assert emu.b200sp_spmv_hostvec_flush(None, None) == 1
+
+
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-5)])
 @pytest.mark.parametrize("variant", ["cgs2", "mgs", "matrixprec"])
 def test_gmres(emu, oracle, dtype, tol, variant):
