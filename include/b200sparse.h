@@ -380,6 +380,11 @@ int b200sp_gs_plan_create(b200sp_gs_plan** plan);
 int b200sp_gs_plan_destroy(b200sp_gs_plan* plan, void* stream);
 int b200sp_gs_symbolic_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
                            int is_graph_symmetric);
+/* Same for a matrix with num_cols >= num_rows -- the local part of a distributed matrix, as Ifpack2 / MueLu hand it over:
+ * columns >= num_rows address ghost entries of x, which the sweeps read and never write and which take no part in the
+ * colouring (x then has num_cols entries; numeric / apply keep their signatures). */
+int b200sp_gs_symbolic_nc_i32(b200sp_gs_plan* plan, void* stream, int n, int ncols, const int* row_ptr,
+                              const int* col_idx, int is_graph_symmetric);
 int b200sp_gs_numeric_f64_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
                               const double* vals);
 int b200sp_gs_numeric_f32_i32(b200sp_gs_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,

@@ -90,6 +90,7 @@ SPARSE_API = {
     "b200sp_gs_plan_create": (i32, [C.POINTER(vp)]),
     "b200sp_gs_plan_destroy": (i32, [vp, vp]),
     "b200sp_gs_symbolic_i32": (i32, [vp, vp, i32, vp, vp, i32]),
+    "b200sp_gs_symbolic_nc_i32": (i32, [vp, vp, i32, i32, vp, vp, i32]),
     "b200sp_gs_numeric_f64_i32": (i32, [vp, vp, i32, vp, vp, vp]),
     "b200sp_gs_numeric_f32_i32": (i32, [vp, vp, i32, vp, vp, vp]),
     "b200sp_gs_apply_f64_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, f64, i32, i32]),

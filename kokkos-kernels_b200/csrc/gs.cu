@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(256) gs_set_kernel(const int* __restrict__ row
 using namespace b200sp;
 
 struct b200sp_gs_plan {
+  int ncols = 0;  // num_cols of the matrix symbolic saw (>= n: columns beyond n are ghost entries of x)
   int n = -1;
   int num_colors = 0;
   int* colors = nullptr;      // device, n
@@ -281,7 +282,8 @@ int gs_apply_impl(b200sp_gs_plan* p, cudaStream_t st, int n, const int* rp, cons
   }
   if (n == 0) return B200SP_OK;
   B200SP_REQUIRE(rp && ci && v && x && y, "gauss_seidel_apply: null array");
-  if (init_zero_x) B200SP_CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(S) * (size_t)n, st));
+  if (init_zero_x)  // all of x, ghost entries included, as the reference's zero_vector(num_cols, ...) does (gauss_seidel_impl.hpp:1426-1428)
+    B200SP_CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(S) * (size_t)std::max(n, p->ncols), st));
   const S* dinv = (const S*)p->dinv;
   for (int s = 0; s < sweeps; ++s) {
     for (int backward = 0; backward < 2; ++backward) {
@@ -328,11 +330,19 @@ int b200sp_gs_plan_destroy(b200sp_gs_plan* p, void* stream) {
 }
 
 int b200sp_gs_symbolic_i32(b200sp_gs_plan* p, void* stream, int n, const int* row_ptr, const int* col_idx, int is_graph_symmetric) {
+  return b200sp_gs_symbolic_nc_i32(p, stream, n, n, row_ptr, col_idx, is_graph_symmetric);
+}
+
+// num_cols >= num_rows: the local matrix of a distributed one; columns >= num_rows address ghost entries of x (read by the sweeps,
+// never written) and take no part in the colouring
+int b200sp_gs_symbolic_nc_i32(b200sp_gs_plan* p, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
+                              int is_graph_symmetric) {
   B200SP_REQUIRE(p != nullptr, "gauss_seidel_symbolic: null plan");
-  B200SP_REQUIRE(n >= 0, "gauss_seidel_symbolic: negative size");
+  B200SP_REQUIRE(n >= 0 && ncols >= n, "gauss_seidel_symbolic: needs 0 <= num_rows <= num_cols (got %d x %d)", n, ncols);
   cudaStream_t st = (cudaStream_t)stream;
   gs_release(p, st);
   p->n = n;
+  p->ncols = ncols;
   p->num_colors = 0;
   p->h_color_ptr.assign(1, 0);
   if (n == 0) {
@@ -349,10 +359,10 @@ int b200sp_gs_symbolic_i32(b200sp_gs_plan* p, void* stream, int n, const int* ro
       *bmax = nullptr, *dmax = nullptr;
   long long *bsum = nullptr, *dtotal = nullptr;
   if (!is_graph_symmetric && nnz > 0) {  // colour on pattern(A) + pattern(A^T)
-    B200SP_CUDA_TRY(tmp.alloc(&trp, (size_t)n + 1));
+    B200SP_CUDA_TRY(tmp.alloc(&trp, (size_t)ncols + 1));  // rows 0 .. n-1 of A^T are the ones the colouring reads
     B200SP_CUDA_TRY(tmp.alloc(&tci, (size_t)nnz));
     B200SP_CUDA_TRY(tmp.alloc(&tsrc, (size_t)nnz));
-    const int rc = transpose_structure(st, n, n, nnz, row_ptr, col_idx, trp, tci, tsrc);
+    const int rc = transpose_structure(st, n, ncols, nnz, row_ptr, col_idx, trp, tci, tsrc);
     if (rc != B200SP_OK) return rc;
   }
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->colors, sizeof(int) * (size_t)n, st));

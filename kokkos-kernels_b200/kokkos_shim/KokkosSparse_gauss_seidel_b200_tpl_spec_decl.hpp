@@ -101,10 +101,9 @@ inline int b200_gs_kind(KernelHandle* handle) {  // 0 point, 1 two-stage (inner 
         gs2->set_call_numeric(false);                                                                                  \
         return;                                                                                                        \
       }                                                                                                                \
-      if (num_rows != num_cols) throw std::runtime_error("KokkosSparse::gauss_seidel_symbolic[TPL_B200]: square matrices only"); \
       auto* gsh = handle->get_point_gs_handle();                                                                       \
-      KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_gs_symbolic_i32(b200_gs_plan_of(gsh), (void*)exec.cuda_stream(), num_rows, row_map.data(), \
-                                                              entries.data(), is_graph_symmetric ? 1 : 0));            \
+      KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_gs_symbolic_nc_i32(b200_gs_plan_of(gsh), (void*)exec.cuda_stream(), num_rows, num_cols, \
+                                                                 row_map.data(), entries.data(), is_graph_symmetric ? 1 : 0)); \
       gsh->set_call_symbolic(true);                                                                                    \
       gsh->set_call_numeric(false);                                                                                    \
     }                                                                                                                  \

@@ -481,9 +481,10 @@ def gauss_seidel_symbolic(handle, num_rows, num_cols, row_map, entries, is_graph
         check(_lib.sparse().b200sp_gs2_symbolic_i32(gh._plan, _stream(), int(num_rows), int(num_cols), _idx(row_map), _idx(entries)))
         gh._symbolic, gh._numeric = True, False
         return
-    if num_rows != num_cols:
-        raise B200SparseError("b200sparse: point Gauss-Seidel needs a square matrix")
-    check(_lib.sparse().b200sp_gs_symbolic_i32(gh._plan, _stream(), int(num_rows), _idx(row_map), _idx(entries), int(bool(is_graph_symmetric))))
+    if num_cols < num_rows:
+        raise B200SparseError("b200sparse: Gauss-Seidel needs num_cols >= num_rows (columns beyond num_rows are ghost entries of x)")
+    check(_lib.sparse().b200sp_gs_symbolic_nc_i32(gh._plan, _stream(), int(num_rows), int(num_cols), _idx(row_map), _idx(entries),
+                                                  int(bool(is_graph_symmetric))))
     gh._symbolic, gh._numeric = True, False
 
 

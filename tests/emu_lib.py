@@ -278,8 +278,11 @@ class GsPlan:
             ok(lib().b200sp_gs_plan_destroy(self.h, None))
             self.h = C.c_void_p()
 
-    def symbolic(self, n, rp, ci, symmetric):
-        ok(lib().b200sp_gs_symbolic_i32(self.h, None, n, ptr(rp), ptr(ci), int(symmetric)))
+    def symbolic(self, n, rp, ci, symmetric, ncols=None):
+        if ncols is None:
+            ok(lib().b200sp_gs_symbolic_i32(self.h, None, n, ptr(rp), ptr(ci), int(symmetric)))
+        else:
+            ok(lib().b200sp_gs_symbolic_nc_i32(self.h, None, n, ncols, ptr(rp), ptr(ci), int(symmetric)))
 
     def numeric(self, n, rp, ci, v):
         return getattr(lib(), "b200sp_gs_numeric_%s_i32" % sfx(v.dtype))(self.h, None, n, ptr(rp), ptr(ci), ptr(v))

@@ -199,3 +199,44 @@ def test_pcg_with_symmetric_gauss_seidel(emu, oracle):
         assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-8
     plan.close()
     gs.close()
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_ghost_columns(emu, oracle, symmetric):
+    """num_cols > num_rows -- the local matrix of a distributed one (what Ifpack2 / MueLu pass): columns >= num_rows are ghost entries
+    of x, read by the sweeps, never written, outside the colouring; init_zero_x zeroes all of x as the reference does."""
+    from test_oracle_gs2 import dd_matrix
+
+    n, ghosts = 2500, 70
+    rp, ci, v = dd_matrix(n, 31, extra_cols=ghosts)
+    ncols = n + ghosts
+    if symmetric:  # symmetrise the square part, keep the ghost columns
+        A = sps.csr_matrix((v, ci, rp), shape=(n, ncols)).tocsc()
+        S = ((A[:, :n] + A[:, :n].T) * 0.5)
+        A = sps.hstack([S, A[:, n:]]).tocsr()
+        A.sort_indices()
+        rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    plan = E.GsPlan()
+    plan.symbolic(n, rp, ci, symmetric, ncols=ncols)
+    nc, colors, cptr, crows = plan.coloring(n)
+    sq = ci < n  # the colouring is of the square part (symmetrised when the graph is not symmetric)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    G = sps.csr_matrix((np.ones(sq.sum()), (rows[sq], ci[sq])), shape=(n, n))
+    G = (G + G.T).tocsr()
+    check_coloring(n, G.indptr, G.indices, nc, colors, cptr, crows)
+    assert plan.numeric(n, rp, ci, v) == 0
+    dinv = 1.0 / np.bincount(rows[rows == ci], weights=v[rows == ci], minlength=n)
+    rng = np.random.default_rng(5)
+    b = rng.uniform(-1, 1, n)
+    x0 = rng.uniform(-1, 1, ncols)
+    for direction in (0, 1, 2):
+        x = x0.copy()
+        assert plan.apply(n, rp, ci, v, x, b, False, 0.9, 2, direction) == 0
+        xo = oracle.gs_apply(rp, ci, v, cptr, crows, dinv, b, x0.copy(), False, 0.9, 2, direction)
+        assert np.array_equal(x[n:], x0[n:]) and np.max(np.abs(x - xo)) <= 1e-12
+    x = x0.copy()
+    assert plan.apply(n, rp, ci, v, x, b, True, 1.0, 1, 0) == 0
+    xo = oracle.gs_apply(rp, ci, v, cptr, crows, dinv, b, np.zeros(ncols), False, 1.0, 1, 0)
+    assert np.all(x[n:] == 0) and np.max(np.abs(x - xo)) <= 1e-12
+    assert E.lib().b200sp_gs_symbolic_nc_i32(plan.h, None, n, n - 1, E.ptr(rp), E.ptr(ci), 1) == 1  # fewer columns than rows
+    plan.close()

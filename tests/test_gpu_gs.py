@@ -75,3 +75,31 @@ def test_pcgsolve_sgs(cuda, oracle):
     xd2 = torch.zeros(n, dtype=torch.float64, device=cuda)
     res2 = sp.pcgsolve(None, A, t(b), xd2, 100000, 1e-7, 8, use_sgs=True)  # handles created inside, as the reference's driver does
     assert res2.iteration == res.iteration
+
+
+def test_gauss_seidel_ghost_columns(cuda, oracle):
+    """num_cols > num_rows (the local matrix of a distributed one): ghost entries of x are read, never written."""
+    from kokkos_kernels_b200 import sparse as sp
+    from test_oracle_gs2 import dd_matrix
+
+    n, ghosts = 20000, 300
+    rp, ci, v = dd_matrix(n, 31, extra_cols=ghosts)
+    ncols = n + ghosts
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    rpd, cid, vd = t(rp), t(ci), t(v)
+    kh = sp.KokkosKernelsHandle()
+    kh.create_gs_handle()
+    sp.gauss_seidel_symbolic(kh, n, ncols, rpd, cid, False)
+    sp.gauss_seidel_numeric(kh, n, ncols, rpd, cid, vd, False)
+    colors, cptr, crows = kh.get_gs_handle().get_coloring(n)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    dinv = 1.0 / np.bincount(rows[rows == ci], weights=v[rows == ci], minlength=n)
+    rng = np.random.default_rng(5)
+    b, x0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, ncols)
+    for direction, fn in enumerate((sp.symmetric_gauss_seidel_apply, sp.forward_sweep_gauss_seidel_apply, sp.backward_sweep_gauss_seidel_apply)):
+        xd = t(x0)
+        fn(kh, n, ncols, rpd, cid, vd, xd, t(b), False, True, 0.9, 2)
+        torch.cuda.synchronize()
+        x = xd.cpu().numpy()
+        xo = oracle.gs_apply(rp, ci, v, cptr, crows, dinv, b, x0.copy(), False, 0.9, 2, direction)
+        assert np.array_equal(x[n:], x0[n:]) and np.max(np.abs(x - xo)) <= 1e-12
