@@ -134,63 +134,72 @@ __global__ void __launch_bounds__(256) gs2_values_kernel(int n, const int* __res
 }
 
 // the vector steps between the SpMVs; every expression is the one the reference's KokkosBlas sequence evaluates.  All of them
-// run over an n x k block (k right-hand sides, column-major): element e -> row e % n, column e / n; the work vectors R, T, Z
-// have leading dimension n, x and b the caller's.
+// run over an n x k block (k right-hand sides, column-major): blockIdx.y is the column, so no index is ever divided; the work
+// vectors R, T, Z have leading dimension n, x and b the caller's.
+#define GS2_ROWS(i) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_copy_kernel(int64_t total, int n, const S* __restrict__ a, int64_t lda, S* __restrict__ out,
+__global__ void __launch_bounds__(256) gs2_copy_kernel(int n, const S* __restrict__ a, int64_t lda, S* __restrict__ out,
                                                        int64_t ldo) {  // scal(out, one, a)
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e % n, j = e / n;
-    out[i + j * ldo] = S(1) * a[i + j * lda];
-  }
+  a += blockIdx.y * lda;
+  out += blockIdx.y * ldo;
+  GS2_ROWS(i) out[i] = S(1) * a[i];
 }
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_diag_term_kernel(int64_t total, int n, const S* __restrict__ Da, const S* __restrict__ x, int64_t ldx,
-                                                            S omega2, S* __restrict__ Z, S* __restrict__ R) {  // Z = Da.*x;  R += omega2 Z
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e % n, j = e / n;
-    const S z = S(1) * Da[i] * x[i + j * ldx];
-    Z[e] = z;
-    R[e] += omega2 * z;
+__global__ void __launch_bounds__(256) gs2_diag_term_kernel(int n, const S* __restrict__ Da, const S* __restrict__ x, int64_t ldx, S omega2,
+                                                            S* __restrict__ Z, S* __restrict__ R) {  // Z = Da.*x;  R += omega2 Z
+  x += blockIdx.y * ldx;
+  Z += (int64_t)blockIdx.y * n;
+  R += (int64_t)blockIdx.y * n;
+  GS2_ROWS(i) {
+    const S z = S(1) * Da[i] * x[i];
+    Z[i] = z;
+    R[i] += omega2 * z;
   }
 }
 // inner == 0:  Z = D.*R (times gamma);  else  T = D.*R, R = T (times gamma)
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_start_kernel(int64_t total, int n, const S* __restrict__ D, S* __restrict__ R, S* __restrict__ T,
-                                                        S* __restrict__ Z, S gamma, int inner) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const S t = S(1) * D[e % n] * R[e];
+__global__ void __launch_bounds__(256) gs2_start_kernel(int n, const S* __restrict__ D, S* __restrict__ R, S* __restrict__ T, S* __restrict__ Z,
+                                                        S gamma, int inner) {
+  const int64_t off = (int64_t)blockIdx.y * n;
+  R += off;
+  T += off;
+  Z += off;
+  GS2_ROWS(i) {
+    const S t = S(1) * D[i] * R[i];
     if (inner == 0) {
-      Z[e] = (gamma != S(1)) ? gamma * t : t;
+      Z[i] = (gamma != S(1)) ? gamma * t : t;
     } else {
-      T[e] = t;
+      T[i] = t;
       const S r = S(1) * t;
-      R[e] = (gamma != S(1)) ? gamma * r : r;
+      R[i] = (gamma != S(1)) ? gamma * r : r;
     }
   }
 }
 // after Z = T - omega M R:  gamma != 1: Z = gamma Z + (1 - gamma) R;  not the last inner sweep: R = Z
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_inner_kernel(int64_t total, S* __restrict__ Z, S* __restrict__ R, S gamma, int copy_back) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    S z = Z[e];
+__global__ void __launch_bounds__(256) gs2_inner_kernel(int n, S* __restrict__ Z, S* __restrict__ R, S gamma, int copy_back) {
+  Z += (int64_t)blockIdx.y * n;
+  R += (int64_t)blockIdx.y * n;
+  GS2_ROWS(i) {
+    S z = Z[i];
     if (gamma != S(1)) {
       z = gamma * z;
-      z += (S(1) - gamma) * R[e];
-      Z[e] = z;
+      z += (S(1) - gamma) * R[i];
+      Z[i] = z;
     }
-    if (copy_back) R[e] = S(1) * z;
+    if (copy_back) R[i] = S(1) * z;
   }
 }
 template <typename S>
-__global__ void __launch_bounds__(256) gs2_update_kernel(int64_t total, int n, const S* __restrict__ Z, S omega, S* __restrict__ x, int64_t ldx,
-                                                         int compact) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = e % n + (e / n) * ldx;
-    if (compact) x[q] = omega * Z[e];
-    else x[q] += omega * Z[e];
+__global__ void __launch_bounds__(256) gs2_update_kernel(int n, const S* __restrict__ Z, S omega, S* __restrict__ x, int64_t ldx, int compact) {
+  Z += (int64_t)blockIdx.y * n;
+  x += blockIdx.y * ldx;
+  GS2_ROWS(i) {
+    if (compact) x[i] = omega * Z[i];
+    else x[i] += omega * Z[i];
   }
 }
+#undef GS2_ROWS
 
 inline int vec_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8)); }
 
@@ -277,6 +286,7 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
   cudaStream_t st = (cudaStream_t)stream;
   B200SP_REQUIRE(p != nullptr, "gs2_apply: null plan");
   B200SP_REQUIRE(direction >= 0 && direction <= 2, "gs2_apply: direction %d not in {0 symmetric, 1 forward, 2 backward}", direction);
+  B200SP_REQUIRE(nrhs <= 65535, "gs2_apply: at most 65535 right-hand sides per call (got %d)", nrhs);
   B200SP_REQUIRE(nrhs >= 0 && num_iter >= 0, "gs2_apply: negative count (nrhs=%d numIter=%d)", nrhs, num_iter);
   if (!p->numeric || p->n != n || p->ncols != ncols || p->key_rp != row_ptr || p->key_ci != col_idx || p->scalar_bytes != (int)sizeof(S)) {
     set_error("gs2_apply: numeric was not called on this plan with this matrix and scalar type");
@@ -301,7 +311,7 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
   }
   S *R = (S*)p->R, *T = (S*)p->T, *Z = (S*)p->Z;
   const S *D = (const S*)p->D, *Da = (const S*)p->Da;
-  const int nb = vec_blocks(total);
+  const dim3 nb((unsigned)vec_blocks(n), (unsigned)k);  // blockIdx.y = right-hand side
   if (k == 1) {
     ldx = ncols;
     ldb = n;
@@ -312,7 +322,7 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
     for (int j = 0; j < k; ++j) B200SP_CUDA_TRY(cudaMemsetAsync(x + (int64_t)j * ldx, 0, sizeof(S) * (size_t)ncols, st));
   for (int sweep = 0; sweep < sweeps; ++sweep) {
     const bool forward = direction == 1 || (direction == 0 && sweep % 2 == 0);
-    gs2_copy_kernel<S><<<nb, 256, 0, st>>>(total, n, b, ldb, R, (int64_t)n);
+    gs2_copy_kernel<S><<<nb, 256, 0, st>>>(n, b, ldb, R, (int64_t)n);
     B200SP_LAUNCH_CHECK();
     int rc = B200SP_OK;
     if (sweep > 0 || !init_zero_x) {
@@ -321,7 +331,7 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
         rc = product<S>(p->plan[q], stream, n, ncols, p->cnt[q], k, -one, p->rp[q], p->ci[q], (const S*)p->v[q], x, ldx, one, R, n);
         if (rc) return rc;
         if (omega != one) {
-          gs2_diag_term_kernel<S><<<nb, 256, 0, st>>>(total, n, Da, x, ldx, one / omega - one, Z, R);
+          gs2_diag_term_kernel<S><<<nb, 256, 0, st>>>(n, Da, x, ldx, one / omega - one, Z, R);
           B200SP_LAUNCH_CHECK();
         }
       } else {
@@ -329,23 +339,23 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
         if (rc) return rc;
       }
     }
-    gs2_start_kernel<S><<<nb, 256, 0, st>>>(total, n, D, R, T, Z, gamma, p->inner);
+    gs2_start_kernel<S><<<nb, 256, 0, st>>>(n, D, R, T, Z, gamma, p->inner);
     B200SP_LAUNCH_CHECK();
     for (int ii = 0; ii < p->inner; ++ii) {
-      gs2_copy_kernel<S><<<nb, 256, 0, st>>>(total, n, T, (int64_t)n, Z, (int64_t)n);
+      gs2_copy_kernel<S><<<nb, 256, 0, st>>>(n, T, (int64_t)n, Z, (int64_t)n);
       B200SP_LAUNCH_CHECK();
       const int q = forward ? kL : kU;
       rc = product<S>(p->plan[q], stream, n, n, p->cnt[q], k, -omega, p->rp[q], p->ci[q], (const S*)p->v[q], R, n, one, Z, n);
       if (rc) return rc;
       const int copy_back = ii + 1 < p->inner;
       if (gamma != one) {
-        gs2_inner_kernel<S><<<nb, 256, 0, st>>>(total, Z, R, gamma, copy_back);
+        gs2_inner_kernel<S><<<nb, 256, 0, st>>>(n, Z, R, gamma, copy_back);
         B200SP_LAUNCH_CHECK();
       } else if (copy_back) {
         std::swap(R, Z);  // R = 1 * Z is exact: the next inner sweep reads the buffer just written, no copy
       }
     }
-    gs2_update_kernel<S><<<nb, 256, 0, st>>>(total, n, Z, omega, x, ldx, p->compact ? 1 : 0);
+    gs2_update_kernel<S><<<nb, 256, 0, st>>>(n, Z, omega, x, ldx, p->compact ? 1 : 0);
     B200SP_LAUNCH_CHECK();
   }
   return B200SP_OK;
