@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <limits.h>
 #include "common.cuh"
 
 namespace b200sp {
@@ -37,6 +38,15 @@ namespace {
 template <typename S>
 __global__ void bsr_scale_kernel(int64_t rows, int k, S beta, S* __restrict__ y, int64_t yr, int64_t yc) {
   const int64_t total = rows * k;
+  if (total <= (int64_t)INT32_MAX) {  // 32-bit index arithmetic (a 64-bit division per element costs more than its traffic)
+    const unsigned t32 = (unsigned)total, r32 = (unsigned)rows, step = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < t32; i += step) {
+      const unsigned c = i / r32, r = i - c * r32;
+      S* p = y + (int64_t)r * yr + (int64_t)c * yc;
+      *p = (beta == S(0)) ? S(0) : beta * *p;
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i % rows, c = i / rows;
     S* p = y + r * yr + c * yc;

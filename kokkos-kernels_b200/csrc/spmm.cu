@@ -15,6 +15,7 @@
 //   spmm_transpose_kernel T/H modes: Y pre-scaled, atomicAdd scatter.
 // Column-major (LayoutLeft) X with k >= 4 goes through a transposed copy so the
 // gather touches one segment per nonzero instead of k sectors.
+#include <limits.h>
 #include "common.cuh"
 #include "tile_ring.cuh"
 #include <algorithm>
@@ -32,10 +33,20 @@ void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s);
 template <typename S>
 __global__ void scale2d_kernel(int64_t rows, int k, S beta, S* __restrict__ Y, int64_t yr, int64_t yc) {
   const int64_t total = rows * k;
+  const bool by_rows = (yc == 1 || yr != 1);  // walk memory-contiguously for either layout
+  if (total <= (int64_t)INT32_MAX) {  // 32-bit index arithmetic: a 64-bit division per element costs more than the element's traffic
+    const unsigned t32 = (unsigned)total, k32 = (unsigned)k, r32 = (unsigned)rows, step = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < t32; i += step) {
+      unsigned r, j;
+      if (by_rows) { r = i / k32; j = i - r * k32; } else { j = i / r32; r = i - j * r32; }
+      S* p = &Y[(int64_t)r * yr + (int64_t)j * yc];
+      *p = (beta == S(0)) ? S(0) : beta * *p;
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // walk memory-contiguously for either layout
     int64_t r, j;
-    if (yc == 1 || yr != 1) { r = i / k; j = i % k; } else { j = i / rows; r = i % rows; }
+    if (by_rows) { r = i / k; j = i % k; } else { j = i / rows; r = i % rows; }
     S* p = &Y[r * yr + j * yc];
     *p = (beta == S(0)) ? S(0) : beta * *p;
   }
