@@ -6,7 +6,7 @@
 #      host-vector deferred completion, the shim driver with every flag
 #   3. the headline bench (SpMV config 2; its e2e leg times the stream-ordered and the deferred host-vector modes)
 #   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
-# then, in a second call, tools/round2_second_call.sh (full-size timings of every suite incl. the 2.2e9-entry matrix, ncu).
+# then tools/round2_promote.sh (gpu_next -> gpu) and, in a second call, tools/round2_second_call.sh (full-size timings of every suite incl. the 2.2e9-entry matrix, ncu).
 # Outputs land in gpurun_out/ (copy the summaries to profiles/ afterwards).  On success change `gpu_next` to `gpu` in
 # tests/test_gpu_{jacobi,bsr,cg,gmres,gs,gs2,spmv64,hostvec_defer}.py and tests/test_shim.py.
 set -u
