@@ -150,6 +150,26 @@ def _cpu_spmv(orc):
         "oracle O2 (OpenMP functor order, spmv_impl.hpp:110-132)"
 
 
+def _best_threads(run, rps, cis, vas, ncols, x, y, threads):
+    """The thread count the CPU loop is fastest with on this box among all / half / a quarter of the hardware threads (SMT siblings
+    and a second socket do not always help a streaming loop): the baseline is the reference at its best, not at a default."""
+    best, best_t, tried = threads, None, []
+    for t in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
+        try:
+            run(rps, cis, vas, ncols, x, y, t)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                run(rps, cis, vas, ncols, x, y, t)
+                ts.append(time.perf_counter() - t0)
+        except Exception:
+            continue
+        tried.append((t, min(ts)))
+        if best_t is None or min(ts) < best_t:
+            best, best_t = t, min(ts)
+    return best, ", ".join(f"{t} threads {ms * 1e3:.1f} ms" for t, ms in tried)
+
+
 def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
     """The reference's host SpMV (see _cpu_spmv) on the first `rows` rows of the same matrix with the full x: a bounded sample
     of the workload.  Returns (gflops, dict)."""
@@ -165,6 +185,7 @@ def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
     y = orc.first_touch_copy(np.zeros(rows), threads)
     ncols = len(x)
     run(rps, cis, vas, ncols, x, y, threads)  # warm-up / first touch
+    threads, sweep = _best_threads(run, rps, cis, vas, ncols, x, y, threads)
     t0 = time.perf_counter()
     run(rps, cis, vas, ncols, x, y, threads)
     one = time.perf_counter() - t0
@@ -179,7 +200,8 @@ def cpu_sample(rp, ci, va, x, threads, seconds_budget=12.0, rows=1_250_000):
     return gf, {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
                 "sample": f"{what}, first {rows} rows of the same "
                           f"matrix ({nnz} nnz), full x, {iters} iterations, mean {mean * 1e3:.2f} ms, "
-                          f"min {min(ts) * 1e3:.2f} ms; {alg_bytes(nnz, rows, ncols) / mean / 1e9:.1f} GB/s algorithmic"}
+                          f"min {min(ts) * 1e3:.2f} ms; {alg_bytes(nnz, rows, ncols) / mean / 1e9:.1f} GB/s algorithmic; "
+                          f"thread count chosen by a sweep ({sweep})"}
 
 
 def run_reference(args, emit):
@@ -204,6 +226,7 @@ def run_reference(args, emit):
     nnz = int(rp[-1])
     # pages first touched by the threads that will stream them (parallel initialisation, reference protocol)
     rp, ci, va, x, y = (orc.first_touch_copy(a, threads) for a in (rp, ci, va, x, y))
+    threads, sweep = _best_threads(run, rp, ci, va, ncols, x, y, threads)
     for _ in range(max(args.warmup, 1)):
         run(rp, ci, va, ncols, x, y, threads)
     t0 = time.perf_counter()
@@ -218,7 +241,7 @@ def run_reference(args, emit):
         "config": {"workload": f"spmv fp64 CrsMatrix lap27({GRID}^3)x{NDOF}dof family, bounded sample: first {rows} rows "
                                f"({nnz} nnz) per step, alpha=1 beta=0"},
         "cpu_baseline": {"value": round(gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
-                         "sample": f"{what}, {rows} rows x {nnz} nnz per step"},
+                         "sample": f"{what}, {rows} rows x {nnz} nnz per step; thread count chosen by a sweep ({sweep})"},
         "e2e": {"value": round(gf, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
