@@ -1,0 +1,34 @@
+"""bench.py --impl reference on the host (no GPU needed): one JSON line with the keys the contract names -- impl, metric, unit,
+value, config.workload, cpu_baseline {kind, cores, sample, value = the line's}, e2e with zero copy bytes -- timing the reference's
+own SPMV_Functor (oracle/_ref) when that library is present."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]  # ONE JSON line on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "spmv_fp64_gflops" and d["unit"] == "GFLOP/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sweep" in cb["sample"]
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libkkref.so")):
+        assert cb["kind"] == "reference"
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
