@@ -28,6 +28,7 @@
 //    in-place bitonic sort kernel.
 #include "common.cuh"
 #include "scan.cuh"
+#include "spgemm_esc.cuh"
 #include <algorithm>
 #include <limits.h>
 #include <stdlib.h>
@@ -120,6 +121,22 @@ __global__ void bin_scatter_kernel(int m, const int* __restrict__ key, BinSpec s
                                    int* __restrict__ rows_out) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x)
     rows_out[atomicAdd(&cursors[bin_of(spec, key[r])], 1)] = r;
+}
+
+// ESC bin key of a row (spgemm_esc.cuh): max(products, 2 * nnz(A_i)), saturated
+__global__ void esc_key_kernel(int m, const int* __restrict__ flops, const int* __restrict__ rpA, int* __restrict__ key) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const long long na2 = 2LL * (rpA[r + 1] - rpA[r]);
+    key[r] = (int)min(max((long long)flops[r], na2), (long long)INT_MAX);
+  }
+}
+// old-path bin key: 0 for rows the ESC kernels take (key <= cap), else max(nnz(C_i), 1); all_rows: every row by nnz(C_i)
+__global__ void rest_key_kernel(int m, const int* __restrict__ esc_key, int cap, const int* __restrict__ rpC, int all_rows,
+                                int* __restrict__ key) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const int nz = rpC[r + 1] - rpC[r];
+    key[r] = all_rows ? nz : (esc_key[r] <= cap ? 0 : max(nz, 1));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -958,6 +975,10 @@ static constexpr int kSymBins = 6;
 static const int kNumThr[] = {64, 256, 1024, 4096, 8192};
 static constexpr int kNumBins = 6;
 static constexpr int kFbCtas = 16;
+// ESC kernels (spgemm_esc.cuh): bins by max(products, 2 nnz(A_i)); rows above the last threshold -> hash kernels
+static const int kEscThr[] = {256, 1024, 4096, 8192};
+static constexpr int kEscBins = 4;
+static constexpr int kEscCap = 8192;
 
 struct b200sp_spgemm_plan {
   bool symbolic_done = false;
@@ -969,9 +990,17 @@ struct b200sp_spgemm_plan {
   // device state kept for numeric
   int *cmin = nullptr, *cmax = nullptr;
   int* flops = nullptr;     // products per row of A*B (numeric variant 2 parks them in shared memory)
-  int numeric_variant = 1;  // 1: two-walk num_hash_kernel, 2/3/4: num2_kernel flavours (B200SP_SPGEMM_NUMERIC)
-  int* num_rows = nullptr;  // rows grouped by numeric bin
+  int numeric_variant = 7;  // 7: ESC kernels (spgemm_esc.cuh) + hash kernels for long rows; 1: two-walk num_hash_kernel, 2..6: num2_kernel flavours (B200SP_SPGEMM_NUMERIC)
+  int* num_rows = nullptr;  // rows grouped by numeric bin (hash kernels): the rows beyond the ESC kernels' capacity
   int num_off[kNumBins + 1] = {0};
+  int* all_rows = nullptr;  // every row grouped by nnz(C_i): built on demand for the hash variants and spgemm_jacobi
+  int all_off[kNumBins + 1] = {0};
+  bool all_built = false;
+  const int* cur_rows = nullptr;  // the grouping the hash-kernel launchers read (num_rows or all_rows)
+  const int* cur_off = nullptr;
+  int* esc_key = nullptr;   // per row: max(products, 2 nnz(A_i))
+  int* esc_rows = nullptr;  // rows grouped by ESC bin
+  int esc_off[kEscBins + 3] = {0};
   int *fb_rows = nullptr, *fb_count = nullptr;
   int fb_static = 0;
   int fb_log2 = 1;
@@ -983,10 +1012,15 @@ struct b200sp_spgemm_plan {
 namespace b200sp {
 
 static void spgemm_release(b200sp_spgemm_plan* p, cudaStream_t st) {
-  void* ptrs[] = {p->cmin, p->cmax, p->flops, p->num_rows, p->fb_rows, p->fb_count, p->fb_keys, p->fb_vals};
+  void* ptrs[] = {p->cmin, p->cmax, p->flops, p->num_rows, p->fb_rows, p->fb_count, p->fb_keys, p->fb_vals,
+                  p->all_rows, p->esc_key, p->esc_rows};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, st);
   p->cmin = p->cmax = p->flops = p->num_rows = p->fb_rows = p->fb_count = p->fb_keys = nullptr;
+  p->all_rows = p->esc_key = p->esc_rows = nullptr;
+  p->all_built = false;
+  p->cur_rows = nullptr;
+  p->cur_off = nullptr;
   p->fb_vals = nullptr;
   p->fb_vals_bytes = 0;
   p->symbolic_done = false;
@@ -1019,7 +1053,8 @@ static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const
   constexpr int RPC = THREADS / G;
   const size_t smem = sizeof(int) * (size_t)RPC * ((size_t)1 << LOG2SLOTS);
   auto kern = sym_hash_kernel<G, LOG2SLOTS, V2>;
-  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // always: the 48 KB default limit counts the kernel's STATIC shared memory too (walker staging, flags)
+  B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, rows, std::min(lb, 32), rpA, ciA, rpB, ciB, row_nnz);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
@@ -1028,15 +1063,16 @@ static int launch_sym(cudaStream_t st, int nrows, const int* rows, int lb, const
 template <typename S, int G, int KSLOTS, int PAD, int VCAP>
 static int launch_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
                       const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
-  const int nrows = p->num_off[bin + 1] - p->num_off[bin];
+  const int nrows = p->cur_off[bin + 1] - p->cur_off[bin];
   if (nrows <= 0) return B200SP_OK;
   using L = NumLayout<S, G, KSLOTS, PAD, VCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = L::PER_AL * RPC;
   auto kern = num_hash_kernel<S, G, KSLOTS, PAD, VCAP>;
-  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
+  // always: the 48 KB default limit counts the kernel's STATIC shared memory too (walker staging, flags)
+  B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->cur_rows + p->cur_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
                                                       rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->fb_rows, p->fb_count);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
@@ -1046,18 +1082,65 @@ template <typename S, int G, int KSLOTS, int PAD, int VCAP, int PCAP, bool EMIT2
 static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
                        const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC, S omega = S(0),
                        const S* dinv = nullptr) {
-  const int nrows = p->num_off[bin + 1] - p->num_off[bin];
+  const int nrows = p->cur_off[bin + 1] - p->cur_off[bin];
   if (nrows <= 0) return B200SP_OK;
   using L = Num2Layout<S, G, KSLOTS, PAD, VCAP, PCAP>;
   constexpr int THREADS = (G <= 32 ? 256 : G);
   constexpr int RPC = THREADS / G;
   const size_t smem = L::PER_AL * RPC;
   auto kern = num2_kernel<S, G, KSLOTS, PAD, VCAP, PCAP, EMIT2, JAC, FASTW>;
-  if (smem > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->num_rows + p->num_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
+  // always: the 48 KB default limit counts the kernel's STATIC shared memory too (walker staging, flags)
+  B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nrows + RPC - 1) / RPC, THREADS, smem, st>>>(nrows, p->cur_rows + p->cur_off[bin], std::min(p->lb, 32), rpA, ciA, vA,
                                                       rpB, ciB, vB, rpC, ciC, vC, p->cmin, p->cmax, p->flops, p->fb_rows,
                                                       p->fb_count, omega, dinv);
   B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <int T, int I, int MINB>
+static int launch_esc_sym(cudaStream_t st, int nrows, const int* rows, const int* rpA, const int* ciA, const int* rpB,
+                          const int* ciB, const int* flops, int* row_nnz) {
+  if (nrows <= 0) return B200SP_OK;
+  using L = EscSymLayout<T, I>;
+  auto kern = esc_sym_kernel<T, I, MINB>;
+  if (L::BYTES > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+  kern<<<nrows, T, L::BYTES, st>>>(nrows, rows, rpA, ciA, rpB, ciB, flops, row_nnz);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+template <typename S, int T, int I, int LOG2NB, int MINB>
+static int launch_esc_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const int* rpA, const int* ciA, const S* vA,
+                          const int* rpB, const int* ciB, const S* vB, const int* rpC, int* ciC, S* vC) {
+  const int nrows = p->esc_off[bin + 1] - p->esc_off[bin];
+  if (nrows <= 0) return B200SP_OK;
+  using L = EscNumLayout<S, T, I, LOG2NB>;
+  auto kern = esc_num_kernel<S, T, I, LOG2NB, MINB>;
+  if (L::BYTES > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+  kern<<<nrows, T, L::BYTES, st>>>(nrows, p->esc_rows + p->esc_off[bin], rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, p->cmin,
+                                   p->cmax, p->flops);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+// every row grouped by nnz(C_i) (the hash variants B200SP_SPGEMM_NUMERIC=1..6 and spgemm_jacobi); built once, synchronises
+static int ensure_all_bins(b200sp_spgemm_plan* p, cudaStream_t st, const int* rpC) {
+  if (p->all_built) return B200SP_OK;
+  DevTmp tmp(st);
+  int *key, *d_counts;
+  B200SP_CUDA_TRY(tmp.alloc(&key, p->m));
+  B200SP_CUDA_TRY(tmp.alloc(&d_counts, MAXBINS));
+  if (!p->all_rows) B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->all_rows, sizeof(int) * (size_t)p->m, st));
+  const int blocks = std::max(1, std::min((p->m + 255) / 256, sm_count() * 8));
+  rest_key_kernel<<<blocks, 256, 0, st>>>(p->m, nullptr, 0, rpC, 1, key);
+  B200SP_LAUNCH_CHECK();
+  BinSpec nspec;
+  nspec.nb = kNumBins;
+  for (int b = 0; b < kNumBins - 1; ++b) nspec.thr[b] = kNumThr[b];
+  const int rc = bin_rows(st, p->m, key, nspec, d_counts, p->all_rows, p->all_off);
+  if (rc) return rc;
+  p->all_built = true;
   return B200SP_OK;
 }
 
@@ -1088,6 +1171,31 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   int rc;
   int variant = p->numeric_variant;
   if (const char* e = getenv("B200SP_SPGEMM_NUMERIC")) variant = atoi(e);
+  if (variant >= 7 && p->esc_rows) {
+    // default: register-resident expand / sort / compress kernels (spgemm_esc.cuh) for rows of <= 8192 products,
+    // the two-walk hash kernels for the rest
+    if ((rc = launch_esc_num<S, 32, 8, 9, 32>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if ((rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if ((rc = launch_esc_num<S, 512, 8, 13, 2>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if ((rc = launch_esc_num<S, 1024, 8, 14, 1>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if (p->esc_off[kEscBins] < m) {
+      p->cur_rows = p->num_rows;
+      p->cur_off = p->num_off;
+      if ((rc = launch_num<S, 32, 256, 32, 64>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+      if ((rc = launch_num<S, 32, 1024, 64, 256>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+      if ((rc = launch_num<S, 128, 4096, 128, 1024>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+      if ((rc = launch_num<S, 256, 16384, 256, 4096>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+      if ((rc = launch_num<S, 512, 32768, 512, 8192>(st, p, 4, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+      num_fallback_kernel<S><<<kFbCtas, 256, 0, st>>>(p->fb_rows, p->fb_count, p->fb_log2, p->fb_keys, (S*)p->fb_vals, rpA,
+                                                      ciA, vA, rpB, ciB, vB, rpC, ciC, vC);
+      B200SP_LAUNCH_CHECK();
+    }
+    return B200SP_OK;
+  }
+  if (variant >= 7) variant = 1;
+  if ((rc = ensure_all_bins(p, st, rpC))) return rc;
+  p->cur_rows = p->all_rows;
+  p->cur_off = p->all_off;
   if (variant == 6) {  // variant 5 + occupancy words from 16-byte key loads and a scan that keeps every warp busy
 #define NUM6(B, G, KS, PAD, VCAP)                                                                                 \
   if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, true, false, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
@@ -1183,6 +1291,9 @@ static int jacobi_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int
   }
   B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_count, &p->fb_static, sizeof(int), cudaMemcpyHostToDevice, st));
   int rc;
+  if ((rc = ensure_all_bins(p, st, rpC))) return rc;
+  p->cur_rows = p->all_rows;
+  p->cur_off = p->all_off;
 #define NUMJ(B, G, KS, PAD, VCAP)                                                                                       \
   if ((rc = launch_num2<S, G, KS, PAD, VCAP, 0, false, true>(st, p, B, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, omega, \
                                                             dinv)))                                                     \
@@ -1304,16 +1415,43 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
                                                                                 p->cmin, p->cmax);
   B200SP_LAUNCH_CHECK();
 
-  // ---- bin by flop bound, count distinct columns per row
-  // B200SP_SPGEMM_SYMBOLIC=2 (opt-in): tables of 2x the flop bound instead of up to 4x (a bin per power of
-  // two: half the shared memory and half the init per row for e.g. config 4's 1024-product rows), 16-byte init
-  int sym_variant = 1;
+  // ---- count distinct columns per row
+  // default (3): rows binned by max(products, 2 nnz(A_i)); up to 8192 -> esc_sym_kernel (spgemm_esc.cuh: products held in
+  // registers, hash set of 2x the bin's capacity); above -> the group-walk hash kernel / global bitmap.
+  // B200SP_SPGEMM_SYMBOLIC=1: round-1 kernels (bins by flop bound, tables of up to 4x); 2: tables of 2x, 16-byte init
+  int sym_variant = 3;
   if (const char* e = getenv("B200SP_SPGEMM_SYMBOLIC")) sym_variant = atoi(e);
   BinSpec sspec;
   int soff[MAXBINS + 1];
   int rc;
   const int lb = p->lb;
   int big_bin;
+  // ESC bins (kept on the plan: the numeric phase uses the same grouping)
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->esc_key, sizeof(int) * (size_t)m, st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->esc_rows, sizeof(int) * (size_t)m, st));
+  {
+    const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
+    esc_key_kernel<<<blocks, 256, 0, st>>>(m, flops, rpA, p->esc_key);
+    B200SP_LAUNCH_CHECK();
+    BinSpec espec;
+    espec.nb = kEscBins + 2;  // 4 ESC bins, <= 16384 (hash kernel), the rest (bitmap)
+    for (int b = 0; b < kEscBins; ++b) espec.thr[b] = kEscThr[b];
+    espec.thr[kEscBins] = 16384;
+    rc = bin_rows(st, m, p->esc_key, espec, d_counts, p->esc_rows, p->esc_off);
+    if (rc) return rc;
+  }
+  if (sym_variant >= 3) {
+    const int* er = p->esc_rows;
+    const int* eo = p->esc_off;
+    if ((rc = launch_esc_sym<32, 8, 1>(st, eo[1] - eo[0], er + eo[0], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<128, 8, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<512, 8, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<1024, 8, 1>(st, eo[4] - eo[3], er + eo[3], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
+    if ((rc = launch_sym<512, 15>(st, eo[5] - eo[4], er + eo[4], lb, rpA, ciA, rpB, ciB, row_nnz))) return rc;
+    for (int b = 0; b <= kEscBins + 2; ++b) soff[b] = eo[b];
+    sym_rows = p->esc_rows;
+    big_bin = kEscBins + 1;
+  } else
   if (sym_variant == 2) {
     static const int thr2[] = {128, 512, 1024, 2048, 4096, 8192, 16384};
     sspec.nb = 8;
@@ -1378,16 +1516,29 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   p->c_nnz = total;
   p->c_max = mx;
 
-  // ---- numeric bins by nnz(C_i) (kept on the plan so numeric stays asynchronous)
-  BinSpec nspec;
-  nspec.nb = kNumBins;
-  for (int b = 0; b < kNumBins - 1; ++b) nspec.thr[b] = kNumThr[b];
-  rc = bin_rows(st, m, row_nnz, nspec, d_counts, p->num_rows, p->num_off);
-  if (rc) return rc;
-  p->fb_static = p->num_off[kNumBins] - p->num_off[kNumBins - 1];
-  if (p->fb_static > 0)
-    B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_rows, p->num_rows + p->num_off[kNumBins - 1], sizeof(int) * (size_t)p->fb_static,
-                                    cudaMemcpyDeviceToDevice, st));
+  // ---- numeric: the ESC grouping above serves rows of <= 8192 products; the rows beyond it are grouped by nnz(C_i) for
+  // the hash kernels here (kept on the plan so that numeric stays asynchronous)
+  for (int b = 0; b <= kNumBins; ++b) p->num_off[b] = 0;
+  p->fb_static = 0;
+  if (p->esc_off[kEscBins] < m) {
+    int* key2;
+    B200SP_CUDA_TRY(tmp.alloc(&key2, m));
+    const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
+    rest_key_kernel<<<blocks, 256, 0, st>>>(m, p->esc_key, kEscCap, rpC, 0, key2);
+    B200SP_LAUNCH_CHECK();
+    BinSpec nspec;
+    nspec.nb = kNumBins + 1;  // bin 0: the ESC rows (key 0), then the hash bins
+    nspec.thr[0] = 0;
+    for (int b = 0; b < kNumBins - 1; ++b) nspec.thr[b + 1] = kNumThr[b];
+    int h_off[MAXBINS + 1];
+    rc = bin_rows(st, m, key2, nspec, d_counts, p->num_rows, h_off);
+    if (rc) return rc;
+    for (int b = 0; b <= kNumBins; ++b) p->num_off[b] = h_off[b + 1];
+    p->fb_static = p->num_off[kNumBins] - p->num_off[kNumBins - 1];
+    if (p->fb_static > 0)
+      B200SP_CUDA_TRY(cudaMemcpyAsync(p->fb_rows, p->num_rows + p->num_off[kNumBins - 1], sizeof(int) * (size_t)p->fb_static,
+                                      cudaMemcpyDeviceToDevice, st));
+  }
   int lg = 1;
   while (((long long)1 << lg) < 2LL * std::max(mx, 1)) ++lg;
   p->fb_log2 = lg;

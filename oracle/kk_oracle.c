@@ -465,6 +465,90 @@ DEF_SPGEMM_NUMERIC(okk_spgemm_numeric_f32, float)
 DEF_SORT_CRS(okk_sort_crs_f64, double)
 DEF_SORT_CRS(okk_sort_crs_f32, float)
 
+/* Row block [r0, r1) of the same product, rows dealt to OpenMP threads (each with its own dense accumulator): per row the very
+ * loops of okk_spgemm_symbolic / okk_spgemm_numeric (impl_seq.hpp:23-182) followed by the row sort (numeric_spec.hpp:138-140),
+ * so every row holds the bits the serial functions give (rows of a product are independent).  Lets the full-size parity tests
+ * (config 4: 2M rows, 2e9 products) check ALL rows in blocks without materialising C on the host.
+ * rowlen[r1-r0] out; ent/val (capacity cap entries) receive the block's rows back to back; returns the block's nnz, or -1 when
+ * cap is too small (nothing written beyond rowlen). */
+#define DEF_SPGEMM_BLOCK(NAME, ST, PAIR, CMP)                                      \
+  OKK_API int64_t NAME(int r0, int r1, int k, const int* rmA, const int* entA, const ST* valA, \
+                       const int* rmB, const int* entB, const ST* valB, int64_t cap, \
+                       int* rowlen, int* ent, ST* val, int threads) {              \
+    const int nr = r1 - r0;                                                        \
+    if (threads < 1) threads = 1;                                                  \
+    _Pragma("omp parallel num_threads(threads)")                                   \
+    {                                                                              \
+      unsigned char* acc_flag = (unsigned char*)calloc((size_t)(k > 0 ? k : 1), 1); \
+      int* cols = (int*)malloc(sizeof(int) * (size_t)(k > 0 ? k : 1));             \
+      _Pragma("omp for schedule(dynamic, 64)")                                     \
+      for (int q = 0; q < nr; ++q) {                                               \
+        const int i = r0 + q;                                                      \
+        int row_size = 0;                                                          \
+        for (int ja = rmA[i]; ja < rmA[i + 1]; ++ja) {                             \
+          const int col = entA[ja];                                                \
+          for (int jb = rmB[col]; jb < rmB[col + 1]; ++jb) {                       \
+            const int b_col = entB[jb];                                            \
+            if (!acc_flag[b_col]) { acc_flag[b_col] = 1; cols[row_size++] = b_col; } \
+          }                                                                        \
+        }                                                                          \
+        rowlen[q] = row_size;                                                      \
+        for (int j = 0; j < row_size; ++j) acc_flag[cols[j]] = 0;                  \
+      }                                                                            \
+      free(acc_flag); free(cols);                                                  \
+    }                                                                              \
+    int64_t total = 0;                                                             \
+    for (int q = 0; q < nr; ++q) total += rowlen[q];                               \
+    if (total > cap) return -1;                                                    \
+    int64_t* start = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nr + 1));         \
+    start[0] = 0;                                                                  \
+    for (int q = 0; q < nr; ++q) start[q + 1] = start[q] + rowlen[q];              \
+    _Pragma("omp parallel num_threads(threads)")                                   \
+    {                                                                              \
+      ST* accumulator = (ST*)calloc((size_t)(k > 0 ? k : 1), sizeof(ST));          \
+      unsigned char* acc_flag = (unsigned char*)calloc((size_t)(k > 0 ? k : 1), 1); \
+      PAIR* buf = NULL;                                                            \
+      int bufcap = 0;                                                              \
+      _Pragma("omp for schedule(dynamic, 64)")                                     \
+      for (int q = 0; q < nr; ++q) {                                               \
+        const int i = r0 + q;                                                      \
+        int* entC = ent + start[q];                                                \
+        ST* valC = val + start[q];                                                 \
+        const int c_row_size = rowlen[q];                                          \
+        int counter = 0;                                                           \
+        for (int ja = rmA[i]; ja < rmA[i + 1]; ++ja) {                             \
+          const int col = entA[ja];                                                \
+          const ST v = valA[ja];                                                   \
+          for (int jb = rmB[col]; jb < rmB[col + 1]; ++jb) {                       \
+            const int b_col = entB[jb];                                            \
+            const ST b_val = valB[jb];                                             \
+            if (!acc_flag[b_col]) { acc_flag[b_col] = 1; entC[counter++] = b_col; } \
+            accumulator[b_col] += b_val * v;                                       \
+          }                                                                        \
+        }                                                                          \
+        if (c_row_size > bufcap) {                                                 \
+          bufcap = c_row_size * 2;                                                 \
+          buf = (PAIR*)realloc(buf, sizeof(PAIR) * (size_t)bufcap);                \
+        }                                                                          \
+        for (int j = 0; j < c_row_size; ++j) {                                     \
+          const int c = entC[j];                                                   \
+          buf[j].c = c;                                                            \
+          buf[j].v = accumulator[c];                                               \
+          accumulator[c] = 0;                                                      \
+          acc_flag[c] = 0;                                                         \
+        }                                                                          \
+        qsort(buf, (size_t)c_row_size, sizeof(PAIR), CMP);                         \
+        for (int j = 0; j < c_row_size; ++j) { entC[j] = buf[j].c; valC[j] = buf[j].v; } \
+      }                                                                            \
+      free(accumulator); free(acc_flag); free(buf);                                \
+    }                                                                              \
+    free(start);                                                                   \
+    return total;                                                                  \
+  }
+
+DEF_SPGEMM_BLOCK(okk_spgemm_block_f64, double, okk_sort_crs_f64_pair, okk_sort_crs_f64_cmp)
+DEF_SPGEMM_BLOCK(okk_spgemm_block_f32, float, okk_sort_crs_f32_pair, okk_sort_crs_f32_cmp)
+
 /* transpose_matrix (sparse/src/KokkosSparse_Utils.hpp:338) -- counting sort by
  * column, stable in row order; used by the issue-402 fixture (C = A*A^T). */
 OKK_API void okk_transpose_f64(int nrow, int ncol, const int* rm, const int* ent,

@@ -35,6 +35,10 @@ class Oracle:
         L.okk_spmv_mv_f32mat_f64vec.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, i64, i64, f64, f64, i32]
         L.okk_spgemm_symbolic.argtypes = [i32, i32, vp, vp, vp, vp, vp]
         L.okk_spgemm_symbolic.restype = i64
+        for sfx in ("f64", "f32"):
+            fn = getattr(L, f"okk_spgemm_block_{sfx}")
+            fn.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32]
+            fn.restype = i64
         L.okk_transpose_f64.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         L.okk_count_rel_mismatch_f64.argtypes = [i64, vp, vp, f64]
         L.okk_count_rel_mismatch_f64.restype = i64
@@ -183,6 +187,23 @@ class Oracle:
         if sort:
             getattr(self.lib, "okk_sort_crs_" + sfx)(m, _p(rpC), _p(ciC), _p(vC))
         return rpC, ciC, vC
+
+    def spgemm_block(self, r0, r1, rpA, ciA, vA, rpB, ciB, vB, k, threads=0, cap=None):
+        """Rows [r0, r1) of O6 (sorted), rows dealt to OpenMP threads -- each row by the serial loops, so the bits are those of
+        spgemm().  Returns (row lengths, entries, values) of the block.  For full-size checks in blocks."""
+        if threads <= 0:
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        nr = r1 - r0
+        if cap is None:
+            lens = np.diff(rpB).astype(np.int64)
+            cap = int(lens[ciA[rpA[r0]:rpA[r1]]].sum())  # products: an upper bound of the block's nnz
+        rowlen = np.zeros(nr, dtype=np.int32)
+        ent = np.empty(max(cap, 1), dtype=np.int32)
+        val = np.empty(max(cap, 1), dtype=vA.dtype)
+        got = getattr(self.lib, "okk_spgemm_block_" + self._sfx(vA))(r0, r1, k, _p(rpA), _p(ciA), _p(vA), _p(rpB), _p(ciB), _p(vB),
+                                                                      cap, _p(rowlen), _p(ent), _p(val), threads)
+        assert got >= 0, "spgemm_block: capacity too small"
+        return rowlen, ent[:got], val[:got]
 
     def spgemm_jacobi(self, rpA, ciA, vA, rpB, ciB, vB, k, omega, dinv, sort=True):
         """spgemm_symbolic + spgemm_jacobi_seq (+ sort_crs_matrix): C = (I - omega diag(dinv) A) B."""

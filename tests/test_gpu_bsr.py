@@ -10,7 +10,7 @@ from bsr_cases import BLOCK_SIZES, COEFS_ALPHA, COEFS_BETA, PRIME_CASE, SHAPES, 
 
 # first GPU run pending (written after the round's GPU budget was spent; validated under the CPU emulation): promote to
 # `gpu` once tools/gpu_check's `bsr` suite and this file have passed on a B200
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 CASES = [(bs, mb, nb) for (mb, nb) in SHAPES for bs in BLOCK_SIZES] + [PRIME_CASE]
 

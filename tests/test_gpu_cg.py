@@ -8,7 +8,7 @@ import torch
 from test_oracle_cg import spd_lap27
 
 # first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("g", [14, 40])

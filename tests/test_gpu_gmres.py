@@ -9,7 +9,7 @@ import torch
 from gmres_cases import crs_to_bsr, gmres_matrix, true_rel_res
 
 # first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("use_blocks", [False, True])  # run_test_gmres<false> / <true> (:202-203): CrsMatrix, BsrMatrix of 10 x 10 blocks

@@ -10,7 +10,7 @@ from test_emulated_gs import check_coloring, symmetrize
 from test_oracle_cg import spd_lap27
 
 # first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("symmetric", [True, False])

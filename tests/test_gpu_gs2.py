@@ -10,7 +10,7 @@ import torch
 from test_oracle_gs2 import dd_matrix
 
 # first GPU run pending (written after the round's GPU budget was spent; validated under the CPU emulation)
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

@@ -9,7 +9,7 @@ from test_oracle_jacobi import diag_dominant
 
 # first GPU run pending (written after the round's GPU budget was spent): promote to `gpu` after tools/gpu_check's
 # `jacobi` suite and this file have passed on a B200
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,per", [(1000, 10), (20000, 6)])

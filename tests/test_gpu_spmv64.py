@@ -11,7 +11,7 @@ import torch
 from test_emulated_spmv64 import random_crs
 
 # first GPU run pending (written after the round's GPU budget was spent; validated under the CPU emulation)
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 def dev_matrix(sp, dev, rp, ci, v, n):

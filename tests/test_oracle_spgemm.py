@@ -71,3 +71,17 @@ def test_issue402_fixture(oracle):
     assert np.allclose(Cd, Cd.T, rtol=1e-9, atol=1e-18)
     Ad = dense_from_csr(rp, ci, v, n)
     assert np.allclose(Cd, Ad @ Ad.T, rtol=1e-9, atol=1e-16)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_row_block_variant_equals_serial(oracle, dtype):
+    """okk_spgemm_block (rows dealt to OpenMP threads, used by the full-size GPU parity tests) == the serial restatement,
+    bit for bit, for any block and thread count"""
+    from spgemm_cases import cases
+
+    for name, A, B, m, n, k in cases(dtype)[3:8]:
+        rpC, ciC, vC = oracle.spgemm(*A, *B, k)
+        for r0, r1, thr in ((0, m, 3), (m // 3, m // 2 + 1, 1), (m - 5, m, 8), (7, 7, 2)):
+            rowlen, ent, val = oracle.spgemm_block(r0, r1, *A, *B, k, threads=thr)
+            assert np.array_equal(rowlen, np.diff(rpC)[r0:r1]), name
+            assert np.array_equal(ent, ciC[rpC[r0]:rpC[r1]]) and np.array_equal(val, vC[rpC[r0]:rpC[r1]]), name

@@ -26,7 +26,7 @@ def test_shim_runs_on_gpu(cuda):
     assert "SHIM DRIVER OK" in out.stdout
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_shim_bsr_runs_on_gpu(cuda):
     """SPMV_BSRMATRIX / SPMV_MV_BSRMATRIX / SPGEMM_JACOBI specialisations (first GPU run pending, see tests/test_gpu_bsr.py)."""
     out = subprocess.run([DRV, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64"], capture_output=True, text=True, timeout=300)
