@@ -177,6 +177,12 @@ int b200sp_peer_join(void* compute_stream, void* const* comm_streams, int n);
  * must share their 16-byte phase.  The SM-driven counterpart of b200sp_peer_push_async for the pipelined
  * row-block SpMV (multigpu.py mode "pipelined_mc"); no reference counterpart. */
 int b200sp_multicast_push(void* stream, const void* src, void* mc_dst, int64_t bytes, int ctas);
+/* ctas > 0: multimem.st (16-byte) from `ctas` CTAs of 128 threads (0: 32); ctas < 0: plain stores from |ctas| CTAs. */
+
+/* SM-driven unicast push: `bytes` (multiple of 8) from src to the same offset of n_dst (<= 8) peer buffers with 16-byte P2P
+ * stores from `ctas` small CTAs (default 32) on `stream`; every 16 bytes are read once.  The SM counterpart of the copy-engine
+ * b200sp_peer_push_async (multigpu.py mode "pipelined_sm"); src and the destinations share their 16-byte phase. */
+int b200sp_peer_push_sm(void* stream, const void* src, int64_t bytes, int n_dst, void* const* dsts, int ctas);
 
 /* ---- SpMV rank-2 (multivector): Y = beta*Y + alpha*op(A)*X, k columns --- */
 /* Replaces SPMV_MV<Kokkos::Cuda,...,false,true>::spmv_mv -> cusparseSpMM

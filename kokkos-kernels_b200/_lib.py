@@ -45,6 +45,7 @@ SPARSE_API = {
     "b200sp_peer_push_async": (i32, [vp, C.POINTER(vp), i32, C.POINTER(vp), vp, i64]),
     "b200sp_peer_join": (i32, [vp, C.POINTER(vp), i32]),
     "b200sp_multicast_push": (i32, [vp, vp, vp, i64, i32]),
+    "b200sp_peer_push_sm": (i32, [vp, vp, i64, i32, C.POINTER(vp), i32]),
     "b200sp_spmv_hostvec_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, f64, vp, vp, vp, vp, f64, vp]),
     "b200sp_spmm_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, f64, vp, vp, vp, vp, i64, i32, f64, vp, i64, i32]),
     "b200sp_spmm_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, f32, vp, vp, vp, vp, i64, i32, f32, vp, i64, i32]),

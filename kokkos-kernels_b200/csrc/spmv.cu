@@ -512,17 +512,93 @@ static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 // (on sm_100 a plain st.global to a multicast address IS multimem.st: the switch replicates it into every
 // GPU's copy).  A few CTAs are enough (80 MB per step); they co-reside with the persistent SpMV CTAs.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) multicast_push_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+// 16-byte store to a multicast address: multimem.st (the switch writes the value into every GPU's copy)
+__device__ __forceinline__ void mc_store16(double2* dst, const double2& v) {
+#ifdef B200SP_EMU
+  *dst = v;
+#else
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__double2loint(v.x)),
+               "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void mc_store8(double* dst, double v) {
+#ifdef B200SP_EMU
+  *dst = v;
+#else
+  asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "r"(__double2loint(v)), "r"(__double2hiint(v))
+               : "memory");
+#endif
+}
+
+// MC = true: dst is the multicast mapping (multimem.st); false: a plain store (also used for a peer's unicast mapping)
+template <bool MC>
+__global__ void __launch_bounds__(128, 16) multicast_push_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
   // head: up to one element so that both pointers are 16-byte aligned (they share their 8-byte phase)
   int64_t head = (((uintptr_t)dst & 15u) != 0 && n > 0) ? 1 : 0;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  if (head && tid == 0) dst[0] = src[0];
+  if (head && tid == 0) {
+    if (MC) mc_store8(dst, src[0]); else dst[0] = src[0];
+  }
   const int64_t n2 = (n - head) >> 1;
   const double2* s2 = reinterpret_cast<const double2*>(src + head);
   double2* d2 = reinterpret_cast<double2*>(dst + head);
-  for (int64_t i = tid; i < n2; i += nthreads) d2[i] = s2[i];
-  if (((n - head) & 1) && tid == 0) dst[n - 1] = src[n - 1];
+  int64_t i = tid;
+#pragma unroll 1
+  for (; i + 3 * nthreads < n2; i += 4 * nthreads) {  // 4 independent 16-byte loads in flight per thread
+    const double2 a = s2[i], b = s2[i + nthreads], c = s2[i + 2 * nthreads], d = s2[i + 3 * nthreads];
+    if (MC) {
+      mc_store16(d2 + i, a); mc_store16(d2 + i + nthreads, b); mc_store16(d2 + i + 2 * nthreads, c); mc_store16(d2 + i + 3 * nthreads, d);
+    } else {
+      d2[i] = a; d2[i + nthreads] = b; d2[i + 2 * nthreads] = c; d2[i + 3 * nthreads] = d;
+    }
+  }
+#pragma unroll 1
+  for (; i < n2; i += nthreads) {
+    const double2 a = s2[i];
+    if (MC) mc_store16(d2 + i, a); else d2[i] = a;
+  }
+  if (((n - head) & 1) && tid == 0) {
+    if (MC) mc_store8(dst + n - 1, src[n - 1]); else dst[n - 1] = src[n - 1];
+  }
+}
+
+// SM-driven unicast push: every 16 bytes of src are read once and stored to the same offset of n_dst peer buffers
+// (P2P stores over NVLink).  src and all destinations share their 16-byte phase.
+struct PeerDsts {
+  double* p[8];
+  int n;
+};
+__global__ void __launch_bounds__(128, 16) peer_push_sm_kernel(const double* __restrict__ src, PeerDsts dsts, int64_t n) {
+  const int64_t head = (((uintptr_t)src & 15u) != 0 && n > 0) ? 1 : 0;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (head && tid == 0)
+    for (int d = 0; d < dsts.n; ++d) dsts.p[d][0] = src[0];
+  const int64_t n2 = (n - head) >> 1;
+  const double2* s2 = reinterpret_cast<const double2*>(src + head);
+  int64_t i = tid;
+#pragma unroll 1
+  for (; i + nthreads < n2; i += 2 * nthreads) {
+    const double2 a = s2[i], b = s2[i + nthreads];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < dsts.n) {
+        double2* q = reinterpret_cast<double2*>(dsts.p[d] + head);
+        q[i] = a;
+        q[i + nthreads] = b;
+      }
+  }
+#pragma unroll 1
+  for (; i < n2; i += nthreads) {
+    const double2 a = s2[i];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < dsts.n) reinterpret_cast<double2*>(dsts.p[d] + head)[i] = a;
+  }
+  if (((n - head) & 1) && tid == 0)
+    for (int d = 0; d < dsts.n; ++d) dsts.p[d][n - 1] = src[n - 1];
 }
 
 }  // namespace b200sp
@@ -1247,8 +1323,31 @@ int b200sp_multicast_push(void* stream, const void* src, void* mc_dst, int64_t b
   B200SP_REQUIRE((((uintptr_t)src ^ (uintptr_t)mc_dst) & 15u) == 0 && ((uintptr_t)src & 7u) == 0,
                  "multicast_push: source and destination must be 8-byte aligned with the same 16-byte phase");
   if (bytes == 0) return B200SP_OK;
-  if (ctas <= 0) ctas = 16;
-  multicast_push_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>((const double*)src, (double*)mc_dst, bytes / 8);
+  // ctas < 0: plain stores to the multicast mapping instead of multimem.st (|ctas| CTAs)
+  const bool plain = ctas < 0;
+  if (ctas < 0) ctas = -ctas;
+  if (ctas == 0) ctas = 32;
+  if (plain)
+    multicast_push_kernel<false><<<ctas, 128, 0, (cudaStream_t)stream>>>((const double*)src, (double*)mc_dst, bytes / 8);
+  else
+    multicast_push_kernel<true><<<ctas, 128, 0, (cudaStream_t)stream>>>((const double*)src, (double*)mc_dst, bytes / 8);
+  B200SP_LAUNCH_CHECK();
+  return B200SP_OK;
+}
+
+int b200sp_peer_push_sm(void* stream, const void* src, int64_t bytes, int n_dst, void* const* dsts, int ctas) {
+  B200SP_REQUIRE(bytes >= 0 && (bytes % 8) == 0, "peer_push_sm: byte count must be a non-negative multiple of 8");
+  B200SP_REQUIRE(n_dst >= 0 && n_dst <= 8 && (n_dst == 0 || dsts != nullptr), "peer_push_sm: 0..8 destinations");
+  if (bytes == 0 || n_dst == 0) return B200SP_OK;
+  B200SP_REQUIRE(src != nullptr && ((uintptr_t)src & 7u) == 0, "peer_push_sm: source must be 8-byte aligned");
+  PeerDsts pd;
+  pd.n = n_dst;
+  for (int d = 0; d < 8; ++d) pd.p[d] = d < n_dst ? (double*)dsts[d] : nullptr;
+  for (int d = 0; d < n_dst; ++d)
+    B200SP_REQUIRE(dsts[d] != nullptr && ((((uintptr_t)src) ^ ((uintptr_t)dsts[d])) & 15u) == 0,
+                   "peer_push_sm: every destination must share the source's 16-byte phase");
+  if (ctas <= 0) ctas = 32;
+  peer_push_sm_kernel<<<ctas, 128, 0, (cudaStream_t)stream>>>((const double*)src, pd, bytes / 8);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
