@@ -37,7 +37,7 @@ def build(force=False, verbose=True):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libb200sparse.so")
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(CSRC, "tile_ring.cuh"), os.path.join(CSRC, "spgemm_esc.cuh"), os.path.join(HERE, "..", "include", "b200sparse.h")]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(CSRC, "tile_ring.cuh"), os.path.join(CSRC, "spgemm_esc.cuh"), os.path.join(CSRC, "spmm_items.h"), os.path.join(HERE, "..", "include", "b200sparse.h")]
     if force or not _newer(out, deps):
         objs = []
         procs = []

@@ -117,10 +117,30 @@ __global__ void bin_count_kernel(int m, const int* __restrict__ key, BinSpec spe
   __syncthreads();
   if (threadIdx.x < MAXBINS && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
-__global__ void bin_scatter_kernel(int m, const int* __restrict__ key, BinSpec spec, int* __restrict__ cursors,
+__global__ void __launch_bounds__(256) bin_scatter_kernel(int m, const int* __restrict__ key, BinSpec spec, int* __restrict__ cursors,
                                    int* __restrict__ rows_out) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x)
-    rows_out[atomicAdd(&cursors[bin_of(spec, key[r])], 1)] = r;
+  // block-aggregated: one global atomic per (CTA pass, bin) instead of one per row (2M atomics on ONE counter serialise for
+  // milliseconds when every row falls into the same bin); the rows of a pass stay together, so a bin's list follows the
+  // natural row order up to the order in which the passes reserve their ranges -- consecutive CTAs of the row kernels then
+  // read neighbouring rows of A and write neighbouring rows of C
+  __shared__ int scnt[MAXBINS];
+  __shared__ int sbase[MAXBINS];
+  const int passes = (m + (int)(gridDim.x * blockDim.x) - 1) / (int)(gridDim.x * blockDim.x);
+  for (int it = 0; it < passes; ++it) {
+    const int r = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (threadIdx.x < MAXBINS) scnt[threadIdx.x] = 0;
+    __syncthreads();
+    int b = -1, rank = 0;
+    if (r < m) {
+      b = bin_of(spec, key[r]);
+      rank = atomicAdd(&scnt[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < MAXBINS && scnt[threadIdx.x] > 0) sbase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], scnt[threadIdx.x]);
+    __syncthreads();
+    if (b >= 0) rows_out[sbase[b] + rank] = r;
+    __syncthreads();
+  }
 }
 
 // ESC bin key of a row (spgemm_esc.cuh): max(products, 2 * nnz(A_i)), saturated
@@ -1098,14 +1118,14 @@ static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const in
   return B200SP_OK;
 }
 
-template <int T, int I, int MINB>
+template <int T, int I, int LOG2NB, int MINB>
 static int launch_esc_sym(cudaStream_t st, int nrows, const int* rows, const int* rpA, const int* ciA, const int* rpB,
-                          const int* ciB, const int* flops, int* row_nnz) {
+                          const int* ciB, const int* flops, const int* cmin, const int* cmax, int* row_nnz) {
   if (nrows <= 0) return B200SP_OK;
-  using L = EscSymLayout<T, I>;
-  auto kern = esc_sym_kernel<T, I, MINB>;
+  using L = EscSymLayout<T, I, LOG2NB>;
+  auto kern = esc_sym_kernel<T, I, LOG2NB, MINB>;
   if (L::BYTES > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-  kern<<<nrows, T, L::BYTES, st>>>(nrows, rows, rpA, ciA, rpB, ciB, flops, row_nnz);
+  kern<<<nrows, T, L::BYTES, st>>>(nrows, rows, rpA, ciA, rpB, ciB, flops, cmin, cmax, row_nnz);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -1443,10 +1463,10 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   if (sym_variant >= 3) {
     const int* er = p->esc_rows;
     const int* eo = p->esc_off;
-    if ((rc = launch_esc_sym<32, 8, 1>(st, eo[1] - eo[0], er + eo[0], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<128, 8, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<512, 8, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<1024, 8, 1>(st, eo[4] - eo[3], er + eo[3], rpA, ciA, rpB, ciB, flops, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<32, 8, 9, 1>(st, eo[1] - eo[0], er + eo[0], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<512, 8, 13, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<1024, 8, 14, 1>(st, eo[4] - eo[3], er + eo[3], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
     if ((rc = launch_sym<512, 15>(st, eo[5] - eo[4], er + eo[4], lb, rpA, ciA, rpB, ciB, row_nnz))) return rc;
     for (int b = 0; b <= kEscBins + 2; ++b) soff[b] = eo[b];
     sym_rows = p->esc_rows;

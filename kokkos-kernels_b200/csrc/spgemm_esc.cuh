@@ -6,19 +6,21 @@
 // gathers of a row are issued back to back from registers (I independent col/val loads per thread in flight)
 // and consecutive lanes read consecutive entries of one B row.  Nothing is gathered twice.
 //
-//  symbolic  esc_sym_kernel : the columns go through a shared-memory hash set (atomicCAS), nnz(C_i) = inserts.
-//  numeric   esc_num_kernel : counting sort by a MONOTONE bucket map of the column
-//      bucket(c) = c - cmin                       (row span <= NB: injective)
-//                = ((c - cmin) * floor(NB*2^32 / span)) >> 32   otherwise
-//    histogram (shared atomicAdd, the returned count is the product's arrival rank in its bucket) -> exclusive
-//    scan -> scatter of the keys -> every product ranks itself among the few members of its bucket by
-//    (column, ordinal) -> the row is sorted, equal columns adjacent in ORDINAL order.  Rows without duplicate
-//    columns (f == nnz(C_i), known from symbolic) leave at once with coalesced stores; otherwise the first
-//    product of each run adds its run up in ordinal order -- the oracle's order, so the values equal the
-//    reference's SPGEMM_DEBUG result bit for bit when it is compiled without FMA contraction -- and an
-//    exclusive scan of the run heads gives the output positions.  No floating-point atomics, no second walk,
-//    deterministic.  Rows come out sorted by column: the reference's separate sort_crs_matrix pass
-//    (sparse/impl/KokkosSparse_spgemm_numeric_spec.hpp:138-140) is not needed.
+// Both phases sort the row's columns with one counting sort over a MONOTONE bucket map
+//      bucket(c) = c - cmin                                          (row span <= NB: injective)
+//                = ((c - cmin) * floor(NB*2^32 / span)) >> 32        otherwise
+//   histogram (shared atomicAdd; the returned count is the product's arrival rank in its bucket) -> exclusive
+//   scan -> scatter of the keys to bucket order.  Buckets hold 0.5 products on average, so what is left is local:
+//  symbolic  esc_sym_kernel : a product is a duplicate iff its bucket holds an equal column at a smaller position;
+//            nnz(C_i) = f - duplicates.
+//  numeric   esc_num_kernel : every product ranks itself among the members of its bucket by (column, ordinal) and
+//            stores (column, value) at its sorted position.  Rows without duplicate columns (f == nnz(C_i), known
+//            from symbolic) leave at once with coalesced stores; otherwise the first product of each run of equal
+//            columns adds the run up in ordinal order -- the oracle's order, and the product is an unfused multiply,
+//            so the VALUES equal the reference's SPGEMM_DEBUG result bit for bit when that is compiled without FMA
+//            contraction -- and a ballot scan of the run heads gives the output positions.
+//  No floating-point atomics, no second walk over B, deterministic, rows come out sorted by column: the reference's
+//  separate sort_crs_matrix pass (sparse/impl/KokkosSparse_spgemm_numeric_spec.hpp:138-140) is not needed.
 //
 // A row qualifies when max(f, 2 * nnz(A_i)) <= T*I (the staged A row shares memory with the sorted output).
 #pragma once
@@ -35,6 +37,26 @@ template <>
 __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
 
 constexpr int esc_log2(int v) { return v <= 1 ? 0 : 1 + esc_log2(v >> 1); }
+
+// (column, value) pairs of the sorted row: one 16-byte (fp64) / 8-byte (fp32) shared-memory access each
+template <typename S>
+struct EscKV;
+template <>
+struct EscKV<double> {
+  using type = int4;
+  static __device__ __forceinline__ int4 pack(int k, double v) {
+    return make_int4(k, 0, __double2loint(v), __double2hiint(v));
+  }
+  static __device__ __forceinline__ int key(const int4& q) { return q.x; }
+  static __device__ __forceinline__ double val(const int4& q) { return __hiloint2double(q.w, q.z); }
+};
+template <>
+struct EscKV<float> {
+  using type = int2;
+  static __device__ __forceinline__ int2 pack(int k, float v) { return make_int2(k, __float_as_int(v)); }
+  static __device__ __forceinline__ int key(const int2& q) { return q.x; }
+  static __device__ __forceinline__ float val(const int2& q) { return __int_as_float(q.y); }
+};
 
 // exclusive scan in place of a[0..n), n <= T*K, thread t owns a[t*K .. t*K+K); every thread gets the total.
 // wsum: 34 ints of shared memory.  Ends with a barrier (a[] and the total are visible to all).
@@ -146,81 +168,91 @@ __device__ __forceinline__ int esc_block_scan1(int v, int* wsum, int& total) {
 }
 
 // ---- staging of A's row and the product -> (entry of A, offset in its B row) map -------------------
-// bs[j] = start of the B row of A's j-th entry, pre[j] = ordinal of its first product (pre[nA] = f).
-// Returns the common length of the B rows (>= 1) when all of them have the same length, else 0.
-template <int T, int I>
-__device__ __forceinline__ int esc_stage_row(int a0, int nA, int f, const int* __restrict__ ciA,
-                                             const int* __restrict__ rpB, int* bs, int* pre, int* wsum, int* sflag) {
-  const int tid = threadIdx.x;
+// bs[j] = start of the B row of A's j-th entry, pre[j] = ordinal of its first product (pre[nA] = f), va[j] = its value
+// (numeric).  Returns the common length of the B rows (>= 1) when all of them have the same length, else 0.
+// Rows of up to 32 entries are staged by warp 0 alone (shuffle scan, one barrier).
+template <int T, typename S, bool WITH_VALS>
+__device__ __forceinline__ int esc_stage_row(int a0, int nA, int f, const int* __restrict__ ciA, const S* __restrict__ vA,
+                                             const int* __restrict__ rpB, int* bs, int* pre, S* va, int* wsum) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  int* sflag = wsum + 35;
+  if (nA <= 32) {
+    if (tid < 32) {
+      int len = 0;
+      if (lane < nA) {
+        const int c = ldg(ciA + a0 + lane);
+        const int b0 = ldg(rpB + c);
+        len = ldg(rpB + c + 1) - b0;
+        bs[lane] = b0;
+        if (WITH_VALS) va[lane] = ldg(vA + a0 + lane);
+      }
+      const int len0 = __shfl_sync(0xffffffffu, len, 0);
+      const bool uni = __all_sync(0xffffffffu, lane >= nA || len == len0) != 0;
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane < nA) pre[lane] = inc - len;
+      if (lane == 0) {
+        pre[nA] = f;
+        *sflag = (uni && len0 > 0) ? len0 : 0;
+      }
+    }
+    __syncthreads();
+    return *sflag;
+  }
   if (tid == 0) *sflag = 0;
   __syncthreads();
-  int first_len = -1;
-  for (int j = tid; j < nA; j += T) {
-    const int c = ldg(ciA + a0 + j);
-    const int b0 = ldg(rpB + c);
-    const int len = ldg(rpB + c + 1) - b0;
-    bs[j] = b0;
-    pre[j] = len;
+  int carry = 0;
+  int len0 = -1;
+  for (int base = 0; base < nA; base += T) {
+    const int j = base + tid;
+    int len = 0;
+    if (j < nA) {
+      const int c = ldg(ciA + a0 + j);
+      const int b0 = ldg(rpB + c);
+      len = ldg(rpB + c + 1) - b0;
+      bs[j] = b0;
+      if (WITH_VALS) va[j] = ldg(vA + a0 + j);
+    }
+    if (base == 0) {
+      if (tid == 0) wsum[34] = len;
+      __syncthreads();
+      len0 = wsum[34];
+    }
+    int total;
+    const int excl = esc_block_scan1<T>(len, wsum, total);
+    if (j < nA) {
+      pre[j] = carry + excl;
+      if (len != len0) *sflag = 1;  // benign race: every writer stores 1
+    }
+    carry += total;
   }
+  if (tid == 0) pre[nA] = f;
   __syncthreads();
-  first_len = pre[0];
-  for (int j = tid; j < nA; j += T)
-    if (pre[j] != first_len) *sflag = 1;  // benign race: every writer stores 1
-  __syncthreads();
-  const bool uniform = (*sflag == 0) && first_len > 0;
-  // nA <= T*I/2: each thread scans I/2 (>= 1) consecutive lengths
-  constexpr int K = (I / 2 > 0) ? I / 2 : 1;
-  if (tid == 0) pre[nA] = f;  // outside the scanned range; published by the scan's closing barrier
-  esc_block_scan<T, K>(pre, nA, wsum);
-  return uniform ? first_len : 0;
+  return (*sflag == 0 && len0 > 0) ? len0 : 0;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// SYMBOLIC
-// ---------------------------------------------------------------------------------------------------
-template <int T, int I>
-struct EscSymLayout {
-  static constexpr int CAP = T * I;
-  static constexpr int SLOTS = 2 * CAP;  // a power of two (T and I are)
-  static constexpr int LOG2SLOTS = esc_log2(SLOTS);
-  static constexpr int NA = CAP / 2;
-  // keys[SLOTS] | bs[NA] | pre[NA + 4] | wsum[36]
-  static constexpr size_t BYTES = sizeof(int) * (size_t)(SLOTS + NA + NA + 4 + 36);
-};
-
-template <int T, int I, int MINB>
-__global__ void __launch_bounds__(T, MINB)
-    esc_sym_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
-                   const int* __restrict__ rpB, const int* __restrict__ ciB, const int* __restrict__ flops,
-                   int* __restrict__ row_nnz) {
-  using L = EscSymLayout<T, I>;
-  constexpr int SLOTS = L::SLOTS;
-  constexpr int EMPTYK = -1;
-  extern __shared__ __align__(16) int esc_sm[];
-  int* keys = esc_sm;
-  int* bs = keys + SLOTS;
-  int* pre = bs + L::NA;
-  int* wsum = pre + L::NA + 4;
+// ---- the products of this thread: columns (and values) in registers ------------------------------------------------
+template <int T, int I, typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_expand(int f, int nA, int L0, const int* bs, const int* pre, const S* va,
+                                           const int* __restrict__ ciB, const S* __restrict__ vB, int nokey, int (&col)[I],
+                                           S (&val)[I]) {
   const int tid = threadIdx.x;
-  const int i = rows[blockIdx.x];
-  const int f = flops[i];
-  if (f == 0) {
-    if (tid == 0) row_nnz[i] = 0;
-    return;
-  }
-  const int a0 = rpA[i], nA = rpA[i + 1] - a0;
-  {
-    int4* k4 = reinterpret_cast<int4*>(keys);
-    for (int s = tid; s < SLOTS / 4; s += T) k4[s] = make_int4(EMPTYK, EMPTYK, EMPTYK, EMPTYK);
-  }
-  const int L0 = esc_stage_row<T, I>(a0, nA, f, ciA, rpB, bs, pre, wsum, wsum + 35);
-  int col[I];
   if (L0 > 0) {
     int j = tid / L0, t = tid - j * L0;
     const int dj = T / L0, dt = T - dj * L0;
 #pragma unroll
     for (int k = 0; k < I; ++k) {
-      col[k] = (k * T + tid < f) ? ld_stream(ciB + bs[j] + t) : EMPTYK;
+      col[k] = nokey;
+      if (WITH_VALS) val[k] = S(0);
+      if (k * T + tid < f) {
+        const int jb = bs[j] + t;
+        col[k] = ld_stream(ciB + jb);
+        if (WITH_VALS) val[k] = mul_rn(ld_stream(vB + jb), va[j]);  // b_val * a_val (impl_seq.hpp:163)
+      }
       j += dj;
       t += dt;
       if (t >= L0) {
@@ -233,41 +265,123 @@ __global__ void __launch_bounds__(T, MINB)
 #pragma unroll
     for (int k = 0; k < I; ++k) {
       const int p = k * T + tid;
-      col[k] = EMPTYK;
+      col[k] = nokey;
+      if (WITH_VALS) val[k] = S(0);
       if (p < f) {
-        int hi = nA;  // largest j with pre[j] <= p (pre[nA] = f > p)
+        int hi = nA;  // largest j with pre[j] <= p (pre[nA] = f > p); p grows with k: search from the last answer
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
           if (pre[mid] <= p) lo = mid; else hi = mid;
         }
-        col[k] = ld_stream(ciB + bs[lo] + (p - pre[lo]));
+        const int jb = bs[lo] + (p - pre[lo]);
+        col[k] = ld_stream(ciB + jb);
+        if (WITH_VALS) val[k] = mul_rn(ld_stream(vB + jb), va[lo]);
       }
     }
   }
-  int mine = 0;
+}
+
+// ---- counting sort of the columns into bucket order.  On return skey[] holds the keys grouped by bucket,
+// pos[k] = position of item k in skey, lc[k] = first position of its bucket | (members of the bucket << 16).
+template <int T, int I, int LOG2NB>
+__device__ __forceinline__ void esc_bucket_sort(int f, int cmin, long long span, int nokey, const int (&col)[I], int* off,
+                                                int* skey, int* wsum, int (&pos)[I], int (&lc)[I]) {
+  constexpr int NB = 1 << LOG2NB;
+  const bool dense = span <= NB;
+  const unsigned long long mult = dense ? 0ull : (((unsigned long long)NB << 32) / (unsigned long long)span);
 #pragma unroll
   for (int k = 0; k < I; ++k) {
-    const int c = col[k];
-    if (c != EMPTYK) {
-      unsigned h = ((unsigned)c * 0x9E3779B1u) >> (32 - L::LOG2SLOTS);
-      while (true) {
-        const int kcur = ((volatile int*)keys)[h];
-        if (kcur == c) break;
-        if (kcur == EMPTYK) {
-          const int old = atomicCAS(&keys[h], EMPTYK, c);
-          if (old == EMPTYK) {
-            ++mine;
-            break;
-          }
-          if (old == c) break;
-        }
-        h = (h + 1) & (unsigned)(SLOTS - 1);
-      }
+    pos[k] = 0;
+    if (col[k] != nokey) {
+      const unsigned d = (unsigned)(col[k] - cmin);
+      const int b = dense ? (int)d : (int)(((unsigned long long)d * mult) >> 32);
+      const int r = atomicAdd(&off[b], 1);
+      pos[k] = b | (r << LOG2NB);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) off[NB] = f;  // outside the scanned range; published by the scan's closing barrier
+  esc_block_scan<T, NB / T>(off, NB, wsum);
+#pragma unroll
+  for (int k = 0; k < I; ++k) {
+    lc[k] = 0;
+    if (col[k] != nokey) {
+      const int b = pos[k] & (NB - 1);
+      const int lo = off[b], hi = off[b + 1];
+      const int p0 = lo + (pos[k] >> LOG2NB);
+      skey[p0] = col[k];
+      pos[k] = p0;
+      lc[k] = lo | ((hi - lo) << 16);
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SYMBOLIC
+// ---------------------------------------------------------------------------------------------------
+template <int T, int I, int LOG2NB>
+struct EscSymLayout {
+  static constexpr int CAP = T * I;
+  static constexpr int NB = 1 << LOG2NB;
+  static constexpr int NA = CAP / 2;
+  // off[NB + 4] | wsum[36] | union { bs[NA], pre[NA + 4] ; skey[CAP] }  (the staging is dead when the keys are scattered)
+  static constexpr size_t BYTES = sizeof(int) * (size_t)(NB + 4 + 36 + CAP + 8);
+};
+
+template <int T, int I, int LOG2NB, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+    esc_sym_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
+                   const int* __restrict__ rpB, const int* __restrict__ ciB, const int* __restrict__ flops,
+                   const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, int* __restrict__ row_nnz) {
+  using L = EscSymLayout<T, I, LOG2NB>;
+  constexpr int NB = L::NB;
+  constexpr int NOKEY = INT_MAX;
+  extern __shared__ __align__(16) int esc_sm[];
+  int* off = esc_sm;
+  int* wsum = off + NB + 4;
+  int* skey = wsum + 36;
+  int* bs = skey;
+  int* pre = bs + L::NA;
+  const int tid = threadIdx.x;
+  const int i = rows[blockIdx.x];
+  const int f = flops[i];
+  if (f == 0) {
+    if (tid == 0) row_nnz[i] = 0;
+    return;
+  }
+  const int a0 = rpA[i], nA = rpA[i + 1] - a0;
+  const int cmin = cmin_arr[i];
+  const long long span = (long long)cmax_arr[i] - cmin + 1;
+  {
+    int4* o4 = reinterpret_cast<int4*>(off);
+    for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
+  }
+  const int L0 = esc_stage_row<T, float, false>(a0, nA, f, ciA, (const float*)nullptr, rpB, bs, pre, (float*)nullptr, wsum);
+  int col[I];
+  float dummy[I];
+  esc_expand<T, I, float, false>(f, nA, L0, bs, pre, (const float*)nullptr, ciB, (const float*)nullptr, NOKEY, col, dummy);
+  int pos[I], lc[I];
+  esc_bucket_sort<T, I, LOG2NB>(f, cmin, span, NOKEY, col, off, skey, wsum, pos, lc);
+  // a product is a duplicate iff an equal column sits at a smaller position of its bucket
+  int dups = 0;
+#pragma unroll
+  for (int k = 0; k < I; ++k)
+    if (col[k] != NOKEY) {
+      const int lo = lc[k] & 0xffff, cnt = lc[k] >> 16;
+      if (cnt > 1) {
+        const int c = col[k];
+        bool dup = false;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (u < cnt && lo + u < pos[k]) dup = dup || (skey[lo + u] == c);
+        for (int m = lo + 3; m < pos[k]; ++m) dup = dup || (skey[m] == c);
+        dups += dup ? 1 : 0;
+      }
+    }
   int total;
-  esc_block_scan1<T>(mine, wsum, total);
-  if (tid == 0) row_nnz[i] = total;
+  esc_block_scan1<T>(dups, wsum, total);
+  if (tid == 0) row_nnz[i] = f - total;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -275,16 +389,18 @@ __global__ void __launch_bounds__(T, MINB)
 // ---------------------------------------------------------------------------------------------------
 template <typename S, int T, int I, int LOG2NB>
 struct EscNumLayout {
+  using KV = typename EscKV<S>::type;
   static constexpr int CAP = T * I;
   static constexpr int NB = 1 << LOG2NB;
   static constexpr int NA = CAP / 2;
-  // off[NB + 4] | skey[CAP] | wsum[36] | sord[CAP] (u16) | union { bs[NA], pre[NA + 4], va[NA] ; skey2[CAP], sval[CAP] }
+  static constexpr int NW = T / 32;
+  // off[NB + 4] | skey[CAP] | wsum[36] | hpre[I * NW + 4] | sord[CAP] (u16) | union { va[NA], bs[NA], pre[NA + 4] ; skv[CAP] }
   static constexpr size_t OFF_BYTES = sizeof(int) * (size_t)(NB + 4);
   static constexpr size_t KEY_BYTES = sizeof(int) * (size_t)CAP;
-  static constexpr size_t WS_BYTES = sizeof(int) * 36;
+  static constexpr size_t WS_BYTES = sizeof(int) * (size_t)(36 + I * NW + 4);
   static constexpr size_t ORD_BYTES = ((sizeof(unsigned short) * (size_t)CAP) + 15) & ~(size_t)15;
   static constexpr size_t STAGE_BYTES = sizeof(int) * (size_t)(NA + NA + 4) + sizeof(S) * (size_t)NA;
-  static constexpr size_t SORT_BYTES = (sizeof(int) + sizeof(S)) * (size_t)CAP;
+  static constexpr size_t SORT_BYTES = sizeof(KV) * (size_t)CAP;
   static constexpr size_t UNION_BYTES = ((STAGE_BYTES > SORT_BYTES ? STAGE_BYTES : SORT_BYTES) + 15) & ~(size_t)15;
   static constexpr size_t BYTES = OFF_BYTES + KEY_BYTES + WS_BYTES + ORD_BYTES + UNION_BYTES;
 };
@@ -296,13 +412,17 @@ __global__ void __launch_bounds__(T, MINB)
                    const S* __restrict__ vB, const int* __restrict__ rpC, int* __restrict__ ciC, S* __restrict__ vC,
                    const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, const int* __restrict__ flops) {
   using L = EscNumLayout<S, T, I, LOG2NB>;
+  using KVT = EscKV<S>;
+  using KV = typename KVT::type;
   constexpr int CAP = L::CAP;
   constexpr int NB = L::NB;
+  constexpr int NW = L::NW;
   constexpr int NOKEY = INT_MAX;
   extern __shared__ __align__(16) unsigned char esc_raw[];
   int* off = reinterpret_cast<int*>(esc_raw);
   int* skey = reinterpret_cast<int*>(esc_raw + L::OFF_BYTES);
   int* wsum = reinterpret_cast<int*>(esc_raw + L::OFF_BYTES + L::KEY_BYTES);
+  int* hpre = wsum + 36;
   unsigned short* sord = reinterpret_cast<unsigned short*>(esc_raw + L::OFF_BYTES + L::KEY_BYTES + L::WS_BYTES);
   unsigned char* un = esc_raw + L::OFF_BYTES + L::KEY_BYTES + L::WS_BYTES + L::ORD_BYTES;
   // staging view (S first: 8-byte alignment)
@@ -310,10 +430,9 @@ __global__ void __launch_bounds__(T, MINB)
   int* bs = reinterpret_cast<int*>(un + sizeof(S) * (size_t)L::NA);
   int* pre = bs + L::NA;
   // sorted view
-  S* sval = reinterpret_cast<S*>(un);
-  int* skey2 = reinterpret_cast<int*>(un + sizeof(S) * (size_t)CAP);
+  KV* skv = reinterpret_cast<KV*>(un);
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = rows[blockIdx.x];
   const int cbase = rpC[i];
   const int nz = rpC[i + 1] - cbase;
@@ -322,136 +441,111 @@ __global__ void __launch_bounds__(T, MINB)
   const int a0 = rpA[i], nA = rpA[i + 1] - a0;
   const int cmin = cmin_arr[i];
   const long long span = (long long)cmax_arr[i] - cmin + 1;
-  const bool dense = span <= NB;
-  const unsigned long long mult = dense ? 0ull : (((unsigned long long)NB << 32) / (unsigned long long)span);
+  const bool nodup = (nz == f);  // no duplicate column in this row (uniform over the CTA)
   {
     int4* o4 = reinterpret_cast<int4*>(off);
     for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
   }
-  for (int j = tid; j < nA; j += T) va[j] = ldg(vA + a0 + j);
-  const int L0 = esc_stage_row<T, I>(a0, nA, f, ciA, rpB, bs, pre, wsum, wsum + 35);
-
-  // ---- expand: I products per thread, in registers
+  const int L0 = esc_stage_row<T, S, true>(a0, nA, f, ciA, vA, rpB, bs, pre, va, wsum);
   int col[I];
   S val[I];
-  if (L0 > 0) {
-    int j = tid / L0, t = tid - j * L0;
-    const int dj = T / L0, dt = T - dj * L0;
+  esc_expand<T, I, S, true>(f, nA, L0, bs, pre, va, ciB, vB, NOKEY, col, val);
+  int pos[I], lc[I];
+  // (the first barrier inside the sort retires the staging arrays: skv aliases them)
+  esc_bucket_sort<T, I, LOG2NB>(f, cmin, span, NOKEY, col, off, skey, wsum, pos, lc);
+  if (nodup) {
+    // ---- rank inside the bucket by column -> sorted position; (column, value) stored there
 #pragma unroll
-    for (int k = 0; k < I; ++k) {
-      col[k] = NOKEY;
-      val[k] = S(0);
-      if (k * T + tid < f) {
-        const int jb = bs[j] + t;
-        col[k] = ld_stream(ciB + jb);
-        val[k] = mul_rn(ld_stream(vB + jb), va[j]);  // b_val * a_val (impl_seq.hpp:163)
-      }
-      j += dj;
-      t += dt;
-      if (t >= L0) {
-        t -= L0;
-        ++j;
-      }
-    }
-  } else {
-    int lo = 0;
+    for (int k = 0; k < I; ++k)
+      if (col[k] != NOKEY) {
+        const int lo = lc[k] & 0xffff, cnt = lc[k] >> 16;
+        int less = 0;
+        if (cnt > 1) {
+          const int c = col[k];
 #pragma unroll
-    for (int k = 0; k < I; ++k) {
-      const int p = k * T + tid;
-      col[k] = NOKEY;
-      val[k] = S(0);
-      if (p < f) {
-        int hi = nA;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (pre[mid] <= p) lo = mid; else hi = mid;
+          for (int u = 0; u < 3; ++u)
+            if (u < cnt) less += (skey[lo + u] < c) ? 1 : 0;
+          for (int u = 3; u < cnt; ++u) less += (skey[lo + u] < c) ? 1 : 0;
         }
-        const int jb = bs[lo] + (p - pre[lo]);
-        col[k] = ld_stream(ciB + jb);
-        val[k] = mul_rn(ld_stream(vB + jb), va[lo]);
+        skv[lo + less] = KVT::pack(col[k], val[k]);
       }
-    }
-  }
-  // ---- histogram over the monotone buckets; the old count is the arrival rank
-  int br[I];
-#pragma unroll
-  for (int k = 0; k < I; ++k) {
-    br[k] = 0;
-    if (col[k] != NOKEY) {
-      const unsigned d = (unsigned)(col[k] - cmin);
-      const int b = dense ? (int)d : (int)(((unsigned long long)d * mult) >> 32);
-      const int r = atomicAdd(&off[b], 1);
-      br[k] = b | (r << LOG2NB);
-    }
-  }
-  __syncthreads();  // staging (bs / pre / va) is dead from here on
-  esc_block_scan<T, NB / T>(off, NB, wsum);
-  if (tid == 0) off[NB] = f;
-  // ---- scatter keys + ordinals to bucket order
-#pragma unroll
-  for (int k = 0; k < I; ++k)
-    if (col[k] != NOKEY) {
-      const int b = br[k] & (NB - 1);
-      const int pos0 = off[b] + (br[k] >> LOG2NB);
-      skey[pos0] = col[k];
-      sord[pos0] = (unsigned short)(k * T + tid);
-    }
-  __syncthreads();
-  // ---- rank inside the bucket by (column, ordinal) -> sorted position
-#pragma unroll
-  for (int k = 0; k < I; ++k)
-    if (col[k] != NOKEY) {
-      const int b = br[k] & (NB - 1);
-      const int lo = off[b], hi = off[b + 1];
-      int less = 0;
-      if (hi - lo > 1) {
-        const int c = col[k];
-        const int p = k * T + tid;
-        for (int m = lo; m < hi; ++m) {
-          const int km = skey[m];
-          less += (km < c || (km == c && (int)sord[m] < p)) ? 1 : 0;
-        }
-      }
-      skey2[lo + less] = col[k];
-      sval[lo + less] = val[k];
-    }
-  __syncthreads();
-  if (nz == f) {  // no duplicate column: the sorted products are the row
+    __syncthreads();
     for (int q = tid; q < f; q += T) {
-      ciC[cbase + q] = skey2[q];
-      vC[cbase + q] = sval[q];
+      const KV e = skv[q];
+      ciC[cbase + q] = KVT::key(e);
+      vC[cbase + q] = KVT::val(e);
     }
     return;
   }
-  // ---- compress: run heads, output positions by an exclusive scan of the head flags
-  int heads = 0;
-  const int q0 = tid * I;
+  // ---- rows with duplicate columns: rank by (column, ordinal), then compress the runs
+#pragma unroll
+  for (int k = 0; k < I; ++k)
+    if (col[k] != NOKEY) sord[pos[k]] = (unsigned short)(k * T + tid);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < I; ++k)
+    if (col[k] != NOKEY) {
+      const int lo = lc[k] & 0xffff, cnt = lc[k] >> 16;
+      int less = 0;
+      if (cnt > 1) {
+        const int c = col[k];
+        const int p = k * T + tid;
+        for (int u = 0; u < cnt; ++u) {
+          const int km = skey[lo + u];
+          less += (km < c || (km == c && (int)sord[lo + u] < p)) ? 1 : 0;
+        }
+      }
+      skv[lo + less] = KVT::pack(col[k], val[k]);
+    }
+  __syncthreads();
+  // run heads in position order q = k*T + tid; output position = heads before q (ballot scan over (k, warp) groups)
+  unsigned hmask = 0;  // bit k: position k*T + tid starts a run
 #pragma unroll
   for (int k = 0; k < I; ++k) {
-    const int q = q0 + k;
-    if (q < f && (q == 0 || skey2[q] != skey2[q - 1])) ++heads;
+    const int q = k * T + tid;
+    bool head = false;
+    if (q < f) head = (q == 0) || (KVT::key(skv[q]) != KVT::key(skv[q - 1]));
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (head) hmask |= 1u << k;
+    if (lane == 0) hpre[k * NW + warp] = __popc(bal);
   }
-  int total;
-  int outp = esc_block_scan1<T>(heads, wsum, total);
-  // positions of the heads, parked in skey (free since the ranking) so that the stores below are in output order
+  __syncthreads();
+  // exclusive scan of the I * NW group counts (<= 256 values): warp 0
+  if (warp == 0) {
+    int carry = 0;
+    for (int g0 = 0; g0 < I * NW; g0 += 32) {
+      const int g = g0 + lane;
+      const int v = g < I * NW ? hpre[g] : 0;
+      int inc = v;
 #pragma unroll
-  for (int k = 0; k < I; ++k) {
-    const int q = q0 + k;
-    if (q < f) {
-      const bool head = (q == 0 || skey2[q] != skey2[q - 1]);
-      skey[q] = head ? outp : -1;
-      if (head) ++outp;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (g < I * NW) hpre[g] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
   __syncthreads();
-  for (int q = tid; q < f; q += T) {
-    const int o = skey[q];
-    if (o >= 0 && o < nz) {
-      const int c = skey2[q];
-      S v = sval[q];
-      for (int q2 = q + 1; q2 < f && skey2[q2] == c; ++q2) v += sval[q2];  // ordinal order = the oracle's order
-      ciC[cbase + o] = c;
-      vC[cbase + o] = v;
+#pragma unroll
+  for (int k = 0; k < I; ++k) {
+    const int q = k * T + tid;
+    const bool head = (hmask >> k) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int o = hpre[k * NW + warp] + __popc(bal & ((1u << lane) - 1u));
+      if (o < nz) {  // more distinct columns than the symbolic pattern holds = precondition violated: drop, do not corrupt
+        const KV e = skv[q];
+        const int c = KVT::key(e);
+        S v = KVT::val(e);
+        for (int q2 = q + 1; q2 < f; ++q2) {  // ordinal order = the oracle's order
+          const KV e2 = skv[q2];
+          if (KVT::key(e2) != c) break;
+          v += KVT::val(e2);
+        }
+        ciC[cbase + o] = c;
+        vC[cbase + o] = v;
+      }
     }
   }
 }

@@ -18,6 +18,7 @@
 #include <limits.h>
 #include "common.cuh"
 #include "tile_ring.cuh"
+#include "spmm_items.h"
 #include <algorithm>
 #include <atomic>
 #include <stdlib.h>
@@ -29,6 +30,7 @@ namespace b200sp {
 // scratch owned by the plan (spmv.cu)
 int plan_mv_scratch(b200sp_spmv_plan* p, cudaStream_t st, size_t xt_bytes, size_t yt_bytes, void** xt, void** yt);
 void plan_set_last_kernel(b200sp_spmv_plan* p, const char* s);
+MMItems* plan_mm_items(b200sp_spmv_plan* p);
 
 template <typename S>
 __global__ void scale2d_kernel(int64_t rows, int k, S beta, S* __restrict__ Y, int64_t yr, int64_t yc) {
@@ -887,6 +889,262 @@ static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m,
   return B200SP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Item kernel (default for row-major X and Y with a plan; B200SP_SPMM_KERNEL=items): the gather-bound formulation.
+// On power-law matrices the tile kernel's row groups of one warp run loops of very different lengths and wait for
+// the longest; here the unit of work is an ITEM -- a run of <= LMAX consecutive entries of one row (spmm_items.h) --
+// and the items are sorted by length, longest first.  A group of KTL lanes (VW adjacent columns each, one 16-byte
+// load of the X row segment per lane and entry) owns one item, so the 32/KTL groups of a warp run loops of equal
+// length with 4 independent gathers in flight per lane, nothing waits, and the long items are scheduled first.
+// (col, val) are read straight from global memory (every lane of the group the same address: one request).
+// Single-item rows write Y; the pieces of longer rows write partial sums that spmm_item_reduce_kernel adds up in
+// piece order (no atomics: deterministic).  Per entry the sum order is the storage order.
+// ---------------------------------------------------------------------------
+static constexpr int MMI_MAXL = 256;
+
+// histogram of item lengths (0..lmax), number of multi-piece rows and of their pieces
+__global__ void __launch_bounds__(256) mmi_count_kernel(int m, const int* __restrict__ row_ptr, int lmax, int* __restrict__ hist,
+                                                        int* __restrict__ counters) {
+  __shared__ int sh[MMI_MAXL + 1];
+  __shared__ int sc[2];
+  for (int i = threadIdx.x; i <= lmax; i += 256) sh[i] = 0;
+  if (threadIdx.x < 2) sc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = blockIdx.x * 256 + threadIdx.x; r < m; r += gridDim.x * 256) {
+    const int len = row_ptr[r + 1] - row_ptr[r];
+    const int pieces = len <= lmax ? 1 : (len + lmax - 1) / lmax;
+    if (pieces == 1) {
+      atomicAdd(&sh[len], 1);
+    } else {
+      atomicAdd(&sh[lmax], pieces - 1);
+      atomicAdd(&sh[len - (pieces - 1) * lmax], 1);
+      atomicAdd(&sc[0], 1);
+      atomicAdd(&sc[1], pieces);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= lmax; i += 256)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+  if (threadIdx.x < 2 && sc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sc[threadIdx.x]);
+}
+
+// cursor[len] = first position of the items of that length (longest first); block-aggregated reservation of ranges
+__global__ void __launch_bounds__(256) mmi_fill_kernel(int m, const int* __restrict__ row_ptr, int lmax, int* __restrict__ cursor,
+                                                       int* __restrict__ counters /* [2] multi cursor, [3] partial cursor */,
+                                                       int4* __restrict__ items, int4* __restrict__ multi) {
+  __shared__ int sh[MMI_MAXL + 1];
+  __shared__ int sbase[MMI_MAXL + 1];
+  const int passes = (m + (int)(gridDim.x * 256) - 1) / (int)(gridDim.x * 256);
+  for (int it = 0; it < passes; ++it) {
+    const int r = (it * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+    for (int i = threadIdx.x; i <= lmax; i += 256) sh[i] = 0;
+    __syncthreads();
+    int len = 0, pieces = 0, rank_last = 0, rank_full = 0, last = 0;
+    if (r < m) {
+      len = row_ptr[r + 1] - row_ptr[r];
+      pieces = len <= lmax ? 1 : (len + lmax - 1) / lmax;
+      last = len - (pieces - 1) * lmax;
+      if (pieces > 1) rank_full = atomicAdd(&sh[lmax], pieces - 1);
+      rank_last = atomicAdd(&sh[last], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= lmax; i += 256)
+      if (sh[i]) sbase[i] = atomicAdd(&cursor[i], sh[i]);
+    __syncthreads();
+    if (r < m) {
+      const int e0 = row_ptr[r];
+      if (pieces == 1) {
+        items[sbase[len] + rank_last] = make_int4(r, e0, len, -1);
+      } else {
+        const int slot0 = atomicAdd(&counters[3], pieces);
+        multi[atomicAdd(&counters[2], 1)] = make_int4(r, slot0, pieces, 0);
+        for (int s = 0; s < pieces - 1; ++s) items[sbase[lmax] + rank_full + s] = make_int4(r, e0 + s * lmax, lmax, slot0 + s);
+        items[sbase[last] + rank_last] = make_int4(r, e0 + (pieces - 1) * lmax, last, slot0 + pieces - 1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int plan_analyse_items(b200sp_spmv_plan* p, cudaStream_t st, int lmax, int m, int64_t nnz, const int* row_ptr, MMItems** out) {
+  MMItems* mi = plan_mm_items(p);
+  *out = mi;
+  if (mi->items && mi->key_row_ptr == row_ptr && mi->key_m == m && mi->key_nnz == nnz && mi->key_lmax == lmax) return B200SP_OK;
+  void* old[] = {mi->items, mi->multi, mi->partial};
+  for (void* q : old)
+    if (q) cudaFreeAsync(q, st);
+  *mi = MMItems();
+  DevTmp tmp(st);
+  int *hist, *counters;
+  B200SP_CUDA_TRY(tmp.alloc(&hist, lmax + 1));
+  B200SP_CUDA_TRY(tmp.alloc(&counters, 4));
+  B200SP_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(lmax + 1), st));
+  B200SP_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 4, st));
+  const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
+  mmi_count_kernel<<<blocks, 256, 0, st>>>(m, row_ptr, lmax, hist, counters);
+  B200SP_LAUNCH_CHECK();
+  int h_hist[MMI_MAXL + 1], h_cnt[4];
+  B200SP_CUDA_TRY(cudaMemcpyAsync(h_hist, hist, sizeof(int) * (size_t)(lmax + 1), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // once per matrix
+  int h_cur[MMI_MAXL + 1];
+  long long total = 0;
+  for (int l = lmax; l >= 0; --l) {  // longest first
+    h_cur[l] = (int)total;
+    total += h_hist[l];
+  }
+  B200SP_REQUIRE(total <= (long long)INT_MAX, "spmm: too many work items");
+  mi->n_items = (int)total;
+  mi->n_multi = h_cnt[0];
+  mi->n_partial = h_cnt[1];
+  mi->lmax = lmax;
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&mi->items, sizeof(int4) * (size_t)std::max(mi->n_items, 1), st));
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&mi->multi, sizeof(int4) * (size_t)std::max(mi->n_multi, 1), st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(hist, h_cur, sizeof(int) * (size_t)(lmax + 1), cudaMemcpyHostToDevice, st));
+  mmi_fill_kernel<<<blocks, 256, 0, st>>>(m, row_ptr, lmax, hist, counters, mi->items, mi->multi);
+  B200SP_LAUNCH_CHECK();
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // h_cur is pageable host memory: consumed before it goes out of scope
+  mi->key_row_ptr = row_ptr;
+  mi->key_m = m;
+  mi->key_nnz = nnz;
+  mi->key_lmax = lmax;
+  return B200SP_OK;
+}
+
+template <typename S, int VW, int KTL>
+__global__ void __launch_bounds__(256)
+    spmm_item_kernel(int n_items, const int4* __restrict__ items, int k, const int* __restrict__ col_idx,
+                     const S* __restrict__ vals, const S* __restrict__ X, int64_t ldx, S* __restrict__ Y, int64_t ldy,
+                     S* __restrict__ partial, S alpha, S beta) {
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t q = gt / KTL;
+  const int t = (int)(gt % KTL);
+  if (q >= n_items) return;
+  const int4 it = __ldg(items + q);
+  const int row = it.x, e0 = it.y, len = it.z, slot = it.w;
+  const int nstrips = (k + KTL * VW - 1) / (KTL * VW);
+  for (int strip = 0; strip < nstrips; ++strip) {
+    const int j = (strip * KTL + t) * VW;
+    if (j >= k) break;  // k % VW == 0: a lane's VW columns are all in or all out
+    Acc<S, VW> acc;
+#pragma unroll
+    for (int c = 0; c < VW; ++c) acc.a[c] = S(0);
+    const S* xb = X + j;
+    int e = e0;
+    const int e4 = e0 + (len & ~3);
+    for (; e < e4; e += 4) {
+      int c[4];
+      S av[4];
+      Acc<S, VW> xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = ld_stream(col_idx + e + u);
+        av[u] = ld_stream(vals + e + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = load_x<S, VW>(xb + (int64_t)c[u] * ldx);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av[u] * xv[u].a[cc];
+    }
+    for (; e < e0 + len; ++e) {
+      const int c = ld_stream(col_idx + e);
+      const S av = ld_stream(vals + e);
+      const Acc<S, VW> xv = load_x<S, VW>(xb + (int64_t)c * ldx);
+#pragma unroll
+      for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av * xv.a[cc];
+    }
+    S o[VW];
+    S* dst;
+    if (slot < 0) {
+      dst = Y + (int64_t)row * ldy + j;
+      if (beta == S(0)) {
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) o[cc] = alpha * acc.a[cc];
+      } else {
+        const Acc<S, VW> old = load_x<S, VW>(dst);
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) o[cc] = beta * old.a[cc] + alpha * acc.a[cc];
+      }
+    } else {
+      dst = partial + (int64_t)slot * k + j;  // raw sums; alpha and beta are applied by the reduce kernel
+#pragma unroll
+      for (int cc = 0; cc < VW; ++cc) o[cc] = acc.a[cc];
+    }
+    if constexpr (VW == 1) {
+      dst[0] = o[0];
+    } else {
+      using V = typename VecOf<S>::type;
+      *reinterpret_cast<V*>(dst) = vec_pack(o);
+    }
+  }
+}
+
+// rows of several pieces: Y(row, :) = beta * Y(row, :) + alpha * (piece 0 + piece 1 + ...), pieces added in order
+template <typename S>
+__global__ void __launch_bounds__(256)
+    spmm_item_reduce_kernel(int n_multi, const int4* __restrict__ multi, int k, const S* __restrict__ partial, S* __restrict__ Y,
+                            int64_t ldy, S alpha, S beta) {
+  const int64_t total = (int64_t)n_multi * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 d = multi[i / k];
+    const int j = (int)(i % k);
+    const S* src = partial + (int64_t)d.y * k + j;
+    S sum = S(0);
+    for (int s = 0; s < d.z; ++s) sum += src[(int64_t)s * k];
+    S* yp = Y + (int64_t)d.x * ldy + j;
+    *yp = (beta == S(0)) ? alpha * sum : beta * *yp + alpha * sum;
+  }
+}
+
+template <typename S>
+static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
+                           const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
+  int LMAX = 128;  // entries per item (B200SP_SPMM_ITEM_LMAX: 16..256)
+  if (const char* e = getenv("B200SP_SPMM_ITEM_LMAX")) {
+    const int v = atoi(e);
+    if (v >= 16 && v <= MMI_MAXL) LMAX = v;
+  }
+  MMItems* mi;
+  int rc = plan_analyse_items(p, st, LMAX, m, nnz, row_ptr, &mi);
+  if (rc) return rc;
+  const size_t need = sizeof(S) * (size_t)mi->n_partial * (size_t)k;
+  if (need > mi->partial_bytes) {
+    if (mi->partial) cudaFreeAsync(mi->partial, st);
+    mi->partial = nullptr;
+    mi->partial_bytes = 0;
+    B200SP_CUDA_TRY(cudaMallocAsync(&mi->partial, need, st));
+    mi->partial_bytes = need;
+  }
+  constexpr int W = VecOf<S>::W;
+  const int lanes_needed = vec ? (k + W - 1) / W : k;
+  int KTL = 1;
+  while (KTL < lanes_needed && KTL < 32) KTL <<= 1;
+  const int64_t threads = (int64_t)mi->n_items * KTL;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  if (grid > 0) {
+#define B200SP_MMI(V, L)                                                                                                   \
+  case L:                                                                                                                  \
+    spmm_item_kernel<S, V, L><<<grid, 256, 0, st>>>(mi->n_items, mi->items, k, col_idx, vals, X, ldx, Y, ldy, (S*)mi->partial, \
+                                                    alpha, beta);                                                          \
+    break;
+    if (vec) {
+      switch (KTL) { B200SP_MMI(W, 1) B200SP_MMI(W, 2) B200SP_MMI(W, 4) B200SP_MMI(W, 8) B200SP_MMI(W, 16) B200SP_MMI(W, 32) }
+    } else {
+      switch (KTL) { B200SP_MMI(1, 1) B200SP_MMI(1, 2) B200SP_MMI(1, 4) B200SP_MMI(1, 8) B200SP_MMI(1, 16) B200SP_MMI(1, 32) }
+    }
+#undef B200SP_MMI
+    B200SP_LAUNCH_CHECK();
+  }
+  if (mi->n_multi > 0) {
+    const int g = (int)std::min<int64_t>(((int64_t)mi->n_multi * k + 255) / 256, (int64_t)sm_count() * 8);
+    spmm_item_reduce_kernel<S><<<std::max(g, 1), 256, 0, st>>>(mi->n_multi, mi->multi, k, (const S*)mi->partial, Y, ldy, alpha, beta);
+    B200SP_LAUNCH_CHECK();
+  }
+  return B200SP_OK;
+}
+
 // which rank-2 kernel: 0 = row per group, 1 = nnz-split, 2 = tile, 3 = tile with 16-byte X loads (default:
 // measured 1.74 ms vs 4.01 ms for the split kernel on R-MAT scale 21 x 16 columns, profiles/README.md).
 // B200SP_SPMM_KERNEL=row|split|tile|tilev overrides.
@@ -896,7 +1154,8 @@ static int mm_kernel_choice(b200sp_spmv_plan* p) {
   if (e && e[0] == 'r') return 0;
   if (e && e[0] == 's') return 1;
   if (e && e[0] == 't') return (e[1] == 'i' && e[2] == 'l' && e[3] == 'e' && e[4] == 'v') ? 3 : 2;
-  return 3;
+  if (e && e[0] == 'i') return 4;
+  return 4;  // items (B200SP_SPMM_KERNEL=items)
 }
 
 static bool use_split_kernel(b200sp_spmv_plan* p) {
@@ -947,6 +1206,12 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
   const bool split = use_split_kernel(p);
   const int choice = mm_kernel_choice(p);
   if (xrm && yrm) {
+    if (choice == 4) {
+      constexpr int W = VecOf<S>::W;
+      const bool vec = (k % W == 0) && (ldx % W == 0) && (ldy % W == 0) && ((((uintptr_t)X) | ((uintptr_t)Y)) & 15u) == 0;
+      plan_set_last_kernel(p, vec ? "spmm_items_vec" : "spmm_items");
+      return launch_mm_items<S>(p, st, vec, m, k, nnz, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
+    }
     if (choice >= 2 && (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0) {
       constexpr int W = VecOf<S>::W;
       const bool vec = choice == 3 && (k % W == 0) && (ldx % W == 0) && (ldy % W == 0) && ((((uintptr_t)X) | ((uintptr_t)Y)) & 15u) == 0;
@@ -983,8 +1248,12 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
         B200SP_LAUNCH_CHECK();
       }
     }
-    const bool tile_ok = choice >= 2 && (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0;
-    if (tile_ok) {
+    const bool tile_ok = choice >= 2 && (choice == 4 || (((uintptr_t)vals | (uintptr_t)col_idx | (uintptr_t)row_ptr) & 15u) == 0);
+    if (choice == 4) {
+      constexpr int W = VecOf<S>::W;
+      const bool vec = (k % W == 0) && (ldxr % W == 0) && (ldyr % W == 0) && ((((uintptr_t)Xr) | ((uintptr_t)Yr)) & 15u) == 0;
+      rc = launch_mm_items<S>(p, st, vec, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
+    } else if (tile_ok) {
       constexpr int W = VecOf<S>::W;
       const bool vec = choice == 3 && (k % W == 0) && (ldxr % W == 0) && (ldyr % W == 0) && ((((uintptr_t)Xr) | ((uintptr_t)Yr)) & 15u) == 0;
       rc = launch_mm_tile<S>(p, st, vec, m, k, nnz, row_ptr, col_idx, vals, Xr, ldxr, Yr, ldyr, alpha, beta);
@@ -997,7 +1266,7 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
       relayout_kernel<S, false><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
       B200SP_LAUNCH_CHECK();
     }
-    plan_set_last_kernel(p, tile_ok ? "spmm_relayout+tile" : (split ? "spmm_relayout+split" : "spmm_relayout+rowmajor"));
+    plan_set_last_kernel(p, choice == 4 ? "spmm_relayout+items" : tile_ok ? "spmm_relayout+tile" : (split ? "spmm_relayout+split" : "spmm_relayout+rowmajor"));
     return B200SP_OK;
   }
   const int g = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, (int64_t)sm_count() * 16);

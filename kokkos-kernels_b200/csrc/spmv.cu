@@ -20,6 +20,7 @@
 //   spmv_transpose_kernel  T/H modes: y pre-scaled, atomicAdd scatter.
 #include "common.cuh"
 #include "tile_ring.cuh"
+#include "spmm_items.h"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -656,6 +657,8 @@ struct b200sp_spmv_plan {
   const int* mm_key_row_ptr = nullptr;
   int mm_key_m = -1, mm_key_cap = -1, mm_key_lmax = -1;
   int64_t mm_key_nnz = -1;
+  // rank-2 item kernel (spmm.cu, spmm_items.h): length-sorted work items
+  b200sp::MMItems mmi;
   // cached transpose (B200SP_SPMV_OPT_CACHE_TRANSPOSE): structure of A^T + source entry of each of its entries,
   // values re-gathered on every call (they may have changed in place), and a plan of its own for A^T
   bool cache_transpose = false;
@@ -727,7 +730,13 @@ static void plan_release_mm(b200sp_spmv_plan* p, cudaStream_t st) {
   p->mm_segs = nullptr;
   p->mm_n_seg = nullptr;
   p->mm_key_row_ptr = nullptr;
+  void* iptrs[] = {p->mmi.items, p->mmi.multi, p->mmi.partial};
+  for (void* q : iptrs)
+    if (q) cudaFreeAsync(q, st);
+  p->mmi = b200sp::MMItems();
 }
+
+b200sp::MMItems* plan_mm_items(b200sp_spmv_plan* p) { return &p->mmi; }
 
 template <typename S>
 static int plan_analyse(b200sp_spmv_plan* p, cudaStream_t st, int cfg, int m, int n, int64_t nnz,

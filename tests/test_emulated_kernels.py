@@ -165,8 +165,8 @@ def test_spmv_cached_transpose(emu, oracle):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("kernel,extra", [("tilev", {}), ("tile", {}), ("split", {}), ("row", {}),
-                                          ("tilev", {"B200SP_SPMM_SEG": "vec"}), ("tilev", {"B200SP_SPMM_LMAX": "64"})])
+@pytest.mark.parametrize("kernel,extra", [("items", {}), ("items", {"B200SP_SPMM_ITEM_LMAX": "16"}), ("tilev", {}), ("tile", {}), ("split", {}),
+                                          ("row", {}), ("tilev", {"B200SP_SPMM_SEG": "vec"}), ("tilev", {"B200SP_SPMM_LMAX": "64"})])
 def test_spmm_kernels_layouts(emu, oracle, dtype, kernel, extra):
     rng = np.random.default_rng(11)
     rows, cols = 1500, 1300
@@ -176,7 +176,7 @@ def test_spmm_kernels_layouts(emu, oracle, dtype, kernel, extra):
     ci = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.int32)
     v = rng.uniform(-1, 1, len(ci)).astype(dtype)
     with env(B200SP_SPMM_KERNEL=kernel, **extra):
-        for k in (1, 3, 8, 17):
+        for k in (1, 3, 8, 17, 16, 40) if kernel == "items" else (1, 3, 8, 17):
             for order in "CF":
                 X = np.asarray(rng.random((cols, k)).astype(dtype), order=order)
                 Y0 = np.asarray(rng.random((rows, k)).astype(dtype), order=order)

@@ -145,6 +145,14 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }  // built with -ffp-contract=off: no fusion
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline int __double2loint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b & 0xffffffffull); }
+static inline int __double2hiint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+  const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)lo;
+  double v; memcpy(&v, &b, 8); return v;
+}
+static inline int __float_as_int(float v) { int b; memcpy(&b, &v, 4); return b; }
+static inline float __int_as_float(int b) { float v; memcpy(&v, &b, 4); return v; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(uintptr_t)p; }
 
 static inline int min(int a, int b) { return a < b ? a : b; }
