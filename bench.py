@@ -21,13 +21,22 @@ import subprocess
 import sys
 
 
-def host_threads():
-    """Hardware threads this process may use (its affinity mask), NOT OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to
-    every rank, which must not turn the CPU legs into single-core runs."""
+def _affinity_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+# Read ONCE, before any OpenMP runtime starts: with OMP_PROC_BIND set, libgomp binds the initial thread to its first place
+# (one core) in the first parallel region, after which the affinity mask of this thread shows 2 hardware threads.
+_HOST_THREADS = _affinity_threads()
+
+
+def host_threads():
+    """Hardware threads this process may use (its affinity mask at start-up), NOT OMP_NUM_THREADS: torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which must not turn the CPU legs into single-core runs."""
+    return _HOST_THREADS
 
 
 _REF_ARM = "reference" in sys.argv and "--impl" in sys.argv

@@ -632,23 +632,15 @@ int launch_tile(b200sp_bsr_plan* p, cudaStream_t st, int mb, int64_t nnzb, int b
   constexpr int UNR = 4;
   auto kern = bsr_tile_kernel<S, NW, STAGES, VCAP, UNR>;
   const size_t smem = sizeof(Smem) + 128;
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.store(true, std::memory_order_release);
-  }
-  static std::atomic<int> occ{0};
-  if (occ.load() == 0) {
-    int o = 0;
-    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, (NW + 1) * 32, smem));
-    occ.store(o > 0 ? o : 1);
-  }
+  static KernelSetup ks;
+  int occ_dev = 1;
+  if (int rc0 = kernel_setup(ks, kern, (NW + 1) * 32, smem, &occ_dev)) return rc0;
   int capb = std::min(Smem::CCAP, VCAP / (bs * bs)) & ~3;
   int rc = bsr_analyse(p, st, mb, nnzb, bs, capb, rp);
   if (rc != B200SP_OK) return rc;
   const double avg = mb > 0 ? (double)nnzb * bs / (double)mb : 0.0;
   const int lpr = pick_lpr(avg, bs, 32);
-  const int grid = std::max(1, std::min(p->n_tiles, sm_count() * occ.load()));
+  const int grid = std::max(1, std::min(p->n_tiles, sm_count() * occ_dev));
   kern<<<grid, (NW + 1) * 32, smem, st>>>(mb, nnzb, bs, lpr, p->lmaxb, p->n_tiles, p->tiles, rp, ci, v, x, y, alpha, beta);
   B200SP_LAUNCH_CHECK();
   // block rows longer than a stage: one warp per point row, list and count stay on the device
@@ -667,21 +659,13 @@ int launch_tile_e(b200sp_bsr_plan* p, cudaStream_t st, int mb, int64_t nnzb, con
   constexpr int UNR = 4;
   auto kern = bsr_tile_e_kernel<S, BS, NW, STAGES, VCAP, UNR>;
   const size_t smem = sizeof(Smem) + 128;
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.store(true, std::memory_order_release);
-  }
-  static std::atomic<int> occ{0};
-  if (occ.load() == 0) {
-    int o = 0;
-    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, (NW + 1) * 32, smem));
-    occ.store(o > 0 ? o : 1);
-  }
+  static KernelSetup ks;
+  int occ_dev = 1;
+  if (int rc0 = kernel_setup(ks, kern, (NW + 1) * 32, smem, &occ_dev)) return rc0;
   const int capb = std::min(Smem::CCAP, VCAP / (BS * BS)) & ~3;
   int rc = bsr_analyse(p, st, mb, nnzb, BS, capb, rp);
   if (rc != B200SP_OK) return rc;
-  const int grid = std::max(1, std::min(p->n_tiles, sm_count() * occ.load()));
+  const int grid = std::max(1, std::min(p->n_tiles, sm_count() * occ_dev));
   kern<<<grid, (NW + 1) * 32, smem, st>>>(mb, nnzb, p->lmaxb, p->n_tiles, p->tiles, rp, ci, v, x, y, alpha, beta);
   B200SP_LAUNCH_CHECK();
   bsr_vector_kernel<S><<<sm_count() * 2, 256, 0, st>>>(mb, BS, 32, rp, ci, v, x, y, alpha, beta, p->long_rows, p->n_long);

@@ -47,6 +47,30 @@ extern std::atomic<long long> g_launches;
 
 int sm_count();  // SMs of the current device (cached per device)
 
+// Launch setup of a kernel with more than 48 KB of dynamic shared memory: the opt-in attribute and the occupancy are
+// per DEVICE, so they are cached per (kernel instantiation, device) -- one process may drive several GPUs.
+struct KernelSetup {
+  std::atomic<int> occ[32];
+  KernelSetup() {
+    for (auto& o : occ) o.store(0);
+  }
+};
+template <class K>
+static inline int kernel_setup(KernelSetup& ks, K kern, int threads, size_t smem, int* occ_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const bool cacheable = dev >= 0 && dev < 32;
+  int occ = cacheable ? ks.occ[dev].load(std::memory_order_acquire) : 0;
+  if (occ == 0) {
+    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    if (cacheable) ks.occ[dev].store(occ, std::memory_order_release);
+  }
+  *occ_out = occ;
+  return B200SP_OK;
+}
+
 // stream-ordered temporaries of one host call
 struct DevTmp {  // frees stream-ordered on scope exit
   cudaStream_t st;
@@ -92,6 +116,15 @@ __device__ __forceinline__ T ldg(const T* p) {
 __device__ __forceinline__ int ld_stream(const int* p) { return *p; }
 __device__ __forceinline__ double ld_stream(const double* p) { return *p; }
 __device__ __forceinline__ float ld_stream(const float* p) { return *p; }
+__device__ __forceinline__ int ld_once(const int* p, uint64_t) { return *p; }
+__device__ __forceinline__ double ld_once(const double* p, uint64_t) { return *p; }
+__device__ __forceinline__ float ld_once(const float* p, uint64_t) { return *p; }
+__device__ __forceinline__ int4 ld_once(const int4* p, uint64_t) { return *p; }
+__device__ __forceinline__ void st_once(int* p, int v, uint64_t) { *p = v; }
+__device__ __forceinline__ void st_once(float* p, float v, uint64_t) { *p = v; }
+__device__ __forceinline__ void st_once(double* p, double v, uint64_t) { *p = v; }
+__device__ __forceinline__ void st_once(float4* p, const float4& v, uint64_t) { *p = v; }
+__device__ __forceinline__ void st_once(double2* p, const double2& v, uint64_t) { *p = v; }
 #else
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -168,6 +201,47 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+
+// data that is touched ONCE per kernel (matrix streams, work-item lists, results): no L1 allocation and an L2 evict-first
+// policy (createpolicy, l2_policy_evict_first()), so that it does not push the gathered operand (x / X rows) out of L2
+__device__ __forceinline__ int ld_once(const int* p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ld_once(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int4 ld_once(const int4* p, uint64_t pol) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_once(int* p, int v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_once(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_once(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_once(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_once(double2* p, const double2& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
 
 #endif  // B200SP_EMU

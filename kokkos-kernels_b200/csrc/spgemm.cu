@@ -1194,10 +1194,20 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   if (variant >= 7 && p->esc_rows) {
     // default: register-resident expand / sort / compress kernels (spgemm_esc.cuh) for rows of <= 8192 products,
     // the two-walk hash kernels for the rest
+    // <S, threads, products per thread, log2(buckets), CTAs per SM for the register budget>.  B200SP_ESC_CFG (tuning): 1 = 256
+    // threads x 4 products for the 1024-product bin (more resident warps), 2 = 1024 buckets, 3 = both
+    int esc_cfg = 0;
+    if (const char* e = getenv("B200SP_ESC_CFG")) esc_cfg = atoi(e);
     if ((rc = launch_esc_num<S, 32, 8, 9, 32>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-    if ((rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-    if ((rc = launch_esc_num<S, 512, 8, 13, 2>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-    if ((rc = launch_esc_num<S, 1024, 8, 14, 1>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    switch (esc_cfg) {
+      case 1: rc = launch_esc_num<S, 256, 4, 11, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 2: rc = launch_esc_num<S, 128, 8, 10, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 3: rc = launch_esc_num<S, 256, 4, 10, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      default: rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+    }
+    if (rc) return rc;
+    if ((rc = launch_esc_num<S, 512, 8, 12, 2>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
+    if ((rc = launch_esc_num<S, 1024, 8, 13, 1>(st, p, 3, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
     if (p->esc_off[kEscBins] < m) {
       p->cur_rows = p->num_rows;
       p->cur_off = p->num_off;
@@ -1334,8 +1344,27 @@ static int jacobi_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int
 
 extern "C" {
 
+// The phases allocate their scratch with cudaMallocAsync.  The default pool hands unused memory back to the driver at every
+// synchronisation point (release threshold 0), and spgemm_symbolic synchronises by contract (it returns nnz(C)): each call
+// would then map a few hundred MB again, which costs more than its kernels.  Keep the pool's memory (once per device).
+static void keep_async_pool_memory() {
+#ifndef B200SP_EMU
+  static std::atomic<unsigned> done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+  if (done.load() & (1u << dev)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done.fetch_or(1u << dev);
+#endif
+}
+
 int b200sp_spgemm_plan_create(b200sp_spgemm_plan** plan) {
   B200SP_REQUIRE(plan != nullptr, "spgemm_plan_create: null output pointer");
+  keep_async_pool_memory();
   b200sp_spgemm_plan* p = new (std::nothrow) b200sp_spgemm_plan();
   if (!p) {
     set_error("spgemm_plan_create: out of host memory");
@@ -1463,10 +1492,18 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   if (sym_variant >= 3) {
     const int* er = p->esc_rows;
     const int* eo = p->esc_off;
+    int esc_cfg = 0;
+    if (const char* e = getenv("B200SP_ESC_CFG")) esc_cfg = atoi(e);
     if ((rc = launch_esc_sym<32, 8, 9, 1>(st, eo[1] - eo[0], er + eo[0], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<512, 8, 13, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
-    if ((rc = launch_esc_sym<1024, 8, 14, 1>(st, eo[4] - eo[3], er + eo[3], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
+    switch (esc_cfg) {
+      case 1: rc = launch_esc_sym<256, 4, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 2: rc = launch_esc_sym<128, 8, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 3: rc = launch_esc_sym<256, 4, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      default: rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+    }
+    if (rc) return rc;
+    if ((rc = launch_esc_sym<512, 8, 12, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
+    if ((rc = launch_esc_sym<1024, 8, 13, 1>(st, eo[4] - eo[3], er + eo[3], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
     if ((rc = launch_sym<512, 15>(st, eo[5] - eo[4], er + eo[4], lb, rpA, ciA, rpB, ciB, row_nnz))) return rc;
     for (int b = 0; b <= kEscBins + 2; ++b) soff[b] = eo[b];
     sym_rows = p->esc_rows;

@@ -241,7 +241,18 @@ __device__ __forceinline__ void esc_expand(int f, int nA, int L0, const int* bs,
                                            const int* __restrict__ ciB, const S* __restrict__ vB, int nokey, int (&col)[I],
                                            S (&val)[I]) {
   const int tid = threadIdx.x;
-  if (L0 > 0) {
+  if (L0 == 32 && f == T * I) {
+    // the regular case (config 4: 32 entries in every row of B, a full bin): item k of this thread is entry `lane` of the
+    // B row of A's entry k * (T/32) + warp -- no index arithmetic, no predicates
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < I; ++k) {
+      const int j = k * (T / 32) + warp;
+      const int jb = bs[j] + lane;
+      col[k] = ld_stream(ciB + jb);
+      if (WITH_VALS) val[k] = mul_rn(ld_stream(vB + jb), va[j]);  // b_val * a_val (impl_seq.hpp:163)
+    }
+  } else if (L0 > 0) {
     int j = tid / L0, t = tid - j * L0;
     const int dj = T / L0, dt = T - dj * L0;
 #pragma unroll
@@ -327,6 +338,7 @@ struct EscSymLayout {
   static constexpr int NA = CAP / 2;
   // off[NB + 4] | wsum[36] | union { bs[NA], pre[NA + 4] ; skey[CAP] }  (the staging is dead when the keys are scattered)
   static constexpr size_t BYTES = sizeof(int) * (size_t)(NB + 4 + 36 + CAP + 8);
+  static_assert(BYTES <= 227 * 1024, "esc_sym_kernel: configuration exceeds the shared memory of an SM");
 };
 
 template <int T, int I, int LOG2NB, int MINB>
@@ -403,6 +415,7 @@ struct EscNumLayout {
   static constexpr size_t SORT_BYTES = sizeof(KV) * (size_t)CAP;
   static constexpr size_t UNION_BYTES = ((STAGE_BYTES > SORT_BYTES ? STAGE_BYTES : SORT_BYTES) + 15) & ~(size_t)15;
   static constexpr size_t BYTES = OFF_BYTES + KEY_BYTES + WS_BYTES + ORD_BYTES + UNION_BYTES;
+  static_assert(BYTES <= 227 * 1024, "esc_num_kernel: configuration exceeds the shared memory of an SM");
 };
 
 template <typename S, int T, int I, int LOG2NB, int MINB>
@@ -470,10 +483,11 @@ __global__ void __launch_bounds__(T, MINB)
         skv[lo + less] = KVT::pack(col[k], val[k]);
       }
     __syncthreads();
+    const uint64_t once = l2_policy_evict_first();  // C is written once: keep L2 for the gathered rows of B
     for (int q = tid; q < f; q += T) {
       const KV e = skv[q];
-      ciC[cbase + q] = KVT::key(e);
-      vC[cbase + q] = KVT::val(e);
+      st_once(ciC + cbase + q, KVT::key(e), once);
+      st_once(vC + cbase + q, KVT::val(e), once);
     }
     return;
   }

@@ -224,8 +224,11 @@ __global__ void __launch_bounds__(256)
     const int chunk = (int)(w / nstrips);
     const int j = (int)(w % nstrips) * KT + t;
     const bool jok = j < k;
-    const int64_t c0 = (int64_t)chunk * Q;
-    const int64_t c1 = (c0 + Q < nnz) ? c0 + Q : nnz;
+    // chunk 0 starts at the first entry of row 0: the windows of the 64-bit-offset path (spmv64.cu) pass relative row maps
+    // that start at 1..3, and the entries before row_ptr[0] belong to the previous window's last row
+    const int64_t cq = (int64_t)chunk * Q;
+    const int64_t c0 = (chunk == 0) ? (int64_t)row_ptr[0] : cq;
+    const int64_t c1 = (cq + Q < nnz) ? cq + Q : nnz;
     int row = (chunk == 0) ? 0 : chunk_row[chunk];
     // cache of KT row ends: lane t holds row_ptr[ebase + 1 + t]
     int ebase = row;
@@ -789,14 +792,9 @@ static int launch_mm_tile_k(cudaStream_t st, const MMTileView& tv, int m, int k,
   using Ring = TileRing<S, CAP, STAGES>;
   auto kern = spmm_tile_kernel<S, VW, KTL, NW, STAGES, CAP, UNR>;
   const size_t smem = sizeof(Ring) + 128;
-  static std::atomic<int> occ_cached{0};  // per instantiation: attribute set + occupancy queried once
-  int occ = occ_cached.load(std::memory_order_acquire);
-  if (occ == 0) {
-    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NW + 1) * 32, smem));
-    if (occ < 1) occ = 1;
-    occ_cached.store(occ, std::memory_order_release);
-  }
+  static KernelSetup ks;  // per instantiation and device: attribute set + occupancy queried once
+  int occ = 1;
+  if (int rc = kernel_setup(ks, kern, (NW + 1) * 32, smem, &occ)) return rc;
   int grid = std::min(tv.n_tiles, sm_count() * occ);
   if (grid < 1) grid = 1;
   kern<<<grid, (NW + 1) * 32, smem, st>>>(m, k, nnz, tv.n_tiles, tv.LMAX, tv.tiles, row_ptr, col_idx, vals, X, ldx, Y, ldy, alpha, beta);
@@ -1020,7 +1018,9 @@ __global__ void __launch_bounds__(256)
   const int64_t q = gt / KTL;
   const int t = (int)(gt % KTL);
   if (q >= n_items) return;
-  const int4 it = __ldg(items + q);
+  // the matrix, the item list and Y pass through once: evict-first in L2, which then belongs to the gathered rows of X
+  const uint64_t once = l2_policy_evict_first();
+  const int4 it = ld_once(items + q, once);
   const int row = it.x, e0 = it.y, len = it.z, slot = it.w;
   const int nstrips = (k + KTL * VW - 1) / (KTL * VW);
   for (int strip = 0; strip < nstrips; ++strip) {
@@ -1038,8 +1038,8 @@ __global__ void __launch_bounds__(256)
       Acc<S, VW> xv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        c[u] = ld_stream(col_idx + e + u);
-        av[u] = ld_stream(vals + e + u);
+        c[u] = ld_once(col_idx + e + u, once);
+        av[u] = ld_once(vals + e + u, once);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) xv[u] = load_x<S, VW>(xb + (int64_t)c[u] * ldx);
@@ -1049,8 +1049,8 @@ __global__ void __launch_bounds__(256)
         for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av[u] * xv[u].a[cc];
     }
     for (; e < e0 + len; ++e) {
-      const int c = ld_stream(col_idx + e);
-      const S av = ld_stream(vals + e);
+      const int c = ld_once(col_idx + e, once);
+      const S av = ld_once(vals + e, once);
       const Acc<S, VW> xv = load_x<S, VW>(xb + (int64_t)c * ldx);
 #pragma unroll
       for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av * xv.a[cc];
@@ -1073,10 +1073,10 @@ __global__ void __launch_bounds__(256)
       for (int cc = 0; cc < VW; ++cc) o[cc] = acc.a[cc];
     }
     if constexpr (VW == 1) {
-      dst[0] = o[0];
+      st_once(dst, o[0], once);
     } else {
       using V = typename VecOf<S>::type;
-      *reinterpret_cast<V*>(dst) = vec_pack(o);
+      st_once(reinterpret_cast<V*>(dst), vec_pack(o), once);
     }
   }
 }
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(256)
 template <typename S>
 static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
                            const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
-  int LMAX = 128;  // entries per item (B200SP_SPMM_ITEM_LMAX: 16..256)
+  int LMAX = 64;  // entries per item (B200SP_SPMM_ITEM_LMAX: 16..256); measured on R-MAT scale 23: 32: 3.22, 64: 2.94, 128: 3.36, 256: 3.66 ms
   if (const char* e = getenv("B200SP_SPMM_ITEM_LMAX")) {
     const int v = atoi(e);
     if (v >= 16 && v <= MMI_MAXL) LMAX = v;

@@ -691,7 +691,9 @@ struct b200sp_spmv_plan {
     int tile_b[9];
     int row_b[9];
     const int* key = nullptr;
-    int key_cfg = -1;
+    int key_cfg = -1, key_m = -1;
+    int64_t key_nnz = -1;
+    const void* key_tiles = nullptr;  // the tile table the piece bounds were cut from
     bool defer = false;  // B200SP_SPMV_OPT_HOSTVEC_DEFER: `stream` does not wait for a call's download before the next call computes
     int last_b = -1;     // buffer of the latest call whose download `stream` has not been made to wait for
   } pipe;
@@ -899,19 +901,11 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   using Smem = TileSmem<S, CAP, STAGES>;
   auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP, UNR>;
   const size_t smem = sizeof(Smem) + 128;
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.store(true, std::memory_order_release);
-  }
-  static std::atomic<int> occ{0};
-  if (occ.load() == 0) {
-    int o = 0;
-    B200SP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, (NW + 1) * 32, smem));
-    occ.store(o > 0 ? o : 1);
-  }
+  static KernelSetup ks;
+  int occ_dev = 1;
+  if (int rc = kernel_setup(ks, kern, (NW + 1) * 32, smem, &occ_dev)) return rc;
   int per_sm = p->ctas_per_sm;
-  if (per_sm <= 0) per_sm = occ.load();
+  if (per_sm <= 0) per_sm = occ_dev;
   const int lo = p->range_hi < 0 ? 0 : p->range_lo;
   const int hi = p->range_hi < 0 ? p->n_tiles : p->range_hi;
   int grid = std::min(hi - lo, sm_count() * per_sm);
@@ -1245,6 +1239,25 @@ int b200sp_spmv_plan_set_option(b200sp_spmv_plan* p, int option, int value) {
   return B200SP_ERR_INVALID_ARGUMENT;
 }
 
+int b200sp_spmv_plan_invalidate(b200sp_spmv_plan* p, void* stream) {
+  B200SP_REQUIRE(p != nullptr, "spmv_plan_invalidate: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  // everything derived from the STRUCTURE of the matrix the plan last saw: tiles, long rows, rank-2 tiles / segments / items,
+  // chunk table, cached transpose, host-vector piece bounds, self-tuning state.  Buffers that only depend on sizes stay.
+  plan_release_analysis(p, st);
+  plan_release_mm(p, st);
+  if (p->chunk_row) cudaFreeAsync(p->chunk_row, st);
+  p->chunk_row = nullptr;
+  p->chunk_key = nullptr;
+  p->n_chunks = 0;
+  p->t_key_rp = p->t_key_ci = nullptr;
+  p->pipe.key = nullptr;
+  p->at_calls = 0;
+  p->at_choice = -1;
+  if (p->tplan) return b200sp_spmv_plan_invalidate(p->tplan, stream);
+  return B200SP_OK;
+}
+
 int b200sp_spmv_plan_tune(b200sp_spmv_plan* p, int cfg, int lanes_per_row, int ctas_per_sm) {
   B200SP_REQUIRE(p != nullptr, "spmv_plan_tune: null plan");
   B200SP_REQUIRE(cfg >= -1 && cfg < kNumCfgs, "spmv_plan_tune: cfg %d out of range", cfg);
@@ -1440,7 +1453,7 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
   const int cfg = p->cfg >= 0 ? p->cfg : 8;
   int rc = plan_analyse<double>(p, st, cfg, m, n, nnz, row_ptr);
   if (rc) return rc;
-  if (q.key != row_ptr || q.key_cfg != cfg) {
+  if (q.key != row_ptr || q.key_cfg != cfg || q.key_m != m || q.key_nnz != nnz || q.key_tiles != (const void*)p->tiles) {
     q.nc = 4;  // pieces of y that go down while the next piece is computed (B200SP_HOSTVEC_PIECES: 1..8, tuning)
     if (const char* e = getenv("B200SP_HOSTVEC_PIECES")) {
       const int v = atoi(e);
@@ -1457,6 +1470,9 @@ int b200sp_spmv_hostvec_f64_i32(b200sp_spmv_plan* p, void* stream, char mode, in
     q.row_b[0] = 0;
     q.key = row_ptr;
     q.key_cfg = cfg;
+    q.key_m = m;
+    q.key_nnz = nnz;
+    q.key_tiles = (const void*)p->tiles;
   }
   const int b = (int)(q.call & 1ull);
   if (q.defer && q.call >= 2) {

@@ -161,6 +161,14 @@ class SPMVHandle:
     def tune(self, cfg=-1, lanes_per_row=-1, ctas_per_sm=-1):
         check(_lib.sparse().b200sp_spmv_plan_tune(self._plan, cfg, lanes_per_row, ctas_per_sm))
 
+    def invalidate(self):
+        """Drop the cached analysis of the matrix this handle last saw (b200sp_spmv_plan_invalidate).  The cache is keyed on
+        (row_map pointer, shape, nnz); call this when a DIFFERENT matrix may sit at the same address with the same shape
+        (an in-place edit of row_map, or a caching allocator reusing the block) -- the reference's contract is one matrix
+        per handle (sparse/src/KokkosSparse_spmv_handle.hpp:276-277)."""
+        if self._plan:
+            check(_lib.sparse().b200sp_spmv_plan_invalidate(self._plan, _stream()))
+
     def last_kernel(self):
         if self._bsr_plan:
             return _lib.sparse().b200sp_bsr_last_kernel(self._bsr_plan).decode()

@@ -173,6 +173,7 @@ struct SPMVHandleImpl {
   TPL_SpMV_Data<ExecutionSpace>* tpl_rank2 = nullptr;
 };
 
+#ifndef B200_SHIM_REFERENCE_SPEC  // tests/shim_ref: the reference's own declarations of these are included in place instead
 template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
 struct spmv_tpl_spec_avail {
   enum : bool { value = false };
@@ -187,6 +188,8 @@ struct SPMV;  // only the TPL specialisations exist in the mock
 template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector, bool integerScalar = false,
           bool tpl_spec_avail = spmv_mv_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value>
 struct SPMV_MV;
+
+#endif  // B200_SHIM_REFERENCE_SPEC
 
 // sparse/tpls/KokkosSparse_spmv_bsrmatrix_tpl_spec_avail.hpp:27-30,121-124 and
 // sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:89-112 (eti always true in the mock, as in a library build)
@@ -444,6 +447,7 @@ struct KokkosKernelsHandle {
 
 namespace KokkosSparse {
 namespace Impl {
+#ifndef B200_SHIM_REFERENCE_SPEC
 template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r>
 struct spgemm_symbolic_tpl_spec_avail {
   enum : bool { value = false };
@@ -452,6 +456,7 @@ template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class
 struct spgemm_numeric_tpl_spec_avail {
   enum : bool { value = false };
 };
+#endif  // B200_SHIM_REFERENCE_SPEC
 // sparse/tpls/KokkosSparse_gmres_tpl_spec_avail.hpp:26-29, sparse/impl/KokkosSparse_gmres_spec.hpp:69-82
 template <class KH, class AT, class AO, class AD, class AM, class AS, class BType, class XType>
 struct gmres_tpl_spec_avail {
@@ -517,11 +522,13 @@ struct spgemm_jacobi_tpl_spec_avail {
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v,
           bool tpl = spgemm_jacobi_tpl_spec_avail<KH, a_r, a_e, a_v, b_r, b_e, b_v, c_r, c_e, c_v, dinv_v>::value, bool eti = true>
 struct SPGEMM_JACOBI;
+#ifndef B200_SHIM_REFERENCE_SPEC
 template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r, bool tpl, bool eti>
 struct SPGEMM_SYMBOLIC;
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v,
           bool tpl, bool eti>
 struct SPGEMM_NUMERIC;
+#endif  // B200_SHIM_REFERENCE_SPEC
 }  // namespace Impl
 }  // namespace KokkosSparse
 

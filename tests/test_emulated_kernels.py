@@ -550,3 +550,23 @@ def test_gmres_bsr(emu, oracle, variant):
     st_o, it_o, _, flag_o = oracle.gmres(A, b, xo, m=m, tol=tol, prec=A if prec is not None else None)
     assert rc == 0 and flag == 0 == flag_o and abs(it - it_o) <= 1, (rc, it, it_o, flag)
     assert true_rel_res(oracle, A, b, x) < tol and res < tol
+
+
+def test_plan_invalidate_drops_stale_analysis(emu, oracle):
+    """A different matrix at the SAME row_map address with the same shape and nnz finds the cached tiles of the first one
+    (the cache key is pointer + shape); b200sp_spmv_plan_invalidate is the documented way out."""
+    rng = np.random.default_rng(5)
+    m = n = 900
+    lens1 = rng.integers(1, 12, m)
+    lens2 = lens1[::-1].copy()  # same nnz, other row boundaries
+    rp = np.concatenate([[0], np.cumsum(lens1)]).astype(np.int32)
+    nnz = int(rp[-1])
+    ci = rng.integers(0, n, nnz).astype(np.int32)
+    v = rng.uniform(-1, 1, nnz)
+    x = rng.random(n)
+    plan = E.SpmvPlan()
+    check_spmv(oracle, plan, "N", rp, ci, v, n, x, np.zeros(m), 1.0, 0.0)
+    rp[:] = np.concatenate([[0], np.cumsum(lens2)]).astype(np.int32)  # edited in place: same pointer, m, nnz
+    E.ok(emu.b200sp_spmv_plan_invalidate(plan.h, None))
+    check_spmv(oracle, plan, "N", rp, ci, v, n, x, np.zeros(m), 1.0, 0.0)
+    plan.close()
