@@ -173,10 +173,12 @@ def _cpu_spmv(orc):
 
 
 def _best_threads(run, rps, cis, vas, ncols, x, y, threads):
-    """The thread count the CPU loop is fastest with on this box among all / half / a quarter of the hardware threads (SMT siblings
-    and a second socket do not always help a streaming loop): the baseline is the reference at its best, not at a default."""
+    """The thread count the CPU loop is fastest with on this box: all hardware threads, then half, a quarter, ... for as long
+    as halving helps (SMT siblings, a second socket or a container CPU quota below the visible thread count make a streaming
+    loop slower with more threads): the baseline is the reference at its best, not at a default."""
     best, best_t, tried = threads, None, []
-    for t in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
+    t = threads
+    while t >= 1:
         try:
             run(rps, cis, vas, ncols, x, y, t)
             ts = []
@@ -185,10 +187,15 @@ def _best_threads(run, rps, cis, vas, ncols, x, y, threads):
                 run(rps, cis, vas, ncols, x, y, t)
                 ts.append(time.perf_counter() - t0)
         except Exception:
-            continue
+            break
         tried.append((t, min(ts)))
         if best_t is None or min(ts) < best_t:
             best, best_t = t, min(ts)
+        elif min(ts) > 1.25 * best_t and t < threads:
+            break  # clearly past the optimum
+        if t == 1:
+            break
+        t = max(1, t // 2)
     return best, ", ".join(f"{t} threads {ms * 1e3:.1f} ms" for t, ms in tried)
 
 

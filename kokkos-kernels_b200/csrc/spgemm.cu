@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <limits.h>
 #include <stdlib.h>
+#include <time.h>
 #include <new>
 
 namespace b200sp {
@@ -1144,6 +1145,32 @@ static int launch_esc_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const
   return B200SP_OK;
 }
 
+// B200SP_SPGEMM_TRACE=1: host wall clock between the phases of spgemm_symbolic (each mark synchronises the stream): a
+// diagnostic for the synchronous phase, never on by default
+struct SymTrace {
+  bool on;
+  cudaStream_t st;
+  double t0;
+  static double now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  explicit SymTrace(cudaStream_t s) : on(getenv("B200SP_SPGEMM_TRACE") != nullptr), st(s), t0(0) {
+    if (on) {
+      cudaStreamSynchronize(st);
+      t0 = now();
+    }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const double t = now();
+    fprintf(stderr, "[spgemm_symbolic] %-28s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
+};
+
 // every row grouped by nnz(C_i) (the hash variants B200SP_SPGEMM_NUMERIC=1..6 and spgemm_jacobi); built once, synchronises
 static int ensure_all_bins(b200sp_spgemm_plan* p, cudaStream_t st, const int* rpC) {
   if (p->all_built) return B200SP_OK;
@@ -1203,6 +1230,10 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
       case 1: rc = launch_esc_num<S, 256, 4, 11, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       case 2: rc = launch_esc_num<S, 128, 8, 10, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       case 3: rc = launch_esc_num<S, 256, 4, 10, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 4: rc = launch_esc_num<S, 256, 4, 9, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 5: rc = launch_esc_num<S, 512, 2, 10, 4>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 6: rc = launch_esc_num<S, 512, 2, 9, 4>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 7: rc = launch_esc_num<S, 256, 4, 10, 7>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       default: rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
     }
     if (rc) return rc;
@@ -1431,6 +1462,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   }
   B200SP_REQUIRE(ciA && ciB, "spgemm_symbolic: null column index array");
 
+  SymTrace trace(st);
   DevTmp tmp(st);
   int *bmin, *bmax, *row_nnz, *sym_rows, *d_counts, *block_max, *d_max;
   long long *block_sum, *d_total;
@@ -1464,6 +1496,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
                                                                                 p->cmin, p->cmax);
   B200SP_LAUNCH_CHECK();
 
+  trace.mark("allocations + row analysis");
   // ---- count distinct columns per row
   // default (3): rows binned by max(products, 2 nnz(A_i)); up to 8192 -> esc_sym_kernel (spgemm_esc.cuh: products held in
   // registers, hash set of 2x the bin's capacity); above -> the group-walk hash kernel / global bitmap.
@@ -1489,6 +1522,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
     rc = bin_rows(st, m, p->esc_key, espec, d_counts, p->esc_rows, p->esc_off);
     if (rc) return rc;
   }
+  trace.mark("bin keys + grouping");
   if (sym_variant >= 3) {
     const int* er = p->esc_rows;
     const int* eo = p->esc_off;
@@ -1498,7 +1532,8 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
     switch (esc_cfg) {
       case 1: rc = launch_esc_sym<256, 4, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
       case 2: rc = launch_esc_sym<128, 8, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      case 3: rc = launch_esc_sym<256, 4, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 3: case 4: case 7: rc = launch_esc_sym<256, 4, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 5: case 6: rc = launch_esc_sym<512, 2, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
       default: rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
     }
     if (rc) return rc;
@@ -1554,6 +1589,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
     }
   }
 
+  trace.mark("distinct-column kernels");
   // ---- row_ptr_C = exclusive scan(row_nnz); total and longest row
   scan_local_kernel<<<nblocks, 256, 0, st>>>(m, row_nnz, rpC, block_sum, block_max);
   B200SP_LAUNCH_CHECK();
@@ -1572,6 +1608,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   }
   p->c_nnz = total;
   p->c_max = mx;
+  trace.mark("scan -> row_ptr_C");
 
   // ---- numeric: the ESC grouping above serves rows of <= 8192 products; the rows beyond it are grouped by nnz(C_i) for
   // the hash kernels here (kept on the plan so that numeric stays asynchronous)
@@ -1601,6 +1638,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   p->fb_log2 = lg;
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->fb_keys, sizeof(int) * (size_t)kFbCtas * ((size_t)1 << lg), st));
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  trace.mark("hash-bin grouping + scratch");
   p->symbolic_done = true;
   if (c_nnz) *c_nnz = total;
   if (c_max_row_nnz) *c_max_row_nnz = mx;

@@ -11,7 +11,8 @@
 //                = ((c - cmin) * floor(NB*2^32 / span)) >> 32        otherwise
 //   histogram (shared atomicAdd; the returned count is the product's arrival rank in its bucket) -> exclusive
 //   scan -> scatter of the keys to bucket order.  Buckets hold 0.5 products on average, so what is left is local:
-//  symbolic  esc_sym_kernel : a product is a duplicate iff its bucket holds an equal column at a smaller position;
+//  symbolic  esc_sym_kernel : a bitmap pre-filter settles the rows with few duplicates without sorting (see there);
+//            otherwise a product is a duplicate iff its bucket holds an equal column at a smaller position;
 //            nnz(C_i) = f - duplicates.
 //  numeric   esc_num_kernel : every product ranks itself among the members of its bucket by (column, ordinal) and
 //            stores (column, value) at its sorted position.  Rows without duplicate columns (f == nnz(C_i), known
@@ -331,13 +332,24 @@ __device__ __forceinline__ void esc_bucket_sort(int f, int cmin, long long span,
 // ---------------------------------------------------------------------------------------------------
 // SYMBOLIC
 // ---------------------------------------------------------------------------------------------------
+// Most product rows have few or no duplicate columns (config 4: 0.26 per 1024 products).  Before sorting anything the
+// columns are therefore hashed into a BITMAP of 128 bits per product slot (atomicOr): a product whose bit was clear is
+// certainly a new column; the few whose bit was already set ("suspects": true duplicates + about f/256 false positives)
+// are resolved exactly -- a suspect is a duplicate iff a non-suspect product holds the same column, or an equal suspect
+// precedes it in the suspect list.  Only rows with more than SUSCAP suspects (duplicate-heavy products such as stencils)
+// go through the bucket sort.
 template <int T, int I, int LOG2NB>
 struct EscSymLayout {
   static constexpr int CAP = T * I;
   static constexpr int NB = 1 << LOG2NB;
   static constexpr int NA = CAP / 2;
-  // off[NB + 4] | wsum[36] | union { bs[NA], pre[NA + 4] ; skey[CAP] }  (the staging is dead when the keys are scattered)
-  static constexpr size_t BYTES = sizeof(int) * (size_t)(NB + 4 + 36 + CAP + 8);
+  static constexpr int LOG2BITS = esc_log2(CAP) + 7;
+  static constexpr int BMW = (1 << LOG2BITS) / 32;       // bitmap words
+  static constexpr int SORTW = NB + 4 + CAP + 8;         // off[NB + 4] | skey[CAP] of the fallback, aliased with the bitmap
+  static constexpr int REGW = BMW > SORTW ? BMW : SORTW;
+  static constexpr int SUSCAP = 64;
+  // region[REGW] | bs[NA] | pre[NA + 4] | wsum[36] | sus_n[4] | sus_col[SUSCAP] | sus_dup[SUSCAP]
+  static constexpr size_t BYTES = sizeof(int) * (size_t)(REGW + NA + NA + 4 + 36 + 4 + 2 * SUSCAP);
   static_assert(BYTES <= 227 * 1024, "esc_sym_kernel: configuration exceeds the shared memory of an SM");
 };
 
@@ -349,12 +361,18 @@ __global__ void __launch_bounds__(T, MINB)
   using L = EscSymLayout<T, I, LOG2NB>;
   constexpr int NB = L::NB;
   constexpr int NOKEY = INT_MAX;
+  constexpr int SUSCAP = L::SUSCAP;
   extern __shared__ __align__(16) int esc_sm[];
-  int* off = esc_sm;
-  int* wsum = off + NB + 4;
-  int* skey = wsum + 36;
-  int* bs = skey;
+  int* region = esc_sm;
+  unsigned* bm = reinterpret_cast<unsigned*>(region);
+  int* off = region;               // fallback view
+  int* skey = region + NB + 4;
+  int* bs = region + L::REGW;
   int* pre = bs + L::NA;
+  int* wsum = pre + L::NA + 4;
+  int* sus_n = wsum + 36;
+  int* sus_col = sus_n + 4;
+  int* sus_dup = sus_col + SUSCAP;
   const int tid = threadIdx.x;
   const int i = rows[blockIdx.x];
   const int f = flops[i];
@@ -363,16 +381,72 @@ __global__ void __launch_bounds__(T, MINB)
     return;
   }
   const int a0 = rpA[i], nA = rpA[i + 1] - a0;
-  const int cmin = cmin_arr[i];
-  const long long span = (long long)cmax_arr[i] - cmin + 1;
   {
-    int4* o4 = reinterpret_cast<int4*>(off);
-    for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
+    int4* b4 = reinterpret_cast<int4*>(region);
+    for (int s = tid; s < L::BMW / 4; s += T) b4[s] = make_int4(0, 0, 0, 0);
+    if (tid == 0) *sus_n = 0;
+    if (tid < SUSCAP) sus_dup[tid] = 0;
+    if (T < SUSCAP)
+      for (int s = tid + T; s < SUSCAP; s += T) sus_dup[s] = 0;
   }
   const int L0 = esc_stage_row<T, float, false>(a0, nA, f, ciA, (const float*)nullptr, rpB, bs, pre, (float*)nullptr, wsum);
   int col[I];
   float dummy[I];
   esc_expand<T, I, float, false>(f, nA, L0, bs, pre, (const float*)nullptr, ciB, (const float*)nullptr, NOKEY, col, dummy);
+  // ---- bitmap pass
+  unsigned smask = 0;  // bit k: item k is a suspect
+#pragma unroll
+  for (int k = 0; k < I; ++k)
+    if (col[k] != NOKEY) {
+      const unsigned h = ((unsigned)col[k] * 0x9E3779B1u) >> (32 - L::LOG2BITS);
+      const unsigned bit = 1u << (h & 31u);
+      const unsigned old = atomicOr(&bm[h >> 5], bit);
+      if (old & bit) {
+        smask |= 1u << k;
+        const int idx = atomicAdd(sus_n, 1);
+        if (idx < SUSCAP) sus_col[idx] = col[k];
+      }
+    }
+  __syncthreads();
+  const int ns = *sus_n;
+  if (ns == 0) {
+    if (tid == 0) row_nnz[i] = f;
+    return;
+  }
+  if (ns <= SUSCAP) {
+    // a suspect equal to a product that was counted as new is a duplicate
+    for (int s = 0; s < ns; ++s) {
+      const int c = sus_col[s];
+      bool hit = false;
+#pragma unroll
+      for (int k = 0; k < I; ++k) hit = hit || (col[k] == c && !((smask >> k) & 1u));
+      if (hit) sus_dup[s] = 1;  // benign race: every writer stores 1
+    }
+    __syncthreads();
+    // ... and so is one that an equal suspect precedes in the list (one of each group of equal suspects counts)
+    if (tid < 32) {
+      int dups = 0;
+      for (int s = tid; s < ns; s += 32) {
+        bool dup = sus_dup[s] != 0;
+        const int c = sus_col[s];
+        for (int s2 = 0; s2 < s && !dup; ++s2) dup = (sus_col[s2] == c);
+        dups += dup ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, o);
+      if (tid == 0) row_nnz[i] = f - dups;
+    }
+    return;
+  }
+  // ---- duplicate-heavy row: counting sort over the monotone buckets, duplicates found inside the buckets
+  __syncthreads();  // every thread has read *sus_n and the bitmap is dead
+  {
+    int4* o4 = reinterpret_cast<int4*>(off);
+    for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const int cmin = cmin_arr[i];
+  const long long span = (long long)cmax_arr[i] - cmin + 1;
   int pos[I], lc[I];
   esc_bucket_sort<T, I, LOG2NB>(f, cmin, span, NOKEY, col, off, skey, wsum, pos, lc);
   // a product is a duplicate iff an equal column sits at a smaller position of its bucket

@@ -322,6 +322,39 @@ DEF_SPMV_MV_TRANS(okk_spmv_mv_transpose_f64, double, double, double)
 DEF_SPMV_MV_TRANS(okk_spmv_mv_transpose_f32, float, float, float)
 
 /* ------------------------------------------------------------------------
+ * O2b: spmv_raw_openmp_no_transpose, sparse/impl/KokkosSparse_spmv_impl_omp.hpp:20-78 (taken by spmv_beta_no_transpose only
+ * for double on OpenMP when the graph carries row_block_offsets with omp_get_max_threads()+1 entries and x, y are 64-byte
+ * aligned, spmv_impl.hpp:307-320).  Thread t owns rows [block_offsets[t], block_offsets[t+1]); per row
+ *   sum = 0;  sum += (alpha * a_ij) * x_j  in storage order;  y_i = (beta == 0) ? sum : beta * y_i + sum
+ * -- alpha is folded into every coefficient (unlike the functor O2, which scales the finished sum), so the two paths
+ * agree bit for bit only for alpha == 1 (tests/test_oracle_spmv.py pins that, and the tolerance law otherwise).
+ * ---------------------------------------------------------------------- */
+OKK_API void okk_spmv_raw_openmp_f64(int nblocks, const int* block_offsets, const int* row_map, const int* col_idx,
+                                     const double* vals, const double* x, double* y, double s_a, double s_b) {
+  const double zero = 0;
+#pragma omp parallel for schedule(static, 1) num_threads(nblocks > 0 ? nblocks : 1)
+  for (int myID = 0; myID < nblocks; ++myID) {
+    const int myStart = block_offsets[myID];
+    const int myEnd = block_offsets[myID + 1];
+    for (int row = myStart; row < myEnd; ++row) {
+      const int rowStart = row_map[row];
+      const int rowEnd = row_map[row + 1];
+      double sum = 0.0;
+      for (int i = rowStart; i < rowEnd; ++i) {
+        const int x_entry = col_idx[i];
+        const double alpha_MC = s_a * vals[i];
+        sum += alpha_MC * x[x_entry];
+      }
+      if (zero == s_b) {
+        y[row] = sum;
+      } else {
+        y[row] = s_b * y[row] + sum;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------
  * Merge matrix (merge-path SpMV partitioning).
  * sparse/impl/KokkosSparse_merge_matrix.hpp:80-227.
  * M[i,j] = 1 iff a[i] > b[j]; diagonal d holds `size()` entries counted from

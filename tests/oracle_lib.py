@@ -140,6 +140,12 @@ class Oracle:
         getattr(self.lib, "okk_spmv_functor_" + self._sfx(v))(m, ncol, _p(rp), _p(ci), _p(v), _p(x), _p(y), alpha, beta, threads)
         return y
 
+    def spmv_raw_openmp(self, block_offsets, rp, ci, v, x, y, alpha, beta):
+        """O2b: spmv_raw_openmp_no_transpose (spmv_impl_omp.hpp:20-78), one OpenMP thread per row block."""
+        bo = np.ascontiguousarray(block_offsets, dtype=np.int32)
+        self.lib.okk_spmv_raw_openmp_f64(len(bo) - 1, _p(bo), _p(rp), _p(ci), _p(v), _p(x), _p(y), C.c_double(alpha), C.c_double(beta))
+        return y
+
     def spmv_test(self, mode, rp, ci, v, x, y, alpha, beta):
         """O3: Test::sequential_spmv (Test_Sparse_spmv.hpp:106-166)."""
         m = len(rp) - 1

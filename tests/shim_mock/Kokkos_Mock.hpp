@@ -96,6 +96,9 @@ template <class Scalar, class Ordinal, class Dev, class MT, class Offset>
 class CrsMatrix {
  public:
   using UM = Kokkos::MemoryTraits<Kokkos::Unmanaged>;
+  // sparse/src/KokkosSparse_CrsMatrix.hpp:338-352 (the reference's spmv_mv_tpl_spec_avail / SPMV_MV read it, spec.hpp:117)
+  using value_type           = Scalar;
+  using non_const_value_type = typename std::remove_const<Scalar>::type;
   struct Graph {
     Kokkos::View<Offset*, Kokkos::LayoutLeft, Dev, UM> row_map;
     Kokkos::View<Ordinal*, Kokkos::LayoutLeft, Dev, UM> entries;

@@ -35,7 +35,11 @@ struct Rank1 {
   using Dev     = Kokkos::Device<Kokkos::Cuda, Mem>;
   using Handle  = SPMVHandleImpl<Kokkos::Cuda, Mem, S, Off, Ord>;
   using AMatrix = CrsMatrix<const S, const Ord, Dev, Kokkos::MemoryTraits<Kokkos::Unmanaged>, const Off>;
+#ifdef B200_NEGATIVE_CONTROL  // a type the front end never passes: the checks below must reject it (the test expects this TU to fail)
+  using XVector = Kokkos::View<const S*, Layout, Dev, Kokkos::MemoryTraits<Kokkos::Unmanaged>>;
+#else
   using XVector = Kokkos::View<const S*, Layout, Dev, Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>>;
+#endif
   using YVector = Kokkos::View<S*, Layout, Dev, Kokkos::MemoryTraits<Kokkos::Unmanaged>>;
   static_assert(spmv_tpl_spec_avail<Kokkos::Cuda, Handle, AMatrix, XVector, YVector>::value, "rank-1 slot not marked available");
   static_assert(SPMV<Kokkos::Cuda, Handle, AMatrix, XVector, YVector>::is_b200sparse, "rank-1 slot: the generic SPMV is selected");

@@ -66,3 +66,36 @@ def test_spmm_powerlaw_rows(cuda, oracle):
         sp.spmv(sp.SPMVHandle(), "N", 1.0, A, _mk(cuda, X, rowmajor), 0.0, Y)
         err = np.max(np.abs(Y.cpu().numpy() - exp))
         assert err <= 10 * np.finfo(np.float32).eps * maxrow
+
+
+def test_config3_full_size(cuda, oracle):
+    """BASELINE.json configs[2] at full size: R-MAT scale 23 (8,388,608 rows, 1.3e8 entries, longest row 152,801), fp32,
+    16-column multivector, both layouts -- EVERY row against the oracle's CPU multivector loop (O4, spmv_impl.hpp:745-926;
+    OpenMP over rows changes no bit of a row).  Criterion: component-wise error scaled by
+    |alpha| sum_j |a_ij||x_jc| + |beta||y0_ic| at most 1e-4 (fp32); alpha = 1.5, beta = 0.5 and the beta == 0 / NaN case."""
+    import os
+
+    from kokkos_kernels_b200 import matgen, sparse as sp
+
+    rp, ci = matgen.rmat(23, 16)
+    n, k = len(rp) - 1, 16
+    assert n == 1 << 23
+    v = matgen.fill(len(ci), 0.0, 1.0, 23, dtype=np.float32)
+    X = matgen.fill(n * k, -1.0, 1.0, 5, dtype=np.float32).reshape(n, k)
+    Y0 = matgen.fill(n * k, -1.0, 1.0, 6, dtype=np.float32).reshape(n, k)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    A = sp.CrsMatrix(torch.from_numpy(rp).to(cuda), torch.from_numpy(ci).to(cuda), torch.from_numpy(v).to(cuda), n)
+    h = sp.SPMVHandle()
+    scale_a = oracle.spmv_mv(rp, ci, np.abs(v), n, np.abs(X), np.zeros((n, k), dtype=np.float32), 1.0, 0.0, threads=threads)
+    for alpha, beta, rowmajor in ((1.0, 0.0, True), (1.5, 0.5, True), (1.5, 0.5, False)):
+        y_in = Y0.copy()
+        if beta == 0.0:
+            y_in[::23] = np.nan  # beta == 0 must overwrite, not scale (Test_Sparse_spmv.hpp:394-408)
+        Yd = _mk(cuda, y_in, rowmajor)
+        sp.spmv(h, "N", alpha, A, _mk(cuda, X, rowmajor), beta, Yd)
+        got = Yd.cpu().numpy()
+        exp = oracle.spmv_mv(rp, ci, v, n, X, np.zeros((n, k), dtype=np.float32) if beta == 0.0 else Y0.copy(), alpha, beta, threads=threads)
+        assert not np.isnan(got).any()
+        scale = abs(alpha) * scale_a.astype(np.float64) + abs(beta) * np.abs(Y0).astype(np.float64)
+        err = np.abs(got.astype(np.float64) - exp.astype(np.float64)) / np.maximum(scale, 1e-30)
+        assert float(err.max()) <= 1e-4, (alpha, beta, rowmajor, float(err.max()), int(err.argmax()) // k)

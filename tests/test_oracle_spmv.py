@@ -226,3 +226,33 @@ def test_o4_equals_the_reference_multivector_code(oracle, order, k):
                     a = oracle.spmv_mv_transpose(rp, ci, v, cols, X, Yin.copy(order=order), alpha, beta)
                 b = oracle.ref_spmv_mv(mode, rp, ci, v, cols, X, Yin.copy(order=order), alpha, beta)
                 assert np.array_equal(a, b), (mode, alpha, beta)
+
+
+def test_raw_openmp_path_a8(oracle):
+    """a8 of SURVEY.md section 8: spmv_raw_openmp_no_transpose (spmv_impl_omp.hpp:20-78).  Folding alpha into every coefficient
+    is exact for alpha == 1, so there the path equals the functor (O2, itself pinned on the reference's own code) bit for bit,
+    whatever the row blocks; for other alpha it obeys the reference's tolerance law; beta == 0 overwrites NaN."""
+    from helpers import kk_matrix, spmv_tolerance
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kokkos-kernels_b200"))
+    import partition
+
+    rp, ci, v = kk_matrix(5000, 4000, 60000, 12, 300)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 4000)
+    y0 = rng.uniform(-1, 1, 5000)
+    for nblocks in (1, 3, 8):
+        bo = partition.balanced_row_blocks(rp, nblocks)
+        for alpha, beta in ((1.0, 0.0), (1.0, 0.5), (2.5, -1.0), (-0.75, 0.0)):
+            y = y0.copy()
+            if beta == 0.0:
+                y[::19] = np.nan
+            oracle.spmv_raw_openmp(bo, rp, ci, v, x, y, alpha, beta)
+            ref = y0.copy()
+            oracle.spmv_functor(rp, ci, v, 4000, x, ref, alpha, beta)
+            assert not np.isnan(y).any()
+            if alpha == 1.0:
+                assert np.array_equal(y, ref)
+            else:
+                tol = spmv_tolerance(np.finfo(np.float64).eps, alpha, beta, int(np.diff(rp).max()))
+                assert np.max(np.abs(y - ref)) <= tol
