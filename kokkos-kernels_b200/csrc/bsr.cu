@@ -749,6 +749,9 @@ int bsr_spmv_impl(b200sp_bsr_plan* p, cudaStream_t st, char mode, int mb, int nb
       default: break;
     }
   }
+  // The run-time block size ("walk") tile kernel loses to the row-vector kernel from bs = 5 on (B200, lap27 pattern, 6.9 M blocks:
+  // bs = 5: 1.13 vs 0.84 ms, bs = 8: 5.91 vs 1.90 ms, profiles/r02c6_bsr_big_*.log): it serves bs <= 4 and explicit requests only.
+  if (bs > 4 && !(force && !strcmp(force, "walk"))) return launch_vector<S>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
   if (bs <= 4) return launch_tile<S, 16, 4, 2048>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
   return launch_tile<S, 16, 3, 4096>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
 }

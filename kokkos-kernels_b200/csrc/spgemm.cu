@@ -1119,14 +1119,29 @@ static int launch_num2(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const in
   return B200SP_OK;
 }
 
+// The ESC kernels are persistent: one wave of CTAs (SMs x resident CTAs per SM), each working through every grid-th row of
+// its bin with the row pipeline of spgemm_esc.cuh.  B200SP_ESC_PERSIST=0 launches one CTA per row instead (the pipeline
+// then degenerates to the plain dependent chain) -- an A/B switch for measurements.
+static int esc_grid(int nrows, int occ) {
+  static const bool persist = [] {
+    const char* e = getenv("B200SP_ESC_PERSIST");
+    return !(e && e[0] == '0');
+  }();
+  if (!persist) return nrows;
+  return (int)std::min<int64_t>((int64_t)nrows, (int64_t)sm_count() * std::max(occ, 1));
+}
+
 template <int T, int I, int LOG2NB, int MINB>
 static int launch_esc_sym(cudaStream_t st, int nrows, const int* rows, const int* rpA, const int* ciA, const int* rpB,
                           const int* ciB, const int* flops, const int* cmin, const int* cmax, int* row_nnz) {
   if (nrows <= 0) return B200SP_OK;
   using L = EscSymLayout<T, I, LOG2NB>;
   auto kern = esc_sym_kernel<T, I, LOG2NB, MINB>;
-  if (L::BYTES > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-  kern<<<nrows, T, L::BYTES, st>>>(nrows, rows, rpA, ciA, rpB, ciB, flops, cmin, cmax, row_nnz);
+  static KernelSetup ks;  // per instantiation and device: shared-memory opt-in + occupancy, queried once
+  int occ = 1;
+  if (int rc = kernel_setup(ks, kern, T, L::BYTES, &occ)) return rc;
+  const int grid = esc_grid(nrows, occ);
+  kern<<<grid, T, L::BYTES, st>>>(nrows, rows, rpA, ciA, rpB, ciB, flops, cmin, cmax, row_nnz);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -1138,8 +1153,11 @@ static int launch_esc_num(cudaStream_t st, b200sp_spgemm_plan* p, int bin, const
   if (nrows <= 0) return B200SP_OK;
   using L = EscNumLayout<S, T, I, LOG2NB>;
   auto kern = esc_num_kernel<S, T, I, LOG2NB, MINB>;
-  if (L::BYTES > 48 * 1024) B200SP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-  kern<<<nrows, T, L::BYTES, st>>>(nrows, p->esc_rows + p->esc_off[bin], rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, p->cmin,
+  static KernelSetup ks;
+  int occ = 1;
+  if (int rc = kernel_setup(ks, kern, T, L::BYTES, &occ)) return rc;
+  const int grid = esc_grid(nrows, occ);
+  kern<<<grid, T, L::BYTES, st>>>(nrows, p->esc_rows + p->esc_off[bin], rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC, p->cmin,
                                    p->cmax, p->flops);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
@@ -1221,20 +1239,19 @@ static int numeric_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, in
   if (variant >= 7 && p->esc_rows) {
     // default: register-resident expand / sort / compress kernels (spgemm_esc.cuh) for rows of <= 8192 products,
     // the two-walk hash kernels for the rest
-    // <S, threads, products per thread, log2(buckets), CTAs per SM for the register budget>.  B200SP_ESC_CFG (tuning): 1 = 256
-    // threads x 4 products for the 1024-product bin (more resident warps), 2 = 1024 buckets, 3 = both
+    // <S, threads, products per thread, log2(buckets), CTAs per SM for the register budget>.  B200SP_ESC_CFG selects the
+    // alternatives of the 1024-product bin for A/B runs
     int esc_cfg = 0;
     if (const char* e = getenv("B200SP_ESC_CFG")) esc_cfg = atoi(e);
     if ((rc = launch_esc_num<S, 32, 8, 9, 32>(st, p, 0, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
-    switch (esc_cfg) {
+    switch (esc_cfg) {  // bin 1; default measured best (round 2: 18.7 ms on config 4 against 22.7 for <128, 8, 11>)
       case 1: rc = launch_esc_num<S, 256, 4, 11, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       case 2: rc = launch_esc_num<S, 128, 8, 10, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
-      case 3: rc = launch_esc_num<S, 256, 4, 10, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
-      case 4: rc = launch_esc_num<S, 256, 4, 9, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 4: rc = launch_esc_num<S, 256, 4, 10, 5>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       case 5: rc = launch_esc_num<S, 512, 2, 10, 4>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
-      case 6: rc = launch_esc_num<S, 512, 2, 9, 4>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
       case 7: rc = launch_esc_num<S, 256, 4, 10, 7>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
-      default: rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      case 8: rc = launch_esc_num<S, 128, 8, 11, 8>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
+      default: rc = launch_esc_num<S, 256, 4, 10, 6>(st, p, 1, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC); break;
     }
     if (rc) return rc;
     if ((rc = launch_esc_num<S, 512, 8, 12, 2>(st, p, 2, rpA, ciA, vA, rpB, ciB, vB, rpC, ciC, vC))) return rc;
@@ -1526,15 +1543,17 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
   if (sym_variant >= 3) {
     const int* er = p->esc_rows;
     const int* eo = p->esc_off;
-    int esc_cfg = 0;
-    if (const char* e = getenv("B200SP_ESC_CFG")) esc_cfg = atoi(e);
+    // bin 1 (<= 1024 products, config 4's bin): 256 threads x 4 products, 1024 buckets measured best on a B200
+    // (profiles/README.md, round 2); B200SP_ESC_SYM_CFG selects the alternatives for A/B runs
+    int sym_cfg = 0;
+    if (const char* e = getenv("B200SP_ESC_SYM_CFG")) sym_cfg = atoi(e);
     if ((rc = launch_esc_sym<32, 8, 9, 1>(st, eo[1] - eo[0], er + eo[0], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
-    switch (esc_cfg) {
-      case 1: rc = launch_esc_sym<256, 4, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      case 2: rc = launch_esc_sym<128, 8, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      case 3: case 4: case 7: rc = launch_esc_sym<256, 4, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      case 5: case 6: rc = launch_esc_sym<512, 2, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      default: rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+    switch (sym_cfg) {
+      case 1: rc = launch_esc_sym<256, 4, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 2: rc = launch_esc_sym<256, 4, 10, 6>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 3: rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      case 4: rc = launch_esc_sym<512, 2, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      default: rc = launch_esc_sym<256, 4, 10, 5>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
     }
     if (rc) return rc;
     if ((rc = launch_esc_sym<512, 8, 12, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;

@@ -236,6 +236,108 @@ __device__ __forceinline__ int esc_stage_row(int a0, int nA, int f, const int* _
   return (*sflag == 0 && len0 > 0) ? len0 : 0;
 }
 
+// ---- row pipeline of the persistent kernels -------------------------------------------------------------------------
+// A CTA works through the rows r = blockIdx.x, blockIdx.x + gridDim.x, ... of its bin.  What a row needs before its
+// first gather is a chain of four dependent global loads (row list -> row header -> A's columns -> B's row
+// pointers): ~3 us that a one-row-per-CTA launch pays once per row (ncu capture r02c6: 40-60 % of all stall samples
+// of both kernels sit on that chain and on the barrier behind it).  Warp 0 therefore runs the chain as a software
+// pipeline in registers, one stage per row built: while row r is built, the B row pointers of row r+G, the A entries
+// of row r+2G, the header of row r+3G and the list entry of row r+4G are in flight, and nothing is waited for at the
+// top of a row.  A header travels as a lane-distributed vector --
+//   lane 0: rpA[i]  1: rpA[i+1]  2: flops[i]  3: rpC[i]  4: rpC[i+1]  5: cmin[i]  6: cmax[i]  7: i (or -1: no row)
+// -- one register per stage.  Rows of more than 32 entries of A are pipelined up to their header only
+// (esc_stage_row stages them when their turn comes).
+template <typename S, bool WITH_VALS>
+struct EscRowPipe {
+  int i3, h2, h1, c1, h0, b0, b1, rn;
+  S va1, va0;
+  __device__ __forceinline__ void init(int first) {
+    i3 = -1;
+    h2 = h1 = h0 = ((threadIdx.x & 31) == 7) ? -1 : 0;
+    c1 = b0 = b1 = 0;
+    va1 = va0 = S(0);
+    rn = first;
+  }
+  // advance every stage by one row and issue the loads of the new occupants (warp 0, all 32 lanes)
+  __device__ __forceinline__ void pump(int nrows, int G, const int* __restrict__ rows, const int* __restrict__ rpA,
+                                       const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
+                                       const int* __restrict__ flops, const int* __restrict__ rpC,
+                                       const int* __restrict__ cmin, const int* __restrict__ cmax) {
+    const int lane = threadIdx.x & 31;
+    {  // stage 0 <- 1: the B row of A's entry `lane`
+      h0 = h1;
+      va0 = va1;
+      const int a0 = __shfl_sync(0xffffffffu, h1, 0);
+      const int nA = __shfl_sync(0xffffffffu, h1, 1) - a0;
+      b0 = b1 = 0;
+      if (nA <= 32 && lane < nA) {
+        b0 = ldg(rpB + c1);
+        b1 = ldg(rpB + c1 + 1);
+      }
+    }
+    {  // stage 1 <- 2: A's entries
+      h1 = h2;
+      const int a0 = __shfl_sync(0xffffffffu, h2, 0);
+      const int nA = __shfl_sync(0xffffffffu, h2, 1) - a0;
+      c1 = 0;
+      va1 = S(0);
+      if (nA <= 32 && lane < nA) {
+        c1 = ldg(ciA + a0 + lane);
+        if (WITH_VALS) va1 = ldg(vA + a0 + lane);
+      }
+    }
+    {  // stage 2 <- 3: the header of row i3
+      const int i = i3;
+      h2 = (lane == 7) ? i : 0;
+      if (i >= 0) {
+        const int* src = nullptr;
+        switch (lane) {
+          case 0: src = rpA + i; break;
+          case 1: src = rpA + i + 1; break;
+          case 2: src = flops + i; break;
+          case 3: src = rpC ? rpC + i : nullptr; break;
+          case 4: src = rpC ? rpC + i + 1 : nullptr; break;
+          case 5: src = cmin + i; break;
+          case 6: src = cmax + i; break;
+          default: break;
+        }
+        if (src) h2 = ldg(src);
+      }
+    }
+    i3 = rn < nrows ? ldg(rows + rn) : -1;  // stage 3
+    rn += G;
+  }
+  // stage 0 -> shared memory (warp 0): the header, and for a row of <= 32 entries of A the staging arrays of
+  // esc_stage_row (bs, pre, va, the uniform-length flag).  The loads were issued one row ago.
+  __device__ __forceinline__ void publish(int* shdr, int* bs, int* pre, S* va, int* wsum) const {
+    const int lane = threadIdx.x & 31;
+    if (lane < 8) shdr[lane] = h0;
+    const int a0 = __shfl_sync(0xffffffffu, h0, 0);
+    const int nA = __shfl_sync(0xffffffffu, h0, 1) - a0;
+    const int f = __shfl_sync(0xffffffffu, h0, 2);
+    if (nA > 32) return;
+    int len = 0;
+    if (lane < nA) {
+      len = b1 - b0;
+      bs[lane] = b0;
+      if (WITH_VALS) va[lane] = va0;
+    }
+    const int len0 = __shfl_sync(0xffffffffu, len, 0);
+    const bool uni = __all_sync(0xffffffffu, lane >= nA || len == len0) != 0;
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane < nA) pre[lane] = inc - len;
+    if (lane == 0) {
+      pre[nA] = f;
+      wsum[35] = (uni && len0 > 0) ? len0 : 0;
+    }
+  }
+};
+
 // ---- the products of this thread: columns (and values) in registers ------------------------------------------------
 template <int T, int I, typename S, bool WITH_VALS>
 __device__ __forceinline__ void esc_expand(int f, int nA, int L0, const int* bs, const int* pre, const S* va,
@@ -348,48 +450,33 @@ struct EscSymLayout {
   static constexpr int SORTW = NB + 4 + CAP + 8;         // off[NB + 4] | skey[CAP] of the fallback, aliased with the bitmap
   static constexpr int REGW = BMW > SORTW ? BMW : SORTW;
   static constexpr int SUSCAP = 64;
-  // region[REGW] | bs[NA] | pre[NA + 4] | wsum[36] | sus_n[4] | sus_col[SUSCAP] | sus_dup[SUSCAP]
-  static constexpr size_t BYTES = sizeof(int) * (size_t)(REGW + NA + NA + 4 + 36 + 4 + 2 * SUSCAP);
+  // region[REGW] | bs[NA] | pre[NA + 4] | wsum[36] | sus_n[4] | sus_col[SUSCAP] | sus_dup[SUSCAP] | shdr[8]
+  static constexpr size_t BYTES = sizeof(int) * (size_t)(REGW + NA + NA + 4 + 36 + 4 + 2 * SUSCAP + 8);
   static_assert(BYTES <= 227 * 1024, "esc_sym_kernel: configuration exceeds the shared memory of an SM");
 };
 
-template <int T, int I, int LOG2NB, int MINB>
-__global__ void __launch_bounds__(T, MINB)
-    esc_sym_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
-                   const int* __restrict__ rpB, const int* __restrict__ ciB, const int* __restrict__ flops,
-                   const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, int* __restrict__ row_nnz) {
+// one row: shdr holds its header, and for nA <= 32 warp 0 has staged bs / pre / the uniform-length flag already
+template <int T, int I, int LOG2NB>
+__device__ __forceinline__ void esc_sym_row(int* region, int* bs, int* pre, int* wsum, int* sus_n, int* sus_col, int* sus_dup,
+                                            const int* shdr, const int* __restrict__ ciA, const int* __restrict__ rpB,
+                                            const int* __restrict__ ciB, int* __restrict__ row_nnz) {
   using L = EscSymLayout<T, I, LOG2NB>;
   constexpr int NB = L::NB;
   constexpr int NOKEY = INT_MAX;
   constexpr int SUSCAP = L::SUSCAP;
-  extern __shared__ __align__(16) int esc_sm[];
-  int* region = esc_sm;
   unsigned* bm = reinterpret_cast<unsigned*>(region);
   int* off = region;               // fallback view
   int* skey = region + NB + 4;
-  int* bs = region + L::REGW;
-  int* pre = bs + L::NA;
-  int* wsum = pre + L::NA + 4;
-  int* sus_n = wsum + 36;
-  int* sus_col = sus_n + 4;
-  int* sus_dup = sus_col + SUSCAP;
   const int tid = threadIdx.x;
-  const int i = rows[blockIdx.x];
-  const int f = flops[i];
+  const int i = shdr[7];
+  const int f = shdr[2];
   if (f == 0) {
     if (tid == 0) row_nnz[i] = 0;
     return;
   }
-  const int a0 = rpA[i], nA = rpA[i + 1] - a0;
-  {
-    int4* b4 = reinterpret_cast<int4*>(region);
-    for (int s = tid; s < L::BMW / 4; s += T) b4[s] = make_int4(0, 0, 0, 0);
-    if (tid == 0) *sus_n = 0;
-    if (tid < SUSCAP) sus_dup[tid] = 0;
-    if (T < SUSCAP)
-      for (int s = tid + T; s < SUSCAP; s += T) sus_dup[s] = 0;
-  }
-  const int L0 = esc_stage_row<T, float, false>(a0, nA, f, ciA, (const float*)nullptr, rpB, bs, pre, (float*)nullptr, wsum);
+  const int a0 = shdr[0], nA = shdr[1] - a0;
+  const int L0 = nA <= 32 ? wsum[35]
+                          : esc_stage_row<T, float, false>(a0, nA, f, ciA, (const float*)nullptr, rpB, bs, pre, (float*)nullptr, wsum);
   int col[I];
   float dummy[I];
   esc_expand<T, I, float, false>(f, nA, L0, bs, pre, (const float*)nullptr, ciB, (const float*)nullptr, NOKEY, col, dummy);
@@ -445,8 +532,8 @@ __global__ void __launch_bounds__(T, MINB)
     for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
   }
   __syncthreads();
-  const int cmin = cmin_arr[i];
-  const long long span = (long long)cmax_arr[i] - cmin + 1;
+  const int cmin = shdr[5];
+  const long long span = (long long)shdr[6] - cmin + 1;
   int pos[I], lc[I];
   esc_bucket_sort<T, I, LOG2NB>(f, cmin, span, NOKEY, col, off, skey, wsum, pos, lc);
   // a product is a duplicate iff an equal column sits at a smaller position of its bucket
@@ -470,6 +557,50 @@ __global__ void __launch_bounds__(T, MINB)
   if (tid == 0) row_nnz[i] = f - total;
 }
 
+template <int T, int I, int LOG2NB, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+    esc_sym_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
+                   const int* __restrict__ rpB, const int* __restrict__ ciB, const int* __restrict__ flops,
+                   const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, int* __restrict__ row_nnz) {
+  using L = EscSymLayout<T, I, LOG2NB>;
+  constexpr int SUSCAP = L::SUSCAP;
+  extern __shared__ __align__(16) int esc_sm[];
+  int* region = esc_sm;
+  int* bs = region + L::REGW;
+  int* pre = bs + L::NA;
+  int* wsum = pre + L::NA + 4;
+  int* sus_n = wsum + 36;
+  int* sus_col = sus_n + 4;
+  int* sus_dup = sus_col + SUSCAP;
+  int* shdr = sus_dup + SUSCAP;
+  const int tid = threadIdx.x;
+  const int G = (int)gridDim.x;
+  EscRowPipe<float, false> pipe;
+  if (tid < 32) {
+    pipe.init((int)blockIdx.x);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) pipe.pump(nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr);
+  }
+#pragma unroll 1
+  for (int r = (int)blockIdx.x; r < nrows_bin; r += G) {
+    {
+      int4* b4 = reinterpret_cast<int4*>(region);
+      for (int s = tid; s < L::BMW / 4; s += T) b4[s] = make_int4(0, 0, 0, 0);
+      if (tid == 0) *sus_n = 0;
+      if (tid < SUSCAP) sus_dup[tid] = 0;
+      if (T < SUSCAP)
+        for (int s = tid + T; s < SUSCAP; s += T) sus_dup[s] = 0;
+    }
+    if (tid < 32) {
+      pipe.publish(shdr, bs, pre, (float*)nullptr, wsum);
+      pipe.pump(nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr);
+    }
+    __syncthreads();
+    esc_sym_row<T, I, LOG2NB>(region, bs, pre, wsum, sus_n, sus_col, sus_dup, shdr, ciA, rpB, ciB, row_nnz);
+    __syncthreads();  // the next row reuses every array
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // NUMERIC
 // ---------------------------------------------------------------------------------------------------
@@ -480,10 +611,10 @@ struct EscNumLayout {
   static constexpr int NB = 1 << LOG2NB;
   static constexpr int NA = CAP / 2;
   static constexpr int NW = T / 32;
-  // off[NB + 4] | skey[CAP] | wsum[36] | hpre[I * NW + 4] | sord[CAP] (u16) | union { va[NA], bs[NA], pre[NA + 4] ; skv[CAP] }
+  // off[NB + 4] | skey[CAP] | wsum[36] | hpre[I * NW + 4] | shdr[8] | sord[CAP] (u16) | union { va[NA], bs[NA], pre[NA + 4] ; skv[CAP] }
   static constexpr size_t OFF_BYTES = sizeof(int) * (size_t)(NB + 4);
   static constexpr size_t KEY_BYTES = sizeof(int) * (size_t)CAP;
-  static constexpr size_t WS_BYTES = sizeof(int) * (size_t)(36 + I * NW + 4);
+  static constexpr size_t WS_BYTES = sizeof(int) * (size_t)(36 + I * NW + 4 + 8);
   static constexpr size_t ORD_BYTES = ((sizeof(unsigned short) * (size_t)CAP) + 15) & ~(size_t)15;
   static constexpr size_t STAGE_BYTES = sizeof(int) * (size_t)(NA + NA + 4) + sizeof(S) * (size_t)NA;
   static constexpr size_t SORT_BYTES = sizeof(KV) * (size_t)CAP;
@@ -492,20 +623,17 @@ struct EscNumLayout {
   static_assert(BYTES <= 227 * 1024, "esc_num_kernel: configuration exceeds the shared memory of an SM");
 };
 
-template <typename S, int T, int I, int LOG2NB, int MINB>
-__global__ void __launch_bounds__(T, MINB)
-    esc_num_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
-                   const S* __restrict__ vA, const int* __restrict__ rpB, const int* __restrict__ ciB,
-                   const S* __restrict__ vB, const int* __restrict__ rpC, int* __restrict__ ciC, S* __restrict__ vC,
-                   const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, const int* __restrict__ flops) {
+// one row: shdr holds its header, and for nA <= 32 warp 0 has staged bs / pre / va / the uniform-length flag already
+template <typename S, int T, int I, int LOG2NB>
+__device__ __forceinline__ void esc_num_row(unsigned char* esc_raw, const int* shdr, const int* __restrict__ ciA,
+                                            const S* __restrict__ vA, const int* __restrict__ rpB,
+                                            const int* __restrict__ ciB, const S* __restrict__ vB, int* __restrict__ ciC,
+                                            S* __restrict__ vC) {
   using L = EscNumLayout<S, T, I, LOG2NB>;
   using KVT = EscKV<S>;
   using KV = typename KVT::type;
-  constexpr int CAP = L::CAP;
-  constexpr int NB = L::NB;
   constexpr int NW = L::NW;
   constexpr int NOKEY = INT_MAX;
-  extern __shared__ __align__(16) unsigned char esc_raw[];
   int* off = reinterpret_cast<int*>(esc_raw);
   int* skey = reinterpret_cast<int*>(esc_raw + L::OFF_BYTES);
   int* wsum = reinterpret_cast<int*>(esc_raw + L::OFF_BYTES + L::KEY_BYTES);
@@ -520,20 +648,15 @@ __global__ void __launch_bounds__(T, MINB)
   KV* skv = reinterpret_cast<KV*>(un);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = rows[blockIdx.x];
-  const int cbase = rpC[i];
-  const int nz = rpC[i + 1] - cbase;
+  const int cbase = shdr[3];
+  const int nz = shdr[4] - cbase;
   if (nz == 0) return;
-  const int f = flops[i];
-  const int a0 = rpA[i], nA = rpA[i + 1] - a0;
-  const int cmin = cmin_arr[i];
-  const long long span = (long long)cmax_arr[i] - cmin + 1;
+  const int f = shdr[2];
+  const int a0 = shdr[0], nA = shdr[1] - a0;
+  const int cmin = shdr[5];
+  const long long span = (long long)shdr[6] - cmin + 1;
   const bool nodup = (nz == f);  // no duplicate column in this row (uniform over the CTA)
-  {
-    int4* o4 = reinterpret_cast<int4*>(off);
-    for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
-  }
-  const int L0 = esc_stage_row<T, S, true>(a0, nA, f, ciA, vA, rpB, bs, pre, va, wsum);
+  const int L0 = nA <= 32 ? wsum[35] : esc_stage_row<T, S, true>(a0, nA, f, ciA, vA, rpB, bs, pre, va, wsum);
   int col[I];
   S val[I];
   esc_expand<T, I, S, true>(f, nA, L0, bs, pre, va, ciB, vB, NOKEY, col, val);
@@ -635,6 +758,46 @@ __global__ void __launch_bounds__(T, MINB)
         vC[cbase + o] = v;
       }
     }
+  }
+}
+
+template <typename S, int T, int I, int LOG2NB, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+    esc_num_kernel(int nrows_bin, const int* __restrict__ rows, const int* __restrict__ rpA, const int* __restrict__ ciA,
+                   const S* __restrict__ vA, const int* __restrict__ rpB, const int* __restrict__ ciB,
+                   const S* __restrict__ vB, const int* __restrict__ rpC, int* __restrict__ ciC, S* __restrict__ vC,
+                   const int* __restrict__ cmin_arr, const int* __restrict__ cmax_arr, const int* __restrict__ flops) {
+  using L = EscNumLayout<S, T, I, LOG2NB>;
+  constexpr int NB = L::NB;
+  extern __shared__ __align__(16) unsigned char esc_raw[];
+  int* off = reinterpret_cast<int*>(esc_raw);
+  int* wsum = reinterpret_cast<int*>(esc_raw + L::OFF_BYTES + L::KEY_BYTES);
+  int* shdr = wsum + 36 + I * L::NW + 4;
+  unsigned char* un = esc_raw + L::OFF_BYTES + L::KEY_BYTES + L::WS_BYTES + L::ORD_BYTES;
+  S* va = reinterpret_cast<S*>(un);
+  int* bs = reinterpret_cast<int*>(un + sizeof(S) * (size_t)L::NA);
+  int* pre = bs + L::NA;
+  const int tid = threadIdx.x;
+  const int G = (int)gridDim.x;
+  EscRowPipe<S, true> pipe;
+  if (tid < 32) {
+    pipe.init((int)blockIdx.x);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) pipe.pump(nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr);
+  }
+#pragma unroll 1
+  for (int r = (int)blockIdx.x; r < nrows_bin; r += G) {
+    {
+      int4* o4 = reinterpret_cast<int4*>(off);
+      for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
+    }
+    if (tid < 32) {
+      pipe.publish(shdr, bs, pre, va, wsum);
+      pipe.pump(nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr);
+    }
+    __syncthreads();
+    esc_num_row<S, T, I, LOG2NB>(esc_raw, shdr, ciA, vA, rpB, ciB, vB, ciC, vC);
+    __syncthreads();  // the next row's staging arrays alias the sorted pairs
   }
 }
 

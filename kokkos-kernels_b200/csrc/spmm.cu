@@ -1081,6 +1081,138 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Cooperative variant (default; B200SP_SPMM_ITEM_COOP=0 selects the kernel above): the same items, the same order of
+// additions (bit-identical Y), but the KTL lanes of a group no longer read the same (col, val) address each -- that
+// costs one L1 wavefront per group and entry for the column, one for the value and one for the X row: 3 per
+// nonzero at 8 groups per warp, and the kernel is bound by exactly that (one wavefront per SM and clock).  Here the
+// group reads a batch of EB consecutive entries with ONE load per lane (adjacent lanes, adjacent entries: the group's
+// EB/KTL loads cover a contiguous 32..64-byte run) and passes them round with shuffles, which run on a different
+// pipe: 1 + 2 * 4/32 wavefronts per nonzero for k = 16 fp32, with EB = 8 gathers of X in flight per lane.
+template <typename S, int VW, int KTL, int EB /* entries per batch: 4 or 8 */>
+__global__ void __launch_bounds__(256)
+    spmm_item_coop_kernel(int n_items, const int4* __restrict__ items, int k, const int* __restrict__ col_idx,
+                          const S* __restrict__ vals, const S* __restrict__ X, int64_t ldx, S* __restrict__ Y, int64_t ldy,
+                          S* __restrict__ partial, S alpha, S beta) {
+  constexpr int PL = (EB + KTL - 1) / KTL;    // entries a lane loads per batch (KTL > EB: lanes >= EB load nothing)
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t q = gt / KTL;
+  const int t = (int)(gt % KTL);
+  if (q >= n_items) return;  // whole groups leave: 256 % KTL == 0
+  const unsigned gmask = KTL == 32 ? 0xffffffffu : (((1u << (KTL & 31)) - 1u) << ((threadIdx.x & 31) & ~(KTL - 1)));
+  const uint64_t once = l2_policy_evict_first();
+  const int4 it = ld_once(items + q, once);
+  const int row = it.x, e0 = it.y, len = it.z, slot = it.w;
+  const int eend = e0 + len;
+  const int nstrips = (k + KTL * VW - 1) / (KTL * VW);
+  for (int strip = 0; strip < nstrips; ++strip) {
+    const int j = (strip * KTL + t) * VW;
+    const bool live = j < k;  // k % VW == 0: a lane's VW columns are all in or all out; dead lanes still load and shuffle
+    Acc<S, VW> acc;
+#pragma unroll
+    for (int c = 0; c < VW; ++c) acc.a[c] = S(0);
+    const S* xb = X + (live ? j : 0);
+    int e = e0;
+    for (; e + EB <= eend; e += EB) {
+      int cl[PL];
+      S vl[PL];
+#pragma unroll
+      for (int i = 0; i < PL; ++i) {
+        const int idx = i * KTL + t;
+        cl[i] = 0;
+        vl[i] = S(0);
+        if (KTL <= EB || idx < EB) {
+          cl[i] = ld_once(col_idx + e + idx, once);
+          vl[i] = ld_once(vals + e + idx, once);
+        }
+      }
+      int c[EB];
+      S av[EB];
+#pragma unroll
+      for (int u = 0; u < EB; ++u) {
+        if constexpr (KTL == 1) {
+          c[u] = cl[u];
+          av[u] = vl[u];
+        } else {
+          c[u] = __shfl_sync(gmask, cl[u / KTL], u % KTL, KTL);
+          av[u] = __shfl_sync(gmask, vl[u / KTL], u % KTL, KTL);
+        }
+      }
+      if (live) {
+        Acc<S, VW> xv[EB];
+#pragma unroll
+        for (int u = 0; u < EB; ++u) xv[u] = load_x<S, VW>(xb + (int64_t)c[u] * ldx);
+#pragma unroll
+        for (int u = 0; u < EB; ++u)
+#pragma unroll
+          for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av[u] * xv[u].a[cc];
+      }
+    }
+    const int rem = eend - e;  // 0 .. EB-1, uniform over the group
+    if (rem > 0) {
+      int cl[PL];
+      S vl[PL];
+#pragma unroll
+      for (int i = 0; i < PL; ++i) {
+        const int idx = i * KTL + t;
+        cl[i] = 0;
+        vl[i] = S(0);
+        if (idx < rem) {
+          cl[i] = ld_once(col_idx + e + idx, once);
+          vl[i] = ld_once(vals + e + idx, once);
+        }
+      }
+      int c[EB];
+      S av[EB];
+#pragma unroll
+      for (int u = 0; u < EB; ++u) {
+        if constexpr (KTL == 1) {
+          c[u] = cl[u];
+          av[u] = vl[u];
+        } else {
+          c[u] = __shfl_sync(gmask, cl[u / KTL], u % KTL, KTL);
+          av[u] = __shfl_sync(gmask, vl[u / KTL], u % KTL, KTL);
+        }
+      }
+      if (live) {
+        Acc<S, VW> xv[EB];
+#pragma unroll
+        for (int u = 0; u < EB - 1; ++u)
+          if (u < rem) xv[u] = load_x<S, VW>(xb + (int64_t)c[u] * ldx);
+#pragma unroll
+        for (int u = 0; u < EB - 1; ++u)
+          if (u < rem) {
+#pragma unroll
+            for (int cc = 0; cc < VW; ++cc) acc.a[cc] += av[u] * xv[u].a[cc];
+          }
+      }
+    }
+    if (!live) continue;
+    S o[VW];
+    S* dst;
+    if (slot < 0) {
+      dst = Y + (int64_t)row * ldy + j;
+      if (beta == S(0)) {
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) o[cc] = alpha * acc.a[cc];
+      } else {
+        const Acc<S, VW> old = load_x<S, VW>(dst);
+#pragma unroll
+        for (int cc = 0; cc < VW; ++cc) o[cc] = beta * old.a[cc] + alpha * acc.a[cc];
+      }
+    } else {
+      dst = partial + (int64_t)slot * k + j;  // raw sums; alpha and beta are applied by the reduce kernel
+#pragma unroll
+      for (int cc = 0; cc < VW; ++cc) o[cc] = acc.a[cc];
+    }
+    if constexpr (VW == 1) {
+      st_once(dst, o[0], once);
+    } else {
+      using V = typename VecOf<S>::type;
+      st_once(reinterpret_cast<V*>(dst), vec_pack(o), once);
+    }
+  }
+}
+
 // rows of several pieces: Y(row, :) = beta * Y(row, :) + alpha * (piece 0 + piece 1 + ...), pieces added in order
 template <typename S>
 __global__ void __launch_bounds__(256)
@@ -1124,10 +1256,21 @@ static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m
   const int64_t threads = (int64_t)mi->n_items * KTL;
   const unsigned grid = (unsigned)((threads + 255) / 256);
   if (grid > 0) {
+    static const int coop = [] {  // B200SP_SPMM_ITEM_COOP=0: every lane reads (col, val) itself (the first item kernel); 4 | 8: batch
+      const char* e = getenv("B200SP_SPMM_ITEM_COOP");
+      return e && e[0] == '0' ? 0 : (e && e[0] == '4' ? 4 : 8);
+    }();
 #define B200SP_MMI(V, L)                                                                                                   \
   case L:                                                                                                                  \
-    spmm_item_kernel<S, V, L><<<grid, 256, 0, st>>>(mi->n_items, mi->items, k, col_idx, vals, X, ldx, Y, ldy, (S*)mi->partial, \
-                                                    alpha, beta);                                                          \
+    if (coop == 8)                                                                                                         \
+      spmm_item_coop_kernel<S, V, L, 8><<<grid, 256, 0, st>>>(mi->n_items, mi->items, k, col_idx, vals, X, ldx, Y, ldy,    \
+                                                              (S*)mi->partial, alpha, beta);                               \
+    else if (coop == 4)                                                                                                    \
+      spmm_item_coop_kernel<S, V, L, 4><<<grid, 256, 0, st>>>(mi->n_items, mi->items, k, col_idx, vals, X, ldx, Y, ldy,    \
+                                                              (S*)mi->partial, alpha, beta);                               \
+    else                                                                                                                   \
+      spmm_item_kernel<S, V, L><<<grid, 256, 0, st>>>(mi->n_items, mi->items, k, col_idx, vals, X, ldx, Y, ldy,            \
+                                                      (S*)mi->partial, alpha, beta);                                       \
     break;
     if (vec) {
       switch (KTL) { B200SP_MMI(W, 1) B200SP_MMI(W, 2) B200SP_MMI(W, 4) B200SP_MMI(W, 8) B200SP_MMI(W, 16) B200SP_MMI(W, 32) }

@@ -97,9 +97,17 @@ def test_reference_sweep_multivector(cuda, oracle, bs, mb, nb, layout):
                     assert np.max(np.abs(got - exp), initial=0.0) <= tolerance(dtype, alpha, beta, max_row), (h.last_kernel(), mode, k, alpha, beta)
 
 
+@pytest.mark.parametrize("force", [None, "walk"])
 @pytest.mark.parametrize("bs", list(range(2, 18)))
-def test_tile_kernel_every_block_size(cuda, oracle, bs):
+def test_tile_kernel_every_block_size(cuda, oracle, bs, force, monkeypatch):
+    """Default selection (element-per-lane tile kernel for bs <= 5, row-vector kernel above: the measured choice) and the
+    run-time block size tile kernel forced for every bs it supports."""
     from kokkos_kernels_b200 import sparse as sp
+
+    if force:
+        monkeypatch.setenv("B200SP_BSR_KERNEL", force)
+    else:
+        monkeypatch.delenv("B200SP_BSR_KERNEL", raising=False)
 
     mb = max(20000, 4000000 // (bs * bs))  # enough tiles per CTA to wrap the ring on 148 SMs
     nb = mb + 13
@@ -109,7 +117,10 @@ def test_tile_kernel_every_block_size(cuda, oracle, bs):
     rng = np.random.default_rng(bs)
     for alpha, beta in ((1.0, 0.0), (3.7, -1.5)):
         run_rank1(sp, oracle, cuda, h, A, (bs, mb, nb, rp, ci, v), "N", rng, alpha, beta, np.float64)
-        assert h.last_kernel().startswith("bsr_tile" if bs <= 16 else "bsr_vector"), h.last_kernel()
+        if force:
+            assert h.last_kernel().startswith("bsr_tile<" if bs <= 16 else "bsr_vector"), h.last_kernel()
+        else:
+            assert h.last_kernel().startswith("bsr_tile_e" if bs <= 5 else "bsr_vector"), h.last_kernel()
     run_rank1(sp, oracle, cuda, h, A, (bs, mb, nb, rp, ci, v), "T", rng, -1.0, 1.0, np.float64)
 
 

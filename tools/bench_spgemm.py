@@ -36,11 +36,15 @@ def main():
     for rep in range(args.reps):
         kh = sp.KokkosKernelsHandle()
         kh.create_spgemm_handle()
+        row_mapC = torch.empty(n + 1, dtype=torch.int32, device=dev)  # the reference driver's protocol (KokkosSparse_spgemm.cpp:395-417)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        C = sp.spgemm_symbolic(kh, A, False, A, False)
+        sp.spgemm_symbolic_views(kh, n, n, n, A.row_map, A.entries, False, A.row_map, A.entries, False, row_mapC)
         torch.cuda.synchronize()
         t_sym = time.perf_counter() - t0
+        cn = kh.get_spgemm_handle().get_c_nnz()
+        C = None
+        C = sp.CrsMatrix(row_mapC, torch.empty(cn, dtype=torch.int32, device=dev), torch.empty(cn, dtype=torch.float64, device=dev), n)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sp.spgemm_numeric(kh, A, False, A, False, C)
