@@ -17,7 +17,9 @@ def pytest_configure(config):
 
 # GPU tests that need the real CUDA runtime (pinned host memory, torch streams, the nvcc-built shim driver)
 _NEEDS_REAL_CUDA = {"test_hostvec_entry", "test_interfaces_and_errors", "test_hostvec_pipeline", "test_shim_runs_on_gpu",
-                    "test_shim_bsr_runs_on_gpu", "test_hostvec_deferred_completion"}
+                    "test_shim_bsr_runs_on_gpu", "test_hostvec_deferred_completion",
+                    # BASELINE-size workloads: hours under the emulation
+                    "test_config4_full_size", "test_config3_full_size"}
 
 
 def pytest_collection_modifyitems(config, items):

@@ -17,7 +17,8 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "kokkos-kernels_b200", "lib")
+LIB = os.environ.get("B200SP_OBJ_DIR", os.path.join(ROOT, "kokkos-kernels_b200", "lib"))  # B200SP_OBJ_DIR: objects of the profiled commit
+CSRC_DIR = os.environ.get("B200SP_SRC_DIR", os.path.join(ROOT, "kokkos-kernels_b200", "csrc"))
 
 
 def ncu_rows(rep, needle):
@@ -98,7 +99,7 @@ def main():
     srcs = {}
     for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         if f not in srcs:
-            p = os.path.join(ROOT, "kokkos-kernels_b200", "csrc", f)
+            p = os.path.join(CSRC_DIR, f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
         text = srcs[f][l - 1].strip()[:70] if 0 < l <= len(srcs[f]) else ""
         print(f"{f}:{l:<5d} inst {100 * a[0] / ti:5.2f}%  samp {100 * a[1] / ts:5.2f}%  smem-wf {100 * a[2] / max(tw, 1):5.2f}% (excess {100 * a[3] / max(tw, 1):5.2f}%)  {text}")
