@@ -85,6 +85,7 @@ SPARSE_API = {
     "b200sp_bsr_spmm_f64_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, i32, f64, vp, vp, vp, vp, i64, i32, f64, vp, i64, i32]),
     "b200sp_bsr_spmm_f32_i32": (i32, [vp, vp, cp, i32, i32, i64, i32, i32, f32, vp, vp, vp, vp, i64, i32, f32, vp, i64, i32]),
     "b200sp_bsr_last_kernel": (C.c_char_p, [vp]),
+    "b200sp_bsr_plan_set_algorithm": (i32, [vp, i32]),
     "b200sp_gmres_f64_i32": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]),
     "b200sp_gmres_f32_i32": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f32, i32, i32, C.POINTER(i32), C.POINTER(f32), C.POINTER(i32)]),
     "b200sp_gmres_bsr_f64_i32": (i32, [vp, vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]),

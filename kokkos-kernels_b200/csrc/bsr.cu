@@ -544,6 +544,91 @@ __global__ void __launch_bounds__(256) bsr_mm_kernel(int mb, int bs, int lpr, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N, multivector, tensor cores (SPMV_BSR_TC; fp64): one warp per block row and super-tile of 8*NT columns of X.
+// The reference's only architecture-specific kernel is this product on wmma fragments (m8n8k4 for double,
+// sparse/impl/KokkosSparse_spmv_bsrmatrix_impl.hpp:74-459, opt-in through SPMV_BSR_TC, spmv_bsrmatrix_spec.hpp:165-245);
+// here it is mma.sync.m8n8k4.f64 issued directly, fragments loaded straight from global memory:
+//   A fragment (8 x 4, row):  lane l holds A_blk(mt*8 + l/4, ks*4 + l%4)  -- 4 lanes read 32 contiguous bytes of a block row
+//   B fragment (4 x 8, col):  lane l holds X(cb*bs + ks*4 + l%4, n0 + l/4) -- 8 lanes read 64 contiguous bytes of a row-major X row
+//   C fragment (8 x 8):       lane l holds Y(mt*8 + l/4, n0 + 2*(l%4) + {0, 1})
+// Rows / columns of a block beyond bs are fed as zeros (any bs <= 8*MT), columns of X beyond k likewise.  Each block of
+// A is read once for all 8*NT columns (the scalar kernel re-reads it per 4 columns).  The sums inside an MMA are the
+// tensor core's; between blocks the order is the storage order.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef B200SP_EMU
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int kk = 0; kk < 4; ++kk) {
+    const double av = __shfl_sync(0xffffffffu, a, g * 4 + kk);
+    const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + kk);
+    const double b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + kk);
+    c[0] += av * b0;
+    c[1] += av * b1;
+  }
+}
+#else
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+#endif
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(256) bsr_mm_tc_kernel(int mb, int bs, int k, const int* __restrict__ row_ptr,
+                                                        const int* __restrict__ col_idx, const double* __restrict__ vals,
+                                                        const double* __restrict__ X, int64_t xr, int64_t xc,
+                                                        double* __restrict__ Y, int64_t yr, int64_t yc, double alpha, double beta) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.y * (8 * NT);
+  const int vpe = bs * bs;
+  const int KS = (bs + 3) >> 2;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t brow = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; brow < mb; brow += warps) {
+    const int rs = row_ptr[brow], re = row_ptr[brow + 1];
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int j = rs; j < re; ++j) {
+      const int cb = ld_stream(col_idx + j);
+      const double* ab = vals + (int64_t)j * vpe;
+      for (int ks = 0; ks < KS; ++ks) {
+        const int kk = ks * 4 + t;  // column of the block = row of the X panel
+        const bool kin = kk < bs;
+        double b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int n = n0 + nt * 8 + g;
+          b[nt] = (kin && n < k) ? ldg(X + ((int64_t)cb * bs + kk) * xr + (int64_t)n * xc) : 0.0;
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int r = mt * 8 + g;
+          const double a = (kin && r < bs) ? ld_stream(ab + r * bs + kk) : 0.0;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt], a, b[nt]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r = mt * 8 + g;
+      if (r < bs) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + nt * 8 + 2 * t + e;
+            if (n < k) bsr_store(Y + ((int64_t)brow * bs + r) * yr + (int64_t)n * yc, acc[mt][nt][e], alpha, beta);
+          }
+      }
+    }
+  }
+}
+
 int pick_lpr(double avg_entries_per_point_row, int bs, int cap) {
   int lpr = avg_entries_per_point_row <= 8.0 ? 2 : avg_entries_per_point_row <= 96.0 ? 4 : avg_entries_per_point_row <= 384.0 ? 8 : 16;
   while (lpr > 1 && bs * lpr > cap) lpr >>= 1;
@@ -571,6 +656,7 @@ struct b200sp_bsr_plan {
   int* n_long = nullptr;
   // blockDim() == 1 is a CrsMatrix (KokkosSparse_spmv.hpp:169-185): forwarded to the CSR path
   b200sp_spmv_plan* crs = nullptr;
+  int algo = 0;  // B200SP_BSR_ALGO_*: 1 = tensor cores for the multivector product (SPMV_BSR_TC)
   char last_kernel[128] = "none";
 };
 
@@ -789,6 +875,36 @@ int bsr_spmm_impl(b200sp_bsr_plan* p, cudaStream_t st, char mode, int mb, int nb
     snprintf(p->last_kernel, sizeof(p->last_kernel), "bsr_transpose<%s,bs=%d>x%d", sizeof(S) == 8 ? "f64" : "f32", bs, k);
     return B200SP_OK;
   }
+  if constexpr (sizeof(S) == 8) {
+    // SPMV_BSR_TC (spmv_bsrmatrix_spec.hpp:176-245): no-transpose multivector products in double; anything else falls back,
+    // as the reference does when its tensor-core functor is unavailable.  B200SP_BSR_MM=tc|scalar overrides the plan.
+    const char* fm = getenv("B200SP_BSR_MM");
+    const bool tc = fm ? !strcmp(fm, "tc") : p->algo == 1;
+    if (tc && bs >= 2 && bs <= 16) {
+      const int NT = k > 8 ? 2 : 1;
+      const int warps_per_cta = 8;
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)mb + warps_per_cta - 1) / warps_per_cta, (int64_t)sm_count() * 16));
+      const int tiles = (k + 8 * NT - 1) / (8 * NT);
+      for (int t0 = 0; t0 < tiles; t0 += 65535) {
+        const int tn = std::min(tiles - t0, 65535);
+        const int c0 = t0 * 8 * NT;
+        const int kc = std::min(k - c0, tn * 8 * NT);
+        const dim3 grid(blocks, tn);
+        const double* Xc = (const double*)X + (int64_t)c0 * xc;
+        double* Yc = (double*)Y + (int64_t)c0 * yc;
+#define B200SP_TC(MT_, NT_) bsr_mm_tc_kernel<MT_, NT_><<<grid, 256, 0, st>>>(mb, bs, kc, rp, ci, (const double*)v, Xc, xr, xc, Yc, yr, yc, (double)alpha, (double)beta)
+        if (bs <= 8) {
+          if (NT == 2) B200SP_TC(1, 2); else B200SP_TC(1, 1);
+        } else {
+          if (NT == 2) B200SP_TC(2, 2); else B200SP_TC(2, 1);
+        }
+#undef B200SP_TC
+        B200SP_LAUNCH_CHECK();
+      }
+      snprintf(p->last_kernel, sizeof(p->last_kernel), "bsr_mm_tc<f64,bs=%d,m8n8k4,MT=%d,NT=%d>", bs, bs <= 8 ? 1 : 2, NT);
+      return B200SP_OK;
+    }
+  }
   constexpr int KT = 4;
   const double avg = (double)nnzb * bs / (double)mb;
   const int lpr = pick_lpr(avg, 1, 32);
@@ -825,6 +941,13 @@ int b200sp_bsr_plan_destroy(b200sp_bsr_plan* p, void* stream) {
 }
 
 const char* b200sp_bsr_last_kernel(const b200sp_bsr_plan* p) { return p ? p->last_kernel : "none"; }
+
+int b200sp_bsr_plan_set_algorithm(b200sp_bsr_plan* p, int algo) {
+  B200SP_REQUIRE(p != nullptr, "bsr_plan_set_algorithm: null plan");
+  B200SP_REQUIRE(algo == B200SP_BSR_ALGO_DEFAULT || algo == B200SP_BSR_ALGO_TENSOR_CORES, "bsr_plan_set_algorithm: unknown algorithm %d", algo);
+  p->algo = algo;
+  return B200SP_OK;
+}
 
 int b200sp_bsr_spmv_f64_i32(b200sp_bsr_plan* plan, void* stream, char mode, int mb, int nb, int64_t nnzb, int bs, double alpha,
                             const int* row_ptr, const int* col_idx, const double* vals, const double* x, double beta, double* y) {

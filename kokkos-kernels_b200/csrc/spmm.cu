@@ -54,41 +54,45 @@ __global__ void scale2d_kernel(int64_t rows, int k, S beta, S* __restrict__ Y, i
   }
 }
 
-// out(r, j) row-major [rows x k] <- in(r, j) with strides (ir, ic)   (or the reverse)
+// out(r, j) row-major [rows x k] <- in(r, j) with strides (sr, sc)   (or the reverse).  256 threads move tiles of 128 rows x
+// <= 32 columns through shared memory: on the strided side consecutive threads touch consecutive rows of one column (512
+// contiguous bytes per column of a LayoutLeft operand in fp32), on the row-major side consecutive elements (the whole tile is
+// one contiguous run when k <= 32); the odd row pitch keeps both phases free of bank conflicts.  Grid-stride over the tiles.
 template <typename S, bool TO_ROWMAJOR>
-__global__ void relayout_kernel(int64_t rows, int k, S* __restrict__ rm, const S* __restrict__ strided_in,
-                                S* __restrict__ strided_out, int64_t sr, int64_t sc) {
-  __shared__ S tile[32][33];
-  // tile: 32 rows x 32 columns
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  for (int j0 = 0; j0 < k; j0 += 32) {
-    if (TO_ROWMAJOR) {
-      // read along the column-major fast axis (rows), write along columns
-      for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
-        const int64_t r = r0 + threadIdx.x;
-        const int j = j0 + jj;
-        if (r < rows && j < k) tile[threadIdx.x][jj] = strided_in[r * sr + (int64_t)j * sc];
+__global__ void __launch_bounds__(256) relayout_kernel(int64_t rows, int k, S* __restrict__ rm, const S* __restrict__ strided_in,
+                                                       S* __restrict__ strided_out, int64_t sr, int64_t sc) {
+  constexpr int R = 128, KC = 32;
+  __shared__ S tile[R][KC + 1];
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (rows + R - 1) / R;
+  for (int64_t tI = blockIdx.x; tI < ntiles; tI += gridDim.x) {
+    const int64_t r0 = tI * R;
+    const int nr = (int)((rows - r0) < (int64_t)R ? (rows - r0) : (int64_t)R);
+    for (int j0 = 0; j0 < k; j0 += KC) {
+      const int nc = (k - j0) < KC ? (k - j0) : KC;
+      if (TO_ROWMAJOR) {
+        for (int idx = tid; idx < R * nc; idx += 256) {
+          const int r = idx % R, j = idx / R;
+          if (r < nr) tile[r][j] = strided_in[(r0 + r) * sr + (int64_t)(j0 + j) * sc];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * nc; idx += 256) {
+          const int r = idx / nc, j = idx - r * nc;
+          rm[(r0 + r) * k + j0 + j] = tile[r][j];
+        }
+      } else {
+        for (int idx = tid; idx < nr * nc; idx += 256) {
+          const int r = idx / nc, j = idx - r * nc;
+          tile[r][j] = rm[(r0 + r) * k + j0 + j];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < R * nc; idx += 256) {
+          const int r = idx % R, j = idx / R;
+          if (r < nr) strided_out[(r0 + r) * sr + (int64_t)(j0 + j) * sc] = tile[r][j];
+        }
       }
       __syncthreads();
-      for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        const int64_t r = r0 + rr;
-        const int j = j0 + threadIdx.x;
-        if (r < rows && j < k) rm[r * k + j] = tile[rr][threadIdx.x];
-      }
-    } else {
-      for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        const int64_t r = r0 + rr;
-        const int j = j0 + threadIdx.x;
-        if (r < rows && j < k) tile[rr][threadIdx.x] = rm[r * k + j];
-      }
-      __syncthreads();
-      for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
-        const int64_t r = r0 + threadIdx.x;
-        const int j = j0 + jj;
-        if (r < rows && j < k) strided_out[r * sr + (int64_t)j * sc] = tile[threadIdx.x][jj];
-      }
     }
-    __syncthreads();
   }
 }
 
@@ -1372,11 +1376,12 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
     const size_t ytb = yrm ? 0 : sizeof(S) * (size_t)yrows * k;
     int rc = plan_mv_scratch(p, st, xtb, ytb, &xt, &yt);
     if (rc) return rc;
-    const dim3 tb(32, 8);
+    const int tb = 256;
+    auto rl_grid = [](int64_t rows) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 127) / 128, (int64_t)sm_count() * 16)); };
     const S* Xr = X;
     int64_t ldxr = ldx;
     if (!xrm) {
-      relayout_kernel<S, true><<<(unsigned)((xrows + 31) / 32), tb, 0, st>>>(xrows, k, (S*)xt, X, nullptr, xr, xc);
+      relayout_kernel<S, true><<<rl_grid(xrows), tb, 0, st>>>(xrows, k, (S*)xt, X, nullptr, xr, xc);
       B200SP_LAUNCH_CHECK();
       Xr = (const S*)xt;
       ldxr = k;
@@ -1387,7 +1392,7 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
       Yr = (S*)yt;
       ldyr = k;
       if (beta != S(0)) {
-        relayout_kernel<S, true><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, Y, nullptr, yr, yc);
+        relayout_kernel<S, true><<<rl_grid(yrows), tb, 0, st>>>(yrows, k, Yr, Y, nullptr, yr, yc);
         B200SP_LAUNCH_CHECK();
       }
     }
@@ -1406,7 +1411,7 @@ static int spmm_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
     }
     if (rc) return rc;
     if (!yrm) {
-      relayout_kernel<S, false><<<(unsigned)((yrows + 31) / 32), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
+      relayout_kernel<S, false><<<rl_grid(yrows), tb, 0, st>>>(yrows, k, Yr, nullptr, Y, yr, yc);
       B200SP_LAUNCH_CHECK();
     }
     plan_set_last_kernel(p, choice == 4 ? "spmm_relayout+items" : tile_ok ? "spmm_relayout+tile" : (split ? "spmm_relayout+split" : "spmm_relayout+rowmajor"));

@@ -110,6 +110,9 @@ inline int b200_call_bsr_spmm(b200sp_bsr_plan* p, void* s, char mode, int mb, in
                                   const coefficient_type& beta, const YVector& Y) {                                   \
       Kokkos::Profiling::pushRegion("KokkosSparse::spmv[TPL_B200,BSRMATRIX," + Kokkos::ArithTraits<SCALAR>::name() + "]"); \
       b200sp_bsr_plan* plan = b200_bsr_plan_of(handle->tpl_rank2, exec);                                              \
+      /* SPMV_BSR_TC: the handle asks for tensor cores (spmv_bsrmatrix_spec.hpp:176-177) */                           \
+      KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_bsr_plan_set_algorithm(                                                 \
+          plan, handle->algo == SPMV_BSR_TC ? B200SP_BSR_ALGO_TENSOR_CORES : B200SP_BSR_ALGO_DEFAULT));               \
       constexpr int rm  = std::is_same<LAYOUT, Kokkos::LayoutRight>::value ? 1 : 0;                                   \
       const int64_t ldx = rm ? (int64_t)X.stride(0) : (int64_t)X.stride(1);                                           \
       const int64_t ldy = rm ? (int64_t)Y.stride(0) : (int64_t)Y.stride(1);                                           \

@@ -141,6 +141,8 @@ class SPMVHandle:
     def _bsr(self):
         if not self._bsr_plan:
             check(_lib.sparse().b200sp_bsr_plan_create(C.byref(self._bsr_plan)))
+            if self.algo == SPMV_BSR_TC:  # spmv_bsrmatrix_spec.hpp:176-177: tensor cores only when the handle asks for them
+                check(_lib.sparse().b200sp_bsr_plan_set_algorithm(self._bsr_plan, 1))
         return self._bsr_plan
 
     def get_algorithm(self):

@@ -90,7 +90,7 @@ using default_layout = Kokkos::LayoutLeft;
 }
 
 namespace KokkosSparse {
-enum SPMVAlgorithm { SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH };
+enum SPMVAlgorithm { SPMV_DEFAULT, SPMV_FAST_SETUP, SPMV_NATIVE, SPMV_MERGE_PATH, SPMV_NATIVE_MERGE_PATH, SPMV_BSR_V41, SPMV_BSR_V42, SPMV_BSR_TC };  // spmv_handle.hpp:33-48
 
 template <class Scalar, class Ordinal, class Dev, class MT, class Offset>
 class CrsMatrix {

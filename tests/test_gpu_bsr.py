@@ -97,6 +97,48 @@ def test_reference_sweep_multivector(cuda, oracle, bs, mb, nb, layout):
                     assert np.max(np.abs(got - exp), initial=0.0) <= tolerance(dtype, alpha, beta, max_row), (h.last_kernel(), mode, k, alpha, beta)
 
 
+@pytest.mark.parametrize("bs", [1, 2, 3, 4, 5, 7, 8, 11, 16, 17])
+@pytest.mark.parametrize("layout", ["left", "right"])
+def test_tensor_core_multivector(cuda, oracle, bs, layout):
+    """SPMV_BSR_TC (the reference's tensor-core functor, spmv_bsrmatrix_impl.hpp:74-459, selected by the handle's algorithm,
+    spmv_bsrmatrix_spec.hpp:176-245): mma.sync m8n8k4 kernel for double / mode N / bs <= 16, the default kernels otherwise."""
+    from kokkos_kernels_b200 import sparse as sp
+
+    dtype = np.float64
+    mb, nb = 300, 280
+    rp, ci, v = bsr_random(bs, mb, nb, seed=40 + bs, dtype=dtype, sort=False)
+    A = to_dev(sp, cuda, bs, nb, rp, ci, v)
+    rng = np.random.default_rng(29)
+    h = sp.SPMVHandle(sp.SPMV_BSR_TC)
+
+    def dev2d(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+        return t if layout == "right" else t.t().contiguous().t()
+
+    for mode in "NT":
+        trans = mode == "T"
+        nx, ny = (mb * bs, nb * bs) if trans else (nb * bs, mb * bs)
+        max_row = op_max_nnz_per_row(bs, rp, ci, nb, trans)
+        for k in (2, 8, 13, 16, 33):
+            X = rng.uniform(0, 10, (nx, k))
+            Y0 = rng.uniform(0, 10, (ny, k))
+            for alpha, beta in ((1.0, 0.0), (-2.5, 1.0), (3.7, -1.5)):
+                Yin = Y0.copy()
+                if beta == 0.0:
+                    Yin[::5] = np.nan
+                Yd = dev2d(Yin)
+                sp.spmv(h, mode, alpha, A, dev2d(X), beta, Yd)
+                torch.cuda.synchronize()
+                got = Yd.cpu().numpy()
+                exp = expected(oracle, mode, bs, nb, rp, ci, v, X, Yin, alpha, beta)
+                assert not np.isnan(got).any()
+                assert np.max(np.abs(got - exp), initial=0.0) <= tolerance(dtype, alpha, beta, max_row), (h.last_kernel(), mode, k, alpha, beta)
+                if mode == "N" and 2 <= bs <= 16:
+                    assert h.last_kernel().startswith("bsr_mm_tc<f64"), h.last_kernel()
+                else:
+                    assert not h.last_kernel().startswith("bsr_mm_tc"), h.last_kernel()
+
+
 @pytest.mark.parametrize("force", [None, "walk"])
 @pytest.mark.parametrize("bs", list(range(2, 18)))
 def test_tile_kernel_every_block_size(cuda, oracle, bs, force, monkeypatch):

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out/r02c8
-timeout 900 python -m pytest tests/test_gpu_spgemm_esc.py tests/test_gpu_spgemm.py tests/test_gpu_spmm.py -q -x > ${O}_pytest.log 2>&1; tail -n 3 ${O}_pytest.log
+timeout 1200 python -m pytest tests/test_gpu_spgemm_esc.py tests/test_gpu_spgemm.py tests/test_gpu_spmm.py tests/test_gpu_bsr.py tests/test_gpu_jacobi.py -q -x > ${O}_pytest.log 2>&1; tail -n 3 ${O}_pytest.log
 run_spgemm() {  # name, env...
   local name=$1; shift
   env "$@" timeout 300 python tools/bench_spgemm.py --reps 3 --out ${O}_spgemm_$name.json > ${O}_spgemm_$name.log 2>&1
@@ -20,6 +20,7 @@ for c in 8 4 0; do
   B200SP_SPMM_ITEM_COOP=$c timeout 300 python tools/bench_spmm.py --scale 23 --out ${O}_spmm_coop$c.json > ${O}_spmm_coop$c.log 2>&1
   echo "spmm coop=$c: $(grep "LayoutRight" ${O}_spmm_coop$c.log | cut -c1-200)"
 done
+timeout 300 python tools/bench_bsr_mm.py --out ${O}_bsr_mm.json > ${O}_bsr_mm.log 2>&1; grep -E "'bs'|max \|" ${O}_bsr_mm.log | cut -c1-230
 timeout 400 ncu --set full --import-source on --clock-control none -k 'regex:spmm_item_coop_kernel' -c 1 -f -o ${O}_spmm_coop \
     python tools/bench_spmm.py --scale 23 --out gpurun_out/scratch.json > ${O}_ncu_spmm.log 2>&1
 timeout 400 ncu --set full --import-source on --clock-control none -k 'regex:esc_(sym|num)_kernel' -c 2 -f -o ${O}_esc \
