@@ -298,6 +298,20 @@ def secondary_spmm(dev, scale=23, k=16, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    # the same product on LayoutLeft operands (the Kokkos default for a multivector in CudaSpace): relayout + kernel + relayout
+    Xl, Yl = Xd.t().contiguous().t(), torch.full((k, n), float("nan"), dtype=torch.float32, device=dev).t()
+    hl = sp.SPMVHandle()
+    for _ in range(2):
+        sp.spmv(hl, "N", 1.0, A, Xl, 0.0, Yl)
+    e0.record()
+    for _ in range(iters):
+        sp.spmv(hl, "N", 1.0, A, Xl, 0.0, Yl)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_left = e0.elapsed_time(e1) / iters
+    left_equal = bool(torch.equal(Yl, Yd))
+    kernel_left = hl.last_kernel()
+    del Xl, Yl, hl
     # parity: sampled rows vs the oracle's multivector loop (O4, spmv_impl.hpp:745-926), component-wise scaled error
     orc = oracle_lib.Oracle()
     Y = Yd.cpu().numpy()
@@ -355,6 +369,9 @@ def secondary_spmm(dev, scale=23, k=16, iters=10):
                    "baseline_config": "configs[2]", "kernel": h.last_kernel(), "parity_max_scaled_err_sampled_rows": worst,
                    "parity_rows_checked": int(len(rows))},
         "metric": "spmm_fp32_gflops", "value": round(2.0 * nnz * k / ms / 1e6, 1), "unit": "GFLOP/s", "ms": round(ms, 4), "dtype": "f32",
+        "layout_left": {"ms": round(ms_left, 4), "gflops": round(2.0 * nnz * k / ms_left / 1e6, 1), "kernel": kernel_left,
+                        "bits_equal_layout_right": left_equal,
+                        "note": "LayoutLeft X and Y (Kokkos' default in CudaSpace): both are relaid out inside the call"},
         "roofline": {"bound": "hbm", "achieved": round(balg / ms / 1e6, 1), "peak": peak, "unit": "GB/s", "frac": round(balg / ms / 1e6 / peak, 4),
                      "algorithmic_bytes_per_launch": balg, "gather_model_bytes": bgather,
                      "frac_gather_model": round(bgather / ms / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src},

@@ -370,12 +370,15 @@ int b200sp_bsr_spmm_f32_i32(b200sp_bsr_plan* plan, void* stream, char mode, int 
                             int64_t ldx, int x_row_major, float beta, float* Y, int64_t ldy, int y_row_major);
 /* Name of the kernel the plan's last call used; static storage (tests / bench). */
 const char* b200sp_bsr_last_kernel(const b200sp_bsr_plan* plan);
-/* The handle's algorithm (sparse/src/KokkosSparse_spmv_handle.hpp: SPMV_BSR_V41 / V42 / TC).  TENSOR_CORES selects, for
- * no-transpose multivector products in double and bs <= 16, the mma.sync m8n8k4 kernel -- what SPMV_BSR_TC selects in
- * the reference (sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:165-245, ..._impl.hpp:74-459: wmma fragments of the
- * same shape); every other call takes the default kernels, as the reference falls back when its functor is unavailable. */
+/* The handle's algorithm (sparse/src/KokkosSparse_spmv_handle.hpp: SPMV_BSR_V41 / V42 / TC).  For no-transpose multivector
+ * products in double with 2 <= bs <= 16 there are two kernels: the mma.sync m8n8k4 kernel -- what SPMV_BSR_TC selects in the
+ * reference (sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:165-245, ..._impl.hpp:74-459: wmma fragments of the same
+ * shape) -- and a scalar one.  DEFAULT picks the tensor-core kernel from 4 columns on (measured 3-14x faster on a B200),
+ * TENSOR_CORES always, SCALAR never (SPMV_BSR_V41 / V42 requests); every other call takes the default kernels, as the
+ * reference falls back when its functor is unavailable. */
 #define B200SP_BSR_ALGO_DEFAULT 0
 #define B200SP_BSR_ALGO_TENSOR_CORES 1
+#define B200SP_BSR_ALGO_SCALAR 2
 int b200sp_bsr_plan_set_algorithm(b200sp_bsr_plan* plan, int algo);
 
 /* ---- point Gauss-Seidel (the preconditioner of the reference's CG driver) ---------------------

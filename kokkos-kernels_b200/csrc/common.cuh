@@ -109,6 +109,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+// per-thread asynchronous copies (cp.async): the emulation copies at issue time
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, BYTES); }
+__device__ __forceinline__ void cp_async_wait_all() {}
 template <typename T>
 __device__ __forceinline__ T ldg(const T* p) {
   return *p;
@@ -170,6 +174,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// per-thread asynchronous copy global -> shared of 4 / 8 / 16 bytes (SASS LDGSTS): no destination register is held while the
+// load is in flight; completion by cp_async_wait_all() in the issuing thread, visibility to others by a barrier after it
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

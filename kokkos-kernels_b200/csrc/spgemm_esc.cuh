@@ -237,106 +237,155 @@ __device__ __forceinline__ int esc_stage_row(int a0, int nA, int f, const int* _
 }
 
 // ---- row pipeline of the persistent kernels -------------------------------------------------------------------------
-// A CTA works through the rows r = blockIdx.x, blockIdx.x + gridDim.x, ... of its bin.  What a row needs before its
-// first gather is a chain of four dependent global loads (row list -> row header -> A's columns -> B's row
-// pointers): ~3 us that a one-row-per-CTA launch pays once per row (ncu capture r02c6: 40-60 % of all stall samples
-// of both kernels sit on that chain and on the barrier behind it).  Warp 0 therefore runs the chain as a software
-// pipeline in registers, one stage per row built: while row r is built, the B row pointers of row r+G, the A entries
-// of row r+2G, the header of row r+3G and the list entry of row r+4G are in flight, and nothing is waited for at the
-// top of a row.  A header travels as a lane-distributed vector --
-//   lane 0: rpA[i]  1: rpA[i+1]  2: flops[i]  3: rpC[i]  4: rpC[i+1]  5: cmin[i]  6: cmax[i]  7: i (or -1: no row)
-// -- one register per stage.  Rows of more than 32 entries of A are pipelined up to their header only
-// (esc_stage_row stages them when their turn comes).
+// A CTA works through the rows r = blockIdx.x, blockIdx.x + gridDim.x, ... of its bin ("sequence" k = 0, 1, ...).  What a
+// row needs before its first gather is a chain of four dependent global loads (row list -> row header -> A's columns ->
+// B's row pointers): ~3 us that a one-row-per-CTA launch pays once per row (ncu capture r02c6: 40-60 % of all stall
+// samples of both kernels sit on that chain and on the barrier behind it).  The chain therefore runs as a software
+// pipeline, one stage per row built: at the top of row k the B row pointers of row k+1, the A entries of row k+2, the
+// header of row k+3 and the list entry of row k+4 are requested, each from what the previous row's requests brought.
+// The requests are cp.async copies global -> shared memory (LDGSTS): no register is held while they are in flight.
+// (A first version kept the stages in registers of warp 0; under the kernels' register budget they were spilled, a spilled
+// destination of a load in flight waits for the load at the spill store, the reloads missed L1 -- the pipeline ran slower
+// than the chain it replaced: ncu r02c8.)  The four jobs of a step touch disjoint state, so four different warps do them
+// concurrently; every thread waits for its own copies at the END of the row, and the end-of-row barrier publishes them.
+//   list     row index of sequence k+3 (or -1)
+//   hdr[4]   ring of headers by sequence & 3:  0: rpA[i]  1: rpA[i+1]  2: flops[i]  3: rpC[i]  4: rpC[i+1]  5: cmin[i]
+//                                              6: cmax[i]  7: i (or -1: no row)
+//   c[2], b0[2], b1[2]   A's columns / the start and end of their B rows, by sequence & 1 (rows of <= 32 entries of A)
+//   va[4]    A's values by sequence & 3
+// Rows of more than 32 entries of A are pipelined up to their header only (esc_stage_row stages them).
 template <typename S, bool WITH_VALS>
-struct EscRowPipe {
-  int i3, h2, h1, c1, h0, b0, b1, rn;
-  S va1, va0;
-  __device__ __forceinline__ void init(int first) {
-    i3 = -1;
-    h2 = h1 = h0 = ((threadIdx.x & 31) == 7) ? -1 : 0;
-    c1 = b0 = b1 = 0;
-    va1 = va0 = S(0);
-    rn = first;
+struct EscPipeMem {
+  int list[4];
+  int hdr[4][8];
+  int c[2][32];
+  int b0[2][32];
+  int b1[2][32];
+  S va[WITH_VALS ? 4 : 1][32];
+};
+
+template <typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_init(EscPipeMem<S, WITH_VALS>& pm) {  // all threads; followed by a barrier
+  const int t = threadIdx.x;
+  if (t < 32) pm.hdr[t >> 3][t & 7] = ((t & 7) == 7) ? -1 : 0;
+  if (t == 0) pm.list[0] = -1;
+}
+
+// job A (one warp): header of sequence k+3 from the list entry that arrived, list entry of sequence k+4
+template <typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_headers(EscPipeMem<S, WITH_VALS>& pm, int k, int nrows, int G,
+                                                 const int* __restrict__ rows, const int* __restrict__ rpA,
+                                                 const int* __restrict__ flops, const int* __restrict__ rpC,
+                                                 const int* __restrict__ cmin, const int* __restrict__ cmax) {
+  const int lane = threadIdx.x & 31;
+  const int i = pm.list[0];
+  __syncwarp();  // every lane has read the entry before lane 0 requests the next one into its place
+  int* h = pm.hdr[(k + 3) & 3];
+  if (lane < 8) {
+    const int* src = nullptr;
+    if (i >= 0) {
+      switch (lane) {
+        case 0: src = rpA + i; break;
+        case 1: src = rpA + i + 1; break;
+        case 2: src = flops + i; break;
+        case 3: src = rpC ? rpC + i : nullptr; break;
+        case 4: src = rpC ? rpC + i + 1 : nullptr; break;
+        case 5: src = cmin + i; break;
+        case 6: src = cmax + i; break;
+        default: break;
+      }
+    }
+    if (src) cp_async<4>(&h[lane], src);
+    else h[lane] = (lane == 7) ? i : 0;
   }
-  // advance every stage by one row and issue the loads of the new occupants (warp 0, all 32 lanes)
-  __device__ __forceinline__ void pump(int nrows, int G, const int* __restrict__ rows, const int* __restrict__ rpA,
-                                       const int* __restrict__ ciA, const S* __restrict__ vA, const int* __restrict__ rpB,
-                                       const int* __restrict__ flops, const int* __restrict__ rpC,
-                                       const int* __restrict__ cmin, const int* __restrict__ cmax) {
-    const int lane = threadIdx.x & 31;
-    {  // stage 0 <- 1: the B row of A's entry `lane`
-      h0 = h1;
-      va0 = va1;
-      const int a0 = __shfl_sync(0xffffffffu, h1, 0);
-      const int nA = __shfl_sync(0xffffffffu, h1, 1) - a0;
-      b0 = b1 = 0;
-      if (nA <= 32 && lane < nA) {
-        b0 = ldg(rpB + c1);
-        b1 = ldg(rpB + c1 + 1);
-      }
-    }
-    {  // stage 1 <- 2: A's entries
-      h1 = h2;
-      const int a0 = __shfl_sync(0xffffffffu, h2, 0);
-      const int nA = __shfl_sync(0xffffffffu, h2, 1) - a0;
-      c1 = 0;
-      va1 = S(0);
-      if (nA <= 32 && lane < nA) {
-        c1 = ldg(ciA + a0 + lane);
-        if (WITH_VALS) va1 = ldg(vA + a0 + lane);
-      }
-    }
-    {  // stage 2 <- 3: the header of row i3
-      const int i = i3;
-      h2 = (lane == 7) ? i : 0;
-      if (i >= 0) {
-        const int* src = nullptr;
-        switch (lane) {
-          case 0: src = rpA + i; break;
-          case 1: src = rpA + i + 1; break;
-          case 2: src = flops + i; break;
-          case 3: src = rpC ? rpC + i : nullptr; break;
-          case 4: src = rpC ? rpC + i + 1 : nullptr; break;
-          case 5: src = cmin + i; break;
-          case 6: src = cmax + i; break;
-          default: break;
-        }
-        if (src) h2 = ldg(src);
-      }
-    }
-    i3 = rn < nrows ? ldg(rows + rn) : -1;  // stage 3
-    rn += G;
+  if (lane == 0) {
+    const long long pos = (long long)blockIdx.x + (long long)(k + 4) * (long long)G;
+    if (pos < (long long)nrows) cp_async<4>(&pm.list[0], rows + pos);
+    else pm.list[0] = -1;
   }
-  // stage 0 -> shared memory (warp 0): the header, and for a row of <= 32 entries of A the staging arrays of
-  // esc_stage_row (bs, pre, va, the uniform-length flag).  The loads were issued one row ago.
-  __device__ __forceinline__ void publish(int* shdr, int* bs, int* pre, S* va, int* wsum) const {
-    const int lane = threadIdx.x & 31;
-    if (lane < 8) shdr[lane] = h0;
-    const int a0 = __shfl_sync(0xffffffffu, h0, 0);
-    const int nA = __shfl_sync(0xffffffffu, h0, 1) - a0;
-    const int f = __shfl_sync(0xffffffffu, h0, 2);
-    if (nA > 32) return;
-    int len = 0;
-    if (lane < nA) {
-      len = b1 - b0;
-      bs[lane] = b0;
-      if (WITH_VALS) va[lane] = va0;
-    }
-    const int len0 = __shfl_sync(0xffffffffu, len, 0);
-    const bool uni = __all_sync(0xffffffffu, lane >= nA || len == len0) != 0;
-    int inc = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane < nA) pre[lane] = inc - len;
+}
+
+// job B (one warp): A's entries of sequence k+2
+template <typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_aentries(EscPipeMem<S, WITH_VALS>& pm, int k, const int* __restrict__ ciA,
+                                                  const S* __restrict__ vA) {
+  const int lane = threadIdx.x & 31;
+  const int* h = pm.hdr[(k + 2) & 3];
+  const int a0 = h[0], nA = h[1] - a0;
+  if (nA <= 32 && lane < nA) {
+    cp_async<4>(&pm.c[(k + 2) & 1][lane], ciA + a0 + lane);
+    if (WITH_VALS) cp_async<(int)sizeof(S)>(&pm.va[WITH_VALS ? ((k + 2) & 3) : 0][lane], vA + a0 + lane);
+  }
+}
+
+// job C (one warp): start and end of the B rows of sequence k+1
+template <typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_bptrs(EscPipeMem<S, WITH_VALS>& pm, int k, const int* __restrict__ rpB) {
+  const int lane = threadIdx.x & 31;
+  const int* h = pm.hdr[(k + 1) & 3];
+  const int nA = h[1] - h[0];
+  if (nA <= 32 && lane < nA) {
+    const int c = pm.c[(k + 1) & 1][lane];
+    cp_async<4>(&pm.b0[(k + 1) & 1][lane], rpB + c);
+    cp_async<4>(&pm.b1[(k + 1) & 1][lane], rpB + c + 1);
+  }
+}
+
+// job D (one warp): sequence k -> the header and, for a row of <= 32 entries of A, the staging arrays of esc_stage_row
+// (bs, pre, va, the uniform-length flag wsum[35]) the CTA builds the row from
+template <typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_publish(const EscPipeMem<S, WITH_VALS>& pm, int k, int* shdr, int* bs, int* pre, S* va,
+                                                 int* wsum) {
+  const int lane = threadIdx.x & 31;
+  const int* h = pm.hdr[k & 3];
+  if (lane < 8) shdr[lane] = h[lane];
+  const int nA = h[1] - h[0];
+  const int f = h[2];
+  if (nA > 32) return;
+  int len = 0;
+  if (lane < nA) {
+    const int b0 = pm.b0[k & 1][lane];
+    len = pm.b1[k & 1][lane] - b0;
+    bs[lane] = b0;
+    if (WITH_VALS) va[lane] = pm.va[WITH_VALS ? (k & 3) : 0][lane];
+  }
+  const int len0 = __shfl_sync(0xffffffffu, len, 0);
+  const bool uni = __all_sync(0xffffffffu, lane >= nA || len == len0) != 0;
+  if (uni && len0 > 0) {  // (the regular case needs no scan)
+    if (lane < nA) pre[lane] = lane * len0;
     if (lane == 0) {
       pre[nA] = f;
-      wsum[35] = (uni && len0 > 0) ? len0 : 0;
+      wsum[35] = len0;
     }
+    return;
   }
-};
+  int inc = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane < nA) pre[lane] = inc - len;
+  if (lane == 0) {
+    pre[nA] = f;
+    wsum[35] = 0;
+  }
+}
+
+// one step of the pipeline at the top of sequence k (k < 0: the prologue), jobs dealt to warps 0..3 (or fewer)
+template <int T, typename S, bool WITH_VALS>
+__device__ __forceinline__ void esc_pipe_step(EscPipeMem<S, WITH_VALS>& pm, int k, int nrows, int G, const int* __restrict__ rows,
+                                              const int* __restrict__ rpA, const int* __restrict__ ciA, const S* __restrict__ vA,
+                                              const int* __restrict__ rpB, const int* __restrict__ flops,
+                                              const int* __restrict__ rpC, const int* __restrict__ cmin,
+                                              const int* __restrict__ cmax, int* shdr, int* bs, int* pre, S* va, int* wsum) {
+  constexpr int NW = T / 32;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 % NW && k >= 0) esc_pipe_publish<S, WITH_VALS>(pm, k, shdr, bs, pre, va, wsum);
+  if (warp == 1 % NW) esc_pipe_bptrs<S, WITH_VALS>(pm, k, rpB);
+  if (warp == 2 % NW) esc_pipe_aentries<S, WITH_VALS>(pm, k, ciA, vA);
+  if (warp == 3 % NW) esc_pipe_headers<S, WITH_VALS>(pm, k, nrows, G, rows, rpA, flops, rpC, cmin, cmax);
+}
 
 // ---- the products of this thread: columns (and values) in registers ------------------------------------------------
 template <int T, int I, typename S, bool WITH_VALS>
@@ -450,8 +499,8 @@ struct EscSymLayout {
   static constexpr int SORTW = NB + 4 + CAP + 8;         // off[NB + 4] | skey[CAP] of the fallback, aliased with the bitmap
   static constexpr int REGW = BMW > SORTW ? BMW : SORTW;
   static constexpr int SUSCAP = 64;
-  // region[REGW] | bs[NA] | pre[NA + 4] | wsum[36] | sus_n[4] | sus_col[SUSCAP] | sus_dup[SUSCAP] | shdr[8]
-  static constexpr size_t BYTES = sizeof(int) * (size_t)(REGW + NA + NA + 4 + 36 + 4 + 2 * SUSCAP + 8);
+  // region[REGW] | bs[NA] | pre[NA + 4] | wsum[36] | sus_n[4] | sus_col[SUSCAP] | sus_dup[SUSCAP] | shdr[8] | pipeline state
+  static constexpr size_t BYTES = sizeof(int) * (size_t)(REGW + NA + NA + 4 + 36 + 4 + 2 * SUSCAP + 8) + sizeof(EscPipeMem<float, false>);
   static_assert(BYTES <= 227 * 1024, "esc_sym_kernel: configuration exceeds the shared memory of an SM");
 };
 
@@ -573,16 +622,21 @@ __global__ void __launch_bounds__(T, MINB)
   int* sus_col = sus_n + 4;
   int* sus_dup = sus_col + SUSCAP;
   int* shdr = sus_dup + SUSCAP;
+  auto& pm = *reinterpret_cast<EscPipeMem<float, false>*>(shdr + 8);
   const int tid = threadIdx.x;
   const int G = (int)gridDim.x;
-  EscRowPipe<float, false> pipe;
-  if (tid < 32) {
-    pipe.init((int)blockIdx.x);
+  esc_pipe_init(pm);
+  __syncthreads();
 #pragma unroll 1
-    for (int s = 0; s < 4; ++s) pipe.pump(nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr);
+  for (int k = -4; k < 0; ++k) {
+    esc_pipe_step<T, float, false>(pm, k, nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr,
+                                   shdr, bs, pre, (float*)nullptr, wsum);
+    cp_async_wait_all();
+    __syncthreads();
   }
+  int k = 0;
 #pragma unroll 1
-  for (int r = (int)blockIdx.x; r < nrows_bin; r += G) {
+  for (int r = (int)blockIdx.x; r < nrows_bin; r += G, ++k) {
     {
       int4* b4 = reinterpret_cast<int4*>(region);
       for (int s = tid; s < L::BMW / 4; s += T) b4[s] = make_int4(0, 0, 0, 0);
@@ -591,13 +645,12 @@ __global__ void __launch_bounds__(T, MINB)
       if (T < SUSCAP)
         for (int s = tid + T; s < SUSCAP; s += T) sus_dup[s] = 0;
     }
-    if (tid < 32) {
-      pipe.publish(shdr, bs, pre, (float*)nullptr, wsum);
-      pipe.pump(nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr);
-    }
+    esc_pipe_step<T, float, false>(pm, k, nrows_bin, G, rows, rpA, ciA, (const float*)nullptr, rpB, flops, nullptr, cmin_arr, cmax_arr,
+                                   shdr, bs, pre, (float*)nullptr, wsum);
     __syncthreads();
     esc_sym_row<T, I, LOG2NB>(region, bs, pre, wsum, sus_n, sus_col, sus_dup, shdr, ciA, rpB, ciB, row_nnz);
-    __syncthreads();  // the next row reuses every array
+    cp_async_wait_all();  // this thread's requests of the step above have had the whole row to arrive
+    __syncthreads();      // ... and are visible to every warp; the next row reuses every array
   }
 }
 
@@ -619,7 +672,8 @@ struct EscNumLayout {
   static constexpr size_t STAGE_BYTES = sizeof(int) * (size_t)(NA + NA + 4) + sizeof(S) * (size_t)NA;
   static constexpr size_t SORT_BYTES = sizeof(KV) * (size_t)CAP;
   static constexpr size_t UNION_BYTES = ((STAGE_BYTES > SORT_BYTES ? STAGE_BYTES : SORT_BYTES) + 15) & ~(size_t)15;
-  static constexpr size_t BYTES = OFF_BYTES + KEY_BYTES + WS_BYTES + ORD_BYTES + UNION_BYTES;
+  static constexpr size_t PIPE_BYTES = (sizeof(EscPipeMem<S, true>) + 15) & ~(size_t)15;
+  static constexpr size_t BYTES = OFF_BYTES + KEY_BYTES + WS_BYTES + ORD_BYTES + UNION_BYTES + PIPE_BYTES;
   static_assert(BYTES <= 227 * 1024, "esc_num_kernel: configuration exceeds the shared memory of an SM");
 };
 
@@ -791,27 +845,29 @@ __global__ void __launch_bounds__(T, MINB)
   S* va = reinterpret_cast<S*>(un);
   int* bs = reinterpret_cast<int*>(un + sizeof(S) * (size_t)L::NA);
   int* pre = bs + L::NA;
+  auto& pm = *reinterpret_cast<EscPipeMem<S, true>*>(esc_raw + L::OFF_BYTES + L::KEY_BYTES + L::WS_BYTES + L::ORD_BYTES + L::UNION_BYTES);
   const int tid = threadIdx.x;
   const int G = (int)gridDim.x;
-  EscRowPipe<S, true> pipe;
-  if (tid < 32) {
-    pipe.init((int)blockIdx.x);
+  esc_pipe_init(pm);
+  __syncthreads();
 #pragma unroll 1
-    for (int s = 0; s < 4; ++s) pipe.pump(nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr);
+  for (int k = -4; k < 0; ++k) {
+    esc_pipe_step<T, S, true>(pm, k, nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr, shdr, bs, pre, va, wsum);
+    cp_async_wait_all();
+    __syncthreads();
   }
+  int k = 0;
 #pragma unroll 1
-  for (int r = (int)blockIdx.x; r < nrows_bin; r += G) {
+  for (int r = (int)blockIdx.x; r < nrows_bin; r += G, ++k) {
     {
       int4* o4 = reinterpret_cast<int4*>(off);
       for (int s = tid; s < (NB + 4) / 4; s += T) o4[s] = make_int4(0, 0, 0, 0);
     }
-    if (tid < 32) {
-      pipe.publish(shdr, bs, pre, va, wsum);
-      pipe.pump(nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr);
-    }
+    esc_pipe_step<T, S, true>(pm, k, nrows_bin, G, rows, rpA, ciA, vA, rpB, flops, rpC, cmin_arr, cmax_arr, shdr, bs, pre, va, wsum);
     __syncthreads();
     esc_num_row<S, T, I, LOG2NB>(esc_raw, shdr, ciA, vA, rpB, ciB, vB, ciC, vC);
-    __syncthreads();  // the next row's staging arrays alias the sorted pairs
+    cp_async_wait_all();  // this thread's requests of the step above have had the whole row to arrive
+    __syncthreads();      // ... and are visible to every warp; the next row's staging arrays alias the sorted pairs
   }
 }
 

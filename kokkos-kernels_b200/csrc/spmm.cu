@@ -1091,7 +1091,8 @@ __global__ void __launch_bounds__(256)
 // nonzero at 8 groups per warp, and the kernel is bound by exactly that (one wavefront per SM and clock).  Here the
 // group reads a batch of EB consecutive entries with ONE load per lane (adjacent lanes, adjacent entries: the group's
 // EB/KTL loads cover a contiguous 32..64-byte run) and passes them round with shuffles, which run on a different
-// pipe: 1 + 2 * 4/32 wavefronts per nonzero for k = 16 fp32, with EB = 8 gathers of X in flight per lane.
+// pipe: 1 + 2 * 4/32 wavefronts per nonzero for k = 16 fp32, with EB gathers of X in flight per lane (EB = 4: 40 registers,
+// 6 CTAs per SM; EB = 8: 80 registers, 3 CTAs -- the same number of gathers in flight per SM, and 4 measured faster).
 template <typename S, int VW, int KTL, int EB /* entries per batch: 4 or 8 */>
 __global__ void __launch_bounds__(256)
     spmm_item_coop_kernel(int n_items, const int4* __restrict__ items, int k, const int* __restrict__ col_idx,
@@ -1260,9 +1261,9 @@ static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m
   const int64_t threads = (int64_t)mi->n_items * KTL;
   const unsigned grid = (unsigned)((threads + 255) / 256);
   if (grid > 0) {
-    static const int coop = [] {  // B200SP_SPMM_ITEM_COOP=0: every lane reads (col, val) itself (the first item kernel); 4 | 8: batch
+    static const int coop = [] {  // B200SP_SPMM_ITEM_COOP=0: every lane reads (col, val) itself (the first item kernel); 4 (default) | 8: batch
       const char* e = getenv("B200SP_SPMM_ITEM_COOP");
-      return e && e[0] == '0' ? 0 : (e && e[0] == '4' ? 4 : 8);
+      return e && e[0] == '0' ? 0 : (e && e[0] == '8' ? 8 : 4);  // measured on R-MAT scale 23 x 16: 2.27 (4), 2.49 (8), 2.95 ms (0)
     }();
 #define B200SP_MMI(V, L)                                                                                                   \
   case L:                                                                                                                  \

@@ -141,8 +141,11 @@ class SPMVHandle:
     def _bsr(self):
         if not self._bsr_plan:
             check(_lib.sparse().b200sp_bsr_plan_create(C.byref(self._bsr_plan)))
-            if self.algo == SPMV_BSR_TC:  # spmv_bsrmatrix_spec.hpp:176-177: tensor cores only when the handle asks for them
-                check(_lib.sparse().b200sp_bsr_plan_set_algorithm(self._bsr_plan, 1))
+            # spmv_bsrmatrix_spec.hpp:176-177: SPMV_BSR_TC asks for tensor cores, V41 / V42 for the scalar functors; the
+            # library's default uses tensor cores where they are faster
+            a = {SPMV_BSR_TC: 1, SPMV_BSR_V41: 2, SPMV_BSR_V42: 2}.get(self.algo, 0)
+            if a:
+                check(_lib.sparse().b200sp_bsr_plan_set_algorithm(self._bsr_plan, a))
         return self._bsr_plan
 
     def get_algorithm(self):

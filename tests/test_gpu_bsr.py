@@ -137,6 +137,17 @@ def test_tensor_core_multivector(cuda, oracle, bs, layout):
                     assert h.last_kernel().startswith("bsr_mm_tc<f64"), h.last_kernel()
                 else:
                     assert not h.last_kernel().startswith("bsr_mm_tc"), h.last_kernel()
+    # the scalar functors on request (SPMV_BSR_V42), the default's choice by the number of columns
+    for algo, k, tc in ((sp.SPMV_BSR_V42, 8, False), (sp.SPMV_DEFAULT, 8, True), (sp.SPMV_DEFAULT, 3, False)):
+        h2 = sp.SPMVHandle(algo)
+        X = rng.uniform(0, 10, (nb * bs, k))
+        Yin = rng.uniform(0, 10, (mb * bs, k))
+        Yd = dev2d(Yin)
+        sp.spmv(h2, "N", 1.5, A, dev2d(X), -0.5, Yd)
+        torch.cuda.synchronize()
+        exp = expected(oracle, "N", bs, nb, rp, ci, v, X, Yin, 1.5, -0.5)
+        assert np.max(np.abs(Yd.cpu().numpy() - exp), initial=0.0) <= tolerance(dtype, 1.5, -0.5, op_max_nnz_per_row(bs, rp, ci, nb, False))
+        assert h2.last_kernel().startswith("bsr_mm_tc") == (tc and 2 <= bs <= 16), (h2.last_kernel(), algo, k)
 
 
 @pytest.mark.parametrize("force", [None, "walk"])

@@ -39,7 +39,7 @@ def main():
         outs = {}
         for layout in ("right", "left"):
             Xd = X if layout == "right" else X.t().contiguous().t()
-            for algo, name in ((sp.SPMV_DEFAULT, "default"), (sp.SPMV_BSR_TC, "tensor_cores")):
+            for algo, name in ((sp.SPMV_BSR_V42, "default"), (sp.SPMV_BSR_TC, "tensor_cores")):  # "default" = the scalar kernel (V42 request)
                 h = sp.SPMVHandle(algo)
                 Yd = torch.zeros((mb * bs, k), dtype=torch.float64, device=dev)
                 if layout == "left":
