@@ -1218,20 +1218,36 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// rows of several pieces: Y(row, :) = beta * Y(row, :) + alpha * (piece 0 + piece 1 + ...), pieces added in order
+// rows of several pieces: Y(row, :) = beta * Y(row, :) + alpha * (sum of the pieces).  One WARP per row: the lanes are
+// KC columns x 32/KC interleaved piece subsequences (k = 16: lane = (piece parity, column)); a lane adds its subsequence in
+// piece order, a fixed xor tree joins the subsequences -- the order of additions depends on the row alone, so the result is
+// reproducible run to run.  (One thread per (row, column) made the longest row of R-MAT scale 23, 2388 pieces, a 0.5 ms tail:
+// 20 % of the whole product, profiles/r02c9_spmm_launches.csv.)
 template <typename S>
 __global__ void __launch_bounds__(256)
     spmm_item_reduce_kernel(int n_multi, const int4* __restrict__ multi, int k, const S* __restrict__ partial, S* __restrict__ Y,
                             int64_t ldy, S alpha, S beta) {
-  const int64_t total = (int64_t)n_multi * k;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int4 d = multi[i / k];
-    const int j = (int)(i % k);
-    const S* src = partial + (int64_t)d.y * k + j;
-    S sum = S(0);
-    for (int s = 0; s < d.z; ++s) sum += src[(int64_t)s * k];
-    S* yp = Y + (int64_t)d.x * ldy + j;
-    *yp = (beta == S(0)) ? alpha * sum : beta * *yp + alpha * sum;
+  const int lane = threadIdx.x & 31;
+  int KC = 1;
+  while (KC < k && KC < 32) KC <<= 1;
+  const int SUB = 32 / KC;
+  const int j0 = lane % KC, sub = lane / KC;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_multi; w += warps) {
+    const int4 d = multi[w];  // (row, first partial slot, pieces, 0)
+    for (int jb = 0; jb < k; jb += KC) {
+      const int j = jb + j0;
+      S sum = S(0);
+      if (j < k) {
+        const S* src = partial + (int64_t)d.y * k + j;
+        for (int s = sub; s < d.z; s += SUB) sum += src[(int64_t)s * k];
+      }
+      for (int o = 16; o >= KC; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (sub == 0 && j < k) {
+        S* yp = Y + (int64_t)d.x * ldy + j;
+        *yp = (beta == S(0)) ? alpha * sum : beta * *yp + alpha * sum;
+      }
+    }
   }
 }
 
@@ -1286,7 +1302,7 @@ static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m
     B200SP_LAUNCH_CHECK();
   }
   if (mi->n_multi > 0) {
-    const int g = (int)std::min<int64_t>(((int64_t)mi->n_multi * k + 255) / 256, (int64_t)sm_count() * 8);
+    const int g = (int)std::min<int64_t>(((int64_t)mi->n_multi + 7) / 8, (int64_t)sm_count() * 16);  // a warp per row
     spmm_item_reduce_kernel<S><<<std::max(g, 1), 256, 0, st>>>(mi->n_multi, mi->multi, k, (const S*)mi->partial, Y, ldy, alpha, beta);
     B200SP_LAUNCH_CHECK();
   }
