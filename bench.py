@@ -526,7 +526,7 @@ def main():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the configs[2] / configs[3] workloads")
     ap.add_argument("--collective", default="auto",
-                    choices=["auto", "pipelined", "pipelined_mc", "pipelined_sm", "fused", "multicast", "nccl"],
+                    choices=["auto", "pipelined", "pipelined_mc", "pipelined_sm", "fused", "multicast", "multicast_fwd", "nccl"],
                     help="N>1: how y is all-gathered into the next x.  auto = time every transport on this box during warm-up and "
                          "keep the fastest: pushes of finished pieces behind the compute by copy engines (pipelined), by a small SM "
                          "kernel to the NVSwitch multicast address (pipelined_mc) or to the 7 peers (pipelined_sm), stores from the "
@@ -598,7 +598,7 @@ def main():
     if world > 1:
         from kokkos_kernels_b200 import multigpu
 
-        cands = ["pipelined_mc", "pipelined_sm", "pipelined", "multicast", "nccl"] if args.collective == "auto" else [args.collective]
+        cands = ["multicast_fwd", "pipelined_mc", "pipelined_sm", "pipelined", "multicast", "nccl"] if args.collective == "auto" else [args.collective]
         ops = {}
         first = None
         for mode in cands:

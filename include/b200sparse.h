@@ -161,6 +161,16 @@ int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* plan, void* stream, int m, int
                                 const int* row_ptr, const int* col_idx, const double* vals, const double* x,
                                 double* y, int n_extra, void* const* y_extra);
 
+/* The same product with ONE further destination fed tile by tile: the kernel's producer warp (the one that streams the matrix
+ * with TMA) copies every finished tile of y from the local slice to `y_forward` (same indexing as y) with coalesced stores --
+ * 256 contiguous bytes per instruction instead of one 8-byte store per row.  Meant for the NVSwitch multicast mapping of the
+ * symmetric next-x buffer: every y value leaves the GPU once, in whole 128-byte NVLink writes, while the rest of the shard is
+ * still being computed (multigpu.py mode "multicast_fwd").  Rows the tiled kernel leaves to its helper kernels are stored to
+ * y_forward by those.  Results identical to b200sp_spmv_f64_i32. */
+int b200sp_spmv_forward_f64_i32(b200sp_spmv_plan* plan, void* stream, int m, int n, int64_t nnz, double alpha,
+                                const int* row_ptr, const int* col_idx, const double* vals, const double* x,
+                                double* y, void* y_forward);
+
 /* Copy `bytes` from device pointer src to n_dst device pointers (peer GPUs' buffers mapped into this
  * process) with copy-engine transfers on `stream` -- the push half of the pipelined row-block SpMV
  * (kokkos-kernels_b200/multigpu.py): chunk c of y is pushed over NVLink while chunk c+1 is computed. */

@@ -41,6 +41,7 @@ SPARSE_API = {
     "b200sp_spmm_f64_i64": (i32, [vp, vp, cp, i64, i64, i64, i32, f64, vp, vp, i32, vp, vp, i64, i32, f64, vp, i64, i32]),
     "b200sp_spmm_f32_i64": (i32, [vp, vp, cp, i64, i64, i64, i32, f32, vp, vp, i32, vp, vp, i64, i32, f32, vp, i64, i32]),
     "b200sp_spmv_scatter_f64_i32": (i32, [vp, vp, i32, i32, i64, f64, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]),
+    "b200sp_spmv_forward_f64_i32": (i32, [vp, vp, i32, i32, i64, f64, vp, vp, vp, vp, vp, vp]),
     "b200sp_spmv_plan_invalidate": (i32, [vp, vp]),
     "b200sp_peer_push": (i32, [vp, vp, i64, i32, C.POINTER(vp)]),
     "b200sp_peer_push_async": (i32, [vp, C.POINTER(vp), i32, C.POINTER(vp), vp, i64]),

@@ -61,7 +61,8 @@ struct EscKV<float> {
 
 // exclusive scan in place of a[0..n), n <= T*K, thread t owns a[t*K .. t*K+K); every thread gets the total.
 // wsum: 34 ints of shared memory.  Ends with a barrier (a[] and the total are visible to all).
-template <int T, int K>
+// PACK: the result word is prefix | (count << 16) (both < 65536 here): one shared-memory read per look-up instead of two.
+template <int T, int K, bool PACK = false>
 __device__ __forceinline__ int esc_block_scan(int* a, int n, int* wsum) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   constexpr int NW = T / 32;
@@ -115,16 +116,16 @@ __device__ __forceinline__ int esc_block_scan(int* a, int n, int* wsum) {
 #pragma unroll
     for (int c = 0; c < K / 4; ++c) {
       int4 q;
-      q.x = run; run += v[4 * c];
-      q.y = run; run += v[4 * c + 1];
-      q.z = run; run += v[4 * c + 2];
-      q.w = run; run += v[4 * c + 3];
+      q.x = PACK ? (run | (v[4 * c] << 16)) : run; run += v[4 * c];
+      q.y = PACK ? (run | (v[4 * c + 1] << 16)) : run; run += v[4 * c + 1];
+      q.z = PACK ? (run | (v[4 * c + 2] << 16)) : run; run += v[4 * c + 2];
+      q.w = PACK ? (run | (v[4 * c + 3] << 16)) : run; run += v[4 * c + 3];
       reinterpret_cast<int4*>(a + base)[c] = q;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      if (base + i < n) a[base + i] = run;
+      if (base + i < n) a[base + i] = PACK ? (run | (v[i] << 16)) : run;
       run += v[i];
     }
   }
@@ -463,18 +464,16 @@ __device__ __forceinline__ void esc_bucket_sort(int f, int cmin, long long span,
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) off[NB] = f;  // outside the scanned range; published by the scan's closing barrier
-  esc_block_scan<T, NB / T>(off, NB, wsum);
+  esc_block_scan<T, NB / T, true>(off, NB, wsum);  // off[b] = first position of bucket b | (members << 16)
 #pragma unroll
   for (int k = 0; k < I; ++k) {
     lc[k] = 0;
     if (col[k] != nokey) {
-      const int b = pos[k] & (NB - 1);
-      const int lo = off[b], hi = off[b + 1];
-      const int p0 = lo + (pos[k] >> LOG2NB);
+      const int w = off[pos[k] & (NB - 1)];
+      const int p0 = (w & 0xffff) + (pos[k] >> LOG2NB);
       skey[p0] = col[k];
       pos[k] = p0;
-      lc[k] = lo | ((hi - lo) << 16);
+      lc[k] = w;
     }
   }
   __syncthreads();

@@ -97,13 +97,25 @@ struct YExtra {
   int n;
 };
 
-template <typename S>
+// ex.n > 0: every value is also stored to ex.n further destinations (P2P mappings of the peers' buffers, or one NVSwitch
+// multicast mapping).  ex.n < 0 ("forward"): ONE further destination, ex.p[0]; the tiled kernel then forwards whole finished
+// tiles from its producer warp (TILE_FORWARDS = true: nothing to do here), every other kernel stores the value itself.
+template <typename S, bool TILE_FORWARDS = false>
 __device__ __forceinline__ void store_y(S* __restrict__ y, int r, S sum, S alpha, S beta, const YExtra& ex) {
   // reference epilogue (spmv_impl.hpp:124-131): sum *= alpha; y = beta*y + sum
   sum *= alpha;
   const S v = (beta == S(0)) ? sum : beta * y[r] + sum;
   y[r] = v;
   for (int d = 0; d < ex.n; ++d) static_cast<S*>(ex.p[d])[r] = v;  // P2P stores
+  if (!TILE_FORWARDS && ex.n < 0) static_cast<S*>(ex.p[0])[r] = v;
+}
+
+// rows [r0, r1) of y -> the forward destination, by one warp: 32 lanes x 8 bytes = 256 contiguous bytes per store instruction
+// (whole 128-byte NVLink writes instead of one 8-byte packet per row).  The loads bypass L1: the values were written by other
+// warps of this CTA a moment ago.
+template <typename S>
+__device__ __forceinline__ void forward_rows(const S* __restrict__ y, S* __restrict__ dst, int r0, int r1, int lane) {
+  for (int r = r0 + lane; r < r1; r += 32) dst[r] = __ldcg(y + r);
 }
 
 // ---------------------------------------------------------------------------
@@ -366,6 +378,8 @@ __global__ void __launch_bounds__((NW + 1) * 32)
     const int64_t nnz_al = nnz & ~(int64_t)3;           // bulk copies stay below this entry
     const int rp_al_end = (m + 1) & ~3;                 // ... and below this row_ptr entry
     int4 mine = make_int4(0, 0, 0, 0);
+    const bool forward = ex.n < 0;  // fused all-gather: finished tiles of y go on to ex.p[0] (see store_y)
+    int n_mine = 0;
     for (int it = 0;; ++it) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
       if (tile >= n_tiles) break;
@@ -381,6 +395,11 @@ __global__ void __launch_bounds__((NW + 1) * 32)
       const int stage = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&sm.empty[stage], ph ^ 1u);
+      if (forward && it >= STAGES) {  // every consumer warp has left tile it - STAGES: its rows of y are final
+        const int4 dp = sm.desc[stage];
+        forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
+        __syncwarp();  // (lane 0 overwrites the descriptor below)
+      }
 
       const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
       S* sv = sm.vals[stage];
@@ -422,6 +441,15 @@ __global__ void __launch_bounds__((NW + 1) * 32)
         if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
       }
       __syncwarp();
+      n_mine = it + 1;
+    }
+    if (forward) {  // the last tiles of this CTA: wait for the consumers to leave each, then forward it
+      for (int j = n_mine > STAGES ? n_mine - STAGES : 0; j < n_mine; ++j) {
+        const int stage = j % STAGES;
+        mbar_wait(&sm.empty[stage], (uint32_t)(j / STAGES) & 1u);
+        const int4 dp = sm.desc[stage];
+        forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
+      }
     }
   } else {
     // ------------------------- consumer warps -----------------------------
@@ -479,7 +507,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
           for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
         }
         sum = subwarp_sum<LPR>(sum);
-        if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta, ex);
+        if (valid && !is_long && sl == 0) store_y<S, true>(y, r, sum, alpha, beta, ex);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -1297,6 +1325,22 @@ int b200sp_spmv_scatter_f64_i32(b200sp_spmv_plan* p, void* stream, int m, int n,
   }
   p->extra.n = n_extra;
   for (int d = 0; d < n_extra; ++d) p->extra.p[d] = y_extra[d];
+  const int rc = spmv_impl<double>(p, (cudaStream_t)stream, 'N', m, n, nnz, alpha, row_ptr, col_idx, vals, x, 0.0, y);
+  p->extra.n = 0;
+  return rc;
+}
+
+int b200sp_spmv_forward_f64_i32(b200sp_spmv_plan* p, void* stream, int m, int n, int64_t nnz, double alpha,
+                                const int* row_ptr, const int* col_idx, const double* vals, const double* x,
+                                double* y, void* y_forward) {
+  B200SP_REQUIRE(p != nullptr, "spmv_forward: a plan is required");
+  B200SP_REQUIRE(y_forward != nullptr, "spmv_forward: y_forward is null");
+  if (alpha == 0.0 || m == 0 || n == 0 || nnz == 0) {
+    set_error("spmv_forward: alpha == 0 / empty matrix is not supported by the fused all-gather form");
+    return B200SP_ERR_INVALID_ARGUMENT;
+  }
+  p->extra.n = -1;
+  p->extra.p[0] = y_forward;
   const int rc = spmv_impl<double>(p, (cudaStream_t)stream, 'N', m, n, nnz, alpha, row_ptr, col_idx, vals, x, 0.0, y);
   p->extra.n = 0;
   return rc;

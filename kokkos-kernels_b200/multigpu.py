@@ -16,6 +16,10 @@ to "fused" when the symmetric-memory handle has no multicast pointer; first meas
 "pipelined_mc" (pieces like "pipelined", but each finished piece is pushed ONCE to the multicast address by a
 small SM kernel with 16-byte stores, b200sp_multicast_push, on one communication stream; falls back to
 "pipelined" without a multicast pointer),
+"multicast_fwd" (one launch like "multicast", but the values reach the multicast address tile by tile from the kernel's
+PRODUCER warp -- finished tiles of y are read back from L2 and stored with 256 contiguous bytes per instruction,
+b200sp_spmv_forward_f64_i32: whole 128-byte NVLink writes instead of one 8-byte packet per row, no separate push kernel, no
+SM taken from the compute),
 "pipelined_sm" (pieces pushed to the 7 peers' unicast mappings by a small SM kernel, every 16 bytes read once and stored
 7 times, b200sp_peer_push_sm), "nccl" (SpMV then all_gather_into_tensor)."""
 import ctypes as C
@@ -27,7 +31,7 @@ import torch.distributed as dist
 from . import _lib, partition, sparse as sp
 
 
-MODES = ("pipelined", "pipelined_mc", "pipelined_sm", "multicast", "fused", "nccl")
+MODES = ("pipelined", "pipelined_mc", "pipelined_sm", "multicast", "multicast_fwd", "fused", "nccl")
 
 
 class RowBlockSpMV:
@@ -65,7 +69,7 @@ class RowBlockSpMV:
                 self.symm[b] = hdl
                 self.peer_ptrs[b] = [int(p) for p in hdl.buffer_ptrs]
                 self.mc_ptr[b] = int(getattr(hdl, "multicast_ptr", 0) or 0)
-            if mode in ("multicast", "pipelined_mc") and (self.mc_ptr[0] == 0 or self.mc_ptr[1] == 0):
+            if mode in ("multicast", "multicast_fwd", "pipelined_mc") and (self.mc_ptr[0] == 0 or self.mc_ptr[1] == 0):
                 raise RuntimeError("no NVSwitch multicast mapping for the symmetric buffer on this box")
         else:
             self.bufs = [torch.empty(n_total, dtype=torch.float64, device=device) for _ in range(2)]
@@ -87,7 +91,7 @@ class RowBlockSpMV:
             for b in range(2):
                 yv = self.bufs[b][r0 + c0: r0 + c1]
                 dsts = []
-                if mode in ("multicast", "pipelined_mc"):
+                if mode in ("multicast", "multicast_fwd", "pipelined_mc"):
                     dsts = [self.mc_ptr[b] + (r0 + c0) * 8]  # one store, replicated by the switch (incl. this rank's copy)
                 elif mode != "nccl":
                     dsts = [self.peer_ptrs[b][q] + (r0 + c0) * 8 for q in range(self.world) if q != self.rank]
@@ -119,7 +123,12 @@ class RowBlockSpMV:
         b = self.parity
         out = self.bufs[b]
         assert x.data_ptr() != out.data_ptr(), "RowBlockSpMV.step: x is the buffer this step writes"
-        if self.mode in ("fused", "multicast"):
+        if self.mode == "multicast_fwd":
+            A, h, per_buf, ev = self.pieces[0]
+            yv, dsts, arr = per_buf[b]
+            sp.spmv_forward(h, 1.0, A, x, yv, dsts[0])
+            self.symm[b].barrier(channel=0)
+        elif self.mode in ("fused", "multicast"):
             A, h, per_buf, ev = self.pieces[0]
             yv, dsts, arr = per_buf[b]
             sp.spmv_scatter(h, 1.0, A, x, yv, dsts)
@@ -171,7 +180,7 @@ class RowBlockSpMV:
             dist.all_gather_into_tensor(out, mine)
             return out
         cs = C.c_void_p(cur.cuda_stream)
-        if self.mode in ("multicast", "pipelined_mc"):
+        if self.mode in ("multicast", "multicast_fwd", "pipelined_mc"):
             _lib.check(lib.b200sp_multicast_push(cs, C.c_void_p(mine.data_ptr()), C.c_void_p(self.mc_ptr[b] + self.r0 * 8),
                                                  mine.numel() * 8, 4 * self.push_ctas))
         elif self.mode == "pipelined":

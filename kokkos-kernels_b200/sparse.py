@@ -620,6 +620,15 @@ def spmv_scatter(handle, alpha, A, x, y, extra_ptrs):
     return y
 
 
+def spmv_forward(handle, alpha, A, x, y, forward_ptr):
+    """Fused SpMV + all-gather through one destination (the NVSwitch multicast mapping): finished tiles of y are forwarded
+    to the raw device pointer `forward_ptr` by the kernel's producer warp (b200sp_spmv_forward_f64_i32)."""
+    check(_lib.sparse().b200sp_spmv_forward_f64_i32(
+        handle._plan, _stream(), A.numRows(), A.numCols(), A.nnz(), alpha, _idx(A.row_map), _idx(A.entries),
+        _ptr(A.values), _ptr(x), _ptr(y), C.c_void_p(int(forward_ptr))))
+    return y
+
+
 def spmv_hostvec(handle, mode, alpha, A, x_host, beta, y_host):
     """End-to-end entry: host x / y (pinned), device-resident matrix."""
     m, n = A.numRows(), A.numCols()

@@ -417,6 +417,20 @@ def test_multi_gpu_kernels_single_process(emu, oracle):
         assert not np.isnan(nxt[q]).any()
         assert np.array_equal(nxt[q], nxt[0])  # every replica bit-identical
         assert np.all(np.abs(nxt[q] - exp) <= 1e-10 * scale + 1e-300)
+    # forward mode: finished tiles go on to ONE destination from the producer warp (the multicast mapping on a GPU)
+    fwd = np.full(n, np.nan)
+    loc = np.full(n, np.nan)
+    for r in range(P):
+        lo, hi = bounds[r], bounds[r + 1]
+        rpl = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        cil, vl = ci[rp[lo]:rp[hi]].copy(), v[rp[lo]:rp[hi]].copy()
+        plan = E.SpmvPlan()
+        E.ok(L.b200sp_spmv_plan_tune(plan.h, 8, 4, 0))
+        E.ok(L.b200sp_spmv_forward_f64_i32(plan.h, None, hi - lo, n, len(cil), 1.0, E.ptr(rpl), E.ptr(cil), E.ptr(vl), E.ptr(x),
+                                           E.ptr(loc[lo:hi]), C.c_void_p(fwd[lo:hi].ctypes.data)))
+        assert plan.kernel().startswith("tile"), plan.kernel()
+        plan.close()
+    assert np.array_equal(fwd, nxt[0]) and np.array_equal(loc, nxt[0])
     # multicast push: 16-byte stores with a one-element head / tail when the 16-byte phase asks for it
     src_all = np.random.default_rng(5).uniform(-1, 1, 5000)
     for off in (0, 1):  # 8-byte phase of both pointers (they must agree)

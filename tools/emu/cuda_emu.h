@@ -136,6 +136,7 @@ void bulk_copy_async(void* smem_dst, const void* gsrc, unsigned bytes, void* bar
 
 // ---------------------------------------------------------------------------------------------- device intrinsics
 static inline void __syncthreads() { b200emu::block_barrier(); }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { b200emu::warp_barrier(mask); }
 static inline void __threadfence() {}  // one fiber runs at a time: memory is always coherent here
 static inline void __threadfence_block() {}
