@@ -395,11 +395,11 @@ __global__ void __launch_bounds__((NW + 1) * 32)
       const int stage = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&sm.empty[stage], ph ^ 1u);
-      if (forward && it >= STAGES) {  // every consumer warp has left tile it - STAGES: its rows of y are final
-        const int4 dp = sm.desc[stage];
-        forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
-        __syncwarp();  // (lane 0 overwrites the descriptor below)
-      }
+      // every consumer warp has left tile it - STAGES: its rows of y are final.  They are forwarded AFTER the refill of the
+      // stage has been issued (below), so that the copy to the peers rides behind the TMA and not in front of it.
+      int4 dp = make_int4(0, 0, 0, 0);
+      if (forward && it >= STAGES) dp = sm.desc[stage];
+      __syncwarp();  // (lane 0 overwrites the descriptor below)
 
       const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
       S* sv = sm.vals[stage];
@@ -441,6 +441,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
         if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
       }
       __syncwarp();
+      if (forward) forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
       n_mine = it + 1;
     }
     if (forward) {  // the last tiles of this CTA: wait for the consumers to leave each, then forward it
