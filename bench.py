@@ -512,6 +512,60 @@ def secondary_spgemm(dev, n=2_000_000, deg=32, reps=2):
     }
 
 
+def gpu_local_cpus(dev_index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), intersected with this process's affinity; None if unknown."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(dev_index)
+        bus = None
+        if hasattr(p, "pci_bus_id"):
+            bus = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{getattr(p, 'pci_device_id', 0):02x}.0"
+        else:
+            import pynvml
+
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(p.uuid)).encode()) if hasattr(p, "uuid") else pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+            bid = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+            bus = (bid.decode() if isinstance(bid, bytes) else bid).lower()[-12:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+class near_gpu:
+    """with near_gpu(i): allocations made inside (pinned host buffers are placed by first touch) land on the NUMA node of GPU i."""
+
+    def __init__(self, dev_index):
+        self.cpus = gpu_local_cpus(dev_index)
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+
 def verify_transport(op, x, n_total, world, rank, dev):
     """One step and two chained steps of a row-block operator: every rank's copy of the gathered vector must be bit-identical to
     every other rank's (probes of each block are exchanged over NCCL), and the first result must not change under the steps
@@ -800,8 +854,11 @@ def main():
     e2e_extra = {}
     if world == 1:
         # through the host-vector C-ABI entry: pinned x -> device, SpMV, y -> pinned host
-        xh = torch.from_numpy(x_host).pin_memory()
-        yh = torch.empty(nrows, dtype=torch.float64).pin_memory()
+        with near_gpu(local) as ng:  # pinned host vectors on the GPU's own NUMA node
+            xh = torch.empty(n_total, dtype=torch.float64).pin_memory()
+            yh = torch.empty(nrows, dtype=torch.float64).pin_memory()
+            xh.copy_(torch.from_numpy(x_host))
+            numa_note = f"; pinned vectors allocated on the GPU's NUMA node ({len(ng.cpus)} local CPUs)" if ng.cpus else ""
         for _ in range(3):
             sp.spmv_hostvec(h, "N", 1.0, A, xh, 0.0, yh)
         torch.cuda.synchronize()
@@ -849,12 +906,16 @@ def main():
         e2e_extra = {"mode": e2e_mode, "ms_per_step_stream_ordered": round(e2e_sync_ms, 4),
                      "ms_per_step_deferred": None if e2e_defer_ms is None else round(e2e_defer_ms, 4),
                      "note": "b200sp_spmv_hostvec_f64_i32: pinned host x -> device, SpMV, y -> pinned host, every step; "
-                             "matrix stays device-resident (as a CrsMatrix in CudaSpace does)"}
+                             "matrix stays device-resident (as a CrsMatrix in CudaSpace does)" + numa_note}
     else:
         # every rank uploads ITS slice of x (n/P values), the all-gather over NVLink completes x on every GPU, local SpMV,
         # every rank downloads its slice of y (RowBlockSpMV.step_host; calls pipelined over the two next-x buffers)
-        xh = torch.from_numpy(x_host[r0:r1].copy()).pin_memory()
-        yh = torch.full((nrows,), float("nan"), dtype=torch.float64).pin_memory()
+        with near_gpu(local) as ng:  # the pinned slices on the GPU's own NUMA node: 8 ranks share the host's memory channels
+            xh = torch.empty(nrows, dtype=torch.float64).pin_memory()
+            yh = torch.empty(nrows, dtype=torch.float64).pin_memory()
+            xh.copy_(torch.from_numpy(x_host[r0:r1].copy()))
+            yh.fill_(float("nan"))
+            numa_note = f"pinned buffers allocated on the GPU's NUMA node ({len(ng.cpus)} local CPUs)" if ng.cpus else "NUMA node of the GPU unknown: default placement"
         for _ in range(3):
             op.step_host(xh, yh)
         op.host_flush()
@@ -871,7 +932,7 @@ def main():
         h2d, d2h = int(n_total * 8), int(n_total * 8)  # all ranks together: every value of x goes up once, of y comes down once
         e2e_extra = {"mode": f"RowBlockSpMV.step_host, all-gather transport {collective}, calls pipelined over two buffers",
                      "note": f"every rank: its {nrows}-value slice of x pinned host -> device, all-gather over NVLink, local SpMV, its slice "
-                             "of y -> pinned host, every step; bytes are the totals over all ranks"}
+                             "of y -> pinned host, every step; bytes are the totals over all ranks; " + numa_note}
     e2e_gflops = 2.0 * total_nnz / (e2e_ms * 1e-3) / 1e9
 
     cpu = None
