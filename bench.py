@@ -545,7 +545,10 @@ class near_gpu:
     """with near_gpu(i): allocations made inside (pinned host buffers are placed by first touch) land on the NUMA node of GPU i."""
 
     def __init__(self, dev_index):
-        self.cpus = gpu_local_cpus(dev_index)
+        # opt-in (B200SP_BENCH_NUMA=1): on the B200 boxes measured, the GPU's own node did not help -- at N = 1 the stream-ordered
+        # host-vector step went from 2.00 to 2.73 ms (a node of a sub-NUMA-clustered socket has a fraction of the memory channels),
+        # and at N = 8 the bound is the PCIe uplink two GPUs share (~26 GB/s each way per GPU), not the placement
+        self.cpus = gpu_local_cpus(dev_index) if os.environ.get("B200SP_BENCH_NUMA") == "1" else None
         self.saved = None
 
     def __enter__(self):
@@ -915,7 +918,7 @@ def main():
             yh = torch.empty(nrows, dtype=torch.float64).pin_memory()
             xh.copy_(torch.from_numpy(x_host[r0:r1].copy()))
             yh.fill_(float("nan"))
-            numa_note = f"pinned buffers allocated on the GPU's NUMA node ({len(ng.cpus)} local CPUs)" if ng.cpus else "NUMA node of the GPU unknown: default placement"
+            numa_note = f"pinned buffers allocated on the GPU's NUMA node ({len(ng.cpus)} local CPUs)" if ng.cpus else "pinned buffers with the default placement"
         for _ in range(3):
             op.step_host(xh, yh)
         op.host_flush()

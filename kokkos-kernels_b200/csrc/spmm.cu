@@ -903,14 +903,15 @@ static int launch_mm_tile(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m,
 // piece order (no atomics: deterministic).  Per entry the sum order is the storage order.
 // ---------------------------------------------------------------------------
 static constexpr int MMI_MAXL = 256;
+static constexpr int MMI_LONG_PIECES = 64;  // rows of more pieces are added up by a whole CTA (spmm_item_reduce_long_kernel)
 
 // histogram of item lengths (0..lmax), number of multi-piece rows and of their pieces
 __global__ void __launch_bounds__(256) mmi_count_kernel(int m, const int* __restrict__ row_ptr, int lmax, int* __restrict__ hist,
                                                         int* __restrict__ counters) {
   __shared__ int sh[MMI_MAXL + 1];
-  __shared__ int sc[2];
+  __shared__ int sc[3];
   for (int i = threadIdx.x; i <= lmax; i += 256) sh[i] = 0;
-  if (threadIdx.x < 2) sc[threadIdx.x] = 0;
+  if (threadIdx.x < 3) sc[threadIdx.x] = 0;
   __syncthreads();
   for (int r = blockIdx.x * 256 + threadIdx.x; r < m; r += gridDim.x * 256) {
     const int len = row_ptr[r + 1] - row_ptr[r];
@@ -922,18 +923,20 @@ __global__ void __launch_bounds__(256) mmi_count_kernel(int m, const int* __rest
       atomicAdd(&sh[len - (pieces - 1) * lmax], 1);
       atomicAdd(&sc[0], 1);
       atomicAdd(&sc[1], pieces);
+      if (pieces > MMI_LONG_PIECES) atomicAdd(&sc[2], 1);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i <= lmax; i += 256)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
   if (threadIdx.x < 2 && sc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sc[threadIdx.x]);
+  if (threadIdx.x == 2 && sc[2]) atomicAdd(&counters[4], sc[2]);
 }
 
 // cursor[len] = first position of the items of that length (longest first); block-aggregated reservation of ranges
 __global__ void __launch_bounds__(256) mmi_fill_kernel(int m, const int* __restrict__ row_ptr, int lmax, int* __restrict__ cursor,
-                                                       int* __restrict__ counters /* [2] multi cursor, [3] partial cursor */,
-                                                       int4* __restrict__ items, int4* __restrict__ multi) {
+                                                       int* __restrict__ counters /* [2] multi cursor, [3] partial cursor, [5] long-row cursor */,
+                                                       int4* __restrict__ items, int4* __restrict__ multi, int n_multi) {
   __shared__ int sh[MMI_MAXL + 1];
   __shared__ int sbase[MMI_MAXL + 1];
   const int passes = (m + (int)(gridDim.x * 256) - 1) / (int)(gridDim.x * 256);
@@ -959,7 +962,9 @@ __global__ void __launch_bounds__(256) mmi_fill_kernel(int m, const int* __restr
         items[sbase[len] + rank_last] = make_int4(r, e0, len, -1);
       } else {
         const int slot0 = atomicAdd(&counters[3], pieces);
-        multi[atomicAdd(&counters[2], 1)] = make_int4(r, slot0, pieces, 0);
+        // rows of many pieces at the END of the list (they get a CTA each in the reduce), the others at the front
+        const int mpos = pieces > MMI_LONG_PIECES ? n_multi - 1 - atomicAdd(&counters[5], 1) : atomicAdd(&counters[2], 1);
+        multi[mpos] = make_int4(r, slot0, pieces, 0);
         for (int s = 0; s < pieces - 1; ++s) items[sbase[lmax] + rank_full + s] = make_int4(r, e0 + s * lmax, lmax, slot0 + s);
         items[sbase[last] + rank_last] = make_int4(r, e0 + (pieces - 1) * lmax, last, slot0 + pieces - 1);
       }
@@ -979,15 +984,15 @@ static int plan_analyse_items(b200sp_spmv_plan* p, cudaStream_t st, int lmax, in
   DevTmp tmp(st);
   int *hist, *counters;
   B200SP_CUDA_TRY(tmp.alloc(&hist, lmax + 1));
-  B200SP_CUDA_TRY(tmp.alloc(&counters, 4));
+  B200SP_CUDA_TRY(tmp.alloc(&counters, 8));
   B200SP_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)(lmax + 1), st));
-  B200SP_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 4, st));
+  B200SP_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 8, st));
   const int blocks = std::max(1, std::min((m + 255) / 256, sm_count() * 8));
   mmi_count_kernel<<<blocks, 256, 0, st>>>(m, row_ptr, lmax, hist, counters);
   B200SP_LAUNCH_CHECK();
-  int h_hist[MMI_MAXL + 1], h_cnt[4];
+  int h_hist[MMI_MAXL + 1], h_cnt[8];
   B200SP_CUDA_TRY(cudaMemcpyAsync(h_hist, hist, sizeof(int) * (size_t)(lmax + 1), cudaMemcpyDeviceToHost, st));
-  B200SP_CUDA_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(h_cnt, counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // once per matrix
   int h_cur[MMI_MAXL + 1];
   long long total = 0;
@@ -998,12 +1003,13 @@ static int plan_analyse_items(b200sp_spmv_plan* p, cudaStream_t st, int lmax, in
   B200SP_REQUIRE(total <= (long long)INT_MAX, "spmm: too many work items");
   mi->n_items = (int)total;
   mi->n_multi = h_cnt[0];
+  mi->n_multi_long = h_cnt[4];
   mi->n_partial = h_cnt[1];
   mi->lmax = lmax;
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&mi->items, sizeof(int4) * (size_t)std::max(mi->n_items, 1), st));
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&mi->multi, sizeof(int4) * (size_t)std::max(mi->n_multi, 1), st));
   B200SP_CUDA_TRY(cudaMemcpyAsync(hist, h_cur, sizeof(int) * (size_t)(lmax + 1), cudaMemcpyHostToDevice, st));
-  mmi_fill_kernel<<<blocks, 256, 0, st>>>(m, row_ptr, lmax, hist, counters, mi->items, mi->multi);
+  mmi_fill_kernel<<<blocks, 256, 0, st>>>(m, row_ptr, lmax, hist, counters, mi->items, mi->multi, mi->n_multi);
   B200SP_LAUNCH_CHECK();
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // h_cur is pageable host memory: consumed before it goes out of scope
   mi->key_row_ptr = row_ptr;
@@ -1251,6 +1257,40 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// the same for the rows of more than MMI_LONG_PIECES pieces (the hubs of a power-law matrix: 2388 pieces in the longest row of
+// R-MAT scale 23), one CTA per row: thread = (piece subsequence, column), 256 / KC subsequences added in piece order each, then
+// joined in subsequence order through shared memory by the threads of subsequence 0.  Fixed order: reproducible.
+template <typename S>
+__global__ void __launch_bounds__(256)
+    spmm_item_reduce_long_kernel(int n_long, const int4* __restrict__ multi_long, int k, const S* __restrict__ partial,
+                                 S* __restrict__ Y, int64_t ldy, S alpha, S beta) {
+  __shared__ S part[256];
+  int KC = 1;
+  while (KC < k && KC < 32) KC <<= 1;
+  const int SUB = 256 / KC;
+  const int j0 = threadIdx.x % KC, sub = threadIdx.x / KC;
+  for (int w = blockIdx.x; w < n_long; w += gridDim.x) {
+    const int4 d = multi_long[w];
+    for (int jb = 0; jb < k; jb += KC) {
+      const int j = jb + j0;
+      S sum = S(0);
+      if (j < k) {
+        const S* src = partial + (int64_t)d.y * k + j;
+        for (int s = sub; s < d.z; s += SUB) sum += src[(int64_t)s * k];
+      }
+      part[threadIdx.x] = sum;
+      __syncthreads();
+      if (sub == 0 && j < k) {
+        S t = part[j0];
+        for (int q = 1; q < SUB; ++q) t += part[q * KC + j0];
+        S* yp = Y + (int64_t)d.x * ldy + j;
+        *yp = (beta == S(0)) ? alpha * t : beta * *yp + alpha * t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 template <typename S>
 static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m, int k, int64_t nnz, const int* row_ptr,
                            const int* col_idx, const S* vals, const S* X, int64_t ldx, S* Y, int64_t ldy, S alpha, S beta) {
@@ -1301,9 +1341,15 @@ static int launch_mm_items(b200sp_spmv_plan* p, cudaStream_t st, bool vec, int m
 #undef B200SP_MMI
     B200SP_LAUNCH_CHECK();
   }
-  if (mi->n_multi > 0) {
-    const int g = (int)std::min<int64_t>(((int64_t)mi->n_multi + 7) / 8, (int64_t)sm_count() * 16);  // a warp per row
-    spmm_item_reduce_kernel<S><<<std::max(g, 1), 256, 0, st>>>(mi->n_multi, mi->multi, k, (const S*)mi->partial, Y, ldy, alpha, beta);
+  const int n_short = mi->n_multi - mi->n_multi_long;
+  if (n_short > 0) {
+    const int g = (int)std::min<int64_t>(((int64_t)n_short + 7) / 8, (int64_t)sm_count() * 16);  // a warp per row
+    spmm_item_reduce_kernel<S><<<std::max(g, 1), 256, 0, st>>>(n_short, mi->multi, k, (const S*)mi->partial, Y, ldy, alpha, beta);
+    B200SP_LAUNCH_CHECK();
+  }
+  if (mi->n_multi_long > 0) {
+    const int g = std::min(mi->n_multi_long, sm_count() * 8);  // a CTA per row
+    spmm_item_reduce_long_kernel<S><<<g, 256, 0, st>>>(mi->n_multi_long, mi->multi + n_short, k, (const S*)mi->partial, Y, ldy, alpha, beta);
     B200SP_LAUNCH_CHECK();
   }
   return B200SP_OK;

@@ -14,6 +14,7 @@ struct MMItems {
   int n_items = 0;
   int4* multi = nullptr;  // rows of several pieces: (row, first partial slot, pieces, 0)
   int n_multi = 0;
+  int n_multi_long = 0;   // of them, at the END of `multi`: rows of more than 64 pieces (added up by a CTA each)
   int n_partial = 0;
   void* partial = nullptr;
   size_t partial_bytes = 0;

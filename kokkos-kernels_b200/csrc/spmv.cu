@@ -348,7 +348,10 @@ struct TileSmem {
   alignas(8) uint64_t empty[STAGES];
 };
 
-template <typename S, int LPR, int NW, int STAGES, int CAP, int UNR>
+// FWD: the fused all-gather form (b200sp_spmv_forward_f64_i32): the producer warp forwards finished tiles of y to ex.p[0].
+// A template parameter, so that the plain kernel -- the one every roofline number of this repository is measured on -- carries
+// no trace of it.
+template <typename S, int LPR, int NW, int STAGES, int CAP, int UNR, bool FWD = false>
 __global__ void __launch_bounds__((NW + 1) * 32)
     spmv_tile_kernel(int m, int64_t nnz, int n_tiles, int LMAX, const int4* __restrict__ tiles,
                      const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
     const int64_t nnz_al = nnz & ~(int64_t)3;           // bulk copies stay below this entry
     const int rp_al_end = (m + 1) & ~3;                 // ... and below this row_ptr entry
     int4 mine = make_int4(0, 0, 0, 0);
-    const bool forward = ex.n < 0;  // fused all-gather: finished tiles of y go on to ex.p[0] (see store_y)
+    constexpr bool forward = FWD;  // fused all-gather: finished tiles of y go on to ex.p[0] (see store_y)
     int n_mine = 0;
     for (int it = 0;; ++it) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
@@ -398,8 +401,10 @@ __global__ void __launch_bounds__((NW + 1) * 32)
       // every consumer warp has left tile it - STAGES: its rows of y are final.  They are forwarded AFTER the refill of the
       // stage has been issued (below), so that the copy to the peers rides behind the TMA and not in front of it.
       int4 dp = make_int4(0, 0, 0, 0);
-      if (forward && it >= STAGES) dp = sm.desc[stage];
-      __syncwarp();  // (lane 0 overwrites the descriptor below)
+      if (forward) {
+        if (it >= STAGES) dp = sm.desc[stage];
+        __syncwarp();  // (lane 0 overwrites the descriptor below)
+      }
 
       const int r0 = d.x, r1 = d.y, s = d.z, e = d.w;
       S* sv = sm.vals[stage];
@@ -441,8 +446,10 @@ __global__ void __launch_bounds__((NW + 1) * 32)
         if (nrp > 0) bulk_g2s(sr, row_ptr + r0_al, (uint32_t)(nrp * 4), &sm.full[stage], pol);
       }
       __syncwarp();
-      if (forward) forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
-      n_mine = it + 1;
+      if (forward) {
+        forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
+        n_mine = it + 1;
+      }
     }
     if (forward) {  // the last tiles of this CTA: wait for the consumers to leave each, then forward it
       for (int j = n_mine > STAGES ? n_mine - STAGES : 0; j < n_mine; ++j) {
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
           for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
         }
         sum = subwarp_sum<LPR>(sum);
-        if (valid && !is_long && sl == 0) store_y<S, true>(y, r, sum, alpha, beta, ex);
+        if (valid && !is_long && sl == 0) store_y<S, FWD>(y, r, sum, alpha, beta, ex);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -928,7 +935,7 @@ template <typename S, int LPR, int NW, int STAGES, int CAP, int UNR = 8>
 static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz, const int* row_ptr,
                        const int* col_idx, const S* vals, const S* x, S* y, S alpha, S beta) {
   using Smem = TileSmem<S, CAP, STAGES>;
-  auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP, UNR>;
+  auto kern = spmv_tile_kernel<S, LPR, NW, STAGES, CAP, UNR, false>;
   const size_t smem = sizeof(Smem) + 128;
   static KernelSetup ks;
   int occ_dev = 1;
@@ -939,8 +946,22 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   const int hi = p->range_hi < 0 ? p->n_tiles : p->range_hi;
   int grid = std::min(hi - lo, sm_count() * per_sm);
   if (grid < 1) grid = 1;
-  kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, hi - lo, p->LMAX, p->tiles + lo, row_ptr, col_idx, vals, x, y,
-                                          alpha, beta, p->extra);
+  bool launched = false;
+  if constexpr (sizeof(S) == 8 && NW == 16 && STAGES == 4 && CAP == 2048 && UNR == 8) {
+    // the forwarding form exists for the default configuration; elsewhere the consumers store to the destination themselves
+    if (p->extra.n < 0) {
+      auto kf = spmv_tile_kernel<S, LPR, NW, STAGES, CAP, UNR, true>;
+      static KernelSetup ksf;
+      int occ_f = 1;
+      if (int rc = kernel_setup(ksf, kf, (NW + 1) * 32, smem, &occ_f)) return rc;
+      kf<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, hi - lo, p->LMAX, p->tiles + lo, row_ptr, col_idx, vals, x, y, alpha, beta,
+                                            p->extra);
+      launched = true;
+    }
+  }
+  if (!launched)
+    kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, hi - lo, p->LMAX, p->tiles + lo, row_ptr, col_idx, vals, x, y,
+                                            alpha, beta, p->extra);
   B200SP_LAUNCH_CHECK();
   snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d,UNR=%d>grid=%d",
            sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, UNR, grid);

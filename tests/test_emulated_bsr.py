@@ -100,7 +100,8 @@ def test_tile_kernel_every_block_size(emu, oracle, bs):
                 for dtype in (np.float64, np.float32):
                     vv = v.astype(dtype)
                     run_rank1(oracle, plan, "N", bs, mb, nb, rp, ci, vv, rng, alpha, beta, dtype)
-                    want = "bsr_vector" if bs > 16 else ("bsr_tile_e<" if (bs <= 5 and not knob) else "bsr_tile<")
+                    # default: element-per-lane tile kernel for bs 2..5, row-vector kernel above (the measured choice)
+                    want = "bsr_vector" if (bs > 16 or (bs > 5 and not knob)) else ("bsr_tile_e<" if (bs <= 5 and not knob) else "bsr_tile<")
                     assert plan.kernel().startswith(want), plan.kernel()
         finally:
             os.environ.pop("B200SP_BSR_KERNEL", None)

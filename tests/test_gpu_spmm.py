@@ -50,6 +50,36 @@ def test_spmm_sweep(cuda, oracle, rows, per, bw, var, nv, dtype):
             assert np.max(np.abs(Ytd.cpu().numpy() - expt)) <= 4 * tol + 1e-300
 
 
+@pytest.mark.parametrize("dtype,k", [(np.float32, 16), (np.float64, 5), (np.float32, 40)])
+def test_spmm_hub_rows(cuda, oracle, dtype, k):
+    """Rows of thousands of entries (more than 64 pieces of 64: the CTA-per-row reduce of the item kernel) next to short
+    and empty rows; beta != 0; twice through one handle (run-to-run identical)."""
+    from kokkos_kernels_b200 import sparse as sp
+
+    rng = np.random.default_rng(77)
+    m, n = 3000, 9000
+    lens = rng.integers(0, 12, m)
+    lens[[7, 1500, 2999]] = [9000, 4097, 6500]
+    lens[100:110] = rng.integers(65, 700, 10)  # a few rows of several pieces (the warp-per-row reduce)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([rng.choice(n, int(l), replace=False) for l in lens]).astype(np.int32)
+    v = rng.uniform(-1, 1, len(ci)).astype(dtype)
+    X = rng.uniform(-1, 1, (n, k)).astype(dtype)
+    Y0 = rng.uniform(-1, 1, (m, k)).astype(dtype)
+    A = sp.CrsMatrix(torch.from_numpy(rp).to(cuda), torch.from_numpy(ci).to(cuda), torch.from_numpy(v).to(cuda), n)
+    exp = oracle.spmv_mv(rp, ci, v, n, X, Y0.copy(), 1.5, -0.5)
+    tol = 10 * np.finfo(dtype).eps * 9000 * 1.5
+    h = sp.SPMVHandle()
+    outs = []
+    for _ in range(2):
+        Y = _mk(cuda, Y0.copy(), True)
+        sp.spmv(h, "N", 1.5, A, _mk(cuda, X, True), -0.5, Y)
+        outs.append(Y.cpu().numpy())
+        assert np.max(np.abs(outs[-1] - exp)) <= tol
+    assert np.array_equal(outs[0], outs[1])
+    assert h.last_kernel().startswith("spmm_items"), h.last_kernel()
+
+
 def test_spmm_powerlaw_rows(cuda, oracle):
     """R-MAT structure (skewed rows), fp32, 16 columns: the config-3 shape at a small scale."""
     from kokkos_kernels_b200 import matgen, sparse as sp
