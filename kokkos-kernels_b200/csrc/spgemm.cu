@@ -1553,7 +1553,7 @@ int b200sp_spgemm_symbolic_i32(b200sp_spgemm_plan* p, void* stream, int m, int n
       case 2: rc = launch_esc_sym<256, 4, 10, 6>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
       case 3: rc = launch_esc_sym<128, 8, 11, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
       case 4: rc = launch_esc_sym<512, 2, 10, 1>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
-      default: rc = launch_esc_sym<256, 4, 10, 5>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
+      default: rc = launch_esc_sym<256, 4, 10, 8>(st, eo[2] - eo[1], er + eo[1], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz); break;
     }
     if (rc) return rc;
     if ((rc = launch_esc_sym<512, 8, 12, 1>(st, eo[3] - eo[2], er + eo[2], rpA, ciA, rpB, ciB, flops, p->cmin, p->cmax, row_nnz))) return rc;
