@@ -125,20 +125,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_spmv_tile_c2_ncu_key_metrics.csv, same workload); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_spmv_tile_c2_ncu_key_metrics.csv")
-    try:
-        vals = {}
-        for ln in open(path):
-            k, u, v = ln.strip().split(",")
-            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u)
-            if scale:
-                vals[k] = float(v) * scale
-        return int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"])
-    except Exception:
-        return None
+def ncu_traffic(files=("r02c15_spmv_tile_ncu_key_metrics.csv", "r01_spmv_tile_c2_ncu_key_metrics.csv"), kernel=None):
+    """(DRAM bytes per launch, file) of a kernel from the newest committed `ncu --set full` capture of it on the bench workload
+    (profiles/*key_metrics*: lines `metric,unit,value`; files holding several kernels separate them by a `Kernel Name` line) --
+    a CONSTANT of the repository, not a measurement of this run; (None, None) if absent."""
+    for name in files:
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            vals, active = {}, kernel is None
+            for ln in open(path):
+                f = ln.strip().split(",")
+                if len(f) >= 3 and f[0] == "Kernel Name":
+                    active = kernel is None or kernel in ln
+                    continue
+                if not active or len(f) != 3:
+                    continue
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(f[1])
+                if scale and f[0] not in vals:
+                    vals[f[0]] = float(f[2]) * scale
+            return int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def alg_bytes(nnz, nrows, ncols, beta_nonzero=False):
@@ -374,7 +382,10 @@ def secondary_spmm(dev, scale=23, k=16, iters=10):
                         "note": "LayoutLeft X and Y (Kokkos' default in CudaSpace): both are relaid out inside the call"},
         "roofline": {"bound": "hbm", "achieved": round(balg / ms / 1e6, 1), "peak": peak, "unit": "GB/s", "frac": round(balg / ms / 1e6 / peak, 4),
                      "algorithmic_bytes_per_launch": balg, "gather_model_bytes": bgather,
-                     "frac_gather_model": round(bgather / ms / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src},
+                     "frac_gather_model": round(bgather / ms / 1e6 / peak, 4),
+                     "traffic": ncu_traffic(("r02c15_spmm_coop_key_metrics.txt", "r02c8_spmm_coop_key_metrics.txt"), "spmm_item_coop_kernel")[0],
+                     "traffic_unit": "DRAM bytes of the item kernel per launch, a constant from the committed ncu --set full capture at this size (profiles/r02c*_spmm_coop_key_metrics.txt)",
+                     "peak_source": peak_src},
         "cpu_baseline": {"value": round(cpu_gf, 2), "unit": "GFLOP/s", "cores": threads, "kind": "port",
                          "sample": f"oracle O4 (CPU multivector strips, spmv_impl.hpp:745-926, OpenMP over rows), first {srows} rows "
                                    f"({snnz} nnz) of the same matrix, full X, 5 iterations, mean {np.mean(ts) * 1e3:.1f} ms"},
@@ -504,7 +515,10 @@ def secondary_spgemm(dev, n=2_000_000, deg=32, reps=2):
         "roofline": {"bound": "hbm", "kernel": "esc_num_kernel<double,256,4,10> (persistent, row pipeline)", "achieved": round(b_num / ms_num / 1e6, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(b_num / ms_num / 1e6 / peak, 4), "algorithmic_bytes_per_launch": b_num,
                      "gather_model_bytes": b_gather, "frac_gather_model": round(b_gather / ms_num / 1e6 / peak, 4),
-                     "symbolic_GBs": round(b_sym / ms_sym / 1e6, 1), "traffic": None, "peak_source": peak_src},
+                     "symbolic_GBs": round(b_sym / ms_sym / 1e6, 1),
+                     "traffic": ncu_traffic(("r02c9_esc_key_metrics.txt",), "esc_num_kernel")[0],
+                     "traffic_unit": "DRAM bytes of the numeric kernel per launch, a constant from the committed ncu --set full capture at this size (profiles/r02c9_esc_key_metrics.txt)",
+                     "peak_source": peak_src},
         "cpu_baseline": {"value": round(cpu_gf, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port",
                          "sample": f"oracle O6 (spgemm_debug symbolic + numeric + row sort, impl_seq.hpp:23-182), rows dealt to {threads} "
                                    f"threads, first {srows} rows ({sprod} products): {t_cpu * 1e3:.0f} ms"},
@@ -974,9 +988,9 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4),
-                         "traffic": ncu_traffic() if (world == 1 and args.grid == GRID) else None,
+                         "traffic": ncu_traffic()[0] if (world == 1 and args.grid == GRID) else None,
                          "traffic_unit": "DRAM bytes per launch, a CONSTANT read from the committed ncu --set full capture of this kernel on "
-                                         "this workload (profiles/r01_spmv_tile_c2_ncu_key_metrics.csv), not measured by this run",
+                                         f"this workload (profiles/{ncu_traffic()[1]}), not measured by this run",
                          "peak_source": peak_src,
                          "kernel_ms": round(kern_ms, 5), "algorithmic_bytes_per_launch": balg},
             "e2e": dict({"value": round(e2e_gflops, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,

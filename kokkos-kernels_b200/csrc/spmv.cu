@@ -98,16 +98,20 @@ struct YExtra {
 };
 
 // ex.n > 0: every value is also stored to ex.n further destinations (P2P mappings of the peers' buffers, or one NVSwitch
-// multicast mapping).  ex.n < 0 ("forward"): ONE further destination, ex.p[0]; the tiled kernel then forwards whole finished
-// tiles from its producer warp (TILE_FORWARDS = true: nothing to do here), every other kernel stores the value itself.
-template <typename S, bool TILE_FORWARDS = false>
+// multicast mapping).  ex.n < 0 ("forward", one destination ex.p[0]) is seen by the forwarding form of the tiled kernel only,
+// whose producer warp copies whole finished tiles (the loop below then stores nothing); every other kernel of a forwarding
+// call gets the same destination as an ordinary extra one (direct_extra()).
+template <typename S>
 __device__ __forceinline__ void store_y(S* __restrict__ y, int r, S sum, S alpha, S beta, const YExtra& ex) {
   // reference epilogue (spmv_impl.hpp:124-131): sum *= alpha; y = beta*y + sum
   sum *= alpha;
   const S v = (beta == S(0)) ? sum : beta * y[r] + sum;
   y[r] = v;
   for (int d = 0; d < ex.n; ++d) static_cast<S*>(ex.p[d])[r] = v;  // P2P stores
-  if (!TILE_FORWARDS && ex.n < 0) static_cast<S*>(ex.p[0])[r] = v;
+}
+static inline YExtra direct_extra(YExtra ex) {
+  if (ex.n < 0) ex.n = 1;
+  return ex;
 }
 
 // rows [r0, r1) of y -> the forward destination, by one warp: 32 lanes x 8 bytes = 256 contiguous bytes per store instruction
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__((NW + 1) * 32)
           for (int u = 0; u < UNR; ++u) sum += av[u] * xv[u];
         }
         sum = subwarp_sum<LPR>(sum);
-        if (valid && !is_long && sl == 0) store_y<S, FWD>(y, r, sum, alpha, beta, ex);
+        if (valid && !is_long && sl == 0) store_y(y, r, sum, alpha, beta, ex);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -961,7 +965,7 @@ static int launch_tile(b200sp_spmv_plan* p, cudaStream_t st, int m, int64_t nnz,
   }
   if (!launched)
     kern<<<grid, (NW + 1) * 32, smem, st>>>(m, nnz, hi - lo, p->LMAX, p->tiles + lo, row_ptr, col_idx, vals, x, y,
-                                            alpha, beta, p->extra);
+                                            alpha, beta, direct_extra(p->extra));
   B200SP_LAUNCH_CHECK();
   snprintf(p->last_kernel, sizeof(p->last_kernel), "tile<%s,LPR=%d,NW=%d,STAGES=%d,CAP=%d,UNR=%d>grid=%d",
            sizeof(S) == 8 ? "f64" : "f32", LPR, NW, STAGES, CAP, UNR, grid);
@@ -997,7 +1001,7 @@ static int launch_vector(b200sp_spmv_plan* p, cudaStream_t st, int lpr, int m, c
   int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count() * 16);
   if (blocks < 1) blocks = 1;
   YExtra ex = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0};
-  if (p) ex = p->extra;
+  if (p) ex = direct_extra(p->extra);
 #define B200SP_VEC(L)                                                                              \
   case L:                                                                                          \
     spmv_vector_kernel<S, L><<<blocks, 256, 0, st>>>(m, row_ptr, col_idx, vals, x, y, alpha, beta, ex, lmax); \
@@ -1189,13 +1193,13 @@ static int spmv_impl(b200sp_spmv_plan* p, cudaStream_t st, char mode, int m, int
       spmv_seg_partial_kernel<S><<<sm_count() * 4, 256, 0, st>>>(p->r1_segs, p->r1_n_seg, col_idx, vals, x, (S*)p->r1_partial);
       B200SP_LAUNCH_CHECK();
       spmv_seg_combine_kernel<S><<<std::max(1, std::min((p->long_cap + 255) / 256, sm_count())), 256, 0, st>>>(
-          p->long_rows, p->n_long, p->r1_row_seg, (const S*)p->r1_partial, y, alpha, beta, p->extra);
+          p->long_rows, p->n_long, p->r1_row_seg, (const S*)p->r1_partial, y, alpha, beta, direct_extra(p->extra));
       B200SP_LAUNCH_CHECK();
       snprintf(p->last_kernel + strlen(p->last_kernel), sizeof(p->last_kernel) - strlen(p->last_kernel), "+seg");
     } else {
       int blocks = p->n_long_known ? std::min(*p->n_long_host, sm_count() * 4) : sm_count() * 2;
       spmv_longrow_kernel<S><<<blocks, 256, 0, st>>>(p->long_rows, p->n_long, row_ptr, col_idx, vals, x, y, alpha, beta,
-                                                     p->extra);
+                                                     direct_extra(p->extra));
       B200SP_LAUNCH_CHECK();
     }
   }
