@@ -34,7 +34,19 @@ def _nvcc():
 
 
 def build(force=False, verbose=True):
+    """Serialised across processes by a lock file (pytest-xdist workers all call this at session start)."""
     os.makedirs(LIB, exist_ok=True)
+    import fcntl
+
+    with open(os.path.join(LIB, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     out = os.path.join(LIB, "libb200sparse.so")
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(CSRC, "tile_ring.cuh"), os.path.join(CSRC, "spgemm_esc.cuh"), os.path.join(CSRC, "spmm_items.h"), os.path.join(HERE, "..", "include", "b200sparse.h")]

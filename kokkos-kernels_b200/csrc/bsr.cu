@@ -837,6 +837,24 @@ int bsr_spmv_impl(b200sp_bsr_plan* p, cudaStream_t st, char mode, int mb, int nb
   }
   // The run-time block size ("walk") tile kernel loses to the row-vector kernel from bs = 5 on (B200, lap27 pattern, 6.9 M blocks:
   // bs = 5: 1.13 vs 0.84 ms, bs = 8: 5.91 vs 1.90 ms, profiles/r02c6_bsr_big_*.log): it serves bs <= 4 and explicit requests only.
+  if constexpr (sizeof(S) == 8) {
+    // bs 6..16 in double: the tensor-core multivector kernel with ONE column (x contiguous: row stride 1).  Seven of the eight
+    // columns of each MMA are zeros, but the MMA is not what bounds the product -- the loads of the blocks are, and the fragment
+    // loads of that kernel (4 lanes x 32 contiguous bytes of a block row) are cheaper than the row-vector kernel's walk.
+    // B200SP_BSR_KERNEL=vector|walk keeps the other kernels; SPMV_BSR_V41 / V42 requests keep the scalar ones as well.
+    if (bs >= 6 && bs <= 16 && !force && p->algo != B200SP_BSR_ALGO_SCALAR) {
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)mb + 7) / 8, (int64_t)sm_count() * 16));
+      if (bs <= 8)
+        bsr_mm_tc_kernel<1, 1><<<dim3(blocks, 1), 256, 0, st>>>(mb, bs, 1, rp, ci, (const double*)v, (const double*)x, 1, 0, (double*)y, 1, 0,
+                                                                (double)alpha, (double)beta);
+      else
+        bsr_mm_tc_kernel<2, 1><<<dim3(blocks, 1), 256, 0, st>>>(mb, bs, 1, rp, ci, (const double*)v, (const double*)x, 1, 0, (double*)y, 1, 0,
+                                                                (double)alpha, (double)beta);
+      B200SP_LAUNCH_CHECK();
+      snprintf(p->last_kernel, sizeof(p->last_kernel), "bsr_mm_tc<f64,bs=%d,m8n8k4,MT=%d,NT=1>x1", bs, bs <= 8 ? 1 : 2);
+      return B200SP_OK;
+    }
+  }
   if (bs > 4 && !(force && !strcmp(force, "walk"))) return launch_vector<S>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
   if (bs <= 4) return launch_tile<S, 16, 4, 2048>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);
   return launch_tile<S, 16, 3, 4096>(p, st, mb, nnzb, bs, rp, ci, v, x, y, alpha, beta);

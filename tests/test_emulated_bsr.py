@@ -101,7 +101,10 @@ def test_tile_kernel_every_block_size(emu, oracle, bs):
                     vv = v.astype(dtype)
                     run_rank1(oracle, plan, "N", bs, mb, nb, rp, ci, vv, rng, alpha, beta, dtype)
                     # default: element-per-lane tile kernel for bs 2..5, row-vector kernel above (the measured choice)
-                    want = "bsr_vector" if (bs > 16 or (bs > 5 and not knob)) else ("bsr_tile_e<" if (bs <= 5 and not knob) else "bsr_tile<")
+                    if bs > 5 and not knob:  # default: tensor-core kernel for double up to bs = 16, row-vector kernel otherwise
+                        want = "bsr_mm_tc<f64" if (dtype == np.float64 and bs <= 16) else "bsr_vector"
+                    else:
+                        want = "bsr_vector" if bs > 16 else ("bsr_tile_e<" if (bs <= 5 and not knob) else "bsr_tile<")
                     assert plan.kernel().startswith(want), plan.kernel()
         finally:
             os.environ.pop("B200SP_BSR_KERNEL", None)

@@ -173,7 +173,8 @@ def test_tile_kernel_every_block_size(cuda, oracle, bs, force, monkeypatch):
         if force:
             assert h.last_kernel().startswith("bsr_tile<" if bs <= 16 else "bsr_vector"), h.last_kernel()
         else:
-            assert h.last_kernel().startswith("bsr_tile_e" if bs <= 5 else "bsr_vector"), h.last_kernel()
+            want = "bsr_tile_e" if bs <= 5 else ("bsr_mm_tc<f64" if bs <= 16 else "bsr_vector")  # double: tensor cores for bs 6..16
+            assert h.last_kernel().startswith(want), h.last_kernel()
     run_rank1(sp, oracle, cuda, h, A, (bs, mb, nb, rp, ci, v), "T", rng, -1.0, 1.0, np.float64)
 
 
