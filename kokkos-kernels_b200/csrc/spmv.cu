@@ -387,6 +387,8 @@ __global__ void __launch_bounds__((NW + 1) * 32)
     int4 mine = make_int4(0, 0, 0, 0);
     constexpr bool forward = FWD;  // fused all-gather: finished tiles of y go on to ex.p[0] (see store_y)
     int n_mine = 0;
+    int fr0 = 0, fr1 = 0;  // rows of the tile whose values (fv0: row fr0 + lane, fv1: row fr0 + 32 + lane) wait to be stored
+    S fv0 = S(0), fv1 = S(0);
     for (int it = 0;; ++it) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
       if (tile >= n_tiles) break;
@@ -451,11 +453,33 @@ __global__ void __launch_bounds__((NW + 1) * 32)
       }
       __syncwarp();
       if (forward) {
-        forward_rows<S>(y, static_cast<S*>(ex.p[0]), dp.x, dp.y, lane);
+        // Software-pipelined by one tile: the values of the tile that just left are only LOADED here (L2, ~0.7 us) and stored
+        // when the next tile comes round -- with ~1.2 us per tile and CTA on config 2 a load-then-store in one go made the
+        // producer warp the bottleneck of the kernel (+12 % on one GPU, profiles/r02c20_forward.log).  Tiles of more than 64
+        // rows are forwarded in one go.
+        S* dst = static_cast<S*>(ex.p[0]);
+        if (fr1 > fr0) {
+          if (fr0 + lane < fr1) dst[fr0 + lane] = fv0;
+          if (fr0 + 32 + lane < fr1) dst[fr0 + 32 + lane] = fv1;
+        }
+        fr0 = fr1 = 0;
+        if (dp.y - dp.x <= 64) {
+          fr0 = dp.x;
+          fr1 = dp.y;
+          if (fr0 + lane < fr1) fv0 = __ldcg(y + fr0 + lane);
+          if (fr0 + 32 + lane < fr1) fv1 = __ldcg(y + fr0 + 32 + lane);
+        } else {
+          forward_rows<S>(y, dst, dp.x, dp.y, lane);
+        }
         n_mine = it + 1;
       }
     }
-    if (forward) {  // the last tiles of this CTA: wait for the consumers to leave each, then forward it
+    if (forward) {  // the pending tile, then the last tiles of this CTA: wait for the consumers to leave each, then forward it
+      S* dst = static_cast<S*>(ex.p[0]);
+      if (fr1 > fr0) {
+        if (fr0 + lane < fr1) dst[fr0 + lane] = fv0;
+        if (fr0 + 32 + lane < fr1) dst[fr0 + 32 + lane] = fv1;
+      }
       for (int j = n_mine > STAGES ? n_mine - STAGES : 0; j < n_mine; ++j) {
         const int stage = j % STAGES;
         mbar_wait(&sm.empty[stage], (uint32_t)(j / STAGES) & 1u);

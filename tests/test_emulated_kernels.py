@@ -440,6 +440,19 @@ def test_multi_gpu_kernels_single_process(emu, oracle):
         assert plan.kernel().startswith("tile"), plan.kernel()
         plan.close()
     assert np.array_equal(fwd, nxt[0]) and np.array_equal(loc, nxt[0])
+    # ... and on ~55 entries per row (tiles of ~37 rows, the config-2 shape): the forwarding is software-pipelined by one tile there
+    rp2, ci2, v2 = kk_matrix(4000, 4000, 4000 * 55, 5, 600)
+    x2 = np.random.default_rng(6).uniform(-1, 1, 4000)
+    exp2 = oracle.spmv_serial(rp2, ci2, v2, x2, np.zeros(4000), 1.0, 0.0)
+    fwd2, loc2 = np.full(4000, np.nan), np.full(4000, np.nan)
+    plan = E.SpmvPlan()
+    E.ok(L.b200sp_spmv_plan_tune(plan.h, 8, 4, 0))
+    E.ok(L.b200sp_spmv_forward_f64_i32(plan.h, None, 4000, 4000, len(ci2), 1.0, E.ptr(rp2), E.ptr(ci2), E.ptr(v2), E.ptr(x2), E.ptr(loc2),
+                                       C.c_void_p(fwd2.ctypes.data)))
+    assert plan.kernel().startswith("tile"), plan.kernel()
+    plan.close()
+    scale2 = rowwise_scale(rp2, ci2, v2, x2, np.zeros(4000), 1.0, 0.0)
+    assert np.array_equal(fwd2, loc2) and np.all(np.abs(loc2 - exp2) <= 1e-10 * scale2 + 1e-300)
     # multicast push: 16-byte stores with a one-element head / tail when the 16-byte phase asks for it
     src_all = np.random.default_rng(5).uniform(-1, 1, 5000)
     for off in (0, 1):  # 8-byte phase of both pointers (they must agree)
