@@ -446,13 +446,16 @@ int b200sp_gs_copy_coloring(const b200sp_gs_plan* plan, void* stream, int* color
  * dimensions ldx / ldb (LayoutLeft, the reference's default_layout on the GPU); direction 0 = symmetric, 1 = forward,
  * 2 = backward; init_zero_x != 0 zeroes x first (and skips the first residual product).  Options (before symbolic for
  * COMPACT_FORM): KokkosKernelsHandle::set_gs_twostage_compact_form / set_gs_set_num_inner_sweeps / _num_outer_sweeps /
- * _inner_damp_factor (sparse/src/KokkosKernels_Handle.hpp:639-683); defaults 0, 1, 1, 1.0.  The sptrsv variant
- * (set_gs_twostage(false, ...)) is not provided.  B200SP_ERR_INVALID_ARGUMENT when a row has no diagonal entry,
+ * _inner_damp_factor (sparse/src/KokkosKernels_Handle.hpp:639-683); defaults 0, 1, 1, 1.0.  TWO_STAGE = 0 (before symbolic) selects
+ * the classic form, set_gs_twostage(false, ...): the inner sweeps are replaced by a triangular solve Z = (L + D)^{-1} R with the lower
+ * (upper) triangle of A (level sets, b200sp_sptrsv below); omega must be 1 there, as in the reference (apply :886-893).
+ * B200SP_ERR_INVALID_ARGUMENT when a row has no diagonal entry,
  * B200SP_ERR_STATE when a phase is called before its predecessor or with another matrix.  symbolic synchronises `stream`. */
 #define B200SP_GS2_COMPACT_FORM 1
 #define B200SP_GS2_NUM_INNER_SWEEPS 2
 #define B200SP_GS2_NUM_OUTER_SWEEPS 3
 #define B200SP_GS2_INNER_DAMP_FACTOR 4
+#define B200SP_GS2_TWO_STAGE 5
 typedef struct b200sp_gs2_plan b200sp_gs2_plan;
 int b200sp_gs2_plan_create(b200sp_gs2_plan** plan);
 int b200sp_gs2_plan_destroy(b200sp_gs2_plan* plan, void* stream);
@@ -468,6 +471,21 @@ int b200sp_gs2_apply_f64_i32(b200sp_gs2_plan* plan, void* stream, int n, int nco
 int b200sp_gs2_apply_f32_i32(b200sp_gs2_plan* plan, void* stream, int n, int ncols, const int* row_ptr, const int* col_idx,
                              const float* vals, float* x, int64_t ldx, const float* b, int64_t ldb, int nrhs,
                              int init_zero_x, float omega, int num_iter, int direction);
+
+/* Sparse triangular solve x = T^{-1} b on a lower or upper triangular CrsMatrix with its diagonal stored (any position in the
+ * row) -- KokkosSparse::sptrsv_symbolic / sptrsv_solve (sparse/src/KokkosSparse_sptrsv.hpp:40-170, :290-480), which the classic
+ * two-stage Gauss-Seidel above calls.  symbolic groups the rows into dependency levels (synchronises `stream`; an entry on the
+ * wrong side of the diagonal is B200SP_ERR_INVALID_ARGUMENT); solve runs one launch per level and computes every row as the
+ * serial substitution loop does (storage order, unfused multiply / subtract, one division): bit-identical to it. */
+typedef struct b200sp_sptrsv_plan b200sp_sptrsv_plan;
+int b200sp_sptrsv_plan_create(b200sp_sptrsv_plan** plan);
+int b200sp_sptrsv_plan_destroy(b200sp_sptrsv_plan* plan, void* stream);
+int b200sp_sptrsv_symbolic_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx, int is_lower);
+int b200sp_sptrsv_levels(const b200sp_sptrsv_plan* plan);
+int b200sp_sptrsv_solve_f64_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                                const double* vals, const double* b, double* x);
+int b200sp_sptrsv_solve_f32_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
+                                const float* vals, const float* b, float* x);
 
 /* ---- CG driver (callers of spmv in a loop) ---------------------------------------------------
  * KokkosKernels::Experimental::Example::pcgsolve with use_sgs = false (perf_test/sparse/KokkosSparse_pcg.hpp:248-466;

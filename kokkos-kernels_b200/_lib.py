@@ -30,6 +30,12 @@ SPARSE_API = {
     "b200sp_gs2_numeric_f32_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
     "b200sp_gs2_apply_f64_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, i64, vp, i64, i32, i32, f64, i32, i32]),
     "b200sp_gs2_apply_f32_i32": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, i64, vp, i64, i32, i32, f32, i32, i32]),
+    "b200sp_sptrsv_plan_create": (i32, [C.POINTER(vp)]),
+    "b200sp_sptrsv_plan_destroy": (i32, [vp, vp]),
+    "b200sp_sptrsv_symbolic_i32": (i32, [vp, vp, i32, vp, vp, i32]),
+    "b200sp_sptrsv_levels": (i32, [vp]),
+    "b200sp_sptrsv_solve_f64_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
+    "b200sp_sptrsv_solve_f32_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
     "b200sp_spmv_hostvec_flush": (i32, [vp, vp]),
     "b200sp_spmv64_plan_create": (i32, [C.POINTER(vp), i32]),
     "b200sp_spmv64_plan_destroy": (i32, [vp, vp]),

@@ -18,15 +18,30 @@
 // KokkosBlas call sequence computes (mult with beta = 0, scal, axpy), so the only difference to the reference is the summation
 // order inside the SpMVs.  No colouring, no atomics: deterministic and independent of the row order.  Several right-hand sides go
 // through the multivector products (spmm.cu), so a sweep reads the matrix once for all of them.
-// The sptrsv variant (two_stage = false, "classic" in the reference's unit test) is not provided: sptrsv is outside the path.
+// The sptrsv variant (two_stage = false, "classic" in the reference's unit test; B200SP_GS2_TWO_STAGE = 0): Z = (L + D)^{-1} R is a
+// level-set triangular solve on the lower (upper) triangle of A itself (sptrsv.cu, no copy of the triangle), then x += Z; omega
+// must be 1, as in the reference (:886-893).
 #include <algorithm>
 #include <new>
 
 #include "common.cuh"
 #include "scan.cuh"
 
+struct b200sp_sptrsv_plan;
+extern "C" int b200sp_sptrsv_plan_create(b200sp_sptrsv_plan** plan);
+extern "C" int b200sp_sptrsv_plan_destroy(b200sp_sptrsv_plan* plan, void* stream);
+namespace b200sp {
+int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const int* rp, const int* ci, bool lower, bool filter);
+template <typename S>
+int sptrsv_solve_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const int* rp, const int* ci, const S* v, const S* b, S* x,
+                      const S* dinv);
+}  // namespace b200sp
+
 struct b200sp_gs2_plan {
   bool compact = false;
+  bool two_stage = true;      // false: the classic form, triangular solves instead of inner Jacobi-Richardson sweeps
+  bool given_dinv = false;    // numeric was handed an inverse diagonal
+  b200sp_sptrsv_plan* tr[2] = {nullptr, nullptr};  // level sets of the lower / upper triangle of A (classic form)
   int inner = 1, outer = 1;
   double gamma = 1.0;
   bool symbolic = false, numeric = false;
@@ -276,6 +291,7 @@ int numeric_impl(b200sp_gs2_plan* p, cudaStream_t st, int n, int ncols, const in
                                                          p->compact ? 1 : 0);
     B200SP_LAUNCH_CHECK();
   }
+  p->given_dinv = given_dinv != nullptr;
   p->numeric = true;
   return B200SP_OK;
 }
@@ -297,6 +313,10 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
   B200SP_REQUIRE(nrhs == 1 || (ldx >= ncols && ldb >= n), "gs2_apply: leading dimensions too small (ldx=%lld ldb=%lld)", (long long)ldx,
                  (long long)ldb);
   const S one = S(1), gamma = (S)p->gamma;
+  if (!p->two_stage && omega != one) {  // the reference throws std::invalid_argument here (:886-893)
+    set_error("gs2_apply: omega != 1 is not supported by the classic (sptrsv) form");
+    return B200SP_ERR_INVALID_ARGUMENT;
+  }
   const int k = nrhs;
   const int64_t total = (int64_t)n * k;
   if (k > p->work_cols) {  // work vectors for k right-hand sides (numeric sizes them for one)
@@ -338,6 +358,17 @@ int apply_impl(b200sp_gs2_plan* p, void* stream, int n, int ncols, const int* ro
         rc = product<S>(p->plan[kA], stream, n, ncols, p->nnz, k, -one, row_ptr, col_idx, vals, x, ldx, one, R, n);
         if (rc) return rc;
       }
+    }
+    if (!p->two_stage) {
+      // ===== classic form: Z = (L + D)^{-1} R  or  (U + D)^{-1} R, one right-hand side at a time (:894-915), then x (+)= Z
+      for (int j = 0; j < k; ++j) {
+        rc = sptrsv_solve_impl<S>(p->tr[forward ? 0 : 1], st, n, row_ptr, col_idx, vals, R + (int64_t)j * n, Z + (int64_t)j * n,
+                                  p->given_dinv ? D : (const S*)nullptr);
+        if (rc) return rc;
+      }
+      gs2_update_kernel<S><<<nb, 256, 0, st>>>(n, Z, one, x, ldx, p->compact ? 1 : 0);
+      B200SP_LAUNCH_CHECK();
+      continue;
     }
     gs2_start_kernel<S><<<nb, 256, 0, st>>>(n, D, R, T, Z, gamma, p->inner);
     B200SP_LAUNCH_CHECK();
@@ -387,6 +418,7 @@ int b200sp_gs2_plan_create(b200sp_gs2_plan** plan) {
 int b200sp_gs2_plan_destroy(b200sp_gs2_plan* p, void* stream) {
   if (!p) return B200SP_OK;
   b200sp::release_parts(p, (cudaStream_t)stream);
+  for (int q = 0; q < 2; ++q) b200sp_sptrsv_plan_destroy(p->tr[q], stream);
   for (int q = 0; q < 5; ++q)
     if (p->plan[q]) b200sp_spmv_plan_destroy(p->plan[q], stream);
   delete p;
@@ -409,6 +441,10 @@ int b200sp_gs2_plan_set(b200sp_gs2_plan* p, int option, double value) {
       p->outer = (int)value;
       return B200SP_OK;
     case B200SP_GS2_INNER_DAMP_FACTOR: p->gamma = value; return B200SP_OK;
+    case B200SP_GS2_TWO_STAGE:
+      if ((value != 0.0) != p->two_stage) p->symbolic = p->numeric = false;  // the level sets are built by symbolic
+      p->two_stage = value != 0.0;
+      return B200SP_OK;
   }
   b200sp::set_error("gs2_plan_set: unknown option %d", option);
   return B200SP_ERR_INVALID_ARGUMENT;
@@ -469,6 +505,16 @@ int b200sp_gs2_symbolic_i32(b200sp_gs2_plan* p, void* stream, int n, int ncols, 
   gs2_entries_kernel<<<vec_blocks(n), 256, 0, st>>>(n, row_ptr, col_idx, p->rp[kL], p->ci[kL], p->rp[kU], p->ci[kU], p->rp[kLa], p->ci[kLa],
                                                     p->rp[kUa], p->ci[kUa], compact ? 1 : 0);
   B200SP_LAUNCH_CHECK();
+  if (!p->two_stage) {  // classic form: level sets of the lower and the upper triangle of A (sptrsv_symbolic, :685-697)
+    for (int q = 0; q < 2; ++q) {
+      if (!p->tr[q]) {
+        const int rc = b200sp_sptrsv_plan_create(&p->tr[q]);
+        if (rc) return rc;
+      }
+      const int rc = sptrsv_symbolic_impl(p->tr[q], st, n, row_ptr, col_idx, q == 0, true);
+      if (rc) return rc;
+    }
+  }
   p->symbolic = true;
   return B200SP_OK;
 }

@@ -11,7 +11,7 @@
 //   GS_DEFAULT / GS_PERMUTED / GS_TEAM -> the point multicolour kernels (b200sp_gs_*);
 //   GS_TWOSTAGE with inner Jacobi-Richardson sweeps -> b200sp_gs2_* (every product the library's SpMV), options read from the
 //     handle (isCompactForm, getNumInnerSweeps, getNumOuterSweeps, getInnerDampFactor) at symbolic / apply time;
-//   GS_CLUSTER, GS_TWOSTAGE with sptrsv (isTwoStage() == false), and point numeric with a given inverse diagonal -> forwarded to
+//   GS_CLUSTER and point numeric with a given inverse diagonal -> forwarded to
 //     the native specialisation (tpl_spec_avail = false) of the same struct, i.e. unchanged behaviour.
 // x / y with several columns: point sweeps column by column (independent systems), two-stage through nrhs.
 #ifndef KOKKOSSPARSE_GAUSS_SEIDEL_B200_TPL_SPEC_DECL_HPP_
@@ -69,10 +69,10 @@ inline int b200_call_gs2_apply(b200sp_gs2_plan* p, void* s, int n, int nc, const
 }
 // what this TPL serves; everything else goes to the native specialisation
 template <class KernelHandle>
-inline int b200_gs_kind(KernelHandle* handle) {  // 0 point, 1 two-stage (inner sweeps), -1 native
+inline int b200_gs_kind(KernelHandle* handle) {  // 0 point, 1 two-stage (inner sweeps or triangular solves), -1 native
   const auto a = handle->get_gs_handle()->get_algorithm_type();
   if (a == GS_CLUSTER) return -1;
-  if (a == GS_TWOSTAGE) return handle->get_twostage_gs_handle()->isTwoStage() ? 1 : -1;
+  if (a == GS_TWOSTAGE) return 1;  // both forms: inner Jacobi-Richardson sweeps and the classic one (sptrsv; isTwoStage() == false)
   return 0;
 }
 
@@ -95,6 +95,7 @@ inline int b200_gs_kind(KernelHandle* handle) {  // 0 point, 1 two-stage (inner 
         auto* gs2 = handle->get_twostage_gs_handle();                                                                  \
         b200sp_gs2_plan* p2 = b200_gs2_plan_of(gs2);                                                                   \
         KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_gs2_plan_set(p2, B200SP_GS2_COMPACT_FORM, gs2->isCompactForm() ? 1.0 : 0.0)); \
+        KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_gs2_plan_set(p2, B200SP_GS2_TWO_STAGE, gs2->isTwoStage() ? 1.0 : 0.0));     \
         KOKKOSSPARSE_IMPL_B200_SAFE_CALL(b200sp_gs2_symbolic_i32(p2, (void*)exec.cuda_stream(), num_rows, num_cols, row_map.data(), \
                                                                  entries.data()));                                     \
         gs2->set_call_symbolic(true);                                                                                  \

@@ -303,6 +303,51 @@ def _spmv_bsr(lib, plan, mc, alpha, A, x, beta, y, f64, xcols):
     return y
 
 
+class SPTRSVHandle:
+    """KokkosSparse::Experimental::SPTRSVHandle as far as sptrsv_symbolic / sptrsv_solve need it (sparse/src/KokkosSparse_sptrsv_handle.hpp:
+    is_lower_tri, nrows, the level sets): owns a b200sp_sptrsv_plan."""
+
+    def __init__(self, nrows, lower_tri):
+        self.nrows, self.lower_tri = int(nrows), bool(lower_tri)
+        self._plan = C.c_void_p(0)
+        check(_lib.sparse().b200sp_sptrsv_plan_create(C.byref(self._plan)))
+        self._symbolic = False
+
+    def is_lower_tri(self): return self.lower_tri
+    def get_nrows(self): return self.nrows
+    def get_num_levels(self): return _lib.sparse().b200sp_sptrsv_levels(self._plan)
+    def is_symbolic_complete(self): return self._symbolic
+
+    def __del__(self):
+        try:
+            if self._plan:
+                st = _stream() if torch.cuda.is_available() else C.c_void_p(0)
+                _lib.sparse().b200sp_sptrsv_plan_destroy(self._plan, st)
+                self._plan = C.c_void_p(0)
+        except Exception:
+            pass
+
+
+def sptrsv_symbolic(handle, row_map, entries):
+    """KokkosSparse::sptrsv_symbolic(handle, rowmap, entries) (sparse/src/KokkosSparse_sptrsv.hpp:40-170): the dependency levels of a
+    lower / upper triangular matrix whose diagonal is stored."""
+    if row_map.numel() != handle.nrows + 1:
+        raise B200SparseError("sptrsv_symbolic: row map does not match the handle's number of rows")
+    check(_lib.sparse().b200sp_sptrsv_symbolic_i32(handle._plan, _stream(), handle.nrows, _idx(row_map), _idx(entries), int(handle.lower_tri)))
+    handle._symbolic = True
+
+
+def sptrsv_solve(handle, row_map, entries, values, b, x):
+    """KokkosSparse::sptrsv_solve(handle, rowmap, entries, values, b, x) (sparse/src/KokkosSparse_sptrsv.hpp:290-480): x = T^{-1} b."""
+    if not handle._symbolic:
+        raise B200SparseError("sptrsv_solve: sptrsv_symbolic was not called on this handle")
+    if b.numel() != handle.nrows or x.numel() != handle.nrows:
+        raise B200SparseError("sptrsv_solve: vector lengths do not match the handle's number of rows")
+    fn = getattr(_lib.sparse(), f"b200sp_sptrsv_solve_{_sfx(values)}_i32")
+    check(fn(handle._plan, _stream(), handle.nrows, _idx(row_map), _idx(entries), _ptr(values), _ptr(b), _ptr(x)))
+    return x
+
+
 class GMRESHandle:
     """sparse/src/KokkosSparse_gmres_handle.hpp:66-186: options (m, tol, max_restart, ortho, verbose) and the statistics of the
     last run (num_iters, end_rel_res, conv_flag_val)."""
@@ -439,9 +484,11 @@ class TwoStageGaussSeidelHandle:
         check(_lib.sparse().b200sp_gs2_plan_set(self._plan, option, C.c_double(float(value))))
 
     def setTwoStage(self, two_stage):
-        if not two_stage:  # the sptrsv variant ("classic" in the reference's unit test) is outside the path
-            raise B200SparseError("b200sparse: two-stage Gauss-Seidel is provided with inner Jacobi-Richardson sweeps only (no sptrsv)")
-        self.two_stage = True
+        """False selects the classic form (gauss_seidel_handle.hpp:560-566): triangular solves (b200sp_sptrsv level sets on the
+        triangles of A) instead of inner Jacobi-Richardson sweeps; omega must be 1 then."""
+        self.two_stage = bool(two_stage)
+        self._set(5, self.two_stage)
+        self._symbolic = self._numeric = False
 
     def isTwoStage(self): return self.two_stage
 

@@ -20,7 +20,7 @@
  *             every SpMV is KokkosSparse::spmv("N", alpha, M, x, one, y): restated with the host loop order O1
  *             (kk_oracle.c okk_spmv_serial_*: y = beta*y + alpha*sum), KokkosBlas::mult / scal / axpy as written (mult with
  *             beta = 0 overwrites).
- * The sptrsv variant (two_stage = false, "classic" in the unit test) is not restated: sptrsv is outside the path.
+ * The sptrsv variant (two_stage = false, "classic" in the unit test) is restated in kk_oracle_sptrsv.c.
  * Pinned by (a) the definition -- with enough inner sweeps the inner iteration converges to the triangular solve, so a
  * forward sweep equals textbook Gauss-Seidel to rounding (tests/test_oracle_gs2.py) -- and (b) the reference unit test's
  * acceptance (sparse/unit_test/Test_Sparse_gauss_seidel.hpp:236-241: error norm below the initial one).  Parity unpinned

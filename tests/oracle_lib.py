@@ -74,6 +74,10 @@ class Oracle:
         L.okk_gs2_apply_f64.argtypes = [i32, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, i32, f64, i32, i32]
         L.okk_gs2_apply_f32.argtypes = [i32, i32, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, i32, f32, i32, i32]
         L.okk_gs2_apply_f64.restype = L.okk_gs2_apply_f32.restype = i32
+        L.okk_sptrsv_f64.argtypes = L.okk_sptrsv_f32.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp]
+        L.okk_sptrsv_f64.restype = L.okk_sptrsv_f32.restype = i32
+        L.okk_gs2_classic_apply_f64.argtypes = L.okk_gs2_classic_apply_f32.argtypes = [i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, i32]
+        L.okk_gs2_classic_apply_f64.restype = L.okk_gs2_classic_apply_f32.restype = i32
         L.okk_cg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64)]
         L.okk_cg_f64.restype = i32
         L.okk_pcg_f64.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, C.POINTER(f64), i32, vp, vp, vp]
@@ -320,6 +324,26 @@ class Oracle:
         """Point Gauss-Seidel sweeps over the given colour sets (direction 0 symmetric, 1 forward, 2 backward); x in place."""
         getattr(self.lib, "okk_gs_apply_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), len(color_ptr) - 1, _p(color_ptr), _p(color_rows),
                                                          _p(dinv), _p(y), _p(x), int(init_zero_x), omega, sweeps, direction)
+        return x
+
+    def sptrsv(self, rp, ci, v, b, lower, side=0, inverse_diagonal=None):
+        """x = T^{-1} b by serial substitution in storage order.  side 0: T as given (raises on an entry on the wrong side of the
+        diagonal), 1 / 2: the lower / upper triangle of a general matrix."""
+        x = np.zeros(len(rp) - 1, dtype=v.dtype)
+        rc = getattr(self.lib, "okk_sptrsv_" + self._sfx(v))(len(rp) - 1, _p(rp), _p(ci), _p(v), _p(b), _p(x), int(lower), int(side),
+                                                            _p(inverse_diagonal))
+        if rc:
+            raise ValueError(f"row {rc - 1} has an entry on the wrong side of the diagonal")
+        return x
+
+    def gs2_classic_apply(self, rp, ci, v, ncols, x, b, init_zero_x, num_iter, direction, compact=False, outer_sweeps=1,
+                          inverse_diagonal=None):
+        """The classic (sptrsv) form of the two-stage Gauss-Seidel: triangular solves instead of inner sweeps, omega = 1."""
+        rc = getattr(self.lib, "okk_gs2_classic_apply_" + self._sfx(v))(len(rp) - 1, ncols, _p(rp), _p(ci), _p(v), _p(inverse_diagonal),
+                                                                       int(compact), outer_sweeps, _p(x), _p(b), int(init_zero_x), num_iter,
+                                                                       direction)
+        if rc:
+            raise ValueError(f"row {rc - 1}: bad triangular structure")
         return x
 
     def gs2_apply(self, rp, ci, v, ncols, x, b, init_zero_x, omega, num_iter, direction, compact=False, inner_sweeps=1, outer_sweeps=1,

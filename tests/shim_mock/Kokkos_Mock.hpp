@@ -490,7 +490,7 @@ template <class Exec, class KH, KokkosSparse::SparseMatrixFormat format, class a
           bool tpl = gauss_seidel_apply_tpl_spec_avail<KH, a_r, a_e, a_v, x_v, y_v>::value, bool eti = true>
 struct GAUSS_SEIDEL_APPLY;
 // the native bodies (tpl = false; sparse/impl/KokkosSparse_gauss_seidel_spec.hpp:153-262): stand-ins that count their calls -- the
-// B200 specialisations forward what they do not serve (cluster Gauss-Seidel, the sptrsv variant of the two-stage method)
+// B200 specialisations forward what they do not serve (cluster Gauss-Seidel)
 inline int& mock_native_gs_calls() {
   static int n = 0;
   return n;

@@ -83,8 +83,8 @@ def test_reference_unit_test_and_multivectors(cuda, oracle):
             xo = np.zeros(n)
             oracle.gs2_apply(rp, ci, v, n, xo, np.ascontiguousarray(Y[:, j]), True, 0.9, 2, direction)
             assert np.allclose(X[:, j], xo, rtol=0, atol=1e-13)
-    with pytest.raises(sp.B200SparseError):
-        kh.set_gs_twostage(False, n)  # the sptrsv variant is not provided
+    kh.set_gs_twostage(False, n)  # the classic (sptrsv) form: tests/test_gpu_sptrsv.py; switching resets the phases
+    assert not kh.get_twostage_gs_handle().isTwoStage() and not kh.get_twostage_gs_handle().is_symbolic_called()
     kh2 = sp.KokkosKernelsHandle()
     kh2.create_gs_handle()
     with pytest.raises(sp.B200SparseError):

@@ -146,6 +146,8 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }  // built with -ffp-contract=off: no fusion
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __double2loint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b & 0xffffffffull); }
 static inline int __double2hiint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b >> 32); }
 static inline double __hiloint2double(int hi, int lo) {
