@@ -249,7 +249,7 @@ int b200sp_spgemm_numeric_f32_i32(b200sp_spgemm_plan* plan, void* stream, int m,
  * square and holds its diagonal, so that row i of B lies inside the pattern of row i of A*B -- the reference's
  * kernels assume the same; rows that violate it are completed without writing past their extent).  dinv has m
  * entries (the reference passes an m x 1 view).  C rows come out sorted.  B200SP_ERR_STATE without a prior
- * symbolic.  Asynchronous on `stream`.  (First GPU run pending: tests are marked gpu_next.) */
+ * symbolic.  Asynchronous on `stream`. */
 int b200sp_spgemm_jacobi_f64_i32(b200sp_spgemm_plan* plan, void* stream, int m, int n, int k,
                                  const int* row_ptr_A, const int* col_idx_A, const double* vals_A,
                                  const int* row_ptr_B, const int* col_idx_B, const double* vals_B,

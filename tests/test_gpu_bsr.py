@@ -8,8 +8,7 @@ import torch
 
 from bsr_cases import BLOCK_SIZES, COEFS_ALPHA, COEFS_BETA, PRIME_CASE, SHAPES, bsr_random, op_max_nnz_per_row, tolerance
 
-# first GPU run pending (written after the round's GPU budget was spent; validated under the CPU emulation): promote to
-# `gpu` once tools/gpu_check's `bsr` suite and this file have passed on a B200
+# first run on a B200: round 2 (profiles/r02_pytest_gpu_next_first_run.log); part of `pytest -m gpu` since
 pytestmark = pytest.mark.gpu
 
 CASES = [(bs, mb, nb) for (mb, nb) in SHAPES for bs in BLOCK_SIZES] + [PRIME_CASE]

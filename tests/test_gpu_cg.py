@@ -7,7 +7,7 @@ import torch
 
 from test_oracle_cg import spd_lap27
 
-# first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
+# first run on a B200: round 2 (profiles/r02_pytest_gpu_next_first_run.log); part of `pytest -m gpu` since
 pytestmark = pytest.mark.gpu
 
 

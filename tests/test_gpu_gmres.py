@@ -8,7 +8,7 @@ import torch
 
 from gmres_cases import crs_to_bsr, gmres_matrix, true_rel_res
 
-# first GPU run pending (validated under the CPU emulation): promote to `gpu` after it has passed on a B200
+# first run on a B200: round 2 (profiles/r02_pytest_gpu_next_first_run.log); part of `pytest -m gpu` since
 pytestmark = pytest.mark.gpu
 
 

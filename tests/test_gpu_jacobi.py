@@ -7,8 +7,7 @@ import torch
 
 from test_oracle_jacobi import diag_dominant
 
-# first GPU run pending (written after the round's GPU budget was spent): promote to `gpu` after tools/gpu_check's
-# `jacobi` suite and this file have passed on a B200
+# first run on a B200: round 2 (profiles/r02_pytest_gpu_next_first_run.log); part of `pytest -m gpu` since
 pytestmark = pytest.mark.gpu
 
 
