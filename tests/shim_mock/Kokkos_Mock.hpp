@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 namespace Kokkos {
 struct LayoutLeft {};
@@ -125,6 +126,7 @@ template <class Scalar, class Ordinal, class Dev, class MT, class Offset>
 class BsrMatrix {
  public:
   using UM = Kokkos::MemoryTraits<Kokkos::Unmanaged>;
+  using non_const_value_type = typename std::remove_const<Scalar>::type;
   struct Graph {
     Kokkos::View<Offset*, Kokkos::LayoutLeft, Dev, UM> row_map;
     Kokkos::View<Ordinal*, Kokkos::LayoutLeft, Dev, UM> entries;
@@ -194,6 +196,7 @@ struct SPMV_MV;
 
 #endif  // B200_SHIM_REFERENCE_SPEC
 
+#ifndef B200_SHIM_REFERENCE_SPEC
 // sparse/tpls/KokkosSparse_spmv_bsrmatrix_tpl_spec_avail.hpp:27-30,121-124 and
 // sparse/impl/KokkosSparse_spmv_bsrmatrix_spec.hpp:89-112 (eti always true in the mock, as in a library build)
 template <class ExecutionSpace, class Handle, class AMatrix, class XVector, class YVector>
@@ -212,6 +215,7 @@ template <class ExecutionSpace, class Handle, class AMatrix, class XVector, clas
           bool tpl_spec_avail = spmv_mv_bsrmatrix_tpl_spec_avail<ExecutionSpace, Handle, AMatrix, XVector, YVector>::value,
           bool eti_spec_avail = true>
 struct SPMV_MV_BSRMATRIX;
+#endif  // B200_SHIM_REFERENCE_SPEC
 }  // namespace Impl
 }  // namespace KokkosSparse
 
@@ -253,6 +257,8 @@ struct b200sp_gs2_plan;
 extern "C" int b200sp_gs2_plan_destroy(b200sp_gs2_plan*, void*);
 struct b200sp_spmv_plan;
 struct b200sp_bsr_plan;
+struct b200sp_sptrsv_plan;
+extern "C" int b200sp_sptrsv_plan_destroy(b200sp_sptrsv_plan*, void*);
 extern "C" int b200sp_spmv_plan_destroy(b200sp_spmv_plan*, void*);
 extern "C" int b200sp_bsr_plan_destroy(b200sp_bsr_plan*, void*);
 
@@ -286,7 +292,22 @@ struct GMRESHandleMock {
   b200sp_spmv_plan* b200_spmv_plan = nullptr;
   b200sp_bsr_plan* b200_bsr_plan   = nullptr;
 };
+// the SPTRSVHandle members the shim touches (sparse/src/KokkosSparse_sptrsv_handle.hpp:897-947) + the plan member INTEGRATION.md adds
+struct SPTRSVHandleMock {
+  SPTRSVHandleMock(size_t nrows_, bool lower_) : nrows(nrows_), lower_tri(lower_) {}
+  ~SPTRSVHandleMock() {
+    if (b200_sptrsv_plan) b200sp_sptrsv_plan_destroy(b200_sptrsv_plan, nullptr);
+  }
+  size_t get_nrows() const { return nrows; }
+  bool is_lower_tri() const { return lower_tri; }
+  bool is_symbolic_complete() const { return symbolic_complete; }
+  void set_symbolic_complete() { symbolic_complete = true; }
+  size_t nrows;
+  bool lower_tri, symbolic_complete = false;
+  b200sp_sptrsv_plan* b200_sptrsv_plan = nullptr;
+};
 namespace Experimental {
+enum class SPTRSVAlgorithm { SEQLVLSCHD_RP, SEQLVLSCHD_TP1, SPTRSV_CUSPARSE };
 template <class AMatrix>
 struct Preconditioner {  // sparse/src/KokkosSparse_Preconditioner.hpp: the base class gmres takes a pointer to
   virtual ~Preconditioner() {}
@@ -436,6 +457,17 @@ struct KokkosKernelsHandle {
     gmh = nullptr;
   }
   KokkosSparse::GMRESHandleMock* gmh = nullptr;
+  // sparse/src/KokkosKernels_Handle.hpp:765-850
+  KokkosSparse::SPTRSVHandleMock* get_sptrsv_handle() { return tsh; }
+  void create_sptrsv_handle(KokkosSparse::Experimental::SPTRSVAlgorithm, size_t nrows, bool lower_tri) {
+    destroy_sptrsv_handle();
+    tsh = new KokkosSparse::SPTRSVHandleMock(nrows, lower_tri);
+  }
+  void destroy_sptrsv_handle() {
+    delete tsh;
+    tsh = nullptr;
+  }
+  KokkosSparse::SPTRSVHandleMock* tsh = nullptr;
   using SPADDHandleType = KokkosSparse::SPADDHandleMock;
   SPADDHandleType* get_spadd_handle() { return ah; }
   void create_spadd_handle(bool input_sorted = false, bool input_merged = false) { ah = new SPADDHandleType(input_sorted, input_merged); }
@@ -460,6 +492,21 @@ struct spgemm_numeric_tpl_spec_avail {
   enum : bool { value = false };
 };
 #endif  // B200_SHIM_REFERENCE_SPEC
+#ifndef B200_SHIM_REFERENCE_SPEC
+// sparse/tpls/KokkosSparse_sptrsv_{symbolic,solve}_tpl_spec_avail.hpp, sparse/impl/KokkosSparse_sptrsv_{symbolic,solve}_spec.hpp
+template <class KH, class a_r, class a_e>
+struct sptrsv_symbolic_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class Exec, class KH, class a_r, class a_e, class a_v, class BType, class XType>
+struct sptrsv_solve_tpl_spec_avail {
+  enum : bool { value = false };
+};
+template <class Exec, class KH, class a_r, class a_e, bool tpl = sptrsv_symbolic_tpl_spec_avail<KH, a_r, a_e>::value, bool eti = true>
+struct SPTRSV_SYMBOLIC;
+template <class Exec, class KH, class a_r, class a_e, class a_v, class BType, class XType,
+          bool tpl = sptrsv_solve_tpl_spec_avail<Exec, KH, a_r, a_e, a_v, BType, XType>::value, bool eti = true>
+struct SPTRSV_SOLVE;
 // sparse/tpls/KokkosSparse_gmres_tpl_spec_avail.hpp:26-29, sparse/impl/KokkosSparse_gmres_spec.hpp:69-82
 template <class KH, class AT, class AO, class AD, class AM, class AS, class BType, class XType>
 struct gmres_tpl_spec_avail {
@@ -525,6 +572,7 @@ struct spgemm_jacobi_tpl_spec_avail {
 template <class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e, class c_v, class dinv_v,
           bool tpl = spgemm_jacobi_tpl_spec_avail<KH, a_r, a_e, a_v, b_r, b_e, b_v, c_r, c_e, c_v, dinv_v>::value, bool eti = true>
 struct SPGEMM_JACOBI;
+#endif  // B200_SHIM_REFERENCE_SPEC
 #ifndef B200_SHIM_REFERENCE_SPEC
 template <class KH, class a_r, class a_e, class b_r, class b_e, class c_r, bool tpl, bool eti>
 struct SPGEMM_SYMBOLIC;
@@ -537,6 +585,7 @@ struct SPGEMM_NUMERIC;
 
 namespace KokkosSparse {
 namespace Impl {
+#ifndef B200_SHIM_REFERENCE_SPEC
 template <class ExecSpace, class KH, class a_r, class a_e, class b_r, class b_e, class c_r>
 struct spadd_symbolic_tpl_spec_avail {
   enum : bool { value = false };
@@ -551,5 +600,6 @@ struct SPADD_SYMBOLIC;
 template <class ExecSpace, class KH, class a_r, class a_e, class a_v, class b_r, class b_e, class b_v, class c_r, class c_e,
           class c_v, bool tpl, bool eti>
 struct SPADD_NUMERIC;
+#endif  // B200_SHIM_REFERENCE_SPEC
 }  // namespace Impl
 }  // namespace KokkosSparse

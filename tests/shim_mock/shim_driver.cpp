@@ -17,10 +17,14 @@
 #include "KokkosSparse_gmres_b200_tpl_spec_avail.hpp"
 #include "KokkosSparse_gmres_b200_tpl_spec_decl.hpp"
 #include "KokkosSparse_spmv_bsrmatrix_b200_tpl_spec_decl.hpp"
+#include "KokkosSparse_sptrsv_b200_tpl_spec_avail.hpp"
+#include "KokkosSparse_sptrsv_b200_tpl_spec_decl.hpp"
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -76,6 +80,7 @@ T* to_dev(const std::vector<T>& h) {
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
   bool with_bsr = false, with_jacobi = false, with_gs = false, with_gmres = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
+  bool with_sptrsv = false;                                                          // --sptrsv: SPTRSV_SYMBOLIC / SPTRSV_SOLVE
   bool with_spmv64 = false;                                                          // --spmv64: the 64-bit-offset specialisations
   for (int a = 1; a < argc; ++a) {
     with_bsr |= std::string(argv[a]) == "--bsr";
@@ -83,6 +88,7 @@ int main(int argc, char** argv) {
     with_gs |= std::string(argv[a]) == "--gs";
     with_gmres |= std::string(argv[a]) == "--gmres";
     with_spmv64 |= std::string(argv[a]) == "--spmv64";
+    with_sptrsv |= std::string(argv[a]) == "--sptrsv";
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -452,6 +458,70 @@ int main(int argc, char** argv) {
     cudaFree(d_vd);
     cudaFree(d_b);
     cudaFree(d_xx);
+  }
+  if (with_sptrsv) {
+    // sptrsv through SPTRSV_SYMBOLIC / SPTRSV_SOLVE<...,true,true>: the lower and the upper triangle (diagonal 3) of the matrix above,
+    // against the serial substitution loop (bit for bit: the library computes every row in storage order with unfused operations)
+    using UMRAV = Kokkos::MemoryTraits<Kokkos::Unmanaged | Kokkos::RandomAccess>;
+    using TRI   = Kokkos::View<const int*, KokkosKernels::default_layout, Dev, UMRAV>;
+    using TRS   = Kokkos::View<const double*, KokkosKernels::default_layout, Dev, UMRAV>;
+    using TRX   = Kokkos::View<double*, KokkosKernels::default_layout, Dev, UM>;
+    using TSY   = Impl::SPTRSV_SYMBOLIC<Kokkos::Cuda, KH, TRI, TRI, true, true>;
+    using TSO   = Impl::SPTRSV_SOLVE<Kokkos::Cuda, KH, TRI, TRI, TRS, TRS, TRX, true, true>;
+    static_assert(Impl::sptrsv_symbolic_tpl_spec_avail<KH, TRI, TRI>::value, "sptrsv_symbolic must be available");
+    static_assert(Impl::sptrsv_solve_tpl_spec_avail<Kokkos::Cuda, KH, TRI, TRI, TRS, TRS, TRX>::value, "sptrsv_solve must be available");
+    int f10 = 0;
+    for (int lower = 1; lower >= 0; --lower) {
+      std::vector<int> trp(n + 1, 0), tci;
+      std::vector<double> tva, bh(n), xr(n), xg(n);
+      for (int i = 0; i < n; ++i) {
+        for (int q = rp[i]; q < rp[i + 1]; ++q)
+          if (lower ? ci[q] <= i : ci[q] >= i) {
+            tci.push_back(ci[q]);
+            tva.push_back(ci[q] == i ? 3.0 : va[q]);
+          }
+        trp[i + 1] = (int)tci.size();
+        bh[i]      = 1.0 + 0.5 * std::cos(0.02 * i);
+      }
+      for (int t = 0; t < n; ++t) {
+        const int i = lower ? t : n - 1 - t;
+        volatile double acc = bh[i];  // volatile: no contraction of the multiply and the subtract
+        double d            = 1.0;
+        for (int q = trp[i]; q < trp[i + 1]; ++q) {
+          if (tci[q] == i) d = tva[q];
+          else {
+            volatile double prod = tva[q] * xr[tci[q]];
+            acc                  = acc - prod;
+          }
+        }
+        xr[i] = acc / d;
+      }
+      int *d_trp = to_dev(trp), *d_tci = to_dev(tci);
+      double *d_tva = to_dev(tva), *d_b = to_dev(bh), *d_xx = to_dev(xg);
+      KH kh;
+      kh.create_sptrsv_handle(Experimental::SPTRSVAlgorithm::SEQLVLSCHD_TP1, n, lower != 0);
+      TRI vrp(d_trp, n + 1), vci(d_tci, tci.size());
+      bool threw = false;
+      try {
+        TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, n), TRX(d_xx, n));
+      } catch (const std::runtime_error&) { threw = true; }
+      if (!threw) ++f10;  // solve before symbolic is an error, as in the front end (sparse/src/KokkosSparse_sptrsv.hpp:300-310)
+      TSY::sptrsv_symbolic(exec, &kh, vrp, vci);
+      if (!kh.get_sptrsv_handle()->is_symbolic_complete()) ++f10;
+      TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, n), TRX(d_xx, n));
+      exec.fence();
+      cudaMemcpy(xg.data(), d_xx, sizeof(double) * n, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < n; ++i)
+        if (std::memcmp(&xg[i], &xr[i], sizeof(double)) != 0) ++f10;
+      kh.destroy_sptrsv_handle();
+      cudaFree(d_trp);
+      cudaFree(d_tci);
+      cudaFree(d_tva);
+      cudaFree(d_b);
+      cudaFree(d_xx);
+    }
+    std::printf("sptrsv through SPTRSV_SYMBOLIC / SPTRSV_SOLVE<...,true,true> (lower and upper) : %d mismatches\n", f10);
+    failures += f10;
   }
   if (with_bsr) {
     // BsrMatrix: block-tridiagonal, 3 x 3 blocks, through SPMV_BSRMATRIX<...,true,true> (N) and

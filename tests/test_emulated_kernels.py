@@ -339,12 +339,12 @@ def test_harness_runs_emulated(suite, order):
 def test_kokkos_shim_driver_emulated():
     """tests/shim_mock/shim_driver.cpp -- the Kokkos TPL specialisations of kokkos_shim/ instantiated as KokkosSparse::spmv /
     spgemm / spadd would -- built against the emulated library: SPMV, SPMV_MV, SPGEMM_*, SPADD_* and (--bsr, --jacobi) the
-    BsrMatrix, SPGEMM_JACOBI, GAUSS_SEIDEL_* and GMRES specialisations run end to end on the host."""
+    BsrMatrix, SPGEMM_JACOBI, GAUSS_SEIDEL_*, GMRES and SPTRSV_* specialisations run end to end on the host."""
     E.harness()  # builds everything under tools/emu/_build
     drv = os.path.join(os.path.dirname(E.harness()), "shim_driver_emu")
-    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64", "--sptrsv"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 13, out.stdout
+    assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 14, out.stdout
 
 
 @pytest.mark.skipif(os.environ.get("B200EMU_NESTED") == "1", reason="this is the nested run")

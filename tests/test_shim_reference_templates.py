@@ -1,5 +1,6 @@
 """The Kokkos Kernels specialisations of kokkos-kernels_b200/kokkos_shim compiled against the REFERENCE'S OWN declarations of
-the unification structs (SPMV, SPMV_MV, SPGEMM_SYMBOLIC, SPGEMM_NUMERIC and their *_tpl_spec_avail traits), included where
+the unification structs (SPMV, SPMV_MV, SPGEMM_SYMBOLIC, SPGEMM_NUMERIC, SPGEMM_JACOBI, SPADD_*, SPMV_BSRMATRIX, SPMV_MV_BSRMATRIX,
+GAUSS_SEIDEL_*, GMRES, SPTRSV_* and their *_tpl_spec_avail traits), included where
 they lie under /root/reference -- tests/shim_ref/check_slots.cpp.  A template-argument mismatch fails to compile instead of
 silently not being selected.  Runs only where the reference tree exists (this container); TEST INFRASTRUCTURE."""
 import os
