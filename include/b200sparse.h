@@ -475,13 +475,16 @@ int b200sp_gs2_apply_f32_i32(b200sp_gs2_plan* plan, void* stream, int n, int nco
 /* Sparse triangular solve x = T^{-1} b on a lower or upper triangular CrsMatrix with its diagonal stored (any position in the
  * row) -- KokkosSparse::sptrsv_symbolic / sptrsv_solve (sparse/src/KokkosSparse_sptrsv.hpp:40-170, :290-480), which the classic
  * two-stage Gauss-Seidel above calls.  symbolic groups the rows into dependency levels (synchronises `stream`; an entry on the
- * wrong side of the diagonal is B200SP_ERR_INVALID_ARGUMENT); solve runs one launch per level and computes every row as the
- * serial substitution loop does (storage order, unfused multiply / subtract, one division): bit-identical to it. */
+ * wrong side of the diagonal is B200SP_ERR_INVALID_ARGUMENT); solve runs one launch per level -- or one single-CTA launch for a
+ * run of consecutive levels of at most 512 rows each (environment B200SP_SPTRSV_CHAIN=0 at symbolic time: always one per level)
+ * -- and computes every row as the serial substitution loop does (storage order, unfused multiply / subtract, one division):
+ * bit-identical to it.  _levels / _launches: the number of dependency levels and of kernel launches of one solve. */
 typedef struct b200sp_sptrsv_plan b200sp_sptrsv_plan;
 int b200sp_sptrsv_plan_create(b200sp_sptrsv_plan** plan);
 int b200sp_sptrsv_plan_destroy(b200sp_sptrsv_plan* plan, void* stream);
 int b200sp_sptrsv_symbolic_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx, int is_lower);
 int b200sp_sptrsv_levels(const b200sp_sptrsv_plan* plan);
+int b200sp_sptrsv_launches(const b200sp_sptrsv_plan* plan);
 int b200sp_sptrsv_solve_f64_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,
                                 const double* vals, const double* b, double* x);
 int b200sp_sptrsv_solve_f32_i32(b200sp_sptrsv_plan* plan, void* stream, int n, const int* row_ptr, const int* col_idx,

@@ -34,6 +34,7 @@ SPARSE_API = {
     "b200sp_sptrsv_plan_destroy": (i32, [vp, vp]),
     "b200sp_sptrsv_symbolic_i32": (i32, [vp, vp, i32, vp, vp, i32]),
     "b200sp_sptrsv_levels": (i32, [vp]),
+    "b200sp_sptrsv_launches": (i32, [vp]),
     "b200sp_sptrsv_solve_f64_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
     "b200sp_sptrsv_solve_f32_i32": (i32, [vp, vp, i32, vp, vp, vp, vp, vp]),
     "b200sp_spmv_hostvec_flush": (i32, [vp, vp]),

@@ -13,9 +13,15 @@
 //             The Gauss-Seidel form solves with the lower (upper) triangle of a general matrix: the entries on the other side and
 //             the ghost columns are skipped (`filter`), no copy of the triangle is made; with a caller-supplied inverse diagonal
 //             the diagonal is 1 / dinv_i, as in the reference.
-// A correctness-first kernel set: a 3-D stencil has O(n^(1/3)) levels, i.e. hundreds of small launches per solve.
+//             Runs of consecutive SMALL levels (<= TR_CHAIN_ROWS rows each: the first and last planes of a stencil, all of a
+//             banded matrix) are solved by ONE launch of a single CTA that walks them with a CTA barrier in between -- the
+//             dependent-launch latency of a level becomes a barrier plus one load round trip (B200SP_SPTRSV_CHAIN=0: off).
+//   symbolic sweeps are launched TR_SWEEP_BATCH at a time between two read-backs of the progress counter (a sweep after the
+//             last row was resolved changes nothing).
 #include <algorithm>
+#include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,10 +34,24 @@ struct b200sp_sptrsv_plan {
   int n_levels = 0;
   int* level_rows = nullptr;      // rows grouped by level (device)
   int* level_ptr_host = nullptr;  // n_levels + 1 offsets (host)
+  int* level_ptr_dev = nullptr;   // the same on the device (the chain kernel walks it)
+  struct Segment {
+    int l0, l1;  // levels [l0, l1): one launch per level, or one single-CTA launch for the whole run when `chain`
+    bool chain;
+  };
+  std::vector<Segment> segments;
 };
 
 namespace b200sp {
 namespace {
+
+constexpr int TR_CHAIN_ROWS   = 512;  // a level of at most this many rows is "small": one CTA of this many threads solves it
+constexpr int TR_SWEEP_BATCH  = 8;    // symbolic: relaxation sweeps per read-back
+
+inline bool tr_chain_enabled() {
+  const char* e = getenv("B200SP_SPTRSV_CHAIN");
+  return !(e && e[0] == '0');
+}
 
 inline int tr_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8)); }
 
@@ -39,8 +59,9 @@ inline int tr_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int6
 // entries on the wrong side of the diagonal
 __global__ void __launch_bounds__(256) tr_level_sweep_kernel(int n, const int* __restrict__ rp, const int* __restrict__ ci, int lower,
                                                              int filter, const int* __restrict__ prev, int* __restrict__ cur,
-                                                             int* __restrict__ resolved, int* __restrict__ bad) {
-  int mine = 0;
+                                                             int* __restrict__ resolved, int* __restrict__ bad,
+                                                             int* __restrict__ max_level) {
+  int mine = 0, top = -1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int lv = prev[i];
     if (lv < 0) {
@@ -65,11 +86,15 @@ __global__ void __launch_bounds__(256) tr_level_sweep_kernel(int n, const int* _
       if (ready) {
         lv = mx + 1;
         ++mine;
+        top = lv > top ? lv : top;
       }
     }
     cur[i] = lv;
   }
-  if (mine) atomicAdd(resolved, mine);
+  if (mine) {
+    atomicAdd(resolved, mine);
+    atomicMax(max_level, top);
+  }
 }
 
 __global__ void __launch_bounds__(256) tr_fill_kernel(int n, int* __restrict__ a, int v) {
@@ -96,37 +121,62 @@ __device__ __forceinline__ double tr_sub<double>(double a, double b) { return __
 template <>
 __device__ __forceinline__ float tr_sub<float>(float a, float b) { return __fsub_rn(a, b); }
 
-// the rows of one level
+// one row of the substitution
 // side: 0 = every off-diagonal entry takes part (a triangular matrix), 1 = only columns < i (the lower triangle of a general
 // matrix), 2 = only columns in (i, n) (its upper triangle).  dinv: the caller's inverse diagonal or null.
+template <typename S>
+__device__ __forceinline__ void tr_solve_row(int i, int n, const int* __restrict__ rp, const int* __restrict__ ci, const S* __restrict__ v,
+                                             const S* __restrict__ b, S* x, int side, const S* __restrict__ dinv) {
+  S acc = b[i];
+  S d = S(1);
+  for (int k = rp[i]; k < rp[i + 1]; ++k) {
+    const int c = ci[k];
+    if (c == i) {
+      d = v[k];
+      continue;
+    }
+    if (side == 1 && c > i) continue;
+    if (side == 2 && (c < i || c >= n)) continue;
+    acc = tr_sub(acc, tr_mul(v[k], x[c]));
+  }
+  // a caller-supplied INVERSE diagonal enters as the diagonal 1 / dinv_i (twostage_gauss_seidel_impl.hpp:446-456)
+  x[i] = dinv ? acc / (S(1) / dinv[i]) : acc / d;
+}
+
+// the rows of one level
 template <typename S>
 __global__ void __launch_bounds__(256) tr_solve_level_kernel(int count, const int* __restrict__ rows, int n, const int* __restrict__ rp,
                                                              const int* __restrict__ ci, const S* __restrict__ v, const S* __restrict__ b,
                                                              S* __restrict__ x, int side, const S* __restrict__ dinv) {
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
-    const int i = rows[q];
-    S acc = b[i];
-    S d = S(1);
-    for (int k = rp[i]; k < rp[i + 1]; ++k) {
-      const int c = ci[k];
-      if (c == i) {
-        d = v[k];
-        continue;
-      }
-      if (side == 1 && c > i) continue;
-      if (side == 2 && (c < i || c >= n)) continue;
-      acc = tr_sub(acc, tr_mul(v[k], x[c]));
-    }
-    // a caller-supplied INVERSE diagonal enters as the diagonal 1 / dinv_i (twostage_gauss_seidel_impl.hpp:446-456)
-    x[i] = dinv ? acc / (S(1) / dinv[i]) : acc / d;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x)
+    tr_solve_row<S>(rows[q], n, rp, ci, v, b, x, side, dinv);
+}
+
+// levels [l0, l1), each of at most blockDim.x rows, by ONE CTA: the x written in a level is read by the next one after the CTA
+// barrier (global writes of a CTA are visible to its own threads after __syncthreads; x is not `restrict` here: it is read and
+// written through the same pointer)
+template <typename S>
+__global__ void __launch_bounds__(TR_CHAIN_ROWS) tr_solve_chain_kernel(int l0, int l1, const int* __restrict__ level_ptr,
+                                                                       const int* __restrict__ rows, int n, const int* __restrict__ rp,
+                                                                       const int* __restrict__ ci, const S* __restrict__ v,
+                                                                       const S* __restrict__ b, S* x, int side, const S* __restrict__ dinv) {
+  int q0 = level_ptr[l0];
+  for (int l = l0; l < l1; ++l) {
+    const int q1 = level_ptr[l + 1];
+    for (int q = q0 + (int)threadIdx.x; q < q1; q += (int)blockDim.x) tr_solve_row<S>(rows[q], n, rp, ci, v, b, x, side, dinv);
+    q0 = q1;
+    __syncthreads();
   }
 }
 
 void tr_release(b200sp_sptrsv_plan* p, cudaStream_t st) {
   if (p->level_rows) cudaFreeAsync(p->level_rows, st);
   p->level_rows = nullptr;
+  if (p->level_ptr_dev) cudaFreeAsync(p->level_ptr_dev, st);
+  p->level_ptr_dev = nullptr;
   delete[] p->level_ptr_host;
   p->level_ptr_host = nullptr;
+  p->segments.clear();
   p->n_levels = 0;
   p->symbolic = false;
 }
@@ -150,16 +200,21 @@ int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const in
   int *lv[2], *cnt;
   B200SP_CUDA_TRY(tmp.alloc(&lv[0], n));
   B200SP_CUDA_TRY(tmp.alloc(&lv[1], n));
-  B200SP_CUDA_TRY(tmp.alloc(&cnt, 2));
+  B200SP_CUDA_TRY(tmp.alloc(&cnt, 3));
   tr_fill_kernel<<<tr_blocks(n), 256, 0, st>>>(n, lv[0], -1);
   B200SP_LAUNCH_CHECK();
-  int h[2] = {0, n};  // rows resolved so far, smallest offending row
+  int h[3] = {0, n, -1};  // rows resolved so far, smallest offending row, highest level handed out
   B200SP_CUDA_TRY(cudaMemcpyAsync(cnt, h, sizeof(h), cudaMemcpyHostToDevice, st));
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));
-  int cur = 0, done = 0, levels = 0;
+  int cur = 0, done = 0;
   while (done < n) {
-    tr_level_sweep_kernel<<<tr_blocks(n), 256, 0, st>>>(n, rp, ci, lower ? 1 : 0, filter ? 1 : 0, lv[cur], lv[cur ^ 1], cnt, cnt + 1);
-    B200SP_LAUNCH_CHECK();
+    // a sweep resolves exactly the rows of the next level; sweeps after the last one copy the levels unchanged
+    for (int k = 0; k < TR_SWEEP_BATCH; ++k) {
+      tr_level_sweep_kernel<<<tr_blocks(n), 256, 0, st>>>(n, rp, ci, lower ? 1 : 0, filter ? 1 : 0, lv[cur], lv[cur ^ 1], cnt, cnt + 1,
+                                                           cnt + 2);
+      B200SP_LAUNCH_CHECK();
+      cur ^= 1;
+    }
     B200SP_CUDA_TRY(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
     B200SP_CUDA_TRY(cudaStreamSynchronize(st));
     if (h[1] < n) {
@@ -172,9 +227,8 @@ int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const in
       return B200SP_ERR_INVALID_ARGUMENT;
     }
     done = h[0];
-    cur ^= 1;
-    ++levels;
   }
+  const int levels = h[2] + 1;
   // rows grouped by level
   int *count, *cursor;
   B200SP_CUDA_TRY(tmp.alloc(&count, levels + 1));
@@ -206,7 +260,22 @@ int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const in
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->level_rows, sizeof(int) * (size_t)n, st));
   tr_place_kernel<<<tr_blocks(n), 256, 0, st>>>(n, lv[cur], cursor, p->level_rows);
   B200SP_LAUNCH_CHECK();
-  B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // level_ptr_host was the source of an asynchronous copy; tmp is released below
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->level_ptr_dev, sizeof(int) * (size_t)(levels + 1), st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(p->level_ptr_dev, p->level_ptr_host, sizeof(int) * (size_t)(levels + 1), cudaMemcpyHostToDevice, st));
+  B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // level_ptr_host was the source of asynchronous copies; tmp is released below
+  // launch plan: runs of two or more consecutive small levels become one single-CTA launch
+  const bool chain = tr_chain_enabled();
+  for (int l = 0; l < levels;) {
+    int e = l;
+    while (chain && e < levels && p->level_ptr_host[e + 1] - p->level_ptr_host[e] <= TR_CHAIN_ROWS) ++e;
+    if (e - l >= 2) {
+      p->segments.push_back({l, e, true});
+      l = e;
+    } else {
+      p->segments.push_back({l, l + 1, false});
+      ++l;
+    }
+  }
   p->n_levels = levels;
   p->symbolic = true;
   return B200SP_OK;
@@ -219,11 +288,16 @@ int sptrsv_solve_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const int* 
     set_error("sptrsv_solve: symbolic was not called on this plan with this matrix");
     return B200SP_ERR_STATE;
   }
-  for (int l = 0; l < p->n_levels; ++l) {
-    const int q0 = p->level_ptr_host[l], cntl = p->level_ptr_host[l + 1] - q0;
+  const int side = p->filter ? (p->lower ? 1 : 2) : 0;
+  for (const auto& sg : p->segments) {
+    if (sg.chain) {
+      tr_solve_chain_kernel<S><<<1, TR_CHAIN_ROWS, 0, st>>>(sg.l0, sg.l1, p->level_ptr_dev, p->level_rows, n, rp, ci, v, b, x, side, dinv);
+      B200SP_LAUNCH_CHECK();
+      continue;
+    }
+    const int q0 = p->level_ptr_host[sg.l0], cntl = p->level_ptr_host[sg.l1] - q0;
     if (cntl <= 0) continue;
-    tr_solve_level_kernel<S><<<tr_blocks(cntl), 256, 0, st>>>(cntl, p->level_rows + q0, n, rp, ci, v, b, x,
-                                                              p->filter ? (p->lower ? 1 : 2) : 0, dinv);
+    tr_solve_level_kernel<S><<<tr_blocks(cntl), 256, 0, st>>>(cntl, p->level_rows + q0, n, rp, ci, v, b, x, side, dinv);
     B200SP_LAUNCH_CHECK();
   }
   return B200SP_OK;
@@ -263,6 +337,7 @@ int b200sp_sptrsv_symbolic_i32(b200sp_sptrsv_plan* p, void* stream, int n, const
 }
 
 int b200sp_sptrsv_levels(const b200sp_sptrsv_plan* p) { return p ? p->n_levels : 0; }
+int b200sp_sptrsv_launches(const b200sp_sptrsv_plan* p) { return p ? (int)p->segments.size() : 0; }
 
 int b200sp_sptrsv_solve_f64_i32(b200sp_sptrsv_plan* p, void* stream, int n, const int* row_ptr, const int* col_idx, const double* vals,
                                 const double* b, double* x) {

@@ -316,6 +316,7 @@ class SPTRSVHandle:
     def is_lower_tri(self): return self.lower_tri
     def get_nrows(self): return self.nrows
     def get_num_levels(self): return _lib.sparse().b200sp_sptrsv_levels(self._plan)
+    def get_num_launches(self): return _lib.sparse().b200sp_sptrsv_launches(self._plan)  # kernel launches of one solve
     def is_symbolic_complete(self): return self._symbolic
 
     def __del__(self):

@@ -79,6 +79,54 @@ def test_sptrsv_chain_and_diagonal_only(cuda, oracle):
     assert h0.get_num_levels() == 0
 
 
+def test_sptrsv_mixed_level_sizes(cuda, oracle, monkeypatch):
+    """levels of more than 512 rows (one launch each) next to runs of small ones (one single-CTA launch per run, sptrsv.cu:
+    tr_solve_chain_kernel) and a lone small level between two large ones; the same with the chaining switched off"""
+    from kokkos_kernels_b200 import sparse as sp
+
+    rng = np.random.default_rng(11)
+    rows = []  # per row: list of dependency columns (all smaller than the row)
+    def block(count, deps_of):
+        base = len(rows)
+        for q in range(count):
+            rows.append(deps_of(base, q))
+        return base
+    block(2000, lambda base, q: [])                                  # level 0: large
+    c1 = block(40, lambda base, q: [base + q - 1] if q else [5])     # 40 levels of one row
+    last1 = c1 + 39
+    block(1500, lambda base, q: [last1, int(rng.integers(0, 2000))])  # one large level
+    big2 = len(rows) - 1
+    block(3, lambda base, q: [big2])                                 # a lone small level (3 rows)
+    lone = len(rows) - 1
+    block(900, lambda base, q: [lone, big2 - q])                     # large again
+    top = len(rows) - 1
+    block(200, lambda base, q: [base + q - 1, int(rng.integers(0, base))] if q else [top])  # 200 small levels at the end
+    n = len(rows)
+    rp = np.zeros(n + 1, np.int32)
+    ci, v = [], []
+    for i, deps in enumerate(rows):
+        cols = sorted(set(deps)) + [i]
+        ci += cols
+        v += list(rng.uniform(-0.4, 0.4, len(cols) - 1)) + [rng.uniform(1.5, 2.5)]
+        rp[i + 1] = len(ci)
+    ci, v = np.array(ci, np.int32), np.array(v)
+    b = rng.uniform(-1, 1, n)
+    exp = oracle.sptrsv(rp, ci, v, b, True)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    rpd, cid, vd, bd = t(rp), t(ci), t(v), t(b)
+    for chain in ("1", "0"):
+        monkeypatch.setenv("B200SP_SPTRSV_CHAIN", chain)
+        h = sp.SPTRSVHandle(n, True)
+        sp.sptrsv_symbolic(h, rpd, cid)
+        assert h.get_num_levels() == 1 + 40 + 1 + 1 + 1 + 200
+        # chained: large, run of 40, large, lone small, large, run of 200
+        assert h.get_num_launches() == (6 if chain == "1" else h.get_num_levels())
+        xd = t(np.full(n, np.nan))
+        sp.sptrsv_solve(h, rpd, cid, vd, bd, xd)
+        torch.cuda.synchronize()
+        assert np.array_equal(xd.cpu().numpy(), exp)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("compact", [False, True])
 def test_classic_two_stage_gauss_seidel(cuda, oracle, dtype, compact):
