@@ -476,8 +476,8 @@ int b200sp_gs2_apply_f32_i32(b200sp_gs2_plan* plan, void* stream, int n, int nco
  * row) -- KokkosSparse::sptrsv_symbolic / sptrsv_solve (sparse/src/KokkosSparse_sptrsv.hpp:40-170, :290-480), which the classic
  * two-stage Gauss-Seidel above calls.  symbolic groups the rows into dependency levels (synchronises `stream`; an entry on the
  * wrong side of the diagonal is B200SP_ERR_INVALID_ARGUMENT); solve runs one launch per level -- or one single-CTA launch for a
- * run of consecutive levels of at most 512 rows each (environment B200SP_SPTRSV_CHAIN=0 at symbolic time: always one per level)
- * -- and computes every row as the serial substitution loop does (storage order, unfused multiply / subtract, one division):
+ * run of consecutive small levels (environment B200SP_SPTRSV_CHAIN=0 at symbolic time: always one per level), a group of 8 / 16 /
+ * 32 lanes per row (B200SP_SPTRSV_GROUP overrides the choice) -- and computes every row as the serial substitution loop does (storage order, unfused multiply / subtract, one division):
  * bit-identical to it.  _levels / _launches: the number of dependency levels and of kernel launches of one solve. */
 typedef struct b200sp_sptrsv_plan b200sp_sptrsv_plan;
 int b200sp_sptrsv_plan_create(b200sp_sptrsv_plan** plan);

@@ -46,6 +46,11 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 int sm_count();  // SMs of the current device (cached per device)
+// Scratch is allocated with cudaMallocAsync.  The default pool hands unused memory back to the driver at every synchronisation
+// point (release threshold 0), and the symbolic phases synchronise by contract (they return counts to the host): each call would
+// then map its scratch again, which costs more than its kernels.  Keeps the pool's memory (once per device); called when a plan
+// whose phases synchronise is created (spgemm, sptrsv).
+void keep_async_pool_memory();
 
 // Launch setup of a kernel with more than 48 KB of dynamic shared memory: the opt-in attribute and the occupancy are
 // per DEVICE, so they are cached per (kernel instantiation, device) -- one process may drive several GPUs.

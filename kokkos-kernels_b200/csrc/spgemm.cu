@@ -1392,27 +1392,9 @@ static int jacobi_impl(b200sp_spgemm_plan* p, cudaStream_t st, int m, int n, int
 
 extern "C" {
 
-// The phases allocate their scratch with cudaMallocAsync.  The default pool hands unused memory back to the driver at every
-// synchronisation point (release threshold 0), and spgemm_symbolic synchronises by contract (it returns nnz(C)): each call
-// would then map a few hundred MB again, which costs more than its kernels.  Keep the pool's memory (once per device).
-static void keep_async_pool_memory() {
-#ifndef B200SP_EMU
-  static std::atomic<unsigned> done{0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
-  if (done.load() & (1u << dev)) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
-  done.fetch_or(1u << dev);
-#endif
-}
-
 int b200sp_spgemm_plan_create(b200sp_spgemm_plan** plan) {
   B200SP_REQUIRE(plan != nullptr, "spgemm_plan_create: null output pointer");
-  keep_async_pool_memory();
+  b200sp::keep_async_pool_memory();
   b200sp_spgemm_plan* p = new (std::nothrow) b200sp_spgemm_plan();
   if (!p) {
     set_error("spgemm_plan_create: out of host memory");

@@ -57,6 +57,21 @@ int sm_count() {
   return cached[dev];
 }
 
+void keep_async_pool_memory() {
+#ifndef B200SP_EMU
+  static std::atomic<unsigned> done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+  if (done.load() & (1u << dev)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done.fetch_or(1u << dev);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // y = beta*y (beta == 0 writes exact zeros without reading y)
 // ---------------------------------------------------------------------------

@@ -7,14 +7,19 @@
 //             dependency chain that ends in row i.  Computed by relaxation sweeps over the still unresolved rows, each sweep
 //             reading the levels of the sweep before (two arrays: the result is the exact longest-path level, independent of
 //             thread timing); as many sweeps as there are levels.  Rows are then grouped by level (counting sort).
-//   solve   : one launch per level, one thread per row:  acc = b_i;  acc -= a_ij * x_j in STORAGE order (unfused multiply and
-//             subtract);  x_i = acc / a_ii  -- operation for operation the serial substitution loop of the oracle
-//             (oracle/kk_oracle_crs.c: okk_sptrsv), so the result is bit-identical to it whatever the level schedule is.
+//   solve   : one launch per level, a GROUP of 8 / 16 / 32 lanes per row (by the mean row length):  acc = b_i;  acc -= a_ij * x_j in
+//             STORAGE order (unfused multiply and subtract);  x_i = acc / a_ii  -- operation for operation the serial substitution
+//             loop of the oracle (oracle/kk_oracle_sptrsv.c: okk_sptrsv), so the result is bit-identical to it whatever the level
+//             schedule is.  The lanes of a group load a batch of the row's (column, value, x[column]) and form the products IN
+//             PARALLEL (each product is rounded on its own either way); only the chain of subtractions runs in order, on values
+//             passed by shuffle.  One thread per row (the first version, 17 us per level on the 27-point operator,
+//             profiles/README.md call 24) spent its time in ~14 serial rounds of dependent loads per row; a group needs three
+//             (row record -> columns / values -> x).  The row record (row, begin, end) is stored with the level lists.
 //             The Gauss-Seidel form solves with the lower (upper) triangle of a general matrix: the entries on the other side and
 //             the ghost columns are skipped (`filter`), no copy of the triangle is made; with a caller-supplied inverse diagonal
 //             the diagonal is 1 / dinv_i, as in the reference.
-//             Runs of consecutive SMALL levels (<= TR_CHAIN_ROWS rows each: the first and last planes of a stencil, all of a
-//             banded matrix) are solved by ONE launch of a single CTA that walks them with a CTA barrier in between -- the
+//             Runs of consecutive SMALL levels (one row per lane group of a 1024-thread CTA: the first and last planes of a stencil,
+//             all of a banded matrix) are solved by ONE launch of a single CTA that walks them with a CTA barrier in between -- the
 //             dependent-launch latency of a level becomes a barrier plus one load round trip (B200SP_SPTRSV_CHAIN=0: off).
 //   symbolic sweeps are launched TR_SWEEP_BATCH at a time between two read-backs of the progress counter (a sweep after the
 //             last row was resolved changes nothing).
@@ -32,12 +37,14 @@ struct b200sp_sptrsv_plan {
   bool symbolic = false;
   const int *key_rp = nullptr, *key_ci = nullptr;
   int n_levels = 0;
-  int* level_rows = nullptr;      // rows grouped by level (device)
+  int4* level_rows = nullptr;     // rows grouped by level (device): (row, first entry, end of the row, -)
+  int group = 8;                  // lanes per row of the solve kernels
   int* level_ptr_host = nullptr;  // n_levels + 1 offsets (host)
   int* level_ptr_dev = nullptr;   // the same on the device (the chain kernel walks it)
   struct Segment {
     int l0, l1;  // levels [l0, l1): one launch per level, or one single-CTA launch for the whole run when `chain`
     bool chain;
+    int threads;  // chain: CTA size = lanes of the largest level of the run (a narrow CTA has a cheaper barrier)
   };
   std::vector<Segment> segments;
 };
@@ -45,8 +52,8 @@ struct b200sp_sptrsv_plan {
 namespace b200sp {
 namespace {
 
-constexpr int TR_CHAIN_ROWS   = 512;  // a level of at most this many rows is "small": one CTA of this many threads solves it
-constexpr int TR_SWEEP_BATCH  = 8;    // symbolic: relaxation sweeps per read-back
+constexpr int TR_CHAIN_THREADS = 1024;  // a level of at most TR_CHAIN_THREADS / group rows is "small": one CTA solves it in one pass
+constexpr int TR_SWEEP_BATCH   = 8;     // symbolic: relaxation sweeps per read-back
 
 inline bool tr_chain_enabled() {
   const char* e = getenv("B200SP_SPTRSV_CHAIN");
@@ -104,8 +111,10 @@ __global__ void __launch_bounds__(256) tr_hist_kernel(int n, const int* __restri
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&count[level[i]], 1);
 }
 // rows of one level, in whatever order the atomics hand out (the solve does not depend on it: a row reads only rows of lower levels)
-__global__ void __launch_bounds__(256) tr_place_kernel(int n, const int* __restrict__ level, int* __restrict__ cursor, int* __restrict__ rows) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rows[atomicAdd(&cursor[level[i]], 1)] = i;
+__global__ void __launch_bounds__(256) tr_place_kernel(int n, const int* __restrict__ rp, const int* __restrict__ level,
+                                                       int* __restrict__ cursor, int4* __restrict__ rows) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    rows[atomicAdd(&cursor[level[i]], 1)] = make_int4(i, rp[i], rp[i + 1], 0);
 }
 
 template <typename S>
@@ -121,51 +130,87 @@ __device__ __forceinline__ double tr_sub<double>(double a, double b) { return __
 template <>
 __device__ __forceinline__ float tr_sub<float>(float a, float b) { return __fsub_rn(a, b); }
 
-// one row of the substitution
+// one row of the substitution by a group of G lanes (gmask: the lanes of the group, gbase: its first lane in the warp)
 // side: 0 = every off-diagonal entry takes part (a triangular matrix), 1 = only columns < i (the lower triangle of a general
 // matrix), 2 = only columns in (i, n) (its upper triangle).  dinv: the caller's inverse diagonal or null.
-template <typename S>
-__device__ __forceinline__ void tr_solve_row(int i, int n, const int* __restrict__ rp, const int* __restrict__ ci, const S* __restrict__ v,
-                                             const S* __restrict__ b, S* x, int side, const S* __restrict__ dinv) {
+template <typename S, int G>
+__device__ __forceinline__ void tr_solve_row(int4 r, int lane, unsigned gmask, int gbase, int n, const int* __restrict__ ci,
+                                             const S* __restrict__ v, const S* __restrict__ b, S* x, int side, const S* __restrict__ dinv) {
+  const int i = r.x;
   S acc = b[i];
   S d = S(1);
-  for (int k = rp[i]; k < rp[i + 1]; ++k) {
-    const int c = ci[k];
-    if (c == i) {
-      d = v[k];
-      continue;
+  for (int base = r.y; base < r.z; base += G) {
+    const int k = base + lane;
+    const bool valid = k < r.z;
+    const int c = valid ? ci[k] : -1;
+    const S a = valid ? v[k] : S(0);
+    const bool diag = valid && c == i;
+    bool take = valid && !diag;
+    if (side == 1 && c > i) take = false;
+    if (side == 2 && (c < i || c >= n)) take = false;
+    const S prod = take ? tr_mul(a, x[c]) : S(0);
+    const unsigned tk = __ballot_sync(gmask, take) >> gbase;
+    const unsigned dg = (__ballot_sync(gmask, diag) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
+    const int cnt = min(G, r.z - base);
+    for (int j = 0; j < cnt; ++j) {  // the serial part: the subtractions, in storage order
+      const S pj = __shfl_sync(gmask, prod, j, G);
+      if ((tk >> j) & 1u) acc = tr_sub(acc, pj);
     }
-    if (side == 1 && c > i) continue;
-    if (side == 2 && (c < i || c >= n)) continue;
-    acc = tr_sub(acc, tr_mul(v[k], x[c]));
+    if (dg) d = __shfl_sync(gmask, a, 31 - __clz(dg), G);  // the last diagonal entry of the batch, as the serial loop keeps it
   }
   // a caller-supplied INVERSE diagonal enters as the diagonal 1 / dinv_i (twostage_gauss_seidel_impl.hpp:446-456)
-  x[i] = dinv ? acc / (S(1) / dinv[i]) : acc / d;
+  if (lane == 0) x[i] = dinv ? acc / (S(1) / dinv[i]) : acc / d;
+}
+
+template <int G>
+__device__ __forceinline__ unsigned tr_group_mask(int gbase) {
+  return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
 }
 
 // the rows of one level
-template <typename S>
-__global__ void __launch_bounds__(256) tr_solve_level_kernel(int count, const int* __restrict__ rows, int n, const int* __restrict__ rp,
-                                                             const int* __restrict__ ci, const S* __restrict__ v, const S* __restrict__ b,
-                                                             S* __restrict__ x, int side, const S* __restrict__ dinv) {
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x)
-    tr_solve_row<S>(rows[q], n, rp, ci, v, b, x, side, dinv);
+template <typename S, int G>
+__global__ void __launch_bounds__(256) tr_solve_level_kernel(int count, const int4* __restrict__ rows, int n, const int* __restrict__ ci,
+                                                             const S* __restrict__ v, const S* __restrict__ b, S* x, int side,
+                                                             const S* __restrict__ dinv) {
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = tr_group_mask<G>(gbase);
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; q < count; q += groups)
+    tr_solve_row<S, G>(rows[q], lane, gmask, gbase, n, ci, v, b, x, side, dinv);
 }
 
-// levels [l0, l1), each of at most blockDim.x rows, by ONE CTA: the x written in a level is read by the next one after the CTA
-// barrier (global writes of a CTA are visible to its own threads after __syncthreads; x is not `restrict` here: it is read and
-// written through the same pointer)
-template <typename S>
-__global__ void __launch_bounds__(TR_CHAIN_ROWS) tr_solve_chain_kernel(int l0, int l1, const int* __restrict__ level_ptr,
-                                                                       const int* __restrict__ rows, int n, const int* __restrict__ rp,
-                                                                       const int* __restrict__ ci, const S* __restrict__ v,
-                                                                       const S* __restrict__ b, S* x, int side, const S* __restrict__ dinv) {
+// levels [l0, l1), each of at most blockDim.x / G rows, by ONE CTA: the x written in a level is read by the next one after the CTA
+// barrier (global writes of a CTA are visible to its own threads after __syncthreads)
+template <typename S, int G>
+__global__ void __launch_bounds__(TR_CHAIN_THREADS) tr_solve_chain_kernel(int l0, int l1, const int* __restrict__ level_ptr,
+                                                                          const int4* __restrict__ rows, int n, const int* __restrict__ ci,
+                                                                          const S* __restrict__ v, const S* __restrict__ b, S* x, int side,
+                                                                          const S* __restrict__ dinv) {
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = tr_group_mask<G>(gbase);
+  const int g = (int)threadIdx.x / G, groups = (int)blockDim.x / G;
   int q0 = level_ptr[l0];
   for (int l = l0; l < l1; ++l) {
     const int q1 = level_ptr[l + 1];
-    for (int q = q0 + (int)threadIdx.x; q < q1; q += (int)blockDim.x) tr_solve_row<S>(rows[q], n, rp, ci, v, b, x, side, dinv);
+    for (int q = q0 + g; q < q1; q += groups) tr_solve_row<S, G>(rows[q], lane, gmask, gbase, n, ci, v, b, x, side, dinv);
     q0 = q1;
     __syncthreads();
+  }
+}
+
+template <typename S, int G>
+void tr_launch_solve(const b200sp_sptrsv_plan* p, cudaStream_t st, int n, const int* ci, const S* v, const S* b, S* x, const S* dinv) {
+  const int side = p->filter ? (p->lower ? 1 : 2) : 0;
+  for (const auto& sg : p->segments) {
+    if (sg.chain) {
+      tr_solve_chain_kernel<S, G><<<1, sg.threads, 0, st>>>(sg.l0, sg.l1, p->level_ptr_dev, p->level_rows, n, ci, v, b, x, side, dinv);
+      continue;
+    }
+    const int q0 = p->level_ptr_host[sg.l0], cntl = p->level_ptr_host[sg.l1] - q0;
+    if (cntl <= 0) continue;
+    tr_solve_level_kernel<S, G><<<tr_blocks((int64_t)cntl * G), 256, 0, st>>>(cntl, p->level_rows + q0, n, ci, v, b, x, side, dinv);
   }
 }
 
@@ -204,8 +249,17 @@ int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const in
   tr_fill_kernel<<<tr_blocks(n), 256, 0, st>>>(n, lv[0], -1);
   B200SP_LAUNCH_CHECK();
   int h[3] = {0, n, -1};  // rows resolved so far, smallest offending row, highest level handed out
+  int nnz = 0;
   B200SP_CUDA_TRY(cudaMemcpyAsync(cnt, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  B200SP_CUDA_TRY(cudaMemcpyAsync(&nnz, rp + n, sizeof(int), cudaMemcpyDeviceToHost, st));
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));
+  // lanes per row: one batch covers the mean row (all its stored entries: the filtered form scans the other triangle too)
+  const double mean = (double)nnz / (double)n;
+  p->group = mean <= 8.0 ? 8 : (mean <= 20.0 ? 16 : 32);
+  if (const char* e = getenv("B200SP_SPTRSV_GROUP")) {
+    const int g = atoi(e);
+    if (g == 8 || g == 16 || g == 32) p->group = g;
+  }
   int cur = 0, done = 0;
   while (done < n) {
     // a sweep resolves exactly the rows of the next level; sweeps after the last one copy the levels unchanged
@@ -257,22 +311,25 @@ int sptrsv_symbolic_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const in
   for (int l = 0; l < levels; ++l) p->level_ptr_host[l + 1] = p->level_ptr_host[l] + hc[l];
   delete[] hc;
   B200SP_CUDA_TRY(cudaMemcpyAsync(cursor, p->level_ptr_host, sizeof(int) * (size_t)(levels + 1), cudaMemcpyHostToDevice, st));
-  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->level_rows, sizeof(int) * (size_t)n, st));
-  tr_place_kernel<<<tr_blocks(n), 256, 0, st>>>(n, lv[cur], cursor, p->level_rows);
+  B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->level_rows, sizeof(int4) * (size_t)n, st));
+  tr_place_kernel<<<tr_blocks(n), 256, 0, st>>>(n, rp, lv[cur], cursor, p->level_rows);
   B200SP_LAUNCH_CHECK();
   B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->level_ptr_dev, sizeof(int) * (size_t)(levels + 1), st));
   B200SP_CUDA_TRY(cudaMemcpyAsync(p->level_ptr_dev, p->level_ptr_host, sizeof(int) * (size_t)(levels + 1), cudaMemcpyHostToDevice, st));
   B200SP_CUDA_TRY(cudaStreamSynchronize(st));  // level_ptr_host was the source of asynchronous copies; tmp is released below
   // launch plan: runs of two or more consecutive small levels become one single-CTA launch
   const bool chain = tr_chain_enabled();
+  const int small = TR_CHAIN_THREADS / p->group;
   for (int l = 0; l < levels;) {
     int e = l;
-    while (chain && e < levels && p->level_ptr_host[e + 1] - p->level_ptr_host[e] <= TR_CHAIN_ROWS) ++e;
+    while (chain && e < levels && p->level_ptr_host[e + 1] - p->level_ptr_host[e] <= small) ++e;
     if (e - l >= 2) {
-      p->segments.push_back({l, e, true});
+      int widest = 1;
+      for (int q = l; q < e; ++q) widest = std::max(widest, p->level_ptr_host[q + 1] - p->level_ptr_host[q]);
+      p->segments.push_back({l, e, true, std::min(TR_CHAIN_THREADS, (widest * p->group + 31) / 32 * 32)});
       l = e;
     } else {
-      p->segments.push_back({l, l + 1, false});
+      p->segments.push_back({l, l + 1, false, 0});
       ++l;
     }
   }
@@ -288,18 +345,13 @@ int sptrsv_solve_impl(b200sp_sptrsv_plan* p, cudaStream_t st, int n, const int* 
     set_error("sptrsv_solve: symbolic was not called on this plan with this matrix");
     return B200SP_ERR_STATE;
   }
-  const int side = p->filter ? (p->lower ? 1 : 2) : 0;
-  for (const auto& sg : p->segments) {
-    if (sg.chain) {
-      tr_solve_chain_kernel<S><<<1, TR_CHAIN_ROWS, 0, st>>>(sg.l0, sg.l1, p->level_ptr_dev, p->level_rows, n, rp, ci, v, b, x, side, dinv);
-      B200SP_LAUNCH_CHECK();
-      continue;
-    }
-    const int q0 = p->level_ptr_host[sg.l0], cntl = p->level_ptr_host[sg.l1] - q0;
-    if (cntl <= 0) continue;
-    tr_solve_level_kernel<S><<<tr_blocks(cntl), 256, 0, st>>>(cntl, p->level_rows + q0, n, rp, ci, v, b, x, side, dinv);
-    B200SP_LAUNCH_CHECK();
+  (void)rp;  // the row limits travel with the level lists
+  switch (p->group) {
+    case 8: tr_launch_solve<S, 8>(p, st, n, ci, v, b, x, dinv); break;
+    case 16: tr_launch_solve<S, 16>(p, st, n, ci, v, b, x, dinv); break;
+    default: tr_launch_solve<S, 32>(p, st, n, ci, v, b, x, dinv); break;
   }
+  B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
 template int sptrsv_solve_impl<double>(b200sp_sptrsv_plan*, cudaStream_t, int, const int*, const int*, const double*, const double*, double*,
@@ -318,6 +370,7 @@ int b200sp_sptrsv_plan_create(b200sp_sptrsv_plan** plan) {
     b200sp::set_error("sptrsv_plan_create: out of host memory");
     return B200SP_ERR_ALLOC;
   }
+  b200sp::keep_async_pool_memory();
   *plan = p;
   return B200SP_OK;
 }

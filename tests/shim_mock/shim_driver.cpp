@@ -471,20 +471,21 @@ int main(int argc, char** argv) {
     static_assert(Impl::sptrsv_symbolic_tpl_spec_avail<KH, TRI, TRI>::value, "sptrsv_symbolic must be available");
     static_assert(Impl::sptrsv_solve_tpl_spec_avail<Kokkos::Cuda, KH, TRI, TRI, TRS, TRS, TRX>::value, "sptrsv_solve must be available");
     int f10 = 0;
+    const int nt = 6000;  // the leading nt x nt block: a tridiagonal matrix has as many levels as rows, and symbolic sweeps once per level
     for (int lower = 1; lower >= 0; --lower) {
-      std::vector<int> trp(n + 1, 0), tci;
-      std::vector<double> tva, bh(n), xr(n), xg(n);
-      for (int i = 0; i < n; ++i) {
+      std::vector<int> trp(nt + 1, 0), tci;
+      std::vector<double> tva, bh(nt), xr(nt), xg(nt);
+      for (int i = 0; i < nt; ++i) {
         for (int q = rp[i]; q < rp[i + 1]; ++q)
-          if (lower ? ci[q] <= i : ci[q] >= i) {
+          if (ci[q] < nt && (lower ? ci[q] <= i : ci[q] >= i)) {
             tci.push_back(ci[q]);
             tva.push_back(ci[q] == i ? 3.0 : va[q]);
           }
         trp[i + 1] = (int)tci.size();
         bh[i]      = 1.0 + 0.5 * std::cos(0.02 * i);
       }
-      for (int t = 0; t < n; ++t) {
-        const int i = lower ? t : n - 1 - t;
+      for (int t = 0; t < nt; ++t) {
+        const int i = lower ? t : nt - 1 - t;
         volatile double acc = bh[i];  // volatile: no contraction of the multiply and the subtract
         double d            = 1.0;
         for (int q = trp[i]; q < trp[i + 1]; ++q) {
@@ -499,19 +500,19 @@ int main(int argc, char** argv) {
       int *d_trp = to_dev(trp), *d_tci = to_dev(tci);
       double *d_tva = to_dev(tva), *d_b = to_dev(bh), *d_xx = to_dev(xg);
       KH kh;
-      kh.create_sptrsv_handle(Experimental::SPTRSVAlgorithm::SEQLVLSCHD_TP1, n, lower != 0);
-      TRI vrp(d_trp, n + 1), vci(d_tci, tci.size());
+      kh.create_sptrsv_handle(Experimental::SPTRSVAlgorithm::SEQLVLSCHD_TP1, nt, lower != 0);
+      TRI vrp(d_trp, nt + 1), vci(d_tci, tci.size());
       bool threw = false;
       try {
-        TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, n), TRX(d_xx, n));
+        TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, nt), TRX(d_xx, nt));
       } catch (const std::runtime_error&) { threw = true; }
       if (!threw) ++f10;  // solve before symbolic is an error, as in the front end (sparse/src/KokkosSparse_sptrsv.hpp:300-310)
       TSY::sptrsv_symbolic(exec, &kh, vrp, vci);
       if (!kh.get_sptrsv_handle()->is_symbolic_complete()) ++f10;
-      TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, n), TRX(d_xx, n));
+      TSO::sptrsv_solve(exec, &kh, vrp, vci, TRS(d_tva, tva.size()), TRS(d_b, nt), TRX(d_xx, nt));
       exec.fence();
-      cudaMemcpy(xg.data(), d_xx, sizeof(double) * n, cudaMemcpyDeviceToHost);
-      for (int i = 0; i < n; ++i)
+      cudaMemcpy(xg.data(), d_xx, sizeof(double) * nt, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < nt; ++i)
         if (std::memcmp(&xg[i], &xr[i], sizeof(double)) != 0) ++f10;
       kh.destroy_sptrsv_handle();
       cudaFree(d_trp);

@@ -3,6 +3,8 @@ mirror -- SPTRSVHandle / sptrsv_symbolic / sptrsv_solve (sparse/src/KokkosSparse
 set_gs_twostage(False, n) (sparse/impl/KokkosSparse_twostage_gauss_seidel_impl.hpp:880-925) -- against the oracle.  The triangular
 solve computes every row as the oracle's serial substitution does: bit-exact.  Runs under the CPU emulation as well
 (tests/test_emulated_sptrsv.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -132,7 +134,8 @@ def test_sptrsv_mixed_level_sizes(cuda, oracle, monkeypatch):
 def test_classic_two_stage_gauss_seidel(cuda, oracle, dtype, compact):
     from kokkos_kernels_b200 import sparse as sp
 
-    n, ghosts = 6000, 80
+    # (under the CPU emulation every lane is a fiber and every shuffle a barrier between fibers: a smaller matrix there)
+    n, ghosts = (6000, 80) if os.environ.get("B200SP_TEST_EMULATED") != "1" else (900, 30)
     rp, ci, v = dd_matrix(n, 13, extra_cols=ghosts)
     v = v.astype(dtype)
     ncols = n + ghosts
@@ -145,6 +148,8 @@ def test_classic_two_stage_gauss_seidel(cuda, oracle, dtype, compact):
     rpd, cid, vd, bd = t(rp), t(ci), t(v), t(b)
     tol = 1e-13 if dtype == np.float64 else 1e-5
     applies = (sp.symmetric_gauss_seidel_apply, sp.forward_sweep_gauss_seidel_apply, sp.backward_sweep_gauss_seidel_apply)
+    if os.environ.get("B200SP_TEST_EMULATED") == "1":
+        applies = applies[:1]  # the symmetric sweep runs both triangular solves
     for given in (None, dinv):
         kh = sp.KokkosKernelsHandle()
         kh.create_gs_handle(sp.GS_TWOSTAGE)
