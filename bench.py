@@ -76,7 +76,11 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU DURING the timed region.  A thread reads them through NVML (nvidia-ml-py: the
+    library nvidia-smi itself reads) every 2 ms from start() to stop(); mark_begin() / mark_end() bracket the timed region and the
+    summary is over the samples taken inside it.  (A 20-step region lasts ~20 ms: nvidia-smi's loop mode, 100 ms at best and 100+ ms
+    to start, cannot land a sample in it -- it stays as the fallback when NVML cannot be loaded, started before the warm-up so that it
+    is polling by then, and its samples cover warm-up + timed region.)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -84,9 +88,52 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # nvidia-smi fallback: raw csv lines
+        self.samples = []    # NVML: (perf_counter, sm MHz, reasons bitmask)
+        self.nvml = None
+        self.handle = None
+        self.max_mhz = None
+        self.t0 = self.t1 = None
+        self._stop = False
+        self.thread = None
+
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:  # the device torch calls `idx`, whatever CUDA_VISIBLE_DEVICES did to the numbering
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # fails here, not in the thread, if unsupported
+        self.nvml, self.handle = pynvml, h
+        try:
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.max_mhz = None
+
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self._nvml_open()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -95,11 +142,42 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def _stop_nvml(self):
+        self._stop = True
+        self.thread.join(timeout=1.0)
+        nv = self.nvml
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside, window = list(self.samples), "warm-up + timed region (no sample fell inside the timed region)"
+        bits = 0
+        for x in inside:
+            bits |= x[2]
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 ("hw_power_brake_slowdown", "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80))
+        reasons = sorted(n for n, attr, dflt in names if bits & int(getattr(nv, attr, dflt)))
+        sm = [x[1] for x in inside]
+        try:
+            nv.nvmlShutdown()
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sm), "window": window, "source": "NVML, 2 ms period"}
+
     def stop(self):
+        if self.nvml is not None and self.thread is not None:
+            return self._stop_nvml()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -122,7 +200,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": "warm-up + timed region", "source": "nvidia-smi -lms 100"}
 
 
 def ncu_traffic(files=("r02c15_spmv_tile_ncu_key_metrics.csv", "r01_spmv_tile_c2_ncu_key_metrics.csv"), kernel=None):
@@ -818,22 +896,24 @@ def main():
             assert bool(torch.isfinite(probe).all())
 
     # ---- timed region (device time, CUDA events on the launching stream, max over ranks)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: the sampler is running (and the clocks are under load) when the timed region begins
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.b200sp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     launches = lib.b200sp_launch_count() - launches0
