@@ -48,8 +48,9 @@ extern std::atomic<long long> g_launches;
 int sm_count();  // SMs of the current device (cached per device)
 // Scratch is allocated with cudaMallocAsync.  The default pool hands unused memory back to the driver at every synchronisation
 // point (release threshold 0), and the symbolic phases synchronise by contract (they return counts to the host): each call would
-// then map its scratch again, which costs more than its kernels.  Keeps the pool's memory (once per device); called when a plan
-// whose phases synchronise is created (spgemm, sptrsv).
+// then map its scratch again, which costs more than its kernels (spadd_symbolic: 24-100 ms instead of ~1, profiles/README.md call
+// 27).  Keeps the pool's memory (once per device); called by every scratch allocation scope (DevTmp) and by the plans that own
+// stream-ordered memory.
 void keep_async_pool_memory();
 
 // Launch setup of a kernel with more than 48 KB of dynamic shared memory: the opt-in attribute and the occupancy are
@@ -81,7 +82,7 @@ struct DevTmp {  // frees stream-ordered on scope exit
   cudaStream_t st;
   void* ptrs[32];
   int n = 0;
-  explicit DevTmp(cudaStream_t s) : st(s) {}
+  explicit DevTmp(cudaStream_t s) : st(s) { keep_async_pool_memory(); }
   ~DevTmp() {
     for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st);
   }

@@ -19,6 +19,7 @@
 #include "scan.cuh"
 #include <algorithm>
 #include <limits.h>
+#include <stdlib.h>
 #include <new>
 
 namespace b200sp {
@@ -257,31 +258,43 @@ __global__ void __launch_bounds__(256)
   if (r < m && sl == 0) counts[r] = u;
 }
 
+// 8 lanes per row: a lane that sits on the first entry of a run of equal columns writes that run -- its place is the number of runs
+// that start before it (ballot / popc), its value the run's entries added in storage order (`acc = v[first]; acc += v[next] ...`, the
+// serial loop's operations).  Runs are short (a merged matrix has none longer than one), so the lanes work side by side where one
+// thread per row walked the row in a serial chain of dependent loads.
 template <typename V, bool HAS_VALS>
 __global__ void __launch_bounds__(256)
     merged_fill_kernel(int m, const int* __restrict__ rp, const int* __restrict__ ci, const V* __restrict__ vals,
                        const int* __restrict__ rp_out, int* __restrict__ ci_out, V* __restrict__ vals_out) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+  constexpr int G = 8;
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = ((1u << G) - 1u) << gbase;
+  const unsigned below = (1u << (gbase + lane)) - 1u;
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int r = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; r < m; r += groups) {
     const int s = rp[r], e = rp[r + 1];
-    if (e == s) continue;
-    V acc = V(0);
-    if (HAS_VALS) acc = vals[s];
-    int col = ci[s];
-    int pos = rp_out[r];
-    for (int j = s + 1; j < e; ++j) {
-      const int c = ci[j];
-      if (c == col) {
-        if (HAS_VALS) acc += vals[j];
-      } else {
-        ci_out[pos] = col;
-        if (HAS_VALS) vals_out[pos] = acc;
-        ++pos;
-        col = c;
-        if (HAS_VALS) acc = vals[j];
+    int before = rp_out[r];  // place of the next run start
+    for (int base = s; base < e; base += G) {
+      const int j = base + lane;
+      int col = 0;
+      bool start = false;
+      if (j < e) {
+        col = ci[j];
+        start = j == s || ci[j - 1] != col;
       }
+      const unsigned sb = __ballot_sync(gmask, start);
+      if (start) {
+        const int pos = before + __popc(sb & below);
+        ci_out[pos] = col;
+        if (HAS_VALS) {
+          V acc = vals[j];
+          for (int q = j + 1; q < e && ci[q] == col; ++q) acc += vals[q];
+          vals_out[pos] = acc;
+        }
+      }
+      before += __popc(sb);
     }
-    ci_out[pos] = col;
-    if (HAS_VALS) vals_out[pos] = acc;
   }
 }
 
@@ -375,6 +388,173 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- sorted spadd by a GROUP of lanes per row -------------------------------------------------------------------------------
+// One thread per row walks two sorted rows in a serial chain of dependent loads (446 GB/s of the ~36 bytes per entry on a B200,
+// profiles/README.md).  Rows WITHOUT a repeated column inside A_i or inside B_i (any merged matrix) need no walk: the place of an
+// entry in C_i is its rank in the union,
+//     pos(a_k) = k + |{b in B_i : b < a_k}| - |{j < k : a_j in B_i}|,      pos(b_k) likewise, written only when b_k is not in A_i,
+// found by one binary search in the other row per entry (the rows were just read: the probes hit L1) and a ballot / popc prefix
+// over the match flags.  The value is the serial loop's, operation for operation: (0 + alpha a) + beta b for a matched pair,
+// 0 + alpha a or 0 + beta b otherwise (the leading 0 + keeps -0 -> +0 as `acc = 0; acc += ...` does).  A row with a repeated
+// column falls back to the serial walk by lane 0 (the reference accumulates the repeats in order).
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+__device__ __forceinline__ int row_lower_bound(const int* __restrict__ c, int len, int key) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// true if some column repeats inside the sorted row [s, e) (uniform over the group)
+template <int G>
+__device__ __forceinline__ bool row_has_repeat(const int* __restrict__ ci, int s, int e, int lane, unsigned gmask) {
+  bool rep = false;
+  for (int base = s; base < e; base += G) {
+    const int k = base + lane;
+    rep |= (k < e && k > s && ci[k] == ci[k - 1]);
+  }
+  return __ballot_sync(gmask, rep) != 0u;
+}
+
+__device__ __forceinline__ int spadd_serial_count(const int* __restrict__ ciA, int ai, int ae, const int* __restrict__ ciB, int bi, int be) {
+  int n = 0;
+  int acol = ai < ae ? ciA[ai] : INT_MAX;
+  int bcol = bi < be ? ciB[bi] : INT_MAX;
+  while (acol != INT_MAX || bcol != INT_MAX) {
+    const int c = acol < bcol ? acol : bcol;
+    ++n;
+    while (acol == c) acol = (++ai < ae) ? ciA[ai] : INT_MAX;
+    while (bcol == c) bcol = (++bi < be) ? ciB[bi] : INT_MAX;
+  }
+  return n;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+    spadd_sorted_count_group_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ ciA, const int* __restrict__ rpB,
+                                    const int* __restrict__ ciB, int* __restrict__ counts) {
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups) {
+    const int as = rpA[i], ae = rpA[i + 1], bs = rpB[i], be = rpB[i + 1];
+    const bool rep = row_has_repeat<G>(ciA, as, ae, lane, gmask) | row_has_repeat<G>(ciB, bs, be, lane, gmask);
+    if (rep) {
+      if (lane == 0) counts[i] = spadd_serial_count(ciA, as, ae, ciB, bs, be);
+      continue;
+    }
+    int matches = 0;
+    for (int base = as; base < ae; base += G) {
+      const int k = base + lane;
+      bool match = false;
+      if (k < ae) {
+        const int col = ciA[k];
+        const int lb = row_lower_bound(ciB + bs, be - bs, col);
+        match = lb < be - bs && ciB[bs + lb] == col;
+      }
+      matches += __popc(__ballot_sync(gmask, match));
+    }
+    if (lane == 0) counts[i] = (ae - as) + (be - bs) - matches;
+  }
+}
+
+template <typename S, int G>
+__global__ void __launch_bounds__(256)
+    spadd_sorted_numeric_group_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ ciA, const S* __restrict__ vA, S alpha,
+                                      const int* __restrict__ rpB, const int* __restrict__ ciB, const S* __restrict__ vB, S beta,
+                                      const int* __restrict__ rpC, int* __restrict__ ciC, S* __restrict__ vC) {
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
+  const unsigned below = (1u << (gbase + lane)) - 1u;  // the lanes before this one (masked with the group's ballot)
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups) {
+    const int as = rpA[i], ae = rpA[i + 1], bs = rpB[i], be = rpB[i + 1];
+    const int cs = rpC[i];
+    const bool rep = row_has_repeat<G>(ciA, as, ae, lane, gmask) | row_has_repeat<G>(ciB, bs, be, lane, gmask);
+    if (rep) {
+      if (lane == 0) {  // the serial walk (SortedNumericSumFunctor, spadd_numeric_impl.hpp:50-92)
+        int ai = as, bi = bs, pos = cs;
+        int acol = ai < ae ? ciA[ai] : INT_MAX;
+        int bcol = bi < be ? ciB[bi] : INT_MAX;
+        while (acol != INT_MAX || bcol != INT_MAX) {
+          const int c = acol < bcol ? acol : bcol;
+          S acc = S(0);
+          while (acol == c) {
+            acc += mul_rn(alpha, vA[ai]);
+            acol = (++ai < ae) ? ciA[ai] : INT_MAX;
+          }
+          while (bcol == c) {
+            acc += mul_rn(beta, vB[bi]);
+            bcol = (++bi < be) ? ciB[bi] : INT_MAX;
+          }
+          ciC[pos] = c;
+          vC[pos] = acc;
+          ++pos;
+        }
+      }
+      continue;
+    }
+    const int alen = ae - as, blen = be - bs;
+    int before = 0;  // matched entries of A in the batches done
+    for (int base = 0; base < alen; base += G) {
+      const int k = base + lane;
+      bool match = false;
+      int col = 0, lb = 0;
+      if (k < alen) {
+        col = ciA[as + k];
+        lb = row_lower_bound(ciB + bs, blen, col);
+        match = lb < blen && ciB[bs + lb] == col;
+      }
+      const unsigned mb = __ballot_sync(gmask, match);
+      if (k < alen) {
+        const int pos = cs + k + lb - (before + __popc(mb & below));
+        S acc = add_rn(S(0), mul_rn(alpha, vA[as + k]));
+        if (match) acc = add_rn(acc, mul_rn(beta, vB[bs + lb]));
+        ciC[pos] = col;
+        vC[pos] = acc;
+      }
+      before += __popc(mb);
+    }
+    before = 0;  // matched entries of B in the batches done
+    for (int base = 0; base < blen; base += G) {
+      const int k = base + lane;
+      bool match = false;
+      int col = 0, lb = 0;
+      if (k < blen) {
+        col = ciB[bs + k];
+        lb = row_lower_bound(ciA + as, alen, col);
+        match = lb < alen && ciA[as + lb] == col;
+      }
+      const unsigned mb = __ballot_sync(gmask, match);
+      if (k < blen && !match) {
+        const int pos = cs + k + lb - (before + __popc(mb & below));
+        ciC[pos] = col;
+        vC[pos] = add_rn(S(0), mul_rn(beta, vB[bs + k]));
+      }
+      before += __popc(mb);
+    }
+  }
+}
+
+// lanes per row of the sorted spadd kernels by the mean length of A_i plus B_i; 0 = the one-thread-per-row kernels
+// (B200SP_SPADD_GROUP = 0 | 8 | 32 overrides)
+static int spadd_group(int m, int64_t nnzA, int64_t nnzB) {
+  if (const char* e = getenv("B200SP_SPADD_GROUP")) {
+    const int g = atoi(e);
+    if (g == 0 || g == 8 || g == 32) return g;
+  }
+  // measured (call 27, 54 + 54 entries per row): 8 lanes 0.41 ms, 32 lanes 0.50 ms, one thread per row 3.49 ms -- more rows in
+  // flight beat wider batches until the rows are long
+  return (double)(nnzA + nnzB) / (double)std::max(m, 1) > 512.0 ? 32 : 8;
+}
+
 __global__ void __launch_bounds__(256)
     spadd_upper_bound_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ rpB, int* __restrict__ counts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
@@ -403,48 +583,105 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// MergeEntriesFunctor (spadd_symbolic_impl.hpp:278-343)
+// MergeEntriesFunctor (spadd_symbolic_impl.hpp:278-343), 8 lanes per row: the place of a union entry in C_i is the number of column
+// changes up to it (ballot / popc prefix).  simple[i] = no column occurs twice in A_i or twice in B_i: then no two entries of one
+// matrix share a place in C_i and the numeric phase may add a row's entries side by side (below).
 __global__ void __launch_bounds__(256)
     spadd_merge_entries_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ rpB,
                                const int* __restrict__ rpU, const int* __restrict__ ciU, const int* __restrict__ perm,
-                               int* __restrict__ counts, int* __restrict__ apos, int* __restrict__ bpos) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+                               int* __restrict__ counts, int* __restrict__ apos, int* __restrict__ bpos, int* __restrict__ simple) {
+  constexpr int G = 8;
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = ((1u << G) - 1u) << gbase;
+  const unsigned upto = (2u << (gbase + lane)) - 1u;  // this lane and the ones before it
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups) {
     const int cs = rpU[i], ce = rpU[i + 1];
     if (ce == cs) {
-      counts[i] = 0;
+      if (lane == 0) {
+        counts[i] = 0;
+        simple[i] = 1;
+      }
       continue;
     }
     const int as = rpA[i], alen = rpA[i + 1] - as;
     const int bs = rpB[i];
-    int cf = 0;
-    for (int it = cs; it < ce; ++it) {
-      if (it > cs && ciU[it] != ciU[it - 1]) ++cf;
-      const int pv = perm[it];
-      if (pv < alen) apos[as + pv] = cf;
-      else bpos[bs + (pv - alen)] = cf;
+    int before = 0;  // column changes in the batches done
+    bool twice = false;
+    for (int base = cs; base < ce; base += G) {
+      const int it = base + lane;
+      bool change = false;
+      int pv = 0;
+      if (it < ce) {
+        pv = perm[it];
+        if (it > cs) {
+          change = ciU[it] != ciU[it - 1];
+          // equal columns are ordered A's entries first (the stable sort keeps the unmerged order): two neighbours of one matrix
+          twice |= !change && ((perm[it - 1] < alen) == (pv < alen));
+        }
+      }
+      const unsigned cb = __ballot_sync(gmask, change);
+      if (it < ce) {
+        const int cf = before + __popc(cb & upto);
+        if (pv < alen) apos[as + pv] = cf;
+        else bpos[bs + (pv - alen)] = cf;
+      }
+      before += __popc(cb);
     }
-    counts[i] = cf + 1;
+    const unsigned tw = __ballot_sync(gmask, twice);
+    if (lane == 0) {
+      counts[i] = before + 1;
+      simple[i] = tw == 0u;
+    }
   }
 }
 
+// UnsortedNumericSumFunctor (spadd_numeric_impl.hpp:131-152), 8 lanes per row.  The three passes of the serial loop -- C_i = 0;
+// C_i[apos] += alpha a in storage order; C_i[bpos] += beta b -- run pass by pass with the lanes side by side when the row is
+// `simple` (inside one pass no two entries then touch the same place, so each place sees the serial loop's operations in its order:
+// (0 + alpha a) + beta b); other rows are walked by lane 0.
 template <typename S>
 __global__ void __launch_bounds__(256)
     spadd_unsorted_numeric_kernel(int m, const int* __restrict__ rpA, const int* __restrict__ ciA,
                                   const S* __restrict__ vA, S alpha, const int* __restrict__ rpB,
                                   const int* __restrict__ ciB, const S* __restrict__ vB, S beta,
-                                  const int* __restrict__ rpC, int* __restrict__ ciC, S* __restrict__ vC,
-                                  const int* __restrict__ apos, const int* __restrict__ bpos) {
-  // UnsortedNumericSumFunctor (spadd_numeric_impl.hpp:131-152)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+                                  const int* __restrict__ rpC, int* __restrict__ ciC, S* vC,
+                                  const int* __restrict__ apos, const int* __restrict__ bpos, const int* __restrict__ simple) {
+  constexpr int G = 8;
+  const int lane = (int)threadIdx.x & (G - 1);
+  const int gbase = ((int)threadIdx.x & 31) & ~(G - 1);
+  const unsigned gmask = ((1u << G) - 1u) << gbase;
+  const int groups = (int)(gridDim.x * blockDim.x) / G;
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups) {
     const int cs = rpC[i], ce = rpC[i + 1];
-    for (int j = cs; j < ce; ++j) vC[j] = S(0);
-    for (int j = rpA[i]; j < rpA[i + 1]; ++j) {
-      vC[cs + apos[j]] += mul_rn(alpha, vA[j]);
-      ciC[cs + apos[j]] = ciA[j];
+    const int as = rpA[i], ae = rpA[i + 1], bs = rpB[i], be = rpB[i + 1];
+    if (!simple[i]) {
+      if (lane == 0) {
+        for (int j = cs; j < ce; ++j) vC[j] = S(0);
+        for (int j = as; j < ae; ++j) {
+          vC[cs + apos[j]] += mul_rn(alpha, vA[j]);
+          ciC[cs + apos[j]] = ciA[j];
+        }
+        for (int j = bs; j < be; ++j) {
+          vC[cs + bpos[j]] += mul_rn(beta, vB[j]);
+          ciC[cs + bpos[j]] = ciB[j];
+        }
+      }
+      continue;
     }
-    for (int j = rpB[i]; j < rpB[i + 1]; ++j) {
-      vC[cs + bpos[j]] += mul_rn(beta, vB[j]);
-      ciC[cs + bpos[j]] = ciB[j];
+    for (int j = cs + lane; j < ce; j += G) vC[j] = S(0);
+    __syncwarp(gmask);
+    for (int j = as + lane; j < ae; j += G) {
+      const int q = cs + apos[j];
+      vC[q] = add_rn(vC[q], mul_rn(alpha, vA[j]));
+      ciC[q] = ciA[j];
+    }
+    __syncwarp(gmask);
+    for (int j = bs + lane; j < be; j += G) {
+      const int q = cs + bpos[j];
+      vC[q] = add_rn(vC[q], mul_rn(beta, vB[j]));
+      ciC[q] = ciB[j];
     }
   }
 }
@@ -551,13 +788,15 @@ struct b200sp_spadd_plan {
   int64_t c_nnz = 0;
   int64_t nnzA = 0, nnzB = 0;
   int *apos = nullptr, *bpos = nullptr;  // unsorted path: position of every A / B entry in its C row
+  int* simple = nullptr;                 // unsorted path, per row: no repeated column inside A_i or inside B_i
 };
 
 namespace b200sp {
 static void spadd_release(b200sp_spadd_plan* p, cudaStream_t st) {
   if (p->apos) cudaFreeAsync(p->apos, st);
   if (p->bpos) cudaFreeAsync(p->bpos, st);
-  p->apos = p->bpos = nullptr;
+  if (p->simple) cudaFreeAsync(p->simple, st);
+  p->apos = p->bpos = p->simple = nullptr;
   p->symbolic_done = false;
 }
 
@@ -591,9 +830,9 @@ static int sort_and_merge_fill(cudaStream_t st, int m, const int* rp, const int*
                                const int* rp_out, int* ci_out, S* v_out) {
   if (m <= 0) return B200SP_OK;
   B200SP_REQUIRE(rp && rp_out, "sort_and_merge: null row map");
-  const int blocks = grid_for(m);
-  if (has_vals) merged_fill_kernel<S, true><<<blocks, 256, 0, st>>>(m, rp, ci, v, rp_out, ci_out, v_out);
-  else merged_fill_kernel<S, false><<<blocks, 256, 0, st>>>(m, rp, ci, nullptr, rp_out, ci_out, nullptr);
+  const int fill_blocks = grid_for((int64_t)m * 8);  // 8 lanes per row
+  if (has_vals) merged_fill_kernel<S, true><<<fill_blocks, 256, 0, st>>>(m, rp, ci, v, rp_out, ci_out, v_out);
+  else merged_fill_kernel<S, false><<<fill_blocks, 256, 0, st>>>(m, rp, ci, nullptr, rp_out, ci_out, nullptr);
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
 }
@@ -616,10 +855,13 @@ static int spadd_numeric_impl(b200sp_spadd_plan* p, cudaStream_t st, int m, int 
   B200SP_REQUIRE((p->nnzA == 0 || (ciA && vA)) && (p->nnzB == 0 || (ciB && vB)), "spadd_numeric: null pointer argument");
   const int blocks = grid_for(m);
   if (p->input_sorted) {
-    spadd_sorted_numeric_kernel<S><<<blocks, 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC);
+    const int g = spadd_group(m, p->nnzA, p->nnzB);
+    if (g == 32) spadd_sorted_numeric_group_kernel<S, 32><<<grid_for((int64_t)m * 32), 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC);
+    else if (g == 8) spadd_sorted_numeric_group_kernel<S, 8><<<grid_for((int64_t)m * 8), 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC);
+    else spadd_sorted_numeric_kernel<S><<<blocks, 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC);
   } else {
-    spadd_unsorted_numeric_kernel<S><<<blocks, 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC,
-                                                            p->apos, p->bpos);
+    spadd_unsorted_numeric_kernel<S><<<grid_for((int64_t)m * 8), 256, 0, st>>>(m, rpA, ciA, vA, alpha, rpB, ciB, vB, beta, rpC, ciC, vC,
+                                                                              p->apos, p->bpos, p->simple);
   }
   B200SP_LAUNCH_CHECK();
   return B200SP_OK;
@@ -733,7 +975,10 @@ int b200sp_spadd_symbolic_i32(b200sp_spadd_plan* p, void* stream, int m, int n, 
   long long total = 0;
   int rc;
   if (p->input_sorted) {
-    spadd_sorted_count_kernel<<<blocks, 256, 0, st>>>(m, rpA, ciA, rpB, ciB, counts);
+    const int g = spadd_group(m, lastA, lastB);
+    if (g == 32) spadd_sorted_count_group_kernel<32><<<grid_for((int64_t)m * 32), 256, 0, st>>>(m, rpA, ciA, rpB, ciB, counts);
+    else if (g == 8) spadd_sorted_count_group_kernel<8><<<grid_for((int64_t)m * 8), 256, 0, st>>>(m, rpA, ciA, rpB, ciB, counts);
+    else spadd_sorted_count_kernel<<<blocks, 256, 0, st>>>(m, rpA, ciA, rpB, ciB, counts);
     B200SP_LAUNCH_CHECK();
     rc = counts_to_offsets(st, m, counts, rpC, &total, nullptr);
     if (rc) return rc;
@@ -753,7 +998,8 @@ int b200sp_spadd_symbolic_i32(b200sp_spadd_plan* p, void* stream, int m, int n, 
     if (rc) return rc;
     B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->apos, sizeof(int) * (size_t)std::max(lastA, 1), st));
     B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->bpos, sizeof(int) * (size_t)std::max(lastB, 1), st));
-    spadd_merge_entries_kernel<<<blocks, 256, 0, st>>>(m, rpA, rpB, rpU, ciU, perm, counts, p->apos, p->bpos);
+    B200SP_CUDA_TRY(cudaMallocAsync((void**)&p->simple, sizeof(int) * (size_t)m, st));
+    spadd_merge_entries_kernel<<<grid_for((int64_t)m * 8), 256, 0, st>>>(m, rpA, rpB, rpU, ciU, perm, counts, p->apos, p->bpos, p->simple);
     B200SP_LAUNCH_CHECK();
     rc = counts_to_offsets(st, m, counts, rpC, &total, nullptr);
     if (rc) return rc;

@@ -154,6 +154,93 @@ def test_spadd(cuda, oracle, sort_rows, m, n, lo, hi, dtype):
     kh.destroy_spadd_handle()
 
 
+@pytest.mark.parametrize("group", ["0", "8", "32"])
+def test_spadd_sorted_kernel_variants(cuda, oracle, monkeypatch, group):
+    """the sorted spadd kernels -- one thread per row (0) and a group of 8 / 32 lanes per row placing every entry by its rank in the
+    union (crs_utils.cu) -- give the oracle's bits: rows with common and disjoint columns, an empty A_i or B_i, a long row, signed
+    zeros (0 + (-0) = +0 as in `acc = 0; acc += ...`), and rows with a repeated column (the serial fallback inside the group kernels)"""
+    from kokkos_kernels_b200 import sparse as sp
+
+    monkeypatch.setenv("B200SP_SPADD_GROUP", group)
+    rng = np.random.default_rng(3)
+    m, n = 400, 5000
+    def mat(seed, repeats):
+        r = np.random.default_rng(seed)
+        rp, ci, v = [0], [], []
+        for i in range(m):
+            ln = 0 if i % 17 == seed % 17 else (3000 if i == 7 else int(r.integers(1, 70)))
+            cols = np.sort(r.choice(n, ln, replace=False))
+            if repeats and i % 29 == 3 and ln >= 2:
+                cols[1] = cols[0]  # a repeated column inside a sorted row
+            vals = r.uniform(-1, 1, ln)
+            vals[r.random(ln) < 0.1] = -0.0
+            ci += list(cols)
+            v += list(vals)
+            rp.append(len(ci))
+        return np.array(rp, np.int32), np.array(ci, np.int32), np.array(v)
+    A, B = mat(1, True), mat(2, False)
+    B[1][B[0][5]:B[0][5] + 3] = A[1][A[0][5]:A[0][5] + 3] if A[0][6] - A[0][5] >= 3 and B[0][6] - B[0][5] >= 3 else B[1][B[0][5]:B[0][5] + 3]
+    # re-sort row 5 of B after planting common columns (and drop accidental repeats by leaving them: repeats are legal)
+    s5, e5 = B[0][5], B[0][6]
+    order = np.argsort(B[1][s5:e5], kind="stable")
+    B[1][s5:e5], B[2][s5:e5] = B[1][s5:e5][order], B[2][s5:e5][order]
+    Ad, Bd = dev_mat(sp, cuda, *A, n), dev_mat(sp, cuda, *B, n)
+    for alpha, beta in ((1.0, 1.0), (0.3, -1.7), (-1.0, 0.0)):
+        kh = sp.KokkosKernelsHandle()
+        kh.create_spadd_handle(True, False)
+        c_rowmap = torch.zeros(m + 1, dtype=torch.int32, device=cuda)
+        sp.spadd_symbolic_views(kh, m, n, Ad.row_map, Ad.entries, Bd.row_map, Bd.entries, c_rowmap)
+        nnz = kh.get_spadd_handle().get_c_nnz()
+        c_entries = torch.full((nnz,), -1, dtype=torch.int32, device=cuda)
+        c_values = torch.full((nnz,), np.nan, dtype=torch.float64, device=cuda)
+        sp.spadd_numeric_views(kh, m, n, Ad.row_map, Ad.entries, Ad.values, alpha, Bd.row_map, Bd.entries, Bd.values, beta, c_rowmap,
+                               c_entries, c_values)
+        exp = oracle.spadd(*A, alpha, *B, beta, True)
+        got = (host(c_rowmap), host(c_entries), host(c_values))
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+        assert np.array_equal(got[2].view(np.int64), exp[2].view(np.int64))  # bits: the sign of a zero counts
+        kh.destroy_spadd_handle()
+
+
+def test_spadd_unsorted_rows_bits(cuda, oracle):
+    """the unsorted path (8 lanes per row: places by a ballot prefix, the three passes of the serial loop side by side on rows without a
+    repeated column, lane 0 alone on the others): shuffled rows with a long row, empty rows, repeated columns and signed zeros"""
+    from kokkos_kernels_b200 import sparse as sp
+
+    m, n = 300, 4000
+    def mat(seed, repeats):
+        r = np.random.default_rng(seed)
+        rp, ci, v = [0], [], []
+        for i in range(m):
+            ln = 0 if i % 13 == seed % 13 else (2500 if i == 11 else int(r.integers(1, 90)))
+            cols = r.choice(n, ln, replace=False)
+            if repeats and i % 7 == 2 and ln >= 3:
+                cols[2] = cols[0]  # a repeated column somewhere in the unsorted row
+            vals = r.uniform(-1, 1, ln)
+            vals[r.random(ln) < 0.1] = -0.0
+            ci += list(cols)
+            v += list(vals)
+            rp.append(len(ci))
+        return np.array(rp, np.int32), np.array(ci, np.int32), np.array(v)
+    A, B = mat(5, True), mat(6, True)
+    Ad, Bd = dev_mat(sp, cuda, *A, n), dev_mat(sp, cuda, *B, n)
+    for alpha, beta in ((1.0, 1.0), (0.3, -1.7)):
+        kh = sp.KokkosKernelsHandle()
+        kh.create_spadd_handle(False, False)
+        c_rowmap = torch.zeros(m + 1, dtype=torch.int32, device=cuda)
+        sp.spadd_symbolic_views(kh, m, n, Ad.row_map, Ad.entries, Bd.row_map, Bd.entries, c_rowmap)
+        nnz = kh.get_spadd_handle().get_c_nnz()
+        c_entries = torch.full((nnz,), -1, dtype=torch.int32, device=cuda)
+        c_values = torch.full((nnz,), np.nan, dtype=torch.float64, device=cuda)
+        sp.spadd_numeric_views(kh, m, n, Ad.row_map, Ad.entries, Ad.values, alpha, Bd.row_map, Bd.entries, Bd.values, beta, c_rowmap,
+                               c_entries, c_values)
+        exp = oracle.spadd(*A, alpha, *B, beta, False)
+        got = (host(c_rowmap), host(c_entries), host(c_values))
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+        assert np.array_equal(got[2].view(np.int64), exp[2].view(np.int64))
+        kh.destroy_spadd_handle()
+
+
 def test_spadd_known_columns_and_misuse(cuda):
     from kokkos_kernels_b200 import sparse as sp
     from kokkos_kernels_b200 import B200SparseError

@@ -147,6 +147,8 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }  // built with -ffp-contract=off: no fusion
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __double2loint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b & 0xffffffffull); }
 static inline int __double2hiint(double v) { unsigned long long b; memcpy(&b, &v, 8); return (int)(unsigned)(b >> 32); }
