@@ -63,6 +63,11 @@ void keep_async_pool_memory() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
   if (done.load() & (1u << dev)) return;
+  const char* keep_env = getenv("B200SP_KEEP_POOL");  // 0: leave the device's default pool as the application configured it
+  if (keep_env && keep_env[0] == '0') {
+    done.fetch_or(1u << dev);
+    return;
+  }
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     uint64_t keep = UINT64_MAX;
