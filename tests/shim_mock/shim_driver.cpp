@@ -80,6 +80,7 @@ T* to_dev(const std::vector<T>& h) {
 int main(int argc, char** argv) {
   // --bsr: also run the BsrMatrix specialisations (not part of the default run until their first pass on a B200)
   bool with_bsr = false, with_jacobi = false, with_gs = false, with_gmres = false;  // --jacobi, --gs: likewise for spgemm_jacobi / Gauss-Seidel
+  int n_arg = 50000;                                                                 // --n N: rows of the test matrix (the CPU emulation runs a smaller one)
   bool with_sptrsv = false;                                                          // --sptrsv: SPTRSV_SYMBOLIC / SPTRSV_SOLVE
   bool with_spmv64 = false;                                                          // --spmv64: the 64-bit-offset specialisations
   for (int a = 1; a < argc; ++a) {
@@ -89,6 +90,7 @@ int main(int argc, char** argv) {
     with_gmres |= std::string(argv[a]) == "--gmres";
     with_spmv64 |= std::string(argv[a]) == "--spmv64";
     with_sptrsv |= std::string(argv[a]) == "--sptrsv";
+    if (std::string(argv[a]) == "--n" && a + 1 < argc) n_arg = std::atoi(argv[a + 1]);
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -96,7 +98,7 @@ int main(int argc, char** argv) {
     return 77;
   }
   // tridiagonal-ish n x n matrix with rows of 3 (ragged at the ends), values depend on (i,j)
-  const int n = 50000;
+  const int n = n_arg >= 8000 ? n_arg : 8000;
   std::vector<int> rp(n + 1, 0), ci;
   std::vector<double> va, x(n), y0(n);
   for (int i = 0; i < n; ++i) {

@@ -342,7 +342,7 @@ def test_kokkos_shim_driver_emulated():
     BsrMatrix, SPGEMM_JACOBI, GAUSS_SEIDEL_*, GMRES and SPTRSV_* specialisations run end to end on the host."""
     E.harness()  # builds everything under tools/emu/_build
     drv = os.path.join(os.path.dirname(E.harness()), "shim_driver_emu")
-    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64", "--sptrsv"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([drv, "--bsr", "--jacobi", "--gs", "--gmres", "--spmv64", "--sptrsv", "--n", "12000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "SHIM DRIVER OK" in out.stdout and out.stdout.count(" 0 mismatches") == 14, out.stdout
 
