@@ -16,9 +16,13 @@
  *                         Z = (L + D)^{-1} R (forward) or (U + D)^{-1} R (backward) with D = a_ii, or 1 / the inverse diagonal
  *                         the caller supplied (numeric :446-456), x += Z (compact: x = Z); omega must be 1 (:886-893).
  *                         The residual product is the host loop order O1 (okk_spmv_serial_*), like kk_oracle_gs2.c.
- * Pinned by the definition: T x == b to rounding, scipy.sparse.linalg.spsolve_triangular, and one classic forward sweep ==
- * textbook Gauss-Seidel in natural order (tests/test_oracle_sptrsv.py).  Parity unpinned against reference bits (the
- * reference's sptrsv needs its Kokkos handle machinery around it).  Compiled with -ffp-contract=off.
+ * Pinned on the reference's own fixtures and check for the level-scheduled algorithms (sparse/unit_test/Test_Sparse_sptrsv.hpp:
+ * 64-118 the "ones" matrices, :140-157 rhs = A * ones, :212-225 sum(lhs) == nrows: exact), on the definition (T x == b to rounding),
+ * on scipy.sparse.linalg.spsolve_triangular, and one classic forward sweep == textbook Gauss-Seidel in natural order
+ * (tests/test_oracle_sptrsv.py).  Not pinned on reference OUTPUT BITS for general inputs: the reference's solver functors
+ * (sparse/impl/KokkosSparse_sptrsv_solve_impl.hpp) pull KokkosBatched / KokkosBlas headers and cannot be compiled in place the way
+ * oracle/kkref_spmv.cpp compiles the SpMV loops; their row recurrence (rhs_i - sum a_ij lhs_j in storage order, / diagonal) is the one
+ * restated here.  Compiled with -ffp-contract=off.
  */
 #include <stdint.h>
 #include <stdlib.h>

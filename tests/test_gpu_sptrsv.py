@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from test_oracle_gs2 import dd_matrix
-from test_oracle_sptrsv import triangle
+from test_oracle_sptrsv import REFERENCE_FIXTURES, fixture_crs, triangle
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +47,27 @@ def test_sptrsv_bit_exact(cuda, oracle, lower, dtype):
     h2 = sp.SPTRSVHandle(n, lower)
     with pytest.raises(sp.B200SparseError):
         sp.sptrsv_symbolic(h2, t(rp), t(ci))
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_FIXTURES))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_reference_fixtures(cuda, name, dtype):
+    """the reference's own level-scheduling fixtures and check (sparse/unit_test/Test_Sparse_sptrsv.hpp:64-118, 140-157, 212-225):
+    rhs = A * ones, the solution is ones and sums to nrows exactly"""
+    from kokkos_kernels_b200 import sparse as sp
+
+    lower, dense = REFERENCE_FIXTURES[name]
+    rp, ci, v, rhs = fixture_crs(dense, dtype)
+    n = len(dense)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    rpd, cid = t(rp), t(ci)
+    h = sp.SPTRSVHandle(n, lower)
+    sp.sptrsv_symbolic(h, rpd, cid)
+    xd = t(np.zeros(n, dtype))
+    sp.sptrsv_solve(h, rpd, cid, t(v), t(rhs), xd)
+    torch.cuda.synchronize()
+    x = xd.cpu().numpy()
+    assert np.array_equal(x, np.ones(n, dtype)) and x.sum() == n
 
 
 def test_sptrsv_chain_and_diagonal_only(cuda, oracle):

@@ -54,3 +54,38 @@ def test_classic_forward_sweep_is_textbook_gauss_seidel(oracle, compact):
     for i in range(n - 1, -1, -1):
         expb[i] = (b[i] - A[i, :i] @ expb[:i] - A[i, i + 1:] @ expb[i + 1:]) / A[i, i]
     assert np.max(np.abs(xb - expb)) <= 1e-12
+
+
+# The reference's own fixtures for the level-scheduled algorithms (sparse/unit_test/Test_Sparse_sptrsv.hpp:64-78, 100-118: the
+# "ones" matrices; the 5x5 fixtures with KEEP_ZERO entries only feed the supernodal tests).  Its check (:140-157, 212-225):
+# rhs = A * ones, solve, sum(lhs) == nrows -- exact, the arithmetic is on small integers.
+REFERENCE_FIXTURES = {
+    "5x5_ut_ones": (False, [[1, 0, 1, 0, 0], [0, 1, 0, 0, 1], [0, 0, 1, 1, 1], [0, 0, 0, 1, 1], [0, 0, 0, 0, 1]]),
+    "6x6_ut_ones": (False, [[1, 1, 0, 0, 0, 0], [0, 1, 0, 0, 0, 1], [0, 0, 1, 1, 0, 1], [0, 0, 0, 1, 0, 1], [0, 0, 0, 0, 1, 1],
+                            [0, 0, 0, 0, 0, 1]]),
+    "5x5_lt_ones": (True, [[1, 0, 0, 0, 0], [0, 1, 0, 0, 0], [1, 0, 1, 0, 0], [0, 0, 1, 1, 0], [0, 1, 1, 1, 1]]),
+    "6x6_lt_ones": (True, [[1, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0], [0, 0, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 1, 1, 0],
+                           [0, 1, 1, 1, 1, 1]]),
+}
+
+
+def fixture_crs(dense, dtype):
+    """compress_matrix (sparse/unit_test/Test_vector_fixtures.hpp:35-90) + rhs = A * ones"""
+    A = np.array(dense, dtype=dtype)
+    rp, ci, v = [0], [], []
+    for row in A:
+        for j, a in enumerate(row):
+            if a != 0:
+                ci.append(j)
+                v.append(a)
+        rp.append(len(ci))
+    return np.array(rp, np.int32), np.array(ci, np.int32), np.array(v, dtype), A @ np.ones(len(A), dtype)
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_FIXTURES))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_reference_fixtures(oracle, name, dtype):
+    lower, dense = REFERENCE_FIXTURES[name]
+    rp, ci, v, rhs = fixture_crs(dense, dtype)
+    x = oracle.sptrsv(rp, ci, v, rhs, lower)
+    assert np.array_equal(x, np.ones(len(dense), dtype)) and x.sum() == len(dense)
