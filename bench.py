@@ -472,6 +472,93 @@ def secondary_spmm(dev, scale=23, k=16, iters=10):
     }
 
 
+def next_rows_bench(dev):
+    """Two of the rows either side of the path, timed beside the headline at N = 1 so that the driver's record holds
+    them: KokkosSparse::spadd on sorted inputs (27.4 M + 27.4 M entries) and the level-set sparse triangular solve (lower triangle of
+    lap27(96^3)) with the classic two-stage Gauss-Seidel sweep built on it.  Stand-alone versions with the kernel variants side by
+    side: tools/bench_spadd.py, tools/bench_sptrsv.py.  Parity of both is tests/test_gpu_crs_utils.py / test_gpu_sptrsv.py's job;
+    here the results are only checked for the obvious (sizes, finiteness)."""
+    import scipy.sparse as sps
+    import torch
+
+    from kokkos_kernels_b200 import matgen, sparse as sp
+
+    def ev_timed(fn, iters):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    peak, _ = peaks()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = {}
+    # ---- spadd, sorted inputs: C = 0.3 A - 1.7 B, B = A's structure with every column moved by one
+    g = 64
+    rp, ci, va = matgen.lap27(g, g, g, ndof=2, noise=0.5)
+    m, n = len(rp) - 1, len(rp)
+    A = sp.CrsMatrix(t(rp), t(ci), t(va), n)
+    B = sp.CrsMatrix(t(rp), t((ci + 1).astype(np.int32)), t(va[::-1].copy()), n)
+    kh = sp.KokkosKernelsHandle()
+    kh.create_spadd_handle(True, True)
+    crp = torch.zeros(m + 1, dtype=torch.int32, device=dev)
+    sym_ms = ev_timed(lambda: sp.spadd_symbolic_views(kh, m, n, A.row_map, A.entries, B.row_map, B.entries, crp), 5)
+    nnzc = int(kh.get_spadd_handle().get_c_nnz())
+    cci = torch.empty(nnzc, dtype=torch.int32, device=dev)
+    cv = torch.empty(nnzc, dtype=torch.float64, device=dev)
+    num_ms = ev_timed(lambda: sp.spadd_numeric_views(kh, m, n, A.row_map, A.entries, A.values, 0.3, B.row_map, B.entries, B.values, -1.7,
+                                                     crp, cci, cv), 10)
+    balg = 12 * (2 * len(ci) + nnzc) + 3 * 4 * (m + 1)
+    out["spadd"] = {"workload": f"spadd fp64, sorted rows: A = lap27({g}^3) x 2 dof ({m} rows, {len(ci)} entries), B = A with every column moved by one; nnz(C) = {nnzc}",
+                    "symbolic_ms": round(sym_ms, 4), "numeric_ms": round(num_ms, 4), "numeric_alg_GBs": round(balg / num_ms / 1e6, 1),
+                    "roofline_frac": round(balg / num_ms / 1e6 / peak, 4), "finite": bool(torch.isfinite(cv).all().item())}
+    kh.destroy_spadd_handle()
+    del A, B, crp, cci, cv
+    # ---- sptrsv: lower triangle of the 27-point operator, and the classic Gauss-Seidel forward sweep on the full operator
+    g = 96
+    rp, ci, va = matgen.lap27(g, g, g, noise=0.5)
+    n = len(rp) - 1
+    L = sps.tril(sps.csr_matrix((va, ci, rp), shape=(n, n))).tocsr()
+    L.sort_indices()
+    lrp, lci, lv = L.indptr.astype(np.int32), L.indices.astype(np.int32), L.data.astype(np.float64)
+    b = matgen.fill(n, -1.0, 1.0, 7)
+    rpd, cid, vd, bd = t(lrp), t(lci), t(lv), t(b)
+    h = sp.SPTRSVHandle(n, True)
+    sp.sptrsv_symbolic(h, rpd, cid)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sp.sptrsv_symbolic(h, rpd, cid)
+    torch.cuda.synchronize()
+    sym_ms = (time.perf_counter() - t0) * 1e3
+    xd = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+    solve_ms = ev_timed(lambda: sp.sptrsv_solve(h, rpd, cid, vd, bd, xd), 10)
+    levels = int(h.get_num_levels())
+    # residual of the solve, row-scaled: max |L x - b| / (|L| |x| + |b|)
+    xh = xd.cpu().numpy()
+    res = np.max(np.abs(L @ xh - b) / (abs(L) @ np.abs(xh) + np.abs(b)))
+    kg = sp.KokkosKernelsHandle()
+    kg.create_gs_handle(sp.GS_TWOSTAGE)
+    kg.set_gs_twostage(False, n)
+    Ad = sp.CrsMatrix(t(rp), t(ci), t(va), n)
+    sp.gauss_seidel_symbolic(kg, n, n, Ad.row_map, Ad.entries, True)
+    sp.gauss_seidel_numeric(kg, n, n, Ad.row_map, Ad.entries, Ad.values, True)
+    xg = torch.zeros((n, 1), dtype=torch.float64, device=dev)
+    gs_ms = ev_timed(lambda: sp.forward_sweep_gauss_seidel_apply(kg, n, n, Ad.row_map, Ad.entries, Ad.values, xg, bd.reshape(n, 1), False, True,
+                                                                1.0, 1), 5)
+    out["sptrsv"] = {"workload": f"sptrsv fp64, lower triangle of lap27({g}^3): {n} rows, {len(lci)} entries, {levels} levels",
+                     "symbolic_ms_wall": round(sym_ms, 3), "solve_ms": round(solve_ms, 4), "us_per_level": round(1e3 * solve_ms / max(1, levels), 3),
+                     "launches_per_solve": int(h.get_num_launches()), "row_scaled_residual": float(res),
+                     "classic_gauss_seidel_forward_sweep_ms": round(gs_ms, 4),
+                     "note": "latency-bound (dependent levels): the time per level is the figure of merit, not GB/s"}
+    kg.destroy_gs_handle()
+    return out
+
+
 def secondary_spgemm(dev, n=2_000_000, deg=32, reps=2):
     """configs[3]: spgemm_symbolic + spgemm_numeric fp64, C = A*A, A = 2M x 2M with exactly 32 distinct uniform-random columns
     per row (seed 4), values U(1,50)."""
@@ -1052,6 +1139,14 @@ def main():
                 secondary.append({"config": {"workload": fn.__name__}, "error": f"{type(exc).__name__}: {exc}"})
             torch.cuda.empty_cache()
 
+    next_rows = None
+    if secondary is not None:
+        try:
+            next_rows = next_rows_bench(dev)
+        except Exception as exc:  # never let the extra rows cost the headline line
+            next_rows = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(gflops, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -1093,6 +1188,8 @@ def main():
             out["cpu_baseline"] = cpu
         if secondary is not None:
             out["secondary"] = secondary
+        if next_rows is not None:
+            out["next_rows"] = next_rows
         emit(out)
     if world > 1:
         dist.destroy_process_group()
