@@ -1143,9 +1143,9 @@ def main():
     if secondary is not None:
         try:
             next_rows = next_rows_bench(dev)
+            torch.cuda.empty_cache()
         except Exception as exc:  # never let the extra rows cost the headline line
             next_rows = {"error": f"{type(exc).__name__}: {exc}"}
-        torch.cuda.empty_cache()
 
     if rank == 0:
         out = {
