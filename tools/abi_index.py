@@ -49,6 +49,7 @@ def table():
     lines = ["| entry points | what (first sentence of the header comment) | reference interface cited there | bound by |", "|---|---|---|---|"]
     for syms, c in groups:
         c = re.sub(r"^-+\s*", "", c)
+        c = " ".join(re.sub(r"-{4,}", ". ", c).split())
         first = re.split(r"(?<=[a-z0-9)\]])[.:;] ", c, maxsplit=1)[0].strip(" -")
         first = (first[:157] + "...") if len(first) > 160 else first
         first = first or "status / version of the library"
