@@ -130,17 +130,26 @@ def op_gs2(rng, orc, verbose):
     b = rng.uniform(-1, 1, n).astype(dtype)
     x0 = rng.uniform(-1, 1, ncols).astype(dtype)
     grp, gci, gv, gb, gx = g(rp, rng), g(ci, rng), g(v, rng), g(b, rng), g(x0, rng)
+    classic = rng.random() < 0.35  # the sptrsv form: triangular solves on A's own triangles (level sets), omega = 1 only
     plan = E.Gs2Plan(compact=compact, inner=inner, outer=outer, gamma=gamma)
+    if classic:
+        omega = 1.0
+        E.ok(plan.set(5, 0.0))
+        os.environ["B200SP_SPTRSV_GROUP"] = str([8, 16, 32][rng.integers(0, 3)])
     E.ok(plan.symbolic(n, ncols, grp, gci))
     E.ok(plan.numeric(n, ncols, grp, gci, gv))
     E.ok(plan.apply(n, ncols, grp, gci, gv, gx, gb, init_zero, omega, num_iter, direction))
     plan.close()
+    os.environ.pop("B200SP_SPTRSV_GROUP", None)
     xo = x0.copy()
-    orc.gs2_apply(rp, ci, v, ncols, xo, b, init_zero, dtype(omega), num_iter, direction, compact=compact, inner_sweeps=inner, outer_sweeps=outer,
-                  gamma=dtype(gamma))
+    if classic:
+        orc.gs2_classic_apply(rp, ci, v, ncols, xo, b, init_zero, num_iter, direction, compact=compact, outer_sweeps=outer)
+    else:
+        orc.gs2_apply(rp, ci, v, ncols, xo, b, init_zero, dtype(omega), num_iter, direction, compact=compact, inner_sweeps=inner,
+                      outer_sweeps=outer, gamma=dtype(gamma))
     tol = 1e-12 if dtype == np.float64 else 5e-5
     ok = bool(np.max(np.abs(gx.astype(np.float64) - xo.astype(np.float64)), initial=0.0) <= tol * max(1.0, np.max(np.abs(xo), initial=0.0)))
-    return ok, f"gs2 {np.dtype(dtype).name} n={n}+{ghosts} nnz={len(ci)} compact={compact} inner={inner} outer={outer} gamma={gamma} omega={omega} dir={direction}"
+    return ok, f"gs2 {'classic ' if classic else ''}{np.dtype(dtype).name} n={n}+{ghosts} nnz={len(ci)} compact={compact} inner={inner} outer={outer} gamma={gamma} omega={omega} dir={direction}"
 
 
 def op_spmv64(rng, orc, verbose):
@@ -370,7 +379,49 @@ def op_gs(rng, orc, verbose):
     return ok, f"gs {np.dtype(dtype).name} n={n} nnz={len(ci)} colors={nc} dir={direction} sweeps={sweeps}"
 
 
-OPS = {"gs": op_gs, "gs2": op_gs2, "spmv": op_spmv, "spmv64": op_spmv64, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr}
+def op_sptrsv(rng, orc, verbose):
+    """Level-set triangular solve: a random lower / upper triangular matrix (unsorted rows, the diagonal anywhere in its row, long
+    dependency chains or wide levels, sometimes a hub row), lane groups of 8 / 16 / 32 and chaining on / off, bit for bit against
+    the oracle's serial substitution."""
+    dtype = [np.float64, np.float32][rng.integers(0, 2)]
+    n = int(rng.integers(1, 1200))
+    lower = bool(rng.integers(0, 2))
+    band = int(rng.integers(1, max(2, n)))  # narrow band: long chains of small levels; wide: few large levels
+    rows = []
+    for i in range(n):
+        k = int(rng.integers(0, 6)) if rng.random() < 0.9 else int(rng.integers(20, 90))
+        lo, hi = (max(0, i - band), i) if lower else (i + 1, min(n, i + 1 + band))
+        cand = np.arange(lo, hi)
+        deps = rng.choice(cand, min(k, len(cand)), replace=False) if len(cand) else np.zeros(0, np.int64)
+        cols = np.concatenate([deps, [i]]).astype(np.int32)
+        rows.append(cols[rng.permutation(len(cols))])
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    ci = np.concatenate(rows).astype(np.int32)
+    rid = np.repeat(np.arange(n), np.diff(rp))
+    v = rng.uniform(-0.5, 0.5, len(ci))
+    v[rid == ci] = rng.uniform(1.0, 2.0, n) * np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    v = v.astype(dtype)
+    b = rng.uniform(-1, 1, n).astype(dtype)
+    os.environ["B200SP_SPTRSV_GROUP"] = str([8, 16, 32][rng.integers(0, 3)])
+    os.environ["B200SP_SPTRSV_CHAIN"] = str(int(rng.integers(0, 2)))
+    L = E.lib()
+    grp, gci, gv, gb = g(rp, rng), g(ci, rng), g(v, rng), g(b, rng)
+    x = E.guarded(np.full(n, np.nan, dtype))
+    h = C.c_void_p()
+    E.ok(L.b200sp_sptrsv_plan_create(C.byref(h)))
+    E.ok(L.b200sp_sptrsv_symbolic_i32(h, None, n, E.ptr(grp), E.ptr(gci), int(lower)))
+    levels, launches = L.b200sp_sptrsv_levels(h), L.b200sp_sptrsv_launches(h)
+    E.ok(getattr(L, f"b200sp_sptrsv_solve_{E.sfx(dtype)}_i32")(h, None, n, E.ptr(grp), E.ptr(gci), E.ptr(gv), E.ptr(gb), E.ptr(x)))
+    E.ok(L.b200sp_sptrsv_plan_destroy(h, None))
+    os.environ.pop("B200SP_SPTRSV_GROUP", None)
+    os.environ.pop("B200SP_SPTRSV_CHAIN", None)
+    exp = orc.sptrsv(rp, ci, v, b, lower)
+    ok = np.array_equal(np.asarray(x).view(np.uint8), exp.view(np.uint8)) and 1 <= levels <= n and 1 <= launches <= levels
+    return ok, f"sptrsv {np.dtype(dtype).name} n={n} nnz={len(ci)} lower={lower} band={band} levels={levels} launches={launches}"
+
+
+OPS = {"gs": op_gs, "gs2": op_gs2, "spmv": op_spmv, "spmv64": op_spmv64, "spmm": op_spmm, "spgemm": op_spgemm, "crs": op_crs, "bsr": op_bsr,
+       "sptrsv": op_sptrsv}
 
 
 def main():
